@@ -1,0 +1,188 @@
+"""Graph / Laplacian construction for the ChebConv hot path (host side, numpy + scipy).
+
+Same public functions, argument meaning and error behaviour as the reference's
+`deepsphere/utils.py` for the HEALPix path of `models.deepsphere.__init__`
+(reference deepsphere/models.py:1827-1839 -> utils.py:388-431), but built from whole-array
+operations on the COO triplets instead of per-pixel healpy calls and sparse-sparse products:
+
+  healpix_weightmatrix  <- utils.py:25-133      build_laplacian <- utils.py:231-242
+  healpix_laplacian     <- utils.py:320-342     rescale_L       <- utils.py:379-385
+  build_laplacians      <- utils.py:388-431     nside2indexes   <- utils.py:434-449
+  ds_index              <- utils.py:452-473
+
+Float32 results are bit-identical to the reference code run on the same numpy (checked in
+tests/test_graph_golden.py against fixtures produced by the reference's own utils.py).
+The icosahedral and irregular (kNN) graphs live in `graphs.py`.
+"""
+import numpy as np
+from scipy import sparse
+import scipy.sparse.linalg  # noqa: F401
+
+from . import healpix as hp
+
+
+def healpix_weightmatrix(nside=16, nest=True, indexes=None, dtype=np.float32, std=None, full=False):
+    """Unnormalised Gaussian weight matrix of the HEALPix 8-neighbour graph (CSR)."""
+    if not nest:
+        raise NotImplementedError()
+    if indexes is None:
+        indexes = np.arange(nside**2 * 12)
+    indexes = np.asarray(indexes)
+    npix = len(indexes)
+    usefast = npix >= (int(indexes.max()) + 1)
+    if usefast:
+        indexes = np.arange(npix)
+
+    x, y, z = hp.pix2vec(nside, indexes, nest=True)
+    coords = np.asarray(np.vstack([x, y, z]).transpose(), dtype=dtype)
+    if full:
+        from scipy import spatial
+        distances = spatial.distance.cdist(coords, coords)**2
+        kernel_width = np.mean(distances) if std is None else std
+        W = np.exp(-distances / (2 * kernel_width))
+        np.fill_diagonal(W, 0.)
+        W[W < 0.01] = 0
+        return sparse.csr_matrix(W, dtype=dtype)
+
+    neighbors = hp.get_all_neighbours(nside, indexes, nest=True)
+    col_index = neighbors.T.reshape(npix * 8)
+    if usefast:
+        row_index = np.repeat(indexes, 8)
+        keep = (col_index < npix) & (col_index >= 0)
+        col_index = col_index[keep]
+        row_index = row_index[keep]
+    else:
+        # arbitrary pixel subset: translate sphere pixel numbers to positions in `indexes`
+        inverse_map = np.full(nside**2 * 12, -1, dtype=np.int64)
+        inverse_map[indexes] = np.arange(npix)
+        row_index = np.repeat(np.arange(npix), 8)
+        keep = col_index >= 0
+        keep[keep] = inverse_map[col_index[keep]] >= 0
+        col_index = inverse_map[col_index[keep]]
+        row_index = row_index[keep]
+
+    distances = np.sum((coords[row_index] - coords[col_index])**2, axis=1)
+    kernel_width = np.mean(distances) if std is None else std
+    weights = np.exp(-distances / (2 * kernel_width))
+    return sparse.csr_matrix((weights, (row_index, col_index)), shape=(npix, npix), dtype=dtype)
+
+
+def build_laplacian(W, lap_type='normalized', dtype=np.float32):
+    """Combinatorial `D - W` or normalised `I - D^-1/2 W D^-1/2` Laplacian of a weight matrix."""
+    d = np.ravel(W.sum(1))
+    if lap_type == 'combinatorial':
+        D = sparse.diags(d, 0, dtype=dtype)
+        return (D - W).tocsc()
+    elif lap_type == 'normalized':
+        # One product per stored entry, evaluated as (d_i^-1/2 * w_ij) * d_j^-1/2 like the
+        # reference's `D12 * W * D12`; no sparse-sparse multiplication needed.
+        Wc = W.tocoo()
+        d12 = np.power(d, -0.5).astype(dtype)
+        off = (d12[Wc.row] * Wc.data.astype(dtype)) * d12[Wc.col]
+        n = d.shape[0]
+        diag = np.arange(n)
+        rows = np.concatenate([diag, Wc.row])
+        cols = np.concatenate([diag, Wc.col])
+        vals = np.concatenate([np.ones(n, dtype=dtype), -off])
+        return sparse.csr_matrix((vals, (rows, cols)), shape=(n, n), dtype=dtype)
+    else:
+        raise ValueError('Unknown Laplacian type {}'.format(lap_type))
+
+
+def healpix_laplacian(nside=16, nest=True, lap_type='normalized', indexes=None, dtype=np.float32,
+                      use_4=False, std=None, full=False, new=False, n_neighbors=8):
+    """HEALPix Laplacian.  Only the in-repo 8-neighbour graph (`new=False`) exists here; the
+    reference's `new=True` delegates to an external PyGSP fork (utils.py:331-334)."""
+    if new:
+        raise NotImplementedError('new=True needs the PyGSP fork graph (SphereHealpix); '
+                                  'use new=False, the in-repo 8-neighbour graph')
+    if use_4:
+        raise NotImplementedError()     # as upstream (utils.py:268-270)
+    W = healpix_weightmatrix(nside=nside, nest=nest, indexes=indexes, dtype=dtype, std=std, full=full)
+    return build_laplacian(W, lap_type=lap_type)
+
+
+def rescale_L(L, lmax=2, scale=1):
+    """Rescale the Laplacian eigenvalues to [-scale, scale]:  L / (lmax/2) - I."""
+    M, M = L.shape
+    I = sparse.identity(M, format='csr', dtype=L.dtype)
+    L /= (lmax / 2)
+    L -= I
+    return L * scale
+
+
+def estimate_lmax(laplacian):
+    """1.02 x largest eigenvalue (ARPACK, deterministic start vector instead of a random one)."""
+    n = laplacian.shape[0]
+    if n < 3:
+        return 1.02 * np.linalg.eigvalsh(laplacian.toarray()).max().astype(laplacian.dtype)
+    v0 = np.cos(np.arange(n, dtype=np.float64) * 0.7390851332151607).astype(laplacian.dtype)
+    return 1.02 * sparse.linalg.eigsh(laplacian, k=1, which='LM', return_eigenvectors=False, v0=v0)[0]
+
+
+def build_laplacians(nsides, indexes=None, use_4=False, sampling='healpix', std=None, full=False,
+                     new=False, n_neighbors=8, lmax=None):
+    """List of rescaled Laplacians (COO, float32) and pooling factors from a list of nsides.
+
+    `lmax` (optional list, one value per level actually built) skips the eigenvalue solve.
+    """
+    L = []
+    p = []
+    if indexes is None:
+        indexes = [None] * len(nsides)
+    if not isinstance(std, list):
+        std = [std] * len(nsides)
+    if not isinstance(full, list):
+        full = [full] * len(nsides)
+    nside_last = -1
+    built = 0
+    for i, (nside, index, sigma, mat) in enumerate(zip(nsides, indexes, std, full)):
+        if isinstance(nside, tuple):
+            nside = nside[0]
+        if i > 0 and sampling != 'icosahedron':
+            p.append((nside_last // nside)**2)
+        if nside == nside_last and i < len(nsides) - 1:
+            L.append(L[-1].copy().tocoo())
+            continue
+        nside_last = nside
+        if i < len(nsides) - 1:
+            if sampling == 'healpix':
+                laplacian = healpix_laplacian(nside=nside, indexes=index, use_4=use_4, std=sigma,
+                                              full=mat, new=new, n_neighbors=n_neighbors)
+            elif sampling == 'icosahedron':
+                from .graphs import icosahedron_laplacian
+                laplacian = icosahedron_laplacian(order=nside)
+            elif sampling == 'equiangular':
+                raise NotImplementedError('equiangular sampling needs the PyGSP fork (out of scope)')
+            else:
+                raise ValueError('Unknown sampling: ' + sampling)
+            lm = estimate_lmax(laplacian) if lmax is None else lmax[built]
+            built += 1
+            laplacian = rescale_L(laplacian, lmax=lm)
+            L.append(laplacian.tocoo())
+    if sampling == 'icosahedron':
+        for order in nsides[1:]:
+            p.append(10 * 4 ** order + 2)
+    return L, p
+
+
+def nside2indexes(nsides, order):
+    """Pixel index lists for a 1/(12 order^2) part of the sphere at every nside."""
+    nsample = 12 * order**2
+    if order == 0:
+        nsample = 1
+    return [np.arange(hp.nside2npix(nside) // nsample) for nside in nsides]
+
+
+def ds_index(index, nsides, nest=True):
+    """Down-sample a nested pixel list given at nsides[0] to every coarser nside."""
+    assert isinstance(nsides, list)
+    assert len(nsides) > 1
+    assert nest
+    indexes = [index]
+    for nside in nsides[1:]:
+        p = (nsides[0] / nside)**2
+        if p < 1:
+            raise NotImplementedError("upsampling not implemented yet")
+        indexes.append(np.unique(index // p).astype(int))
+    return indexes

@@ -1,0 +1,168 @@
+"""Graph construction: oracle and product vs fixtures produced by the reference's own utils.py
+(tests/golden/make_golden.py), and the two HEALPix geometry implementations vs each other."""
+import os
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+from conftest import GOLDEN
+from oracle import graph as ograph
+from oracle import healpix as ohp
+from deepsphere_tf1_b200 import healpix as php
+from deepsphere_tf1_b200 import utils as putils
+
+G = np.load(os.path.join(GOLDEN, 'graph_golden.npz'))
+
+
+def parts(A):
+    A = sparse.csr_matrix(A).copy()
+    A.sum_duplicates()
+    A.sort_indices()
+    return A.data, A.indices.astype(np.int64), A.indptr.astype(np.int64)
+
+
+def assert_same(A, prefix, exact=True, rtol=0.0):
+    data, ind, ptr = parts(A)
+    assert tuple(G[prefix + '_shape']) == A.shape
+    np.testing.assert_array_equal(ptr, G[prefix + '_indptr'])
+    np.testing.assert_array_equal(ind, G[prefix + '_indices'])
+    assert data.dtype == G[prefix + '_data'].dtype == np.float32
+    if exact:
+        np.testing.assert_array_equal(data, G[prefix + '_data'])      # bit-exact
+    else:
+        np.testing.assert_allclose(data, G[prefix + '_data'], rtol=rtol, atol=rtol)
+
+
+IMPLS = [pytest.param(ograph, id='oracle'), pytest.param(putils, id='product')]
+
+
+@pytest.mark.parametrize('mod', IMPLS)
+@pytest.mark.parametrize('nside', [1, 2, 4, 8])
+def test_full_sphere_weights_and_laplacians_bit_exact(mod, nside):
+    W = mod.healpix_weightmatrix(nside=nside, nest=True, dtype=np.float32)
+    assert_same(W, 'full%d_W' % nside)
+    assert_same(mod.build_laplacian(W, 'normalized'), 'full%d_Lnorm' % nside)
+    assert_same(mod.build_laplacian(W, 'combinatorial'), 'full%d_Lcomb' % nside)
+
+
+@pytest.mark.parametrize('mod', IMPLS)
+def test_partial_sphere_fast_path(mod):
+    idx = mod.nside2indexes([32, 16, 8, 4, 4], 2)
+    for i in range(5):
+        np.testing.assert_array_equal(idx[i], G['n2i_order2_%d' % i])
+    np.testing.assert_array_equal(mod.nside2indexes([32], 1)[0], G['n2i_order1_0'])
+    np.testing.assert_array_equal(mod.nside2indexes([32, 16, 8, 4, 4], 0)[4], G['n2i_order0_4'])
+    W = mod.healpix_weightmatrix(nside=32, nest=True, indexes=idx[0], dtype=np.float32)
+    assert_same(W, 'part32o2_W')
+    assert_same(mod.build_laplacian(W, 'normalized'), 'part32o2_Lnorm')
+
+
+@pytest.mark.parametrize('mod', IMPLS)
+def test_partial_sphere_arbitrary_indexes(mod):
+    W = mod.healpix_weightmatrix(nside=8, nest=True, indexes=G['sel8_indexes'], dtype=np.float32)
+    assert_same(W, 'sel8_W')
+
+
+@pytest.mark.parametrize('mod', IMPLS)
+def test_explicit_kernel_width(mod):
+    assert_same(mod.healpix_weightmatrix(nside=4, nest=True, dtype=np.float32, std=0.05), 'full4std_W')
+
+
+@pytest.mark.parametrize('mod', IMPLS)
+def test_rescale_bit_exact(mod):
+    W = mod.healpix_weightmatrix(nside=4, nest=True, dtype=np.float32)
+    L = mod.build_laplacian(W, 'normalized')
+    assert_same(mod.rescale_L(sparse.csr_matrix(L).copy(), lmax=np.float32(1.93)), 'rescale4')
+
+
+@pytest.mark.parametrize('mod', IMPLS)
+def test_ds_index(mod):
+    ds = mod.ds_index(np.arange(512, 1024), [16, 8, 4])
+    for i, a in enumerate(ds):
+        np.testing.assert_array_equal(np.asarray(a), G['ds_index_%d' % i])
+
+
+@pytest.mark.parametrize('mod', IMPLS)
+def test_build_laplacians_pipeline(mod):
+    """Whole pipeline incl. the ARPACK lmax (start-vector dependent -> 1e-5 tolerance)."""
+    nsides = [32, 16, 8, 4, 4]
+    Ls, p = mod.build_laplacians(nsides, indexes=mod.nside2indexes(nsides, 2))
+    np.testing.assert_array_equal(np.array(p), G['bl_p'])
+    assert len(Ls) == int(G['bl_n'])
+    for i, L in enumerate(Ls):
+        assert L.format == 'coo' and L.dtype == np.float32
+        assert_same(L, 'bl_L%d' % i, exact=False, rtol=2e-5)
+    Ls, p = mod.build_laplacians([4, 2, 1])
+    np.testing.assert_array_equal(np.array(p), G['blfull_p'])
+    for i, L in enumerate(Ls):
+        assert_same(L, 'blfull_L%d' % i, exact=False, rtol=2e-5)
+
+
+def test_build_laplacians_product_equals_oracle_with_same_lmax():
+    nsides = [16, 8, 4, 4]
+    idx = putils.nside2indexes(nsides, 1)
+    lmax = [np.float32(1.9), np.float32(1.85), np.float32(1.8)]
+    La, pa = ograph.build_laplacians(nsides, indexes=idx, lmax=lmax)
+    Lb, pb = putils.build_laplacians(nsides, indexes=idx, lmax=lmax)
+    assert pa == pb == [4, 4, 1]
+    for A, B in zip(La, Lb):
+        for u, v in zip(parts(A), parts(B)):
+            np.testing.assert_array_equal(u, v)
+
+
+# ---- HEALPix geometry: scalar oracle vs vectorised product, plus SURVEY Appendix C invariants
+
+def test_healpy_docstring_example():
+    want = [11, 7, 3, -1, 0, 5, 8, -1]
+    assert list(ohp.get_all_neighbours(1, 4)) == want
+    assert list(php.get_all_neighbours(1, 4)) == want
+
+
+@pytest.mark.parametrize('nside', [1, 2, 4, 8, 16])
+def test_geometry_oracle_equals_product(nside):
+    npix = 12 * nside * nside
+    a = np.array(ohp.pix2vec(nside, range(npix)))
+    b = np.array(php.pix2vec(nside, np.arange(npix)))
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(ohp.get_all_neighbours(nside, range(npix)),
+                                  php.get_all_neighbours(nside, np.arange(npix)))
+
+
+@pytest.mark.parametrize('nside', [2, 8, 32, 64])
+def test_geometry_invariants(nside):
+    npix = 12 * nside * nside
+    pix = np.arange(npix)
+    v = np.array(php.pix2vec(nside, pix))
+    assert np.abs(np.linalg.norm(v, axis=0) - 1).max() < 1e-15
+    assert len(np.unique(np.round(v[2], 12))) == 4 * nside - 1
+    assert np.abs(v.sum(axis=1)).max() < 1e-9
+    nb = php.get_all_neighbours(nside, pix)
+    missing = (nb < 0).sum(axis=0)
+    assert (missing == 1).sum() == 24 and (missing > 1).sum() == 0
+    rows = np.repeat(pix, 8)
+    cols = nb.T.reshape(-1)
+    keep = cols >= 0
+    A = sparse.csr_matrix((np.ones(keep.sum()), (rows[keep], cols[keep])), shape=(npix, npix))
+    assert A.max() == 1                               # no duplicate neighbours
+    assert (A != A.T).nnz == 0                        # symmetric relation
+    assert A.nnz == 8 * npix - 24
+    d2 = ((v[:, rows[keep]] - v[:, cols[keep]])**2).sum(axis=0) / (4 * np.pi / npix)
+    assert 0.6 < d2.min() and d2.max() < 4.5
+    if nside >= 2:                                    # nested parent = mean of the 4 children
+        parent = np.array(php.pix2vec(nside // 2, np.arange(npix // 4)))
+        child = v.reshape(3, npix // 4, 4).mean(axis=2)
+        child /= np.linalg.norm(child, axis=0)
+        ang = np.arccos(np.clip((parent * child).sum(axis=0), -1, 1))
+        assert ang.max() < 0.2 * np.sqrt(4 * np.pi / (npix // 4))
+
+
+def test_cosmo_patch_is_a_square_grid():
+    """order-2 patches are open-boundary squares; degree histogram."""
+    nside = 64
+    idx = putils.nside2indexes([nside], 2)[0]
+    W = putils.healpix_weightmatrix(nside=nside, indexes=idx)
+    n = nside // 2
+    deg = np.diff(W.indptr)
+    assert (deg == 3).sum() == 4 and (deg == 5).sum() == 4 * (n - 2) and (deg == 8).sum() == (n - 2)**2
+    assert abs(W - W.T).max() < 1e-7
