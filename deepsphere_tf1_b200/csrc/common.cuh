@@ -1,0 +1,56 @@
+// Shared helpers for libdsb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/dsb200.h"
+
+namespace dsb200 {
+
+void set_error(const char* msg);
+void count_launch(int n = 1);     // host-side tally of kernel launches issued by this library
+
+#define DSB_REQUIRE(cond, msg) \
+    do { if (!(cond)) { ::dsb200::set_error(msg); return -1; } } while (0)
+#define DSB_LAUNCH_CHECK() \
+    do { ::dsb200::count_launch(); cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) { ::dsb200::set_error(cudaGetErrorString(e__)); return (int)e__; } return 0; } while (0)
+
+constexpr int kNumSMs = 148;       // B200: 2 dies x 74 SMs
+
+static inline int grid_for(long long work_items, int threads, int ctas_per_sm = 8) {
+    long long blocks = (work_items + threads - 1) / threads;
+    long long cap = (long long)kNumSMs * ctas_per_sm;
+    if (blocks > cap) blocks = cap;          // grid-stride loops cover the rest
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float act_fwd(float z, int act) {
+    switch (act) {
+        case DSB200_ACT_RELU: return z > 0.f ? z : 0.f;
+        case DSB200_ACT_ELU: return z > 0.f ? z : expm1f(z);
+        case DSB200_ACT_TANH: return tanhf(z);
+        case DSB200_ACT_SIGMOID: return 1.f / (1.f + expf(-z));
+        case DSB200_ACT_LEAKY_RELU: return z > 0.f ? z : 0.2f * z;
+        case DSB200_ACT_SOFTPLUS: return z > 20.f ? z : log1pf(expf(z));
+        case DSB200_ACT_RELU6: return fminf(fmaxf(z, 0.f), 6.f);
+        default: return z;
+    }
+}
+// derivative of the activation w.r.t. its input z
+__device__ __forceinline__ float act_grad(float z, int act) {
+    switch (act) {
+        case DSB200_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+        case DSB200_ACT_ELU: return z > 0.f ? 1.f : expf(z);
+        case DSB200_ACT_TANH: { float t = tanhf(z); return 1.f - t * t; }
+        case DSB200_ACT_SIGMOID: { float s = 1.f / (1.f + expf(-z)); return s * (1.f - s); }
+        case DSB200_ACT_LEAKY_RELU: return z > 0.f ? 1.f : 0.2f;
+        case DSB200_ACT_SOFTPLUS: return 1.f / (1.f + expf(-z));
+        case DSB200_ACT_RELU6: return (z > 0.f && z < 6.f) ? 1.f : 0.f;
+        default: return 1.f;
+    }
+}
+
+}  // namespace dsb200

@@ -1,0 +1,949 @@
+"""`cgcnn` / `deepsphere` models with the reference's constructor and fit / predict / evaluate
+API (reference deepsphere/models.py:929-1035 ctor, 432-618 fit, 113-260 predict / probs,
+343-430 evaluate, 1827-1839 deepsphere front-end), driving the libdsb200 CUDA kernels.
+
+The reference builds a static TF1 graph once (`build_graph`, models.py:647-726) and then issues
+one `sess.run` per batch.  Here the constructor builds a static *layer program* (a list of
+ChebConv / head / decoder stages with pre-bound device graphs and parameter views); a training
+step runs the program forward, walks it backwards with hand-written adjoint kernels, and applies
+the optimizer -- all as libdsb200 launches on one CUDA stream, optionally replayed as one CUDA
+graph.  PyTorch supplies device memory, streams and (for data parallelism) NCCL; no torch
+operator computes anything on the hot path and there is no CPU fallback.
+
+Differences from the reference that a user sees (also listed in DESIGN.md):
+  * `scheduler(step) -> float` and `optimizer(lr) -> deepsphere_tf1_b200.optimizers.*Optimizer`
+    replace the lambdas that returned TF objects;
+  * `tf_dataset` may be any Python iterator of `(data, labels)` batches;
+  * checkpoints are `torch.save` files `checkpoints/<dir_name>/model-<step>.pt` keyed by the
+    reference's variable names (`conv1/weights`, `conv1/batch_normalization/moving_mean`, ...);
+  * `conv='monomials'`, `statistics='histogram'`, `dropFilt < 1`, `extra_loss`, `weighted`,
+    equiangular sampling: NotImplementedError (outside the hot path).
+"""
+import glob
+import json
+import os
+import shutil
+import time
+
+import numpy as np
+import torch
+
+from . import ops, utils
+from ._consts import ACT, UNPOOL_REPEAT, UNPOOL_ZEROFILL
+from .graph import DeviceGraph
+from .optimizers import _Optimizer
+
+process_time = time.process_time
+perf_counter = time.perf_counter
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.9
+
+
+def _truncated_normal(rs, shape, std):
+    """tf.truncated_normal_initializer: samples beyond 2 sigma are re-drawn."""
+    a = rs.randn(*shape)
+    bad = np.abs(a) > 2
+    while bad.any():
+        a[bad] = rs.randn(int(bad.sum()))
+        bad = np.abs(a) > 2
+    return (a * std).astype(np.float32)
+
+
+class _ParamStore(object):
+    """All trainable variables in ONE flat fp32 device buffer (plus flat gradient, optimizer
+    slots and the per-element regularisation coefficient), so that the regulariser, the
+    data-parallel all-reduce and the optimizer are one launch each (models.py:806-808, 831-832)."""
+
+    def __init__(self):
+        self.specs = []          # (name, shape, offset, size, std or None)
+        self.size = 0
+
+    def add(self, name, shape, init, std=None):
+        n = int(np.prod(shape))
+        off = (self.size + 3) // 4 * 4                     # 16-byte aligned views
+        self.specs.append((name, tuple(shape), off, n, std, init))
+        self.size = off + n
+        return len(self.specs) - 1
+
+    def materialise(self, device, regularization):
+        host = np.zeros(self.size, dtype=np.float32)
+        coef = np.zeros(self.size, dtype=np.float32)
+        n_weights = sum(s[3] for s in self.specs if s[4] is not None)
+        for name, shape, off, n, std, init in self.specs:
+            host[off:off + n] = init.reshape(-1)
+            if std is not None:
+                # regularization * (l2_loss(W) / std^2) / n_weights   (models.py:806-808, 866)
+                coef[off:off + n] = regularization / (std * std) / max(n_weights, 1)
+        self.w = torch.from_numpy(host).to(device)
+        self.coef = torch.from_numpy(coef).to(device)
+        self.g = torch.zeros_like(self.w)
+        self.views = {}
+        self.gviews = {}
+        for name, shape, off, n, std, init in self.specs:
+            self.views[name] = self.w[off:off + n]
+            self.gviews[name] = self.g[off:off + n]
+        self.shapes = {s[0]: s[1] for s in self.specs}
+        self.n_trainable = sum(s[3] for s in self.specs)
+        self.has_reg = bool(regularization) and n_weights > 0
+
+
+class _ChebStage(object):
+    """filter -> [batch norm] -> [bias] -> [activation] -> [pool]   (models.py:1229-1243;
+    decoder up-conv / de-conv / out-conv, models.py:1304-1341, with the unused parts off)."""
+
+    def __init__(self, model, scope, graph, Fin, Fout, K, bn, bias, act, p=1, pool='max', keep=None):
+        self.m, self.scope, self.graph = model, scope, graph
+        self.Fin, self.Fout, self.K = Fin, Fout, K
+        self.bn, self.has_bias, self.act = bn, bias, act
+        self.p, self.pool = p, pool            # HEALPix pooling over p consecutive vertices
+        self.keep = keep                       # icosahedral "pooling": keep the first `keep` vertices
+        std = 1 / np.sqrt(Fin * (K + 0.5) / 2)                             # models.py:1080-1083
+        model._P.add(scope + '/weights', (Fin * K, Fout), _truncated_normal(model._rs, (Fin * K, Fout), std), std)
+        if bn:
+            model._add_bn(scope, Fout)
+        if bias:
+            model._P.add(scope + '/bias', (1, 1, Fout), np.zeros(Fout, np.float32))
+        self.post = bn or bias or act != 'identity' or p > 1
+        self.saved = None
+
+    def forward(self, x, training, save):
+        m = self.m
+        B, M, Fin = x.shape
+        if M != self.graph.M or Fin != self.Fin:
+            raise ValueError('{}: input [{}, {}] does not fit the Laplacian ({} vertices) / weights ({} features)'
+                             .format(self.scope, M, Fin, self.graph.M, self.Fin))
+        W = m._P.views[self.scope + '/weights']
+        basis = ops.cheb_basis(self.graph, x, self.K)                      # models.py:1049-1061
+        sums = None
+        if self.bn and training:
+            sums = torch.zeros(2 * self.Fout, dtype=torch.float64, device=x.device)
+        y = ops.contract_fwd(x, basis, W, self.K, self.Fout, sums)         # models.py:1062-1078
+        mean = rstd = None
+        count = float(B * M * m.world_size)
+        if self.bn:
+            mean, rstd = m._bn_buffers(self.scope, self.Fout)
+            mm, mv = m._state[self.scope + '/batch_normalization/moving_mean'], \
+                m._state[self.scope + '/batch_normalization/moving_variance']
+            if training:
+                m._allreduce(sums)                                         # SyncBN over the data-parallel group
+                ops.bn_finalize(sums, count, self.Fout, mean, rstd, mm, mv, BN_EPS, BN_MOMENTUM)
+            else:
+                ops.bn_from_moving(mm, mv, mean, rstd, BN_EPS)
+        out = y
+        if self.post:
+            b = m._P.views[self.scope + '/bias'] if self.has_bias else None
+            out = ops.bn_act_pool_fwd(y, mean, rstd, b, self.p, self.pool, self.act)
+        if self.keep is not None and self.keep != out.shape[1]:
+            out = ops.vertex_resize(out, self.keep, 0.0)                   # x[:, :p, :]  (models.py:1138,1157)
+        if save:
+            self.saved = (x, basis, y, mean, rstd, count, training)
+        return out
+
+    def backward(self, dout, need_dx=True):
+        m = self.m
+        x, basis, y, mean, rstd, count, training = self.saved
+        self.saved = None
+        B, M, Fin = x.shape
+        if self.keep is not None and dout.shape[1] != M // self.p:
+            dout = ops.vertex_resize(dout, M // self.p, 0.0)               # adjoint of the slice
+        dy = dout
+        if self.post:
+            b = m._P.views[self.scope + '/bias'] if self.has_bias else None
+            dy, sums = ops.bn_act_pool_bwd(y, mean, rstd, b, dout, self.p, self.pool, self.act)
+            if self.bn and training:
+                m._allreduce(sums)
+            if self.has_bias:
+                    # with synchronised batch norm the sums are already global: pre-divide so that the
+                # flat gradient all-reduce (a sum over ranks) leaves the bias gradient unchanged
+                gb = m._P.gviews[self.scope + '/bias']
+                ops.sums_to_float(sums, gb)
+                if self.bn and training and m.world_size > 1:
+                    ops.scale(gb, 1.0 / m.world_size)            # the flat all-reduce sums it back
+            if self.bn and training:
+                ops.bn_bwd_apply(y, mean, rstd, sums, count, dy)
+        ops.contract_bwd_weight(x, basis, dy, m._P.gviews[self.scope + '/weights'], self.K)
+        if not need_dx:
+            return None
+        W = m._P.views[self.scope + '/weights']
+        G = ops.contract_bwd_data(dy, W, self.K, Fin)
+        return ops.cheb_basis_bwd(self.graph, G)
+
+
+class _FcStage(object):
+    """cgcnn.fc (+ activation + dropout) (models.py:1205-1217, 1275-1285)."""
+
+    def __init__(self, model, scope, Min, Mout, bias, act, dropout):
+        self.m, self.scope, self.Min, self.Mout = model, scope, Min, Mout
+        self.has_bias, self.act, self.dropout = bias, act, dropout
+        std = 1 / np.sqrt(Min)
+        model._P.add(scope + '/weights', (Min, Mout), _truncated_normal(model._rs, (Min, Mout), std), std)
+        if bias:
+            model._P.add(scope + '/bias', (Mout,), np.zeros(Mout, np.float32))
+        if act not in ('relu', 'identity'):
+            raise NotImplementedError('fully connected layers support relu / identity activations')
+
+    def forward(self, x, training, save):
+        m = self.m
+        W = m._P.views[self.scope + '/weights']
+        b = m._P.views[self.scope + '/bias'] if self.has_bias else None
+        y = ops.fc_fwd(x, W, b, self.act)
+        out, u = y, None
+        if training and self.dropout < 1:
+            u = m._dropout_uniform(self.scope, y)
+            out = ops.dropout(y, u, self.dropout)
+        if save:
+            self.saved = (x, y, u)
+        return out
+
+    def backward(self, dout, need_dx=True):
+        m = self.m
+        x, y, u = self.saved
+        self.saved = None
+        if u is not None:
+            dout = ops.dropout(dout, u, self.dropout)
+        W = m._P.views[self.scope + '/weights']
+        db = m._P.gviews[self.scope + '/bias'] if self.has_bias else None
+        return ops.fc_bwd(x, W, y, dout, m._P.gviews[self.scope + '/weights'], db, self.act, need_dx)
+
+
+class base_model(object):
+    """Run loops shared by all models (reference `base_model`, models.py:68-879)."""
+
+    sampling = 'healpix'
+    icosahedron_finest = 10 * 4 ** 5 + 2       # the reference hard-codes the level-5 mesh (models.py:1300)
+
+    # ------------------------------------------------------------------ high-level interface
+    def _batches(self, data, labels, cache):
+        """Yield (begin, end, device batch, device labels | None, host labels | None) with the
+        tail batch zero-padded to `batch_size` like the reference (models.py:136-160)."""
+        size = data.N if cache else data.shape[0]
+        bs = self.batch_size
+        data_iter = data.iter(bs) if cache else None
+        for begin in range(0, size, bs):
+            end = min(begin + bs, size)
+            host_labels = None
+            if cache:
+                batch_data, host_labels = next(data_iter)
+                batch_data = self._as_bmf(np.asarray(batch_data))
+            else:
+                tmp = data[begin:end]
+                if not isinstance(tmp, np.ndarray):
+                    tmp = tmp.toarray()
+                tmp = self._as_bmf(tmp)
+                batch_data = np.zeros((bs,) + tmp.shape[1:], dtype=np.float32)
+                batch_data[:end - begin] = tmp
+                if labels is not None:
+                    lshape = (bs, self.L[0].shape[0]) if self.dense else (bs,)
+                    host_labels = np.zeros(lshape, dtype=np.float32 if self.regression else np.int32)
+                    host_labels[:end - begin] = labels[begin:end]
+            yield begin, end, self._to_device(batch_data), self._labels_to_device(host_labels), host_labels
+
+    @staticmethod
+    def _as_bmf(a):
+        a = np.asarray(a, dtype=np.float32)
+        return a[:, :, None] if a.ndim == 2 else a
+
+    def get_descriptor(self, data, sess=None, cache=True):
+        """Output of the last convolutional stage for every sample (models.py:77-111)."""
+        self._get_session(sess)
+        size = data.N if cache else data.shape[0]
+        out = None
+        for begin, end, x, _, _ in self._batches(data, None, cache):
+            _, desc = self._forward(x, training=False, save=False)
+            desc = desc.cpu().numpy()
+            if out is None:
+                out = np.empty((size,) + desc.shape[1:])
+            out[begin:end] = desc[:end - begin]
+        return out
+
+    def _run_eval(self, data, labels, sess, cache, want):
+        self._get_session(sess)
+        size = data.N if cache else data.shape[0]
+        loss, out, have_labels = 0.0, None, False
+        for begin, end, x, dev_labels, host_labels in self._batches(data, labels, cache):
+            logits, _ = self._forward(x, training=False, save=False)
+            if dev_labels is not None:
+                have_labels = True
+                loss += self._loss_only(logits, dev_labels)
+            if want == 'prediction':
+                if self.regression:
+                    batch = logits.reshape(logits.shape[0], -1).squeeze(-1) if not self.dense else logits.squeeze(-1)
+                    batch = batch.cpu().numpy()
+                else:
+                    batch = ops.softmax_argmax(logits, False)[1].cpu().numpy()
+            else:
+                batch = ops.softmax_argmax(logits, True)[0].cpu().numpy()
+            if out is None:
+                out = np.empty((size,) + batch.shape[1:])
+            out[begin:end] = batch[:end - begin]
+        if have_labels:
+            return out, loss * self.batch_size / size
+        return out
+
+    def predict(self, data, labels=None, sess=None, cache=False):
+        """Predicted classes (or regressed values); with labels also the loss (models.py:113-181)."""
+        return self._run_eval(data, labels, sess, cache, 'prediction')
+
+    def probs(self, data, nb_class, labels=None, sess=None, cache=False):
+        """Class probabilities; with labels also the loss (models.py:183-260)."""
+        return self._run_eval(data, labels, sess, cache, 'probabilities')
+
+    def evaluate(self, data, labels, sess=None, cache=False):
+        """One evaluation pass; returns (string, accuracy, f1, loss, metrics) (models.py:343-430)."""
+        import sklearn.metrics
+        import sklearn.preprocessing
+        t_cpu, t_wall = process_time(), time.time()
+        if self.dense and not self.regression:
+            probabilities, loss = self.probs(data, 3, labels, sess, cache=cache)
+            predictions = np.argmax(probabilities, axis=-1)
+        else:
+            predictions, loss = self.predict(data, labels, sess, cache=cache)
+        if cache:
+            labels = data.get_labels()
+        if hasattr(self, 'val_mask'):
+            predictions = predictions * data[..., -2]
+            labels = labels * data[..., -1]
+        if self.regression:
+            exp_var = sklearn.metrics.explained_variance_score(labels, predictions)
+            r2 = sklearn.metrics.r2_score(labels, predictions)
+            mae = sklearn.metrics.mean_absolute_error(labels, predictions)
+            string = 'explained variance: {:.4f}, r2: {:.4f}, loss (MSE): {:.3e}, loss (MAE): {:.3e}'.format(
+                exp_var, r2, loss, mae)
+            accuracy, f1 = exp_var, r2
+            mre = np.mean(np.abs((labels - predictions) / np.clip(labels, 1, None))) * 100
+            metrics = mae, mre
+        elif self.dense:
+            # the reference reports the per-class average precision and zeroes accuracy / f1
+            # for the 3-class climate task (models.py:390-418)
+            labels = np.asarray(labels).flatten()
+            true = sklearn.preprocessing.label_binarize(labels, classes=[0, 1, 2])
+            AP = sklearn.metrics.average_precision_score(true, probabilities.reshape(-1, 3), average=None)
+            ncorrects, class_acc, accuracy, f1 = 0, [0, 0, 0], 0, [0, 0, 0]
+            string = 'accuracy: {:.2f} ({:d} / {:d}), f1 (TC): {:.2f}, f1 (AR): {:.2f}, loss: {:.2e}'.format(
+                accuracy, ncorrects, len(labels), 100 * f1[1], 100 * f1[2], loss)
+            metrics = AP, class_acc
+        else:
+            metrics = None
+            labels = np.asarray(labels).flatten()
+            predictions = predictions.flatten()
+            ncorrects = int(np.sum(predictions == labels))
+            accuracy = 100 * sklearn.metrics.accuracy_score(labels, predictions)
+            f1 = 100 * sklearn.metrics.f1_score(labels, predictions, average='weighted')
+            string = 'accuracy: {:.2f} ({:d} / {:d}), f1 (weighted): {:.2f}, loss: {:.2e}'.format(
+                accuracy, ncorrects, len(labels), f1, loss)
+        if sess is None:
+            string += '\nCPU time: {:.0f}s, wall time: {:.0f}s'.format(process_time() - t_cpu, time.time() - t_wall)
+        return string, accuracy, f1, loss, metrics
+
+    def fit(self, train_dataset, val_dataset, use_tf_dataset=False, restore=True, verbose=True, cache=False):
+        """Training loop (models.py:432-618).  Returns (accuracies_validation, losses_validation,
+        losses_training, t_step, mean time per batch)."""
+        t_cpu, t_wall = process_time(), time.time()
+        ckpt_dir = self._get_path('checkpoints')
+        start_step = 1
+        if restore and self._restore_latest():
+            start_step = self.global_step + 1
+            print('training from last checkpoint')
+        else:
+            print('training from scratch')
+            shutil.rmtree(self._get_path('summaries'), ignore_errors=True)
+            shutil.rmtree(ckpt_dir, ignore_errors=True)
+            os.makedirs(ckpt_dir)
+            self._reset_variables()
+        os.makedirs(self._get_path('summaries'), exist_ok=True)
+        summary = open(os.path.join(self._get_path('summaries'), 'scalars.jsonl'), 'a')
+
+        accuracies_validation, losses_validation, losses_training = [], [], []
+        num_steps = int(self.num_epochs * train_dataset.N / self.batch_size)
+        if use_tf_dataset:
+            if self.tf_dataset is None:
+                raise ValueError('use_tf_dataset=True needs the tf_dataset constructor argument')
+            train_iter = iter(self.tf_dataset)
+        else:
+            train_iter = train_dataset.iter(self.batch_size)
+        if not cache:
+            val_data, val_labels = val_dataset.get_all_data()
+            if len(val_data.shape) == 2:
+                val_data = np.expand_dims(val_data, axis=2)
+
+        times = []
+        loss = float('nan')
+        for step in range(start_step, num_steps + 1):
+            t_begin = perf_counter()
+            batch_data, batch_labels = next(train_iter)
+            if not isinstance(batch_data, (np.ndarray, torch.Tensor)):
+                batch_data = batch_data.toarray()
+            evaluate = (step % self.eval_frequency == 0) or (step == num_steps)
+            t_begin_load = perf_counter()
+            learning_rate, loss_dev = self.train_step(batch_data, batch_labels)
+            if evaluate or self.sync_every_step:
+                loss = float(loss_dev)                      # device -> host read of the step's loss
+            t_end = perf_counter()
+            times.append(t_end - t_begin)
+            if not evaluate:
+                continue
+            epoch = step * self.batch_size / train_dataset.N
+            if verbose:
+                print('step {} / {} (epoch {:.2f} / {}):'.format(step, num_steps, epoch, self.num_epochs))
+                print('  learning_rate = {:.2e}, training loss = {:.2e}'.format(learning_rate, loss))
+            losses_training.append(loss)
+            record = {'step': step, 'learning_rate': learning_rate, 'loss/total': loss}
+            if cache:
+                string, accuracy, f1, vloss, metrics = self.evaluate(val_dataset, None, self, cache=cache)
+            else:
+                string, accuracy, f1, vloss, metrics = self.evaluate(val_data, val_labels, self)
+            if not self.regression:
+                accuracies_validation.append(accuracy)
+            losses_validation.append(vloss)
+            record.update({'validation/accuracy': float(np.mean(accuracy)), 'validation/loss': float(vloss)})
+            if verbose:
+                print('  validation {}'.format(string))
+                print('  CPU time: {:.0f}s, wall time: {:.0f}s, perf_time_load: {:.3f}s, perf_time: {:.3f}s'.format(
+                    process_time() - t_cpu, time.time() - t_wall, t_end - t_begin_load, times[-1]))
+            summary.write(json.dumps(record) + '\n')
+            summary.flush()
+            self.save_checkpoint(step)
+
+        if verbose and not self.regression and accuracies_validation:
+            print('validation accuracy: best = {:.2f}, mean = {:.2f}'.format(
+                max(accuracies_validation), np.mean(accuracies_validation[-10:])))
+        summary.close()
+        if verbose and times:
+            print('time per batch: mean = {:.5f}, var = {:.5f}'.format(np.mean(times), np.var(times)))
+        t_step = (time.time() - t_wall) / max(num_steps, 1)
+        return accuracies_validation, losses_validation, losses_training, t_step, (np.mean(times) if times else 0.0)
+
+    def get_var(self, name):
+        """Value of a variable by its reference name, from the latest checkpoint if one exists
+        (models.py:620-625)."""
+        self._get_session(None)
+        if name in self._P.views:
+            return self._P.views[name].cpu().numpy().reshape(self._P.shapes[name])
+        return self._state[name].cpu().numpy()
+
+    def get_nbr_var(self):
+        total = 0
+        for name, shape, off, n, std, init in self._P.specs:
+            print(name + ':0', n)
+            total += n
+        return total
+
+    # ------------------------------------------------------------------ checkpoints
+    def _get_path(self, folder):
+        path = os.path.dirname(os.path.realpath(__file__))
+        return os.path.join(path, '..', folder, self.dir_name)
+
+    def state_dict(self):
+        sd = {name: self._P.views[name].cpu().reshape(self._P.shapes[name]).clone() for name in self._P.views}
+        sd.update({k: v.cpu().clone() for k, v in self._state.items()})
+        sd['global_step'] = self.global_step
+        for i, s in enumerate(self._slots):
+            sd['optimizer/slot{}'.format(i)] = s.cpu().clone()
+        return sd
+
+    def load_state_dict(self, sd):
+        for name, view in self._P.views.items():
+            view.copy_(torch.as_tensor(sd[name], dtype=torch.float32).reshape(-1))
+        for k in self._state:
+            self._state[k].copy_(torch.as_tensor(sd[k], dtype=torch.float32))
+        self.global_step = int(sd.get('global_step', 0))
+        for i, s in enumerate(self._slots):
+            key = 'optimizer/slot{}'.format(i)
+            if key in sd:
+                s.copy_(sd[key])
+
+    def save_checkpoint(self, step):
+        if self.rank != 0:
+            return
+        d = self._get_path('checkpoints')
+        os.makedirs(d, exist_ok=True)
+        torch.save(self.state_dict(), os.path.join(d, 'model-{}.pt'.format(step)))
+        kept = sorted(glob.glob(os.path.join(d, 'model-*.pt')), key=lambda f: int(f.split('-')[-1][:-3]))
+        for f in kept[:-5]:                                  # tf.train.Saver(max_to_keep=5)
+            os.remove(f)
+
+    def _latest_checkpoint(self):
+        files = glob.glob(os.path.join(self._get_path('checkpoints'), 'model-*.pt'))
+        if not files:
+            return None
+        return max(files, key=lambda f: int(f.split('-')[-1][:-3]))
+
+    def _restore_latest(self):
+        f = self._latest_checkpoint()
+        if f is None:
+            return False
+        self.load_state_dict(torch.load(f, map_location='cpu'))
+        return True
+
+    def _get_session(self, sess=None):
+        """The reference restores the latest checkpoint when no session is passed
+        (models.py:851-860); a live model (`sess` = anything not None) keeps its weights."""
+        if sess is None:
+            self._restore_latest()
+        return self
+
+
+class cgcnn(base_model):
+    """Graph CNN with Chebyshev filters (reference `cgcnn`, models.py:882-1419).
+
+    Same hyper-parameters as the reference: L, F, K, p, batch_norm (one entry per graph
+    convolution), M (fully connected sizes, last = classes), conv / pool / activation /
+    statistics choices, Fseg, regularization, dropout, batch_size, eval_frequency, regression,
+    dense, dir_name.  Extra keyword arguments: `device` (default current CUDA device), `seed`,
+    `process_group` (torch.distributed group for data parallelism; default: the world group if
+    initialised), `cuda_graph` (replay the training step as one CUDA graph), `sync_every_step`.
+    """
+
+    def __init__(self, L, F, K, p, batch_norm, M,
+                 num_epochs, scheduler, optimizer, num_feat_in=1, tf_dataset=None, restore=False,
+                 conv='chebyshev5', pool='max', activation='relu', statistics=None, Fseg=None, dtype=np.float32,
+                 regularization=0, dropout=1, batch_size=128, eval_frequency=200, regression=False, dense=False,
+                 weighted=False, mask=None, extra_loss=False, dropFilt=1, dir_name='', profile=False, debug=False,
+                 device=None, seed=None, process_group=None, cuda_graph=False, sync_every_step=True, verbose=True):
+        # Verify the consistency w.r.t. the number of layers (models.py:937-950).
+        if not len(L) == len(F) == len(K) == len(p) == len(batch_norm):
+            raise ValueError('Wrong specification of the convolutional layers: '
+                             'parameters L, F, K, p, batch_norm, must have the same length.')
+        if not np.all(np.array(p) >= 1):
+            raise ValueError('Down-sampling factors p should be greater or equal to one.')
+        p_log2 = np.where(np.array(p) > 1, np.log2(p), 0)
+        if not np.all(np.mod(p_log2, 1) == 0) and self.sampling != 'icosahedron':
+            raise ValueError('Down-sampling factors p should be powers of two.')
+        if len(M) == 0 and p[-1] != 1 and self.sampling != 'icosahedron' and not dense:
+            raise ValueError('Down-sampling should not be used in the last '
+                             'layer if no fully connected layer follows.')
+        if mask and not isinstance(mask, list):
+            raise ValueError('Must provide a list of mask for training and validation.')
+        if conv != 'chebyshev5':
+            raise NotImplementedError("conv='{}' is outside the ChebConv hot path".format(conv))
+        if pool not in ('max', 'average'):
+            raise AttributeError("'cgcnn' object has no attribute 'pool_{}'".format(pool))
+        if activation not in ACT:
+            raise AttributeError("unknown activation '{}'".format(activation))
+        if statistics not in (None, 'mean', 'var', 'meanvar', 'max'):
+            if statistics == 'histogram':
+                raise NotImplementedError('the learned histogram layer is outside the hot path')
+            raise ValueError('Unknown statistical layer {}'.format(statistics))
+        if dropFilt < 1 or extra_loss or weighted:
+            raise NotImplementedError('dropFilt / extra_loss / weighted are outside the hot path')
+        if self.sampling == 'equiangular':
+            raise NotImplementedError('equiangular sampling is outside the hot path')
+        if np.dtype(dtype) != np.float32:
+            raise NotImplementedError('only float32 Laplacians are supported')
+        if not torch.cuda.is_available():
+            raise RuntimeError('deepsphere_tf1_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+
+        self.L, self.F, self.K, self.p, self.M = L, F, K, p, M
+        self.Fseg = Fseg
+        self.num_epochs = num_epochs
+        self.scheduler, self.optimizer = scheduler, optimizer
+        self.regularization, self.dropout = regularization, dropout
+        self.batch_size, self.eval_frequency = batch_size, eval_frequency
+        self.batch_norm = batch_norm
+        self.dir_name = dir_name
+        self.pool_kind, self.activation_name, self.statistics = pool, activation, statistics
+        self.profile, self.debug = profile, debug
+        self.regression, self.dense = regression, dense
+        self.restore, self.tf_dataset = restore, tf_dataset
+        self.num_feat_in = num_feat_in
+        self.cuda_graph, self.sync_every_step = cuda_graph, sync_every_step
+        if mask:
+            self.train_mask, self.val_mask = mask[0], mask[1]
+            raise NotImplementedError('masked regression is outside the hot path')
+
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        import torch.distributed as dist
+        self.pg = process_group
+        if dist.is_available() and dist.is_initialized():
+            self.world_size = dist.get_world_size(self.pg)
+            self.rank = dist.get_rank(self.pg)
+        else:
+            self.world_size, self.rank = 1, 0
+
+        if verbose:
+            self._print_architecture(num_feat_in)
+        self._build_program(seed)
+        self.global_step = 0
+        if restore:
+            self._restore_latest()
+
+    # ------------------------------------------------------------------ construction
+    def _print_architecture(self, num_feat_in):
+        L, F, K, p, M = self.L, self.F, self.K, self.p, self.M
+        print('NN architecture')
+        print('  input: M_0 = {}'.format(L[0].shape[0]))
+        for i in range(len(p)):
+            print('  layer {0}: cgconv{0}'.format(i + 1))
+            print('    representation: M_{0} * F_{1} / p_{1} = {2} * {3} / {4} = {5}'.format(
+                i, i + 1, L[i].shape[0], F[i], p[i], L[i].shape[0] * F[i] // p[i]))
+            F_last = F[i - 1] if i > 0 else num_feat_in
+            print('    weights: F_{0} * F_{1} * K_{1} = {2} * {3} * {4} = {5}'.format(
+                i, i + 1, F_last, F[i], K[i], F_last * F[i] * K[i]))
+            if not (i == len(p) - 1 and len(M) == 0):
+                print('    biases: F_{} = {}'.format(i + 1, F[i]))
+            if self.batch_norm[i]:
+                print('    batch normalization')
+        if self.statistics is not None:
+            print('  Statistical layer: {}'.format(self.statistics))
+
+    def _add_bn(self, scope, F):
+        self._state[scope + '/batch_normalization/moving_mean'] = torch.zeros(F, device=self.device)
+        self._state[scope + '/batch_normalization/moving_variance'] = torch.ones(F, device=self.device)
+
+    def _bn_buffers(self, scope, F):
+        if scope not in self._bn_buf:
+            self._bn_buf[scope] = (torch.empty(F, device=self.device), torch.empty(F, device=self.device))
+        return self._bn_buf[scope]
+
+    def _graph_for(self, i):
+        """Device copy of Laplacian level i; identical consecutive levels share one copy."""
+        if i in self._graphs:
+            return self._graphs[i]
+        for j, g in list(self._graphs.items()):
+            Lj = self.L[j]
+            if Lj.shape == self.L[i].shape and Lj.nnz == self.L[i].nnz and (Lj != self.L[i]).nnz == 0:
+                self._graphs[i] = g
+                return g
+        self._graphs[i] = DeviceGraph(self.L[i], self.device)
+        return self._graphs[i]
+
+    def _build_program(self, seed):
+        self._rs = np.random.RandomState(seed)
+        self._P = _ParamStore()
+        self._state, self._bn_buf, self._graphs = {}, {}, {}
+        n = len(self.p)
+        icos = self.sampling == 'icosahedron'
+        act, pool = self.activation_name, self.pool_kind
+        self._encoder = []
+        Fin, Mv = self.num_feat_in, self.L[0].shape[0]
+        skipF = [Fin]
+        for i in range(n):
+            scope = 'conv{}'.format(i + 1)
+            g = self._graph_for(i)
+            Mv = g.M
+            if i == n - 1 and len(self.M) == 0:            # linear layer before the softmax (models.py:1232-1234)
+                self._encoder.append(_ChebStage(self, scope, g, Fin, self.F[i], self.K[i], False, False, 'identity'))
+                Fin = self.F[i]
+                break
+            pi = self.p[i]
+            if icos:
+                st = _ChebStage(self, scope, g, Fin, self.F[i], self.K[i], self.batch_norm[i], True, act,
+                                keep=(pi if pi > 1 else None))
+                if pi > 1:
+                    Mv = pi
+            else:
+                if Mv % pi:
+                    raise ValueError('layer {}: {} vertices cannot be pooled by {}'.format(i + 1, Mv, pi))
+                st = _ChebStage(self, scope, g, Fin, self.F[i], self.K[i], self.batch_norm[i], True, act, p=pi, pool=pool)
+                Mv //= pi
+            self._encoder.append(st)
+            Fin = self.F[i]
+            skipF.append(Fin)
+        # statistics + fully connected head (models.py:1249-1285)
+        self._fc = []
+        if self.M:
+            Min = {None: Mv * Fin, 'meanvar': 2 * Fin}.get(self.statistics, Fin)
+            for i, Mo in enumerate(self.M[:-1]):
+                self._fc.append(_FcStage(self, 'fc{}'.format(i + 1), Min, Mo, True, act, self.dropout))
+                Min = Mo
+            self._fc.append(_FcStage(self, 'logits', Min, self.M[-1], False, 'identity', 1))
+        # decoder (models.py:1289-1344)
+        self._decoder = []
+        self._has_decoder = bool(self.dense and (np.asarray(self.p) > 1).any())
+        if self._has_decoder:
+            for i in range(1, n + 1):
+                j = n - i
+                g = self._graph_for(j)
+                up = None
+                if self.p[-i] > 1:
+                    if icos:
+                        target = self.p[-i - 1] if i + 1 <= n else self.icosahedron_finest  # models.py:1297-1301
+                        unpool = ('pad', target)
+                    else:
+                        if pool == 'max':
+                            unpool = ('zerofill', self.p[-i])
+                        else:
+                            unpool = ('repeat', self.p[-i])
+                    up = (unpool, _ChebStage(self, 'upconv{}'.format(j), g, Fin, self.F[-i], self.K[-i],
+                                             False, True, 'identity'))
+                    Fin = self.F[-i] + skipF[-i]
+                de = _ChebStage(self, 'deconv{}'.format(j), g, Fin, self.F[-i], self.K[-i],
+                                self.batch_norm[-i], True, act)
+                Fin = self.F[-i]
+                self._decoder.append((up, de, len(skipF) - i))        # pool_layers[-i]  (models.py:1311)
+            self._outconv = _ChebStage(self, 'outconv', self._graph_for(0), Fin, self.Fseg, 1, False, False, 'identity')
+        self._P.materialise(self.device, self.regularization)
+        self._init_w = self._P.w.clone()
+        # optimizer state
+        self._opt = self.optimizer(self.scheduler(0)) if self.optimizer is not None else None
+        if self._opt is not None and not isinstance(self._opt, _Optimizer):
+            raise TypeError('optimizer(lr) must return a deepsphere_tf1_b200.optimizers.*Optimizer')
+        self._slots = []
+        if self._opt is not None:
+            for s in range(self._opt.slots):
+                init = self._opt.slot1_init if s == 0 else 0.0
+                self._slots.append(torch.full_like(self._P.w, init))
+        self._hyper = torch.zeros(8, device=self.device)
+        self._loss = torch.zeros(1, device=self.device)
+        self._dropout_u = {}
+        self._gen = torch.Generator(device=self.device)
+        self._gen.manual_seed(0 if seed is None else int(seed))
+        self._graph_exec = None
+
+    def _reset_variables(self):
+        """`sess.run(op_init)`: back to the initial values (models.py:476-479)."""
+        self._P.w.copy_(self._init_w)
+        for k, v in self._state.items():
+            v.fill_(0.0 if k.endswith('moving_mean') else 1.0)
+        for s, buf in enumerate(self._slots):
+            buf.fill_(self._opt.slot1_init if s == 0 else 0.0)
+        self.global_step = 0
+        self._graph_exec = None
+
+    def set_var(self, name, value):
+        """Overwrite a variable / batch-norm statistic by its reference name."""
+        t = torch.as_tensor(np.asarray(value), dtype=torch.float32).reshape(-1).to(self.device)
+        if name in self._P.views:
+            self._P.views[name].copy_(t)
+        else:
+            self._state[name].copy_(t)
+
+    def get_filter_coeffs(self, layer, ind_in=None, ind_out=None):
+        """Chebyshev coefficients of a layer as K x Fout x Fin (models.py:1377-1401)."""
+        K, Fout = self.K[layer - 1], self.F[layer - 1]
+        w = self.get_var('conv{}/weights'.format(layer)).reshape((-1, K, Fout)).transpose([1, 2, 0])
+        if ind_in:
+            w = w[:, :, ind_in]
+        if ind_out:
+            w = w[:, ind_out, :]
+        return w
+
+    # ------------------------------------------------------------------ device plumbing
+    def _to_device(self, a):
+        if isinstance(a, torch.Tensor):
+            t = a.to(self.device, dtype=torch.float32, non_blocking=True)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(self._as_bmf(a))).to(self.device, non_blocking=True)
+        if t.dim() == 2:
+            t = t.unsqueeze(2)
+        return t.contiguous()
+
+    def _labels_to_device(self, labels):
+        if labels is None:
+            return None
+        if isinstance(labels, torch.Tensor):
+            t = labels.to(self.device, non_blocking=True)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(labels)).to(self.device, non_blocking=True)
+        t = t.to(torch.float32 if self.regression else torch.int32)
+        return t.contiguous()
+
+    def _allreduce(self, t):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.pg)
+
+    def _dropout_uniform(self, scope, like):
+        u = self._dropout_u.get(scope)
+        if u is None or u.shape != like.shape:
+            u = torch.empty_like(like)
+            self._dropout_u[scope] = u
+        u.uniform_(generator=self._gen)
+        return u
+
+    # ------------------------------------------------------------------ the layer program
+    def _forward(self, x, training, save):
+        """`_inference` (+ `_decoder`): returns (logits, descriptor) (models.py:1219-1344)."""
+        skips = [x]
+        for st in self._encoder:
+            x = st.forward(x, training, save)
+            if st.post:
+                skips.append(x)
+        descriptor = x
+        B = x.shape[0]
+        self._stat_saved = None
+        if self.statistics is not None:
+            s = ops.stat_fwd(x, self.statistics)
+            if save:
+                self._stat_saved = (x,)
+            x = s
+        elif self.M:
+            if save:
+                self._stat_saved = (x.shape,)
+            x = x.reshape(B, -1)
+        for fc in self._fc:
+            x = fc.forward(x, training, save)
+        if self._has_decoder:
+            for up, de, j in self._decoder:
+                if up is not None:
+                    (kind, arg), stage = up
+                    if kind == 'pad':
+                        xin = ops.vertex_resize(x, arg, 1.0)                 # tf.pad(..., constant_values=1)
+                    else:
+                        xin = ops.unpool_fwd(x, arg, UNPOOL_REPEAT if kind == 'repeat' else UNPOOL_ZEROFILL)
+                    if xin.shape[1] != stage.graph.M:
+                        raise ValueError('Down-sampling should not be used in the first layers if training '
+                                         'for segmentation task')
+                    stage.prev_M = x.shape[1]
+                    x = stage.forward(xin, training, save)
+                    x = ops.concat_f(x, skips[j])
+                x = de.forward(x, training, save)
+            x = self._outconv.forward(x, training, save)
+        return x, descriptor
+
+    def _backward(self, dlogits):
+        """Adjoint of `_forward`, accumulating into the flat gradient buffer."""
+        n_enc = len(self._encoder)
+        skip_grads = {}                                    # encoder skip index -> gradient from the decoder
+        d = dlogits
+        if self._has_decoder:
+            d = self._outconv.backward(d)
+            for up, de, j in reversed(self._decoder):
+                d = de.backward(d)
+                if up is not None:
+                    (kind, arg), stage = up
+                    Fa = stage.Fout
+                    da, db = ops.split_f(d, Fa)
+                    if j in skip_grads:
+                        ops.axpy(db, skip_grads[j], 1.0)
+                    else:
+                        skip_grads[j] = db
+                    dxin = stage.backward(da)
+                    if kind == 'pad':
+                        Mprev = stage.prev_M
+                        d = ops.vertex_resize(dxin, Mprev, 0.0) if dxin.shape[1] != Mprev else dxin
+                    else:
+                        d = ops.unpool_bwd(dxin, arg, UNPOOL_REPEAT if kind == 'repeat' else UNPOOL_ZEROFILL)
+        for fc in reversed(self._fc):
+            d = fc.backward(d)
+        if self.statistics is not None:
+            d = ops.stat_bwd(self._stat_saved[0], d, self.statistics)
+        elif self.M:
+            d = d.reshape(self._stat_saved[0])
+        # encoder: stage k produced skips[k + 1] (when it has a post chain)
+        for k in range(n_enc - 1, -1, -1):
+            st = self._encoder[k]
+            if st.post and (k + 1) in skip_grads:
+                ops.axpy(skip_grads.pop(k + 1), d, 1.0)
+            d = st.backward(d, need_dx=k > 0)
+        return d
+
+    def _loss_fwd_bwd(self, logits, labels, need_grad):
+        """Data term of `base_model.loss` (models.py:777-805) into self._loss; returns dlogits."""
+        gs = 1.0 / self.world_size
+        if self.regression:
+            pred = logits.reshape(-1)
+            tgt = labels.reshape(-1)
+            if pred.numel() != tgt.numel():
+                raise ValueError('regression: logits {} do not match labels {}'.format(tuple(logits.shape),
+                                                                                       tuple(labels.shape)))
+            d = ops.mse(pred, tgt, self._loss, gs, need_grad)
+            return d.reshape(logits.shape) if need_grad else None
+        return ops.softmax_ce(logits, labels, self._loss, gs, need_grad)
+
+    def _loss_only(self, logits, labels):
+        self._loss.zero_()
+        self._loss_fwd_bwd(logits, labels, False)
+        if self._P.has_reg:
+            ops.l2_reg(self._P.w, self._P.coef, None, self._loss)
+        return float(self._loss)
+
+    # ------------------------------------------------------------------ one training step
+    def _step_device(self, x, labels):
+        """forward + loss + backward + all-reduce + regulariser + optimizer, all on the stream.
+        The loss of the step (data term averaged over the ranks + regulariser) lands in self._loss."""
+        P = self._P
+        ops.fill(P.g, 0.0)
+        self._loss.zero_()
+        logits, _ = self._forward(x, training=True, save=True)
+        dlogits = self._loss_fwd_bwd(logits, labels, True)
+        self._backward(dlogits)
+        if self.world_size > 1:
+            self._allreduce(P.g)                           # one flat NCCL all-reduce for every gradient
+            ops.scale(self._loss, 1.0 / self.world_size)
+            self._allreduce(self._loss)
+        if P.has_reg:
+            ops.l2_reg(P.w, P.coef, P.g, self._loss)
+        ops.optimizer_step(self._opt.kind, P.w, P.g, self._slots[0] if self._slots else None,
+                           self._slots[1] if len(self._slots) > 1 else None, self._hyper)
+
+    def _advance_hyper(self):
+        """Learning rate of this step (`scheduler(global_step)`, models.py:826-827) and the
+        optimizer's scalars -> device; increments global_step.  The 32-byte copy comes from
+        pageable memory so the host may run ahead of the stream without overwriting it."""
+        step = self.global_step
+        lr = float(self.scheduler(step))
+        self._hyper.copy_(torch.tensor(self._opt.hyper(lr, step + 1), dtype=torch.float32), non_blocking=True)
+        self.global_step = step + 1
+        return lr
+
+    def train_step(self, batch_data, batch_labels):
+        """One `sess.run([op_train, op_loss])` (models.py:535-536, 822-843).  Returns
+        (learning_rate, loss) with the loss still on the device (a 1-element tensor)."""
+        if self._opt is None:
+            raise RuntimeError('model was built without an optimizer')
+        x = self._to_device(batch_data)
+        labels = self._labels_to_device(batch_labels)
+        if x.shape[0] != self.batch_size:
+            raise ValueError('batch of {} samples, model built for batch_size={}'.format(x.shape[0], self.batch_size))
+        lr = self._advance_hyper()
+        if self.cuda_graph:
+            self._step_graphed(x, labels)
+        else:
+            self._step_device(x, labels)
+        return lr, self._loss
+
+    def _capture(self, x, labels):
+        self._gx = x.clone()
+        self._gl = labels.clone()
+        # one eager warm-up on a side stream (allocator, NCCL), undone afterwards, then capture
+        snap = (self._P.w.clone(), [s.clone() for s in self._slots],
+                {k: v.clone() for k, v in self._state.items()})
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._step_device(self._gx, self._gl)
+        torch.cuda.current_stream().wait_stream(side)
+        self._P.w.copy_(snap[0])
+        for s, c in zip(self._slots, snap[1]):
+            s.copy_(c)
+        for k, v in snap[2].items():
+            self._state[k].copy_(v)
+        g = torch.cuda.CUDAGraph()
+        if self._dropout_u and hasattr(g, 'register_generator_state'):
+            g.register_generator_state(self._gen)
+        with torch.cuda.graph(g):
+            self._step_device(self._gx, self._gl)
+        self._graph_exec = g
+
+    def _step_graphed(self, x, labels):
+        """Replay the captured training step on a new batch."""
+        if self._graph_exec is None:
+            self._capture(x, labels)
+        self._gx.copy_(x, non_blocking=True)
+        self._gl.copy_(labels, non_blocking=True)
+        self._graph_exec.replay()
+
+    def _step_graph_resident(self, x=None, labels=None):
+        """Replay on the batch already sitting in the graph's input buffers."""
+        if self._graph_exec is None:
+            self._capture(x, labels)
+        self._graph_exec.replay()
+
+
+class deepsphere(cgcnn):
+    """Spherical CNN front-end: Laplacians and pooling factors from a list of nsides
+    (reference `deepsphere`, models.py:1784-1839).  `new=True` (the PyGSP-fork kNN graph) is
+    not available: the default here is the in-repo 8-neighbour graph, `new=False`."""
+
+    def __init__(self, nsides, indexes=None, use_4=False, sampling='healpix', std=None, full=False, new=False,
+                 n_neighbors=8, lmax=None, **kwargs):
+        L, p = utils.build_laplacians(nsides, indexes=indexes, use_4=use_4, sampling=sampling,
+                                      std=std, full=full, new=new, n_neighbors=n_neighbors, lmax=lmax)
+        self.sampling = sampling
+        if sampling == 'equiangular':
+            self.ratio = nsides[0][1] / nsides[0][0] if isinstance(nsides[0], tuple) else 1.
+        self.nsides = nsides
+        self.pygsp_graphs = [None] * len(nsides)
+        super(deepsphere, self).__init__(L=L, p=p, **kwargs)

@@ -1,0 +1,216 @@
+"""Tensor-level wrappers of the libdsb200 kernels (allocation + argument plumbing only).
+
+Every function takes / returns contiguous fp32 CUDA tensors in the reference's [B, M, F]
+layout and enqueues on torch's current stream.  The arithmetic lives in csrc/*.cu; PyTorch is
+used for device memory and streams, nothing else.  Reference call sites are cited per function.
+"""
+import torch
+
+from ._consts import ACT, POOL, STAT, UNPOOL_REPEAT, UNPOOL_ZEROFILL  # noqa: F401
+from ._lib import call
+
+
+def _new(shape, like, dtype=torch.float32):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, transpose=False):
+    """out = alpha * L x + beta * y + gamma * z  (tf.sparse_tensor_dense_matmul, models.py:1056,1059)."""
+    B, M, F = x.shape
+    rowptr, col, val, width = graph.bwd if transpose else graph.fwd
+    if out is None:
+        out = _new((B, M, F), x)
+    if rowptr is None:
+        call('spmm_ell', col, val, width, B, M, F, x, y, z, out, alpha, beta, gamma)
+    else:
+        call('spmm_csr', rowptr, col, val, B, M, F, x, y, z, out, alpha, beta, gamma)
+    return out
+
+
+def cheb_basis(graph, x, K):
+    """Orders 1..K-1 of the Chebyshev basis of x (models.py:1049-1061) as [K-1, B, M, F]."""
+    if K == 1:
+        return None
+    B, M, F = x.shape
+    rowptr, col, val, width = graph.fwd
+    basis = _new((K - 1, B, M, F), x)
+    call('cheb_basis', rowptr, col, val, width, B, M, F, K, x, basis)
+    return basis
+
+
+def cheb_basis_bwd(graph, G):
+    """Adjoint of the recurrence, in place: G [K, B, M, F] -> G[0] = dLoss/dx."""
+    K, B, M, F = G.shape
+    rowptr, col, val, width = graph.bwd
+    call('cheb_basis_bwd', rowptr, col, val, width, B, M, F, K, G)
+    return G[0]
+
+
+def contract_fwd(x, basis, W, K, Fout, bn_sums=None):
+    """Y = [X_0 .. X_{K-1}] . W  (tf.matmul, models.py:1062-1078), optional batch-norm sums."""
+    B, M, Fin = x.shape
+    y = _new((B, M, Fout), x)
+    call('cheb_contract_fwd', x, basis, W, y, B * M, Fin, K, Fout, bn_sums)
+    return y
+
+
+def contract_bwd_data(dy, W, K, Fin):
+    B, M, Fout = dy.shape
+    G = _new((K, B, M, Fin), dy)
+    call('cheb_contract_bwd_data', dy, W, G, B * M, Fin, K, Fout)
+    return G
+
+
+def contract_bwd_weight(x, basis, dy, dW, K):
+    B, M, Fin = x.shape
+    call('cheb_contract_bwd_weight', x, basis, dy, dW, B * M, Fin, K, dy.shape[2])
+
+
+def bn_finalize(sums, count, F, mean, rstd, moving_mean=None, moving_var=None, eps=1e-5, momentum=0.9):
+    call('bn_finalize', sums, float(count), F, eps, momentum, mean, rstd, moving_mean, moving_var)
+
+
+def bn_from_moving(moving_mean, moving_var, mean, rstd, eps=1e-5):
+    call('bn_from_moving', moving_mean, moving_var, moving_mean.numel(), eps, mean, rstd)
+
+
+def bn_act_pool_fwd(y, mean, rstd, bias, p, pool, act):
+    B, M, F = y.shape
+    out = _new((B, M // p, F), y)
+    call('bn_act_pool_fwd', y, mean, rstd, bias, out, B, M, F, p, POOL[pool], ACT[act])
+    return out
+
+
+def bn_act_pool_bwd(y, mean, rstd, bias, dout, p, pool, act):
+    B, M, F = y.shape
+    gz = _new((B, M, F), y)
+    sums = torch.zeros(2 * F, dtype=torch.float64, device=y.device)
+    call('bn_act_pool_bwd', y, mean, rstd, bias, dout, gz, sums, B, M, F, p, POOL[pool], ACT[act])
+    return gz, sums
+
+
+def bn_bwd_apply(y, mean, rstd, sums, count, gz):
+    B, M, F = y.shape
+    call('bn_bwd_apply', y, mean, rstd, sums, float(count), gz, B * M, F)
+
+
+def sums_to_float(sums, out):
+    call('sums_to_float', sums, out, out.numel())
+
+
+def vertex_resize(x, Mout, fill):
+    B, Min, F = x.shape
+    out = _new((B, Mout, F), x)
+    call('vertex_resize', x, out, B, Min, Mout, F, float(fill))
+    return out
+
+
+def unpool_fwd(x, p, mode):
+    B, M, F = x.shape
+    out = _new((B, M * p, F), x)
+    call('unpool_fwd', x, out, B, M, F, p, mode)
+    return out
+
+
+def unpool_bwd(dout, p, mode):
+    B, Mp, F = dout.shape
+    dx = _new((B, Mp // p, F), dout)
+    call('unpool_bwd', dout, dx, B, Mp // p, F, p, mode)
+    return dx
+
+
+def concat_f(a, b):
+    B, M, Fa = a.shape
+    Fb = b.shape[2]
+    out = _new((B, M, Fa + Fb), a)
+    call('concat_f', a, b, out, B * M, Fa, Fb)
+    return out
+
+
+def split_f(dout, Fa, db=None):
+    """da = dout[..., :Fa]; db (+)= dout[..., Fa:] (accumulates when db is given)."""
+    B, M, F = dout.shape
+    da = _new((B, M, Fa), dout)
+    acc = 1 if db is not None else 0
+    if db is None:
+        db = _new((B, M, F - Fa), dout)
+    call('split_f', dout, da, db, B * M, Fa, F - Fa, acc)
+    return da, db
+
+
+def stat_fwd(x, kind):
+    B, M, F = x.shape
+    out = _new((B, 2 * F if kind == 'meanvar' else F), x)
+    call('stat_fwd', x, out, B, M, F, STAT[kind])
+    return out
+
+
+def stat_bwd(x, dout, kind):
+    B, M, F = x.shape
+    dx = _new((B, M, F), x)
+    call('stat_bwd', x, dout, dx, B, M, F, STAT[kind])
+    return dx
+
+
+def fc_fwd(x, W, b, act):
+    N, Min = x.shape
+    y = _new((N, W.shape[1]), x)
+    call('fc_fwd', x, W, b, y, N, Min, W.shape[1], ACT[act])
+    return y
+
+
+def fc_bwd(x, W, y, dy, dW, db, act, need_dx=True):
+    N, Min = x.shape
+    dx = _new((N, Min), x) if need_dx else None
+    call('fc_bwd', x, W, y, dy, dx, dW, db, N, Min, W.shape[1], ACT[act])
+    return dx
+
+
+def softmax_ce(logits, labels, loss_out, grad_scale=1.0, need_grad=True):
+    C = logits.shape[-1]
+    R = logits.numel() // C
+    dlogits = torch.empty_like(logits) if need_grad else None
+    call('softmax_ce', logits, labels, dlogits, loss_out, R, C, grad_scale)
+    return dlogits
+
+
+def mse(pred, target, loss_out, grad_scale=1.0, need_grad=True):
+    dpred = torch.empty_like(pred) if need_grad else None
+    call('mse', pred, target, dpred, loss_out, pred.numel(), grad_scale)
+    return dpred
+
+
+def softmax_argmax(logits, want_probs=False):
+    C = logits.shape[-1]
+    R = logits.numel() // C
+    probs = torch.empty_like(logits) if want_probs else None
+    pred = torch.empty(logits.shape[:-1], dtype=torch.int32, device=logits.device)
+    call('softmax_argmax', logits, probs, pred, R, C)
+    return probs, pred
+
+
+def l2_reg(w, coef, g, loss_out):
+    call('l2_reg', w, coef, g, w.numel(), loss_out)
+
+
+def optimizer_step(kind, w, g, s1, s2, hyper):
+    call('optimizer_step', kind, w, g, s1, s2, hyper, w.numel())
+
+
+def fill(x, v):
+    call('fill', x, float(v), x.numel())
+
+
+def axpy(x, y, a=1.0):
+    call('axpy', x, y, float(a), x.numel())
+
+
+def scale(x, a):
+    call('scale', x, float(a), x.numel())
+
+
+def dropout(x, u, keep):
+    """tf.nn.dropout with an explicit uniform tensor (models.py:1279-1280); also its own backward."""
+    out = torch.empty_like(x)
+    call('dropout', x, u, float(keep), out, x.numel())
+    return out

@@ -1,0 +1,177 @@
+/*
+ * dsb200.h -- C ABI of the B200-native DeepSphere ChebConv hot path (libdsb200.so).
+ *
+ * The reference (deepsphere/deepsphere-tf1) is pure Python on TensorFlow 1.10 and has no
+ * FFI; its only operator seam is the `getattr` binding in cgcnn.__init__
+ * (deepsphere/models.py:1017-1020: self.filter / self.pool / self.unpool / self.activation)
+ * plus the TF ops those methods call.  Each entry point below replaces one of those TF op
+ * call sites (cited per function); a maintainer binds them with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer; the caller owns all buffers (the library never
+ *    allocates or frees device memory on the data path);
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no host sync,
+ *    no global state => re-entrant across streams and CUDA-graph capturable;
+ *  - return value: 0 on success, otherwise a cudaError_t (or -1 for invalid arguments);
+ *    dsb200_last_error() returns a static message for the last failure on this thread;
+ *  - activations are fp32 in the reference's own layout  x[b][m][f]  ("BMF": sample b, vertex
+ *    m, feature f; models.py:675) -- a row-major matrix [R, F] with R = B*M rows for the dense
+ *    contraction, and B independent row-major [M, F] matrices for the sparse products;
+ *  - Chebyshev weights keep the reference layout W[Fin*K, Fout], row = fin*K + k
+ *    (models.py:1062-1066);
+ *  - the rescaled Laplacian is passed as ELL (col[M*width], val[M*width], row-major, unused
+ *    slots col = -1 at the end of a row) or as CSR (rowptr[M+1], col[nnz], val[nnz]).
+ */
+#ifndef DSB200_H
+#define DSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSB200_ABI_VERSION 2
+
+/* activation ids (models.py:1020 `getattr(tf.nn, activation)`) */
+enum { DSB200_ACT_IDENTITY = 0, DSB200_ACT_RELU = 1, DSB200_ACT_ELU = 2, DSB200_ACT_TANH = 3,
+       DSB200_ACT_SIGMOID = 4, DSB200_ACT_LEAKY_RELU = 5, DSB200_ACT_SOFTPLUS = 6, DSB200_ACT_RELU6 = 7 };
+/* pooling ids (models.py:1018 `getattr(self, 'pool_' + pool)`) */
+enum { DSB200_POOL_MAX = 0, DSB200_POOL_AVERAGE = 1 };
+/* statistics ids (models.py:1249-1270) */
+enum { DSB200_STAT_MEAN = 0, DSB200_STAT_VAR = 1, DSB200_STAT_MEANVAR = 2, DSB200_STAT_MAX = 3 };
+/* optimizer ids (tf.train.*Optimizer passed through params['optimizer']) */
+enum { DSB200_OPT_SGD = 0, DSB200_OPT_MOMENTUM = 1, DSB200_OPT_ADAM = 2, DSB200_OPT_RMSPROP = 3 };
+/* unpooling modes (models.py:1347-1375) */
+enum { DSB200_UNPOOL_REPEAT = 0, DSB200_UNPOOL_ZEROFILL = 1 };
+
+int dsb200_abi_version(void);
+const char* dsb200_last_error(void);
+/* number of CUDA kernels this library has launched in this process (all threads) */
+long long dsb200_kernel_launches(void);
+
+/* ---- K1: one sparse-Laplacian product with fused recurrence arithmetic, for all B samples
+ *      out[b] = alpha * L x[b] + beta * y[b] + gamma * z[b]    (y, z NULL when beta/gamma == 0;
+ *      out may alias y or z)
+ * replaces tf.sparse_tensor_dense_matmul + `2*..-x0` (models.py:1056,1059); with
+ * (alpha,beta)=(1,0) it is X1 = L X0, with (2,-1) it is X_k = 2 L X_{k-1} - X_{k-2}; the
+ * backward pass uses it with L^T for the adjoint recurrence (autodiff of 1056-1061). */
+int dsb200_spmm_ell(const int32_t* col, const float* val, int width, int B, int M, int F,
+                    const float* x, const float* y, const float* z, float* out,
+                    float alpha, float beta, float gamma, void* stream);
+int dsb200_spmm_csr(const int32_t* rowptr, const int32_t* col, const float* val, int B, int M, int F,
+                    const float* x, const float* y, const float* z, float* out,
+                    float alpha, float beta, float gamma, void* stream);
+
+/* ---- all K Chebyshev orders of one layer (models.py:1049-1061).  x0 [B,M,F]; basis receives
+ * orders 1..K-1 as [K-1][B][M][F] (order 0 is x0 itself, never copied).  ELL if rowptr==NULL. */
+int dsb200_cheb_basis(const int32_t* rowptr, const int32_t* col, const float* val, int width,
+                      int B, int M, int F, int K, const float* x0, float* basis, void* stream);
+/* adjoint of the recurrence: G [K][B][M][F] holds dLoss/dX_k on entry; on exit G[0] holds
+ * dLoss/dX_0.  (colT, valT / rowptrT) describe L^T.  Overwrites G[1..K-1]. */
+int dsb200_cheb_basis_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int width,
+                          int B, int M, int F, int K, float* G, void* stream);
+
+/* ---- K2: dense contraction over (fin, k)  (tf.matmul, models.py:1062-1078)
+ *   Y[r, fo] = sum_{k, fi} X_k[r, fi] * W[fi*K + k, fo],   r < R = B*M
+ * x0 = order 0 [R,Fin], xk = orders 1..K-1 [K-1][R][Fin] (may be NULL when K == 1).
+ * If bn_sums != NULL (double[2*Fout], zeroed by the caller) the epilogue also accumulates
+ * sum_r Y and sum_r Y^2 per output feature (tf.nn.moments inside
+ * tf.layers.batch_normalization, models.py:1197-1203). */
+int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const float* W, float* Y,
+                             long long R, int Fin, int K, int Fout, double* bn_sums, void* stream);
+/* dX_k[r, fi] = sum_fo dY[r, fo] * W[fi*K + k, fo]  -> G [K][R][Fin]  (autodiff of 1077) */
+int dsb200_cheb_contract_bwd_data(const float* dY, const float* W, float* G,
+                                  long long R, int Fin, int K, int Fout, void* stream);
+/* dW[fi*K + k, fo] += sum_r X_k[r, fi] * dY[r, fo]  (dW must be zeroed by the caller) */
+int dsb200_cheb_contract_bwd_weight(const float* x0, const float* xk, const float* dY, float* dW,
+                                    long long R, int Fin, int K, int Fout, void* stream);
+
+/* ---- batch-norm statistics -> mean / rstd, moving-average update (models.py:1194-1203,
+ * UPDATE_OPS at 840-842).  sums = double[2*F] (sum, sum of squares over `count` rows, already
+ * all-reduced over ranks).  moving_* may be NULL.  momentum 0.9, eps 1e-5 in the reference. */
+int dsb200_bn_finalize(const double* sums, double count, int F, float eps, float momentum,
+                       float* mean, float* rstd, float* moving_mean, float* moving_var, void* stream);
+/* evaluation mode: mean/rstd from the moving statistics */
+int dsb200_bn_from_moving(const float* moving_mean, const float* moving_var, int F, float eps,
+                          float* mean, float* rstd, void* stream);
+
+/* ---- K3: fused  normalise -> + bias -> activation -> pool  (models.py:1235-1243)
+ *   y [B,M,F] -> out [B,M/p,F];   z = (y - mean)*rstd + bias (mean/rstd NULL = no batch norm,
+ *   bias NULL = none); pooling over p consecutive vertices (HEALPix nested order). */
+int dsb200_bn_act_pool_fwd(const float* y, const float* mean, const float* rstd, const float* bias,
+                           float* out, int B, int M, int F, int p, int pool, int act, void* stream);
+/* backward of the same chain: gz [B,M,F] = dLoss/dz, and sums_bwd (double[2*F], zeroed by the
+ * caller) += (sum gz, sum gz * xhat) per feature; sum gz is also the bias gradient. */
+int dsb200_bn_act_pool_bwd(const float* y, const float* mean, const float* rstd, const float* bias,
+                           const float* dout, float* gz, double* sums_bwd,
+                           int B, int M, int F, int p, int pool, int act, void* stream);
+/* dy = rstd * (gz - S1/count - xhat * S2/count), in place on gz (batch-norm backward);
+ * dbias (float[F], may be NULL) receives S1. */
+int dsb200_bn_bwd_apply(const float* y, const float* mean, const float* rstd, const double* sums_bwd,
+                        double count, float* gz, long long R, int F, void* stream);
+/* dbias[f] = (float) sums_bwd[f] */
+int dsb200_sums_to_float(const double* sums, float* out, int n, void* stream);
+
+/* ---- vertex-count change: out[b, m, f] = m < Min ? x[b, m, f] : fill,  m < Mout.
+ * Mout < Min is the icosahedral "pool" x[:, :p, :] (models.py:1138,1157); Mout > Min with
+ * fill = 1 is the icosahedral unpool tf.pad(..., constant_values=1) (models.py:1356-1358);
+ * fill = 0 gives the backward of the slice. */
+int dsb200_vertex_resize(const float* x, float* out, int B, int Min, int Mout, int F, float fill, void* stream);
+/* ---- HEALPix unpooling (models.py:1362-1364 repeat, 1372-1375 value then p-1 zeros) */
+int dsb200_unpool_fwd(const float* x, float* out, int B, int M, int F, int p, int mode, void* stream);
+int dsb200_unpool_bwd(const float* dout, float* dx, int B, int M, int F, int p, int mode, void* stream);
+
+/* ---- feature concat of two tensors along F (tf.concat axis=-1... models.py:1311) */
+int dsb200_concat_f(const float* a, const float* b, float* out, long long R, int Fa, int Fb, void* stream);
+/* da = dout[:, :Fa];  db (+)= dout[:, Fa:]  (accumulate_b != 0 adds into db) */
+int dsb200_split_f(const float* dout, float* da, float* db, long long R, int Fa, int Fb, int accumulate_b,
+                   void* stream);
+
+/* ---- K4: statistical head over vertices (models.py:1249-1270): x [B,M,F] -> out [B, F or 2F] */
+int dsb200_stat_fwd(const float* x, float* out, int B, int M, int F, int kind, void* stream);
+int dsb200_stat_bwd(const float* x, const float* dout, float* dx, int B, int M, int F, int kind, void* stream);
+
+/* ---- small dense layers of the head (cgcnn.fc, models.py:1205-1217): y = act(x W + b) */
+int dsb200_fc_fwd(const float* x, const float* W, const float* b, float* y, int N, int Min, int Mout,
+                  int act, void* stream);
+/* dz = dy * act'(z) is computed from y (= act(z)) for relu / identity only; dx = dz W^T,
+ * dW += x^T dz, db += sum dz.  dx may be NULL. */
+int dsb200_fc_bwd(const float* x, const float* W, const float* y, const float* dy, float* dx, float* dW,
+                  float* db, int N, int Min, int Mout, int act, void* stream);
+
+/* ---- losses (models.py:777-805).  logits [R, C] row-major, labels int32 [R]; loss_out[0] +=
+ * mean CE, dlogits = (softmax - onehot) * grad_scale / R (dlogits may be NULL).
+ * MSE: pred/target [n]. */
+int dsb200_softmax_ce(const float* logits, const int32_t* labels, float* dlogits, float* loss_out,
+                      long long R, int C, float grad_scale, void* stream);
+int dsb200_mse(const float* pred, const float* target, float* dpred, float* loss_out,
+               long long n, float grad_scale, void* stream);
+/* softmax probabilities / argmax (models.py:750-763); probs or pred may be NULL */
+int dsb200_softmax_argmax(const float* logits, float* probs, int32_t* pred, long long R, int C, void* stream);
+
+/* ---- regularisation term  sum_i ||W_i||^2 / 2 / std_i^2  over a flat parameter buffer with a
+ * per-element coefficient (models.py:806-808, 866): loss_out[0] += sum coef*w^2/2 and
+ * g += coef * w */
+int dsb200_l2_reg(const float* w, const float* coef, float* g, long long n, float* loss_out, void* stream);
+
+/* ---- optimizer step over a flat parameter buffer (tf.train.*Optimizer.apply_gradients,
+ * models.py:831-832).  hyper (DEVICE, float[8]): [0] lr, [1] beta1 | momentum | decay,
+ * [2] beta2 | rmsprop momentum, [3] epsilon, [4] lr_t (Adam bias-corrected step size),
+ * [5] gradient scale (1/world for data parallel sums), [6..7] unused.
+ * s1/s2 = optimizer slots (Adam m, v; Momentum accumulator; RMSProp ms, mom). */
+int dsb200_optimizer_step(int kind, float* w, const float* g, float* s1, float* s2,
+                          const float* hyper, long long n, void* stream);
+
+/* ---- misc */
+int dsb200_fill(float* x, float v, long long n, void* stream);
+int dsb200_axpy(const float* x, float* y, float a, long long n, void* stream); /* y += a*x */
+int dsb200_scale(float* x, float a, long long n, void* stream);               /* x *= a */
+/* tf.nn.dropout on the fc layers (models.py:1279-1280): out = u < keep ? x / keep : 0 with u a
+ * caller-supplied uniform [0,1) tensor; the same call applied to dout is the backward. */
+int dsb200_dropout(const float* x, const float* u, float keep, float* out, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSB200_H */

@@ -1,0 +1,155 @@
+"""Oracle restatement of the reference's TF1 graph operators, in torch-CPU (autograd gives
+the gradients TF1's `optimizer.compute_gradients` would, deepsphere/models.py:831).
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity unpinned: TensorFlow 1.10 cannot
+run here and the reference has no golden vectors for these operators; each function follows
+the cited lines of deepsphere/models.py statement by statement (same transposes / reshapes
+/ concatenations, so the memory order of every intermediate is the reference's).
+"""
+import numpy as np
+import torch
+import torch.nn.functional as TF
+
+
+def sparse_to_torch(L, dtype=torch.float32):
+    """models.py:1044-1047: COO triplets -> SparseTensor, reordered row-major, cast to dtype."""
+    L = L.tocoo()
+    order = np.lexsort((L.col, L.row))                       # tf.sparse_reorder
+    idx = torch.from_numpy(np.vstack([L.row[order], L.col[order]]).astype(np.int64))
+    val = torch.from_numpy(L.data[order].astype(np.float64)).to(dtype)
+    return torch.sparse_coo_tensor(idx, val, L.shape).coalesce().to_sparse_csr()
+
+
+def chebyshev5(x, L, W, K):
+    """models.py:1039-1078.  x [N, M, Fin], L torch sparse [M, M], W [Fin*K, Fout]."""
+    N, M, Fin = x.shape
+    Fout = W.shape[1]
+    x0 = x.permute(1, 2, 0)                                   # M x Fin x N        (1049)
+    x0 = x0.reshape(M, Fin * N)                               # M x Fin*N          (1050)
+    xs = x0.unsqueeze(0)                                      # 1 x M x Fin*N      (1051)
+    if K > 1:
+        x1 = torch.sparse.mm(L, x0)                           #                    (1056)
+        xs = torch.cat([xs, x1.unsqueeze(0)], dim=0)          #                    (1057)
+    for k in range(2, K):
+        x2 = 2 * torch.sparse.mm(L, x1) - x0                  #                    (1059)
+        xs = torch.cat([xs, x2.unsqueeze(0)], dim=0)
+        x0, x1 = x1, x2                                       #                    (1061)
+    xs = xs.reshape(K, M, Fin, N)                             #                    (1062)
+    xs = xs.permute(3, 1, 2, 0)                               # N x M x Fin x K    (1063)
+    xs = xs.reshape(N * M, Fin * K)                           #                    (1064)
+    y = xs @ W                                                #                    (1077)
+    return y.reshape(N, M, Fout)                              #                    (1078)
+
+
+def monomials(x, L, W, K):
+    """models.py:1085-1120 (monomial basis x, Lx, L^2x, ...)."""
+    N, M, Fin = x.shape
+    Fout = W.shape[1]
+    x0 = x.permute(1, 2, 0).reshape(M, Fin * N)
+    xs = x0.unsqueeze(0)
+    for k in range(1, K):
+        x1 = torch.sparse.mm(L, x0)
+        xs = torch.cat([xs, x1.unsqueeze(0)], dim=0)
+        x0 = x1
+    xs = xs.reshape(K, M, Fin, N).permute(3, 1, 2, 0).reshape(N * M, Fin * K)
+    return (xs @ W).reshape(N, M, Fout)
+
+
+def bias(x, b):
+    """models.py:1122-1126: one bias per filter, b of shape [1, 1, F]."""
+    return x + b.reshape(1, 1, -1)
+
+
+def batch_normalization(x, moving_mean, moving_var, training, momentum=0.9, eps=1e-5):
+    """models.py:1194-1203 -> tf.layers.batch_normalization(axis=-1, center=False,
+    scale=False): rank-3 input => non-fused path: tf.nn.moments over axes (0, 1) (biased
+    variance), y = (x - mean) * rsqrt(var + eps); moving <- moving*momentum + batch*(1-momentum)
+    through UPDATE_OPS (models.py:840-842).  Returns (y, new_moving_mean, new_moving_var)."""
+    if training:
+        mean = x.mean(dim=(0, 1))
+        var = ((x - mean) ** 2).mean(dim=(0, 1))
+        new_mean = moving_mean * momentum + mean.detach() * (1 - momentum)
+        new_var = moving_var * momentum + var.detach() * (1 - momentum)
+    else:
+        mean, var = moving_mean, moving_var
+        new_mean, new_var = moving_mean, moving_var
+    y = (x - mean) * torch.rsqrt(var + eps)
+    return y, new_mean, new_var
+
+
+def pool(x, p, kind, sampling):
+    """models.py:1128-1163: healpix = max/avg over p consecutive vertices (ksize [1,p,1,1],
+    SAME padding, M divisible by p); icosahedron = keep the first p vertices."""
+    if p > 1:
+        if sampling == 'equiangular':
+            raise NotImplementedError('equiangular pooling is out of scope (SURVEY section 2)')
+        if sampling == 'icosahedron':
+            return x[:, :p, :]
+        N, M, F = x.shape
+        xr = x.reshape(N, M // p, p, F)
+        return xr.max(dim=2).values if kind == 'max' else xr.mean(dim=2)
+    return x
+
+
+def unpool(x, p, kind, sampling):
+    """models.py:1347-1375.  average: healpix repeats each vertex p times, icosahedron pads to
+    p vertices with the constant 1; max: healpix puts the value first and p-1 zeros."""
+    N, M, F = x.shape
+    if kind == 'average':
+        if sampling == 'equiangular':
+            raise NotImplementedError('equiangular unpooling is out of scope')
+        if sampling == 'icosahedron':
+            return TF.pad(x, (0, 0, 0, int(p - M)), mode='constant', value=1.0)   # (1358)
+        return x.unsqueeze(2).repeat(1, 1, p, 1).reshape(N, M * p, F)             # (1363-1364)
+    if sampling in ('equiangular', 'icosahedron'):
+        raise NotImplementedError('unpooling max with {} sampling is not yet implemented'.format(sampling))
+    zeros = torch.zeros(N, M, p - 1, F, dtype=x.dtype)
+    return torch.cat([x.unsqueeze(2), zeros], dim=2).reshape(N, M * p, F)         # (1372-1375)
+
+
+def statistics(x, kind, has_fc):
+    """models.py:1249-1270 (tf.nn.moments => biased variance)."""
+    N, M, F = x.shape
+    if kind is None:
+        return x.reshape(N, M * F) if has_fc else x
+    if kind == 'mean':
+        return x.mean(dim=1)
+    if kind == 'var':
+        return ((x - x.mean(dim=1, keepdim=True)) ** 2).mean(dim=1)
+    if kind == 'meanvar':
+        mean = x.mean(dim=1)
+        var = ((x - x.mean(dim=1, keepdim=True)) ** 2).mean(dim=1)
+        return torch.cat([mean, var], dim=1)
+    if kind == 'max':
+        return x.max(dim=1).values
+    raise ValueError('Unknown statistical layer {}'.format(kind))
+
+
+def fc(x, W, b=None):
+    """models.py:1205-1212."""
+    y = x @ W
+    if b is not None:
+        y = y + b
+    return y
+
+
+ACTIVATIONS = {
+    'relu': torch.relu, 'elu': TF.elu, 'tanh': torch.tanh, 'sigmoid': torch.sigmoid,
+    'softplus': TF.softplus, 'leaky_relu': lambda x: TF.leaky_relu(x, 0.2),   # tf.nn.leaky_relu alpha=0.2
+    'relu6': TF.relu6,
+}
+
+
+def loss(logits, labels, regression, weights_and_std, regularization):
+    """models.py:777-820 (cross-entropy / MSE + regularization * sum_i(l2_loss(W_i)/std_i^2)/sum_i size_i).
+    `weights_and_std` = [(W_i, std_i)] in creation order (models.py:862-869)."""
+    if regression:
+        predictions = logits.squeeze()
+        data_loss = ((labels - predictions) ** 2).mean()                   # tf.losses.mean_squared_error
+    else:
+        C = logits.shape[-1]
+        ce = TF.cross_entropy(logits.reshape(-1, C), labels.reshape(-1).long(), reduction='none')
+        data_loss = ce.mean()
+    n_weights = sum(int(np.prod(W.shape)) for W, _ in weights_and_std)
+    reg = sum(((W ** 2).sum() / 2) / std ** 2 for W, std in weights_and_std) / n_weights
+    return data_loss + regularization * reg, data_loss

@@ -1,0 +1,209 @@
+"""GPU parity of whole models (`cgcnn` / `deepsphere` with the reference's constructor) against
+the CPU oracle `OracleCgcnn` on the same weights and inputs: logits, loss, every gradient, and a
+few optimizer steps.  Small versions of the five BASELINE.json configurations.
+Tolerance: fp32, max error <= 1e-4 of the largest expected magnitude (north_star); after several
+Adam steps 5e-4 (the optimizer divides by sqrt(v), which amplifies the 1e-7 noise of tiny gradients)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, copy_weights, healpix_L, random_knn_L
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+def _pair(L, sampling='healpix', seed=2, batch_size=4, finest=None, **kw):
+    from deepsphere_tf1_b200 import models, optimizers
+    from oracle.model import OracleCgcnn
+    okw = {k: v for k, v in kw.items() if k in ('F', 'K', 'p', 'batch_norm', 'M', 'num_feat_in', 'pool', 'activation',
+                                                'statistics', 'Fseg', 'regularization', 'dropout', 'regression', 'dense')}
+    attrs = {'sampling': sampling}
+    if finest is not None:
+        okw['finest_vertices'] = finest
+        attrs['icosahedron_finest'] = finest
+    oracle = OracleCgcnn(L, sampling=sampling, seed=seed, **okw)
+    cls = type('cgcnn_' + sampling, (models.cgcnn,), attrs)
+    kw.setdefault('optimizer', lambda lr: optimizers.AdamOptimizer(lr, epsilon=1e-8))
+    kw.setdefault('scheduler', lambda step: optimizers.exponential_decay(2e-3, step, 10, 0.9))
+    model = cls(L=L, num_epochs=1, batch_size=batch_size, eval_frequency=10, dir_name='_test_parity', verbose=False, **kw)
+    copy_weights(oracle, model)
+    return oracle, model
+
+
+def _check_step(oracle, model, x, labels, steps=3, rtol_after=5e-4, opt=None):
+    from oracle import optim_tf1
+    xt = torch.from_numpy(x)
+    lt = torch.from_numpy(labels)
+    # ---- forward / loss / gradients on identical weights
+    total, logits_ref, grads, _ = oracle.loss_and_grads(xt, lt, training=True)
+    xd, ld = model._to_device(x), model._labels_to_device(labels)
+    model._P.g.zero_()
+    model._loss.zero_()
+    logits, _ = model._forward(xd, training=True, save=True)
+    assert_close(logits, logits_ref.reshape(logits.shape), RTOL, 'logits')
+    d = model._loss_fwd_bwd(logits, ld, True)
+    model._backward(d)
+    from deepsphere_tf1_b200 import ops
+    if model._P.has_reg:
+        ops.l2_reg(model._P.w, model._P.coef, model._P.g, model._loss)
+    assert_close(model._loss, total.reshape(1), RTOL, 'loss')
+    for name, g in grads.items():
+        assert_close(model._P.gviews[name], g.reshape(-1), 2 * RTOL, 'grad ' + name)
+    # undo the batch-norm moving-average update of the probe forward
+    for k, v in oracle.state.items():
+        model.set_var(k, v.numpy())
+    # ---- a few optimizer steps (sess.run([op_train, op_loss]))
+    opt = opt or optim_tf1.Adam(epsilon=1e-8)
+    for t in range(steps):
+        lr = model.scheduler(t)
+        loss_ref, _ = oracle.train_step(xt, lt, opt, lr)
+        lr_p, loss_p = model.train_step(x, labels)
+        assert lr_p == pytest.approx(lr)
+        assert float(loss_p) == pytest.approx(loss_ref, rel=rtol_after)
+    for name, v in oracle.params.items():
+        assert_close(model._P.views[name], v.reshape(-1), rtol_after, 'weights ' + name)
+    for name, v in oracle.state.items():
+        assert_close(model._state[name], v, rtol_after, name)
+    # ---- inference mode (moving statistics)
+    ref, desc_ref = oracle.predict_logits(xt)
+    out, desc = model._forward(xd, training=False, save=False)
+    assert_close(out, ref.reshape(out.shape), rtol_after, 'eval logits')
+    assert_close(desc, desc_ref, rtol_after, 'descriptor')
+
+
+def test_cosmo_like_fcn_statistics_head():
+    """config 2 in miniature: partial sphere (order 2), K=5, max-pool 4, BN everywhere, last layer
+    linear, statistics='mean', M=[]  (experiments/cosmo/experiment_deepsphere.py:39-47)."""
+    from deepsphere_tf1_b200 import utils
+    nsides = [32, 16, 8, 4, 4]
+    idx = utils.nside2indexes(nsides, 2)
+    L, p = utils.build_laplacians(nsides, indexes=idx, new=False)
+    assert p == [4, 4, 4, 1] and [l.shape[0] for l in L] == [256, 64, 16, 4]
+    oracle, model = _pair(L, F=[16, 32, 64, 2], K=[5] * 4, p=p, batch_norm=[True] * 4, M=[], statistics='mean')
+    rs = np.random.RandomState(0)
+    x = (rs.randn(4, 256, 1) * 3.6).astype(np.float32)
+    labels = np.random.RandomState(1).randint(0, 2, size=4).astype(np.int32)
+    _check_step(oracle, model, x, labels)
+
+
+def test_shrec_like_cnn_head_full_sphere():
+    """config 1 in miniature: full sphere, 6 input features, K=4, fully connected softmax layer,
+    L2 regularisation, Adam with epsilon=0.1 (experiments/shrec17/hyperparameters.py:114-150)."""
+    from deepsphere_tf1_b200 import optimizers, utils
+    from oracle import optim_tf1
+    nsides = [8, 4, 2, 1, 1]
+    L, p = utils.build_laplacians(nsides, new=False)
+    oracle, model = _pair(L, F=[16, 32, 64, 128], K=[4] * 4, p=p, batch_norm=[True] * 4, M=[55], num_feat_in=6,
+                          statistics='mean', regularization=0.1, batch_size=5,
+                          optimizer=lambda lr: optimizers.AdamOptimizer(lr, epsilon=0.1))
+    rs = np.random.RandomState(0)
+    x = rs.randn(5, 768, 6).astype(np.float32)
+    labels = np.random.RandomState(1).randint(0, 55, size=5).astype(np.int32)
+    _check_step(oracle, model, x, labels, opt=optim_tf1.Adam(epsilon=0.1))
+
+
+@pytest.mark.parametrize('stat,M,pool', [(None, [20, 3], 'average'), ('meanvar', [3], 'max'), ('max', [3], 'max'),
+                                         ('var', [3], 'average')])
+def test_heads_and_pools(stat, M, pool):
+    L = [healpix_L(4), healpix_L(2)]
+    oracle, model = _pair(L, F=[8, 12], K=[3, 3], p=[4, 1], batch_norm=[True, False], M=M, num_feat_in=2,
+                          statistics=stat, pool=pool, activation='elu' if stat == 'var' else 'relu')
+    rs = np.random.RandomState(4)
+    x = rs.randn(4, 192, 2).astype(np.float32)
+    labels = rs.randint(0, 3, size=4).astype(np.int32)
+    # fully connected layers only support relu in the product; the elu case has no hidden fc layer
+    _check_step(oracle, model, x, labels)
+
+
+@pytest.mark.parametrize('pool', ['max', 'average'])
+def test_healpix_encoder_decoder_segmentation(pool):
+    """dense=True with HEALPix pooling: unpool -> upconv -> concat skip -> deconv, outconv K=1
+    (models.py:1289-1344)."""
+    L = [healpix_L(4), healpix_L(2), healpix_L(1)]
+    oracle, model = _pair(L, F=[8, 16, 16], K=[3, 3, 3], p=[4, 4, 1], batch_norm=[True, True, True], M=[],
+                          num_feat_in=3, pool=pool, dense=True, Fseg=3, regularization=0.05)
+    rs = np.random.RandomState(6)
+    x = rs.randn(4, 192, 3).astype(np.float32)
+    labels = rs.randint(0, 3, size=(4, 192)).astype(np.int32)
+    _check_step(oracle, model, x, labels)
+
+
+def test_climate_like_icosahedral_segmentation():
+    """config 3 in miniature: icosahedral pooling = keep the first p vertices, unpooling = pad with
+    ones (models.py:1137-1138, 1356-1358); level sizes 162 -> 42 -> 12 with kNN stand-in graphs
+    (the pooling logic only depends on the vertex counts)."""
+    sizes = [162, 162, 42, 12]
+    L = [random_knn_L(n, 6, seed=n) for n in sizes]
+    p = [162, 42, 12, 12]
+    # the reference pads the finest level to a hard-coded 10*4**5+2 vertices (models.py:1300), which
+    # only fits level-5 meshes; the miniature overrides that constant with its own finest size
+    oracle, model = _pair(L, sampling='icosahedron', finest=162, F=[8, 16, 16, 16], K=[4] * 4, p=p,
+                          batch_norm=[True] * 4, M=[], num_feat_in=4, pool='average', dense=True, Fseg=3)
+    rs = np.random.RandomState(8)
+    x = rs.randn(4, 162, 4).astype(np.float32)
+    labels = rs.choice(3, size=(4, 162), p=[0.9, 0.02, 0.08]).astype(np.int32)
+    _check_step(oracle, model, x, labels)
+
+
+def test_ghcn_like_irregular_graph_dense_regression():
+    """config 5 in miniature: irregular kNN graph (CSR path), un-rescaled combinatorial Laplacian,
+    p = 1 everywhere, dense regression (experiments/ghcn/GHCN_train.py:7-32)."""
+    Lg = random_knn_L(300, 10, rescale=False)
+    L = [Lg] * 3
+    oracle, model = _pair(L, F=[10, 20, 1], K=[5] * 3, p=[1] * 3, batch_norm=[True] * 3, M=[], num_feat_in=5,
+                          regression=True, dense=True)
+    assert not model._graphs[0].is_ell or model._graphs[0].max_degree <= 16
+    rs = np.random.RandomState(9)
+    x = rs.randn(4, 300, 5).astype(np.float32)
+    labels = rs.randn(4, 300).astype(np.float32)
+    _check_step(oracle, model, x, labels, rtol_after=2e-3)
+
+
+def test_cuda_graph_replay_matches_eager():
+    L = [healpix_L(4), healpix_L(2)]
+    kw = dict(F=[8, 4], K=[3, 3], p=[4, 1], batch_norm=[True, True], M=[], statistics='mean')
+    _, eager = _pair(L, **kw)
+    _, graphed = _pair(L, cuda_graph=True, **kw)
+    rs = np.random.RandomState(3)
+    for t in range(4):
+        x = rs.randn(4, 192, 1).astype(np.float32)
+        labels = rs.randint(0, 4, size=4).astype(np.int32)
+        _, l1 = eager.train_step(x, labels)
+        _, l2 = graphed.train_step(x, labels)
+        assert float(l1) == pytest.approx(float(l2), rel=1e-5)
+    assert_close(graphed._P.w, eager._P.w, 1e-5, 'weights after graph replay')
+
+
+def test_fit_predict_evaluate_api(tmp_path):
+    """Reference-style end-to-end use: datasets in, tuples out (models.py:432-618, 343-430)."""
+    from deepsphere_tf1_b200 import models, optimizers
+    from deepsphere_tf1_b200.data import LabeledDataset
+    rs = np.random.RandomState(0)
+    n = 40
+    labels = rs.randint(0, 2, size=n)
+    x = rs.randn(n, 192).astype(np.float32) + labels[:, None] * 1.5          # separable by the mean
+    train, val = LabeledDataset(x[:32], labels[:32]), LabeledDataset(x[32:], labels[32:], shuffle=False)
+    model = models.deepsphere(nsides=[4, 2, 2], F=[8, 2], K=[3, 3], batch_norm=[True, True], M=[], statistics='mean',
+                              num_epochs=12, batch_size=8, eval_frequency=16, seed=1, verbose=False,
+                              scheduler=lambda step: 2e-2, optimizer=lambda lr: optimizers.AdamOptimizer(lr),
+                              dir_name='_test_fit')
+    acc, loss_val, loss_train, t_step, t_batch = model.fit(train, val, restore=False, verbose=False)
+    assert len(acc) == len(loss_val) == len(loss_train) == 3 and t_step > 0 and t_batch > 0
+    assert loss_train[-1] < loss_train[0]
+    pred = model.predict(x[32:].reshape(8, 192, 1), sess=model)
+    assert pred.shape == (8,)
+    pred2, loss = model.predict(x[32:].reshape(8, 192, 1), labels[32:], sess=model)
+    np.testing.assert_array_equal(pred, pred2)
+    string, accuracy, f1, loss2, metrics = model.evaluate(x[32:].reshape(8, 192, 1), labels[32:], sess=model)
+    assert 'accuracy' in string and loss2 == pytest.approx(loss) and accuracy >= 75
+    # a fresh model restores the latest checkpoint when no session is given (models.py:851-860)
+    again = models.deepsphere(nsides=[4, 2, 2], F=[8, 2], K=[3, 3], batch_norm=[True, True], M=[], statistics='mean',
+                              num_epochs=12, batch_size=8, eval_frequency=16, seed=5, verbose=False,
+                              scheduler=lambda step: 2e-2, optimizer=lambda lr: optimizers.AdamOptimizer(lr),
+                              dir_name='_test_fit')
+    np.testing.assert_array_equal(again.predict(x[32:].reshape(8, 192, 1)), pred)
+    assert again.get_var('conv1/weights').shape == (3, 8)
+    import shutil
+    shutil.rmtree(model._get_path('checkpoints'), ignore_errors=True)
+    shutil.rmtree(model._get_path('summaries'), ignore_errors=True)

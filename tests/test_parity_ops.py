@@ -1,0 +1,269 @@
+"""GPU parity: every libdsb200 kernel (called through the C ABI via ctypes) against the CPU
+oracle on the same seeded inputs.  Tolerance (BASELINE.json north_star): fp32, max error
+<= 1e-4 of the largest expected magnitude; index / arg-max results exact."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import assert_close, healpix_L, random_knn_L, random_L
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+@pytest.fixture(scope='module')
+def dev():
+    from deepsphere_tf1_b200 import _lib
+    _lib.LIB.load()
+    return torch.device('cuda', 0)
+
+
+def _graph(L, dev, force_csr=False):
+    from deepsphere_tf1_b200.graph import DeviceGraph
+    return DeviceGraph(L, dev, force_csr=force_csr)
+
+
+def _oracle_basis(L, x, K):
+    """X_k planes [K, B, M, F] with the reference's recurrence (models.py:1049-1061)."""
+    from oracle import ops as oops
+    Lt = oops.sparse_to_torch(L)
+    B, M, F = x.shape
+    x0 = x.permute(1, 2, 0).reshape(M, F * B)
+    planes = [x0]
+    if K > 1:
+        planes.append(torch.sparse.mm(Lt, x0))
+    for k in range(2, K):
+        planes.append(2 * torch.sparse.mm(Lt, planes[-1]) - planes[-2])
+    return torch.stack([p.reshape(M, F, B).permute(2, 0, 1) for p in planes])
+
+
+@pytest.mark.parametrize('F', [1, 2, 3, 4, 6, 16, 33, 64])
+@pytest.mark.parametrize('kind', ['ell', 'csr'])
+def test_cheb_basis_matches_oracle(dev, F, kind):
+    from deepsphere_tf1_b200 import ops
+    L = healpix_L(8) if kind == 'ell' else random_knn_L(500, 7)
+    g = _graph(L, dev, force_csr=(kind == 'csr'))
+    assert g.is_ell == (kind == 'ell')
+    rs = np.random.RandomState(F)
+    x = torch.from_numpy(rs.randn(3, L.shape[0], F).astype(np.float32))
+    K = 5
+    basis = ops.cheb_basis(g, x.to(dev), K)
+    assert_close(basis, _oracle_basis(L, x, K)[1:], RTOL, 'basis')
+
+
+def test_spmm_general_form_and_aliasing(dev):
+    from deepsphere_tf1_b200 import ops
+    from oracle import ops as oops
+    L = random_L(300, 5)
+    g = _graph(L, dev)
+    rs = np.random.RandomState(0)
+    x, y, z = [torch.from_numpy(rs.randn(2, 300, 8).astype(np.float32)) for _ in range(3)]
+    Ld = torch.from_numpy(L.toarray())
+    LT = Ld.t()
+    exp = 0.5 * torch.einsum('ij,bjf->bif', Ld, x) - 1.5 * y + 0.25 * z
+    out = ops.spmm(g, x.to(dev), y.to(dev), z.to(dev), alpha=0.5, beta=-1.5, gamma=0.25)
+    assert_close(out, exp, RTOL, 'spmm')
+    # transposed matrix, result written over y
+    yd = y.to(dev).clone()
+    ops.spmm(g, x.to(dev), yd, None, out=yd, alpha=2.0, beta=1.0, transpose=True)
+    assert_close(yd, 2 * torch.einsum('ij,bjf->bif', LT, x) + y, RTOL, 'spmm^T in place')
+    assert oops is not None
+
+
+@pytest.mark.parametrize('shape', [(2, 192, 1, 16, 5), (2, 192, 16, 32, 5), (3, 100, 6, 16, 4), (1, 77, 3, 5, 3),
+                                   (2, 64, 64, 64, 5), (2, 48, 32, 2, 5), (4, 33, 7, 9, 1), (2, 50, 96, 40, 4)])
+def test_contraction_forward_backward(dev, shape):
+    """Y = Xcat W with the reference's row order fin*K + k (models.py:1062-1078) and both
+    gradients of tf.matmul, plus the batch-norm sums of the epilogue."""
+    from deepsphere_tf1_b200 import ops
+    B, M, Fin, Fout, K = shape
+    rs = np.random.RandomState(Fin * 100 + Fout)
+    planes = torch.from_numpy(rs.randn(K, B, M, Fin).astype(np.float32))
+    W = torch.from_numpy((rs.randn(Fin * K, Fout) / np.sqrt(Fin * K)).astype(np.float32))
+    dy = torch.from_numpy(rs.randn(B, M, Fout).astype(np.float32))
+    xcat = planes.permute(1, 2, 3, 0).reshape(B * M, Fin * K).double()        # N x M x Fin x K (1063-1064)
+    y_ref = (xcat @ W.double()).reshape(B, M, Fout)
+    dW_ref = xcat.t() @ dy.reshape(B * M, Fout).double()
+    dX_ref = (dy.reshape(B * M, Fout).double() @ W.double().t()).reshape(B, M, Fin, K).permute(3, 0, 1, 2)
+
+    x0 = planes[0].contiguous().to(dev)
+    xk = planes[1:].contiguous().to(dev) if K > 1 else None
+    sums = torch.zeros(2 * Fout, dtype=torch.float64, device=dev)
+    y = ops.contract_fwd(x0, xk, W.to(dev), K, Fout, sums)
+    assert_close(y, y_ref, RTOL, 'Y')
+    assert_close(sums[:Fout], y_ref.sum((0, 1)), RTOL, 'sum y')
+    assert_close(sums[Fout:], (y_ref ** 2).sum((0, 1)), RTOL, 'sum y^2')
+    y2 = ops.contract_fwd(x0, xk, W.to(dev), K, Fout, None)
+    assert torch.equal(y, y2)
+    G = ops.contract_bwd_data(dy.to(dev), W.to(dev), K, Fin)
+    assert_close(G, dX_ref, RTOL, 'dX_k')
+    dW = torch.zeros(Fin * K, Fout, device=dev)
+    ops.contract_bwd_weight(x0, xk, dy.to(dev), dW, K)
+    assert_close(dW, dW_ref, RTOL, 'dW')
+
+
+@pytest.mark.parametrize('kind', ['ell', 'csr', 'nonsym'])
+def test_chebconv_gradients_match_oracle_autograd(dev, kind):
+    """Whole filter (recurrence + contraction), forward and both gradients, vs torch-CPU autograd
+    of oracle.ops.chebyshev5."""
+    from deepsphere_tf1_b200 import ops
+    from oracle import ops as oops
+    L = {'ell': lambda: healpix_L(4), 'csr': lambda: random_knn_L(200, 6), 'nonsym': lambda: random_L(150, 4)}[kind]()
+    g = _graph(L, dev, force_csr=(kind == 'csr'))
+    M = L.shape[0]
+    B, Fin, Fout, K = 3, 5, 7, 4
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy(rs.randn(B, M, Fin).astype(np.float32)).requires_grad_(True)
+    W = torch.from_numpy((rs.randn(Fin * K, Fout) * 0.3).astype(np.float32)).requires_grad_(True)
+    dy = torch.from_numpy(rs.randn(B, M, Fout).astype(np.float32))
+    y_ref = oops.chebyshev5(x, oops.sparse_to_torch(L), W, K)
+    y_ref.backward(dy)
+
+    xd, Wd = x.detach().to(dev), W.detach().to(dev)
+    basis = ops.cheb_basis(g, xd, K)
+    y = ops.contract_fwd(xd, basis, Wd, K, Fout)
+    assert_close(y, y_ref, RTOL, 'y')
+    dW = torch.zeros_like(Wd)
+    ops.contract_bwd_weight(xd, basis, dy.to(dev), dW, K)
+    assert_close(dW, W.grad, RTOL, 'dW')
+    G = ops.contract_bwd_data(dy.to(dev), Wd, K, Fin)
+    dx = ops.cheb_basis_bwd(g, G)
+    assert_close(dx, x.grad, RTOL, 'dx')
+
+
+@pytest.mark.parametrize('F', [3, 16, 64])
+@pytest.mark.parametrize('p,pool', [(1, 'max'), (4, 'max'), (4, 'average'), (16, 'max')])
+@pytest.mark.parametrize('act', ['relu', 'elu', 'identity'])
+@pytest.mark.parametrize('bn', [True, False])
+def test_bn_bias_act_pool_chain(dev, F, p, pool, act, bn):
+    """normalise -> bias -> activation -> pool (models.py:1235-1243) forward and backward,
+    including the batch-norm backward through the batch statistics."""
+    from deepsphere_tf1_b200 import ops
+    from oracle import ops as oops
+    B, M = 3, 64
+    rs = np.random.RandomState(F + p)
+    y = torch.from_numpy((rs.randn(B, M, F) * 2 + 0.5).astype(np.float32)).requires_grad_(True)
+    b = torch.from_numpy(rs.randn(F).astype(np.float32) * 0.3).requires_grad_(True)
+    z = y
+    if bn:
+        z, nm, nv = oops.batch_normalization(z, torch.zeros(F), torch.ones(F), True)
+    z = oops.bias(z, b)
+    z = oops.ACTIVATIONS[act](z) if act != 'identity' else z
+    out_ref = oops.pool(z, p, pool, 'healpix')
+    dout = torch.from_numpy(rs.randn(*out_ref.shape).astype(np.float32))
+    out_ref.backward(dout)
+
+    yd, bd = y.detach().to(dev), b.detach().to(dev)
+    mean = rstd = None
+    count = float(B * M)
+    if bn:
+        # statistics exactly as the contraction epilogue + finalize produce them
+        sums = torch.cat([yd.double().sum((0, 1)), (yd.double() ** 2).sum((0, 1))])
+        mean, rstd = torch.empty(F, device=dev), torch.empty(F, device=dev)
+        mm, mv = torch.zeros(F, device=dev), torch.ones(F, device=dev)
+        ops.bn_finalize(sums, count, F, mean, rstd, mm, mv)
+        assert_close(mm, nm, RTOL, 'moving mean')
+        assert_close(mv, nv, RTOL, 'moving variance')
+    out = ops.bn_act_pool_fwd(yd, mean, rstd, bd, p, pool, act)
+    assert_close(out, out_ref, RTOL, 'out')
+    gz, s = ops.bn_act_pool_bwd(yd, mean, rstd, bd, dout.to(dev), p, pool, act)
+    assert_close(s[:F], b.grad, 2 * RTOL, 'dbias')
+    if bn:
+        ops.bn_bwd_apply(yd, mean, rstd, s, count, gz)
+    assert_close(gz, y.grad, 2 * RTOL, 'dy')
+
+
+@pytest.mark.parametrize('kind', ['mean', 'var', 'meanvar', 'max'])
+def test_statistics_head(dev, kind):
+    from deepsphere_tf1_b200 import ops
+    from oracle import ops as oops
+    rs = np.random.RandomState(1)
+    x = torch.from_numpy(rs.randn(4, 100, 6).astype(np.float32)).requires_grad_(True)
+    ref = oops.statistics(x, kind, False)
+    d = torch.from_numpy(rs.randn(*ref.shape).astype(np.float32))
+    ref.backward(d)
+    out = ops.stat_fwd(x.detach().to(dev), kind)
+    assert_close(out, ref, RTOL, 'stat')
+    dx = ops.stat_bwd(x.detach().to(dev), d.to(dev), kind)
+    assert_close(dx, x.grad, RTOL, 'dstat')
+
+
+def test_resize_unpool_concat(dev):
+    from deepsphere_tf1_b200 import ops
+    from deepsphere_tf1_b200._consts import UNPOOL_REPEAT, UNPOOL_ZEROFILL
+    from oracle import ops as oops
+    rs = np.random.RandomState(2)
+    x = torch.from_numpy(rs.randn(2, 12, 5).astype(np.float32))
+    xd = x.to(dev)
+    assert torch.equal(ops.vertex_resize(xd, 42, 1.0).cpu(), oops.unpool(x, 42, 'average', 'icosahedron'))
+    assert torch.equal(ops.vertex_resize(xd, 7, 0.0).cpu(), oops.pool(x, 7, 'average', 'icosahedron'))
+    assert torch.equal(ops.unpool_fwd(xd, 4, UNPOOL_REPEAT).cpu(), oops.unpool(x, 4, 'average', 'healpix'))
+    assert torch.equal(ops.unpool_fwd(xd, 4, UNPOOL_ZEROFILL).cpu(), oops.unpool(x, 4, 'max', 'healpix'))
+    d = torch.from_numpy(rs.randn(2, 48, 5).astype(np.float32))
+    assert_close(ops.unpool_bwd(d.to(dev), 4, UNPOOL_REPEAT), d.reshape(2, 12, 4, 5).sum(2), 1e-6, 'unpool bwd')
+    assert torch.equal(ops.unpool_bwd(d.to(dev), 4, UNPOOL_ZEROFILL).cpu(), d.reshape(2, 12, 4, 5)[:, :, 0])
+    b = torch.from_numpy(rs.randn(2, 12, 3).astype(np.float32))
+    cat = ops.concat_f(xd, b.to(dev))
+    assert torch.equal(cat.cpu(), torch.cat([x, b], -1))
+    da, db = ops.split_f(cat, 5)
+    assert torch.equal(da.cpu(), x) and torch.equal(db.cpu(), b)
+    da, db2 = ops.split_f(cat, 5, db)
+    assert torch.equal(db2.cpu(), 2 * b)
+
+
+def test_fc_losses_regulariser(dev):
+    from deepsphere_tf1_b200 import ops
+    from oracle import ops as oops
+    rs = np.random.RandomState(5)
+    x = torch.from_numpy(rs.randn(8, 20).astype(np.float32)).requires_grad_(True)
+    W = torch.from_numpy(rs.randn(20, 7).astype(np.float32) * 0.2).requires_grad_(True)
+    b = torch.from_numpy(rs.randn(7).astype(np.float32)).requires_grad_(True)
+    labels = torch.from_numpy(rs.randint(0, 7, size=8).astype(np.int32))
+    h = torch.relu(oops.fc(x, W, b))
+    total, data_loss = oops.loss(h, labels, False, [(W, 0.5)], 0.3)
+    total.backward()
+    hd = ops.fc_fwd(x.detach().to(dev), W.detach().to(dev), b.detach().to(dev), 'relu')
+    assert_close(hd, h, RTOL, 'fc')
+    loss = torch.zeros(1, device=dev)
+    dl = ops.softmax_ce(hd, labels.to(dev), loss)
+    assert_close(loss, data_loss.reshape(1), RTOL, 'ce')
+    dW, db = torch.zeros(20, 7, device=dev), torch.zeros(7, device=dev)
+    dx = ops.fc_bwd(x.detach().to(dev), W.detach().to(dev), hd, dl, dW, db, 'relu')
+    coef = torch.full((140,), 0.3 / 0.25 / 140, device=dev)
+    ops.l2_reg(W.detach().to(dev).reshape(-1), coef, dW.reshape(-1), loss)
+    assert_close(loss, total.reshape(1), RTOL, 'total loss')
+    assert_close(dx, x.grad, RTOL, 'dx')
+    assert_close(dW, W.grad, RTOL, 'dW')
+    assert_close(db, b.grad, RTOL, 'db')
+    probs, pred = ops.softmax_argmax(hd, True)
+    assert_close(probs, torch.softmax(h.detach(), -1), RTOL, 'probs')
+    assert torch.equal(pred.cpu().long(), h.detach().argmax(-1))
+    # MSE (tf.losses.mean_squared_error, models.py:788)
+    t = torch.from_numpy(rs.randn(8, 7).astype(np.float32))
+    loss.zero_()
+    dp = ops.mse(hd.reshape(-1), t.to(dev).reshape(-1), loss)
+    assert_close(loss, ((h.detach() - t) ** 2).mean().reshape(1), RTOL, 'mse')
+    assert_close(dp.reshape(8, 7), 2 * (h.detach() - t) / 56, RTOL, 'dmse')
+
+
+@pytest.mark.parametrize('name', ['Adam', 'Momentum', 'SGD', 'RMSProp'])
+def test_optimizers_follow_tf1_update_rules(dev, name):
+    from deepsphere_tf1_b200 import ops, optimizers
+    from oracle import optim_tf1
+    rs = np.random.RandomState(7)
+    w = torch.from_numpy(rs.randn(1000).astype(np.float32))
+    prod = {'Adam': optimizers.AdamOptimizer(1e-2, epsilon=0.1), 'Momentum': optimizers.MomentumOptimizer(1e-2, 0.9),
+            'SGD': optimizers.GradientDescentOptimizer(1e-2), 'RMSProp': optimizers.RMSPropOptimizer(1e-2, momentum=0.5)}[name]
+    orc = {'Adam': optim_tf1.Adam(epsilon=0.1), 'Momentum': optim_tf1.Momentum(0.9), 'SGD': optim_tf1.SGD(),
+           'RMSProp': optim_tf1.RMSProp(momentum=0.5)}[name]
+    wd = w.to(dev).clone()
+    slots = [torch.full_like(wd, prod.slot1_init if i == 0 else 0.0) for i in range(prod.slots)]
+    params = {'w': w.clone()}
+    for t in range(1, 6):
+        g = torch.from_numpy(rs.randn(1000).astype(np.float32))
+        lr = 1e-2 * 0.9 ** t
+        params = orc.step(params, {'w': g}, lr)
+        hyper = torch.tensor(prod.hyper(lr, t), dtype=torch.float32, device=dev)
+        ops.optimizer_step(prod.kind, wd, g.to(dev), slots[0] if slots else None, slots[1] if len(slots) > 1 else None, hyper)
+    assert_close(wd, params['w'], RTOL, name)
