@@ -8,6 +8,8 @@
 // FP32 FFMA register-tiled kernels (exact-precision path); the tcgen05 path lives in
 // contract_tc.cu.
 #include "common.cuh"
+#include "tc_common.cuh"
+#include <atomic>
 
 namespace dsb200 {
 
@@ -333,6 +335,9 @@ contract_bwd_weight_kernel(Planar A, const float* __restrict__ dY, float* __rest
     }
 }
 
+// tensor-core (tcgen05) path on by default; dsb200_set_tensor_cores(0) forces the FP32 FFMA kernels
+static std::atomic<int> g_use_tc{1};
+
 static inline bool small_path(int Q, int Fout) { return Q <= 16 && Fout % 4 == 0 && Fout <= 256 && 256 % (Fout / 4) == 0; }
 
 }  // namespace dsb200
@@ -347,6 +352,10 @@ extern "C" int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const 
     cudaStream_t s = (cudaStream_t)stream;
     Planar A{x0, xk, Fin, R * (long long)Fin};
     const int Q = K * Fin;
+    if (g_use_tc.load(std::memory_order_relaxed) && Q > 16) {
+        const int rc = tc::contract_fwd_tc(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, s);
+        if (rc != 1) return rc;                            // 1 = shape not supported on the tensor-core path
+    }
     if (small_path(Q, Fout) && (((uintptr_t)Y & 15) == 0)) {
         const int rows_per_iter = 256 / (Fout / 4);
         const int grid = grid_for((R + rows_per_iter - 1) / rows_per_iter * 256, 256, 8);
@@ -364,6 +373,10 @@ extern "C" int dsb200_cheb_contract_bwd_data(const float* dY, const float* W, fl
 {
     DSB_REQUIRE(R > 0 && Fin > 0 && K > 0 && Fout > 0, "contract_bwd_data: bad shape");
     DSB_REQUIRE(dY && W && G, "contract_bwd_data: null pointer");
+    if (g_use_tc.load(std::memory_order_relaxed)) {
+        const int rc = tc::contract_bwd_data_tc(dY, W, G, R, Fin, K, Fout, (cudaStream_t)stream);
+        if (rc != 1) return rc;
+    }
     Planar A{dY, nullptr, Fout, 0};
     const int N = K * Fin;
     dim3 grid((unsigned)((R + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
@@ -399,4 +412,9 @@ extern "C" int dsb200_cheb_contract_bwd_weight(const float* x0, const float* xk,
         contract_bwd_weight_kernel<<<grid, 256, 0, s>>>(A, dY, dW, R, Fin, K, Fout, Q, rows_per_split);
     }
     DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_set_tensor_cores(int on)
+{
+    return g_use_tc.exchange(on ? 1 : 0);
 }

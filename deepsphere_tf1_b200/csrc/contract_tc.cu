@@ -1,0 +1,430 @@
+// K2 on the 5th-generation tensor cores: the dense contraction of cgcnn.chebyshev5
+//   Y[r, fo] = sum_{k, fi} X_k[r, fi] * W[fi*K + k, fo]            (reference models.py:1062-1078)
+// and its data gradient  dX_k[r, fi] = sum_fo dY[r, fo] * W[fi*K + k, fo]  (autodiff of 1077),
+// as persistent, warp-specialised tcgen05 kernels:
+//   warp 0      TMA producer: 128-row x kc-column fp32 tiles of the activation planes -> shared memory
+//               (cp.async.bulk.tensor, hardware 32/64/128-byte swizzle, mbarrier completion)
+//   warps 2-5   split every landed tile into TF32 "hi" (in place) and "lo" (second buffer) parts
+//   warp 1      one thread issues tcgen05.mma kind::tf32 into TMEM:  D = A_hi*[W_hi | W_lo] + A_lo*W_hi
+//               (3xTF32 error-compensated product: fp32-level accuracy, fp32 accumulation)
+//   warps 6-9   epilogue: tcgen05.ld the accumulator, add the two halves, batch-norm sums
+//               (tf.nn.moments, models.py:1197-1203), coalesced fp32 stores
+// The weights are tiny: they are split and laid out once per CTA in the canonical K-major swizzled
+// layout and stay resident in shared memory.  TMEM accumulators are double buffered when they fit.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace dsb200 {
+namespace tc {
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int make_tmap_f32(CUtensorMap* out, const float* base, long long cols, long long rows, long long planes,
+                  int box_cols, int box_rows, int swz, bool rank3)
+{
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return -1;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * 4 * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapSwizzle sw = swz == 3 ? CU_TENSOR_MAP_SWIZZLE_128B : swz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swz == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    const cuuint32_t rank = rank3 ? 3 : 2;
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 320;
+constexpr int kMaxStages = 8;
+enum { MODE_FWD = 0, MODE_BWD_DATA = 1 };
+
+struct alignas(64) RowGemmParams {
+    CUtensorMap tmA0;          // plane 0 (x0, or dY for the data gradient)
+    CUtensorMap tmAk;          // planes 1..K-1 (forward only)
+    const float* W;            // [Fin*K, Fout], row = fi*K + k
+    float* out;                // Y [R, Fout]  |  G [K][R][Fin]
+    double* bn_sums;           // forward only, may be NULL
+    long long R;
+    int Fin, K, Fout;
+    int kc, nchunk, nkb;       // reduction: chunk width, chunks per plane, k-blocks per tile
+    int Npad, Nreal, n0;       // accumulator width (multiple of 16), valid columns, first column of this n-block
+    int swz;                   // 1 / 2 / 3 = 32 / 64 / 128-byte swizzle (row of a tile = kc*4 bytes)
+    int nstages, acc_stages;
+    int ntiles;
+};
+
+template <int MODE, int SUMS_N>
+__global__ void __launch_bounds__(kThreads, 1)
+rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rowbytes = p.kc * 4;
+    const uint32_t tile_bytes = (uint32_t)kTileM * rowbytes;
+    const uint32_t wblk_bytes = 2u * p.Npad * rowbytes;
+    const int S = p.nstages;
+
+    uint8_t* sW = smem;
+    uint8_t* sA = sW + (size_t)p.nkb * wblk_bytes;                 // stage s: A at 2*s, A_lo at 2*s+1
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)S * 2 * tile_bytes);
+    uint64_t* full_tma = bars;
+    uint64_t* full_mma = bars + kMaxStages;
+    uint64_t* empty = bars + 2 * kMaxStages;
+    uint64_t* acc_full = bars + 3 * kMaxStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);           // [2][64] batch-norm partial sums
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full_tma + s, 1); mbar_init(full_mma + s, 128); mbar_init(empty + s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 128); }
+        fence_barrier_init();
+        prefetch_tmap(&p.tmA0);
+        if (MODE == MODE_FWD && p.K > 1) prefetch_tmap(&p.tmAk);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (SUMS_N > 0) for (int i = threadIdx.x; i < 2 * 64; i += kThreads) red[i] = 0.f;
+
+    // ---- weights: TF32 hi / lo split, canonical K-major swizzled layout, rows [0,Npad) = hi, [Npad,2Npad) = lo
+    {
+        const int per_blk = 2 * p.Npad * p.kc;
+        const int total = p.nkb * per_blk;
+        for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+            const int j = idx / per_blk;
+            const int rem = idx - j * per_blk;
+            const int n2 = rem / p.kc, kk = rem - n2 * p.kc;
+            const int half = n2 >= p.Npad;
+            const int n = n2 - half * p.Npad;
+            float w = 0.f;
+            if (n < p.Nreal) {
+                if (MODE == MODE_FWD) {
+                    const int k = j / p.nchunk, c = j - k * p.nchunk;
+                    w = __ldg(p.W + ((long long)(c * p.kc + kk) * p.K + k) * p.Fout + (p.n0 + n));
+                } else {
+                    const int q = p.n0 + n;
+                    const int kq = q / p.Fin, fi = q - kq * p.Fin;
+                    w = __ldg(p.W + ((long long)fi * p.K + kq) * p.Fout + (j * p.kc + kk));
+                }
+            }
+            const float hi = to_tf32(w);
+            const float v = half ? to_tf32(w - hi) : hi;
+            const int chunk = (kk >> 2) ^ swizzle_xor(n2, p.swz);
+            *reinterpret_cast<float*>(sW + (size_t)j * wblk_bytes + (size_t)n2 * rowbytes + chunk * 16 + (kk & 3) * 4) = v;
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int acc_cols = 2 * p.Npad;
+
+    if (warp == 0) {
+        // ======================= TMA producer =======================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+                const int row0 = t * kTileM;
+                int k = 0, c = 0;                                   // plane, chunk within the plane
+                for (int j = 0; j < p.nkb; ++j) {
+                    mbar_wait(empty + s, ph ^ 1u, 1);
+                    mbar_expect_tx(full_tma + s, tile_bytes);
+                    uint8_t* dst = sA + (size_t)(2 * s) * tile_bytes;
+                    if (MODE == MODE_FWD) {
+                        if (k == 0) tma_load_2d(dst, &p.tmA0, full_tma + s, c * p.kc, row0);
+                        else tma_load_3d(dst, &p.tmAk, full_tma + s, c * p.kc, row0, k - 1);
+                        if (++c == p.nchunk) { c = 0; ++k; }
+                    } else {
+                        tma_load_2d(dst, &p.tmA0, full_tma + s, j * p.kc, row0);
+                    }
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================= MMA issuer =======================
+        if (lane == 0) {
+            const bool merged = acc_cols <= 256;
+            const uint32_t idesc_wide = make_idesc_tf32(kTileM, merged ? acc_cols : p.Npad, 0, 0);
+            const uint32_t idesc_half = make_idesc_tf32(kTileM, p.Npad, 0, 0);
+            const uint32_t sbo = 8u * rowbytes;
+            const int ksteps = p.kc / 8;
+            // descriptors differ only in the 14-bit start-address field (bytes >> 4): build them once
+            const uint64_t dA0 = make_smem_desc(smem_u32(sA), 16, sbo, p.swz);
+            const uint64_t dB0 = make_smem_desc(smem_u32(sW), 16, sbo, p.swz);
+            const uint32_t a_stage = (2u * tile_bytes) >> 4, a_lo = tile_bytes >> 4;
+            const uint32_t b_blk = wblk_bytes >> 4, b_lo = ((uint32_t)p.Npad * rowbytes) >> 4;
+            int s = 0, ti = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
+                const int a = p.acc_stages == 2 ? (ti & 1) : 0;
+                const uint32_t use = (uint32_t)(p.acc_stages == 2 ? (ti >> 1) : ti);
+                mbar_wait(acc_empty + a, (use & 1) ^ 1u, 2);
+                tc_fence_after();
+                const uint32_t d_hi = tmem_base + (uint32_t)(a * acc_cols);
+                const uint32_t d_lo = d_hi + (uint32_t)p.Npad;
+                uint64_t dB = dB0;
+                for (int j = 0; j < p.nkb; ++j, dB += b_blk) {
+                    mbar_wait(full_mma + s, ph, 3);
+                    tc_fence_after();
+                    const uint64_t dA = dA0 + (uint64_t)(a_stage * (uint32_t)s);
+#pragma unroll 4
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+                        const uint64_t dAH = dA + 2u * ks, dBH = dB + 2u * ks;  // +32 bytes per k-step of 8
+                        if (merged) {
+                            mma_tf32(d_hi, dAH, dBH, idesc_wide, acc);          // A_hi * [W_hi | W_lo]
+                        } else {
+                            mma_tf32(d_hi, dAH, dBH, idesc_half, acc);
+                            mma_tf32(d_lo, dAH, dBH + b_lo, idesc_half, acc);
+                        }
+                        mma_tf32(d_hi, dAH + a_lo, dBH, idesc_half, 1u);        // A_lo * W_hi
+                    }
+                    tc_commit(empty + s);                                       // stage free once the MMAs have read it
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                }
+                tc_commit(acc_full + a);
+            }
+        }
+    } else if (warp < 6) {
+        // ======================= TF32 hi / lo split of the landed tiles =======================
+        const int tt = threadIdx.x - 64;
+        const int nvec = (int)(tile_bytes / 16);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            for (int j = 0; j < p.nkb; ++j) {
+                mbar_wait(full_tma + s, ph, 4);
+                float4* A = reinterpret_cast<float4*>(sA + (size_t)(2 * s) * tile_bytes);
+                float4* Al = reinterpret_cast<float4*>(sA + (size_t)(2 * s + 1) * tile_bytes);
+#pragma unroll 4
+                for (int i = tt; i < nvec; i += 128) {
+                    const float4 v = A[i];
+                    float4 h, l;
+                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+                    A[i] = h;
+                    Al[i] = l;
+                }
+                fence_proxy_async();
+                mbar_arrive(full_mma + s);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        // ======================= epilogue =======================
+        const int q = warp & 3;                                     // TMEM lane quarter of this warp
+        constexpr int NS = SUMS_N > 0 ? SUMS_N : 1;
+        float s1[NS], s2[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        int ti = 0;
+        for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
+            const int a = p.acc_stages == 2 ? (ti & 1) : 0;
+            const uint32_t use = (uint32_t)(p.acc_stages == 2 ? (ti >> 1) : ti);
+            mbar_wait(acc_full + a, use & 1, 5);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + (uint32_t)(a * acc_cols) + ((uint32_t)(q * 32) << 16);
+            const long long row = (long long)t * kTileM + q * 32 + lane;
+            const bool ok = row < p.R;
+            if (MODE == MODE_FWD) {
+                float* orow = p.out + row * p.Fout;
+                if (SUMS_N > 0) {
+#pragma unroll
+                    for (int c0 = 0; c0 < NS; c0 += 16) {
+                        float hi[16], lo[16];
+                        tmem_ld16(tbase + c0, hi);
+                        tmem_ld16(tbase + p.Npad + c0, lo);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            hi[i] += lo[i];
+                            s1[c0 + i] += hi[i];
+                            s2[c0 + i] = fmaf(hi[i], hi[i], s2[c0 + i]);
+                        }
+                        if (ok) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                if (c0 + i + 3 < p.Fout) st4(orow + c0 + i, make_float4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]));
+                                else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) if (c0 + i + e < p.Fout) orow[c0 + i + e] = hi[i + e];
+                                }
+                        }
+                    }
+                } else {
+                    for (int c0 = 0; c0 < p.Nreal; c0 += 16) {
+                        float hi[16], lo[16];
+                        tmem_ld16(tbase + c0, hi);
+                        tmem_ld16(tbase + p.Npad + c0, lo);
+                        tmem_ld_wait();
+                        if (ok) {
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const int c = p.n0 + c0 + i;
+                                if (c + 3 < p.Fout && (p.Fout & 3) == 0)
+                                    st4(orow + c, make_float4(hi[i] + lo[i], hi[i + 1] + lo[i + 1], hi[i + 2] + lo[i + 2], hi[i + 3] + lo[i + 3]));
+                                else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) if (c + e < p.Fout && c0 + i + e < p.Nreal) orow[c + e] = hi[i + e] + lo[i + e];
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                const long long plane = p.R * (long long)p.Fin;
+                for (int c0 = 0; c0 < p.Nreal; c0 += 8) {
+                    float hi[8], lo[8];
+                    tmem_ld8(tbase + c0, hi);
+                    tmem_ld8(tbase + p.Npad + c0, lo);
+                    tmem_ld_wait();
+                    if (ok) {
+                        const int qq = p.n0 + c0;
+                        const int kq = qq / p.Fin, fi = qq - kq * p.Fin;
+                        float* o = p.out + kq * plane + row * p.Fin + fi;
+                        st4(o, make_float4(hi[0] + lo[0], hi[1] + lo[1], hi[2] + lo[2], hi[3] + lo[3]));
+                        st4(o + 4, make_float4(hi[4] + lo[4], hi[5] + lo[5], hi[6] + lo[6], hi[7] + lo[7]));
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty + a);
+        }
+        if (SUMS_N > 0) {
+            // per-thread partial sums over this CTA's rows -> warp -> CTA -> one double atomic per feature
+#pragma unroll
+            for (int c = 0; c < NS; ++c) {
+                float a1 = s1[c], a2 = s2[c];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+                if (lane == 0) { atomicAdd(red + c, a1); atomicAdd(red + 64 + c, a2); }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int e = threadIdx.x - 192;
+            if (e < p.Fout) {
+                atomicAdd(p.bn_sums + e, (double)red[e]);
+                atomicAdd(p.bn_sums + p.Fout + e, (double)red[64 + e]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+struct RowGemmPlan {
+    int kc, swz, nchunk, nkb, Npad, nstages, acc_stages;
+    size_t smem;
+};
+
+// Shared-memory plan; returns false if the shape does not fit the tensor-core path.
+static bool plan_rowgemm(int red_per_plane, int planes, int Npad, RowGemmPlan* pl)
+{
+    if (red_per_plane % 8) return false;
+    pl->kc = red_per_plane % 32 == 0 ? 32 : red_per_plane % 16 == 0 ? 16 : 8;
+    pl->swz = pl->kc == 32 ? 3 : pl->kc == 16 ? 2 : 1;
+    pl->nchunk = red_per_plane / pl->kc;
+    pl->nkb = planes * pl->nchunk;
+    pl->Npad = Npad;
+    const size_t wbytes = (size_t)pl->nkb * 2 * Npad * pl->kc * 4;
+    const size_t stage = 2 * (size_t)kTileM * pl->kc * 4;
+    const size_t fixed = 1024 /*align*/ + 3 * kMaxStages * 8 + 4 * 8 + 16 + 2 * 64 * 4 + 64;
+    const size_t budget = 227 * 1024;
+    if (wbytes + fixed + 2 * stage > budget) return false;
+    size_t ns = (budget - wbytes - fixed) / stage;
+    if (ns > kMaxStages) ns = kMaxStages;
+    pl->nstages = (int)ns;
+    pl->acc_stages = (4 * Npad <= 512) ? 2 : 1;
+    pl->smem = wbytes + fixed + ns * stage;
+    if (pl->smem < 120 * 1024) pl->smem = 120 * 1024;      // one CTA per SM: every CTA allocates all 512 TMEM columns
+    return true;
+}
+
+template <int MODE, int SUMS_N>
+static int launch_rowgemm(const RowGemmParams& p, size_t smem, cudaStream_t s)
+{
+    static bool configured = false;                // per template instance
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(rowgemm_tc_kernel<MODE, SUMS_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
+    rowgemm_tc_kernel<MODE, SUMS_N><<<grid, kThreads, smem, s>>>(p);
+    DSB_LAUNCH_CHECK();
+}
+
+// Forward contraction on the tensor cores.  Returns 1 if the shape is not supported (caller falls back).
+int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
+                    double* bn_sums, cudaStream_t s)
+{
+    if (R < kTileM || R > 0x7fffff00LL || Fout > 256 || (Fout & 3)) return 1;
+    if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y) & 15) != 0) return 1;
+    const int Npad = (Fout + 15) / 16 * 16;
+    if (bn_sums && Npad > 64) return 1;
+    RowGemmPlan pl;
+    if (!plan_rowgemm(Fin, K, Npad, &pl)) return 1;
+    RowGemmParams p;
+    if (make_tmap_f32(&p.tmA0, x0, Fin, R, 1, pl.kc, kTileM, pl.swz, false)) return 1;
+    if (K > 1) { if (make_tmap_f32(&p.tmAk, xk, Fin, R, K - 1, pl.kc, kTileM, pl.swz, true)) return 1; }
+    else p.tmAk = p.tmA0;
+    p.W = W; p.out = Y; p.bn_sums = bn_sums; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
+    p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.Npad = Npad; p.Nreal = Fout; p.n0 = 0; p.swz = pl.swz;
+    p.nstages = pl.nstages; p.acc_stages = pl.acc_stages;
+    p.ntiles = (int)((R + kTileM - 1) / kTileM);
+    if (!bn_sums) return launch_rowgemm<MODE_FWD, 0>(p, pl.smem, s);
+    if (Npad == 16) return launch_rowgemm<MODE_FWD, 16>(p, pl.smem, s);
+    if (Npad == 32) return launch_rowgemm<MODE_FWD, 32>(p, pl.smem, s);
+    if (Npad == 48) return launch_rowgemm<MODE_FWD, 48>(p, pl.smem, s);
+    return launch_rowgemm<MODE_FWD, 64>(p, pl.smem, s);
+}
+
+// Data gradient on the tensor cores: G[k][r][fi] = sum_fo dY[r, fo] W[fi*K + k, fo].
+int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R, int Fin, int K, int Fout, cudaStream_t s)
+{
+    if (R < kTileM || R > 0x7fffff00LL || (Fin & 7) || (Fout & 7)) return 1;
+    if ((((uintptr_t)dY | (uintptr_t)G) & 15) != 0) return 1;
+    const int Q = K * Fin;
+    // n-blocks of at most 160 output columns (hi + lo accumulators = 320 TMEM columns)
+    const int nb = (Q + 159) / 160;
+    const int NB = ((Q + nb - 1) / nb + 15) / 16 * 16;
+    RowGemmPlan pl;
+    if (!plan_rowgemm(Fout, 1, NB, &pl)) return 1;
+    for (int b = 0; b < nb; ++b) {
+        RowGemmParams p;
+        if (make_tmap_f32(&p.tmA0, dY, Fout, R, 1, pl.kc, kTileM, pl.swz, false)) return 1;
+        p.tmAk = p.tmA0;
+        p.W = W; p.out = G; p.bn_sums = nullptr; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
+        p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.Npad = NB; p.n0 = b * NB;
+        p.Nreal = (Q - p.n0 < NB) ? (Q - p.n0) : NB;
+        p.swz = pl.swz; p.nstages = pl.nstages; p.acc_stages = pl.acc_stages;
+        p.ntiles = (int)((R + kTileM - 1) / kTileM);
+        int rc = launch_rowgemm<MODE_BWD_DATA, 0>(p, pl.smem, s);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace dsb200

@@ -1,0 +1,347 @@
+// ChebConv layers with a tiny reduction depth Q = K*Fin <= 8 (the first layer of the cosmo and
+// similar nets: Fin = 1, K = 5, Fout = 16 on 262,144 vertices x 16 samples).  There the filter output
+// y [B, M, Fout] is Fout/Q times larger than the Chebyshev basis it is computed from, so it is never
+// written to memory: every consumer recomputes  y[r, :] = sum_q X_q[r] W[q, :]  (Q FMAs per output)
+// from the basis.
+//   * batch-norm statistics (tf.nn.moments, models.py:1197-1203) come from the Q x Q Gram matrix of the
+//     basis:  sum_r y_f = sum_q W_qf s_q,   sum_r y_f^2 = sum_qq' W_qf W_q'f G_qq'
+//   * forward:  basis -> y -> normalise -> bias -> activation -> pool in one pass (models.py:1229-1243)
+//   * backward: basis + dout -> gz (recomputed), S1 = sum gz, S2 = sum gz*xhat, A = X^T gz in one pass;
+//     the batch-norm backward and the weight gradient X^T dy then follow in closed form from A, S1, S2
+//     and the Gram matrix (no dy, no gz, no y in memory).
+// Index conventions: q = k*Fin + fi inside this file; the weight row in W is fi*K + k (models.py:1062-1066).
+#include "common.cuh"
+#include <float.h>
+
+namespace dsb200 {
+
+constexpr int QMAX = 8;
+
+struct Planes {
+    const float* p0;
+    const float* pk;
+    long long plane_stride;      // R * Fin
+    int Fin, K;
+    __device__ __forceinline__ float at(int q, long long r) const {
+        const int k = q / Fin, fi = q - k * Fin;
+        const float* base = k == 0 ? p0 : pk + (long long)(k - 1) * plane_stride;
+        return __ldg(base + r * Fin + fi);
+    }
+};
+
+// gram[0..Q) = sum_r X_q[r];  gram[Q + q*Q + q'] = sum_r X_q[r] X_q'[r]   (double, caller zeroes)
+template <int Q>
+__global__ void __launch_bounds__(256)
+gram_kernel(Planes P, long long R, double* __restrict__ gram)
+{
+    __shared__ float red[Q + Q * Q];
+    for (int i = threadIdx.x; i < Q + Q * Q; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    float s[Q], g[Q * (Q + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < Q; ++i) s[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < Q * (Q + 1) / 2; ++i) g[i] = 0.f;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
+        float x[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) x[q] = P.at(q, r);
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < Q; ++a) {
+            s[a] += x[a];
+#pragma unroll
+            for (int b = a; b < Q; ++b) { g[t] = fmaf(x[a], x[b], g[t]); ++t; }
+        }
+    }
+    // warp reduce, then shared, then one double atomic per entry and block
+    int t = 0;
+#pragma unroll
+    for (int a = 0; a < Q; ++a) {
+        float v = s[a];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&red[a], v);
+#pragma unroll
+        for (int b = a; b < Q; ++b) {
+            float w = g[t++];
+            for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+            if ((threadIdx.x & 31) == 0) { atomicAdd(&red[Q + a * Q + b], w); if (b != a) atomicAdd(&red[Q + b * Q + a], w); }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < Q + Q * Q; i += blockDim.x) atomicAdd(gram + i, (double)red[i]);
+}
+
+// sums[f] = sum_q W_qf s_q ; sums[F + f] = sum_qq' W_qf W_q'f G_qq'
+__global__ void bn_sums_from_gram_kernel(const double* __restrict__ gram, const float* __restrict__ W,
+                                         int Fin, int K, int Fout, double* __restrict__ sums)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= Fout) return;
+    const int Q = Fin * K;
+    double w[QMAX];
+    for (int q = 0; q < Q; ++q) { const int k = q / Fin, fi = q - k * Fin; w[q] = (double)W[(fi * K + k) * Fout + f]; }
+    double s1 = 0.0, s2 = 0.0;
+    for (int a = 0; a < Q; ++a) {
+        s1 += w[a] * gram[a];
+        for (int b = 0; b < Q; ++b) s2 += w[a] * w[b] * gram[Q + a * Q + b];
+    }
+    sums[f] = s1;
+    sums[Fout + f] = s2;
+}
+
+// One thread = one pooled row x 4 output features.
+template <int Q>
+__global__ void __launch_bounds__(256)
+smallconv_fwd_kernel(Planes P, const float* __restrict__ W, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ bias, float* __restrict__ out, long long Rout, int Fout, int p, int pool, int act)
+{
+    extern __shared__ float sm[];                    // Ws[Q][Fout], mu[Fout], rs[Fout], bs[Fout]
+    float* Ws = sm;
+    float* mu = sm + Q * Fout;
+    float* rs = mu + Fout;
+    float* bs = rs + Fout;
+    for (int i = threadIdx.x; i < Q * Fout; i += blockDim.x) {
+        const int q = i / Fout, f = i - q * Fout;
+        const int k = q / P.Fin, fi = q - k * P.Fin;
+        Ws[i] = __ldg(W + (fi * P.K + k) * Fout + f);
+    }
+    for (int f = threadIdx.x; f < Fout; f += blockDim.x) {
+        mu[f] = mean ? __ldg(mean + f) : 0.f;
+        rs[f] = rstd ? __ldg(rstd + f) : 1.f;
+        bs[f] = bias ? __ldg(bias + f) : 0.f;
+    }
+    __syncthreads();
+    const int Fv = Fout / 4;
+    const long long total = Rout * Fv;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const long long ro = g / Fv;
+        const int f0 = (int)(g - ro * Fv) * 4;
+        float acc[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[v] = (pool == DSB200_POOL_MAX) ? -FLT_MAX : 0.f;
+        for (int j = 0; j < p; ++j) {
+            const long long r = ro * p + j;
+            float y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float x = P.at(q, r);
+                const float4 w = *reinterpret_cast<const float4*>(Ws + q * Fout + f0);
+                y[0] = fmaf(x, w.x, y[0]); y[1] = fmaf(x, w.y, y[1]); y[2] = fmaf(x, w.z, y[2]); y[3] = fmaf(x, w.w, y[3]);
+            }
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float a = act_fwd((y[v] - mu[f0 + v]) * rs[f0 + v] + bs[f0 + v], act);
+                acc[v] = (pool == DSB200_POOL_MAX) ? fmaxf(acc[v], a) : acc[v] + a;
+            }
+        }
+        if (pool != DSB200_POOL_MAX) {
+            const float inv = 1.f / (float)p;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[v] *= inv;
+        }
+        st4(out + ro * Fout + f0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    }
+}
+
+// acc (double, zeroed): [0, Q*Fout) A[q][f] = sum_r X_q[r] gz[r,f];  then S1[f] = sum gz, S2[f] = sum gz*xhat
+template <int Q>
+__global__ void __launch_bounds__(256)
+smallconv_bwd_kernel(Planes P, const float* __restrict__ W, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ bias, const float* __restrict__ dout, double* __restrict__ accg,
+                     long long Rout, int Fout, int p, int pool, int act)
+{
+    extern __shared__ float sm[];                    // Ws[Q][Fout], mu, rs, bs, red[(Q+2)*Fout]
+    float* Ws = sm;
+    float* mu = sm + Q * Fout;
+    float* rs = mu + Fout;
+    float* bs = rs + Fout;
+    float* red = bs + Fout;
+    for (int i = threadIdx.x; i < Q * Fout; i += blockDim.x) {
+        const int q = i / Fout, f = i - q * Fout;
+        const int k = q / P.Fin, fi = q - k * P.Fin;
+        Ws[i] = __ldg(W + (fi * P.K + k) * Fout + f);
+    }
+    for (int f = threadIdx.x; f < Fout; f += blockDim.x) {
+        mu[f] = mean ? __ldg(mean + f) : 0.f;
+        rs[f] = rstd ? __ldg(rstd + f) : 1.f;
+        bs[f] = bias ? __ldg(bias + f) : 0.f;
+    }
+    for (int i = threadIdx.x; i < (Q + 2) * Fout; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int Fv = Fout / 4;
+    // threads of a block keep their feature group over the grid-stride loop: blockDim.x % Fv == 0
+    const int rows_per_block = blockDim.x / Fv;
+    const int f0 = (threadIdx.x % Fv) * 4, rl = threadIdx.x / Fv;
+    float A[Q][4], s1[4], s2[4];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) { A[q][0] = A[q][1] = A[q][2] = A[q][3] = 0.f; }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { s1[v] = 0.f; s2[v] = 0.f; }
+    for (long long ro = (long long)blockIdx.x * rows_per_block + rl; ro < Rout; ro += (long long)gridDim.x * rows_per_block) {
+        const float4 d4 = ldg4(dout + ro * Fout + f0);
+        const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+        float best[4], gsel[4], xhsel[4];
+        int arg[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { best[v] = -FLT_MAX; arg[v] = 0; gsel[v] = 0.f; xhsel[v] = 0.f; }
+        const float inv = 1.f / (float)p;
+        for (int j = 0; j < p; ++j) {
+            const long long r = ro * p + j;
+            float x[Q], y[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                x[q] = P.at(q, r);
+                const float4 w = *reinterpret_cast<const float4*>(Ws + q * Fout + f0);
+                y[0] = fmaf(x[q], w.x, y[0]); y[1] = fmaf(x[q], w.y, y[1]); y[2] = fmaf(x[q], w.z, y[2]); y[3] = fmaf(x[q], w.w, y[3]);
+            }
+            if (pool == DSB200_POOL_MAX && p > 1) {
+                // remember the first arg-max sibling; its contribution is added after the loop
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float xh = (y[v] - mu[f0 + v]) * rs[f0 + v];
+                    const float a = act_fwd(xh + bs[f0 + v], act);
+                    if (a > best[v]) { best[v] = a; arg[v] = j; xhsel[v] = xh; gsel[v] = d[v] * act_grad(xh + bs[f0 + v], act); }
+                }
+            } else {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const float xh = (y[v] - mu[f0 + v]) * rs[f0 + v];
+                    const float g = d[v] * inv * act_grad(xh + bs[f0 + v], act);
+                    s1[v] += g; s2[v] = fmaf(g, xh, s2[v]);
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) A[q][v] = fmaf(x[q], g, A[q][v]);
+                }
+            }
+        }
+        if (pool == DSB200_POOL_MAX && p > 1) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) { s1[v] += gsel[v]; s2[v] = fmaf(gsel[v], xhsel[v], s2[v]); }
+            // X of the arg-max sibling of every feature (re-read: L1 hit)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) A[q][v] = fmaf(P.at(q, ro * p + arg[v]), gsel[v], A[q][v]);
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) atomicAdd(&red[q * Fout + f0 + v], A[q][v]);
+        atomicAdd(&red[Q * Fout + f0 + v], s1[v]);
+        atomicAdd(&red[(Q + 1) * Fout + f0 + v], s2[v]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (Q + 2) * Fout; i += blockDim.x) atomicAdd(accg + i, (double)red[i]);
+}
+
+// dW[fi*K+k, f] += rstd_f (A_qf - S1_f/n s_q - S2_f/n rstd_f (sum_q' G_qq' W_q'f - mean_f s_q));  dbias_f = S1_f
+__global__ void smallconv_bwd_finalize_kernel(const double* __restrict__ acc, const double* __restrict__ gram,
+                                              const float* __restrict__ W, const float* __restrict__ mean,
+                                              const float* __restrict__ rstd, double count, int Fin, int K, int Fout,
+                                              float* dW, float* dbias)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int Q = Fin * K;
+    if (i >= Q * Fout) return;
+    const int q = i / Fout, f = i - q * Fout;
+    const int k = q / Fin, fi = q - k * Fin;
+    const double S1 = acc[Q * Fout + f], S2 = acc[(Q + 1) * Fout + f];
+    double g = acc[i];
+    if (mean) {
+        const double rs = (double)rstd[f], mu = (double)mean[f];
+        double xy = 0.0;
+        for (int b = 0; b < Q; ++b) {
+            const int kb = b / Fin, fb = b - kb * Fin;
+            xy += gram[Q + q * Q + b] * (double)W[(fb * K + kb) * Fout + f];
+        }
+        g = rs * (g - S1 / count * gram[q] - S2 / count * rs * (xy - mu * gram[q]));
+    }
+    dW[(fi * K + k) * Fout + f] += (float)g;
+    if (q == 0 && dbias) dbias[f] = (float)S1;
+}
+
+static inline bool smallconv_ok(int Fin, int K, int Fout) { return Fin * K >= 1 && Fin * K <= QMAX && Fout % 4 == 0 && Fout <= 256 && 256 % (Fout / 4) == 0; }
+
+}  // namespace dsb200
+
+using namespace dsb200;
+#define STREAM ((cudaStream_t)stream)
+
+template <int Q> static void launch_gram(Planes P, long long R, double* gram, int grid, cudaStream_t st)
+{ gram_kernel<Q><<<grid, 256, 0, st>>>(P, R, gram); }
+template <int Q> static void launch_fwd(Planes P, const float* W, const float* mean, const float* rstd, const float* bias,
+                                        float* out, long long Rout, int Fout, int p, int pool, int act, int grid, size_t smem, cudaStream_t st)
+{ smallconv_fwd_kernel<Q><<<grid, 256, smem, st>>>(P, W, mean, rstd, bias, out, Rout, Fout, p, pool, act); }
+template <int Q> static void launch_bwd(Planes P, const float* W, const float* mean, const float* rstd, const float* bias,
+                                        const float* dout, double* acc, long long Rout, int Fout, int p, int pool, int act,
+                                        int grid, size_t smem, cudaStream_t st)
+{ smallconv_bwd_kernel<Q><<<grid, 256, smem, st>>>(P, W, mean, rstd, bias, dout, acc, Rout, Fout, p, pool, act); }
+
+#define DISPATCH_Q(Q, FN, ...) \
+    switch (Q) { case 1: FN<1>(__VA_ARGS__); break; case 2: FN<2>(__VA_ARGS__); break; case 3: FN<3>(__VA_ARGS__); break; \
+                 case 4: FN<4>(__VA_ARGS__); break; case 5: FN<5>(__VA_ARGS__); break; case 6: FN<6>(__VA_ARGS__); break; \
+                 case 7: FN<7>(__VA_ARGS__); break; default: FN<8>(__VA_ARGS__); break; }
+
+extern "C" int dsb200_smallconv_supported(int Fin, int K, int Fout) { return smallconv_ok(Fin, K, Fout) ? 1 : 0; }
+
+extern "C" int dsb200_cheb_gram(const float* x0, const float* xk, long long R, int Fin, int K, double* gram, void* stream)
+{
+    DSB_REQUIRE(x0 && gram && R > 0 && (K == 1 || xk), "cheb_gram: bad arguments");
+    DSB_REQUIRE(Fin * K <= QMAX, "cheb_gram: K*Fin too large");
+    Planes P{x0, xk, R * (long long)Fin, Fin, K};
+    const int grid = grid_for(R, 256, 4);
+    DISPATCH_Q(Fin * K, launch_gram, P, R, gram, grid, STREAM);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_bn_sums_from_gram(const double* gram, const float* W, int Fin, int K, int Fout, double* sums, void* stream)
+{
+    DSB_REQUIRE(gram && W && sums && Fin * K <= QMAX && Fout > 0, "bn_sums_from_gram: bad arguments");
+    bn_sums_from_gram_kernel<<<(Fout + 63) / 64, 64, 0, STREAM>>>(gram, W, Fin, K, Fout, sums);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_smallconv_fwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
+                                    const float* bias, float* out, int B, int M, int Fin, int K, int Fout, int p, int pool,
+                                    int act, void* stream)
+{
+    DSB_REQUIRE(x0 && W && out && (K == 1 || xk) && B > 0 && M > 0 && p >= 1 && M % p == 0, "smallconv_fwd: bad arguments");
+    DSB_REQUIRE(smallconv_ok(Fin, K, Fout), "smallconv_fwd: unsupported shape");
+    DSB_REQUIRE((mean == nullptr) == (rstd == nullptr), "smallconv_fwd: mean and rstd go together");
+    const long long R = (long long)B * M, Rout = R / p;
+    Planes P{x0, xk, R * (long long)Fin, Fin, K};
+    const int Q = Fin * K;
+    const size_t smem = (size_t)(Q + 3) * Fout * sizeof(float);
+    const int grid = grid_for(Rout * (Fout / 4), 256, 8);
+    DISPATCH_Q(Q, launch_fwd, P, W, mean, rstd, bias, out, Rout, Fout, p, pool, act, grid, smem, STREAM);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_smallconv_bwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
+                                    const float* bias, const float* dout, double* acc, int B, int M, int Fin, int K, int Fout,
+                                    int p, int pool, int act, void* stream)
+{
+    DSB_REQUIRE(x0 && W && dout && acc && (K == 1 || xk) && B > 0 && M > 0 && p >= 1 && M % p == 0, "smallconv_bwd: bad arguments");
+    DSB_REQUIRE(smallconv_ok(Fin, K, Fout), "smallconv_bwd: unsupported shape");
+    const long long R = (long long)B * M, Rout = R / p;
+    Planes P{x0, xk, R * (long long)Fin, Fin, K};
+    const int Q = Fin * K;
+    const size_t smem = (size_t)(2 * Q + 5) * Fout * sizeof(float);
+    const int rpb = 256 / (Fout / 4);
+    const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 4);
+    DISPATCH_Q(Q, launch_bwd, P, W, mean, rstd, bias, dout, acc, Rout, Fout, p, pool, act, grid, smem, STREAM);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_smallconv_bwd_finalize(const double* acc, const double* gram, const float* W, const float* mean,
+                                             const float* rstd, double count, int Fin, int K, int Fout, float* dW,
+                                             float* dbias, void* stream)
+{
+    DSB_REQUIRE(acc && W && dW && Fin * K <= QMAX && Fout > 0, "smallconv_bwd_finalize: bad arguments");
+    DSB_REQUIRE(!mean || (rstd && gram && count > 0), "smallconv_bwd_finalize: batch norm needs rstd, gram and count");
+    const int n = Fin * K * Fout;
+    smallconv_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, STREAM>>>(acc, gram, W, mean, rstd, count, Fin, K, Fout, dW, dbias);
+    DSB_LAUNCH_CHECK();
+}

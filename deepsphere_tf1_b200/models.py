@@ -81,8 +81,9 @@ class _ParamStore(object):
         self.views = {}
         self.gviews = {}
         for name, shape, off, n, std, init in self.specs:
-            self.views[name] = self.w[off:off + n]
-            self.gviews[name] = self.g[off:off + n]
+            shape2 = shape if len(shape) == 2 else (n,)     # matrices keep their shape, biases are flat
+            self.views[name] = self.w[off:off + n].view(shape2)
+            self.gviews[name] = self.g[off:off + n].view(shape2)
         self.shapes = {s[0]: s[1] for s in self.specs}
         self.n_trainable = sum(s[3] for s in self.specs)
         self.has_reg = bool(regularization) and n_weights > 0
@@ -92,7 +93,7 @@ class _ChebStage(object):
     """filter -> [batch norm] -> [bias] -> [activation] -> [pool]   (models.py:1229-1243;
     decoder up-conv / de-conv / out-conv, models.py:1304-1341, with the unused parts off)."""
 
-    def __init__(self, model, scope, graph, Fin, Fout, K, bn, bias, act, p=1, pool='max', keep=None):
+    def __init__(self, model, scope, graph, Fin, Fout, K, bn, bias, act, p=1, pool='max', keep=None, first=False):
         self.m, self.scope, self.graph = model, scope, graph
         self.Fin, self.Fout, self.K = Fin, Fout, K
         self.bn, self.has_bias, self.act = bn, bias, act
@@ -105,6 +106,8 @@ class _ChebStage(object):
         if bias:
             model._P.add(scope + '/bias', (1, 1, Fout), np.zeros(Fout, np.float32))
         self.post = bn or bias or act != 'identity' or p > 1
+        # tiny reduction depth (K*Fin <= 8) on the input layer: never materialise y (csrc/smallconv.cu)
+        self.small = bool(first and self.post and model.fused_small and ops.smallconv_supported(Fin, K, Fout))
         self.saved = None
 
     def forward(self, x, training, save):
@@ -115,6 +118,8 @@ class _ChebStage(object):
                              .format(self.scope, M, Fin, self.graph.M, self.Fin))
         W = m._P.views[self.scope + '/weights']
         basis = ops.cheb_basis(self.graph, x, self.K)                      # models.py:1049-1061
+        if self.small:
+            return self._forward_small(x, basis, W, training, save)
         sums = None
         if self.bn and training:
             sums = torch.zeros(2 * self.Fout, dtype=torch.float64, device=x.device)
@@ -140,8 +145,59 @@ class _ChebStage(object):
             self.saved = (x, basis, y, mean, rstd, count, training)
         return out
 
+    def _forward_small(self, x, basis, W, training, save):
+        m = self.m
+        B, M, Fin = x.shape
+        count = float(B * M * m.world_size)
+        mean = rstd = gram = None
+        if self.bn:
+            mean, rstd = m._bn_buffers(self.scope, self.Fout)
+            mm, mv = m._state[self.scope + '/batch_normalization/moving_mean'], \
+                m._state[self.scope + '/batch_normalization/moving_variance']
+            if training:
+                gram = ops.cheb_gram(x, basis, self.K)
+                m._allreduce(gram)
+                sums = ops.bn_sums_from_gram(gram, W, Fin, self.K, self.Fout)
+                ops.bn_finalize(sums, count, self.Fout, mean, rstd, mm, mv, BN_EPS, BN_MOMENTUM)
+            else:
+                ops.bn_from_moving(mm, mv, mean, rstd, BN_EPS)
+        b = m._P.views[self.scope + '/bias'] if self.has_bias else None
+        out = ops.smallconv_fwd(x, basis, W, self.K, self.Fout, mean, rstd, b, self.p, self.pool, self.act)
+        if self.keep is not None and self.keep != out.shape[1]:
+            out = ops.vertex_resize(out, self.keep, 0.0)
+        if save:
+            self.saved = (x, basis, gram, mean, rstd, count, training)
+        return out
+
+    def _backward_small(self, dout):
+        m = self.m
+        x, basis, gram, mean, rstd, count, training = self.saved
+        self.saved = None
+        B, M, Fin = x.shape
+        if self.keep is not None and dout.shape[1] != M // self.p:
+            dout = ops.vertex_resize(dout, M // self.p, 0.0)
+        W = m._P.views[self.scope + '/weights']
+        b = m._P.views[self.scope + '/bias'] if self.has_bias else None
+        acc = ops.smallconv_bwd(x, basis, W, self.K, self.Fout, mean, rstd, b, dout, self.p, self.pool, self.act)
+        sync = self.bn and training
+        if sync:
+            m._allreduce(acc)
+        gW = m._P.gviews[self.scope + '/weights']
+        gb = m._P.gviews[self.scope + '/bias'] if self.has_bias else None
+        ops.smallconv_bwd_finalize(acc, gram if sync else None, W, mean if sync else None, rstd if sync else None,
+                                   count, Fin, self.K, self.Fout, gW, gb)
+        if sync and m.world_size > 1:                      # already global: the flat all-reduce sums them back
+            ops.scale(gW, 1.0 / m.world_size)
+            if gb is not None:
+                ops.scale(gb, 1.0 / m.world_size)
+        return None
+
     def backward(self, dout, need_dx=True):
         m = self.m
+        if self.small:
+            if need_dx:
+                raise RuntimeError('the fused input layer does not produce an input gradient')
+            return self._backward_small(dout)
         x, basis, y, mean, rstd, count, training = self.saved
         self.saved = None
         B, M, Fin = x.shape
@@ -444,7 +500,7 @@ class base_model(object):
 
     def load_state_dict(self, sd):
         for name, view in self._P.views.items():
-            view.copy_(torch.as_tensor(sd[name], dtype=torch.float32).reshape(-1))
+            view.copy_(torch.as_tensor(sd[name], dtype=torch.float32).reshape(view.shape))
         for k in self._state:
             self._state[k].copy_(torch.as_tensor(sd[k], dtype=torch.float32))
         self.global_step = int(sd.get('global_step', 0))
@@ -500,7 +556,8 @@ class cgcnn(base_model):
                  conv='chebyshev5', pool='max', activation='relu', statistics=None, Fseg=None, dtype=np.float32,
                  regularization=0, dropout=1, batch_size=128, eval_frequency=200, regression=False, dense=False,
                  weighted=False, mask=None, extra_loss=False, dropFilt=1, dir_name='', profile=False, debug=False,
-                 device=None, seed=None, process_group=None, cuda_graph=False, sync_every_step=True, verbose=True):
+                 device=None, seed=None, process_group=None, cuda_graph=False, sync_every_step=True, verbose=True,
+                 fused_small=True):
         # Verify the consistency w.r.t. the number of layers (models.py:937-950).
         if not len(L) == len(F) == len(K) == len(p) == len(batch_norm):
             raise ValueError('Wrong specification of the convolutional layers: '
@@ -548,6 +605,7 @@ class cgcnn(base_model):
         self.restore, self.tf_dataset = restore, tf_dataset
         self.num_feat_in = num_feat_in
         self.cuda_graph, self.sync_every_step = cuda_graph, sync_every_step
+        self.fused_small = fused_small
         if mask:
             self.train_mask, self.val_mask = mask[0], mask[1]
             raise NotImplementedError('masked regression is outside the hot path')
@@ -629,13 +687,14 @@ class cgcnn(base_model):
             pi = self.p[i]
             if icos:
                 st = _ChebStage(self, scope, g, Fin, self.F[i], self.K[i], self.batch_norm[i], True, act,
-                                keep=(pi if pi > 1 else None))
+                                keep=(pi if pi > 1 else None), first=(i == 0))
                 if pi > 1:
                     Mv = pi
             else:
                 if Mv % pi:
                     raise ValueError('layer {}: {} vertices cannot be pooled by {}'.format(i + 1, Mv, pi))
-                st = _ChebStage(self, scope, g, Fin, self.F[i], self.K[i], self.batch_norm[i], True, act, p=pi, pool=pool)
+                st = _ChebStage(self, scope, g, Fin, self.F[i], self.K[i], self.batch_norm[i], True, act, p=pi, pool=pool,
+                                first=(i == 0))
                 Mv //= pi
             self._encoder.append(st)
             Fin = self.F[i]
@@ -703,11 +762,9 @@ class cgcnn(base_model):
 
     def set_var(self, name, value):
         """Overwrite a variable / batch-norm statistic by its reference name."""
-        t = torch.as_tensor(np.asarray(value), dtype=torch.float32).reshape(-1).to(self.device)
-        if name in self._P.views:
-            self._P.views[name].copy_(t)
-        else:
-            self._state[name].copy_(t)
+        t = torch.as_tensor(np.asarray(value), dtype=torch.float32).to(self.device)
+        dst = self._P.views[name] if name in self._P.views else self._state[name]
+        dst.copy_(t.reshape(dst.shape))
 
     def get_filter_coeffs(self, layer, ind_in=None, ind_out=None):
         """Chebyshev coefficients of a layer as K x Fout x Fin (models.py:1377-1401)."""

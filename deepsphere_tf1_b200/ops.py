@@ -214,3 +214,47 @@ def dropout(x, u, keep):
     out = torch.empty_like(x)
     call('dropout', x, u, float(keep), out, x.numel())
     return out
+
+
+def set_tensor_cores(on):
+    """Enable / disable the tcgen05 contraction kernels (FP32 FFMA fallback); returns the previous setting."""
+    from ._lib import LIB
+    return bool(LIB.load().dsb200_set_tensor_cores(1 if on else 0))
+
+
+def smallconv_supported(Fin, K, Fout):
+    from ._lib import LIB
+    return bool(LIB.load().dsb200_smallconv_supported(Fin, K, Fout))
+
+
+def cheb_gram(x, basis, K):
+    """Column sums and Gram matrix of the Chebyshev basis (double[Q + Q*Q], Q = K*Fin)."""
+    B, M, Fin = x.shape
+    Q = K * Fin
+    gram = torch.zeros(Q + Q * Q, dtype=torch.float64, device=x.device)
+    call('cheb_gram', x, basis, B * M, Fin, K, gram)
+    return gram
+
+
+def bn_sums_from_gram(gram, W, Fin, K, Fout):
+    sums = torch.empty(2 * Fout, dtype=torch.float64, device=W.device)
+    call('bn_sums_from_gram', gram, W, Fin, K, Fout, sums)
+    return sums
+
+
+def smallconv_fwd(x, basis, W, K, Fout, mean, rstd, bias, p, pool, act):
+    B, M, Fin = x.shape
+    out = _new((B, M // p, Fout), x)
+    call('smallconv_fwd', x, basis, W, mean, rstd, bias, out, B, M, Fin, K, Fout, p, POOL[pool], ACT[act])
+    return out
+
+
+def smallconv_bwd(x, basis, W, K, Fout, mean, rstd, bias, dout, p, pool, act):
+    B, M, Fin = x.shape
+    acc = torch.zeros((K * Fin + 2) * Fout, dtype=torch.float64, device=x.device)
+    call('smallconv_bwd', x, basis, W, mean, rstd, bias, dout, acc, B, M, Fin, K, Fout, p, POOL[pool], ACT[act])
+    return acc
+
+
+def smallconv_bwd_finalize(acc, gram, W, mean, rstd, count, Fin, K, Fout, dW, dbias):
+    call('smallconv_bwd_finalize', acc, gram, W, mean, rstd, float(count), Fin, K, Fout, dW, dbias)

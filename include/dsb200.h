@@ -87,6 +87,37 @@ int dsb200_cheb_contract_bwd_data(const float* dY, const float* W, float* G,
 int dsb200_cheb_contract_bwd_weight(const float* x0, const float* xk, const float* dY, float* dW,
                                     long long R, int Fin, int K, int Fout, void* stream);
 
+/* The three contraction entry points run on the tcgen05 tensor cores (3xTF32 error-compensated,
+ * FP32 accumulate in TMEM) when the shape allows (Fin, Fout multiples of 8, R >= 128) and fall
+ * back to FP32 FFMA kernels otherwise; dsb200_set_tensor_cores(0) forces the FFMA kernels.
+ * Returns the previous setting. */
+int dsb200_set_tensor_cores(int on);
+
+/* ---- ChebConv layers with a tiny reduction depth K*Fin <= 8 (first layer of the cosmo net: Fin = 1):
+ * the filter output y is Fout/(K*Fin) times larger than the basis, so it is never materialised.
+ * Replaces, for such layers, the whole of models.py:1062-1078 + 1194-1203 + 1122-1163 and their
+ * gradients.  dsb200_smallconv_supported says whether a shape qualifies. */
+int dsb200_smallconv_supported(int Fin, int K, int Fout);
+/* gram (double[Q + Q*Q], Q = K*Fin, zeroed by the caller): column sums and Gram matrix of the basis
+ * over all R rows; index q = k*Fin + fi.  Summed over ranks by the caller for data parallelism. */
+int dsb200_cheb_gram(const float* x0, const float* xk, long long R, int Fin, int K, double* gram, void* stream);
+/* batch-norm sums (double[2*Fout]: sum y, sum y^2) of y = Xcat W from the Gram matrix */
+int dsb200_bn_sums_from_gram(const double* gram, const float* W, int Fin, int K, int Fout, double* sums, void* stream);
+/* out [B, M/p, Fout] = pool(act((Xcat W - mean) * rstd + bias)); mean/rstd/bias may be NULL */
+int dsb200_smallconv_fwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
+                         const float* bias, float* out, int B, int M, int Fin, int K, int Fout, int p, int pool,
+                         int act, void* stream);
+/* acc (double[(Q+2)*Fout], zeroed): A[q][f] = sum_r X_q[r] gz[r,f], then S1[f] = sum gz, S2[f] = sum gz*xhat,
+ * with gz = dLoss/d(normalised + bias) recomputed from the basis and dout [B, M/p, Fout] */
+int dsb200_smallconv_bwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
+                         const float* bias, const float* dout, double* acc, int B, int M, int Fin, int K, int Fout,
+                         int p, int pool, int act, void* stream);
+/* dW (+=) and dbias (=, may be NULL) from acc (already summed over ranks) and the Gram matrix; with
+ * mean == NULL there is no batch norm and dW += A. */
+int dsb200_smallconv_bwd_finalize(const double* acc, const double* gram, const float* W, const float* mean,
+                                  const float* rstd, double count, int Fin, int K, int Fout, float* dW,
+                                  float* dbias, void* stream);
+
 /* ---- batch-norm statistics -> mean / rstd, moving-average update (models.py:1194-1203,
  * UPDATE_OPS at 840-842).  sums = double[2*F] (sum, sum of squares over `count` rows, already
  * all-reduced over ranks).  moving_* may be NULL.  momentum 0.9, eps 1e-5 in the reference. */

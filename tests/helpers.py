@@ -51,11 +51,12 @@ def copy_weights(oracle, model):
         model.set_var(name, v.detach().numpy())
 
 
-def assert_close(actual, expected, rtol, name=''):
-    """Relative to the largest magnitude of the expected tensor (robust to near-zero entries)."""
+def assert_close(actual, expected, rtol, name='', floor=0.0):
+    """Max error relative to the largest magnitude of the expected tensor (robust to near-zero
+    entries); `floor` is a lower bound of that scale for tensors that are numerically zero."""
     a = actual.detach().cpu().double().numpy() if isinstance(actual, torch.Tensor) else np.asarray(actual, np.float64)
     e = expected.detach().cpu().double().numpy() if isinstance(expected, torch.Tensor) else np.asarray(expected, np.float64)
     assert a.shape == e.shape, (name, a.shape, e.shape)
-    scale = max(np.abs(e).max(), 1e-30)
+    scale = max(np.abs(e).max(), floor, 1e-30)
     err = np.abs(a - e).max() / scale
     assert err <= rtol, '{}: max error {:.3e} relative to max |expected| {:.3e} (rtol {})'.format(name, err, scale, rtol)

@@ -71,11 +71,25 @@ def test_spmm_general_form_and_aliasing(dev):
     assert oops is not None
 
 
+@pytest.mark.parametrize('tensor_cores', [True, False])
 @pytest.mark.parametrize('shape', [(2, 192, 1, 16, 5), (2, 192, 16, 32, 5), (3, 100, 6, 16, 4), (1, 77, 3, 5, 3),
-                                   (2, 64, 64, 64, 5), (2, 48, 32, 2, 5), (4, 33, 7, 9, 1), (2, 50, 96, 40, 4)])
-def test_contraction_forward_backward(dev, shape):
+                                   (2, 64, 64, 64, 5), (2, 48, 32, 2, 5), (4, 33, 7, 9, 1), (2, 50, 96, 40, 4),
+                                   (3, 1000, 16, 32, 5), (2, 700, 32, 64, 5), (2, 300, 64, 64, 5), (2, 300, 8, 16, 3),
+                                   (2, 300, 24, 40, 2), (1, 4100, 64, 8, 5), (5, 1111, 16, 16, 1), (2, 333, 128, 128, 2),
+                                   (1, 20000, 32, 64, 5)])
+def test_contraction_forward_backward(dev, shape, tensor_cores):
     """Y = Xcat W with the reference's row order fin*K + k (models.py:1062-1078) and both
-    gradients of tf.matmul, plus the batch-norm sums of the epilogue."""
+    gradients of tf.matmul, plus the batch-norm sums of the epilogue -- on the tcgen05 path
+    (3xTF32, where the shape allows) and on the FP32 FFMA path."""
+    from deepsphere_tf1_b200 import ops
+    prev = ops.set_tensor_cores(tensor_cores)
+    try:
+        _contraction_case(dev, shape)
+    finally:
+        ops.set_tensor_cores(prev)
+
+
+def _contraction_case(dev, shape):
     from deepsphere_tf1_b200 import ops
     B, M, Fin, Fout, K = shape
     rs = np.random.RandomState(Fin * 100 + Fout)
@@ -95,7 +109,7 @@ def test_contraction_forward_backward(dev, shape):
     assert_close(sums[:Fout], y_ref.sum((0, 1)), RTOL, 'sum y')
     assert_close(sums[Fout:], (y_ref ** 2).sum((0, 1)), RTOL, 'sum y^2')
     y2 = ops.contract_fwd(x0, xk, W.to(dev), K, Fout, None)
-    assert torch.equal(y, y2)
+    assert_close(y2, y, 1e-6, 'Y without the batch-norm epilogue')
     G = ops.contract_bwd_data(dy.to(dev), W.to(dev), K, Fin)
     assert_close(G, dX_ref, RTOL, 'dX_k')
     dW = torch.zeros(Fin * K, Fout, device=dev)
