@@ -392,6 +392,10 @@ extern "C" int dsb200_cheb_contract_bwd_weight(const float* x0, const float* xk,
     cudaStream_t s = (cudaStream_t)stream;
     Planar A{x0, xk, Fin, R * (long long)Fin};
     const int Q = K * Fin;
+    if (g_use_tc.load(std::memory_order_relaxed) && Q > 16) {
+        const int rc = tc::contract_bwd_weight_tc(x0, xk, dY, dW, R, Fin, K, Fout, s);
+        if (rc != 1) return rc;
+    }
     if (small_path(Q, Fout) && (((uintptr_t)dY & 15) == 0)) {
         const int rows_per_iter = 256 / (Fout / 4);
         const int grid = grid_for((R + rows_per_iter - 1) / rows_per_iter * 256, 256, 4);

@@ -40,7 +40,8 @@ int make_tmap_f32(CUtensorMap* out, const float* base, long long cols, long long
     cuuint64_t strides[2] = {(cuuint64_t)cols * 4, (cuuint64_t)cols * 4 * (cuuint64_t)rows};
     cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    const CUtensorMapSwizzle sw = swz == 3 ? CU_TENSOR_MAP_SWIZZLE_128B : swz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+    const CUtensorMapSwizzle sw = swz == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                : swz == 3 ? CU_TENSOR_MAP_SWIZZLE_128B : swz == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : swz == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
     const cuuint32_t rank = rank3 ? 3 : 2;
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, (void*)base, dims, strides, box, estr,
@@ -424,6 +425,247 @@ int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R,
         if (rc) return rc;
     }
     return 0;
+}
+
+}  // namespace tc
+}  // namespace dsb200
+
+// =====================================================================================================
+// Weight gradient on the tensor cores:  dW[fi*K + k, fo] += sum_r X_k[r, fi] * dY[r, fo]   (autodiff of
+// tf.matmul, models.py:1077).  The reduction runs over the (sample, vertex) rows, so both operands are
+// "MN-major" in UMMA terms.  For 32-bit (TF32) MN-major operands the only shared-memory layout the tensor
+// core accepts is the 128-byte swizzle with 32-byte atomicity: a TMA box of RS rows x 32 columns
+// (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B; narrower planes are zero-filled to 32 columns) lands as that
+// canonical layout, one box per 32-column block of every plane of X and of dY.
+//   D[q, fo] (TMEM, one 128-lane tile per 128 values of q)  +=  Xh^T [dYh | dYl]  +  Xl^T dYh
+// Every CTA owns a contiguous range of rows, accumulates in TMEM over its whole range and adds its
+// partial result to dW with one fp32 atomic per entry at the end.
+namespace dsb200 {
+namespace tc {
+
+constexpr int kMNBlock = 32;                     // columns per MN-major block (128 bytes of fp32)
+
+struct alignas(64) WGradParams {
+    CUtensorMap tmX0, tmXk, tmdY;
+    float* dW;
+    long long R;
+    int Fin, K, Fout;
+    int nblkA, nblkB;          // 32-column blocks per plane of X / of dY
+    int pad_blocks;            // unused blocks at the end of a stage (the last 128-wide tile of q may read past X_lo)
+    int RS;                    // rows per pipeline stage (multiple of 8)
+    int nstages;
+    int mtiles;                // ceil(K * nblkA * 32 / 128)
+    long long iters_total;     // ceil(R / RS)
+    long long iters_per_cta;
+};
+
+// descriptor of an MN-major TF32 operand: layout type 1 (128B swizzle, 32B atoms), 4-row k-groups
+__device__ __forceinline__ uint64_t make_mn_desc(uint32_t saddr, uint32_t block_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)((block_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((512u >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (1ull << 61);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ WGradParams p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = p.nstages;
+    const uint32_t blk = (uint32_t)p.RS * kMNBlock * 4;               // one 32-column block of RS rows
+    const int nA = p.K * p.nblkA;
+    const uint32_t xbytes = blk * nA, ybytes = blk * p.nblkB;
+    const uint32_t stage_bytes = 2 * (xbytes + ybytes) + blk * p.pad_blocks;   // [X][X_lo][dY][dY_lo][pad]
+    const int Np = p.nblkB * kMNBlock;                                // dY columns incl. zero padding
+
+    uint8_t* sA = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)S * stage_bytes);
+    uint64_t* full_tma = bars;
+    uint64_t* full_mma = bars + kMaxStages;
+    uint64_t* empty = bars + 2 * kMaxStages;
+    uint64_t* acc_full = bars + 3 * kMaxStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full_tma + s, 1); mbar_init(full_mma + s, 128); mbar_init(empty + s, 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+        prefetch_tmap(&p.tmX0);
+        prefetch_tmap(&p.tmXk);
+        prefetch_tmap(&p.tmdY);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const long long it0 = (long long)blockIdx.x * p.iters_per_cta;
+    long long it1 = it0 + p.iters_per_cta;
+    if (it1 > p.iters_total) it1 = p.iters_total;
+    const int niter = it1 > it0 ? (int)(it1 - it0) : 0;
+    const int acc_cols = 2 * Np;                                      // per M-tile: [hi | lo]
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < niter; ++i) {
+                const int row0 = (int)((it0 + i) * p.RS);
+                mbar_wait(empty + s, ph ^ 1u, 11);
+                mbar_expect_tx(full_tma + s, xbytes + ybytes);
+                uint8_t* dst = sA + (size_t)s * stage_bytes;
+                for (int k = 0; k < p.K; ++k)
+                    for (int c = 0; c < p.nblkA; ++c) {
+                        uint8_t* d = dst + (size_t)(k * p.nblkA + c) * blk;
+                        if (k == 0) tma_load_2d(d, &p.tmX0, full_tma + s, c * kMNBlock, row0);
+                        else tma_load_3d(d, &p.tmXk, full_tma + s, c * kMNBlock, row0, k - 1);
+                    }
+                uint8_t* dy = dst + 2 * (size_t)xbytes;
+                for (int c = 0; c < p.nblkB; ++c) tma_load_2d(dy + (size_t)c * blk, &p.tmdY, full_tma + s, c * kMNBlock, row0);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && niter > 0) {
+            const bool merged = acc_cols <= 256;
+            const uint32_t idesc_wide = make_idesc_tf32(kTileM, merged ? acc_cols : Np, 1, 1);
+            const uint32_t idesc_half = make_idesc_tf32(kTileM, Np, 1, 1);
+            const uint64_t dA0 = make_mn_desc(smem_u32(sA), blk);
+            const uint64_t dB0 = make_mn_desc(smem_u32(sA) + 2 * xbytes, blk);
+            const uint32_t kstep = (8u * kMNBlock * 4) >> 4;                         // 8 rows of 128 bytes
+            const uint32_t mtA = ((uint32_t)(kTileM / kMNBlock) * blk) >> 4;         // next 128 values of q
+            const uint32_t loA = xbytes >> 4, loB = ybytes >> 4, stg = stage_bytes >> 4;
+            const int ksteps = p.RS / 8;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < niter; ++i) {
+                mbar_wait(full_mma + s, ph, 13);
+                tc_fence_after();
+                const uint64_t dA = dA0 + (uint64_t)(stg * (uint32_t)s), dB = dB0 + (uint64_t)(stg * (uint32_t)s);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
+                    const uint64_t b = dB + kstep * ks;
+                    for (int mt = 0; mt < p.mtiles; ++mt) {
+                        const uint64_t a = dA + kstep * ks + mtA * mt;
+                        const uint32_t d = tmem_base + (uint32_t)(mt * acc_cols);
+                        if (merged) {
+                            mma_tf32(d, a, b, idesc_wide, acc);                   // Xh^T [dYh | dYl]
+                        } else {
+                            mma_tf32(d, a, b, idesc_half, acc);
+                            mma_tf32(d + Np, a, b + loB, idesc_half, acc);
+                        }
+                        mma_tf32(d, a + loA, b, idesc_half, 1u);                  // Xl^T dYh
+                    }
+                }
+                tc_commit(empty + s);
+                if (++s == S) { s = 0; ph ^= 1u; }
+            }
+            tc_commit(acc_full);
+        }
+    } else if (warp < 6) {
+        const int tt = threadIdx.x - 64;
+        const int nvecX = (int)(xbytes / 16), nvecY = (int)(ybytes / 16);
+        int s = 0;
+        uint32_t ph = 0;
+        for (int i = 0; i < niter; ++i) {
+            mbar_wait(full_tma + s, ph, 14);
+            float4* X = reinterpret_cast<float4*>(sA + (size_t)s * stage_bytes);
+            float4* Xl = X + nvecX;
+            float4* Y = Xl + nvecX;
+            float4* Yl = Y + nvecY;
+#pragma unroll 4
+            for (int j = tt; j < nvecX + nvecY; j += 128) {
+                float4* src = j < nvecX ? X + j : Y + (j - nvecX);
+                float4* dlo = j < nvecX ? Xl + j : Yl + (j - nvecX);
+                const float4 v = *src;
+                float4 h, l;
+                h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+                *src = h;
+                *dlo = l;
+            }
+            fence_proxy_async();
+            mbar_arrive(full_mma + s);
+            if (++s == S) { s = 0; ph ^= 1u; }
+        }
+    } else if (niter > 0) {
+        // epilogue: once per CTA
+        const int qd = warp & 3;
+        mbar_wait(acc_full, 0, 15);
+        tc_fence_after();
+        for (int mt = 0; mt < p.mtiles; ++mt) {
+            const int q = mt * kTileM + qd * 32 + lane;              // (block, column in block) of the padded Xcat
+            const int bq = q / kMNBlock;
+            const int k = bq / p.nblkA;
+            const int fi = (bq - k * p.nblkA) * kMNBlock + (q - bq * kMNBlock);
+            const bool ok = k < p.K && fi < p.Fin;
+            float* dst = p.dW + ((long long)fi * p.K + k) * p.Fout;
+            const uint32_t tbase = tmem_base + (uint32_t)(mt * acc_cols) + ((uint32_t)(qd * 32) << 16);
+            for (int c0 = 0; c0 < p.Fout; c0 += 8) {
+                float hi[8], lo[8];
+                tmem_ld8(tbase + c0, hi);
+                tmem_ld8(tbase + Np + c0, lo);
+                tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) atomicAdd(dst + c0 + e, hi[e] + lo[e]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K,
+                           int Fout, cudaStream_t s)
+{
+    if (R < 128 || R > 0x7fffff00LL || (Fin & 7) || (Fout & 7) || Fout > 256) return 1;
+    if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)dY) & 15) != 0) return 1;
+    WGradParams p;
+    p.nblkA = (Fin + kMNBlock - 1) / kMNBlock;
+    p.nblkB = (Fout + kMNBlock - 1) / kMNBlock;
+    const int nA = K * p.nblkA, nB = p.nblkB;
+    p.mtiles = (nA * kMNBlock + kTileM - 1) / kTileM;
+    if (p.mtiles * 2 * nB * kMNBlock > 512) return 1;
+    // the last 128-wide tile of q may read past the X_lo blocks: keep it inside the stage ([X][X_lo][dY][dY_lo][pad])
+    p.pad_blocks = p.mtiles * (kTileM / kMNBlock) - (nA + 2 * nB);
+    if (p.pad_blocks < 0) p.pad_blocks = 0;
+    int RS = (48 * 1024) / (kMNBlock * 4 * (2 * (nA + nB) + p.pad_blocks)) / 8 * 8;     // ~48 KB stages
+    if (RS > 128) RS = 128;
+    if (RS < 8) return 1;
+    p.RS = RS;
+    const size_t stage = (size_t)RS * kMNBlock * 4 * (2 * (nA + nB) + p.pad_blocks);
+    const size_t fixed = 1024 + 3 * kMaxStages * 8 + 64;
+    const size_t budget = 227 * 1024;
+    size_t ns = (budget - fixed) / stage;
+    if (ns > kMaxStages) ns = kMaxStages;
+    if (ns < 2) return 1;
+    p.nstages = (int)ns;
+    size_t smem = fixed + ns * stage;
+    if (smem < 120 * 1024) smem = 120 * 1024;
+    const int SW = 4;                                                   // 128B swizzle, 32B atoms
+    if (make_tmap_f32(&p.tmX0, x0, Fin, R, 1, kMNBlock, RS, SW, false)) return 1;
+    if (K > 1) { if (make_tmap_f32(&p.tmXk, xk, Fin, R, K - 1, kMNBlock, RS, SW, true)) return 1; }
+    else p.tmXk = p.tmX0;
+    if (make_tmap_f32(&p.tmdY, dY, Fout, R, 1, kMNBlock, RS, SW, false)) return 1;
+    p.dW = dW; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
+    p.iters_total = (R + RS - 1) / RS;
+    int grid = p.iters_total < kNumSMs ? (int)p.iters_total : kNumSMs;
+    p.iters_per_cta = (p.iters_total + grid - 1) / grid;
+    grid = (int)((p.iters_total + p.iters_per_cta - 1) / p.iters_per_cta);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    wgrad_tc_kernel<<<grid, kThreads, smem, s>>>(p);
+    DSB_LAUNCH_CHECK();
 }
 
 }  // namespace tc
