@@ -22,10 +22,10 @@ struct Planes {
     const float* pk;
     long long plane_stride;      // R * Fin
     int Fin, K;
-    __device__ __forceinline__ float at(int q, long long r) const {
+    // pointer to element (row 0, column q) of the concatenated basis; hoisted out of the row loops
+    __device__ __forceinline__ const float* col(int q) const {
         const int k = q / Fin, fi = q - k * Fin;
-        const float* base = k == 0 ? p0 : pk + (long long)(k - 1) * plane_stride;
-        return __ldg(base + r * Fin + fi);
+        return (k == 0 ? p0 : pk + (long long)(k - 1) * plane_stride) + fi;
     }
 };
 
@@ -42,10 +42,14 @@ gram_kernel(Planes P, long long R, double* __restrict__ gram)
     for (int i = 0; i < Q; ++i) s[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < Q * (Q + 1) / 2; ++i) g[i] = 0.f;
+    const float* cp[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) cp[q] = P.col(q);
+    const int Fin = P.Fin;
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < R; r += (long long)gridDim.x * blockDim.x) {
         float x[Q];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) x[q] = P.at(q, r);
+        for (int q = 0; q < Q; ++q) x[q] = __ldg(cp[q] + r * Fin);
         int t = 0;
 #pragma unroll
         for (int a = 0; a < Q; ++a) {
@@ -114,6 +118,10 @@ smallconv_fwd_kernel(Planes P, const float* __restrict__ W, const float* __restr
     __syncthreads();
     const int Fv = Fout / 4;
     const long long total = Rout * Fv;
+    const float* cp[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) cp[q] = P.col(q);
+    const int Fin = P.Fin;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
         const long long ro = g / Fv;
         const int f0 = (int)(g - ro * Fv) * 4;
@@ -125,7 +133,7 @@ smallconv_fwd_kernel(Planes P, const float* __restrict__ W, const float* __restr
             float y[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                const float x = P.at(q, r);
+                const float x = __ldg(cp[q] + r * Fin);
                 const float4 w = *reinterpret_cast<const float4*>(Ws + q * Fout + f0);
                 y[0] = fmaf(x, w.x, y[0]); y[1] = fmaf(x, w.y, y[1]); y[2] = fmaf(x, w.z, y[2]); y[3] = fmaf(x, w.w, y[3]);
             }
@@ -174,8 +182,10 @@ smallconv_bwd_kernel(Planes P, const float* __restrict__ W, const float* __restr
     const int rows_per_block = blockDim.x / Fv;
     const int f0 = (threadIdx.x % Fv) * 4, rl = threadIdx.x / Fv;
     float A[Q][4], s1[4], s2[4];
+    const float* cp[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) { A[q][0] = A[q][1] = A[q][2] = A[q][3] = 0.f; }
+    for (int q = 0; q < Q; ++q) { A[q][0] = A[q][1] = A[q][2] = A[q][3] = 0.f; cp[q] = P.col(q); }
+    const int Fin = P.Fin;
 #pragma unroll
     for (int v = 0; v < 4; ++v) { s1[v] = 0.f; s2[v] = 0.f; }
     for (long long ro = (long long)blockIdx.x * rows_per_block + rl; ro < Rout; ro += (long long)gridDim.x * rows_per_block) {
@@ -191,7 +201,7 @@ smallconv_bwd_kernel(Planes P, const float* __restrict__ W, const float* __restr
             float x[Q], y[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                x[q] = P.at(q, r);
+                x[q] = __ldg(cp[q] + r * Fin);
                 const float4 w = *reinterpret_cast<const float4*>(Ws + q * Fout + f0);
                 y[0] = fmaf(x[q], w.x, y[0]); y[1] = fmaf(x[q], w.y, y[1]); y[2] = fmaf(x[q], w.z, y[2]); y[3] = fmaf(x[q], w.w, y[3]);
             }
@@ -221,7 +231,7 @@ smallconv_bwd_kernel(Planes P, const float* __restrict__ W, const float* __restr
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
 #pragma unroll
-                for (int v = 0; v < 4; ++v) A[q][v] = fmaf(P.at(q, ro * p + arg[v]), gsel[v], A[q][v]);
+                for (int v = 0; v < 4; ++v) A[q][v] = fmaf(__ldg(cp[q] + (ro * p + arg[v]) * Fin), gsel[v], A[q][v]);
             }
         }
     }

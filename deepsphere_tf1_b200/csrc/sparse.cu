@@ -46,7 +46,7 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
         else { j0 = m * width; j1 = j0 + width; }
         for (int j = j0; j < j1; ++j) {
             const int c = __ldg(col + j);
-            if (!CSR && c < 0) break;                       // ELL padding sits at the end of a row
+            if (!CSR && c < 0) break;                       // tolerate (col = -1) padding as well
             const float w = __ldg(val + j);
             const float* xr = x + ((base + c) * Fv + fv) * VEC;
             if (VEC == 4) {
@@ -80,6 +80,113 @@ spmm_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     }
 }
 
+// Main kernel (F % 4 == 0).  A CTA works on a compact TILE: TR consecutive vertex rows (a square patch of
+// the sphere in HEALPix nested = Morton order) x a slab of at most 64 16-byte chunks (1 KB) of the feature
+// row, so that the 9 gathers per row mostly hit the rows its neighbours in the same tile just fetched
+// (L1-resident: about (sqrt(TR)+2)^2 distinct rows for 9*TR gathers).  Inside the tile a group of
+// LG = 2^lg2 lanes owns one row and sweeps its chunks, PASSES chunks per lane: a warp gathers whole
+// 128-byte lines as soon as the slab is >= 32 floats wide, the (col, val) pair of a neighbour is loaded
+// once per lane and reused for PASSES gathers, and PASSES x (unrolled j) independent 16-byte loads are in
+// flight per lane.  ELL padding slots hold (col = row, val = 0): uniform trip count, no data-dependent
+// exit.  Tiles = (sample, row tile, column slab), distributed grid-stride over the CTAs.
+// W > 0: ELL rows of exactly W slots, fully unrolled: all W (col, val) pairs are fetched first, then all
+// W x PASSES gathers are issued back to back (one memory latency per row instead of one per neighbour).
+template <int PASSES, int W, bool CSR>
+__global__ void __launch_bounds__(256)
+spmm_rows_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+                 int width, int B, int M, int chunks, int lg2, int TR, int CB,
+                 const float4* __restrict__ x, const float4* y, const float4* z, float4* out,
+                 float alpha, float beta, float gamma)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int LG = 1 << lg2, rpw = 32 >> lg2;                    // lanes per row, rows per warp
+    const int sub = lane >> lg2, lg = lane & (LG - 1);
+    const int rtiles = (M + TR - 1) / TR, ctiles = (chunks + CB - 1) / CB;
+    const long long tiles = (long long)B * rtiles * ctiles;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int ct = (int)(t % ctiles);
+        const long long t2 = t / ctiles;
+        const int rt = (int)(t2 % rtiles), b = (int)(t2 / rtiles);
+        const long long sbase = (long long)b * M * chunks;        // first chunk of this sample
+        const float4* xb = x + sbase + ct * CB + lg;
+        const int mend = min(M, (rt + 1) * TR);
+        bool on[PASSES];
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) on[p] = (ct * CB + lg + p * LG < chunks) && (lg + p * LG < CB);
+        for (int m = rt * TR + warp * rpw + sub; m < mend; m += 8 * rpw) {
+            float4 acc[PASSES];
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (W > 0) {
+                int c[W > 0 ? W : 1];
+                float wv[W > 0 ? W : 1];
+#pragma unroll
+                for (int j = 0; j < W; ++j) { c[j] = __ldg(col + (long long)m * W + j); wv[j] = __ldg(val + (long long)m * W + j); }
+                float4 v[W > 0 ? W : 1][PASSES];
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+#pragma unroll
+                    for (int p = 0; p < PASSES; ++p)
+                        v[j][p] = on[p] ? __ldg(xb + (long long)c[j] * chunks + p * LG) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+#pragma unroll
+                    for (int p = 0; p < PASSES; ++p) {
+                        acc[p].x = fmaf(wv[j], v[j][p].x, acc[p].x); acc[p].y = fmaf(wv[j], v[j][p].y, acc[p].y);
+                        acc[p].z = fmaf(wv[j], v[j][p].z, acc[p].z); acc[p].w = fmaf(wv[j], v[j][p].w, acc[p].w);
+                    }
+                }
+            } else {
+                int j0, j1;
+                if (CSR) { j0 = __ldg(rowptr + m); j1 = __ldg(rowptr + m + 1); }
+                else { j0 = m * width; j1 = j0 + width; }
+#pragma unroll 4
+                for (int j = j0; j < j1; ++j) {
+                    const int c = __ldg(col + j);
+                    const float wv = __ldg(val + j);
+                    const float4* xr = xb + (long long)c * chunks;
+#pragma unroll
+                    for (int p = 0; p < PASSES; ++p) {
+                        if (on[p]) {
+                            const float4 v = __ldg(xr + p * LG);
+                            acc[p].x = fmaf(wv, v.x, acc[p].x); acc[p].y = fmaf(wv, v.y, acc[p].y);
+                            acc[p].z = fmaf(wv, v.z, acc[p].z); acc[p].w = fmaf(wv, v.w, acc[p].w);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) {
+                if (on[p]) {
+                    const long long o = sbase + (long long)m * chunks + ct * CB + lg + p * LG;
+                    float4 r = make_float4(acc[p].x * alpha, acc[p].y * alpha, acc[p].z * alpha, acc[p].w * alpha);
+                    if (y) { const float4 t4 = y[o]; r.x = fmaf(beta, t4.x, r.x); r.y = fmaf(beta, t4.y, r.y); r.z = fmaf(beta, t4.z, r.z); r.w = fmaf(beta, t4.w, r.w); }
+                    if (z) { const float4 t4 = z[o]; r.x = fmaf(gamma, t4.x, r.x); r.y = fmaf(gamma, t4.y, r.y); r.z = fmaf(gamma, t4.z, r.z); r.w = fmaf(gamma, t4.w, r.w); }
+                    out[o] = r;
+                }
+            }
+        }
+    }
+}
+
+template <int PASSES>
+static void launch_rows(const int32_t* rowptr, const int32_t* col, const float* val, int width, int B, int M, int chunks,
+                        int lg2, int TR, int CB, const float* x, const float* y, const float* z, float* out,
+                        float alpha, float beta, float gamma, cudaStream_t s)
+{
+    const long long tiles = (long long)B * ((M + TR - 1) / TR) * ((chunks + CB - 1) / CB);
+    const long long cap = (long long)kNumSMs * 8;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+#define DSB_ROWS(WW, CC) spmm_rows_kernel<PASSES, WW, CC><<<grid, 256, 0, s>>>(rowptr, col, val, width, B, M, chunks, lg2, TR, CB, \
+            (const float4*)x, (const float4*)y, (const float4*)z, (float4*)out, alpha, beta, gamma)
+    if (rowptr) DSB_ROWS(0, true);
+    else if (width == 9) DSB_ROWS(9, false);
+    else if (width == 7) DSB_ROWS(7, false);
+    else DSB_ROWS(0, false);
+#undef DSB_ROWS
+}
+
 static int spmm_launch(const int32_t* rowptr, const int32_t* col, const float* val, int width, int B, int M, int F,
                        const float* x, const float* y, const float* z, float* out,
                        float alpha, float beta, float gamma, cudaStream_t s)
@@ -91,10 +198,25 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const float* v
     if (gamma == 0.f) z = nullptr;
     const uintptr_t align = (uintptr_t)x | (uintptr_t)out | (uintptr_t)y | (uintptr_t)z;
     const int vec = (F % 4 == 0 && (align & 15) == 0) ? 4 : (F % 2 == 0 && (align & 7) == 0) ? 2 : 1;
+    if (!rowptr) DSB_REQUIRE(width > 0, "spmm_ell: width must be positive");
+    if (vec == 4) {
+        const int chunks = F / 4;
+        const int CB = chunks < 64 ? chunks : 64;                  // column slab: at most 1 KB of a row
+        int lg2 = 0;
+        while ((1 << lg2) < CB && lg2 < 5) ++lg2;
+        const int passes = (CB + (1 << lg2) - 1) >> lg2;           // 1 or 2
+        // rows per tile: ~64 KB of x per tile (it has to live in L1 next to its halo), 32..512 rows
+        int TR = 32768 / (CB * 16);
+        TR = TR < 32 ? 32 : TR > 256 ? 256 : TR;
+        // keep enough tiles to fill the machine a few times over
+        while (TR > 16 && (long long)B * ((M + TR - 1) / TR) * ((chunks + CB - 1) / CB) < 8LL * kNumSMs) TR >>= 1;
+        if (passes <= 1) launch_rows<1>(rowptr, col, val, width, B, M, chunks, lg2, TR, CB, x, y, z, out, alpha, beta, gamma, s);
+        else launch_rows<2>(rowptr, col, val, width, B, M, chunks, lg2, TR, CB, x, y, z, out, alpha, beta, gamma, s);
+        DSB_LAUNCH_CHECK();
+    }
     const int Fv = F / vec;
     const long long R = (long long)B * M;
     const int grid = grid_for(R * Fv, 256, 8);
-    if (!rowptr) DSB_REQUIRE(width > 0, "spmm_ell: width must be positive");
 #define DSB_SPMM(V, C) spmm_kernel<V, C><<<grid, 256, 0, s>>>(rowptr, col, val, width, R, M, Fv, x, y, z, out, alpha, beta, gamma)
     if (rowptr) { if (vec == 4) DSB_SPMM(4, true); else if (vec == 2) DSB_SPMM(2, true); else DSB_SPMM(1, true); }
     else        { if (vec == 4) DSB_SPMM(4, false); else if (vec == 2) DSB_SPMM(2, false); else DSB_SPMM(1, false); }

@@ -41,7 +41,8 @@ class DeviceGraph(object):
     def _pack(self, A):
         if self.is_ell:
             width = max(self.max_degree, int(np.diff(A.indptr).max()))
-            col = np.full((self.M, width), -1, dtype=np.int32)
+            # padding slots: (col = row, val = 0) -- a harmless gather, so kernels need no early exit
+            col = np.repeat(np.arange(self.M, dtype=np.int32)[:, None], width, axis=1)
             val = np.zeros((self.M, width), dtype=np.float32)
             counts = np.diff(A.indptr)
             rows = np.repeat(np.arange(self.M), counts)

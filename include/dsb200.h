@@ -20,7 +20,8 @@
  *  - Chebyshev weights keep the reference layout W[Fin*K, Fout], row = fin*K + k
  *    (models.py:1062-1066);
  *  - the rescaled Laplacian is passed as ELL (col[M*width], val[M*width], row-major, unused
- *    slots col = -1 at the end of a row) or as CSR (rowptr[M+1], col[nnz], val[nnz]).
+ *    slots at the end of a row hold col = the row itself, val = 0) or as CSR (rowptr[M+1],
+ *    col[nnz], val[nnz]).
  */
 #ifndef DSB200_H
 #define DSB200_H

@@ -67,6 +67,8 @@ for li in [int(v) for v in args.layers.split(',')]:
     out = torch.empty_like(x)
     W = torch.randn(Fin * K, Fout, device=dev) * 0.1
     timeit('spmm step (k>=2)', li, 3 * X + 8 * g.nnz, lambda: ops.spmm(g, x1, x, None, out=out, alpha=2.0, beta=-1.0))
+    xi, x1i, outi = x.view(1, M, B * Fin), x1.view(1, M, B * Fin), out.view(1, M, B * Fin)
+    timeit('spmm step, interleaved', li, 3 * X + 8 * g.nnz, lambda: ops.spmm(g, x1i, xi, None, out=outi, alpha=2.0, beta=-1.0))
     basis = ops.cheb_basis(g, x, K)
     timeit('cheb_basis (4 steps)', li, (2 + 3 * 3) * X + 4 * 8 * g.nnz, lambda: ops.cheb_basis(g, x, K))
     sums = torch.zeros(2 * Fout, dtype=torch.float64, device=dev)
