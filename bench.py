@@ -305,8 +305,14 @@ def run_gpu(args):
         }
         print(json.dumps(out))
     if world > 1:
+        # Captured CUDA graphs hold NCCL work; tearing the process group down under them can block
+        # (seen with NCCL 2.28 / torch 2.11).  Release the graph, meet at a barrier, flush and leave.
+        model._graph_exec = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

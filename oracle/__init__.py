@@ -1,7 +1,6 @@
 """CPU oracle for the DeepSphere ChebConv hot path -- TEST INFRASTRUCTURE ONLY.
 
-This package is a CPU restatement (numpy / scipy / torch-CPU autograd, plus a small C
-file for the ELL Chebyshev recurrence) of the algorithms in the reference
+This package is a CPU restatement (numpy / scipy / torch-CPU autograd) of the algorithms in the reference
 `deepsphere/models.py` and `deepsphere/utils.py`.  Every function cites the reference
 file:line it follows.
 
