@@ -96,76 +96,132 @@ bn_act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
 // Backward of the chain.  Threads are arranged [rows_per_block][Fv] so that a thread keeps the
 // same feature group over its grid-stride loop and can accumulate sum(gz), sum(gz*xhat) in
 // registers; one shared-memory and one double-precision global atomic pass at the end.
-template <int VEC>
+//   MODE 0: write gz and accumulate the sums          (no batch norm: gz is already dy)
+//   MODE 1: accumulate the sums only                  (batch norm, pass 1: nothing is written)
+//   MODE 2: write dy = rstd (gz - S1/n - xhat S2/n)   (batch norm, pass 2: gz is recomputed, never stored)
+template <int VEC> __device__ __forceinline__ void load_vec(const float* p, float* v) {
+    if (VEC == 4) { const float4 q = ldg4(p); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+    else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = __ldg(p + i);
+    }
+}
+template <int VEC> __device__ __forceinline__ void store_vec(float* p, const float* v) {
+    if (VEC == 4) st4(p, make_float4(v[0], v[1], v[2], v[3]));
+    else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) p[i] = v[i];
+    }
+}
+
+template <int VEC, int MODE>
 __global__ void __launch_bounds__(256)
 bn_act_pool_bwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ bias, const float* __restrict__ dout, float* __restrict__ gz,
-                       double* __restrict__ sums_bwd, long long Rout, int Fv, int p, int pool, int act)
+                       double* __restrict__ sums_bwd, double count, long long Rout, int Fv, int p, int pool, int act)
 {
     extern __shared__ float red[];                          // [2][F]
     const int F = Fv * VEC;
-    for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) red[i] = 0.f;
-    __syncthreads();
+    if (MODE != 2) {
+        for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) red[i] = 0.f;
+        __syncthreads();
+    }
     const int rows_per_block = blockDim.x / Fv;
     const int fvi = threadIdx.x % Fv, rl = threadIdx.x / Fv;
     const int f0 = fvi * VEC;
-    float s1[VEC], s2[VEC], mu[VEC], rs[VEC], bs[VEC];
+    float s1[VEC], s2[VEC], mu[VEC], rs[VEC], bs[VEC], m1[VEC], m2[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
         s1[v] = 0.f; s2[v] = 0.f;
         mu[v] = mean ? __ldg(mean + f0 + v) : 0.f;
         rs[v] = rstd ? __ldg(rstd + f0 + v) : 1.f;
         bs[v] = bias ? __ldg(bias + f0 + v) : 0.f;
+        m1[v] = MODE == 2 ? (float)(sums_bwd[f0 + v] / count) : 0.f;
+        m2[v] = MODE == 2 ? (float)(sums_bwd[F + f0 + v] / count) : 0.f;
     }
     if (rl < rows_per_block) {
+        constexpr int PC = 4;                               // sibling rows kept in registers
         for (long long ro = (long long)blockIdx.x * rows_per_block + rl; ro < Rout; ro += (long long)gridDim.x * rows_per_block) {
             float d[VEC];
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) d[v] = __ldg(dout + ro * F + f0 + v);
+            load_vec<VEC>(dout + ro * F + f0, d);
             const float* yp = y + (ro * p) * F + f0;
-            float* gp = gz + (ro * p) * F + f0;
-            if (pool == DSB200_POOL_MAX && p > 1) {
-                // first arg-max of the activation over the p rows
-                float best[VEC]; int arg[VEC];
+            float* gp = MODE != 1 ? gz + (ro * p) * F + f0 : nullptr;
+            const bool is_max = pool == DSB200_POOL_MAX && p > 1;
+            const float inv = is_max ? 1.f : 1.f / (float)p;
+            if (p <= PC) {
+                float yv[PC][VEC];
+                int arg[VEC];
+                float best[VEC];
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) { best[v] = -FLT_MAX; arg[v] = 0; }
-                for (int j = 0; j < p; ++j) {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        const float a = act_fwd((__ldg(yp + (long long)j * F + v) - mu[v]) * rs[v] + bs[v], act);
-                        if (a > best[v]) { best[v] = a; arg[v] = j; }
+                for (int j = 0; j < PC; ++j) {
+                    if (j < p) {
+                        load_vec<VEC>(yp + (long long)j * F, yv[j]);
+                        if (is_max) {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                const float a = act_fwd((yv[j][v] - mu[v]) * rs[v] + bs[v], act);
+                                if (a > best[v]) { best[v] = a; arg[v] = j; }
+                            }
+                        }
                     }
                 }
-                for (int j = 0; j < p; ++j) {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) {
-                        float g = 0.f;
-                        if (arg[v] == j) {
-                            const float xh = (__ldg(yp + (long long)j * F + v) - mu[v]) * rs[v];
-                            g = d[v] * act_grad(xh + bs[v], act);
-                            s1[v] += g; s2[v] = fmaf(g, xh, s2[v]);
+                for (int j = 0; j < PC; ++j) {
+                    if (j < p) {
+                        float o[VEC];
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            const float xh = (yv[j][v] - mu[v]) * rs[v];
+                            float g = 0.f;
+                            if (!is_max || arg[v] == j) g = d[v] * inv * act_grad(xh + bs[v], act);
+                            if (MODE != 2) { s1[v] += g; s2[v] = fmaf(g, xh, s2[v]); }
+                            o[v] = MODE == 2 ? rs[v] * (g - m1[v] - xh * m2[v]) : g;
                         }
-                        gp[(long long)j * F + v] = g;
+                        if (MODE != 1) store_vec<VEC>(gp + (long long)j * F, o);
                     }
                 }
             } else {
-                const float inv = 1.f / (float)p;
+                int arg[VEC];
+                float best[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) { best[v] = -FLT_MAX; arg[v] = 0; }
+                if (is_max) {
+                    for (int j = 0; j < p; ++j) {
+                        float yv[VEC];
+                        load_vec<VEC>(yp + (long long)j * F, yv);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) {
+                            const float a = act_fwd((yv[v] - mu[v]) * rs[v] + bs[v], act);
+                            if (a > best[v]) { best[v] = a; arg[v] = j; }
+                        }
+                    }
+                }
                 for (int j = 0; j < p; ++j) {
+                    float yv[VEC], o[VEC];
+                    load_vec<VEC>(yp + (long long)j * F, yv);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) {
-                        const float xh = (__ldg(yp + (long long)j * F + v) - mu[v]) * rs[v];
-                        const float g = d[v] * inv * act_grad(xh + bs[v], act);
-                        s1[v] += g; s2[v] = fmaf(g, xh, s2[v]);
-                        gp[(long long)j * F + v] = g;
+                        const float xh = (yv[v] - mu[v]) * rs[v];
+                        float g = 0.f;
+                        if (!is_max || arg[v] == j) g = d[v] * inv * act_grad(xh + bs[v], act);
+                        if (MODE != 2) { s1[v] += g; s2[v] = fmaf(g, xh, s2[v]); }
+                        o[v] = MODE == 2 ? rs[v] * (g - m1[v] - xh * m2[v]) : g;
                     }
+                    if (MODE != 1) store_vec<VEC>(gp + (long long)j * F, o);
                 }
             }
         }
+        if (MODE != 2) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { atomicAdd(&red[f0 + v], s1[v]); atomicAdd(&red[F + f0 + v], s2[v]); }
+            for (int v = 0; v < VEC; ++v) { atomicAdd(&red[f0 + v], s1[v]); atomicAdd(&red[F + f0 + v], s2[v]); }
+        }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) atomicAdd(sums_bwd + i, (double)red[i]);
+    if (MODE != 2) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) atomicAdd(sums_bwd + i, (double)red[i]);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -575,26 +631,44 @@ extern "C" int dsb200_bn_act_pool_fwd(const float* y, const float* mean, const f
     DSB_LAUNCH_CHECK();
 }
 
-extern "C" int dsb200_bn_act_pool_bwd(const float* y, const float* mean, const float* rstd, const float* bias,
-                                      const float* dout, float* gz, double* sums_bwd,
-                                      int B, int M, int F, int p, int pool, int act, void* stream)
+template <int MODE>
+static int bn_act_pool_bwd_launch(const float* y, const float* mean, const float* rstd, const float* bias,
+                                  const float* dout, float* gz, double* sums_bwd, double count,
+                                  int B, int M, int F, int p, int pool, int act, cudaStream_t st)
 {
-    DSB_REQUIRE(y && dout && gz && sums_bwd && B > 0 && M > 0 && F > 0 && p >= 1, "bn_act_pool_bwd: bad arguments");
+    DSB_REQUIRE(y && dout && sums_bwd && B > 0 && M > 0 && F > 0 && p >= 1, "bn_act_pool_bwd: bad arguments");
     DSB_REQUIRE(M % p == 0, "bn_act_pool_bwd: M must be a multiple of p");
     DSB_REQUIRE(F <= 4096, "bn_act_pool_bwd: F too large");
     const long long Rout = (long long)B * (M / p);
     const size_t smem = 2 * (size_t)F * sizeof(float);
-    if (F % 4 == 0 && F / 4 <= 256) {
+    const bool a16 = ((((uintptr_t)y | (uintptr_t)dout | (uintptr_t)gz) & 15) == 0);
+    if (F % 4 == 0 && F / 4 <= 256 && a16) {
         const int Fv = F / 4, rpb = 256 / Fv;
-        const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 4);
-        bn_act_pool_bwd_kernel<4><<<grid, 256, smem, STREAM>>>(y, mean, rstd, bias, dout, gz, sums_bwd, Rout, Fv, p, pool, act);
+        const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 8);
+        bn_act_pool_bwd_kernel<4, MODE><<<grid, 256, smem, st>>>(y, mean, rstd, bias, dout, gz, sums_bwd, count, Rout, Fv, p, pool, act);
     } else {
         DSB_REQUIRE(F <= 256, "bn_act_pool_bwd: F must be a multiple of 4 when > 256");
         const int rpb = 256 / F;
-        const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 4);
-        bn_act_pool_bwd_kernel<1><<<grid, 256, smem, STREAM>>>(y, mean, rstd, bias, dout, gz, sums_bwd, Rout, F, p, pool, act);
+        const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 8);
+        bn_act_pool_bwd_kernel<1, MODE><<<grid, 256, smem, st>>>(y, mean, rstd, bias, dout, gz, sums_bwd, count, Rout, F, p, pool, act);
     }
     DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_bn_act_pool_bwd(const float* y, const float* mean, const float* rstd, const float* bias,
+                                      const float* dout, float* gz, double* sums_bwd,
+                                      int B, int M, int F, int p, int pool, int act, void* stream)
+{
+    if (gz) return bn_act_pool_bwd_launch<0>(y, mean, rstd, bias, dout, gz, sums_bwd, 1.0, B, M, F, p, pool, act, STREAM);
+    return bn_act_pool_bwd_launch<1>(y, mean, rstd, bias, dout, nullptr, sums_bwd, 1.0, B, M, F, p, pool, act, STREAM);
+}
+
+extern "C" int dsb200_bn_act_pool_bwd_dy(const float* y, const float* mean, const float* rstd, const float* bias,
+                                         const float* dout, const double* sums_bwd, double count, float* dy,
+                                         int B, int M, int F, int p, int pool, int act, void* stream)
+{
+    DSB_REQUIRE(mean && rstd && dy && count > 0, "bn_act_pool_bwd_dy: bad arguments");
+    return bn_act_pool_bwd_launch<2>(y, mean, rstd, bias, dout, dy, const_cast<double*>(sums_bwd), count, B, M, F, p, pool, act, STREAM);
 }
 
 extern "C" int dsb200_bn_bwd_apply(const float* y, const float* mean, const float* rstd, const double* sums_bwd,

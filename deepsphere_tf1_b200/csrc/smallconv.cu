@@ -29,6 +29,22 @@ struct Planes {
     }
 };
 
+// Row addressing of the basis planes.  Classic: row (b, m) = b*M + m.  Sample-interleaved (il != 0): the input
+// was transposed to [M, B, Fin] before the recurrence (so that the sparse products gather B*Fin contiguous
+// floats per neighbour instead of Fin), row (b, m) = m*B + b.  Work items t enumerate pooled rows with the
+// sample index fastest in the interleaved case (coalesced basis reads); outputs keep the classic layout.
+struct RowMap {
+    int B, M, Mo, p, il;
+    __device__ __forceinline__ void decode(long long t, int& b, int& mo) const {
+        if (il) { mo = (int)(t / B); b = (int)(t - (long long)mo * B); }
+        else { b = (int)(t / Mo); mo = (int)(t - (long long)b * Mo); }
+    }
+    __device__ __forceinline__ long long xrow(int b, int mo, int j) const {
+        const int m = mo * p + j;
+        return il ? (long long)m * B + b : (long long)b * M + m;
+    }
+};
+
 // gram[0..Q) = sum_r X_q[r];  gram[Q + q*Q + q'] = sum_r X_q[r] X_q'[r]   (double, caller zeroes)
 template <int Q>
 __global__ void __launch_bounds__(256)
@@ -97,8 +113,9 @@ __global__ void bn_sums_from_gram_kernel(const double* __restrict__ gram, const 
 // One thread = one pooled row x 4 output features.
 template <int Q>
 __global__ void __launch_bounds__(256)
-smallconv_fwd_kernel(Planes P, const float* __restrict__ W, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     const float* __restrict__ bias, float* __restrict__ out, long long Rout, int Fout, int p, int pool, int act)
+smallconv_fwd_kernel(Planes P, RowMap rm, const float* __restrict__ W, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ bias, float* __restrict__ out,
+                     long long Rout, int Fout, int p, int pool, int act)
 {
     extern __shared__ float sm[];                    // Ws[Q][Fout], mu[Fout], rs[Fout], bs[Fout]
     float* Ws = sm;
@@ -123,13 +140,16 @@ smallconv_fwd_kernel(Planes P, const float* __restrict__ W, const float* __restr
     for (int q = 0; q < Q; ++q) cp[q] = P.col(q);
     const int Fin = P.Fin;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
-        const long long ro = g / Fv;
-        const int f0 = (int)(g - ro * Fv) * 4;
+        const long long t = g / Fv;
+        const int f0 = (int)(g - t * Fv) * 4;
+        int b, mo;
+        rm.decode(t, b, mo);
+        const long long ro = (long long)b * rm.Mo + mo;
         float acc[4];
 #pragma unroll
         for (int v = 0; v < 4; ++v) acc[v] = (pool == DSB200_POOL_MAX) ? -FLT_MAX : 0.f;
         for (int j = 0; j < p; ++j) {
-            const long long r = ro * p + j;
+            const long long r = rm.xrow(b, mo, j);
             float y[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
@@ -155,9 +175,9 @@ smallconv_fwd_kernel(Planes P, const float* __restrict__ W, const float* __restr
 // acc (double, zeroed): [0, Q*Fout) A[q][f] = sum_r X_q[r] gz[r,f];  then S1[f] = sum gz, S2[f] = sum gz*xhat
 template <int Q>
 __global__ void __launch_bounds__(256)
-smallconv_bwd_kernel(Planes P, const float* __restrict__ W, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     const float* __restrict__ bias, const float* __restrict__ dout, double* __restrict__ accg,
-                     long long Rout, int Fout, int p, int pool, int act)
+smallconv_bwd_kernel(Planes P, RowMap rm, const float* __restrict__ W, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ bias, const float* __restrict__ dout,
+                     double* __restrict__ accg, long long Rout, int Fout, int p, int pool, int act)
 {
     extern __shared__ float sm[];                    // Ws[Q][Fout], mu, rs, bs, red[(Q+2)*Fout]
     float* Ws = sm;
@@ -188,7 +208,10 @@ smallconv_bwd_kernel(Planes P, const float* __restrict__ W, const float* __restr
     const int Fin = P.Fin;
 #pragma unroll
     for (int v = 0; v < 4; ++v) { s1[v] = 0.f; s2[v] = 0.f; }
-    for (long long ro = (long long)blockIdx.x * rows_per_block + rl; ro < Rout; ro += (long long)gridDim.x * rows_per_block) {
+    for (long long t = (long long)blockIdx.x * rows_per_block + rl; t < Rout; t += (long long)gridDim.x * rows_per_block) {
+        int b, mo;
+        rm.decode(t, b, mo);
+        const long long ro = (long long)b * rm.Mo + mo;
         const float4 d4 = ldg4(dout + ro * Fout + f0);
         const float d[4] = {d4.x, d4.y, d4.z, d4.w};
         float best[4], gsel[4], xhsel[4];
@@ -197,7 +220,7 @@ smallconv_bwd_kernel(Planes P, const float* __restrict__ W, const float* __restr
         for (int v = 0; v < 4; ++v) { best[v] = -FLT_MAX; arg[v] = 0; gsel[v] = 0.f; xhsel[v] = 0.f; }
         const float inv = 1.f / (float)p;
         for (int j = 0; j < p; ++j) {
-            const long long r = ro * p + j;
+            const long long r = rm.xrow(b, mo, j);
             float x[Q], y[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
@@ -231,7 +254,7 @@ smallconv_bwd_kernel(Planes P, const float* __restrict__ W, const float* __restr
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
 #pragma unroll
-                for (int v = 0; v < 4; ++v) A[q][v] = fmaf(__ldg(cp[q] + (ro * p + arg[v]) * Fin), gsel[v], A[q][v]);
+                for (int v = 0; v < 4; ++v) A[q][v] = fmaf(__ldg(cp[q] + rm.xrow(b, mo, arg[v]) * Fin), gsel[v], A[q][v]);
             }
         }
     }
@@ -272,6 +295,26 @@ __global__ void smallconv_bwd_finalize_kernel(const double* __restrict__ acc, co
     if (q == 0 && dbias) dbias[f] = (float)S1;
 }
 
+// out[m][b][f] = x[b][m][f]: tiles of TM vertices staged through shared memory, coalesced on both sides
+__global__ void __launch_bounds__(256)
+interleave_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int M, int F, int TM)
+{
+    extern __shared__ float tile[];                  // [B][TM*F + 1]
+    const int m0 = blockIdx.x * TM;
+    const int tm = min(TM, M - m0);
+    const int w = tm * F, pitch = TM * F + 1;
+    for (int i = threadIdx.x; i < B * w; i += blockDim.x) {
+        const int b = i / w, r = i - b * w;
+        tile[b * pitch + r] = __ldg(x + ((long long)b * M + m0) * F + r);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B * w; i += blockDim.x) {
+        const int m = i / (B * F), r = i - m * (B * F);
+        const int b = r / F, f = r - b * F;
+        out[(long long)m0 * B * F + i] = tile[b * pitch + m * F + f];
+    }
+}
+
 static inline bool smallconv_ok(int Fin, int K, int Fout) { return Fin * K >= 1 && Fin * K <= QMAX && Fout % 4 == 0 && Fout <= 256 && 256 % (Fout / 4) == 0; }
 
 }  // namespace dsb200
@@ -281,13 +324,13 @@ using namespace dsb200;
 
 template <int Q> static void launch_gram(Planes P, long long R, double* gram, int grid, cudaStream_t st)
 { gram_kernel<Q><<<grid, 256, 0, st>>>(P, R, gram); }
-template <int Q> static void launch_fwd(Planes P, const float* W, const float* mean, const float* rstd, const float* bias,
+template <int Q> static void launch_fwd(Planes P, RowMap rm, const float* W, const float* mean, const float* rstd, const float* bias,
                                         float* out, long long Rout, int Fout, int p, int pool, int act, int grid, size_t smem, cudaStream_t st)
-{ smallconv_fwd_kernel<Q><<<grid, 256, smem, st>>>(P, W, mean, rstd, bias, out, Rout, Fout, p, pool, act); }
-template <int Q> static void launch_bwd(Planes P, const float* W, const float* mean, const float* rstd, const float* bias,
+{ smallconv_fwd_kernel<Q><<<grid, 256, smem, st>>>(P, rm, W, mean, rstd, bias, out, Rout, Fout, p, pool, act); }
+template <int Q> static void launch_bwd(Planes P, RowMap rm, const float* W, const float* mean, const float* rstd, const float* bias,
                                         const float* dout, double* acc, long long Rout, int Fout, int p, int pool, int act,
                                         int grid, size_t smem, cudaStream_t st)
-{ smallconv_bwd_kernel<Q><<<grid, 256, smem, st>>>(P, W, mean, rstd, bias, dout, acc, Rout, Fout, p, pool, act); }
+{ smallconv_bwd_kernel<Q><<<grid, 256, smem, st>>>(P, rm, W, mean, rstd, bias, dout, acc, Rout, Fout, p, pool, act); }
 
 #define DISPATCH_Q(Q, FN, ...) \
     switch (Q) { case 1: FN<1>(__VA_ARGS__); break; case 2: FN<2>(__VA_ARGS__); break; case 3: FN<3>(__VA_ARGS__); break; \
@@ -315,7 +358,7 @@ extern "C" int dsb200_bn_sums_from_gram(const double* gram, const float* W, int 
 
 extern "C" int dsb200_smallconv_fwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
                                     const float* bias, float* out, int B, int M, int Fin, int K, int Fout, int p, int pool,
-                                    int act, void* stream)
+                                    int act, int interleaved, void* stream)
 {
     DSB_REQUIRE(x0 && W && out && (K == 1 || xk) && B > 0 && M > 0 && p >= 1 && M % p == 0, "smallconv_fwd: bad arguments");
     DSB_REQUIRE(smallconv_ok(Fin, K, Fout), "smallconv_fwd: unsupported shape");
@@ -325,13 +368,14 @@ extern "C" int dsb200_smallconv_fwd(const float* x0, const float* xk, const floa
     const int Q = Fin * K;
     const size_t smem = (size_t)(Q + 3) * Fout * sizeof(float);
     const int grid = grid_for(Rout * (Fout / 4), 256, 8);
-    DISPATCH_Q(Q, launch_fwd, P, W, mean, rstd, bias, out, Rout, Fout, p, pool, act, grid, smem, STREAM);
+    RowMap rm{B, M, M / p, p, interleaved};
+    DISPATCH_Q(Q, launch_fwd, P, rm, W, mean, rstd, bias, out, Rout, Fout, p, pool, act, grid, smem, STREAM);
     DSB_LAUNCH_CHECK();
 }
 
 extern "C" int dsb200_smallconv_bwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
                                     const float* bias, const float* dout, double* acc, int B, int M, int Fin, int K, int Fout,
-                                    int p, int pool, int act, void* stream)
+                                    int p, int pool, int act, int interleaved, void* stream)
 {
     DSB_REQUIRE(x0 && W && dout && acc && (K == 1 || xk) && B > 0 && M > 0 && p >= 1 && M % p == 0, "smallconv_bwd: bad arguments");
     DSB_REQUIRE(smallconv_ok(Fin, K, Fout), "smallconv_bwd: unsupported shape");
@@ -341,7 +385,8 @@ extern "C" int dsb200_smallconv_bwd(const float* x0, const float* xk, const floa
     const size_t smem = (size_t)(2 * Q + 5) * Fout * sizeof(float);
     const int rpb = 256 / (Fout / 4);
     const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 4);
-    DISPATCH_Q(Q, launch_bwd, P, W, mean, rstd, bias, dout, acc, Rout, Fout, p, pool, act, grid, smem, STREAM);
+    RowMap rm{B, M, M / p, p, interleaved};
+    DISPATCH_Q(Q, launch_bwd, P, rm, W, mean, rstd, bias, dout, acc, Rout, Fout, p, pool, act, grid, smem, STREAM);
     DSB_LAUNCH_CHECK();
 }
 
@@ -353,5 +398,17 @@ extern "C" int dsb200_smallconv_bwd_finalize(const double* acc, const double* gr
     DSB_REQUIRE(!mean || (rstd && gram && count > 0), "smallconv_bwd_finalize: batch norm needs rstd, gram and count");
     const int n = Fin * K * Fout;
     smallconv_bwd_finalize_kernel<<<(n + 127) / 128, 128, 0, STREAM>>>(acc, gram, W, mean, rstd, count, Fin, K, Fout, dW, dbias);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_interleave(const float* x, float* out, int B, int M, int F, void* stream)
+{
+    DSB_REQUIRE(x && out && B > 0 && M > 0 && F > 0 && x != out, "interleave: bad arguments");
+    int TM = 8192 / (B * F);
+    if (TM < 1) TM = 1;
+    if (TM > M) TM = M;
+    const size_t smem = (size_t)B * (TM * F + 1) * sizeof(float);
+    DSB_REQUIRE(smem <= 48 * 1024, "interleave: B*F too large");
+    interleave_kernel<<<(M + TM - 1) / TM, 256, smem, STREAM>>>(x, out, B, M, F, TM);
     DSB_LAUNCH_CHECK();
 }

@@ -117,9 +117,9 @@ class _ChebStage(object):
             raise ValueError('{}: input [{}, {}] does not fit the Laplacian ({} vertices) / weights ({} features)'
                              .format(self.scope, M, Fin, self.graph.M, self.Fin))
         W = m._P.views[self.scope + '/weights']
-        basis = ops.cheb_basis(self.graph, x, self.K)                      # models.py:1049-1061
         if self.small:
-            return self._forward_small(x, basis, W, training, save)
+            return self._forward_small(x, W, training, save)
+        basis = ops.cheb_basis(self.graph, x, self.K)                      # models.py:1049-1061
         sums = None
         if self.bn and training:
             sums = torch.zeros(2 * self.Fout, dtype=torch.float64, device=x.device)
@@ -145,9 +145,13 @@ class _ChebStage(object):
             self.saved = (x, basis, y, mean, rstd, count, training)
         return out
 
-    def _forward_small(self, x, basis, W, training, save):
+    def _forward_small(self, x, W, training, save):
         m = self.m
         B, M, Fin = x.shape
+        shape = (B, M, Fin)
+        # sample-interleaved layout [M, B, Fin]: the sparse products gather B*Fin contiguous floats
+        x = ops.interleave(x)
+        basis = ops.cheb_basis(self.graph, x.view(1, M, B * Fin), self.K)
         count = float(B * M * m.world_size)
         mean = rstd = gram = None
         if self.bn:
@@ -155,30 +159,30 @@ class _ChebStage(object):
             mm, mv = m._state[self.scope + '/batch_normalization/moving_mean'], \
                 m._state[self.scope + '/batch_normalization/moving_variance']
             if training:
-                gram = ops.cheb_gram(x, basis, self.K)
+                gram = ops.cheb_gram(x, basis, self.K, shape)
                 m._allreduce(gram)
                 sums = ops.bn_sums_from_gram(gram, W, Fin, self.K, self.Fout)
                 ops.bn_finalize(sums, count, self.Fout, mean, rstd, mm, mv, BN_EPS, BN_MOMENTUM)
             else:
                 ops.bn_from_moving(mm, mv, mean, rstd, BN_EPS)
         b = m._P.views[self.scope + '/bias'] if self.has_bias else None
-        out = ops.smallconv_fwd(x, basis, W, self.K, self.Fout, mean, rstd, b, self.p, self.pool, self.act)
+        out = ops.smallconv_fwd(x, basis, W, self.K, self.Fout, mean, rstd, b, self.p, self.pool, self.act, shape)
         if self.keep is not None and self.keep != out.shape[1]:
             out = ops.vertex_resize(out, self.keep, 0.0)
         if save:
-            self.saved = (x, basis, gram, mean, rstd, count, training)
+            self.saved = (x, basis, gram, mean, rstd, count, training, shape)
         return out
 
     def _backward_small(self, dout):
         m = self.m
-        x, basis, gram, mean, rstd, count, training = self.saved
+        x, basis, gram, mean, rstd, count, training, shape = self.saved
         self.saved = None
-        B, M, Fin = x.shape
+        B, M, Fin = shape
         if self.keep is not None and dout.shape[1] != M // self.p:
             dout = ops.vertex_resize(dout, M // self.p, 0.0)
         W = m._P.views[self.scope + '/weights']
         b = m._P.views[self.scope + '/bias'] if self.has_bias else None
-        acc = ops.smallconv_bwd(x, basis, W, self.K, self.Fout, mean, rstd, b, dout, self.p, self.pool, self.act)
+        acc = ops.smallconv_bwd(x, basis, W, self.K, self.Fout, mean, rstd, b, dout, self.p, self.pool, self.act, shape)
         sync = self.bn and training
         if sync:
             m._allreduce(acc)
@@ -206,8 +210,9 @@ class _ChebStage(object):
         dy = dout
         if self.post:
             b = m._P.views[self.scope + '/bias'] if self.has_bias else None
-            dy, sums = ops.bn_act_pool_bwd(y, mean, rstd, b, dout, self.p, self.pool, self.act)
-            if self.bn and training:
+            two_pass = self.bn and training          # batch norm: sums first, then dy directly (gz never stored)
+            dy, sums = ops.bn_act_pool_bwd(y, mean, rstd, b, dout, self.p, self.pool, self.act, want_gz=not two_pass)
+            if two_pass:
                 m._allreduce(sums)
             if self.has_bias:
                     # with synchronised batch norm the sums are already global: pre-divide so that the
@@ -216,8 +221,8 @@ class _ChebStage(object):
                 ops.sums_to_float(sums, gb)
                 if self.bn and training and m.world_size > 1:
                     ops.scale(gb, 1.0 / m.world_size)            # the flat all-reduce sums it back
-            if self.bn and training:
-                ops.bn_bwd_apply(y, mean, rstd, sums, count, dy)
+            if two_pass:
+                dy = ops.bn_act_pool_bwd_dy(y, mean, rstd, b, dout, sums, count, self.p, self.pool, self.act)
         ops.contract_bwd_weight(x, basis, dy, m._P.gviews[self.scope + '/weights'], self.K)
         if not need_dx:
             return None

@@ -81,12 +81,22 @@ def bn_act_pool_fwd(y, mean, rstd, bias, p, pool, act):
     return out
 
 
-def bn_act_pool_bwd(y, mean, rstd, bias, dout, p, pool, act):
+def bn_act_pool_bwd(y, mean, rstd, bias, dout, p, pool, act, want_gz=True):
+    """gz = dLoss/d(normalised + bias) and the per-feature sums (sum gz, sum gz*xhat); with
+    want_gz=False only the sums (pass 1 of the batch-norm backward)."""
     B, M, F = y.shape
-    gz = _new((B, M, F), y)
+    gz = _new((B, M, F), y) if want_gz else None
     sums = torch.zeros(2 * F, dtype=torch.float64, device=y.device)
     call('bn_act_pool_bwd', y, mean, rstd, bias, dout, gz, sums, B, M, F, p, POOL[pool], ACT[act])
     return gz, sums
+
+
+def bn_act_pool_bwd_dy(y, mean, rstd, bias, dout, sums, count, p, pool, act):
+    """Pass 2 of the batch-norm backward: dy from y, dout and the (all-reduced) sums."""
+    B, M, F = y.shape
+    dy = _new((B, M, F), y)
+    call('bn_act_pool_bwd_dy', y, mean, rstd, bias, dout, sums, float(count), dy, B, M, F, p, POOL[pool], ACT[act])
+    return dy
 
 
 def bn_bwd_apply(y, mean, rstd, sums, count, gz):
@@ -227,9 +237,9 @@ def smallconv_supported(Fin, K, Fout):
     return bool(LIB.load().dsb200_smallconv_supported(Fin, K, Fout))
 
 
-def cheb_gram(x, basis, K):
+def cheb_gram(x, basis, K, shape=None):
     """Column sums and Gram matrix of the Chebyshev basis (double[Q + Q*Q], Q = K*Fin)."""
-    B, M, Fin = x.shape
+    B, M, Fin = shape if shape is not None else x.shape
     Q = K * Fin
     gram = torch.zeros(Q + Q * Q, dtype=torch.float64, device=x.device)
     call('cheb_gram', x, basis, B * M, Fin, K, gram)
@@ -242,17 +252,28 @@ def bn_sums_from_gram(gram, W, Fin, K, Fout):
     return sums
 
 
-def smallconv_fwd(x, basis, W, K, Fout, mean, rstd, bias, p, pool, act):
-    B, M, Fin = x.shape
-    out = _new((B, M // p, Fout), x)
-    call('smallconv_fwd', x, basis, W, mean, rstd, bias, out, B, M, Fin, K, Fout, p, POOL[pool], ACT[act])
+def interleave(x):
+    """[B, M, F] -> [M, B, F] (sample-interleaved layout for the sparse products of a narrow input layer)."""
+    B, M, F = x.shape
+    out = _new((M, B, F), x)
+    call('interleave', x, out, B, M, F)
     return out
 
 
-def smallconv_bwd(x, basis, W, K, Fout, mean, rstd, bias, dout, p, pool, act):
-    B, M, Fin = x.shape
+def smallconv_fwd(x, basis, W, K, Fout, mean, rstd, bias, p, pool, act, shape=None):
+    """`shape` = (B, M, Fin) when x / basis are in the sample-interleaved layout [M, B, Fin]."""
+    B, M, Fin = shape if shape is not None else x.shape
+    out = _new((B, M // p, Fout), x)
+    call('smallconv_fwd', x, basis, W, mean, rstd, bias, out, B, M, Fin, K, Fout, p, POOL[pool], ACT[act],
+         1 if shape is not None else 0)
+    return out
+
+
+def smallconv_bwd(x, basis, W, K, Fout, mean, rstd, bias, dout, p, pool, act, shape=None):
+    B, M, Fin = shape if shape is not None else x.shape
     acc = torch.zeros((K * Fin + 2) * Fout, dtype=torch.float64, device=x.device)
-    call('smallconv_bwd', x, basis, W, mean, rstd, bias, dout, acc, B, M, Fin, K, Fout, p, POOL[pool], ACT[act])
+    call('smallconv_bwd', x, basis, W, mean, rstd, bias, dout, acc, B, M, Fin, K, Fout, p, POOL[pool], ACT[act],
+         1 if shape is not None else 0)
     return acc
 
 

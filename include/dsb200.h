@@ -104,15 +104,20 @@ int dsb200_smallconv_supported(int Fin, int K, int Fout);
 int dsb200_cheb_gram(const float* x0, const float* xk, long long R, int Fin, int K, double* gram, void* stream);
 /* batch-norm sums (double[2*Fout]: sum y, sum y^2) of y = Xcat W from the Gram matrix */
 int dsb200_bn_sums_from_gram(const double* gram, const float* W, int Fin, int K, int Fout, double* sums, void* stream);
-/* out [B, M/p, Fout] = pool(act((Xcat W - mean) * rstd + bias)); mean/rstd/bias may be NULL */
+/* out [B, M/p, Fout] = pool(act((Xcat W - mean) * rstd + bias)); mean/rstd/bias may be NULL.
+ * interleaved != 0: the basis planes are in the sample-interleaved layout [M, B, Fin] (the input was
+ * passed through dsb200_interleave before the recurrence, which then ran on 1 "sample" of B*Fin features);
+ * outputs / dout keep the classic [B, M/p, Fout] layout. */
 int dsb200_smallconv_fwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
                          const float* bias, float* out, int B, int M, int Fin, int K, int Fout, int p, int pool,
-                         int act, void* stream);
+                         int act, int interleaved, void* stream);
+/* out [M, B, F] = transpose of x [B, M, F] over (sample, vertex) */
+int dsb200_interleave(const float* x, float* out, int B, int M, int F, void* stream);
 /* acc (double[(Q+2)*Fout], zeroed): A[q][f] = sum_r X_q[r] gz[r,f], then S1[f] = sum gz, S2[f] = sum gz*xhat,
  * with gz = dLoss/d(normalised + bias) recomputed from the basis and dout [B, M/p, Fout] */
 int dsb200_smallconv_bwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
                          const float* bias, const float* dout, double* acc, int B, int M, int Fin, int K, int Fout,
-                         int p, int pool, int act, void* stream);
+                         int p, int pool, int act, int interleaved, void* stream);
 /* dW (+=) and dbias (=, may be NULL) from acc (already summed over ranks) and the Gram matrix; with
  * mean == NULL there is no batch norm and dW += A. */
 int dsb200_smallconv_bwd_finalize(const double* acc, const double* gram, const float* W, const float* mean,
@@ -134,10 +139,16 @@ int dsb200_bn_from_moving(const float* moving_mean, const float* moving_var, int
 int dsb200_bn_act_pool_fwd(const float* y, const float* mean, const float* rstd, const float* bias,
                            float* out, int B, int M, int F, int p, int pool, int act, void* stream);
 /* backward of the same chain: gz [B,M,F] = dLoss/dz, and sums_bwd (double[2*F], zeroed by the
- * caller) += (sum gz, sum gz * xhat) per feature; sum gz is also the bias gradient. */
+ * caller) += (sum gz, sum gz * xhat) per feature; sum gz is also the bias gradient.  gz == NULL:
+ * accumulate the sums only (pass 1 of the batch-norm backward; nothing is written). */
 int dsb200_bn_act_pool_bwd(const float* y, const float* mean, const float* rstd, const float* bias,
                            const float* dout, float* gz, double* sums_bwd,
                            int B, int M, int F, int p, int pool, int act, void* stream);
+/* pass 2 of the batch-norm backward without a stored gz: dy = rstd * (gz - S1/count - xhat * S2/count)
+ * with gz recomputed from y and dout; sums_bwd already summed over ranks */
+int dsb200_bn_act_pool_bwd_dy(const float* y, const float* mean, const float* rstd, const float* bias,
+                              const float* dout, const double* sums_bwd, double count, float* dy,
+                              int B, int M, int F, int p, int pool, int act, void* stream);
 /* dy = rstd * (gz - S1/count - xhat * S2/count), in place on gz (batch-norm backward);
  * dbias (float[F], may be NULL) receives S1. */
 int dsb200_bn_bwd_apply(const float* y, const float* mean, const float* rstd, const double* sums_bwd,

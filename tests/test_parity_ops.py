@@ -186,6 +186,13 @@ def test_bn_bias_act_pool_chain(dev, F, p, pool, act, bn):
     if bn:
         ops.bn_bwd_apply(yd, mean, rstd, s, count, gz)
     assert_close(gz, y.grad, 2 * RTOL, 'dy')
+    if bn:
+        # two-pass variant used by the model: sums only, then dy straight from y and dout
+        none, s2 = ops.bn_act_pool_bwd(yd, mean, rstd, bd, dout.to(dev), p, pool, act, want_gz=False)
+        assert none is None
+        assert_close(s2, s, 1e-6, 'sums (pass 1)')
+        dy = ops.bn_act_pool_bwd_dy(yd, mean, rstd, bd, dout.to(dev), s2, count, p, pool, act)
+        assert_close(dy, y.grad, 2 * RTOL, 'dy (pass 2)')
 
 
 @pytest.mark.parametrize('kind', ['mean', 'var', 'meanvar', 'max'])
