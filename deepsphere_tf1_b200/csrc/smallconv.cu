@@ -269,6 +269,151 @@ smallconv_bwd_kernel(Planes P, RowMap rm, const float* __restrict__ W, const flo
     for (int i = threadIdx.x; i < (Q + 2) * Fout; i += blockDim.x) atomicAdd(accg + i, (double)red[i]);
 }
 
+// ---- fast path: ReLU + max pooling over 4 siblings (the configuration of every BASELINE classifier).
+// One thread = one pooled row x 8 output features.  relu and max commute with the positive affine map of
+// batch norm, so the forward keeps a running max of z = y*rstd + c and clamps once; it also records which
+// sibling won (1 byte per output).  The backward then needs no recomputation of y at all: with
+// out = relu(xhat + b) the gradient is gz = dout * (out > 0), xhat = out - b where it matters, and the
+// arg-max byte selects the basis row for A = X^T gz.
+template <int Q>
+__global__ void __launch_bounds__(256)
+smallconv_fwd_fast_kernel(Planes P, RowMap rm, const float* __restrict__ W, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, const float* __restrict__ bias, float* __restrict__ out,
+                          uint8_t* __restrict__ argmax, long long Rout, int Fout)
+{
+    extern __shared__ float sm[];                    // Ws[Q][Fout], rs[Fout], cs[Fout]
+    float* Ws = sm;
+    float* rs = sm + Q * Fout;
+    float* cs = rs + Fout;
+    for (int i = threadIdx.x; i < Q * Fout; i += blockDim.x) {
+        const int q = i / Fout, f = i - q * Fout;
+        const int k = q / P.Fin, fi = q - k * P.Fin;
+        Ws[i] = __ldg(W + (fi * P.K + k) * Fout + f);
+    }
+    for (int f = threadIdx.x; f < Fout; f += blockDim.x) {
+        const float r = rstd ? __ldg(rstd + f) : 1.f;
+        rs[f] = r;
+        cs[f] = (bias ? __ldg(bias + f) : 0.f) - (mean ? __ldg(mean + f) : 0.f) * r;      // z = y*r + c
+    }
+    __syncthreads();
+    const int Fg = Fout / 8;
+    const long long total = Rout * Fg;
+    const float* cp[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) cp[q] = P.col(q);
+    const int Fin = P.Fin;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
+        const long long t = g / Fg;
+        const int f0 = (int)(g - t * Fg) * 8;
+        int b, mo;
+        rm.decode(t, b, mo);
+        float x[4][Q];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long r = rm.xrow(b, mo, j) * Fin;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) x[j][q] = __ldg(cp[q] + r);
+        }
+        float y[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int v = 0; v < 8; ++v) y[j][v] = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const float4 w0 = *reinterpret_cast<const float4*>(Ws + q * Fout + f0);
+            const float4 w1 = *reinterpret_cast<const float4*>(Ws + q * Fout + f0 + 4);
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int v = 0; v < 8; ++v) y[j][v] = fmaf(x[j][q], w[v], y[j][v]);
+        }
+        float o[8];
+        uint32_t a0 = 0, a1 = 0;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const float r = rs[f0 + v], c = cs[f0 + v];
+            float best = fmaf(y[0][v], r, c);
+            uint32_t arg = 0;
+#pragma unroll
+            for (int j = 1; j < 4; ++j) {
+                const float z = fmaf(y[j][v], r, c);
+                if (z > best) { best = z; arg = j; }
+            }
+            o[v] = fmaxf(best, 0.f);
+            if (v < 4) a0 |= arg << (8 * v); else a1 |= arg << (8 * (v - 4));
+        }
+        const long long ro = (long long)b * rm.Mo + mo;
+        st4(out + ro * Fout + f0, make_float4(o[0], o[1], o[2], o[3]));
+        st4(out + ro * Fout + f0 + 4, make_float4(o[4], o[5], o[6], o[7]));
+        if (argmax) *reinterpret_cast<uint2*>(argmax + ro * Fout + f0) = make_uint2(a0, a1);
+    }
+}
+
+template <int Q>
+__global__ void __launch_bounds__(256)
+smallconv_bwd_fast_kernel(Planes P, RowMap rm, const float* __restrict__ bias, const float* __restrict__ out,
+                          const uint8_t* __restrict__ argmax, const float* __restrict__ dout,
+                          double* __restrict__ accg, long long Rout, int Fout)
+{
+    extern __shared__ float red[];                   // [(Q+2)*Fout]
+    for (int i = threadIdx.x; i < (Q + 2) * Fout; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int Fg = Fout / 8;
+    const int rows_per_block = blockDim.x / Fg;      // blockDim.x % Fg == 0
+    const int f0 = (threadIdx.x % Fg) * 8, rl = threadIdx.x / Fg;
+    float A[Q][8], s1[8], s2[8], bs[8];
+    const float* cp[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        cp[q] = P.col(q);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) A[q][v] = 0.f;
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) { s1[v] = 0.f; s2[v] = 0.f; bs[v] = bias ? __ldg(bias + f0 + v) : 0.f; }
+    const int Fin = P.Fin;
+    for (long long t = (long long)blockIdx.x * rows_per_block + rl; t < Rout; t += (long long)gridDim.x * rows_per_block) {
+        int b, mo;
+        rm.decode(t, b, mo);
+        const long long ro = (long long)b * rm.Mo + mo;
+        const float4 d0 = ldg4(dout + ro * Fout + f0), d1 = ldg4(dout + ro * Fout + f0 + 4);
+        const float4 o0 = ldg4(out + ro * Fout + f0), o1 = ldg4(out + ro * Fout + f0 + 4);
+        const uint2 ab = __ldg(reinterpret_cast<const uint2*>(argmax + ro * Fout + f0));
+        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        float x[4][Q];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const long long r = rm.xrow(b, mo, j) * Fin;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) x[j][q] = __ldg(cp[q] + r);
+        }
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const float gz = o[v] > 0.f ? d[v] : 0.f;
+            const uint32_t arg = ((v < 4 ? ab.x >> (8 * v) : ab.y >> (8 * (v - 4))) & 3u);
+            s1[v] += gz;
+            s2[v] = fmaf(gz, o[v] - bs[v], s2[v]);           // xhat = out - bias wherever gz != 0
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float xs = arg == 0 ? x[0][q] : arg == 1 ? x[1][q] : arg == 2 ? x[2][q] : x[3][q];
+                A[q][v] = fmaf(xs, gz, A[q][v]);
+            }
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) atomicAdd(&red[q * Fout + f0 + v], A[q][v]);
+        atomicAdd(&red[Q * Fout + f0 + v], s1[v]);
+        atomicAdd(&red[(Q + 1) * Fout + f0 + v], s2[v]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (Q + 2) * Fout; i += blockDim.x) atomicAdd(accg + i, (double)red[i]);
+}
+
 // dW[fi*K+k, f] += rstd_f (A_qf - S1_f/n s_q - S2_f/n rstd_f (sum_q' G_qq' W_q'f - mean_f s_q));  dbias_f = S1_f
 __global__ void smallconv_bwd_finalize_kernel(const double* __restrict__ acc, const double* __restrict__ gram,
                                               const float* __restrict__ W, const float* __restrict__ mean,
@@ -315,6 +460,10 @@ interleave_kernel(const float* __restrict__ x, float* __restrict__ out, int B, i
     }
 }
 
+static inline bool smallconv_fast_ok(int Fout, int p, int pool, int act) {
+    return Fout % 8 == 0 && 256 % (Fout / 8) == 0 && p == 4 && pool == DSB200_POOL_MAX && act == DSB200_ACT_RELU;
+}
+
 static inline bool smallconv_ok(int Fin, int K, int Fout) { return Fin * K >= 1 && Fin * K <= QMAX && Fout % 4 == 0 && Fout <= 256 && 256 % (Fout / 4) == 0; }
 
 }  // namespace dsb200
@@ -327,6 +476,14 @@ template <int Q> static void launch_gram(Planes P, long long R, double* gram, in
 template <int Q> static void launch_fwd(Planes P, RowMap rm, const float* W, const float* mean, const float* rstd, const float* bias,
                                         float* out, long long Rout, int Fout, int p, int pool, int act, int grid, size_t smem, cudaStream_t st)
 { smallconv_fwd_kernel<Q><<<grid, 256, smem, st>>>(P, rm, W, mean, rstd, bias, out, Rout, Fout, p, pool, act); }
+template <int Q> static void launch_fwd_fast(Planes P, RowMap rm, const float* W, const float* mean, const float* rstd,
+                                             const float* bias, float* out, uint8_t* argmax, long long Rout, int Fout,
+                                             int grid, size_t smem, cudaStream_t st)
+{ smallconv_fwd_fast_kernel<Q><<<grid, 256, smem, st>>>(P, rm, W, mean, rstd, bias, out, argmax, Rout, Fout); }
+template <int Q> static void launch_bwd_fast(Planes P, RowMap rm, const float* bias, const float* out, const uint8_t* argmax,
+                                             const float* dout, double* acc, long long Rout, int Fout, int grid, size_t smem,
+                                             cudaStream_t st)
+{ smallconv_bwd_fast_kernel<Q><<<grid, 256, smem, st>>>(P, rm, bias, out, argmax, dout, acc, Rout, Fout); }
 template <int Q> static void launch_bwd(Planes P, RowMap rm, const float* W, const float* mean, const float* rstd, const float* bias,
                                         const float* dout, double* acc, long long Rout, int Fout, int p, int pool, int act,
                                         int grid, size_t smem, cudaStream_t st)
@@ -338,6 +495,7 @@ template <int Q> static void launch_bwd(Planes P, RowMap rm, const float* W, con
                  case 7: FN<7>(__VA_ARGS__); break; default: FN<8>(__VA_ARGS__); break; }
 
 extern "C" int dsb200_smallconv_supported(int Fin, int K, int Fout) { return smallconv_ok(Fin, K, Fout) ? 1 : 0; }
+extern "C" int dsb200_smallconv_has_argmax(int Fout, int p, int pool, int act) { return smallconv_fast_ok(Fout, p, pool, act) ? 1 : 0; }
 
 extern "C" int dsb200_cheb_gram(const float* x0, const float* xk, long long R, int Fin, int K, double* gram, void* stream)
 {
@@ -358,7 +516,7 @@ extern "C" int dsb200_bn_sums_from_gram(const double* gram, const float* W, int 
 
 extern "C" int dsb200_smallconv_fwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
                                     const float* bias, float* out, int B, int M, int Fin, int K, int Fout, int p, int pool,
-                                    int act, int interleaved, void* stream)
+                                    int act, int interleaved, uint8_t* argmax, void* stream)
 {
     DSB_REQUIRE(x0 && W && out && (K == 1 || xk) && B > 0 && M > 0 && p >= 1 && M % p == 0, "smallconv_fwd: bad arguments");
     DSB_REQUIRE(smallconv_ok(Fin, K, Fout), "smallconv_fwd: unsupported shape");
@@ -369,13 +527,21 @@ extern "C" int dsb200_smallconv_fwd(const float* x0, const float* xk, const floa
     const size_t smem = (size_t)(Q + 3) * Fout * sizeof(float);
     const int grid = grid_for(Rout * (Fout / 4), 256, 8);
     RowMap rm{B, M, M / p, p, interleaved};
+    if (smallconv_fast_ok(Fout, p, pool, act)) {
+        const size_t smf = (size_t)(Q + 2) * Fout * sizeof(float);
+        const int gf = grid_for(Rout * (Fout / 8), 256, 8);
+        DISPATCH_Q(Q, launch_fwd_fast, P, rm, W, mean, rstd, bias, out, argmax, Rout, Fout, gf, smf, STREAM);
+        DSB_LAUNCH_CHECK();
+    }
+    DSB_REQUIRE(!argmax, "smallconv_fwd: the arg-max record needs relu + max pooling over 4 vertices");
     DISPATCH_Q(Q, launch_fwd, P, rm, W, mean, rstd, bias, out, Rout, Fout, p, pool, act, grid, smem, STREAM);
     DSB_LAUNCH_CHECK();
 }
 
 extern "C" int dsb200_smallconv_bwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
                                     const float* bias, const float* dout, double* acc, int B, int M, int Fin, int K, int Fout,
-                                    int p, int pool, int act, int interleaved, void* stream)
+                                    int p, int pool, int act, int interleaved, const float* out, const uint8_t* argmax,
+                                    void* stream)
 {
     DSB_REQUIRE(x0 && W && dout && acc && (K == 1 || xk) && B > 0 && M > 0 && p >= 1 && M % p == 0, "smallconv_bwd: bad arguments");
     DSB_REQUIRE(smallconv_ok(Fin, K, Fout), "smallconv_bwd: unsupported shape");
@@ -386,6 +552,14 @@ extern "C" int dsb200_smallconv_bwd(const float* x0, const float* xk, const floa
     const int rpb = 256 / (Fout / 4);
     const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 4);
     RowMap rm{B, M, M / p, p, interleaved};
+    if (out && argmax) {
+        DSB_REQUIRE(smallconv_fast_ok(Fout, p, pool, act), "smallconv_bwd: arg-max path needs relu + max pooling over 4 vertices");
+        const size_t smf = (size_t)(Q + 2) * Fout * sizeof(float);
+        const int rpf = 256 / (Fout / 8);
+        const int gf = grid_for((Rout + rpf - 1) / rpf * 256, 256, 4);
+        DISPATCH_Q(Q, launch_bwd_fast, P, rm, bias, out, argmax, dout, acc, Rout, Fout, gf, smf, STREAM);
+        DSB_LAUNCH_CHECK();
+    }
     DISPATCH_Q(Q, launch_bwd, P, rm, W, mean, rstd, bias, dout, acc, Rout, Fout, p, pool, act, grid, smem, STREAM);
     DSB_LAUNCH_CHECK();
 }

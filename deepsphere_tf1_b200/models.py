@@ -166,23 +166,26 @@ class _ChebStage(object):
             else:
                 ops.bn_from_moving(mm, mv, mean, rstd, BN_EPS)
         b = m._P.views[self.scope + '/bias'] if self.has_bias else None
-        out = ops.smallconv_fwd(x, basis, W, self.K, self.Fout, mean, rstd, b, self.p, self.pool, self.act, shape)
+        want_arg = save and ops.smallconv_has_argmax(self.Fout, self.p, self.pool, self.act)
+        out, arg = ops.smallconv_fwd(x, basis, W, self.K, self.Fout, mean, rstd, b, self.p, self.pool, self.act, shape,
+                                     want_argmax=want_arg)
+        if save:
+            self.saved = (x, basis, gram, mean, rstd, count, training, shape, out if want_arg else None, arg)
         if self.keep is not None and self.keep != out.shape[1]:
             out = ops.vertex_resize(out, self.keep, 0.0)
-        if save:
-            self.saved = (x, basis, gram, mean, rstd, count, training, shape)
         return out
 
     def _backward_small(self, dout):
         m = self.m
-        x, basis, gram, mean, rstd, count, training, shape = self.saved
+        x, basis, gram, mean, rstd, count, training, shape, out, arg = self.saved
         self.saved = None
         B, M, Fin = shape
         if self.keep is not None and dout.shape[1] != M // self.p:
             dout = ops.vertex_resize(dout, M // self.p, 0.0)
         W = m._P.views[self.scope + '/weights']
         b = m._P.views[self.scope + '/bias'] if self.has_bias else None
-        acc = ops.smallconv_bwd(x, basis, W, self.K, self.Fout, mean, rstd, b, dout, self.p, self.pool, self.act, shape)
+        acc = ops.smallconv_bwd(x, basis, W, self.K, self.Fout, mean, rstd, b, dout, self.p, self.pool, self.act, shape,
+                                out=out, argmax=arg)
         sync = self.bn and training
         if sync:
             m._allreduce(acc)

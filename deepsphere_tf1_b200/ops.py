@@ -260,20 +260,27 @@ def interleave(x):
     return out
 
 
-def smallconv_fwd(x, basis, W, K, Fout, mean, rstd, bias, p, pool, act, shape=None):
-    """`shape` = (B, M, Fin) when x / basis are in the sample-interleaved layout [M, B, Fin]."""
+def smallconv_has_argmax(Fout, p, pool, act):
+    from ._lib import LIB
+    return bool(LIB.load().dsb200_smallconv_has_argmax(Fout, p, POOL[pool], ACT[act]))
+
+
+def smallconv_fwd(x, basis, W, K, Fout, mean, rstd, bias, p, pool, act, shape=None, want_argmax=False):
+    """`shape` = (B, M, Fin) when x / basis are in the sample-interleaved layout [M, B, Fin].
+    Returns (out, argmax | None)."""
     B, M, Fin = shape if shape is not None else x.shape
     out = _new((B, M // p, Fout), x)
+    arg = torch.empty((B, M // p, Fout), dtype=torch.uint8, device=x.device) if want_argmax else None
     call('smallconv_fwd', x, basis, W, mean, rstd, bias, out, B, M, Fin, K, Fout, p, POOL[pool], ACT[act],
-         1 if shape is not None else 0)
-    return out
+         1 if shape is not None else 0, arg)
+    return out, arg
 
 
-def smallconv_bwd(x, basis, W, K, Fout, mean, rstd, bias, dout, p, pool, act, shape=None):
+def smallconv_bwd(x, basis, W, K, Fout, mean, rstd, bias, dout, p, pool, act, shape=None, out=None, argmax=None):
     B, M, Fin = shape if shape is not None else x.shape
     acc = torch.zeros((K * Fin + 2) * Fout, dtype=torch.float64, device=x.device)
     call('smallconv_bwd', x, basis, W, mean, rstd, bias, dout, acc, B, M, Fin, K, Fout, p, POOL[pool], ACT[act],
-         1 if shape is not None else 0)
+         1 if shape is not None else 0, out, argmax)
     return acc
 
 

@@ -110,14 +110,19 @@ int dsb200_bn_sums_from_gram(const double* gram, const float* W, int Fin, int K,
  * outputs / dout keep the classic [B, M/p, Fout] layout. */
 int dsb200_smallconv_fwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
                          const float* bias, float* out, int B, int M, int Fin, int K, int Fout, int p, int pool,
-                         int act, int interleaved, void* stream);
+                         int act, int interleaved, uint8_t* argmax, void* stream);
+/* relu + max pooling over 4 vertices (dsb200_smallconv_has_argmax != 0): the forward can record the winning
+ * sibling (argmax, uint8 [B, M/p, Fout], may be NULL); given `out` and `argmax` the backward needs no
+ * recomputation of y (gz = dout * (out > 0), xhat = out - bias). */
+int dsb200_smallconv_has_argmax(int Fout, int p, int pool, int act);
 /* out [M, B, F] = transpose of x [B, M, F] over (sample, vertex) */
 int dsb200_interleave(const float* x, float* out, int B, int M, int F, void* stream);
 /* acc (double[(Q+2)*Fout], zeroed): A[q][f] = sum_r X_q[r] gz[r,f], then S1[f] = sum gz, S2[f] = sum gz*xhat,
  * with gz = dLoss/d(normalised + bias) recomputed from the basis and dout [B, M/p, Fout] */
 int dsb200_smallconv_bwd(const float* x0, const float* xk, const float* W, const float* mean, const float* rstd,
                          const float* bias, const float* dout, double* acc, int B, int M, int Fin, int K, int Fout,
-                         int p, int pool, int act, int interleaved, void* stream);
+                         int p, int pool, int act, int interleaved, const float* out, const uint8_t* argmax,
+                         void* stream);
 /* dW (+=) and dbias (=, may be NULL) from acc (already summed over ranks) and the Gram matrix; with
  * mean == NULL there is no batch norm and dW += A. */
 int dsb200_smallconv_bwd_finalize(const double* acc, const double* gram, const float* W, const float* mean,
