@@ -344,8 +344,14 @@ static inline bool small_path(int Q, int Fout) { return Q <= 16 && Fout % 4 == 0
 
 using namespace dsb200;
 
+extern "C" long long dsb200_contract_workspace_bytes(int Fin, int K, int Fout)
+{
+    return (long long)tc::contract_workspace_bytes(Fin, K, Fout);
+}
+
 extern "C" int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const float* W, float* Y,
-                                        long long R, int Fin, int K, int Fout, double* bn_sums, void* stream)
+                                        long long R, int Fin, int K, int Fout, double* bn_sums, void* workspace,
+                                        void* stream)
 {
     DSB_REQUIRE(R > 0 && Fin > 0 && K > 0 && Fout > 0, "contract_fwd: bad shape");
     DSB_REQUIRE(x0 && W && Y && (K == 1 || xk), "contract_fwd: null pointer");
@@ -353,7 +359,7 @@ extern "C" int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const 
     Planar A{x0, xk, Fin, R * (long long)Fin};
     const int Q = K * Fin;
     if (g_use_tc.load(std::memory_order_relaxed) && Q > 16) {
-        const int rc = tc::contract_fwd_tc(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, s);
+        const int rc = tc::contract_fwd_tc(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, workspace, s);
         if (rc != 1) return rc;                            // 1 = shape not supported on the tensor-core path
     }
     if (small_path(Q, Fout) && (((uintptr_t)Y & 15) == 0)) {
@@ -369,12 +375,12 @@ extern "C" int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const 
 }
 
 extern "C" int dsb200_cheb_contract_bwd_data(const float* dY, const float* W, float* G,
-                                             long long R, int Fin, int K, int Fout, void* stream)
+                                             long long R, int Fin, int K, int Fout, void* workspace, void* stream)
 {
     DSB_REQUIRE(R > 0 && Fin > 0 && K > 0 && Fout > 0, "contract_bwd_data: bad shape");
     DSB_REQUIRE(dY && W && G, "contract_bwd_data: null pointer");
     if (g_use_tc.load(std::memory_order_relaxed)) {
-        const int rc = tc::contract_bwd_data_tc(dY, W, G, R, Fin, K, Fout, (cudaStream_t)stream);
+        const int rc = tc::contract_bwd_data_tc(dY, W, G, R, Fin, K, Fout, workspace, (cudaStream_t)stream);
         if (rc != 1) return rc;
     }
     Planar A{dY, nullptr, Fout, 0};

@@ -51,27 +51,89 @@ int make_tmap_f32(CUtensorMap* out, const float* base, long long cols, long long
 }
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 320;
 constexpr int kMaxStages = 8;
 enum { MODE_FWD = 0, MODE_BWD_DATA = 1 };
+
+// warp roles of the row-GEMM kernel
+constexpr int kRgThreads = 448;          // 14 warps
+constexpr int kWarpTma = 0, kWarpMma = 1, kWarpSplit0 = 2, kWarpEpi0 = 10;   // split: warps 2-5 and 6-9
 
 struct alignas(64) RowGemmParams {
     CUtensorMap tmA0;          // plane 0 (x0, or dY for the data gradient)
     CUtensorMap tmAk;          // planes 1..K-1 (forward only)
     const float* W;            // [Fin*K, Fout], row = fi*K + k
+    const float* wpack;        // pre-split weights in the shared-memory image layout (pack_w_kernel), or NULL
     float* out;                // Y [R, Fout]  |  G [K][R][Fin]
     double* bn_sums;           // forward only, may be NULL
     long long R;
     int Fin, K, Fout;
     int kc, nchunk, nkb;       // reduction: chunk width, chunks per plane, k-blocks per tile
+    int G;                     // k-blocks per pipeline stage
     int Npad, Nreal, n0;       // accumulator width (multiple of 16), valid columns, first column of this n-block
     int swz;                   // 1 / 2 / 3 = 32 / 64 / 128-byte swizzle (row of a tile = kc*4 bytes)
     int nstages, acc_stages;
     int ntiles;
 };
 
-template <int MODE, int SUMS_N>
-__global__ void __launch_bounds__(kThreads, 1)
+// Element (j, n2, kk) of the weight image: k-block j, row n2 in [0, 2*Npad) (hi rows then lo rows), column kk.
+template <int MODE>
+__device__ __forceinline__ float w_image_value(const RowGemmParams& p, int j, int n2, int kk)
+{
+    const int half = n2 >= p.Npad;
+    const int n = n2 - half * p.Npad;
+    float w = 0.f;
+    if (n < p.Nreal) {
+        if (MODE == MODE_FWD) {
+            const int k = j / p.nchunk, c = j - k * p.nchunk;
+            w = __ldg(p.W + ((long long)(c * p.kc + kk) * p.K + k) * p.Fout + (p.n0 + n));
+        } else {
+            const int q = p.n0 + n;
+            const int kq = q / p.Fin, fi = q - kq * p.Fin;
+            w = __ldg(p.W + ((long long)fi * p.K + kq) * p.Fout + (j * p.kc + kk));
+        }
+    }
+    const float hi = to_tf32(w);
+    return half ? to_tf32(w - hi) : hi;
+}
+__device__ __forceinline__ uint32_t w_image_offset(const RowGemmParams& p, int j, int n2, int kk)
+{
+    const int rowbytes = p.kc * 4;
+    const int chunk = (kk >> 2) ^ swizzle_xor(n2, p.swz);
+    return (uint32_t)j * (2u * p.Npad * rowbytes) + (uint32_t)n2 * rowbytes + chunk * 16 + (kk & 3) * 4;
+}
+
+// Weights -> TF32 hi / lo, canonical K-major swizzled layout, once per launch into global scratch.
+template <int MODE>
+__global__ void __launch_bounds__(256) pack_w_kernel(const __grid_constant__ RowGemmParams p, float* __restrict__ image)
+{
+    const int per_blk = 2 * p.Npad * p.kc;
+    const int total = p.nkb * per_blk;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int j = idx / per_blk;
+        const int rem = idx - j * per_blk;
+        const int n2 = rem / p.kc, kk = rem - n2 * p.kc;
+        image[w_image_offset(p, j, n2, kk) >> 2] = w_image_value<MODE>(p, j, n2, kk);
+    }
+}
+
+// Column sums over the 32 rows held by the lanes of a warp: v[i] = value of column i in this lane's row.
+// Transposing butterfly (31 shuffles): afterwards lane l holds the sum of column l in v[0].
+__device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane)
+{
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int i = 0; i < s; ++i) {
+            const float keep = up ? v[i + s] : v[i];
+            const float send = up ? v[i] : v[i + s];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+    }
+}
+
+template <int MODE, bool SUMS>
+__global__ void __launch_bounds__(kRgThreads, 1)
 rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -82,18 +144,20 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
     const int rowbytes = p.kc * 4;
     const uint32_t tile_bytes = (uint32_t)kTileM * rowbytes;
     const uint32_t wblk_bytes = 2u * p.Npad * rowbytes;
+    const uint32_t stage_bytes = 2u * p.G * tile_bytes;           // [G tiles of A][G tiles of A_lo]
     const int S = p.nstages;
+    const int ngroups = (p.nkb + p.G - 1) / p.G;                  // pipeline stages per row tile
 
     uint8_t* sW = smem;
-    uint8_t* sA = sW + (size_t)p.nkb * wblk_bytes;                 // stage s: A at 2*s, A_lo at 2*s+1
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)S * 2 * tile_bytes);
+    uint8_t* sA = sW + (size_t)p.nkb * wblk_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)S * stage_bytes);
     uint64_t* full_tma = bars;
     uint64_t* full_mma = bars + kMaxStages;
     uint64_t* empty = bars + 2 * kMaxStages;
     uint64_t* acc_full = bars + 3 * kMaxStages;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-    float* red = reinterpret_cast<float*>(tmem_slot + 2);           // [2][64] batch-norm partial sums
+    float* red = reinterpret_cast<float*>(tmem_slot + 2);           // [2][256] batch-norm partial sums
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full_tma + s, 1); mbar_init(full_mma + s, 128); mbar_init(empty + s, 1); }
@@ -102,44 +166,33 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
         prefetch_tmap(&p.tmA0);
         if (MODE == MODE_FWD && p.K > 1) prefetch_tmap(&p.tmAk);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
-    if (SUMS_N > 0) for (int i = threadIdx.x; i < 2 * 64; i += kThreads) red[i] = 0.f;
+    if (warp == kWarpMma) tmem_alloc(tmem_slot, 512);
+    if (SUMS) for (int i = threadIdx.x; i < 2 * 256; i += kRgThreads) red[i] = 0.f;
 
-    // ---- weights: TF32 hi / lo split, canonical K-major swizzled layout, rows [0,Npad) = hi, [Npad,2Npad) = lo
-    {
+    // ---- weights: rows [0,Npad) = TF32 hi, [Npad,2Npad) = lo, K-major swizzled, resident for the whole kernel
+    if (p.wpack) {
+        const int nvec = (int)((size_t)p.nkb * wblk_bytes / 16);
+        const float4* src = reinterpret_cast<const float4*>(p.wpack);
+        float4* dst = reinterpret_cast<float4*>(sW);
+        for (int i = threadIdx.x; i < nvec; i += kRgThreads) dst[i] = __ldg(src + i);
+    } else {
         const int per_blk = 2 * p.Npad * p.kc;
         const int total = p.nkb * per_blk;
-        for (int idx = threadIdx.x; idx < total; idx += kThreads) {
+        for (int idx = threadIdx.x; idx < total; idx += kRgThreads) {
             const int j = idx / per_blk;
             const int rem = idx - j * per_blk;
             const int n2 = rem / p.kc, kk = rem - n2 * p.kc;
-            const int half = n2 >= p.Npad;
-            const int n = n2 - half * p.Npad;
-            float w = 0.f;
-            if (n < p.Nreal) {
-                if (MODE == MODE_FWD) {
-                    const int k = j / p.nchunk, c = j - k * p.nchunk;
-                    w = __ldg(p.W + ((long long)(c * p.kc + kk) * p.K + k) * p.Fout + (p.n0 + n));
-                } else {
-                    const int q = p.n0 + n;
-                    const int kq = q / p.Fin, fi = q - kq * p.Fin;
-                    w = __ldg(p.W + ((long long)fi * p.K + kq) * p.Fout + (j * p.kc + kk));
-                }
-            }
-            const float hi = to_tf32(w);
-            const float v = half ? to_tf32(w - hi) : hi;
-            const int chunk = (kk >> 2) ^ swizzle_xor(n2, p.swz);
-            *reinterpret_cast<float*>(sW + (size_t)j * wblk_bytes + (size_t)n2 * rowbytes + chunk * 16 + (kk & 3) * 4) = v;
+            *reinterpret_cast<float*>(sW + w_image_offset(p, j, n2, kk)) = w_image_value<MODE>(p, j, n2, kk);
         }
-        fence_proxy_async();
     }
+    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int acc_cols = 2 * p.Npad;
 
-    if (warp == 0) {
+    if (warp == kWarpTma) {
         // ======================= TMA producer =======================
         if (lane == 0) {
             int s = 0;
@@ -147,22 +200,25 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
                 const int row0 = t * kTileM;
                 int k = 0, c = 0;                                   // plane, chunk within the plane
-                for (int j = 0; j < p.nkb; ++j) {
+                for (int j0 = 0; j0 < p.nkb; j0 += p.G) {
+                    const int cnt = min(p.G, p.nkb - j0);
                     mbar_wait(empty + s, ph ^ 1u, 1);
-                    mbar_expect_tx(full_tma + s, tile_bytes);
-                    uint8_t* dst = sA + (size_t)(2 * s) * tile_bytes;
-                    if (MODE == MODE_FWD) {
-                        if (k == 0) tma_load_2d(dst, &p.tmA0, full_tma + s, c * p.kc, row0);
-                        else tma_load_3d(dst, &p.tmAk, full_tma + s, c * p.kc, row0, k - 1);
-                        if (++c == p.nchunk) { c = 0; ++k; }
-                    } else {
-                        tma_load_2d(dst, &p.tmA0, full_tma + s, j * p.kc, row0);
+                    mbar_expect_tx(full_tma + s, cnt * tile_bytes);
+                    uint8_t* dst = sA + (size_t)s * stage_bytes;
+                    for (int u = 0; u < cnt; ++u, dst += tile_bytes) {
+                        if (MODE == MODE_FWD) {
+                            if (k == 0) tma_load_2d(dst, &p.tmA0, full_tma + s, c * p.kc, row0);
+                            else tma_load_3d(dst, &p.tmAk, full_tma + s, c * p.kc, row0, k - 1);
+                            if (++c == p.nchunk) { c = 0; ++k; }
+                        } else {
+                            tma_load_2d(dst, &p.tmA0, full_tma + s, (j0 + u) * p.kc, row0);
+                        }
                     }
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kWarpMma) {
         // ======================= MMA issuer =======================
         if (lane == 0) {
             const bool merged = acc_cols <= 256;
@@ -173,7 +229,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
             // descriptors differ only in the 14-bit start-address field (bytes >> 4): build them once
             const uint64_t dA0 = make_smem_desc(smem_u32(sA), 16, sbo, p.swz);
             const uint64_t dB0 = make_smem_desc(smem_u32(sW), 16, sbo, p.swz);
-            const uint32_t a_stage = (2u * tile_bytes) >> 4, a_lo = tile_bytes >> 4;
+            const uint32_t a_stage = stage_bytes >> 4, a_tile = tile_bytes >> 4, a_lo = (p.G * tile_bytes) >> 4;
             const uint32_t b_blk = wblk_bytes >> 4, b_lo = ((uint32_t)p.Npad * rowbytes) >> 4;
             int s = 0, ti = 0;
             uint32_t ph = 0;
@@ -185,21 +241,24 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                 const uint32_t d_hi = tmem_base + (uint32_t)(a * acc_cols);
                 const uint32_t d_lo = d_hi + (uint32_t)p.Npad;
                 uint64_t dB = dB0;
-                for (int j = 0; j < p.nkb; ++j, dB += b_blk) {
+                for (int j0 = 0; j0 < p.nkb; j0 += p.G) {
+                    const int cnt = min(p.G, p.nkb - j0);
                     mbar_wait(full_mma + s, ph, 3);
                     tc_fence_after();
-                    const uint64_t dA = dA0 + (uint64_t)(a_stage * (uint32_t)s);
+                    uint64_t dA = dA0 + (uint64_t)(a_stage * (uint32_t)s);
+                    for (int u = 0; u < cnt; ++u, dA += a_tile, dB += b_blk) {
 #pragma unroll 4
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-                        const uint64_t dAH = dA + 2u * ks, dBH = dB + 2u * ks;  // +32 bytes per k-step of 8
-                        if (merged) {
-                            mma_tf32(d_hi, dAH, dBH, idesc_wide, acc);          // A_hi * [W_hi | W_lo]
-                        } else {
-                            mma_tf32(d_hi, dAH, dBH, idesc_half, acc);
-                            mma_tf32(d_lo, dAH, dBH + b_lo, idesc_half, acc);
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint32_t acc = (j0 + u > 0 || ks > 0) ? 1u : 0u;
+                            const uint64_t dAH = dA + 2u * ks, dBH = dB + 2u * ks;  // +32 bytes per k-step of 8
+                            if (merged) {
+                                mma_tf32(d_hi, dAH, dBH, idesc_wide, acc);          // A_hi * [W_hi | W_lo]
+                            } else {
+                                mma_tf32(d_hi, dAH, dBH, idesc_half, acc);
+                                mma_tf32(d_lo, dAH, dBH + b_lo, idesc_half, acc);
+                            }
+                            mma_tf32(d_hi, dAH + a_lo, dBH, idesc_half, 1u);        // A_lo * W_hi
                         }
-                        mma_tf32(d_hi, dAH + a_lo, dBH, idesc_half, 1u);        // A_lo * W_hi
                     }
                     tc_commit(empty + s);                                       // stage free once the MMAs have read it
                     if (++s == S) { s = 0; ph ^= 1u; }
@@ -207,38 +266,39 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                 tc_commit(acc_full + a);
             }
         }
-    } else if (warp < 6) {
-        // ======================= TF32 hi / lo split of the landed tiles =======================
-        const int tt = threadIdx.x - 64;
-        const int nvec = (int)(tile_bytes / 16);
+    } else if (warp < kWarpEpi0) {
+        // ======================= TF32 hi / lo split: two groups of 4 warps take alternate stages =======================
+        const int grp = (warp - kWarpSplit0) >> 2;
+        const int tt = (threadIdx.x - kWarpSplit0 * 32) & 127;
         int s = 0;
-        uint32_t ph = 0;
+        uint32_t ph = 0, it = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-            for (int j = 0; j < p.nkb; ++j) {
-                mbar_wait(full_tma + s, ph, 4);
-                float4* A = reinterpret_cast<float4*>(sA + (size_t)(2 * s) * tile_bytes);
-                float4* Al = reinterpret_cast<float4*>(sA + (size_t)(2 * s + 1) * tile_bytes);
+            for (int j0 = 0; j0 < p.nkb; j0 += p.G, ++it) {
+                if ((int)(it & 1u) == grp) {
+                    const int cnt = min(p.G, p.nkb - j0);
+                    mbar_wait(full_tma + s, ph, 4);
+                    float4* A = reinterpret_cast<float4*>(sA + (size_t)s * stage_bytes);
+                    float4* Al = reinterpret_cast<float4*>(sA + (size_t)s * stage_bytes + (size_t)p.G * tile_bytes);
+                    const int nvec = (int)(cnt * tile_bytes / 16);
 #pragma unroll 4
-                for (int i = tt; i < nvec; i += 128) {
-                    const float4 v = A[i];
-                    float4 h, l;
-                    h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-                    l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-                    A[i] = h;
-                    Al[i] = l;
+                    for (int i = tt; i < nvec; i += 128) {
+                        const float4 v = A[i];
+                        float4 h, l;
+                        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
+                        l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
+                        A[i] = h;
+                        Al[i] = l;
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(full_mma + s);
                 }
-                fence_proxy_async();
-                mbar_arrive(full_mma + s);
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
         }
+        (void)ngroups;
     } else {
         // ======================= epilogue =======================
         const int q = warp & 3;                                     // TMEM lane quarter of this warp
-        constexpr int NS = SUMS_N > 0 ? SUMS_N : 1;
-        float s1[NS], s2[NS];
-#pragma unroll
-        for (int i = 0; i < NS; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
         int ti = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
             const int a = p.acc_stages == 2 ? (ti & 1) : 0;
@@ -250,47 +310,46 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
             const bool ok = row < p.R;
             if (MODE == MODE_FWD) {
                 float* orow = p.out + row * p.Fout;
-                if (SUMS_N > 0) {
-#pragma unroll
-                    for (int c0 = 0; c0 < NS; c0 += 16) {
-                        float hi[16], lo[16];
-                        tmem_ld16(tbase + c0, hi);
+                for (int c0 = 0; c0 < p.Nreal; c0 += 32) {
+                    float v[32];
+                    {
+                        float lo[16];
+                        tmem_ld16(tbase + c0, v);
                         tmem_ld16(tbase + p.Npad + c0, lo);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            hi[i] += lo[i];
-                            s1[c0 + i] += hi[i];
-                            s2[c0 + i] = fmaf(hi[i], hi[i], s2[c0 + i]);
-                        }
-                        if (ok) {
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                if (c0 + i + 3 < p.Fout) st4(orow + c0 + i, make_float4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]));
-                                else {
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) if (c0 + i + e < p.Fout) orow[c0 + i + e] = hi[i + e];
-                                }
-                        }
+                        for (int i = 0; i < 16; ++i) v[i] += lo[i];
                     }
-                } else {
-                    for (int c0 = 0; c0 < p.Nreal; c0 += 16) {
-                        float hi[16], lo[16];
-                        tmem_ld16(tbase + c0, hi);
-                        tmem_ld16(tbase + p.Npad + c0, lo);
+                    if (c0 + 16 < p.Npad) {
+                        float lo[16];
+                        tmem_ld16(tbase + c0 + 16, v + 16);
+                        tmem_ld16(tbase + p.Npad + c0 + 16, lo);
                         tmem_ld_wait();
-                        if (ok) {
 #pragma unroll
-                            for (int i = 0; i < 16; i += 4) {
-                                const int c = p.n0 + c0 + i;
-                                if (c + 3 < p.Fout && (p.Fout & 3) == 0)
-                                    st4(orow + c, make_float4(hi[i] + lo[i], hi[i + 1] + lo[i + 1], hi[i + 2] + lo[i + 2], hi[i + 3] + lo[i + 3]));
-                                else {
+                        for (int i = 0; i < 16; ++i) v[16 + i] += lo[i];
+                    } else {
 #pragma unroll
-                                    for (int e = 0; e < 4; ++e) if (c + e < p.Fout && c0 + i + e < p.Nreal) orow[c + e] = hi[i + e] + lo[i + e];
-                                }
+                        for (int i = 16; i < 32; ++i) v[i] = 0.f;
+                    }
+                    if (ok) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const int c = p.n0 + c0 + i;
+                            if (c + 3 < p.Fout && (p.Fout & 3) == 0) st4(orow + c, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+                            else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) if (c + e < p.Fout && c0 + i + e < p.Nreal) orow[c + e] = v[i + e];
                             }
                         }
+                    }
+                    if (SUMS) {
+                        // rows past R are zero (TMA zero fill), columns past Fout are zero weights
+                        float w[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) w[i] = v[i] * v[i];
+                        warp_column_sums(v, lane);
+                        warp_column_sums(w, lane);
+                        if (c0 + lane < p.Fout) { atomicAdd(red + c0 + lane, v[0]); atomicAdd(red + 256 + c0 + lane, w[0]); }
                     }
                 }
             } else {
@@ -312,31 +371,22 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
             tc_fence_before();
             mbar_arrive(acc_empty + a);
         }
-        if (SUMS_N > 0) {
-            // per-thread partial sums over this CTA's rows -> warp -> CTA -> one double atomic per feature
-#pragma unroll
-            for (int c = 0; c < NS; ++c) {
-                float a1 = s1[c], a2 = s2[c];
-#pragma unroll
-                for (int o = 16; o; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
-                if (lane == 0) { atomicAdd(red + c, a1); atomicAdd(red + 64 + c, a2); }
-            }
+        if (SUMS) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            const int e = threadIdx.x - 192;
-            if (e < p.Fout) {
+            for (int e = threadIdx.x - kWarpEpi0 * 32; e < p.Fout; e += 128) {
                 atomicAdd(p.bn_sums + e, (double)red[e]);
-                atomicAdd(p.bn_sums + p.Fout + e, (double)red[64 + e]);
+                atomicAdd(p.bn_sums + p.Fout + e, (double)red[256 + e]);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
 }
 
 struct RowGemmPlan {
-    int kc, swz, nchunk, nkb, Npad, nstages, acc_stages;
-    size_t smem;
+    int kc, swz, nchunk, nkb, Npad, G, nstages, acc_stages;
+    size_t smem, wbytes;
 };
 
 // Shared-memory plan; returns false if the shape does not fit the tensor-core path.
@@ -348,42 +398,60 @@ static bool plan_rowgemm(int red_per_plane, int planes, int Npad, RowGemmPlan* p
     pl->nchunk = red_per_plane / pl->kc;
     pl->nkb = planes * pl->nchunk;
     pl->Npad = Npad;
-    const size_t wbytes = (size_t)pl->nkb * 2 * Npad * pl->kc * 4;
-    const size_t stage = 2 * (size_t)kTileM * pl->kc * 4;
-    const size_t fixed = 1024 /*align*/ + 3 * kMaxStages * 8 + 4 * 8 + 16 + 2 * 64 * 4 + 64;
+    pl->G = 32 / pl->kc;                                   // 16 KB of activations per stage
+    if (pl->G > pl->nkb) pl->G = pl->nkb;
+    pl->wbytes = (size_t)pl->nkb * 2 * Npad * pl->kc * 4;
+    const size_t fixed = 1024 /*align*/ + 3 * kMaxStages * 8 + 4 * 8 + 16 + 2 * 256 * 4 + 64;
     const size_t budget = 227 * 1024;
-    if (wbytes + fixed + 2 * stage > budget) return false;
-    size_t ns = (budget - wbytes - fixed) / stage;
+    size_t stage = 2 * (size_t)pl->G * kTileM * pl->kc * 4;
+    while (pl->G > 1 && pl->wbytes + fixed + 3 * stage > budget) { pl->G >>= 1; stage >>= 1; }
+    if (pl->wbytes + fixed + 2 * stage > budget) return false;
+    size_t ns = (budget - pl->wbytes - fixed) / stage;
     if (ns > kMaxStages) ns = kMaxStages;
     pl->nstages = (int)ns;
     pl->acc_stages = (4 * Npad <= 512) ? 2 : 1;
-    pl->smem = wbytes + fixed + ns * stage;
+    pl->smem = pl->wbytes + fixed + ns * stage;
     if (pl->smem < 120 * 1024) pl->smem = 120 * 1024;      // one CTA per SM: every CTA allocates all 512 TMEM columns
     return true;
 }
 
-template <int MODE, int SUMS_N>
-static int launch_rowgemm(const RowGemmParams& p, size_t smem, cudaStream_t s)
+template <int MODE, bool SUMS>
+static int launch_rowgemm(RowGemmParams& p, size_t smem, float* image, cudaStream_t s)
 {
     static bool configured = false;                // per template instance
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rowgemm_tc_kernel<MODE, SUMS_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(rowgemm_tc_kernel<MODE, SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
+    p.wpack = image;
+    if (image) {
+        const int total = p.nkb * 2 * p.Npad * p.kc;
+        pack_w_kernel<MODE><<<(total + 255) / 256, 256, 0, s>>>(p, image);
+        count_launch();
+    }
     const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
-    rowgemm_tc_kernel<MODE, SUMS_N><<<grid, kThreads, smem, s>>>(p);
+    rowgemm_tc_kernel<MODE, SUMS><<<grid, kRgThreads, smem, s>>>(p);
     DSB_LAUNCH_CHECK();
+}
+
+size_t contract_workspace_bytes(int Fin, int K, int Fout)
+{
+    const size_t Q = (size_t)K * Fin;
+    const size_t fwd = 2 * (size_t)((Fout + 15) / 16 * 16) * Q * 4;
+    const size_t nb = (Q + 159) / 160;
+    const size_t NB = ((Q + nb - 1) / nb + 15) / 16 * 16;
+    const size_t bwd = 2 * nb * NB * (size_t)Fout * 4;
+    return (fwd > bwd ? fwd : bwd) + 1024;
 }
 
 // Forward contraction on the tensor cores.  Returns 1 if the shape is not supported (caller falls back).
 int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
-                    double* bn_sums, cudaStream_t s)
+                    double* bn_sums, void* workspace, cudaStream_t s)
 {
     if (R < kTileM || R > 0x7fffff00LL || Fout > 256 || (Fout & 3)) return 1;
-    if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y) & 15) != 0) return 1;
+    if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y | (uintptr_t)workspace) & 15) != 0) return 1;
     const int Npad = (Fout + 15) / 16 * 16;
-    if (bn_sums && Npad > 64) return 1;
     RowGemmPlan pl;
     if (!plan_rowgemm(Fin, K, Npad, &pl)) return 1;
     RowGemmParams p;
@@ -391,21 +459,20 @@ int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, 
     if (K > 1) { if (make_tmap_f32(&p.tmAk, xk, Fin, R, K - 1, pl.kc, kTileM, pl.swz, true)) return 1; }
     else p.tmAk = p.tmA0;
     p.W = W; p.out = Y; p.bn_sums = bn_sums; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
-    p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.Npad = Npad; p.Nreal = Fout; p.n0 = 0; p.swz = pl.swz;
+    p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.G = pl.G; p.Npad = Npad; p.Nreal = Fout; p.n0 = 0; p.swz = pl.swz;
     p.nstages = pl.nstages; p.acc_stages = pl.acc_stages;
     p.ntiles = (int)((R + kTileM - 1) / kTileM);
-    if (!bn_sums) return launch_rowgemm<MODE_FWD, 0>(p, pl.smem, s);
-    if (Npad == 16) return launch_rowgemm<MODE_FWD, 16>(p, pl.smem, s);
-    if (Npad == 32) return launch_rowgemm<MODE_FWD, 32>(p, pl.smem, s);
-    if (Npad == 48) return launch_rowgemm<MODE_FWD, 48>(p, pl.smem, s);
-    return launch_rowgemm<MODE_FWD, 64>(p, pl.smem, s);
+    float* image = (float*)workspace;
+    if (!bn_sums) return launch_rowgemm<MODE_FWD, false>(p, pl.smem, image, s);
+    return launch_rowgemm<MODE_FWD, true>(p, pl.smem, image, s);
 }
 
 // Data gradient on the tensor cores: G[k][r][fi] = sum_fo dY[r, fo] W[fi*K + k, fo].
-int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R, int Fin, int K, int Fout, cudaStream_t s)
+int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R, int Fin, int K, int Fout,
+                         void* workspace, cudaStream_t s)
 {
     if (R < kTileM || R > 0x7fffff00LL || (Fin & 7) || (Fout & 7)) return 1;
-    if ((((uintptr_t)dY | (uintptr_t)G) & 15) != 0) return 1;
+    if ((((uintptr_t)dY | (uintptr_t)G | (uintptr_t)workspace) & 15) != 0) return 1;
     const int Q = K * Fin;
     // n-blocks of at most 160 output columns (hi + lo accumulators = 320 TMEM columns)
     const int nb = (Q + 159) / 160;
@@ -417,11 +484,12 @@ int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R,
         if (make_tmap_f32(&p.tmA0, dY, Fout, R, 1, pl.kc, kTileM, pl.swz, false)) return 1;
         p.tmAk = p.tmA0;
         p.W = W; p.out = G; p.bn_sums = nullptr; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
-        p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.Npad = NB; p.n0 = b * NB;
+        p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.G = pl.G; p.Npad = NB; p.n0 = b * NB;
         p.Nreal = (Q - p.n0 < NB) ? (Q - p.n0) : NB;
         p.swz = pl.swz; p.nstages = pl.nstages; p.acc_stages = pl.acc_stages;
         p.ntiles = (int)((R + kTileM - 1) / kTileM);
-        int rc = launch_rowgemm<MODE_BWD_DATA, 0>(p, pl.smem, s);
+        float* image = workspace ? (float*)((uint8_t*)workspace + (size_t)b * pl.wbytes) : nullptr;
+        int rc = launch_rowgemm<MODE_BWD_DATA, false>(p, pl.smem, image, s);
         if (rc) return rc;
     }
     return 0;
@@ -444,6 +512,7 @@ namespace dsb200 {
 namespace tc {
 
 constexpr int kMNBlock = 32;                     // columns per MN-major block (128 bytes of fp32)
+constexpr int kWgThreads = 320;                  // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue
 
 struct alignas(64) WGradParams {
     CUtensorMap tmX0, tmXk, tmdY;
@@ -465,7 +534,7 @@ __device__ __forceinline__ uint64_t make_mn_desc(uint32_t saddr, uint32_t block_
            ((uint64_t)((512u >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (1ull << 61);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ WGradParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -664,7 +733,7 @@ int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, fl
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
-    wgrad_tc_kernel<<<grid, kThreads, smem, s>>>(p);
+    wgrad_tc_kernel<<<grid, kWgThreads, smem, s>>>(p);
     DSB_LAUNCH_CHECK();
 }
 

@@ -134,8 +134,10 @@ int make_tmap_f32(CUtensorMap* out, const float* base, long long cols, long long
 
 // tensor-core contraction entry points (contract_tc.cu); return 1 when the shape is not supported
 int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
-                    double* bn_sums, cudaStream_t s);
-int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R, int Fin, int K, int Fout, cudaStream_t s);
+                    double* bn_sums, void* workspace, cudaStream_t s);
+int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R, int Fin, int K, int Fout,
+                         void* workspace, cudaStream_t s);
+size_t contract_workspace_bytes(int Fin, int K, int Fout);
 int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K,
                            int Fout, cudaStream_t s);
 

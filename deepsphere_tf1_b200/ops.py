@@ -46,18 +46,26 @@ def cheb_basis_bwd(graph, G):
     return G[0]
 
 
+def _workspace(Fin, K, Fout, device):
+    """Scratch for the split-weight image of the tensor-core contraction (one allocation per call from
+    torch's caching allocator: stream-ordered, CUDA-graph safe)."""
+    from ._lib import LIB
+    n = int(LIB.load().dsb200_contract_workspace_bytes(Fin, K, Fout))
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
 def contract_fwd(x, basis, W, K, Fout, bn_sums=None):
     """Y = [X_0 .. X_{K-1}] . W  (tf.matmul, models.py:1062-1078), optional batch-norm sums."""
     B, M, Fin = x.shape
     y = _new((B, M, Fout), x)
-    call('cheb_contract_fwd', x, basis, W, y, B * M, Fin, K, Fout, bn_sums)
+    call('cheb_contract_fwd', x, basis, W, y, B * M, Fin, K, Fout, bn_sums, _workspace(Fin, K, Fout, x.device))
     return y
 
 
 def contract_bwd_data(dy, W, K, Fin):
     B, M, Fout = dy.shape
     G = _new((K, B, M, Fin), dy)
-    call('cheb_contract_bwd_data', dy, W, G, B * M, Fin, K, Fout)
+    call('cheb_contract_bwd_data', dy, W, G, B * M, Fin, K, Fout, _workspace(Fin, K, Fout, dy.device))
     return G
 
 

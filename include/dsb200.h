@@ -80,10 +80,14 @@ int dsb200_cheb_basis_bwd(const int32_t* rowptrT, const int32_t* colT, const flo
  * sum_r Y and sum_r Y^2 per output feature (tf.nn.moments inside
  * tf.layers.batch_normalization, models.py:1197-1203). */
 int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const float* W, float* Y,
-                             long long R, int Fin, int K, int Fout, double* bn_sums, void* stream);
+                             long long R, int Fin, int K, int Fout, double* bn_sums, void* workspace, void* stream);
 /* dX_k[r, fi] = sum_fo dY[r, fo] * W[fi*K + k, fo]  -> G [K][R][Fin]  (autodiff of 1077) */
 int dsb200_cheb_contract_bwd_data(const float* dY, const float* W, float* G,
-                                  long long R, int Fin, int K, int Fout, void* stream);
+                                  long long R, int Fin, int K, int Fout, void* workspace, void* stream);
+/* `workspace` (device, 16-byte aligned, dsb200_contract_workspace_bytes(Fin, K, Fout) bytes, may be NULL):
+ * scratch for the TF32 hi / lo split weight image of the tensor-core path; without it every CTA splits
+ * the weights itself (slower for small layers). */
+long long dsb200_contract_workspace_bytes(int Fin, int K, int Fout);
 /* dW[fi*K + k, fo] += sum_r X_k[r, fi] * dY[r, fo]  (dW must be zeroed by the caller) */
 int dsb200_cheb_contract_bwd_weight(const float* x0, const float* xk, const float* dY, float* dW,
                                     long long R, int Fin, int K, int Fout, void* stream);
