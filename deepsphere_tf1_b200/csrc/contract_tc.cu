@@ -73,6 +73,7 @@ struct alignas(64) RowGemmParams {
     int swz;                   // 1 / 2 / 3 = 32 / 64 / 128-byte swizzle (row of a tile = kc*4 bytes)
     int nstages, acc_stages;
     int ntiles;
+    int wstream;               // 1: the weight image is too large to stay resident: each stage carries its k-blocks' weights
 };
 
 // Element (j, n2, kk) of the weight image: k-block j, row n2 in [0, 2*Npad) (hi rows then lo rows), column kk.
@@ -144,12 +145,13 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
     const int rowbytes = p.kc * 4;
     const uint32_t tile_bytes = (uint32_t)kTileM * rowbytes;
     const uint32_t wblk_bytes = 2u * p.Npad * rowbytes;
-    const uint32_t stage_bytes = 2u * p.G * tile_bytes;           // [G tiles of A][G tiles of A_lo]
+    // stage: [G tiles of A][G tiles of A_lo] (+ [G weight blocks] when the weights are streamed)
+    const uint32_t stage_bytes = 2u * p.G * tile_bytes + (p.wstream ? p.G * wblk_bytes : 0u);
     const int S = p.nstages;
     const int ngroups = (p.nkb + p.G - 1) / p.G;                  // pipeline stages per row tile
 
     uint8_t* sW = smem;
-    uint8_t* sA = sW + (size_t)p.nkb * wblk_bytes;
+    uint8_t* sA = sW + (p.wstream ? 0 : (size_t)p.nkb * wblk_bytes);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)S * stage_bytes);
     uint64_t* full_tma = bars;
     uint64_t* full_mma = bars + kMaxStages;
@@ -170,7 +172,9 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
     if (SUMS) for (int i = threadIdx.x; i < 2 * 256; i += kRgThreads) red[i] = 0.f;
 
     // ---- weights: rows [0,Npad) = TF32 hi, [Npad,2Npad) = lo, K-major swizzled, resident for the whole kernel
-    if (p.wpack) {
+    if (p.wstream) {
+        // nothing resident
+    } else if (p.wpack) {
         const int nvec = (int)((size_t)p.nkb * wblk_bytes / 16);
         const float4* src = reinterpret_cast<const float4*>(p.wpack);
         float4* dst = reinterpret_cast<float4*>(sW);
@@ -203,8 +207,11 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                 for (int j0 = 0; j0 < p.nkb; j0 += p.G) {
                     const int cnt = min(p.G, p.nkb - j0);
                     mbar_wait(empty + s, ph ^ 1u, 1);
-                    mbar_expect_tx(full_tma + s, cnt * tile_bytes);
+                    mbar_expect_tx(full_tma + s, cnt * (tile_bytes + (p.wstream ? wblk_bytes : 0u)));
                     uint8_t* dst = sA + (size_t)s * stage_bytes;
+                    if (p.wstream)
+                        bulk_load(dst + 2 * (size_t)p.G * tile_bytes, reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)j0 * wblk_bytes,
+                                  cnt * wblk_bytes, full_tma + s);
                     for (int u = 0; u < cnt; ++u, dst += tile_bytes) {
                         if (MODE == MODE_FWD) {
                             if (k == 0) tma_load_2d(dst, &p.tmA0, full_tma + s, c * p.kc, row0);
@@ -246,6 +253,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                     mbar_wait(full_mma + s, ph, 3);
                     tc_fence_after();
                     uint64_t dA = dA0 + (uint64_t)(a_stage * (uint32_t)s);
+                    if (p.wstream) dB = dA + 2u * p.G * a_tile;                      // this stage's weight blocks
                     for (int u = 0; u < cnt; ++u, dA += a_tile, dB += b_blk) {
 #pragma unroll 4
                         for (int ks = 0; ks < ksteps; ++ks) {
@@ -385,12 +393,12 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
 }
 
 struct RowGemmPlan {
-    int kc, swz, nchunk, nkb, Npad, G, nstages, acc_stages;
+    int kc, swz, nchunk, nkb, Npad, G, nstages, acc_stages, wstream;
     size_t smem, wbytes;
 };
 
 // Shared-memory plan; returns false if the shape does not fit the tensor-core path.
-static bool plan_rowgemm(int red_per_plane, int planes, int Npad, RowGemmPlan* pl)
+static bool plan_rowgemm(int red_per_plane, int planes, int Npad, bool can_stream, RowGemmPlan* pl)
 {
     if (red_per_plane % 8) return false;
     pl->kc = red_per_plane % 32 == 0 ? 32 : red_per_plane % 16 == 0 ? 16 : 8;
@@ -404,6 +412,20 @@ static bool plan_rowgemm(int red_per_plane, int planes, int Npad, RowGemmPlan* p
     const size_t fixed = 1024 /*align*/ + 3 * kMaxStages * 8 + 4 * 8 + 16 + 2 * 256 * 4 + 64;
     const size_t budget = 227 * 1024;
     size_t stage = 2 * (size_t)pl->G * kTileM * pl->kc * 4;
+    pl->wstream = 0;
+    if (can_stream && pl->wbytes + fixed + 4 * stage > budget) {
+        // resident weights would leave fewer than 4 stages: stream the weight blocks with the activations
+        pl->wstream = 1;
+        pl->G = 1;
+        stage = 2 * (size_t)kTileM * pl->kc * 4 + 2 * (size_t)Npad * pl->kc * 4;
+        if (fixed + 2 * stage > budget) return false;
+        size_t ns = (budget - fixed) / stage;
+        if (ns > kMaxStages) ns = kMaxStages;
+        pl->nstages = (int)ns;
+        pl->acc_stages = (4 * Npad <= 512) ? 2 : 1;
+        pl->smem = fixed + ns * stage;
+        return true;
+    }
     while (pl->G > 1 && pl->wbytes + fixed + 3 * stage > budget) { pl->G >>= 1; stage >>= 1; }
     if (pl->wbytes + fixed + 2 * stage > budget) return false;
     size_t ns = (budget - pl->wbytes - fixed) / stage;
@@ -453,14 +475,14 @@ int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, 
     if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y | (uintptr_t)workspace) & 15) != 0) return 1;
     const int Npad = (Fout + 15) / 16 * 16;
     RowGemmPlan pl;
-    if (!plan_rowgemm(Fin, K, Npad, &pl)) return 1;
+    if (!plan_rowgemm(Fin, K, Npad, workspace != nullptr, &pl)) return 1;
     RowGemmParams p;
     if (make_tmap_f32(&p.tmA0, x0, Fin, R, 1, pl.kc, kTileM, pl.swz, false)) return 1;
     if (K > 1) { if (make_tmap_f32(&p.tmAk, xk, Fin, R, K - 1, pl.kc, kTileM, pl.swz, true)) return 1; }
     else p.tmAk = p.tmA0;
     p.W = W; p.out = Y; p.bn_sums = bn_sums; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
     p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.G = pl.G; p.Npad = Npad; p.Nreal = Fout; p.n0 = 0; p.swz = pl.swz;
-    p.nstages = pl.nstages; p.acc_stages = pl.acc_stages;
+    p.nstages = pl.nstages; p.acc_stages = pl.acc_stages; p.wstream = pl.wstream;
     p.ntiles = (int)((R + kTileM - 1) / kTileM);
     float* image = (float*)workspace;
     if (!bn_sums) return launch_rowgemm<MODE_FWD, false>(p, pl.smem, image, s);
@@ -478,7 +500,7 @@ int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R,
     const int nb = (Q + 159) / 160;
     const int NB = ((Q + nb - 1) / nb + 15) / 16 * 16;
     RowGemmPlan pl;
-    if (!plan_rowgemm(Fout, 1, NB, &pl)) return 1;
+    if (!plan_rowgemm(Fout, 1, NB, workspace != nullptr, &pl)) return 1;
     for (int b = 0; b < nb; ++b) {
         RowGemmParams p;
         if (make_tmap_f32(&p.tmA0, dY, Fout, R, 1, pl.kc, kTileM, pl.swz, false)) return 1;
@@ -486,7 +508,7 @@ int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R,
         p.W = W; p.out = G; p.bn_sums = nullptr; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
         p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.G = pl.G; p.Npad = NB; p.n0 = b * NB;
         p.Nreal = (Q - p.n0 < NB) ? (Q - p.n0) : NB;
-        p.swz = pl.swz; p.nstages = pl.nstages; p.acc_stages = pl.acc_stages;
+        p.swz = pl.swz; p.nstages = pl.nstages; p.acc_stages = pl.acc_stages; p.wstream = pl.wstream;
         p.ntiles = (int)((R + kTileM - 1) / kTileM);
         float* image = workspace ? (float*)((uint8_t*)workspace + (size_t)b * pl.wbytes) : nullptr;
         int rc = launch_rowgemm<MODE_BWD_DATA, false>(p, pl.smem, image, s);
