@@ -53,4 +53,12 @@ __device__ __forceinline__ float act_grad(float z, int act) {
     }
 }
 
+// Threads of a block are laid out [rows][G] (G = feature groups, a power of two): lanes whose index is equal
+// modulo G hold partial sums of the same features.  Sum v over those lanes (G < 32); afterwards lanes 0..G-1
+// of every warp hold the warp totals.  Cuts same-address shared-memory atomics by 32/G.
+__device__ __forceinline__ float warp_sum_mod(float v, int G) {
+    for (int o = 16; o >= G; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
 }  // namespace dsb200

@@ -50,6 +50,18 @@ int make_tmap_f32(CUtensorMap* out, const float* base, long long cols, long long
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
+// general fp32 tensor map: dims / box innermost first, strides (bytes) for dims 1..rank-1
+static int make_tmap_nd(CUtensorMap* out, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                        const cuuint32_t* box, CUtensorMapSwizzle sw)
+{
+    EncodeTiledFn enc = get_encode_tiled();
+    if (!enc) return -1;
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
 constexpr int kTileM = 128;
 constexpr int kMaxStages = 8;
 enum { MODE_FWD = 0, MODE_BWD_DATA = 1 };
@@ -471,7 +483,7 @@ size_t contract_workspace_bytes(int Fin, int K, int Fout)
 int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
                     double* bn_sums, void* workspace, cudaStream_t s)
 {
-    if (R < kTileM || R > 0x7fffff00LL || Fout > 256 || (Fout & 3)) return 1;
+    if (R < kTileM || R > 0x7fffff00LL || Fout > 256) return 1;
     if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y | (uintptr_t)workspace) & 15) != 0) return 1;
     const int Npad = (Fout + 15) / 16 * 16;
     RowGemmPlan pl;
@@ -534,14 +546,16 @@ namespace dsb200 {
 namespace tc {
 
 constexpr int kMNBlock = 32;                     // columns per MN-major block (128 bytes of fp32)
-constexpr int kWgThreads = 320;                  // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue
+constexpr int kWgThreads = 448;                  // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 split (alternate stages), warps 10-13 epilogue
 
 struct alignas(64) WGradParams {
     CUtensorMap tmX0, tmXk, tmdY;
     float* dW;
     long long R;
     int Fin, K, Fout;
-    int nblkA, nblkB;          // 32-column blocks per plane of X / of dY
+    int nblkA, nblkB;          // 32-column blocks per plane of X (Fin >= 32) / of dY
+    int pack;                  // Fin < 32: planes 1..K-1 are packed `pack` = 32/Fin to a block (plane 0 has its own block)
+    int nA;                    // number of X blocks per stage
     int pad_blocks;            // unused blocks at the end of a stage (the last 128-wide tile of q may read past X_lo)
     int RS;                    // rows per pipeline stage (multiple of 8)
     int nstages;
@@ -565,7 +579,7 @@ wgrad_tc_kernel(const __grid_constant__ WGradParams p)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.nstages;
     const uint32_t blk = (uint32_t)p.RS * kMNBlock * 4;               // one 32-column block of RS rows
-    const int nA = p.K * p.nblkA;
+    const int nA = p.nA;
     const uint32_t xbytes = blk * nA, ybytes = blk * p.nblkB;
     const uint32_t stage_bytes = 2 * (xbytes + ybytes) + blk * p.pad_blocks;   // [X][X_lo][dY][dY_lo][pad]
     const int Np = p.nblkB * kMNBlock;                                // dY columns incl. zero padding
@@ -607,12 +621,19 @@ wgrad_tc_kernel(const __grid_constant__ WGradParams p)
                 mbar_wait(empty + s, ph ^ 1u, 11);
                 mbar_expect_tx(full_tma + s, xbytes + ybytes);
                 uint8_t* dst = sA + (size_t)s * stage_bytes;
-                for (int k = 0; k < p.K; ++k)
-                    for (int c = 0; c < p.nblkA; ++c) {
-                        uint8_t* d = dst + (size_t)(k * p.nblkA + c) * blk;
-                        if (k == 0) tma_load_2d(d, &p.tmX0, full_tma + s, c * kMNBlock, row0);
-                        else tma_load_3d(d, &p.tmXk, full_tma + s, c * kMNBlock, row0, k - 1);
-                    }
+                if (p.pack > 0) {
+                    // block 0 = plane 0 (zero-filled to 32 columns); block b >= 1 = planes 1+(b-1)*pack .. of the basis
+                    tma_load_2d(dst, &p.tmX0, full_tma + s, 0, row0);
+                    for (int bq = 1; bq < nA; ++bq)
+                        tma_load_3d(dst + (size_t)bq * blk, &p.tmXk, full_tma + s, 0, (bq - 1) * p.pack, row0);
+                } else {
+                    for (int k = 0; k < p.K; ++k)
+                        for (int c = 0; c < p.nblkA; ++c) {
+                            uint8_t* d = dst + (size_t)(k * p.nblkA + c) * blk;
+                            if (k == 0) tma_load_2d(d, &p.tmX0, full_tma + s, c * kMNBlock, row0);
+                            else tma_load_3d(d, &p.tmXk, full_tma + s, c * kMNBlock, row0, k - 1);
+                        }
+                }
                 uint8_t* dy = dst + 2 * (size_t)xbytes;
                 for (int c = 0; c < p.nblkB; ++c) tma_load_2d(dy + (size_t)c * blk, &p.tmdY, full_tma + s, c * kMNBlock, row0);
                 if (++s == S) { s = 0; ph ^= 1u; }
@@ -655,12 +676,14 @@ wgrad_tc_kernel(const __grid_constant__ WGradParams p)
             }
             tc_commit(acc_full);
         }
-    } else if (warp < 6) {
-        const int tt = threadIdx.x - 64;
+    } else if (warp < kWarpEpi0) {
+        const int grp = (warp - kWarpSplit0) >> 2;
+        const int tt = (threadIdx.x - kWarpSplit0 * 32) & 127;
         const int nvecX = (int)(xbytes / 16), nvecY = (int)(ybytes / 16);
         int s = 0;
         uint32_t ph = 0;
         for (int i = 0; i < niter; ++i) {
+            if ((i & 1) != grp) { if (++s == S) { s = 0; ph ^= 1u; } continue; }
             mbar_wait(full_tma + s, ph, 14);
             float4* X = reinterpret_cast<float4*>(sA + (size_t)s * stage_bytes);
             float4* Xl = X + nvecX;
@@ -688,10 +711,16 @@ wgrad_tc_kernel(const __grid_constant__ WGradParams p)
         tc_fence_after();
         for (int mt = 0; mt < p.mtiles; ++mt) {
             const int q = mt * kTileM + qd * 32 + lane;              // (block, column in block) of the padded Xcat
-            const int bq = q / kMNBlock;
-            const int k = bq / p.nblkA;
-            const int fi = (bq - k * p.nblkA) * kMNBlock + (q - bq * kMNBlock);
-            const bool ok = k < p.K && fi < p.Fin;
+            const int bq = q / kMNBlock, cq = q - bq * kMNBlock;
+            int k, fi;
+            if (p.pack > 0) {
+                if (bq == 0) { k = 0; fi = cq; }
+                else { k = 1 + (bq - 1) * p.pack + cq / p.Fin; fi = cq % p.Fin; }
+            } else {
+                k = bq / p.nblkA;
+                fi = (bq - k * p.nblkA) * kMNBlock + cq;
+            }
+            const bool ok = bq < nA && k < p.K && fi < p.Fin;
             float* dst = p.dW + ((long long)fi * p.K + k) * p.Fout;
             const uint32_t tbase = tmem_base + (uint32_t)(mt * acc_cols) + ((uint32_t)(qd * 32) << 16);
             for (int c0 = 0; c0 < p.Fout; c0 += 8) {
@@ -720,7 +749,13 @@ int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, fl
     WGradParams p;
     p.nblkA = (Fin + kMNBlock - 1) / kMNBlock;
     p.nblkB = (Fout + kMNBlock - 1) / kMNBlock;
-    const int nA = K * p.nblkA, nB = p.nblkB;
+    // Packing several narrow planes into one 128-byte row with a 3-D box does NOT work: under the swizzled
+    // modes TMA pads every inner-box row to the swizzle span (tools/experiments/tma_box_layout.cu), so narrow
+    // planes are zero-filled to 32 columns instead (pack = 0).
+    p.pack = 0;
+    const int nA = p.pack > 0 ? 1 + (K - 1 + p.pack - 1) / p.pack : K * p.nblkA;
+    p.nA = nA;
+    const int nB = p.nblkB;
     p.mtiles = (nA * kMNBlock + kTileM - 1) / kTileM;
     if (p.mtiles * 2 * nB * kMNBlock > 512) return 1;
     // the last 128-wide tile of q may read past the X_lo blocks: keep it inside the stage ([X][X_lo][dY][dY_lo][pad])
@@ -741,7 +776,13 @@ int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, fl
     if (smem < 120 * 1024) smem = 120 * 1024;
     const int SW = 4;                                                   // 128B swizzle, 32B atoms
     if (make_tmap_f32(&p.tmX0, x0, Fin, R, 1, kMNBlock, RS, SW, false)) return 1;
-    if (K > 1) { if (make_tmap_f32(&p.tmXk, xk, Fin, R, K - 1, kMNBlock, RS, SW, true)) return 1; }
+    if (p.pack > 0) {
+        // basis [K-1][R][Fin] seen as (fi, plane, row): a box of Fin x pack x RS lands as RS rows of pack*Fin = 32 floats
+        const cuuint64_t dims[3] = {(cuuint64_t)Fin, (cuuint64_t)(K - 1), (cuuint64_t)R};
+        const cuuint64_t strides[2] = {(cuuint64_t)R * Fin * 4, (cuuint64_t)Fin * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)Fin, (cuuint32_t)p.pack, (cuuint32_t)RS};
+        if (make_tmap_nd(&p.tmXk, xk, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    } else if (K > 1) { if (make_tmap_f32(&p.tmXk, xk, Fin, R, K - 1, kMNBlock, RS, SW, true)) return 1; }
     else p.tmXk = p.tmX0;
     if (make_tmap_f32(&p.tmdY, dY, Fout, R, 1, kMNBlock, RS, SW, false)) return 1;
     p.dW = dW; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;

@@ -213,9 +213,16 @@ bn_act_pool_bwd_kernel(const float* __restrict__ y, const float* __restrict__ me
                 }
             }
         }
-        if (MODE != 2) {
+    }
+    if (MODE != 2) {
+        // (all threads take part in the shuffles; idle threads carry zeros)
+        const bool pw = Fv < 32 && (Fv & (Fv - 1)) == 0 && (blockDim.x % Fv) == 0;
+        const bool leader = rl < rows_per_block && (!pw || (threadIdx.x & 31) < Fv);
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) { atomicAdd(&red[f0 + v], s1[v]); atomicAdd(&red[F + f0 + v], s2[v]); }
+        for (int v = 0; v < VEC; ++v) {
+            const float a1 = pw ? warp_sum_mod(s1[v], Fv) : s1[v];
+            const float a2 = pw ? warp_sum_mod(s2[v], Fv) : s2[v];
+            if (leader) { atomicAdd(&red[f0 + v], a1); atomicAdd(&red[F + f0 + v], a2); }
         }
     }
     if (MODE != 2) {

@@ -258,12 +258,18 @@ smallconv_bwd_kernel(Planes P, RowMap rm, const float* __restrict__ W, const flo
             }
         }
     }
+    const bool pw = Fv < 32 && (Fv & (Fv - 1)) == 0;
+    const bool leader = !pw || (threadIdx.x & 31) < Fv;
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q) atomicAdd(&red[q * Fout + f0 + v], A[q][v]);
-        atomicAdd(&red[Q * Fout + f0 + v], s1[v]);
-        atomicAdd(&red[(Q + 1) * Fout + f0 + v], s2[v]);
+        for (int q = 0; q < Q; ++q) {
+            const float a = pw ? warp_sum_mod(A[q][v], Fv) : A[q][v];
+            if (leader) atomicAdd(&red[q * Fout + f0 + v], a);
+        }
+        const float a1 = pw ? warp_sum_mod(s1[v], Fv) : s1[v];
+        const float a2 = pw ? warp_sum_mod(s2[v], Fv) : s2[v];
+        if (leader) { atomicAdd(&red[Q * Fout + f0 + v], a1); atomicAdd(&red[(Q + 1) * Fout + f0 + v], a2); }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < (Q + 2) * Fout; i += blockDim.x) atomicAdd(accg + i, (double)red[i]);
@@ -403,12 +409,19 @@ smallconv_bwd_fast_kernel(Planes P, RowMap rm, const float* __restrict__ bias, c
             }
         }
     }
+    // lanes equal modulo Fg hold the same features: reduce inside the warp before touching shared memory
+    const bool pw = Fg < 32 && (Fg & (Fg - 1)) == 0;
+    const bool leader = !pw || (threadIdx.x & 31) < Fg;
 #pragma unroll
     for (int v = 0; v < 8; ++v) {
 #pragma unroll
-        for (int q = 0; q < Q; ++q) atomicAdd(&red[q * Fout + f0 + v], A[q][v]);
-        atomicAdd(&red[Q * Fout + f0 + v], s1[v]);
-        atomicAdd(&red[(Q + 1) * Fout + f0 + v], s2[v]);
+        for (int q = 0; q < Q; ++q) {
+            const float a = pw ? warp_sum_mod(A[q][v], Fg) : A[q][v];
+            if (leader) atomicAdd(&red[q * Fout + f0 + v], a);
+        }
+        const float a1 = pw ? warp_sum_mod(s1[v], Fg) : s1[v];
+        const float a2 = pw ? warp_sum_mod(s2[v], Fg) : s2[v];
+        if (leader) { atomicAdd(&red[Q * Fout + f0 + v], a1); atomicAdd(&red[(Q + 1) * Fout + f0 + v], a2); }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < (Q + 2) * Fout; i += blockDim.x) atomicAdd(accg + i, (double)red[i]);
