@@ -53,6 +53,19 @@ __device__ __forceinline__ float act_grad(float z, int act) {
     }
 }
 
+// compile-time activation (ACT >= 0) or run-time dispatch (ACT < 0): the run-time switch costs ~30 instructions
+// per element, which makes the elementwise kernels issue-bound
+template <int ACT> __device__ __forceinline__ float act_fwd_t(float z, int act) {
+    if (ACT == DSB200_ACT_RELU) return fmaxf(z, 0.f);
+    if (ACT == DSB200_ACT_IDENTITY) return z;
+    return act_fwd(z, act);
+}
+template <int ACT> __device__ __forceinline__ float act_grad_t(float z, int act) {
+    if (ACT == DSB200_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+    if (ACT == DSB200_ACT_IDENTITY) return 1.f;
+    return act_grad(z, act);
+}
+
 // Threads of a block are laid out [rows][G] (G = feature groups, a power of two): lanes whose index is equal
 // modulo G hold partial sums of the same features.  Sum v over those lanes (G < 32); afterwards lanes 0..G-1
 // of every warp hold the warp totals.  Cuts same-address shared-memory atomics by 32/G.

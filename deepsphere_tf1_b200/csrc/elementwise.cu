@@ -45,7 +45,7 @@ __global__ void sums_to_float_kernel(const double* __restrict__ s, float* out, i
 // ------------------------------------------------------------------------------------------
 // normalise -> + bias -> activation -> pool over p consecutive vertices.
 // One thread owns VEC features of one pooled (sample, vertex) row.
-template <int VEC>
+template <int VEC, int ACT>
 __global__ void __launch_bounds__(256)
 bn_act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ bias, float* __restrict__ out,
@@ -75,7 +75,7 @@ bn_act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
             }
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                const float a = act_fwd((t[v] - mu[v]) * rs[v] + bs[v], act);
+                const float a = act_fwd_t<ACT>((t[v] - mu[v]) * rs[v] + bs[v], act);
                 acc[v] = (pool == DSB200_POOL_MAX) ? fmaxf(acc[v], a) : acc[v] + a;
             }
         }
@@ -114,7 +114,7 @@ template <int VEC> __device__ __forceinline__ void store_vec(float* p, const flo
     }
 }
 
-template <int VEC, int MODE>
+template <int VEC, int MODE, int ACT>
 __global__ void __launch_bounds__(256)
 bn_act_pool_bwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ bias, const float* __restrict__ dout, float* __restrict__ gz,
@@ -161,7 +161,7 @@ bn_act_pool_bwd_kernel(const float* __restrict__ y, const float* __restrict__ me
                         if (is_max) {
 #pragma unroll
                             for (int v = 0; v < VEC; ++v) {
-                                const float a = act_fwd((yv[j][v] - mu[v]) * rs[v] + bs[v], act);
+                                const float a = act_fwd_t<ACT>((yv[j][v] - mu[v]) * rs[v] + bs[v], act);
                                 if (a > best[v]) { best[v] = a; arg[v] = j; }
                             }
                         }
@@ -175,7 +175,7 @@ bn_act_pool_bwd_kernel(const float* __restrict__ y, const float* __restrict__ me
                         for (int v = 0; v < VEC; ++v) {
                             const float xh = (yv[j][v] - mu[v]) * rs[v];
                             float g = 0.f;
-                            if (!is_max || arg[v] == j) g = d[v] * inv * act_grad(xh + bs[v], act);
+                            if (!is_max || arg[v] == j) g = d[v] * inv * act_grad_t<ACT>(xh + bs[v], act);
                             if (MODE != 2) { s1[v] += g; s2[v] = fmaf(g, xh, s2[v]); }
                             o[v] = MODE == 2 ? rs[v] * (g - m1[v] - xh * m2[v]) : g;
                         }
@@ -193,7 +193,7 @@ bn_act_pool_bwd_kernel(const float* __restrict__ y, const float* __restrict__ me
                         load_vec<VEC>(yp + (long long)j * F, yv);
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) {
-                            const float a = act_fwd((yv[v] - mu[v]) * rs[v] + bs[v], act);
+                            const float a = act_fwd_t<ACT>((yv[v] - mu[v]) * rs[v] + bs[v], act);
                             if (a > best[v]) { best[v] = a; arg[v] = j; }
                         }
                     }
@@ -205,7 +205,7 @@ bn_act_pool_bwd_kernel(const float* __restrict__ y, const float* __restrict__ me
                     for (int v = 0; v < VEC; ++v) {
                         const float xh = (yv[v] - mu[v]) * rs[v];
                         float g = 0.f;
-                        if (!is_max || arg[v] == j) g = d[v] * inv * act_grad(xh + bs[v], act);
+                        if (!is_max || arg[v] == j) g = d[v] * inv * act_grad_t<ACT>(xh + bs[v], act);
                         if (MODE != 2) { s1[v] += g; s2[v] = fmaf(g, xh, s2[v]); }
                         o[v] = MODE == 2 ? rs[v] * (g - m1[v] - xh * m2[v]) : g;
                     }
@@ -630,11 +630,17 @@ extern "C" int dsb200_bn_act_pool_fwd(const float* y, const float* mean, const f
     DSB_REQUIRE(M % p == 0, "bn_act_pool_fwd: M must be a multiple of p");
     DSB_REQUIRE((mean == nullptr) == (rstd == nullptr), "bn_act_pool_fwd: mean and rstd go together");
     const long long Rout = (long long)B * (M / p);
+#define DSB_FWD(V, A, G) bn_act_pool_fwd_kernel<V, A><<<G, 256, 0, STREAM>>>(y, mean, rstd, bias, out, Rout, F / V, p, pool, act)
     if (F % 4 == 0 && aligned16(y, out)) {
-        bn_act_pool_fwd_kernel<4><<<grid_for(Rout * (F / 4), 256), 256, 0, STREAM>>>(y, mean, rstd, bias, out, Rout, F / 4, p, pool, act);
+        const int g = grid_for(Rout * (F / 4), 256);
+        if (act == DSB200_ACT_RELU) DSB_FWD(4, DSB200_ACT_RELU, g);
+        else if (act == DSB200_ACT_IDENTITY) DSB_FWD(4, DSB200_ACT_IDENTITY, g);
+        else DSB_FWD(4, -1, g);
     } else {
-        bn_act_pool_fwd_kernel<1><<<grid_for(Rout * F, 256), 256, 0, STREAM>>>(y, mean, rstd, bias, out, Rout, F, p, pool, act);
+        const int g = grid_for(Rout * F, 256);
+        DSB_FWD(1, -1, g);
     }
+#undef DSB_FWD
     DSB_LAUNCH_CHECK();
 }
 
@@ -649,16 +655,20 @@ static int bn_act_pool_bwd_launch(const float* y, const float* mean, const float
     const long long Rout = (long long)B * (M / p);
     const size_t smem = 2 * (size_t)F * sizeof(float);
     const bool a16 = ((((uintptr_t)y | (uintptr_t)dout | (uintptr_t)gz) & 15) == 0);
+#define DSB_BWD(V, A) bn_act_pool_bwd_kernel<V, MODE, A><<<grid, 256, smem, st>>>(y, mean, rstd, bias, dout, gz, sums_bwd, count, Rout, F / V, p, pool, act)
     if (F % 4 == 0 && F / 4 <= 256 && a16) {
         const int Fv = F / 4, rpb = 256 / Fv;
         const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 8);
-        bn_act_pool_bwd_kernel<4, MODE><<<grid, 256, smem, st>>>(y, mean, rstd, bias, dout, gz, sums_bwd, count, Rout, Fv, p, pool, act);
+        if (act == DSB200_ACT_RELU) DSB_BWD(4, DSB200_ACT_RELU);
+        else if (act == DSB200_ACT_IDENTITY) DSB_BWD(4, DSB200_ACT_IDENTITY);
+        else DSB_BWD(4, -1);
     } else {
         DSB_REQUIRE(F <= 256, "bn_act_pool_bwd: F must be a multiple of 4 when > 256");
         const int rpb = 256 / F;
         const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 8);
-        bn_act_pool_bwd_kernel<1, MODE><<<grid, 256, smem, st>>>(y, mean, rstd, bias, dout, gz, sums_bwd, count, Rout, F, p, pool, act);
+        DSB_BWD(1, -1);
     }
+#undef DSB_BWD
     DSB_LAUNCH_CHECK();
 }
 

@@ -35,13 +35,15 @@ struct Planes {
 // sample index fastest in the interleaved case (coalesced basis reads); outputs keep the classic layout.
 struct RowMap {
     int B, M, Mo, p, il;
-    __device__ __forceinline__ void decode(long long t, int& b, int& mo) const {
-        if (il) { mo = (int)(t / B); b = (int)(t - (long long)mo * B); }
-        else { b = (int)(t / Mo); mo = (int)(t - (long long)b * Mo); }
+    // B * M < 2^31 (checked by the launchers): 32-bit index arithmetic
+    __device__ __forceinline__ void decode(long long t64, int& b, int& mo) const {
+        const unsigned t = (unsigned)t64;
+        if (il) { mo = (int)(t / (unsigned)B); b = (int)(t - (unsigned)mo * (unsigned)B); }
+        else { b = (int)(t / (unsigned)Mo); mo = (int)(t - (unsigned)b * (unsigned)Mo); }
     }
-    __device__ __forceinline__ long long xrow(int b, int mo, int j) const {
+    __device__ __forceinline__ int xrow(int b, int mo, int j) const {
         const int m = mo * p + j;
-        return il ? (long long)m * B + b : (long long)b * M + m;
+        return il ? m * B + b : b * M + m;
     }
 };
 
@@ -309,14 +311,15 @@ smallconv_fwd_fast_kernel(Planes P, RowMap rm, const float* __restrict__ W, cons
     for (int q = 0; q < Q; ++q) cp[q] = P.col(q);
     const int Fin = P.Fin;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
-        const long long t = g / Fg;
-        const int f0 = (int)(g - t * Fg) * 8;
+        const unsigned gu = (unsigned)g;                 // Rout * Fg < 2^31
+        const unsigned t = gu / (unsigned)Fg;
+        const int f0 = (int)(gu - t * (unsigned)Fg) * 8;
         int b, mo;
         rm.decode(t, b, mo);
         float x[4][Q];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const long long r = rm.xrow(b, mo, j) * Fin;
+            const long long r = (long long)rm.xrow(b, mo, j) * Fin;
 #pragma unroll
             for (int q = 0; q < Q; ++q) x[j][q] = __ldg(cp[q] + r);
         }
@@ -392,7 +395,7 @@ smallconv_bwd_fast_kernel(Planes P, RowMap rm, const float* __restrict__ bias, c
         float x[4][Q];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const long long r = rm.xrow(b, mo, j) * Fin;
+            const long long r = (long long)rm.xrow(b, mo, j) * Fin;
 #pragma unroll
             for (int q = 0; q < Q; ++q) x[j][q] = __ldg(cp[q] + r);
         }
@@ -402,10 +405,11 @@ smallconv_bwd_fast_kernel(Planes P, RowMap rm, const float* __restrict__ bias, c
             const uint32_t arg = ((v < 4 ? ab.x >> (8 * v) : ab.y >> (8 * (v - 4))) & 3u);
             s1[v] += gz;
             s2[v] = fmaf(gz, o[v] - bs[v], s2[v]);           // xhat = out - bias wherever gz != 0
+            const bool b0 = (arg & 1u) != 0, b1 = (arg & 2u) != 0;
 #pragma unroll
             for (int q = 0; q < Q; ++q) {
-                const float xs = arg == 0 ? x[0][q] : arg == 1 ? x[1][q] : arg == 2 ? x[2][q] : x[3][q];
-                A[q][v] = fmaf(xs, gz, A[q][v]);
+                const float lo = b0 ? x[1][q] : x[0][q], hi = b0 ? x[3][q] : x[2][q];
+                A[q][v] = fmaf(b1 ? hi : lo, gz, A[q][v]);
             }
         }
     }
@@ -535,6 +539,7 @@ extern "C" int dsb200_smallconv_fwd(const float* x0, const float* xk, const floa
     DSB_REQUIRE(smallconv_ok(Fin, K, Fout), "smallconv_fwd: unsupported shape");
     DSB_REQUIRE((mean == nullptr) == (rstd == nullptr), "smallconv_fwd: mean and rstd go together");
     const long long R = (long long)B * M, Rout = R / p;
+    DSB_REQUIRE(R < 0x7fffffffLL, "smallconv_fwd: too many rows");
     Planes P{x0, xk, R * (long long)Fin, Fin, K};
     const int Q = Fin * K;
     const size_t smem = (size_t)(Q + 3) * Fout * sizeof(float);
@@ -559,6 +564,7 @@ extern "C" int dsb200_smallconv_bwd(const float* x0, const float* xk, const floa
     DSB_REQUIRE(x0 && W && dout && acc && (K == 1 || xk) && B > 0 && M > 0 && p >= 1 && M % p == 0, "smallconv_bwd: bad arguments");
     DSB_REQUIRE(smallconv_ok(Fin, K, Fout), "smallconv_bwd: unsupported shape");
     const long long R = (long long)B * M, Rout = R / p;
+    DSB_REQUIRE(R < 0x7fffffffLL, "smallconv_bwd: too many rows");
     Planes P{x0, xk, R * (long long)Fin, Fin, K};
     const int Q = Fin * K;
     const size_t smem = (size_t)(2 * Q + 5) * Fout * sizeof(float);
