@@ -13,6 +13,7 @@
 // layout and stay resident in shared memory.  TMEM accumulators are double buffered when they fit.
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace dsb200 {
 namespace tc {
@@ -86,6 +87,7 @@ struct alignas(64) RowGemmParams {
     int nstages, acc_stages;
     int ntiles;
     int wstream;               // 1: the weight image is too large to stay resident: each stage carries its k-blocks' weights
+    int tmem_cols;             // TMEM columns to allocate (power of two >= acc_stages * 2 * Npad)
 };
 
 // Element (j, n2, kk) of the weight image: k-block j, row n2 in [0, 2*Npad) (hi rows then lo rows), column kk.
@@ -146,7 +148,7 @@ __device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane)
 }
 
 template <int MODE, bool SUMS>
-__global__ void __launch_bounds__(kRgThreads, 1)
+__global__ void __launch_bounds__(kRgThreads, 2)
 rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
 {
     extern __shared__ uint8_t smem_raw[];
@@ -180,7 +182,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
         prefetch_tmap(&p.tmA0);
         if (MODE == MODE_FWD && p.K > 1) prefetch_tmap(&p.tmAk);
     }
-    if (warp == kWarpMma) tmem_alloc(tmem_slot, 512);
+    if (warp == kWarpMma) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     if (SUMS) for (int i = threadIdx.x; i < 2 * 256; i += kRgThreads) red[i] = 0.f;
 
     // ---- weights: rows [0,Npad) = TF32 hi, [Npad,2Npad) = lo, K-major swizzled, resident for the whole kernel
@@ -401,16 +403,33 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kWarpMma) tmem_dealloc(tmem_base, 512);
+    if (warp == kWarpMma) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 struct RowGemmPlan {
-    int kc, swz, nchunk, nkb, Npad, G, nstages, acc_stages, wstream;
+    int kc, swz, nchunk, nkb, Npad, G, nstages, acc_stages, wstream, tmem_cols, ctas;
     size_t smem, wbytes;
 };
 
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 // Shared-memory plan; returns false if the shape does not fit the tensor-core path.
-static bool plan_rowgemm(int red_per_plane, int planes, int Npad, bool can_stream, RowGemmPlan* pl)
+static bool plan_rowgemm_n(int red_per_plane, int planes, int Npad, bool can_stream, int ctas, RowGemmPlan* pl);
+
+// Try `ctas` CTAs per SM first (independent pipelines hide the TMA -> split -> MMA -> epilogue latency chain of a
+// CTA), fall back to one.
+static bool plan_rowgemm(int red_per_plane, int planes, int Npad, bool can_stream, int ctas, RowGemmPlan* pl)
+{
+    for (; ctas >= 1; --ctas)
+        if (plan_rowgemm_n(red_per_plane, planes, Npad, can_stream, ctas, pl) && (ctas == 1 || (!pl->wstream && pl->nstages >= 3))) return true;
+    return false;
+}
+
+static bool plan_rowgemm_n(int red_per_plane, int planes, int Npad, bool can_stream, int ctas, RowGemmPlan* pl)
 {
     if (red_per_plane % 8) return false;
     pl->kc = red_per_plane % 32 == 0 ? 32 : red_per_plane % 16 == 0 ? 16 : 8;
@@ -422,7 +441,14 @@ static bool plan_rowgemm(int red_per_plane, int planes, int Npad, bool can_strea
     if (pl->G > pl->nkb) pl->G = pl->nkb;
     pl->wbytes = (size_t)pl->nkb * 2 * Npad * pl->kc * 4;
     const size_t fixed = 1024 /*align*/ + 3 * kMaxStages * 8 + 4 * 8 + 16 + 2 * 256 * 4 + 64;
-    const size_t budget = 227 * 1024;
+    const size_t budget = (size_t)(227 * 1024) / ctas - (ctas > 1 ? 1024 : 0);
+    const size_t min_smem = (size_t)(227 * 1024) / (ctas + 1) + 1024;     // never more CTAs per SM than planned (TMEM)
+    pl->ctas = ctas;
+    pl->acc_stages = (4 * Npad * ctas <= 512) ? 2 : 1;
+    if (pl->acc_stages * 2 * Npad * ctas > 512) return false;
+    pl->tmem_cols = 32;
+    while (pl->tmem_cols < pl->acc_stages * 2 * Npad) pl->tmem_cols <<= 1;
+    if (pl->tmem_cols * ctas > 512) return false;
     size_t stage = 2 * (size_t)pl->G * kTileM * pl->kc * 4;
     pl->wstream = 0;
     if (can_stream && pl->wbytes + fixed + 4 * stage > budget) {
@@ -434,8 +460,8 @@ static bool plan_rowgemm(int red_per_plane, int planes, int Npad, bool can_strea
         size_t ns = (budget - fixed) / stage;
         if (ns > kMaxStages) ns = kMaxStages;
         pl->nstages = (int)ns;
-        pl->acc_stages = (4 * Npad <= 512) ? 2 : 1;
         pl->smem = fixed + ns * stage;
+        if (pl->smem < min_smem) pl->smem = min_smem;
         return true;
     }
     while (pl->G > 1 && pl->wbytes + fixed + 3 * stage > budget) { pl->G >>= 1; stage >>= 1; }
@@ -443,14 +469,30 @@ static bool plan_rowgemm(int red_per_plane, int planes, int Npad, bool can_strea
     size_t ns = (budget - pl->wbytes - fixed) / stage;
     if (ns > kMaxStages) ns = kMaxStages;
     pl->nstages = (int)ns;
-    pl->acc_stages = (4 * Npad <= 512) ? 2 : 1;
     pl->smem = pl->wbytes + fixed + ns * stage;
-    if (pl->smem < 120 * 1024) pl->smem = 120 * 1024;      // one CTA per SM: every CTA allocates all 512 TMEM columns
+    if (pl->smem < min_smem) pl->smem = min_smem;
     return true;
 }
 
+// CTAs per SM the register file allows for this instance (65536 registers per SM)
 template <int MODE, bool SUMS>
-static int launch_rowgemm(RowGemmParams& p, size_t smem, float* image, cudaStream_t s)
+static int rowgemm_max_ctas()
+{
+    static int cached = 0;
+    if (!cached) {
+        cudaFuncAttributes a;
+        cached = 1;
+        if (cudaFuncGetAttributes(&a, rowgemm_tc_kernel<MODE, SUMS>) == cudaSuccess && a.numRegs > 0) {
+            const int regs = (a.numRegs + 7) / 8 * 8;
+            cached = 65536 / (regs * kRgThreads);
+            if (cached < 1) cached = 1;
+        }
+    }
+    return cached;
+}
+
+template <int MODE, bool SUMS>
+static int launch_rowgemm(RowGemmParams& p, size_t smem, int ctas, float* image, cudaStream_t s)
 {
     static bool configured = false;                // per template instance
     if (!configured) {
@@ -464,7 +506,8 @@ static int launch_rowgemm(RowGemmParams& p, size_t smem, float* image, cudaStrea
         pack_w_kernel<MODE><<<(total + 255) / 256, 256, 0, s>>>(p, image);
         count_launch();
     }
-    const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
+    const int slots = kNumSMs * ctas;
+    const int grid = p.ntiles < slots ? p.ntiles : slots;
     rowgemm_tc_kernel<MODE, SUMS><<<grid, kRgThreads, smem, s>>>(p);
     DSB_LAUNCH_CHECK();
 }
@@ -487,8 +530,12 @@ int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, 
     if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y | (uintptr_t)workspace) & 15) != 0) return 1;
     const int Npad = (Fout + 15) / 16 * 16;
     RowGemmPlan pl;
-    if (!plan_rowgemm(Fin, K, Npad, workspace != nullptr, &pl)) return 1;
+    int ctas = env_int("DSB200_RG_CTAS", 2);
+    const int rmax = bn_sums ? rowgemm_max_ctas<MODE_FWD, true>() : rowgemm_max_ctas<MODE_FWD, false>();
+    if (ctas > rmax) ctas = rmax;
+    if (!plan_rowgemm(Fin, K, Npad, workspace != nullptr, ctas, &pl)) return 1;
     RowGemmParams p;
+    p.tmem_cols = pl.tmem_cols;
     if (make_tmap_f32(&p.tmA0, x0, Fin, R, 1, pl.kc, kTileM, pl.swz, false)) return 1;
     if (K > 1) { if (make_tmap_f32(&p.tmAk, xk, Fin, R, K - 1, pl.kc, kTileM, pl.swz, true)) return 1; }
     else p.tmAk = p.tmA0;
@@ -497,8 +544,8 @@ int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, 
     p.nstages = pl.nstages; p.acc_stages = pl.acc_stages; p.wstream = pl.wstream;
     p.ntiles = (int)((R + kTileM - 1) / kTileM);
     float* image = (float*)workspace;
-    if (!bn_sums) return launch_rowgemm<MODE_FWD, false>(p, pl.smem, image, s);
-    return launch_rowgemm<MODE_FWD, true>(p, pl.smem, image, s);
+    if (!bn_sums) return launch_rowgemm<MODE_FWD, false>(p, pl.smem, pl.ctas, image, s);
+    return launch_rowgemm<MODE_FWD, true>(p, pl.smem, pl.ctas, image, s);
 }
 
 // Data gradient on the tensor cores: G[k][r][fi] = sum_fo dY[r, fo] W[fi*K + k, fo].
@@ -512,9 +559,12 @@ int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R,
     const int nb = (Q + 159) / 160;
     const int NB = ((Q + nb - 1) / nb + 15) / 16 * 16;
     RowGemmPlan pl;
-    if (!plan_rowgemm(Fout, 1, NB, workspace != nullptr, &pl)) return 1;
+    int ctas = env_int("DSB200_RG_CTAS", 2);
+    if (ctas > rowgemm_max_ctas<MODE_BWD_DATA, false>()) ctas = rowgemm_max_ctas<MODE_BWD_DATA, false>();
+    if (!plan_rowgemm(Fout, 1, NB, workspace != nullptr, ctas, &pl)) return 1;
     for (int b = 0; b < nb; ++b) {
         RowGemmParams p;
+        p.tmem_cols = pl.tmem_cols;
         if (make_tmap_f32(&p.tmA0, dY, Fout, R, 1, pl.kc, kTileM, pl.swz, false)) return 1;
         p.tmAk = p.tmA0;
         p.W = W; p.out = G; p.bn_sums = nullptr; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
@@ -523,7 +573,7 @@ int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R,
         p.swz = pl.swz; p.nstages = pl.nstages; p.acc_stages = pl.acc_stages; p.wstream = pl.wstream;
         p.ntiles = (int)((R + kTileM - 1) / kTileM);
         float* image = workspace ? (float*)((uint8_t*)workspace + (size_t)b * pl.wbytes) : nullptr;
-        int rc = launch_rowgemm<MODE_BWD_DATA, false>(p, pl.smem, image, s);
+        int rc = launch_rowgemm<MODE_BWD_DATA, false>(p, pl.smem, pl.ctas, image, s);
         if (rc) return rc;
     }
     return 0;
@@ -553,8 +603,12 @@ struct alignas(64) WGradParams {
     float* dW;
     long long R;
     int Fin, K, Fout;
-    int nblkA, nblkB;          // 32-column blocks per plane of X (Fin >= 32) / of dY
-    int pack;                  // Fin < 32: planes 1..K-1 are packed `pack` = 32/Fin to a block (plane 0 has its own block)
+    int nblkA, nblkB;          // 32-column blocks per plane of X / of dY (after row packing)
+    int pack;                  // unused plane packing experiment (always 0)
+    int rpk;                   // Fin < 32: rpk = 32/Fin consecutive rows are viewed as ONE row of rpk*Fin features (and of
+                               // rpk*Fout gradient columns); only the diagonal blocks (same sub-row) of D are used
+    int tmem_cols;             // TMEM columns to allocate (power of two >= mtiles * 2 * Np)
+    int vec_red;               // dW rows are 16-byte aligned: red.global.add.v4.f32
     int nA;                    // number of X blocks per stage
     int pad_blocks;            // unused blocks at the end of a stage (the last 128-wide tile of q may read past X_lo)
     int RS;                    // rows per pipeline stage (multiple of 8)
@@ -600,7 +654,7 @@ wgrad_tc_kernel(const __grid_constant__ WGradParams p)
         prefetch_tmap(&p.tmXk);
         prefetch_tmap(&p.tmdY);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -709,28 +763,31 @@ wgrad_tc_kernel(const __grid_constant__ WGradParams p)
         const int qd = warp & 3;
         mbar_wait(acc_full, 0, 15);
         tc_fence_after();
+        const int Fx = p.Fin * p.rpk;                                // features of a packed row of X
         for (int mt = 0; mt < p.mtiles; ++mt) {
             const int q = mt * kTileM + qd * 32 + lane;              // (block, column in block) of the padded Xcat
             const int bq = q / kMNBlock, cq = q - bq * kMNBlock;
-            int k, fi;
-            if (p.pack > 0) {
-                if (bq == 0) { k = 0; fi = cq; }
-                else { k = 1 + (bq - 1) * p.pack + cq / p.Fin; fi = cq % p.Fin; }
-            } else {
-                k = bq / p.nblkA;
-                fi = (bq - k * p.nblkA) * kMNBlock + cq;
-            }
-            const bool ok = bq < nA && k < p.K && fi < p.Fin;
+            const int k = bq / p.nblkA;
+            const int cc = (bq - k * p.nblkA) * kMNBlock + cq;       // column within the packed plane
+            const int h = cc / p.Fin, fi = cc - h * p.Fin;           // sub-row, feature
+            const bool ok = bq < nA && k < p.K && cc < Fx;
             float* dst = p.dW + ((long long)fi * p.K + k) * p.Fout;
             const uint32_t tbase = tmem_base + (uint32_t)(mt * acc_cols) + ((uint32_t)(qd * 32) << 16);
             for (int c0 = 0; c0 < p.Fout; c0 += 8) {
-                float hi[8], lo[8];
-                tmem_ld8(tbase + c0, hi);
-                tmem_ld8(tbase + Np + c0, lo);
-                tmem_ld_wait();
-                if (ok) {
+                for (int hh = 0; hh < p.rpk; ++hh) {                 // TMEM loads are warp-uniform: read every sub-row block
+                    float hi[8], lo[8];
+                    tmem_ld8(tbase + hh * p.Fout + c0, hi);
+                    tmem_ld8(tbase + Np + hh * p.Fout + c0, lo);
+                    tmem_ld_wait();
+                    if (ok && hh == h) {
+                        if (p.vec_red) {
+                            red_add_v4(dst + c0, hi[0] + lo[0], hi[1] + lo[1], hi[2] + lo[2], hi[3] + lo[3]);
+                            red_add_v4(dst + c0 + 4, hi[4] + lo[4], hi[5] + lo[5], hi[6] + lo[6], hi[7] + lo[7]);
+                        } else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) atomicAdd(dst + c0 + e, hi[e] + lo[e]);
+                            for (int e = 0; e < 8; ++e) atomicAdd(dst + c0 + e, hi[e] + lo[e]);
+                        }
+                    }
                 }
             }
         }
@@ -738,7 +795,7 @@ wgrad_tc_kernel(const __grid_constant__ WGradParams p)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
 }
 
 int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K,
@@ -747,47 +804,62 @@ int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, fl
     if (R < 128 || R > 0x7fffff00LL || (Fin & 7) || (Fout & 7) || Fout > 256) return 1;
     if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)dY) & 15) != 0) return 1;
     WGradParams p;
-    p.nblkA = (Fin + kMNBlock - 1) / kMNBlock;
-    p.nblkB = (Fout + kMNBlock - 1) / kMNBlock;
-    // Packing several narrow planes into one 128-byte row with a 3-D box does NOT work: under the swizzled
-    // modes TMA pads every inner-box row to the swizzle span (tools/experiments/tma_box_layout.cu), so narrow
-    // planes are zero-filled to 32 columns instead (pack = 0).
+    // Narrow planes (Fin < 32): view rpk = 32/Fin consecutive rows as one row, X [R/rpk, 32] and dY [R/rpk, rpk*Fout].
+    // Every TMA row is then a full 128-byte line and no shared memory holds zero padding; the product has rpk x rpk
+    // blocks of which the rpk diagonal ones add up to dW (the tensor pipe has the headroom for the rest).
+    int rpk = 1;
+    if (Fin < kMNBlock && kMNBlock % Fin == 0 && R % (kMNBlock / Fin) == 0 && (kMNBlock / Fin) * Fout <= 256) rpk = kMNBlock / Fin;
+    if (env_int("DSB200_WG_NOPACK", 0)) rpk = 1;
+    p.rpk = rpk;
+    const long long Rp = R / rpk;
+    const int Fx = Fin * rpk, Fy = Fout * rpk;
+    p.nblkA = (Fx + kMNBlock - 1) / kMNBlock;
+    p.nblkB = (Fy + kMNBlock - 1) / kMNBlock;
     p.pack = 0;
-    const int nA = p.pack > 0 ? 1 + (K - 1 + p.pack - 1) / p.pack : K * p.nblkA;
+    const int nA = K * p.nblkA;
     p.nA = nA;
     const int nB = p.nblkB;
     p.mtiles = (nA * kMNBlock + kTileM - 1) / kTileM;
-    if (p.mtiles * 2 * nB * kMNBlock > 512) return 1;
+    const int need_cols = p.mtiles * 2 * nB * kMNBlock;
+    if (need_cols > 512) return 1;
+    int tcols = 32;
+    while (tcols < need_cols) tcols <<= 1;
+    p.tmem_cols = tcols;
+    // CTAs per SM: limited by TMEM (512 columns) and by shared memory
+    int ctas = 512 / tcols;
+    const int want = env_int("DSB200_WG_CTAS", 2);
+    if (ctas > want) ctas = want;
+    if (ctas < 1) ctas = 1;
     // the last 128-wide tile of q may read past the X_lo blocks: keep it inside the stage ([X][X_lo][dY][dY_lo][pad])
     p.pad_blocks = p.mtiles * (kTileM / kMNBlock) - (nA + 2 * nB);
     if (p.pad_blocks < 0) p.pad_blocks = 0;
-    int RS = (48 * 1024) / (kMNBlock * 4 * (2 * (nA + nB) + p.pad_blocks)) / 8 * 8;     // ~48 KB stages
+    const int per_row = kMNBlock * 4 * (2 * (nA + nB) + p.pad_blocks);
+    const int stage_kb = env_int("DSB200_WG_STAGE_KB", ctas > 1 ? 32 : 48);
+    int RS = (stage_kb * 1024) / per_row / 8 * 8;
     if (RS > 128) RS = 128;
-    if (RS < 8) return 1;
+    if (RS < 8) RS = 8;
+    if (RS > Rp) return 1;
     p.RS = RS;
-    const size_t stage = (size_t)RS * kMNBlock * 4 * (2 * (nA + nB) + p.pad_blocks);
+    const size_t stage = (size_t)RS * per_row;
     const size_t fixed = 1024 + 3 * kMaxStages * 8 + 64;
-    const size_t budget = 227 * 1024;
+    const size_t budget = (size_t)(227 * 1024) / ctas - (ctas > 1 ? 1024 : 0);      // 1 KB per CTA is reserved by the driver
+    if (budget < fixed + 2 * stage) return 1;
     size_t ns = (budget - fixed) / stage;
     if (ns > kMaxStages) ns = kMaxStages;
-    if (ns < 2) return 1;
     p.nstages = (int)ns;
     size_t smem = fixed + ns * stage;
-    if (smem < 120 * 1024) smem = 120 * 1024;
+    const size_t min_smem = (size_t)(227 * 1024) / (ctas + 1) + 1024;                  // never more CTAs per SM than TMEM allows
+    if (smem < min_smem) smem = min_smem;
     const int SW = 4;                                                   // 128B swizzle, 32B atoms
-    if (make_tmap_f32(&p.tmX0, x0, Fin, R, 1, kMNBlock, RS, SW, false)) return 1;
-    if (p.pack > 0) {
-        // basis [K-1][R][Fin] seen as (fi, plane, row): a box of Fin x pack x RS lands as RS rows of pack*Fin = 32 floats
-        const cuuint64_t dims[3] = {(cuuint64_t)Fin, (cuuint64_t)(K - 1), (cuuint64_t)R};
-        const cuuint64_t strides[2] = {(cuuint64_t)R * Fin * 4, (cuuint64_t)Fin * 4};
-        const cuuint32_t box[3] = {(cuuint32_t)Fin, (cuuint32_t)p.pack, (cuuint32_t)RS};
-        if (make_tmap_nd(&p.tmXk, xk, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
-    } else if (K > 1) { if (make_tmap_f32(&p.tmXk, xk, Fin, R, K - 1, kMNBlock, RS, SW, true)) return 1; }
+    if (make_tmap_f32(&p.tmX0, x0, Fx, Rp, 1, kMNBlock, RS, SW, false)) return 1;
+    if (K > 1) { if (make_tmap_f32(&p.tmXk, xk, Fx, Rp, K - 1, kMNBlock, RS, SW, true)) return 1; }
     else p.tmXk = p.tmX0;
-    if (make_tmap_f32(&p.tmdY, dY, Fout, R, 1, kMNBlock, RS, SW, false)) return 1;
-    p.dW = dW; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
-    p.iters_total = (R + RS - 1) / RS;
-    int grid = p.iters_total < kNumSMs ? (int)p.iters_total : kNumSMs;
+    if (make_tmap_f32(&p.tmdY, dY, Fy, Rp, 1, kMNBlock, RS, SW, false)) return 1;
+    p.dW = dW; p.R = Rp; p.Fin = Fin; p.K = K; p.Fout = Fout;
+    p.vec_red = (((uintptr_t)dW & 15) == 0) ? 1 : 0;
+    p.iters_total = (Rp + RS - 1) / RS;
+    const long long slots = (long long)kNumSMs * ctas;
+    int grid = p.iters_total < slots ? (int)p.iters_total : (int)slots;
     p.iters_per_cta = (p.iters_total + grid - 1) / grid;
     grid = (int)((p.iters_total + p.iters_per_cta - 1) / p.iters_per_cta);
     static bool configured = false;

@@ -231,6 +231,118 @@ bn_act_pool_bwd_kernel(const float* __restrict__ y, const float* __restrict__ me
     }
 }
 
+// Lean path of the two-pass batch-norm backward for the combination every DeepSphere encoder layer uses:
+// relu + max pool over P consecutive vertices (or no pool, P = 1), F % 4 == 0.
+//
+// Pass 1 needs no pre-pool tensor at all.  gz is non-zero only at the arg-max child of a pooled row, and only
+// where the pooled output is positive; there  xhat = out - bias  (out = relu(max_j xhat_j + bias)).  Hence
+//   sum gz       = sum_{pooled rows} [out > 0] dout
+//   sum gz*xhat  = sum_{pooled rows} [out > 0] dout (out - bias)
+// read from the two POOLED tensors (2 * Y/P bytes instead of Y + Y/P).
+__global__ void __launch_bounds__(256)
+bn_relu_pool_sums_kernel(const float* __restrict__ out, const float* __restrict__ dout, const float* __restrict__ bias,
+                         double* __restrict__ sums_bwd, long long Rout, int Fv)
+{
+    extern __shared__ float red[];                          // [2][F]
+    const int F = Fv * 4;
+    for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    const int rows_per_block = blockDim.x / Fv;
+    const int fvi = threadIdx.x % Fv, rl = threadIdx.x / Fv;
+    const int f0 = fvi * 4;
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    float bs[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) bs[v] = bias ? __ldg(bias + f0 + v) : 0.f;
+    if (rl < rows_per_block) {
+        const long long step = (long long)gridDim.x * rows_per_block;
+#pragma unroll 4
+        for (long long ro = (long long)blockIdx.x * rows_per_block + rl; ro < Rout; ro += step) {
+            const float4 o = ldg4(out + ro * F + f0);
+            const float4 d = ldg4(dout + ro * F + f0);
+            const float ov[4] = {o.x, o.y, o.z, o.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float g = ov[v] > 0.f ? dv[v] : 0.f;
+                s1[v] += g;
+                s2[v] = fmaf(g, ov[v] - bs[v], s2[v]);
+            }
+        }
+    }
+    const bool pw = Fv < 32 && (Fv & (Fv - 1)) == 0 && (blockDim.x % Fv) == 0;
+    const bool leader = rl < rows_per_block && (!pw || (threadIdx.x & 31) < Fv);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        const float a1 = pw ? warp_sum_mod(s1[v], Fv) : s1[v];
+        const float a2 = pw ? warp_sum_mod(s2[v], Fv) : s2[v];
+        if (leader) { atomicAdd(&red[f0 + v], a1); atomicAdd(&red[F + f0 + v], a2); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) atomicAdd(sums_bwd + i, (double)red[i]);
+}
+
+// Pass 2: dy = rstd (gz - S1/n - xhat S2/n); one thread = one float4 feature group of one pooled row and its
+// P children.  The arg-max is recomputed from y (first maximum wins, as in the forward pass).
+template <int P>
+__global__ void __launch_bounds__(256)
+bn_relu_max_bwd_dy_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                          const float* __restrict__ bias, const float* __restrict__ dout, float* __restrict__ dy,
+                          const double* __restrict__ sums_bwd, double count, long long total, int Fv)
+{
+    extern __shared__ float par[];                          // [5][F]: mean, rstd, bias, S1/n, S2/n
+    const int F = Fv * 4;
+    for (int i = threadIdx.x; i < F; i += blockDim.x) {
+        par[i] = __ldg(mean + i);
+        par[F + i] = __ldg(rstd + i);
+        par[2 * F + i] = bias ? __ldg(bias + i) : 0.f;
+        par[3 * F + i] = (float)(sums_bwd[i] / count);
+        par[4 * F + i] = (float)(sums_bwd[F + i] / count);
+    }
+    __syncthreads();
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const long long ro = g / Fv;
+    const int f0 = (int)(g - ro * Fv) * 4;
+    const float4 mu4 = *reinterpret_cast<const float4*>(par + f0), rs4 = *reinterpret_cast<const float4*>(par + F + f0);
+    const float4 bs4 = *reinterpret_cast<const float4*>(par + 2 * F + f0);
+    const float4 a4 = *reinterpret_cast<const float4*>(par + 3 * F + f0), b4 = *reinterpret_cast<const float4*>(par + 4 * F + f0);
+    const float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rs[4] = {rs4.x, rs4.y, rs4.z, rs4.w}, bs[4] = {bs4.x, bs4.y, bs4.z, bs4.w};
+    const float m1[4] = {a4.x, a4.y, a4.z, a4.w}, m2[4] = {b4.x, b4.y, b4.z, b4.w};
+    const float4 d4 = ldg4(dout + ro * F + f0);
+    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+    const float* yp = y + (ro * P) * F + f0;
+    float* op = dy + (ro * P) * F + f0;
+    float xh[P][4];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const float4 q = ldg4(yp + (long long)j * F);
+        xh[j][0] = (q.x - mu[0]) * rs[0]; xh[j][1] = (q.y - mu[1]) * rs[1];
+        xh[j][2] = (q.z - mu[2]) * rs[2]; xh[j][3] = (q.w - mu[3]) * rs[3];
+    }
+    int arg[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        float best = xh[0][v] + bs[v];
+        arg[v] = 0;
+#pragma unroll
+        for (int j = 1; j < P; ++j) {
+            const float t = xh[j][v] + bs[v];
+            if (t > best) { best = t; arg[v] = j; }
+        }
+        if (!(best > 0.f)) arg[v] = -1;                      // relu inactive: no gradient at all
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        float o[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const float gg = arg[v] == j ? d[v] : 0.f;
+            o[v] = rs[v] * (gg - m1[v] - xh[j][v] * m2[v]);
+        }
+        st4(op + (long long)j * F, make_float4(o[0], o[1], o[2], o[3]));
+    }
+}
+
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const double* __restrict__ sums_bwd, double count, float* gz, long long R, int F)
@@ -655,6 +767,18 @@ static int bn_act_pool_bwd_launch(const float* y, const float* mean, const float
     const long long Rout = (long long)B * (M / p);
     const size_t smem = 2 * (size_t)F * sizeof(float);
     const bool a16 = ((((uintptr_t)y | (uintptr_t)dout | (uintptr_t)gz) & 15) == 0);
+    if (MODE == 2 && F % 4 == 0 && F <= 2048 && a16 && act == DSB200_ACT_RELU && mean && rstd &&
+        (p == 1 || (pool == DSB200_POOL_MAX && (p == 2 || p == 4)))) {
+        const long long total = Rout * (F / 4);
+        const long long blocks = (total + 255) / 256;
+        if (blocks <= 0x7fffffffLL) {
+            const size_t sm = 5 * (size_t)F * sizeof(float);
+#define DSB_DY(PP) bn_relu_max_bwd_dy_kernel<PP><<<(unsigned)blocks, 256, sm, st>>>(y, mean, rstd, bias, dout, gz, sums_bwd, count, total, F / 4)
+            if (p == 1) DSB_DY(1); else if (p == 2) DSB_DY(2); else DSB_DY(4);
+#undef DSB_DY
+            DSB_LAUNCH_CHECK();
+        }
+    }
 #define DSB_BWD(V, A) bn_act_pool_bwd_kernel<V, MODE, A><<<grid, 256, smem, st>>>(y, mean, rstd, bias, dout, gz, sums_bwd, count, Rout, F / V, p, pool, act)
     if (F % 4 == 0 && F / 4 <= 256 && a16) {
         const int Fv = F / 4, rpb = 256 / Fv;
@@ -686,6 +810,18 @@ extern "C" int dsb200_bn_act_pool_bwd_dy(const float* y, const float* mean, cons
 {
     DSB_REQUIRE(mean && rstd && dy && count > 0, "bn_act_pool_bwd_dy: bad arguments");
     return bn_act_pool_bwd_launch<2>(y, mean, rstd, bias, dout, dy, const_cast<double*>(sums_bwd), count, B, M, F, p, pool, act, STREAM);
+}
+
+extern "C" int dsb200_bn_relu_pool_sums(const float* out, const float* dout, const float* bias, double* sums_bwd,
+                                        long long Rout, int F, void* stream)
+{
+    DSB_REQUIRE(out && dout && sums_bwd && Rout > 0 && F > 0, "bn_relu_pool_sums: bad arguments");
+    DSB_REQUIRE(F % 4 == 0 && F <= 1024, "bn_relu_pool_sums: F must be a multiple of 4, at most 1024");
+    DSB_REQUIRE(aligned16(out, dout), "bn_relu_pool_sums: tensors must be 16-byte aligned");
+    const int Fv = F / 4, rpb = 256 / Fv;
+    const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 4);
+    bn_relu_pool_sums_kernel<<<grid, 256, 2 * (size_t)F * sizeof(float), STREAM>>>(out, dout, bias, sums_bwd, Rout, Fv);
+    DSB_LAUNCH_CHECK();
 }
 
 extern "C" int dsb200_bn_bwd_apply(const float* y, const float* mean, const float* rstd, const double* sums_bwd,

@@ -139,10 +139,12 @@ class _ChebStage(object):
         if self.post:
             b = m._P.views[self.scope + '/bias'] if self.has_bias else None
             out = ops.bn_act_pool_fwd(y, mean, rstd, b, self.p, self.pool, self.act)
+        if save:
+            # the pooled output feeds pass 1 of the batch-norm backward (it is the next layer's input anyway)
+            lean = self.post and self.bn and training and ops.bn_relu_pool_sums_supported(self.Fout, self.p, self.pool, self.act)
+            self.saved = (x, basis, y, mean, rstd, count, training, out if lean else None)
         if self.keep is not None and self.keep != out.shape[1]:
             out = ops.vertex_resize(out, self.keep, 0.0)                   # x[:, :p, :]  (models.py:1138,1157)
-        if save:
-            self.saved = (x, basis, y, mean, rstd, count, training)
         return out
 
     def _forward_small(self, x, W, training, save):
@@ -205,7 +207,7 @@ class _ChebStage(object):
             if need_dx:
                 raise RuntimeError('the fused input layer does not produce an input gradient')
             return self._backward_small(dout)
-        x, basis, y, mean, rstd, count, training = self.saved
+        x, basis, y, mean, rstd, count, training, out = self.saved
         self.saved = None
         B, M, Fin = x.shape
         if self.keep is not None and dout.shape[1] != M // self.p:
@@ -214,7 +216,10 @@ class _ChebStage(object):
         if self.post:
             b = m._P.views[self.scope + '/bias'] if self.has_bias else None
             two_pass = self.bn and training          # batch norm: sums first, then dy directly (gz never stored)
-            dy, sums = ops.bn_act_pool_bwd(y, mean, rstd, b, dout, self.p, self.pool, self.act, want_gz=not two_pass)
+            if two_pass and out is not None:
+                dy, sums = None, ops.bn_relu_pool_sums(out, dout, b)       # pooled tensors only
+            else:
+                dy, sums = ops.bn_act_pool_bwd(y, mean, rstd, b, dout, self.p, self.pool, self.act, want_gz=not two_pass)
             if two_pass:
                 m._allreduce(sums)
             if self.has_bias:

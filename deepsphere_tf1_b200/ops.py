@@ -99,6 +99,18 @@ def bn_act_pool_bwd(y, mean, rstd, bias, dout, p, pool, act, want_gz=True):
     return gz, sums
 
 
+def bn_relu_pool_sums_supported(F, p, pool, act):
+    return act == 'relu' and (p == 1 or pool == 'max') and F % 4 == 0 and F <= 1024
+
+
+def bn_relu_pool_sums(out, dout, bias):
+    """Pass 1 of the batch-norm backward for relu (+ max pool) from the pooled tensors only."""
+    F = out.shape[-1]
+    sums = torch.zeros(2 * F, dtype=torch.float64, device=out.device)
+    call('bn_relu_pool_sums', out, dout, bias, sums, out.numel() // F, F)
+    return sums
+
+
 def bn_act_pool_bwd_dy(y, mean, rstd, bias, dout, sums, count, p, pool, act):
     """Pass 2 of the batch-norm backward: dy from y, dout and the (all-reduced) sums."""
     B, M, F = y.shape

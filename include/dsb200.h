@@ -158,6 +158,12 @@ int dsb200_bn_act_pool_bwd(const float* y, const float* mean, const float* rstd,
 int dsb200_bn_act_pool_bwd_dy(const float* y, const float* mean, const float* rstd, const float* bias,
                               const float* dout, const double* sums_bwd, double count, float* dy,
                               int B, int M, int F, int p, int pool, int act, void* stream);
+/* pass 1 of the batch-norm backward for relu + max pool (or relu without pooling), from the POOLED
+ * tensors only: out [Rout, F] (the layer output saved by the forward pass) and dout [Rout, F];
+ * sums_bwd (double[2*F], zeroed by the caller) += (sum gz, sum gz * xhat), using
+ * gz != 0 only where out > 0, and xhat = out - bias there (models.py:1235-1243 autodiff). */
+int dsb200_bn_relu_pool_sums(const float* out, const float* dout, const float* bias, double* sums_bwd,
+                             long long Rout, int F, void* stream);
 /* dy = rstd * (gz - S1/count - xhat * S2/count), in place on gz (batch-norm backward);
  * dbias (float[F], may be NULL) receives S1. */
 int dsb200_bn_bwd_apply(const float* y, const float* mean, const float* rstd, const double* sums_bwd,

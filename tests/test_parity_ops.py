@@ -193,6 +193,10 @@ def test_bn_bias_act_pool_chain(dev, F, p, pool, act, bn):
         assert_close(s2, s, 1e-6, 'sums (pass 1)')
         dy = ops.bn_act_pool_bwd_dy(yd, mean, rstd, bd, dout.to(dev), s2, count, p, pool, act)
         assert_close(dy, y.grad, 2 * RTOL, 'dy (pass 2)')
+        if ops.bn_relu_pool_sums_supported(F, p, pool, act):
+            # lean pass 1: the same sums from the pooled output and its gradient only
+            s3 = ops.bn_relu_pool_sums(out, dout.to(dev), bd)
+            assert_close(s3, s, 1e-5, 'sums (pass 1, pooled tensors)')
 
 
 @pytest.mark.parametrize('kind', ['mean', 'var', 'meanvar', 'max'])
