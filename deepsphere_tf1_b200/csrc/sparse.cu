@@ -5,6 +5,7 @@
 // TF autodiff of the same lines (Clenshaw evaluation of sum_k T_k(L)^T G_k).
 #include "common.cuh"
 #include <atomic>
+#include <stdlib.h>
 
 namespace dsb200 {
 
@@ -201,13 +202,15 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const float* v
     if (!rowptr) DSB_REQUIRE(width > 0, "spmm_ell: width must be positive");
     if (vec == 4) {
         const int chunks = F / 4;
-        const int CB = chunks < 64 ? chunks : 64;                  // column slab: at most 1 KB of a row
+        int CB = chunks < 64 ? chunks : 64;                        // column slab: at most 1 KB of a row
+        if (const char* e = getenv("DSB200_SPMM_CB")) { const int v = atoi(e); if (v > 0 && v < CB) CB = v; }
         int lg2 = 0;
         while ((1 << lg2) < CB && lg2 < 5) ++lg2;
         const int passes = (CB + (1 << lg2) - 1) >> lg2;           // 1 or 2
         // rows per tile: ~64 KB of x per tile (it has to live in L1 next to its halo), 32..512 rows
         int TR = 32768 / (CB * 16);
         TR = TR < 32 ? 32 : TR > 256 ? 256 : TR;
+        if (const char* e = getenv("DSB200_SPMM_TR")) { const int v = atoi(e); if (v > 0) TR = v; }
         // keep enough tiles to fill the machine a few times over
         while (TR > 16 && (long long)B * ((M + TR - 1) / TR) * ((chunks + CB - 1) / CB) < 8LL * kNumSMs) TR >>= 1;
         if (passes <= 1) launch_rows<1>(rowptr, col, val, width, B, M, chunks, lg2, TR, CB, x, y, z, out, alpha, beta, gamma, s);

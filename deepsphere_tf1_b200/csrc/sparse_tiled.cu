@@ -192,7 +192,7 @@ static int tiled_step(const int32_t* info, const void* recs, const int32_t* ext,
     DSB_REQUIRE(width >= 1 && width <= kSlots, "cheb_tiled: at most 10 entries per row");
     DSB_REQUIRE(out1 || out2, "cheb_tiled: no output");
     DSB_REQUIRE(x != out1 && x != out2, "cheb_tiled: outputs must not alias x (halo rows of x are read by other tiles)");
-    DSB_REQUIRE(!out2 || (y != out1 && z != out1), "cheb_tiled: out1 must not alias y / z in a two-step launch (ring-1 reads)");
+    DSB_REQUIRE(!out2 || !out1 || (y != out1 && z != out1), "cheb_tiled: out1 must not alias y / z in a two-step launch (ring-1 reads)");
     const uintptr_t al = (uintptr_t)x | (uintptr_t)y | (uintptr_t)z | (uintptr_t)u | (uintptr_t)out1 | (uintptr_t)out2;
     DSB_REQUIRE((al & 15) == 0, "cheb_tiled: tensors must be 16-byte aligned");
     if (b1 == 0.f) y = nullptr;

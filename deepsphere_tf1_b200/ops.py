@@ -27,20 +27,55 @@ def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, tra
     return out
 
 
+USE_TILED = True          # shared-memory tiled recurrence (two orders per launch) when the graph has a tile plan
+
+
+def set_tiled(on):
+    global USE_TILED
+    USE_TILED = bool(on)
+
+
+def _tiles(graph, which, F):
+    plan = getattr(graph, which + '_tiles', None)
+    return plan if (USE_TILED and plan is not None and F % 4 == 0) else None
+
+
+def cheb_tiled_step(graph, x, y=None, z=None, u=None, out1=None, out2=None, coef1=(1.0, 0.0, 0.0), coef2=None,
+                    transpose=False):
+    """T1 = a1 L x + b1 y + c1 z -> out1;  with coef2: T2 = a2 L T1 + b2 x + c2 u -> out2  (one launch)."""
+    B, M, F = x.shape
+    plan = getattr(graph, ('bwd' if transpose else 'fwd') + '_tiles')
+    if plan is None:
+        raise RuntimeError('this graph has no tile plan')
+    a2, b2, c2 = coef2 if coef2 is not None else (0.0, 0.0, 0.0)
+    call('cheb_tiled_step', *plan.args(), B, M, F, x, y, z, u, out1, out2 if coef2 is not None else None,
+         coef1[0], coef1[1], coef1[2], a2, b2, c2)
+    return out1, out2
+
+
 def cheb_basis(graph, x, K):
     """Orders 1..K-1 of the Chebyshev basis of x (models.py:1049-1061) as [K-1, B, M, F]."""
     if K == 1:
         return None
     B, M, F = x.shape
-    rowptr, col, val, width = graph.fwd
     basis = _new((K - 1, B, M, F), x)
+    plan = _tiles(graph, 'fwd', F)
+    if plan is not None:
+        call('cheb_basis_tiled', *plan.args(), B, M, F, K, x, basis)
+        return basis
+    rowptr, col, val, width = graph.fwd
     call('cheb_basis', rowptr, col, val, width, B, M, F, K, x, basis)
     return basis
 
 
 def cheb_basis_bwd(graph, G):
-    """Adjoint of the recurrence, in place: G [K, B, M, F] -> G[0] = dLoss/dx."""
+    """Adjoint of the recurrence: G [K, B, M, F] -> dLoss/dx [B, M, F] (G is overwritten on the gather path)."""
     K, B, M, F = G.shape
+    plan = _tiles(graph, 'bwd', F)
+    if plan is not None and K >= 2:
+        S = _new((K, B, M, F), G)
+        call('cheb_basis_bwd_tiled', *plan.args(), B, M, F, K, G, S)
+        return S[0]
     rowptr, col, val, width = graph.bwd
     call('cheb_basis_bwd', rowptr, col, val, width, B, M, F, K, G)
     return G[0]

@@ -73,6 +73,28 @@ int dsb200_cheb_basis(const int32_t* rowptr, const int32_t* col, const float* va
 int dsb200_cheb_basis_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int width,
                           int B, int M, int F, int K, float* G, void* stream);
 
+/* ---- K1, shared-memory tiled: one or two recurrence steps per launch (csrc/sparse_tiled.cu)
+ *      T1 = a1 * L x  + b1 * y + c1 * z  -> out1 (may be NULL in a two-step launch)
+ *      T2 = a2 * L T1 + b2 * x + c2 * u  -> out2 (NULL: single step)
+ * The tile plan (graph.py: TilePlan) is built once per Laplacian from its ELL packing: tile_info int32[ntiles][4]
+ * = (first record, rows of tile + ring 1, rows incl. ring 2, first ext entry); tile_recs = 64-byte records
+ * (10 fp32 values, 10 uint16 local columns) of the tile + ring-1 rows; tile_ext = global ids of the halo rows.
+ * F % 4 == 0; outputs must not alias x (nor y / z in a two-step launch).  Replaces the same TF ops as
+ * dsb200_spmm_ell (models.py:1056-1061), two at a time. */
+int dsb200_cheb_tiled_step(const int32_t* tile_info, const void* tile_recs, const int32_t* tile_ext,
+                           int ntiles, int TR, int n1cap, int n2cap, int width, int B, int M, int F,
+                           const float* x, const float* y, const float* z, const float* u,
+                           float* out1, float* out2, float a1, float b1, float c1, float a2, float b2, float c2,
+                           void* stream);
+/* all orders 1..K-1 of the basis, two per launch (same result as dsb200_cheb_basis) */
+int dsb200_cheb_basis_tiled(const int32_t* tile_info, const void* tile_recs, const int32_t* tile_ext,
+                            int ntiles, int TR, int n1cap, int n2cap, int width, int B, int M, int F, int K,
+                            const float* x0, float* basis, void* stream);
+/* adjoint recurrence with the tile plan of L^T: G [K][B,M,F] read only, S [K][B,M,F] scratch, result S[0] */
+int dsb200_cheb_basis_bwd_tiled(const int32_t* tile_info, const void* tile_recs, const int32_t* tile_ext,
+                                int ntiles, int TR, int n1cap, int n2cap, int width, int B, int M, int F, int K,
+                                const float* G, float* S, void* stream);
+
 /* ---- K2: dense contraction over (fin, k)  (tf.matmul, models.py:1062-1078)
  *   Y[r, fo] = sum_{k, fi} X_k[r, fi] * W[fi*K + k, fo],   r < R = B*M
  * x0 = order 0 [R,Fin], xk = orders 1..K-1 [K-1][R][Fin] (may be NULL when K == 1).

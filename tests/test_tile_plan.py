@@ -1,0 +1,105 @@
+"""Host logic of the shared-memory tiled recurrence: the tile plan (row tiles + two halo rings + 64-byte row
+records, deepsphere_tf1_b200/graph.py: TilePlan) is executed here by a numpy emulation of the kernel's three
+phases (csrc/sparse_tiled.cu) and compared with scipy `L @ x` -- no GPU needed."""
+import numpy as np
+import pytest
+import torch
+from scipy import sparse
+
+from helpers import healpix_L, random_L
+from deepsphere_tf1_b200.graph import DeviceGraph, TilePlan, TILE_SLOTS
+
+
+def _emulate(plan, M, x, y=None, z=None, u=None, coef1=(1.0, 0.0, 0.0), coef2=None):
+    """What cheb_tiled_kernel computes, tile by tile, from the plan's own arrays."""
+    info, recs, ext = plan.info.numpy(), plan.recs.numpy(), plan.ext.numpy()
+    vals = recs[:, :40].copy().view(np.float32).reshape(-1, TILE_SLOTS)
+    lcol = recs[:, 40:60].copy().view(np.uint16).reshape(-1, TILE_SLOTS).astype(np.int64)
+    out1 = np.zeros_like(x)
+    out2 = np.zeros_like(x) if coef2 is not None else None
+    for t in range(plan.ntiles):
+        soff, n1, n2, eoff = info[t]
+        r0 = t * plan.TR
+        nt = min(plan.TR, M - r0)
+        rows = np.concatenate([np.arange(r0, r0 + nt), ext[eoff:eoff + n2 - nt]])
+        A = x[rows]                                                    # phase 0
+        nrows1 = n1 if coef2 is not None else nt
+        v, c = vals[soff:soff + nrows1], lcol[soff:soff + nrows1]
+        assert c.max() < (n2 if coef2 is not None else n1)
+        T1 = coef1[0] * np.einsum('rj,rjf->rf', v, A[c])               # phase 1
+        if y is not None:
+            T1 = T1 + coef1[1] * y[rows[:nrows1]]
+        if z is not None:
+            T1 = T1 + coef1[2] * z[rows[:nrows1]]
+        out1[r0:r0 + nt] = T1[:nt]
+        if coef2 is not None:                                          # phase 2
+            v, c = vals[soff:soff + nt], lcol[soff:soff + nt]
+            assert c.max() < n1
+            T2 = coef2[0] * np.einsum('rj,rjf->rf', v, T1[c]) + coef2[1] * A[:nt]
+            if u is not None:
+                T2 = T2 + coef2[2] * u[r0:r0 + nt]
+            out2[r0:r0 + nt] = T2
+    return out1, out2
+
+
+@pytest.mark.parametrize('case', ['full_sphere', 'partial_sphere', 'ragged_last_tile'])
+def test_tile_plan_reproduces_two_recurrence_steps(case):
+    L = {'full_sphere': lambda: healpix_L(16), 'partial_sphere': lambda: healpix_L(32, order=2),
+         'ragged_last_tile': lambda: healpix_L(8).tocsr()[:700, :700]}[case]()
+    L = sparse.csr_matrix(L, dtype=np.float32)
+    M = L.shape[0]
+    g = DeviceGraph(L, torch.device('cpu'))
+    plan = g.fwd_tiles
+    assert plan is not None and plan.valid and plan.ntiles == (M + plan.TR - 1) // plan.TR
+    rs = np.random.RandomState(0)
+    x, y, u = [rs.randn(M, 4).astype(np.float64) for _ in range(3)]
+    Ld = L.astype(np.float64)
+    # single step
+    o1, _ = _emulate(plan, M, x, y, None, None, (2.0, -1.0, 0.0))
+    np.testing.assert_allclose(o1, 2 * (Ld @ x) - y, rtol=0, atol=1e-5)
+    # two fused steps: X_k = 2 L x - y ; X_k+1 = 2 L X_k - x (+ u, as in the adjoint pairs)
+    o1, o2 = _emulate(plan, M, x, y, None, u, (2.0, -1.0, 0.0), (2.0, -1.0, 0.5))
+    t1 = 2 * (Ld @ x) - y
+    np.testing.assert_allclose(o1, t1, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(o2, 2 * (Ld @ t1) - x + 0.5 * u, rtol=0, atol=1e-5)
+
+
+def test_tile_plan_halo_rings_are_minimal_and_disjoint():
+    L = sparse.csr_matrix(healpix_L(16), dtype=np.float32)
+    g = DeviceGraph(L, torch.device('cpu'))
+    plan = g.fwd_tiles
+    info, ext = plan.info.numpy(), plan.ext.numpy()
+    pattern = sparse.csr_matrix((np.ones(L.nnz), L.indices, L.indptr), shape=L.shape)
+    for t in range(plan.ntiles):
+        soff, n1, n2, eoff = info[t]
+        r0 = t * plan.TR
+        nt = min(plan.TR, L.shape[0] - r0)
+        tile = np.arange(r0, r0 + nt)
+        ring1, ring2 = ext[eoff:eoff + n1 - nt], ext[eoff + n1 - nt:eoff + n2 - nt]
+        reach1 = np.unique(pattern[tile].indices)
+        assert set(ring1) == set(reach1) - set(tile)
+        reach2 = np.unique(pattern[np.concatenate([tile, ring1])].indices)
+        assert set(ring2) == set(reach2) - set(tile) - set(ring1)
+        assert len(set(ring1) & set(ring2)) == 0
+
+
+def test_graphs_without_locality_or_wide_rows_keep_the_gather_kernels():
+    # random sparse matrix: the halo of a 256-row tile is (almost) the whole graph
+    g = DeviceGraph(random_L(6000, 6), torch.device('cpu'))
+    assert g.fwd_tiles is None and g.bwd_tiles is None
+    # more than 10 entries per row do not fit a row record
+    n = 600
+    A = sparse.random(n, n, density=14.0 / n, random_state=1, format='csr', dtype=np.float32)
+    plan = TilePlan(np.zeros((n, 12), np.int32), np.zeros((n, 12), np.float32), torch.device('cpu'))
+    assert not plan.valid and A.shape == (n, n)
+
+
+def test_nonsymmetric_values_get_their_own_transposed_plan():
+    L = sparse.csr_matrix(healpix_L(8), dtype=np.float32)
+    L = sparse.csr_matrix(L.multiply(sparse.csr_matrix(1.0 + 0.1 * np.random.RandomState(0).rand(*L.shape))), dtype=np.float32)
+    g = DeviceGraph(L, torch.device('cpu'))
+    assert g.bwd_tiles is not None and g.bwd_tiles is not g.fwd_tiles
+    rs = np.random.RandomState(1)
+    x = rs.randn(L.shape[0], 4)
+    o1, _ = _emulate(g.bwd_tiles, L.shape[0], x)
+    np.testing.assert_allclose(o1, L.T.astype(np.float64) @ x, rtol=0, atol=1e-5)
