@@ -6,6 +6,7 @@
 #include "common.cuh"
 #include <atomic>
 #include <stdlib.h>
+#include <stdlib.h>
 
 namespace dsb200 {
 
@@ -209,7 +210,8 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const float* v
         const int passes = (CB + (1 << lg2) - 1) >> lg2;           // 1 or 2
         // rows per tile: ~64 KB of x per tile (it has to live in L1 next to its halo), 32..512 rows
         int TR = 32768 / (CB * 16);
-        TR = TR < 32 ? 32 : TR > 256 ? 256 : TR;
+        TR = TR < 32 ? 32 : TR > 128 ? 128 : TR;                   // 128-row tiles measured best on B200 (tools/sweep_spmm.py)
+        if (const char* e = getenv("DSB200_SPMM_TR")) { const int v = atoi(e); if (v > 0) TR = v; }
         if (const char* e = getenv("DSB200_SPMM_TR")) { const int v = atoi(e); if (v > 0) TR = v; }
         // keep enough tiles to fill the machine a few times over
         while (TR > 16 && (long long)B * ((M + TR - 1) / TR) * ((chunks + CB - 1) / CB) < 8LL * kNumSMs) TR >>= 1;

@@ -10,23 +10,22 @@
 // (Morton) order is a compact patch of the sphere; its two halo rings are precomputed on the host from the sparsity
 // pattern itself (graph.py: TilePlan), so the kernel works for any graph whose vertex order has locality.
 //   phase 0  cp.async: x rows of tile + ring 1 + ring 2 -> A;  y rows of tile + ring 1 -> Bf        (coalesced 16 B)
-//   phase 1  one thread per (row, chunk pair): 9 gathers from A (bank-conflict-free XOR swizzle)  -> Bf (in place)
+//   phase 1  one thread per row: 9 x NCH 16-byte gathers from A (bank-conflict-free XOR swizzle)    -> Bf (in place)
 //   phase 2  Bf rows of the tile -> out1 (coalesced);  second step gathers from Bf -> A (in place)  -> out2
-// Per tile row the host stores one 64-byte record: 10 fp32 values + 10 uint16 LOCAL column indices.
+// Per local row the host stores a 16-word record (10 fp32 values + 10 uint16 LOCAL column indices), word-major per
+// tile, so that the 32 rows of a warp read every record word with one coalesced request.
 #include "common.cuh"
 
 namespace dsb200 {
 
 constexpr int kSlots = 10;                 // neighbour slots of a row record
+constexpr int kRecWords = 16;              // 10 fp32 values, 5 words of uint16 local columns, 1 pad
 constexpr int kTileThreads = 256;
 
-struct alignas(16) RowRec { float v[kSlots]; uint16_t c[kSlots]; uint32_t pad; };
-static_assert(sizeof(RowRec) == 64, "row record must be 64 bytes");
-
 struct TiledArgs {
-    const int4* info;          // per tile: (first record, n1 = tile + ring 1 rows, n2 = + ring 2 rows, first ext entry)
-    const RowRec* recs;
-    const int32_t* ext;        // global row ids of the halo rows (ring 1 then ring 2) of every tile
+    const int4* info;          // per tile: (first record word, n1 = local rows incl. ring 1, n2 = incl. ring 2, first ext entry)
+    const uint32_t* recs;      // per tile [16][n1] record words (word-major: consecutive rows are consecutive words)
+    const int32_t* ext;        // global row of every local index >= nt of every tile (holes: the tile's first row)
     const float4 *x, *y, *z, *u;
     float4 *out1, *out2;
     int B, M, chunks, nslab, TR, ntiles, n1cap, n2cap;
@@ -38,39 +37,35 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// physical 16-byte chunk of (row r, logical chunk c): rows are NCH chunks wide; the XOR makes 8 consecutive (or
-// spatially adjacent) rows hit 8 different 16-byte bank groups when every lane reads the same logical chunk
-template <int NCH> __device__ __forceinline__ int swz(int r, int c) {
-    if (NCH == 4) return r * 4 + (c ^ ((r >> 1) & 3));
-    if (NCH == 2) return r * 2 + (c ^ ((r >> 2) & 1));
-    return r;
-}
+// Shared-memory rows are padded to an ODD number of 16-byte chunks (NCH + 1 for NCH = 2, 4).  The 16-byte bank group
+// of chunk i of row r is then (STRIDE * r + i) mod 8, a bijection of r mod 8: rows whose indices differ in their low
+// 3 bits -- 8 consecutive tile rows, and also their neighbours in one direction (a shifted 2 x 4 block in Morton
+// order) -- land in 8 different bank groups when every lane of a quarter warp reads the same chunk.  No XOR swizzle:
+// the 4 chunks of a neighbour row are read with immediate offsets from one address.
+template <int NCH> struct RowStride { static constexpr int value = NCH == 1 ? 1 : NCH + 1; };
 
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
     acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
 }
 
-// gather sum_j v[j] * S[c[j]] for CPT chunks starting at chunk c0 of every neighbour row
-template <int NCH, int CPT, int W>
-__device__ __forceinline__ void gather_row(const RowRec* __restrict__ rec, const float4* S, int c0, float4 (&acc)[CPT])
+// acc[i] = sum_j v[j] * S[c[j]][chunk i] for local row r: one thread owns the whole NCH-chunk row
+template <int NCH, int W>
+__device__ __forceinline__ void gather_row(const uint32_t* __restrict__ rec, int n1, int r, const float4* S, float4 (&acc)[NCH])
 {
-    const float4* r4 = reinterpret_cast<const float4*>(rec);
-    const float4 q0 = __ldg(r4), q1 = __ldg(r4 + 1), q2 = __ldg(r4 + 2), q3 = __ldg(r4 + 3);
-    const float v[kSlots] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y};
-    const uint32_t cw[5] = {__float_as_uint(q2.z), __float_as_uint(q2.w), __float_as_uint(q3.x), __float_as_uint(q3.y), __float_as_uint(q3.z)};
+    float v[W];
+    uint32_t cw[(W + 1) / 2];
 #pragma unroll
-    for (int i = 0; i < CPT; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 g[W][CPT];
+    for (int j = 0; j < W; ++j) v[j] = __uint_as_float(__ldg(rec + j * n1 + r));
 #pragma unroll
-    for (int j = 0; j < W; ++j) {
-        const int cj = (int)((cw[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+    for (int j = 0; j < (W + 1) / 2; ++j) cw[j] = __ldg(rec + (kSlots + j) * n1 + r);
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) g[j][i] = S[swz<NCH>(cj, c0 + i)];
-    }
+    for (int i = 0; i < NCH; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < W; ++j) {
+        const int cj = (j & 1) ? (int)(cw[j >> 1] >> 16) : (int)(cw[j >> 1] & 0xffffu);
+        const float4* row = S + cj * RowStride<NCH>::value;
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) fma4(acc[i], v[j], g[j][i]);
+        for (int i = 0; i < NCH; ++i) fma4(acc[i], v[j], row[i]);
     }
 }
 
@@ -78,11 +73,10 @@ template <int NCH, int W>
 __global__ void __launch_bounds__(kTileThreads)
 cheb_tiled_kernel(const __grid_constant__ TiledArgs a)
 {
-    constexpr int CPT = NCH >= 2 ? 2 : 1;          // chunks per thread
-    constexpr int TPR = NCH / CPT;                 // threads per row
     extern __shared__ float4 smem4[];
-    float4* A = smem4;                              // [n2cap][NCH]
-    float4* Bf = smem4 + (size_t)a.n2cap * NCH;     // [n1cap][NCH]
+    constexpr int RS = RowStride<NCH>::value;
+    float4* A = smem4;                              // [n2cap][RS]
+    float4* Bf = smem4 + (size_t)a.n2cap * RS;      // [n1cap][RS]
     const bool two = a.out2 != nullptr;
 
     // CTA -> (tile, sample, slab): slabs and samples of a tile are neighbours in the launch order (shared records / halos in L2)
@@ -93,70 +87,70 @@ cheb_tiled_kernel(const __grid_constant__ TiledArgs a)
     const int r0 = t * a.TR;
     const int nt = min(a.TR, a.M - r0);
     const int n1 = inf.y, n2 = inf.z;
-    const RowRec* recs = a.recs + inf.x;
+    const uint32_t* rec = a.recs + inf.x;
     const int32_t* ext = a.ext + inf.w;
     const long long sbase = (long long)b * a.M * a.chunks + slab * NCH;       // chunk offset of (sample, slab)
     const int nrows1 = two ? n1 : nt;              // rows computed in step 1
     const int nload = two ? n2 : n1;               // rows of x needed
 
-    // ---- phase 0: stage x (and y) rows
+    // ---- phase 0: stage x (and y) rows, 16 bytes per thread and instruction, coalesced
     for (int idx = threadIdx.x; idx < nload * NCH; idx += kTileThreads) {
         const int r = idx / NCH, c = idx - r * NCH;
         const int gr = r < nt ? r0 + r : __ldg(ext + r - nt);
-        cp_async16(A + swz<NCH>(r, c), a.x + sbase + (long long)gr * a.chunks + c);
+        cp_async16(A + r * RS + c, a.x + sbase + (long long)gr * a.chunks + c);
     }
     if (a.y) {
         for (int idx = threadIdx.x; idx < nrows1 * NCH; idx += kTileThreads) {
             const int r = idx / NCH, c = idx - r * NCH;
             const int gr = r < nt ? r0 + r : __ldg(ext + r - nt);
-            cp_async16(Bf + swz<NCH>(r, c), a.y + sbase + (long long)gr * a.chunks + c);
+            cp_async16(Bf + r * RS + c, a.y + sbase + (long long)gr * a.chunks + c);
         }
     }
     cp_async_wait_all();
     __syncthreads();
 
-    // ---- phase 1: T1 on tile (+ ring 1)
-    for (int it = threadIdx.x; it < nrows1 * TPR; it += kTileThreads) {
-        const int r = it / TPR, c0 = (it - r * TPR) * CPT;
-        float4 acc[CPT];
-        gather_row<NCH, CPT, W>(recs + r, A, c0, acc);
-        const int gr = r < nt ? r0 + r : __ldg(ext + r - nt);
+    // ---- phase 1: T1 on the tile (+ ring 1), one thread per row
+    for (int r = threadIdx.x; r < nrows1; r += kTileThreads) {
+        float4 acc[NCH];
+        gather_row<NCH, W>(rec, n1, r, A, acc);
+        float4* mine = Bf + r * RS;
+        const float4* zr = nullptr;
+        if (a.z) zr = a.z + sbase + (long long)(r < nt ? r0 + r : __ldg(ext + r - nt)) * a.chunks;
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) {
+        for (int i = 0; i < NCH; ++i) {
             float4 res = make_float4(a.a1 * acc[i].x, a.a1 * acc[i].y, a.a1 * acc[i].z, a.a1 * acc[i].w);
-            float4* slot = Bf + swz<NCH>(r, c0 + i);
-            if (a.y) fma4(res, a.b1, *slot);
-            if (a.z) fma4(res, a.c1, __ldg(a.z + sbase + (long long)gr * a.chunks + c0 + i));
-            *slot = res;
+            if (a.y) fma4(res, a.b1, mine[i]);
+            if (a.z) fma4(res, a.c1, __ldg(zr + i));
+            mine[i] = res;
         }
     }
     __syncthreads();
 
-    // ---- phase 2: write T1 of the tile rows; second step
+    // ---- phase 2: T1 of the tile rows -> out1; second step from Bf into A (in place), then -> out2
     if (a.out1) {
         for (int idx = threadIdx.x; idx < nt * NCH; idx += kTileThreads) {
             const int r = idx / NCH, c = idx - r * NCH;
-            a.out1[sbase + (long long)(r0 + r) * a.chunks + c] = Bf[swz<NCH>(r, c)];
+            a.out1[sbase + (long long)(r0 + r) * a.chunks + c] = Bf[r * RS + c];
         }
     }
     if (!two) return;
-    for (int it = threadIdx.x; it < nt * TPR; it += kTileThreads) {
-        const int r = it / TPR, c0 = (it - r * TPR) * CPT;
-        float4 acc[CPT];
-        gather_row<NCH, CPT, W>(recs + r, Bf, c0, acc);
+    for (int r = threadIdx.x; r < nt; r += kTileThreads) {
+        float4 acc[NCH];
+        gather_row<NCH, W>(rec, n1, r, Bf, acc);
+        float4* mine = A + r * RS;
+        const float4* ur = a.u ? a.u + sbase + (long long)(r0 + r) * a.chunks : nullptr;
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) {
+        for (int i = 0; i < NCH; ++i) {
             float4 res = make_float4(a.a2 * acc[i].x, a.a2 * acc[i].y, a.a2 * acc[i].z, a.a2 * acc[i].w);
-            float4* slot = A + swz<NCH>(r, c0 + i);
-            fma4(res, a.b2, *slot);
-            if (a.u) fma4(res, a.c2, __ldg(a.u + sbase + (long long)(r0 + r) * a.chunks + c0 + i));
-            *slot = res;
+            fma4(res, a.b2, mine[i]);
+            if (a.u) fma4(res, a.c2, __ldg(ur + i));
+            mine[i] = res;
         }
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < nt * NCH; idx += kTileThreads) {
         const int r = idx / NCH, c = idx - r * NCH;
-        a.out2[sbase + (long long)(r0 + r) * a.chunks + c] = A[swz<NCH>(r, c)];
+        a.out2[sbase + (long long)(r0 + r) * a.chunks + c] = A[r * RS + c];
     }
 }
 
@@ -201,13 +195,13 @@ static int tiled_step(const int32_t* info, const void* recs, const int32_t* ext,
     const int chunks = F / 4;
     const int nch = chunks % 4 == 0 ? 4 : chunks % 2 == 0 ? 2 : 1;
     TiledArgs a;
-    a.info = (const int4*)info; a.recs = (const RowRec*)recs; a.ext = ext;
+    a.info = (const int4*)info; a.recs = (const uint32_t*)recs; a.ext = ext;
     a.x = (const float4*)x; a.y = (const float4*)y; a.z = (const float4*)z; a.u = (const float4*)u;
     a.out1 = (float4*)out1; a.out2 = (float4*)out2;
     a.B = B; a.M = M; a.chunks = chunks; a.nslab = chunks / nch; a.TR = TR; a.ntiles = ntiles;
-    a.n1cap = out2 ? n1cap : TR; a.n2cap = out2 ? n2cap : n1cap;
+    a.n1cap = out2 ? n1cap : (TR + 7) / 8 * 8; a.n2cap = out2 ? n2cap : n1cap;
     a.a1 = a1; a.b1 = b1; a.c1 = c1; a.a2 = a2; a.b2 = b2; a.c2 = c2;
-    const size_t smem = (size_t)(a.n1cap + a.n2cap) * nch * 16;
+    const size_t smem = (size_t)(a.n1cap + a.n2cap) * (nch == 1 ? 1 : nch + 1) * 16;
     DSB_REQUIRE(smem <= 200 * 1024, "cheb_tiled: tile + halo does not fit shared memory");
     if (nch == 4) return launch_tiled<4>(a, width, smem, s);
     if (nch == 2) return launch_tiled<2>(a, width, smem, s);

@@ -13,16 +13,35 @@ from scipy import sparse
 ELL_MAX_WIDTH = 16
 TILE_SLOTS = 10            # neighbour slots of a row record of the tiled kernels (csrc/sparse_tiled.cu: RowRec)
 TILE_ROWS = 256            # rows per tile: 16 x 16 pixels in HEALPix nested order
-TILE_SMEM_ROWS = 1600      # tile + ring 1 + tile + ring 1 + ring 2 rows that fit shared memory with >= 2 CTAs per SM
+TILE_SMEM_ROWS = 1700      # (tile + ring 1) + (tile + ring 1 + ring 2) local rows that fit shared memory with >= 2 CTAs per SM
+
+
+def _bucket_slots(rows, base):
+    """Local slots for halo rows that keep the low 3 bits of the global id: local = base + 8*q + (g & 7).
+    Returns (local ids, size of the region, a multiple of 8)."""
+    if len(rows) == 0:
+        return np.zeros(0, np.int64), 0
+    b = (rows & 7).astype(np.int64)
+    order = np.argsort(b, kind='stable')
+    cnt = np.bincount(b, minlength=8)
+    start = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+    pos = np.empty(len(rows), np.int64)
+    pos[order] = np.arange(len(rows)) - start[b[order]]
+    return base + 8 * pos + b, 8 * int(cnt.max())
 
 
 class TilePlan(object):
-    """Row tiles with two halo rings for the shared-memory tiled recurrence kernels.
+    """Row tiles with two halo rings for the shared-memory tiled recurrence kernels (csrc/sparse_tiled.cu).
 
     Tile t owns the consecutive rows [t*TR, (t+1)*TR).  Ring 1 = rows referenced by the tile's rows that lie
-    outside the tile, ring 2 = rows referenced by ring 1 outside tile + ring 1 (both sorted by global id).
-    LOCAL indices: tile rows 0..nt-1, ring 1 nt..n1-1, ring 2 n1..n2-1.  Every row of tile + ring 1 gets one
-    64-byte record: 10 fp32 values + 10 uint16 local columns (unused slots: value 0, own index)."""
+    outside the tile, ring 2 = rows referenced by ring 1 outside tile + ring 1.
+    LOCAL indices: tile rows 0..nt-1 (offset in the tile); ring 1 in [ntp, n1), ring 2 in [n1, n2) with
+    ntp = nt rounded up to 8.  A halo row keeps the low 3 bits of its global id in its local index (8 vertices that
+    are neighbours on the sphere then sit in 8 different shared-memory bank groups); unused slots are holes.
+    Every local row < n1 has a record of 16 words -- 10 fp32 values, 5 words of uint16 local columns, 1 pad --
+    stored word-major per tile ([16][n1]) so that consecutive threads read consecutive words.  Holes have zero
+    values and point at themselves; `ext` gives the global row of every local index >= nt (holes: the tile's
+    first row, a harmless load)."""
 
     def __init__(self, col, val, device, TR=TILE_ROWS):
         M, W = col.shape
@@ -31,55 +50,54 @@ class TilePlan(object):
             return
         T = (M + TR - 1) // TR
         info = np.zeros((T, 4), np.int32)
-        vals, lcols, exts = [], [], []
-        soff = eoff = 0
+        recs, exts = [], []
+        woff = eoff = 0
         n1cap = n2cap = 0
         for t in range(T):
             r0, r1 = t * TR, min(M, (t + 1) * TR)
             nt = r1 - r0
+            ntp = (nt + 7) // 8 * 8
             c_t = col[r0:r1]
             u = np.unique(c_t)
             ring1 = u[(u < r0) | (u >= r1)]
-            c_1 = col[ring1]
-            u2 = np.unique(c_1)
+            u2 = np.unique(col[ring1])
             u2 = u2[(u2 < r0) | (u2 >= r1)]
             ring2 = np.setdiff1d(u2, ring1, assume_unique=True)
-            h1, h2 = len(ring1), len(ring2)
-            n1, n2 = nt + h1, nt + h1 + h2
-            if 2 * n1 + h2 > TILE_SMEM_ROWS or n2 > 65535:
+            l1, s1 = _bucket_slots(ring1, ntp)
+            n1 = ntp + s1
+            l2, s2 = _bucket_slots(ring2, n1)
+            n2 = n1 + s2
+            if n1 + n2 > TILE_SMEM_ROWS or n2 > 65535:
                 return                                   # vertex order without locality: keep the gather kernels
-            allc = np.concatenate([c_t, c_1], 0).astype(np.int64)
-            loc = allc - r0
-            out = (allc < r0) | (allc >= r1)
-            g = allc[out]
-            if len(g):
-                i1 = np.minimum(np.searchsorted(ring1, g), max(h1 - 1, 0))
-                in1 = ring1[i1] == g
-                i2 = np.minimum(np.searchsorted(ring2, g), max(h2 - 1, 0))
-                if h2:
-                    assert np.all(in1 | (ring2[i2] == g))
-                else:
-                    assert np.all(in1)
-                loc[out] = np.where(in1, nt + i1, nt + h1 + i2)
+            # global -> local lookup over tile + rings
+            gid = np.concatenate([np.arange(r0, r1), ring1, ring2]).astype(np.int64)
+            lid = np.concatenate([np.arange(nt), l1, l2]).astype(np.int64)
+            order = np.argsort(gid)
+            gid_s, lid_s = gid[order], lid[order]
+            rows_g = np.concatenate([np.arange(r0, r1), ring1])            # real rows that get a record
+            rows_l = np.concatenate([np.arange(nt), l1]).astype(np.int64)
+            cg = col[rows_g].astype(np.int64)
+            pos = np.searchsorted(gid_s, cg)
+            assert np.array_equal(gid_s[pos], cg)
+            words = np.zeros((16, n1), np.uint32)
+            lc = np.repeat(np.arange(n1, dtype=np.uint32)[:, None], TILE_SLOTS, axis=1)   # holes / unused slots: own index
+            lc[rows_l, :W] = lid_s[pos].astype(np.uint32)
             v = np.zeros((n1, TILE_SLOTS), np.float32)
-            v[:, :W] = np.concatenate([val[r0:r1], val[ring1]], 0)
-            lc = np.repeat(np.arange(n1, dtype=np.uint16)[:, None], TILE_SLOTS, axis=1)
-            lc[:, :W] = loc.astype(np.uint16)
-            vals.append(v)
-            lcols.append(lc)
-            exts.append(ring1.astype(np.int32))
-            exts.append(ring2.astype(np.int32))
-            info[t] = (soff, n1, n2, eoff)
-            soff += n1
-            eoff += h1 + h2
+            v[rows_l, :W] = val[rows_g]
+            words[:TILE_SLOTS] = v.view(np.uint32).T
+            words[TILE_SLOTS:TILE_SLOTS + 5] = (lc[:, 0::2] | (lc[:, 1::2] << 16)).T
+            ext = np.full(n2 - nt, r0, np.int32)
+            ext[l1 - nt] = ring1
+            ext[l2 - nt] = ring2
+            recs.append(words.ravel())
+            exts.append(ext)
+            info[t] = (woff, n1, n2, eoff)
+            woff += 16 * n1
+            eoff += n2 - nt
             n1cap, n2cap = max(n1cap, n1), max(n2cap, n2)
-        recs = np.zeros((soff, 64), np.uint8)
-        recs[:, :40] = np.concatenate(vals, 0).view(np.uint8).reshape(soff, 40)
-        recs[:, 40:60] = np.concatenate(lcols, 0).view(np.uint8).reshape(soff, 20)
-        ext = np.concatenate(exts + [np.zeros(1, np.int32)])
         self.info = torch.from_numpy(info).to(device)
-        self.recs = torch.from_numpy(recs).to(device)
-        self.ext = torch.from_numpy(ext).to(device)
+        self.recs = torch.from_numpy(np.concatenate(recs).view(np.int32)).to(device)
+        self.ext = torch.from_numpy(np.concatenate(exts + [np.zeros(1, np.int32)])).to(device)
         self.ntiles, self.TR, self.n1cap, self.n2cap, self.width = T, TR, n1cap, n2cap, W
         self.valid = True
 

@@ -27,7 +27,7 @@ def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, tra
     return out
 
 
-USE_TILED = True          # shared-memory tiled recurrence (two orders per launch) when the graph has a tile plan
+USE_TILED = False         # shared-memory tiled recurrence (two orders per launch) when the graph has a tile plan
 
 
 def set_tiled(on):

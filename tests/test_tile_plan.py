@@ -12,19 +12,23 @@ from deepsphere_tf1_b200.graph import DeviceGraph, TilePlan, TILE_SLOTS
 
 def _emulate(plan, M, x, y=None, z=None, u=None, coef1=(1.0, 0.0, 0.0), coef2=None):
     """What cheb_tiled_kernel computes, tile by tile, from the plan's own arrays."""
-    info, recs, ext = plan.info.numpy(), plan.recs.numpy(), plan.ext.numpy()
-    vals = recs[:, :40].copy().view(np.float32).reshape(-1, TILE_SLOTS)
-    lcol = recs[:, 40:60].copy().view(np.uint16).reshape(-1, TILE_SLOTS).astype(np.int64)
+    info, recs, ext = plan.info.numpy(), plan.recs.numpy().view(np.uint32), plan.ext.numpy()
     out1 = np.zeros_like(x)
     out2 = np.zeros_like(x) if coef2 is not None else None
     for t in range(plan.ntiles):
-        soff, n1, n2, eoff = info[t]
+        woff, n1, n2, eoff = info[t]
         r0 = t * plan.TR
         nt = min(plan.TR, M - r0)
-        rows = np.concatenate([np.arange(r0, r0 + nt), ext[eoff:eoff + n2 - nt]])
+        words = recs[woff:woff + 16 * n1].reshape(16, n1)
+        vals = words[:TILE_SLOTS].T.copy().view(np.float32)
+        pk = words[TILE_SLOTS:TILE_SLOTS + 5].T
+        lcol = np.empty((n1, TILE_SLOTS), np.int64)
+        lcol[:, 0::2] = pk & 0xffff
+        lcol[:, 1::2] = pk >> 16
+        rows = np.concatenate([np.arange(r0, r0 + nt), ext[eoff:eoff + n2 - nt]])     # global row of every local index
         A = x[rows]                                                    # phase 0
         nrows1 = n1 if coef2 is not None else nt
-        v, c = vals[soff:soff + nrows1], lcol[soff:soff + nrows1]
+        v, c = vals[:nrows1], lcol[:nrows1]
         assert c.max() < (n2 if coef2 is not None else n1)
         T1 = coef1[0] * np.einsum('rj,rjf->rf', v, A[c])               # phase 1
         if y is not None:
@@ -33,7 +37,7 @@ def _emulate(plan, M, x, y=None, z=None, u=None, coef1=(1.0, 0.0, 0.0), coef2=No
             T1 = T1 + coef1[2] * z[rows[:nrows1]]
         out1[r0:r0 + nt] = T1[:nt]
         if coef2 is not None:                                          # phase 2
-            v, c = vals[soff:soff + nt], lcol[soff:soff + nt]
+            v, c = vals[:nt], lcol[:nt]
             assert c.max() < n1
             T2 = coef2[0] * np.einsum('rj,rjf->rf', v, T1[c]) + coef2[1] * A[:nt]
             if u is not None:
@@ -64,23 +68,33 @@ def test_tile_plan_reproduces_two_recurrence_steps(case):
     np.testing.assert_allclose(o2, 2 * (Ld @ t1) - x + 0.5 * u, rtol=0, atol=1e-5)
 
 
-def test_tile_plan_halo_rings_are_minimal_and_disjoint():
+def test_tile_plan_halo_rings_are_minimal_and_keep_bank_bits():
     L = sparse.csr_matrix(healpix_L(16), dtype=np.float32)
     g = DeviceGraph(L, torch.device('cpu'))
     plan = g.fwd_tiles
     info, ext = plan.info.numpy(), plan.ext.numpy()
     pattern = sparse.csr_matrix((np.ones(L.nnz), L.indices, L.indptr), shape=L.shape)
+    recs = plan.recs.numpy().view(np.uint32)
     for t in range(plan.ntiles):
-        soff, n1, n2, eoff = info[t]
+        woff, n1, n2, eoff = info[t]
         r0 = t * plan.TR
         nt = min(plan.TR, L.shape[0] - r0)
         tile = np.arange(r0, r0 + nt)
-        ring1, ring2 = ext[eoff:eoff + n1 - nt], ext[eoff + n1 - nt:eoff + n2 - nt]
+        e = ext[eoff:eoff + n2 - nt]
+        loc = np.arange(nt, n2)
+        vals = recs[woff:woff + 16 * n1].reshape(16, n1)[:TILE_SLOTS].T.copy().view(np.float32)
+        hole = np.ones(n2 - nt, bool)
+        hole[:n1 - nt] = ~np.any(vals[nt:n1] != 0, axis=1)              # ring-1 holes have all-zero records
+        real1 = e[:n1 - nt][~hole[:n1 - nt]]
         reach1 = np.unique(pattern[tile].indices)
-        assert set(ring1) == set(reach1) - set(tile)
-        reach2 = np.unique(pattern[np.concatenate([tile, ring1])].indices)
-        assert set(ring2) == set(reach2) - set(tile) - set(ring1)
-        assert len(set(ring1) & set(ring2)) == 0
+        assert set(real1) == set(reach1) - set(tile)
+        reach2 = set(np.unique(pattern[np.concatenate([tile, real1])].indices)) - set(tile) - set(real1)
+        ring2 = e[n1 - nt:]
+        assert reach2 <= set(ring2) and set(ring2) <= reach2 | {r0}
+        # a real halo row keeps the low 3 bits of its global id in its local index
+        keep = np.concatenate([~hole[:n1 - nt], ring2 != r0])
+        assert np.all((e[keep] & 7) == (loc[keep] & 7))
+        assert n1 % 8 == 0 and n2 % 8 == 0
 
 
 def test_graphs_without_locality_or_wide_rows_keep_the_gather_kernels():
