@@ -88,6 +88,8 @@ struct alignas(64) RowGemmParams {
     int ntiles;
     int wstream;               // 1: the weight image is too large to stay resident: each stage carries its k-blocks' weights
     int tmem_cols;             // TMEM columns to allocate (power of two >= acc_stages * 2 * Npad)
+    int nostore;               // experiment: skip the epilogue stores (DSB200_RG_NOSTORE)
+    long long* dbg;            // experiment: per-stage timestamps of CTA 0 (DSB200_RG_DBG = device pointer)
 };
 
 // Element (j, n2, kk) of the weight image: k-block j, row n2 in [0, 2*Npad) (hi rows then lo rows), column kk.
@@ -146,6 +148,9 @@ __device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane)
         }
     }
 }
+
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define RG_DBG(slot, ev) do { if (p.dbg && blockIdx.x == 0 && (slot) < 256) p.dbg[(slot) * 8 + (ev)] = gtimer(); } while (0)
 
 template <int MODE, bool SUMS>
 __global__ void __launch_bounds__(kRgThreads, 2)
@@ -213,14 +218,17 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
     if (warp == kWarpTma) {
         // ======================= TMA producer =======================
         if (lane == 0) {
-            int s = 0;
+            int s = 0, dbgi = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
                 const int row0 = t * kTileM;
                 int k = 0, c = 0;                                   // plane, chunk within the plane
                 for (int j0 = 0; j0 < p.nkb; j0 += p.G) {
                     const int cnt = min(p.G, p.nkb - j0);
+                    RG_DBG(dbgi, 0);
                     mbar_wait(empty + s, ph ^ 1u, 1);
+                    RG_DBG(dbgi, 1);
+                    ++dbgi;
                     mbar_expect_tx(full_tma + s, cnt * (tile_bytes + (p.wstream ? wblk_bytes : 0u)));
                     uint8_t* dst = sA + (size_t)s * stage_bytes;
                     if (p.wstream)
@@ -252,7 +260,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
             const uint64_t dB0 = make_smem_desc(smem_u32(sW), 16, sbo, p.swz);
             const uint32_t a_stage = stage_bytes >> 4, a_tile = tile_bytes >> 4, a_lo = (p.G * tile_bytes) >> 4;
             const uint32_t b_blk = wblk_bytes >> 4, b_lo = ((uint32_t)p.Npad * rowbytes) >> 4;
-            int s = 0, ti = 0;
+            int s = 0, ti = 0, dbgm = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
                 const int a = p.acc_stages == 2 ? (ti & 1) : 0;
@@ -265,6 +273,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                 for (int j0 = 0; j0 < p.nkb; j0 += p.G) {
                     const int cnt = min(p.G, p.nkb - j0);
                     mbar_wait(full_mma + s, ph, 3);
+                    RG_DBG(dbgm, 4);
                     tc_fence_after();
                     uint64_t dA = dA0 + (uint64_t)(a_stage * (uint32_t)s);
                     if (p.wstream) dB = dA + 2u * p.G * a_tile;                      // this stage's weight blocks
@@ -283,6 +292,8 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                         }
                     }
                     tc_commit(empty + s);                                       // stage free once the MMAs have read it
+                    RG_DBG(dbgm, 5);
+                    ++dbgm;
                     if (++s == S) { s = 0; ph ^= 1u; }
                 }
                 tc_commit(acc_full + a);
@@ -299,6 +310,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                 if ((int)(it & 1u) == grp) {
                     const int cnt = min(p.G, p.nkb - j0);
                     mbar_wait(full_tma + s, ph, 4);
+                    if (tt == 0) RG_DBG((int)it, 2);
                     float4* A = reinterpret_cast<float4*>(sA + (size_t)s * stage_bytes);
                     float4* Al = reinterpret_cast<float4*>(sA + (size_t)s * stage_bytes + (size_t)p.G * tile_bytes);
                     const int nvec = (int)(cnt * tile_bytes / 16);
@@ -313,6 +325,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                     }
                     fence_proxy_async();
                     mbar_arrive(full_mma + s);
+                    if (tt == 0) RG_DBG((int)it, 3);
                 }
                 if (++s == S) { s = 0; ph ^= 1u; }
             }
@@ -329,7 +342,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
             tc_fence_after();
             const uint32_t tbase = tmem_base + (uint32_t)(a * acc_cols) + ((uint32_t)(q * 32) << 16);
             const long long row = (long long)t * kTileM + q * 32 + lane;
-            const bool ok = row < p.R;
+            const bool ok = row < p.R && !p.nostore;
             if (MODE == MODE_FWD) {
                 float* orow = p.out + row * p.Fout;
                 for (int c0 = 0; c0 < p.Nreal; c0 += 32) {
@@ -425,7 +438,7 @@ static bool plan_rowgemm_n(int red_per_plane, int planes, int Npad, bool can_str
 static bool plan_rowgemm(int red_per_plane, int planes, int Npad, bool can_stream, int ctas, RowGemmPlan* pl)
 {
     for (; ctas >= 1; --ctas)
-        if (plan_rowgemm_n(red_per_plane, planes, Npad, can_stream, ctas, pl) && (ctas == 1 || (!pl->wstream && pl->nstages >= 3))) return true;
+        if (plan_rowgemm_n(red_per_plane, planes, Npad, can_stream && ctas == 1, ctas, pl) && (ctas == 1 || pl->nstages >= 3)) return true;
     return false;
 }
 
@@ -501,6 +514,8 @@ static int launch_rowgemm(RowGemmParams& p, size_t smem, int ctas, float* image,
         configured = true;
     }
     p.wpack = image;
+    p.nostore = env_int("DSB200_RG_NOSTORE", 0);
+    { const char* d = getenv("DSB200_RG_DBG"); p.dbg = (d && *d) ? (long long*)strtoull(d, nullptr, 0) : nullptr; }
     if (image) {
         const int total = p.nkb * 2 * p.Npad * p.kc;
         pack_w_kernel<MODE><<<(total + 255) / 256, 256, 0, s>>>(p, image);
@@ -609,6 +624,8 @@ struct alignas(64) WGradParams {
                                // rpk*Fout gradient columns); only the diagonal blocks (same sub-row) of D are used
     int tmem_cols;             // TMEM columns to allocate (power of two >= mtiles * 2 * Np)
     int vec_red;               // dW rows are 16-byte aligned: red.global.add.v4.f32
+    int swap;                  // 1: dY on the M side ([dYh; dYl] stacked, 128 lanes), X blocks on the N side (see below)
+    int nNb, bpn;              // swap: number of N blocks, X blocks per N block (N = 32 * bpn <= 256)
     int nA;                    // number of X blocks per stage
     int pad_blocks;            // unused blocks at the end of a stage (the last 128-wide tile of q may read past X_lo)
     int RS;                    // rows per pipeline stage (multiple of 8)
@@ -710,6 +727,26 @@ wgrad_tc_kernel(const __grid_constant__ WGradParams p)
                 mbar_wait(full_mma + s, ph, 13);
                 tc_fence_after();
                 const uint64_t dA = dA0 + (uint64_t)(stg * (uint32_t)s), dB = dB0 + (uint64_t)(stg * (uint32_t)s);
+                if (p.swap) {
+                    // One tcgen05.mma costs ~87 ns whatever its M and N (tools/experiments/mma_rate.cu), so the widest
+                    // operand goes on N: D[(hi|lo, fo), q] += [dYh; dYl]^T (X_h + X_l), two instructions per 8 rows
+                    // and N block (the lo x lo term it adds is below fp32 resolution).
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
+                        const uint64_t a = dB + kstep * ks;                           // [dYh | dYl | pad] blocks: M = 128
+                        for (int nb = 0; nb < p.nNb; ++nb) {
+                            const int nblk = min(p.bpn, nA - nb * p.bpn);
+                            const uint32_t idesc = make_idesc_tf32(kTileM, nblk * kMNBlock, 1, 1);
+                            const uint64_t b = dA + kstep * ks + (uint64_t)(((uint32_t)(nb * p.bpn) * blk) >> 4);
+                            const uint32_t d = tmem_base + (uint32_t)(nb * p.bpn * kMNBlock);
+                            mma_tf32(d, a, b, idesc, acc);
+                            mma_tf32(d, a, b + loA, idesc, 1u);
+                        }
+                    }
+                    tc_commit(empty + s);
+                    if (++s == S) { s = 0; ph ^= 1u; }
+                    continue;
+                }
                 for (int ks = 0; ks < ksteps; ++ks) {
                     const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
                     const uint64_t b = dB + kstep * ks;
@@ -764,6 +801,30 @@ wgrad_tc_kernel(const __grid_constant__ WGradParams p)
         mbar_wait(acc_full, 0, 15);
         tc_fence_after();
         const int Fx = p.Fin * p.rpk;                                // features of a packed row of X
+        if (p.swap) {
+            // lanes: (hi | lo part, gradient column), columns: q.  Lanes of a warp hold consecutive fo: coalesced reductions.
+            const int Fy = p.Fout * p.rpk;
+            const int L = qd * 32 + lane;
+            const int part = L / Np, cy = L - part * Np;             // Np = gradient columns incl. the zero fill of the last block
+            const int hy = cy / p.Fout, fo = cy - hy * p.Fout;
+            const bool lane_ok = part < 2 && cy < Fy;
+            const uint32_t tbase = tmem_base + ((uint32_t)(qd * 32) << 16);
+            const int ncols = nA * kMNBlock;
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                float v[16];
+                tmem_ld16(tbase + c0, v);
+                tmem_ld_wait();
+                const int bq = c0 / kMNBlock;
+                const int k = bq / p.nblkA;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int cc = (bq - k * p.nblkA) * kMNBlock + (c0 % kMNBlock) + e;   // column within the packed plane
+                    const int hx = cc / p.Fin, fi = cc - hx * p.Fin;
+                    if (lane_ok && hx == hy && cc < Fx) atomicAdd(p.dW + ((long long)fi * p.K + k) * p.Fout + fo, v[e]);
+                }
+            }
+            tc_fence_before();
+        } else
         for (int mt = 0; mt < p.mtiles; ++mt) {
             const int q = mt * kTileM + qd * 32 + lane;              // (block, column in block) of the padded Xcat
             const int bq = q / kMNBlock, cq = q - bq * kMNBlock;
@@ -820,7 +881,11 @@ int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, fl
     p.nA = nA;
     const int nB = p.nblkB;
     p.mtiles = (nA * kMNBlock + kTileM - 1) / kTileM;
-    const int need_cols = p.mtiles * 2 * nB * kMNBlock;
+    // swapped roles when [dYh; dYl] fits the 128 lanes of one accumulator
+    p.swap = (nB <= 2 && env_int("DSB200_WG_SWAP", 0)) ? 1 : 0;     // measured: no faster (the kernel is latency bound, not MMA bound)
+    p.nNb = (nA * kMNBlock + 255) / 256;
+    p.bpn = (nA + p.nNb - 1) / p.nNb;
+    const int need_cols = p.swap ? nA * kMNBlock : p.mtiles * 2 * nB * kMNBlock;
     if (need_cols > 512) return 1;
     int tcols = 32;
     while (tcols < need_cols) tcols <<= 1;
@@ -832,6 +897,7 @@ int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, fl
     if (ctas < 1) ctas = 1;
     // the last 128-wide tile of q may read past the X_lo blocks: keep it inside the stage ([X][X_lo][dY][dY_lo][pad])
     p.pad_blocks = p.mtiles * (kTileM / kMNBlock) - (nA + 2 * nB);
+    if (p.swap) p.pad_blocks = kTileM / kMNBlock - 2 * nB;         // the 128-lane operand [dYh | dYl | pad] stays inside the stage
     if (p.pad_blocks < 0) p.pad_blocks = 0;
     const int per_row = kMNBlock * 4 * (2 * (nA + nB) + p.pad_blocks);
     const int stage_kb = env_int("DSB200_WG_STAGE_KB", ctas > 1 ? 32 : 48);
