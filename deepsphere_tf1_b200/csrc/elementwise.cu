@@ -360,6 +360,19 @@ bn_bwd_apply_kernel(const float* __restrict__ y, const float* __restrict__ mean,
 
 // ------------------------------------------------------------------------------------------
 // vertex resize / unpool / concat
+// rows of a [M, F] matrix picked by index: out[i, :] = x[idx[i], :]  (send buffer of the halo exchange)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ x, const int32_t* __restrict__ idx, long long n, int F, float* __restrict__ out)
+{
+    const long long total = n * F;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        const long long i = g / F;
+        const int f = (int)(g - i * F);
+        out[g] = __ldg(x + (long long)__ldg(idx + i) * F + f);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 vertex_resize_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int Min, int Mout, int F, float fill)
 {
@@ -836,6 +849,13 @@ extern "C" int dsb200_vertex_resize(const float* x, float* out, int B, int Min, 
 {
     DSB_REQUIRE(x && out && B > 0 && Min > 0 && Mout > 0 && F > 0, "vertex_resize: bad arguments");
     vertex_resize_kernel<<<grid_for((long long)B * Mout * F, 256), 256, 0, STREAM>>>(x, out, B, Min, Mout, F, fill);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_gather_rows(const float* x, const int32_t* idx, long long n, int F, float* out, void* stream)
+{
+    DSB_REQUIRE(x && idx && out && n > 0 && F > 0, "gather_rows: bad arguments");
+    gather_rows_kernel<<<grid_for(n * F, 256), 256, 0, STREAM>>>(x, idx, n, F, out);
     DSB_LAUNCH_CHECK();
 }
 

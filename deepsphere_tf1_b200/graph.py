@@ -108,7 +108,9 @@ class TilePlan(object):
 class DeviceGraph(object):
     """One Laplacian level on the GPU.  `.fwd` / `.bwd` = (rowptr | None, col, val, width)."""
 
-    def __init__(self, L, device, force_csr=False, tiled=True):
+    def __init__(self, L, device, force_csr=False, tiled=True, LT=None):
+        """`LT`: the matrix to use for the transposed products instead of L.T (vertex-sharded mode: the rows of
+        L^T this rank owns are not the transpose of the rows of L it owns)."""
         L = sparse.csr_matrix(L, dtype=np.float32)
         L.sum_duplicates()
         L.sort_indices()                                   # row-major, ascending columns (tf.sparse_reorder)
@@ -119,12 +121,18 @@ class DeviceGraph(object):
         self.device = device
         counts = np.diff(L.indptr)
         self.max_degree = int(counts.max()) if self.M else 0
+        if LT is not None:
+            LT = sparse.csr_matrix(LT, dtype=np.float32)
+            LT.sum_duplicates()
+            LT.sort_indices()
+            self.max_degree = max(self.max_degree, int(np.diff(LT.indptr).max()))
         self.is_ell = (not force_csr) and self.max_degree <= ELL_MAX_WIDTH
         self._want_tiles = tiled
         self.fwd_tiles = self.bwd_tiles = None
         self.fwd = self._pack(L, 'fwd')
-        LT = sparse.csr_matrix(L.T)
-        LT.sort_indices()
+        if LT is None:
+            LT = sparse.csr_matrix(L.T)
+            LT.sort_indices()
         self.symmetric_pattern = (LT.nnz == L.nnz and np.array_equal(LT.indptr, L.indptr)
                                   and np.array_equal(LT.indices, L.indices))
         if self.symmetric_pattern and np.array_equal(LT.data, L.data):
@@ -155,3 +163,63 @@ class DeviceGraph(object):
     def bytes_stored(self):
         """Bytes one sparse product reads for the matrix (8 per stored entry)."""
         return 8 * self.nnz + (0 if self.is_ell else 4 * (self.M + 1))
+
+
+class ShardedGraph(object):
+    """One Laplacian level of the vertex-sharded mode (new, the reference is single-device).
+
+    Rank r of W owns the contiguous vertex range [r*M/W, (r+1)*M/W) -- in HEALPix nested order a set of whole
+    base-pixel quadrants, so pooling by 4 stays rank-local at every level.  The local matrix has Ml = M/W owned rows
+    and Me = Ml + H columns: the owned vertices first, then the H ghost vertices (1-ring halo) sorted by global id,
+    i.e. grouped by owner.  It is stored square (Me x Me, empty ghost rows) so that the kernels of the single-GPU
+    path run unchanged on [1, Me, F] tensors whose last H rows are ghosts.  `send[q]` lists the owned rows rank q
+    needs (ascending), `recv[q]` = (first ghost slot, count) of the ghosts owned by q."""
+
+    def __init__(self, L, rank, world, device):
+        L = sparse.csr_matrix(L, dtype=np.float32)
+        L.sum_duplicates()
+        M = L.shape[0]
+        if M % world:
+            raise ValueError('{} vertices cannot be split over {} ranks'.format(M, world))
+        Ml = M // world
+        LT = sparse.csr_matrix(L.T)
+        self.M_global, self.Ml, self.rank, self.world = M, Ml, rank, world
+
+        def ghosts_of(q):
+            lo, hi = q * Ml, (q + 1) * Ml
+            c = np.union1d(L[lo:hi].indices, LT[lo:hi].indices)
+            return c[(c < lo) | (c >= hi)]
+
+        lo, hi = rank * Ml, (rank + 1) * Ml
+        ghosts = ghosts_of(rank)
+        H = len(ghosts)
+        self.H, self.Me = H, Ml + H
+        self.ghost_ids = ghosts
+
+        def localise(A):
+            rows = A[lo:hi].tocoo()
+            c = rows.col.astype(np.int64)
+            own = (c >= lo) & (c < hi)
+            lc = np.where(own, c - lo, Ml + np.searchsorted(ghosts, c))
+            return sparse.csr_matrix((rows.data, (rows.row, lc)), shape=(self.Me, self.Me), dtype=np.float32)
+
+        self.L_local, self.LT_local = localise(L), localise(LT)
+        owner = ghosts // Ml
+        self.recv = {}
+        for q in range(world):
+            n = int((owner == q).sum())
+            if n:
+                self.recv[q] = (int(np.searchsorted(owner, q)), n)
+        self.send = {}
+        for q in range(world):
+            if q == rank:
+                continue
+            g = ghosts_of(q)
+            mine = g[(g >= lo) & (g < hi)] - lo
+            if len(mine):
+                self.send[q] = mine.astype(np.int32)
+        self.device = device
+        if device is not None:
+            self.graph = DeviceGraph(self.L_local, device, tiled=False, LT=self.LT_local)
+            self.M = self.Me
+            self.send_dev = {q: torch.from_numpy(v).to(device) for q, v in self.send.items()}

@@ -28,9 +28,9 @@ import time
 import numpy as np
 import torch
 
-from . import ops, utils
+from . import halo, ops, utils
 from ._consts import ACT, UNPOOL_REPEAT, UNPOOL_ZEROFILL
-from .graph import DeviceGraph
+from .graph import DeviceGraph, ShardedGraph
 from .optimizers import _Optimizer
 
 process_time = time.process_time
@@ -94,7 +94,9 @@ class _ChebStage(object):
     decoder up-conv / de-conv / out-conv, models.py:1304-1341, with the unused parts off)."""
 
     def __init__(self, model, scope, graph, Fin, Fout, K, bn, bias, act, p=1, pool='max', keep=None, first=False):
-        self.m, self.scope, self.graph = model, scope, graph
+        self.m, self.scope = model, scope
+        self.sg = graph if isinstance(graph, ShardedGraph) else None      # vertex-sharded mode
+        self.graph = graph.graph if self.sg is not None else graph
         self.Fin, self.Fout, self.K = Fin, Fout, K
         self.bn, self.has_bias, self.act = bn, bias, act
         self.p, self.pool = p, pool            # HEALPix pooling over p consecutive vertices
@@ -107,18 +109,22 @@ class _ChebStage(object):
             model._P.add(scope + '/bias', (1, 1, Fout), np.zeros(Fout, np.float32))
         self.post = bn or bias or act != 'identity' or p > 1
         # tiny reduction depth (K*Fin <= 8) on the input layer: never materialise y (csrc/smallconv.cu)
-        self.small = bool(first and self.post and model.fused_small and ops.smallconv_supported(Fin, K, Fout))
+        self.small = bool(first and self.post and model.fused_small and self.sg is None
+                          and ops.smallconv_supported(Fin, K, Fout))
         self.saved = None
 
     def forward(self, x, training, save):
         m = self.m
         B, M, Fin = x.shape
-        if M != self.graph.M or Fin != self.Fin:
+        Mg = self.sg.Ml if self.sg is not None else self.graph.M
+        if M != Mg or Fin != self.Fin:
             raise ValueError('{}: input [{}, {}] does not fit the Laplacian ({} vertices) / weights ({} features)'
-                             .format(self.scope, M, Fin, self.graph.M, self.Fin))
+                             .format(self.scope, M, Fin, Mg, self.Fin))
         W = m._P.views[self.scope + '/weights']
         if self.small:
             return self._forward_small(x, W, training, save)
+        if self.sg is not None and self.K > 1:
+            return self._forward_sharded(x, W, training, save)
         basis = ops.cheb_basis(self.graph, x, self.K)                      # models.py:1049-1061
         sums = None
         if self.bn and training:
@@ -201,8 +207,95 @@ class _ChebStage(object):
                 ops.scale(gb, 1.0 / m.world_size)
         return None
 
+    # ------------------------------------------------------------------ vertex-sharded mode (one sample)
+    def _forward_sharded(self, x, W, training, save):
+        """The same layer on this rank's vertex range [1, Ml, Fin].  Every plane of the basis carries the H ghost
+        rows of the 1-ring halo behind the Ml owned rows ([1, Me, Fin]); one halo exchange precedes every sparse
+        product.  The ghost rows are zeroed afterwards so that the contraction can run over all Me rows without
+        touching the batch-norm sums or the weight gradient."""
+        m, sg, g, K = self.m, self.sg, self.graph, self.K
+        B, Ml, Fin = x.shape
+        if B != 1:
+            raise ValueError('the vertex-sharded mode takes one sample per step')
+        E = torch.empty((K, 1, sg.Me, Fin), dtype=torch.float32, device=x.device)
+        ops.vertex_resize(x, sg.Me, 0.0, out=E[0])
+        halo.exchange(sg, E[0], m.pg)
+        for k in range(1, K):
+            ops.spmm(g, E[k - 1], E[k - 2] if k >= 2 else None, None, out=E[k], alpha=1.0 if k == 1 else 2.0,
+                     beta=0.0 if k == 1 else -1.0, rows=Ml)
+            if k < K - 1:
+                halo.exchange(sg, E[k], m.pg)
+        if sg.H:
+            for k in range(K):
+                ops.fill(E[k, 0, Ml:], 0.0)
+        sums = None
+        if self.bn and training:
+            sums = torch.zeros(2 * self.Fout, dtype=torch.float64, device=x.device)
+        y = ops.contract_fwd(E[0], E[1:], W, K, self.Fout, sums)           # [1, Me, Fout], ghost rows = 0
+        mean = rstd = None
+        count = float(Ml * m.world_size)
+        if self.bn:
+            mean, rstd = m._bn_buffers(self.scope, self.Fout)
+            mm, mv = m._state[self.scope + '/batch_normalization/moving_mean'], \
+                m._state[self.scope + '/batch_normalization/moving_variance']
+            if training:
+                m._allreduce(sums)
+                ops.bn_finalize(sums, count, self.Fout, mean, rstd, mm, mv, BN_EPS, BN_MOMENTUM)
+            else:
+                ops.bn_from_moving(mm, mv, mean, rstd, BN_EPS)
+        yo = y[:, :Ml]                                                     # owned rows: a contiguous prefix (one sample)
+        out = yo
+        if self.post:
+            b = m._P.views[self.scope + '/bias'] if self.has_bias else None
+            out = ops.bn_act_pool_fwd(yo, mean, rstd, b, self.p, self.pool, self.act)
+        if save:
+            lean = self.post and self.bn and training and ops.bn_relu_pool_sums_supported(self.Fout, self.p, self.pool, self.act)
+            self.saved = (E, y, mean, rstd, count, training, out if lean else None)
+        return out
+
+    def _backward_sharded(self, dout, need_dx):
+        m, sg, g, K = self.m, self.sg, self.graph, self.K
+        E, y, mean, rstd, count, training, out = self.saved
+        self.saved = None
+        Ml, Fin = sg.Ml, self.Fin
+        yo = y[:, :Ml]
+        if self.post:
+            dy = torch.zeros_like(y)                                        # ghost rows stay zero
+            dyo = dy[:, :Ml]
+            b = m._P.views[self.scope + '/bias'] if self.has_bias else None
+            two_pass = self.bn and training
+            if two_pass and out is not None:
+                sums = ops.bn_relu_pool_sums(out, dout, b)
+            else:
+                _, sums = ops.bn_act_pool_bwd(yo, mean, rstd, b, dout, self.p, self.pool, self.act, want_gz=not two_pass,
+                                              out=dyo)
+            if two_pass:
+                m._allreduce(sums)
+            if self.has_bias:
+                gb = m._P.gviews[self.scope + '/bias']
+                ops.sums_to_float(sums, gb)
+                if two_pass and m.world_size > 1:
+                    ops.scale(gb, 1.0 / m.world_size)
+            if two_pass:
+                ops.bn_act_pool_bwd_dy(yo, mean, rstd, b, dout, sums, count, self.p, self.pool, self.act, out=dyo)
+        else:
+            dy = ops.vertex_resize(dout, sg.Me, 0.0)
+        ops.contract_bwd_weight(E[0], E[1:], dy, m._P.gviews[self.scope + '/weights'], K)
+        if not need_dx:
+            return None
+        W = m._P.views[self.scope + '/weights']
+        G = ops.contract_bwd_data(dy, W, K, Fin)                           # [K, 1, Me, Fin]
+        for k in range(K - 2, -1, -1):                                     # adjoint recurrence (csrc/sparse.cu)
+            halo.exchange(sg, G[k + 1], m.pg)
+            a2 = G[k + 2] if k + 2 <= K - 1 else None
+            ops.spmm(g, G[k + 1], G[k], a2, out=G[k], alpha=2.0 if k >= 1 else 1.0, beta=1.0,
+                     gamma=-1.0 if a2 is not None else 0.0, transpose=True, rows=Ml)
+        return G[0][:, :Ml]
+
     def backward(self, dout, need_dx=True):
         m = self.m
+        if self.sg is not None and self.K > 1:
+            return self._backward_sharded(dout, need_dx)
         if self.small:
             if need_dx:
                 raise RuntimeError('the fused input layer does not produce an input gradient')
@@ -570,7 +663,7 @@ class cgcnn(base_model):
                  regularization=0, dropout=1, batch_size=128, eval_frequency=200, regression=False, dense=False,
                  weighted=False, mask=None, extra_loss=False, dropFilt=1, dir_name='', profile=False, debug=False,
                  device=None, seed=None, process_group=None, cuda_graph=False, sync_every_step=True, verbose=True,
-                 fused_small=True):
+                 fused_small=True, vertex_shard=False):
         # Verify the consistency w.r.t. the number of layers (models.py:937-950).
         if not len(L) == len(F) == len(K) == len(p) == len(batch_norm):
             raise ValueError('Wrong specification of the convolutional layers: '
@@ -619,6 +712,12 @@ class cgcnn(base_model):
         self.num_feat_in = num_feat_in
         self.cuda_graph, self.sync_every_step = cuda_graph, sync_every_step
         self.fused_small = fused_small
+        self.vertex_shard = bool(vertex_shard)
+        if self.vertex_shard:
+            # contiguous nested-index vertex ranges, 1-ring halo exchange per sparse product
+            if batch_size != 1 or len(M) or dense or statistics != 'mean' or cuda_graph or self.sampling != 'healpix':
+                raise NotImplementedError('vertex_shard=True supports one sample per step, HEALPix pooling, '
+                                          "statistics='mean', no fully connected layers, no decoder, no CUDA graph")
         if mask:
             self.train_mask, self.val_mask = mask[0], mask[1]
             raise NotImplementedError('masked regression is outside the hot path')
@@ -676,7 +775,10 @@ class cgcnn(base_model):
             if Lj.shape == self.L[i].shape and Lj.nnz == self.L[i].nnz and (Lj != self.L[i]).nnz == 0:
                 self._graphs[i] = g
                 return g
-        self._graphs[i] = DeviceGraph(self.L[i], self.device)
+        if self.vertex_shard:
+            self._graphs[i] = ShardedGraph(self.L[i], self.rank, self.world_size, self.device)
+        else:
+            self._graphs[i] = DeviceGraph(self.L[i], self.device)
         return self._graphs[i]
 
     def _build_program(self, seed):
@@ -692,7 +794,7 @@ class cgcnn(base_model):
         for i in range(n):
             scope = 'conv{}'.format(i + 1)
             g = self._graph_for(i)
-            Mv = g.M
+            Mv = g.Ml if self.vertex_shard else g.M
             if i == n - 1 and len(self.M) == 0:            # linear layer before the softmax (models.py:1232-1234)
                 self._encoder.append(_ChebStage(self, scope, g, Fin, self.F[i], self.K[i], False, False, 'identity'))
                 Fin = self.F[i]
@@ -797,6 +899,9 @@ class cgcnn(base_model):
             t = torch.from_numpy(np.ascontiguousarray(self._as_bmf(a))).to(self.device, non_blocking=True)
         if t.dim() == 2:
             t = t.unsqueeze(2)
+        if self.vertex_shard:                              # this rank's contiguous vertex range
+            Ml = t.shape[1] // self.world_size
+            t = t[:, self.rank * Ml:(self.rank + 1) * Ml]
         return t.contiguous()
 
     def _labels_to_device(self, labels):
@@ -835,6 +940,10 @@ class cgcnn(base_model):
         self._stat_saved = None
         if self.statistics is not None:
             s = ops.stat_fwd(x, self.statistics)
+            if self.vertex_shard and self.world_size > 1:
+                # mean over the whole sphere = mean of the equally sized per-rank means
+                self._allreduce(s)
+                ops.scale(s, 1.0 / self.world_size)
             if save:
                 self._stat_saved = (x,)
             x = s

@@ -14,9 +14,15 @@ def _new(shape, like, dtype=torch.float32):
     return torch.empty(shape, dtype=dtype, device=like.device)
 
 
-def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, transpose=False):
-    """out = alpha * L x + beta * y + gamma * z  (tf.sparse_tensor_dense_matmul, models.py:1056,1059)."""
+def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, transpose=False, rows=None):
+    """out = alpha * L x + beta * y + gamma * z  (tf.sparse_tensor_dense_matmul, models.py:1056,1059).
+    `rows`: compute only the first `rows` rows (vertex-sharded mode, one sample: the trailing ghost rows of x are
+    inputs only)."""
     B, M, F = x.shape
+    if rows is not None:
+        if B != 1:
+            raise ValueError('rows= needs a single sample')
+        M = rows
     rowptr, col, val, width = graph.bwd if transpose else graph.fwd
     if out is None:
         out = _new((B, M, F), x)
@@ -124,11 +130,11 @@ def bn_act_pool_fwd(y, mean, rstd, bias, p, pool, act):
     return out
 
 
-def bn_act_pool_bwd(y, mean, rstd, bias, dout, p, pool, act, want_gz=True):
+def bn_act_pool_bwd(y, mean, rstd, bias, dout, p, pool, act, want_gz=True, out=None):
     """gz = dLoss/d(normalised + bias) and the per-feature sums (sum gz, sum gz*xhat); with
     want_gz=False only the sums (pass 1 of the batch-norm backward)."""
     B, M, F = y.shape
-    gz = _new((B, M, F), y) if want_gz else None
+    gz = (_new((B, M, F), y) if out is None else out) if want_gz else None
     sums = torch.zeros(2 * F, dtype=torch.float64, device=y.device)
     call('bn_act_pool_bwd', y, mean, rstd, bias, dout, gz, sums, B, M, F, p, POOL[pool], ACT[act])
     return gz, sums
@@ -146,10 +152,18 @@ def bn_relu_pool_sums(out, dout, bias):
     return sums
 
 
-def bn_act_pool_bwd_dy(y, mean, rstd, bias, dout, sums, count, p, pool, act):
+def gather_rows(x, idx):
+    """out[i] = x[idx[i]] for a [M, F] matrix (send buffer of the halo exchange)."""
+    F = x.shape[-1]
+    out = _new((idx.numel(), F), x)
+    call('gather_rows', x, idx, idx.numel(), F, out)
+    return out
+
+
+def bn_act_pool_bwd_dy(y, mean, rstd, bias, dout, sums, count, p, pool, act, out=None):
     """Pass 2 of the batch-norm backward: dy from y, dout and the (all-reduced) sums."""
     B, M, F = y.shape
-    dy = _new((B, M, F), y)
+    dy = _new((B, M, F), y) if out is None else out
     call('bn_act_pool_bwd_dy', y, mean, rstd, bias, dout, sums, float(count), dy, B, M, F, p, POOL[pool], ACT[act])
     return dy
 
@@ -163,9 +177,10 @@ def sums_to_float(sums, out):
     call('sums_to_float', sums, out, out.numel())
 
 
-def vertex_resize(x, Mout, fill):
+def vertex_resize(x, Mout, fill, out=None):
     B, Min, F = x.shape
-    out = _new((B, Mout, F), x)
+    if out is None:
+        out = _new((B, Mout, F), x)
     call('vertex_resize', x, out, B, Min, Mout, F, float(fill))
     return out
 

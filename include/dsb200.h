@@ -198,6 +198,9 @@ int dsb200_sums_to_float(const double* sums, float* out, int n, void* stream);
  * fill = 1 is the icosahedral unpool tf.pad(..., constant_values=1) (models.py:1356-1358);
  * fill = 0 gives the backward of the slice. */
 int dsb200_vertex_resize(const float* x, float* out, int B, int Min, int Mout, int F, float fill, void* stream);
+/* out[i, :] = x[idx[i], :] for i < n: packs the boundary rows a neighbouring rank needs into the send buffer of
+ * the halo exchange of the vertex-sharded mode (new; the reference is single-device). */
+int dsb200_gather_rows(const float* x, const int32_t* idx, long long n, int F, float* out, void* stream);
 /* ---- HEALPix unpooling (models.py:1362-1364 repeat, 1372-1375 value then p-1 zeros) */
 int dsb200_unpool_fwd(const float* x, float* out, int B, int M, int F, int p, int mode, void* stream);
 int dsb200_unpool_bwd(const float* dout, float* dx, int B, int M, int F, int p, int mode, void* stream);
