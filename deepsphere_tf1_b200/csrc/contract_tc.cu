@@ -389,7 +389,28 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                 }
             } else {
                 const long long plane = p.R * (long long)p.Fin;
-                for (int c0 = 0; c0 < p.Nreal; c0 += 8) {
+                const bool wide = (((uintptr_t)p.out | (uintptr_t)(plane * 4)) & 31) == 0;   // 32-byte stores possible
+                int c0 = 0;
+                for (; c0 + 16 <= p.Nreal; c0 += 16) {              // 16 columns per TMEM round trip
+                    float hi[16], lo[16];
+                    tmem_ld16(tbase + c0, hi);
+                    tmem_ld16(tbase + p.Npad + c0, lo);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) hi[i] += lo[i];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int qq = p.n0 + c0 + 8 * h;
+                            const int kq = qq / p.Fin, fi = qq - kq * p.Fin;
+                            float* o = p.out + kq * plane + row * p.Fin + fi;
+                            if (wide) st8(o, hi + 8 * h);
+                            else { st4(o, make_float4(hi[8 * h], hi[8 * h + 1], hi[8 * h + 2], hi[8 * h + 3]));
+                                   st4(o + 4, make_float4(hi[8 * h + 4], hi[8 * h + 5], hi[8 * h + 6], hi[8 * h + 7])); }
+                        }
+                    }
+                }
+                for (; c0 < p.Nreal; c0 += 8) {
                     float hi[8], lo[8];
                     tmem_ld8(tbase + c0, hi);
                     tmem_ld8(tbase + p.Npad + c0, lo);
@@ -398,8 +419,10 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                         const int qq = p.n0 + c0;
                         const int kq = qq / p.Fin, fi = qq - kq * p.Fin;
                         float* o = p.out + kq * plane + row * p.Fin + fi;
-                        st4(o, make_float4(hi[0] + lo[0], hi[1] + lo[1], hi[2] + lo[2], hi[3] + lo[3]));
-                        st4(o + 4, make_float4(hi[4] + lo[4], hi[5] + lo[5], hi[6] + lo[6], hi[7] + lo[7]));
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) hi[i] += lo[i];
+                        if (wide) st8(o, hi);
+                        else { st4(o, make_float4(hi[0], hi[1], hi[2], hi[3])); st4(o + 4, make_float4(hi[4], hi[5], hi[6], hi[7])); }
                     }
                 }
             }

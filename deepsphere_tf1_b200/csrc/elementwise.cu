@@ -93,6 +93,41 @@ bn_act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
     }
 }
 
+// Lean forward for the combination every DeepSphere encoder layer uses (batch norm, relu, max pool over P children,
+// F % 4 == 0), same arithmetic as the general kernel.  One thread = one float4 feature group of one pooled row, its P
+// loads issued back to back; the per-feature parameters sit in shared memory.
+template <int P>
+__global__ void __launch_bounds__(256)
+bn_relu_max_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ bias, float* __restrict__ out, long long total, int Fv)
+{
+    extern __shared__ float par[];                          // [3][F]: mean, rstd, bias
+    const int F = Fv * 4;
+    for (int i = threadIdx.x; i < F; i += blockDim.x) {
+        par[i] = __ldg(mean + i);
+        par[F + i] = __ldg(rstd + i);
+        par[2 * F + i] = bias ? __ldg(bias + i) : 0.f;
+    }
+    __syncthreads();
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const long long ro = g / Fv;
+    const int f0 = (int)(g - ro * Fv) * 4;
+    const float* yp = y + (ro * P) * F + f0;
+    float4 q[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) q[j] = ldg4(yp + (long long)j * F);
+    const float4 mu = *reinterpret_cast<const float4*>(par + f0), rs = *reinterpret_cast<const float4*>(par + F + f0);
+    const float4 bs = *reinterpret_cast<const float4*>(par + 2 * F + f0);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);            // relu folded into the running maximum
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        r.x = fmaxf(r.x, (q[j].x - mu.x) * rs.x + bs.x); r.y = fmaxf(r.y, (q[j].y - mu.y) * rs.y + bs.y);
+        r.z = fmaxf(r.z, (q[j].z - mu.z) * rs.z + bs.z); r.w = fmaxf(r.w, (q[j].w - mu.w) * rs.w + bs.w);
+    }
+    st4(out + ro * F + f0, r);
+}
+
 // Backward of the chain.  Threads are arranged [rows_per_block][Fv] so that a thread keeps the
 // same feature group over its grid-stride loop and can accumulate sum(gz), sum(gz*xhat) in
 // registers; one shared-memory and one double-precision global atomic pass at the end.
@@ -755,6 +790,18 @@ extern "C" int dsb200_bn_act_pool_fwd(const float* y, const float* mean, const f
     DSB_REQUIRE(M % p == 0, "bn_act_pool_fwd: M must be a multiple of p");
     DSB_REQUIRE((mean == nullptr) == (rstd == nullptr), "bn_act_pool_fwd: mean and rstd go together");
     const long long Rout = (long long)B * (M / p);
+    if (F % 4 == 0 && F <= 2048 && aligned16(y, out) && act == DSB200_ACT_RELU && mean && rstd &&
+        (p == 1 || (pool == DSB200_POOL_MAX && (p == 2 || p == 4)))) {
+        const long long total = Rout * (F / 4);
+        const long long blocks = (total + 255) / 256;
+        if (blocks <= 0x7fffffffLL) {
+            const size_t sm = 3 * (size_t)F * sizeof(float);
+#define DSB_LEAN(PP) bn_relu_max_fwd_kernel<PP><<<(unsigned)blocks, 256, sm, STREAM>>>(y, mean, rstd, bias, out, total, F / 4)
+            if (p == 1) DSB_LEAN(1); else if (p == 2) DSB_LEAN(2); else DSB_LEAN(4);
+#undef DSB_LEAN
+            DSB_LAUNCH_CHECK();
+        }
+    }
 #define DSB_FWD(V, A, G) bn_act_pool_fwd_kernel<V, A><<<G, 256, 0, STREAM>>>(y, mean, rstd, bias, out, Rout, F / V, p, pool, act)
     if (F % 4 == 0 && aligned16(y, out)) {
         const int g = grid_for(Rout * (F / 4), 256);

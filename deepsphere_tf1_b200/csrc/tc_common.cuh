@@ -107,6 +107,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// one 32-byte store (sm_100+): a full sector per thread instead of two half-sector writes; dst 32-byte aligned
+__device__ __forceinline__ void st8(float* dst, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor.  swz: 0 none, 1 32B, 2 64B, 3 128B (log2 of the atom width in 16-byte units).
