@@ -715,9 +715,9 @@ class cgcnn(base_model):
         self.vertex_shard = bool(vertex_shard)
         if self.vertex_shard:
             # contiguous nested-index vertex ranges, 1-ring halo exchange per sparse product
-            if batch_size != 1 or len(M) or dense or statistics != 'mean' or cuda_graph or self.sampling != 'healpix':
+            if batch_size != 1 or len(M) or dense or statistics != 'mean' or self.sampling != 'healpix':
                 raise NotImplementedError('vertex_shard=True supports one sample per step, HEALPix pooling, '
-                                          "statistics='mean', no fully connected layers, no decoder, no CUDA graph")
+                                          "statistics='mean', no fully connected layers, no decoder")
         if mask:
             self.train_mask, self.val_mask = mask[0], mask[1]
             raise NotImplementedError('masked regression is outside the hot path')
