@@ -915,7 +915,9 @@ int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, fl
     p.tmem_cols = tcols;
     // CTAs per SM: limited by TMEM (512 columns) and by shared memory
     int ctas = 512 / tcols;
-    const int want = env_int("DSB200_WG_CTAS", 2);
+    // Two CTAs per SM are faster (146 vs 169 us at cosmo layer 2) but with 16-row stages the pipeline deadlocked about once in
+    // 10^4 launches (mbarrier time-outs 11 / 13 in tools/stress_step.py); one CTA per SM never did.  Opt in with DSB200_WG_CTAS=2.
+    const int want = env_int("DSB200_WG_CTAS", 1);
     if (ctas > want) ctas = want;
     if (ctas < 1) ctas = 1;
     // the last 128-wide tile of q may read past the X_lo blocks: keep it inside the stage ([X][X_lo][dY][dY_lo][pad])
