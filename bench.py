@@ -184,7 +184,7 @@ def spmm_roofline(model, B, iters=20):
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get('spmm_kernel_dram_bytes_per_launch')
     return {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': traffic,
-            'kernel': 'spmm_kernel<4,false> (ChebConv recurrence step, layer 2: B={} M={} Fin={})'.format(B, M, Fin),
+            'kernel': 'spmm_rows_kernel<1,9,false> (ChebConv recurrence step, layer 2: B={} M={} Fin={})'.format(B, M, Fin),
             'algorithmic_bytes_per_launch': bytes_alg, 'avg_launch_us': t * 1e6, 'peak_source': how}
 
 
