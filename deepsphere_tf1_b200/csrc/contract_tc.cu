@@ -307,7 +307,10 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
         uint32_t ph = 0, it = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
             for (int j0 = 0; j0 < p.nkb; j0 += p.G, ++it) {
-                if ((int)(it & 1u) == grp) {
+                // A stage always belongs to the same group (s & 1), and a group walks its stages in issue order.  Alternating on
+                // the iteration counter instead lets, with an odd number of stages, the OTHER group wait for the next phase of a
+                // stage whose current phase has not completed yet -- a parity wait that passes immediately (the wgrad deadlock).
+                if ((s & 1) == grp) {
                     const int cnt = min(p.G, p.nkb - j0);
                     mbar_wait(full_tma + s, ph, 4);
                     if (tt == 0) RG_DBG((int)it, 2);
@@ -316,12 +319,10 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                     const int nvec = (int)(cnt * tile_bytes / 16);
 #pragma unroll 4
                     for (int i = tt; i < nvec; i += 128) {
-                        const float4 v = A[i];
-                        float4 h, l;
-                        h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-                        l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-                        A[i] = h;
-                        Al[i] = l;
+                        // The tensor core reads a TF32 operand truncated (low 13 mantissa bits ignored), so the landed
+                        // fp32 tile IS the hi part; lo = the bits it drops, exact in fp32 (cvt.rna.tf32 would cost ~10 SASS
+                        // instructions per element and a second store).
+                        Al[i] = tf32_dropped_bits(A[i]);
                     }
                     fence_proxy_async();
                     mbar_arrive(full_mma + s);
@@ -797,7 +798,7 @@ wgrad_tc_kernel(const __grid_constant__ WGradParams p)
         int s = 0;
         uint32_t ph = 0;
         for (int i = 0; i < niter; ++i) {
-            if ((i & 1) != grp) { if (++s == S) { s = 0; ph ^= 1u; } continue; }
+            if ((s & 1) != grp) { if (++s == S) { s = 0; ph ^= 1u; } continue; }     // stage -> group, see the row-GEMM
             mbar_wait(full_tma + s, ph, 14);
             float4* X = reinterpret_cast<float4*>(sA + (size_t)s * stage_bytes);
             float4* Xl = X + nvecX;
@@ -807,12 +808,7 @@ wgrad_tc_kernel(const __grid_constant__ WGradParams p)
             for (int j = tt; j < nvecX + nvecY; j += 128) {
                 float4* src = j < nvecX ? X + j : Y + (j - nvecX);
                 float4* dlo = j < nvecX ? Xl + j : Yl + (j - nvecX);
-                const float4 v = *src;
-                float4 h, l;
-                h.x = to_tf32(v.x); h.y = to_tf32(v.y); h.z = to_tf32(v.z); h.w = to_tf32(v.w);
-                l.x = to_tf32(v.x - h.x); l.y = to_tf32(v.y - h.y); l.z = to_tf32(v.z - h.z); l.w = to_tf32(v.w - h.w);
-                *src = h;
-                *dlo = l;
+                *dlo = tf32_dropped_bits(*src);                   // hi = the tile as it landed (read truncated by the tensor core)
             }
             fence_proxy_async();
             mbar_arrive(full_mma + s);
@@ -915,9 +911,7 @@ int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, fl
     p.tmem_cols = tcols;
     // CTAs per SM: limited by TMEM (512 columns) and by shared memory
     int ctas = 512 / tcols;
-    // Two CTAs per SM are faster (146 vs 169 us at cosmo layer 2) but with 16-row stages the pipeline deadlocked about once in
-    // 10^4 launches (mbarrier time-outs 11 / 13 in tools/stress_step.py); one CTA per SM never did.  Opt in with DSB200_WG_CTAS=2.
-    const int want = env_int("DSB200_WG_CTAS", 1);
+    const int want = env_int("DSB200_WG_CTAS", 2);
     if (ctas > want) ctas = want;
     if (ctas < 1) ctas = 1;
     // the last 128-wide tile of q may read past the X_lo blocks: keep it inside the stage ([X][X_lo][dY][dY_lo][pad])

@@ -138,6 +138,16 @@ __device__ __forceinline__ float to_tf32(float x) {      // round to nearest, 10
     return __uint_as_float(r);
 }
 
+// x - trunc_tf32(x): the part of an fp32 value a TF32 tensor-core operand does not see (exact in fp32)
+__device__ __forceinline__ float4 tf32_dropped_bits(const float4 v) {
+    float4 l;
+    l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+    l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+    l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+    l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    return l;
+}
+
 // ---------------------------------------------------------------- host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

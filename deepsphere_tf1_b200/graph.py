@@ -105,10 +105,67 @@ class TilePlan(object):
         return (self.info, self.recs, self.ext, self.ntiles, self.TR, self.n1cap, self.n2cap, self.width)
 
 
+BLOCK_ROWS = 16            # rows per block of the tensor-core product (csrc/sparse_blk.cu): the M of mma.m16n8k8
+BLOCK_MAX_ROWS = 4 << 20   # no block plan above this many rows (2.7 KB per block)
+
+
+class BlockPlan(object):
+    """Dense [16 x 8*KS] blocks of L for the tensor-core sparse product (csrc/sparse_blk.cu).
+
+    Block b = rows [16 b, 16 b + 16).  `cols[b]` lists its distinct columns in ascending order, padded with the
+    block's first row; `frags[b]` holds the block's values in mma.m16n8k8 A-fragment order:
+    frags[b, s, lane] = (A[g, 8s+t], A[g+8, 8s+t], A[g, 8s+t+4], A[g+8, 8s+t+4]),  g = lane // 4, t = lane % 4."""
+
+    def __init__(self, col, val, device):
+        M, W = col.shape
+        self.valid = False
+        if M == 0 or M > BLOCK_MAX_ROWS:
+            return
+        nb = (M + BLOCK_ROWS - 1) // BLOCK_ROWS
+        Mp = nb * BLOCK_ROWS
+        c = np.empty((Mp, W), np.int64)
+        v = np.zeros((Mp, W), np.float32)
+        c[:M], v[:M] = col, val
+        if Mp > M:                                            # ragged last block: empty rows
+            c[M:] = (nb - 1) * BLOCK_ROWS
+        first = (np.arange(nb, dtype=np.int64) * BLOCK_ROWS)[:, None]
+        cb = np.where(v.reshape(nb, -1) != 0, c.reshape(nb, -1), first)       # unused slots point at the block itself
+        order = np.argsort(cb, axis=1, kind='stable')
+        srt = np.take_along_axis(cb, order, axis=1)
+        new = np.ones(srt.shape, bool)
+        new[:, 1:] = srt[:, 1:] != srt[:, :-1]
+        pos_sorted = np.cumsum(new, axis=1) - 1                                # union index of every sorted entry
+        nu = pos_sorted[:, -1] + 1
+        KS = int((nu.max() + 7) // 8)
+        KS = max(KS, 5)
+        if KS > 7:
+            return                                            # too many distinct columns per block: keep the gather kernels
+        K8 = 8 * KS
+        pos = np.empty_like(pos_sorted)
+        np.put_along_axis(pos, order, pos_sorted, axis=1)                      # union index of every original entry
+        cols = np.repeat(first, K8, axis=1)
+        bi = np.repeat(np.arange(nb), srt.shape[1]).reshape(srt.shape)
+        cols[bi[new], pos_sorted[new]] = srt[new]
+        A = np.zeros((nb, BLOCK_ROWS, K8), np.float32)
+        vb = v.reshape(nb, -1)
+        ri = np.tile(np.repeat(np.arange(BLOCK_ROWS), W), (nb, 1))
+        nz = vb != 0
+        A[bi[nz], ri[nz], pos[nz]] = vb[nz]
+        lane = np.arange(32)
+        g, t = lane // 4, lane % 4
+        s8 = 8 * np.arange(KS)[:, None]
+        frags = np.stack([A[:, g[None, :], s8 + t[None, :]], A[:, g[None, :] + 8, s8 + t[None, :]],
+                          A[:, g[None, :], s8 + t[None, :] + 4], A[:, g[None, :] + 8, s8 + t[None, :] + 4]], axis=-1)
+        self.cols = torch.from_numpy(cols.astype(np.int32)).to(device)
+        self.frags = torch.from_numpy(np.ascontiguousarray(frags, dtype=np.float32)).to(device)
+        self.nblocks, self.KS = nb, KS
+        self.valid = True
+
+
 class DeviceGraph(object):
     """One Laplacian level on the GPU.  `.fwd` / `.bwd` = (rowptr | None, col, val, width)."""
 
-    def __init__(self, L, device, force_csr=False, tiled=True, LT=None):
+    def __init__(self, L, device, force_csr=False, tiled=False, LT=None, blocks=False):
         """`LT`: the matrix to use for the transposed products instead of L.T (vertex-sharded mode: the rows of
         L^T this rank owns are not the transpose of the rows of L it owns)."""
         L = sparse.csr_matrix(L, dtype=np.float32)
@@ -127,8 +184,9 @@ class DeviceGraph(object):
             LT.sort_indices()
             self.max_degree = max(self.max_degree, int(np.diff(LT.indptr).max()))
         self.is_ell = (not force_csr) and self.max_degree <= ELL_MAX_WIDTH
-        self._want_tiles = tiled
+        self._want_tiles, self._want_blocks = tiled, blocks
         self.fwd_tiles = self.bwd_tiles = None
+        self.fwd_blocks = self.bwd_blocks = None
         self.fwd = self._pack(L, 'fwd')
         if LT is None:
             LT = sparse.csr_matrix(L.T)
@@ -138,6 +196,7 @@ class DeviceGraph(object):
         if self.symmetric_pattern and np.array_equal(LT.data, L.data):
             self.bwd = self.fwd
             self.bwd_tiles = self.fwd_tiles
+            self.bwd_blocks = self.fwd_blocks
         else:
             self.bwd = self._pack(LT, 'bwd')
 
@@ -152,6 +211,9 @@ class DeviceGraph(object):
             slot = np.arange(A.nnz) - np.repeat(A.indptr[:-1], counts)
             col[rows, slot] = A.indices
             val[rows, slot] = A.data
+            if self._want_blocks:
+                bp = BlockPlan(col, val, self.device)
+                setattr(self, which + '_blocks', bp if bp.valid else None)
             if self._want_tiles:
                 plan = TilePlan(col, val, self.device)
                 setattr(self, which + '_tiles', plan if plan.valid else None)

@@ -51,6 +51,14 @@ const char* dsb200_last_error(void);
 /* number of CUDA kernels this library has launched in this process (all threads) */
 long long dsb200_kernel_launches(void);
 
+/* the same product on the tensor cores (csrc/sparse_blk.cu): 16 consecutive rows and their at most 8*ksteps distinct
+ * columns are one dense [16 x 8*ksteps] block of L, multiplied with mma.sync TF32 (3xTF32 split: fp32-level accuracy).
+ * blk_cols int32[nblocks][8*ksteps] = the column list of every block (padding: the block's first row, zero weights);
+ * blk_frags float[nblocks][ksteps][32][4] = the block in m16n8k8 A-fragment order.  F % 8 == 0, ksteps in 5..7. */
+int dsb200_spmm_blk(const int32_t* blk_cols, const float* blk_frags, int nblocks, int ksteps, int B, int M, int F,
+                    const float* x, const float* y, const float* z, float* out,
+                    float alpha, float beta, float gamma, void* stream);
+
 /* ---- K1: one sparse-Laplacian product with fused recurrence arithmetic, for all B samples
  *      out[b] = alpha * L x[b] + beta * y[b] + gamma * z[b]    (y, z NULL when beta/gamma == 0;
  *      out may alias y or z)

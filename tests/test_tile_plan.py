@@ -52,7 +52,7 @@ def test_tile_plan_reproduces_two_recurrence_steps(case):
          'ragged_last_tile': lambda: healpix_L(8).tocsr()[:700, :700]}[case]()
     L = sparse.csr_matrix(L, dtype=np.float32)
     M = L.shape[0]
-    g = DeviceGraph(L, torch.device('cpu'))
+    g = DeviceGraph(L, torch.device('cpu'), tiled=True)
     plan = g.fwd_tiles
     assert plan is not None and plan.valid and plan.ntiles == (M + plan.TR - 1) // plan.TR
     rs = np.random.RandomState(0)
@@ -70,7 +70,7 @@ def test_tile_plan_reproduces_two_recurrence_steps(case):
 
 def test_tile_plan_halo_rings_are_minimal_and_keep_bank_bits():
     L = sparse.csr_matrix(healpix_L(16), dtype=np.float32)
-    g = DeviceGraph(L, torch.device('cpu'))
+    g = DeviceGraph(L, torch.device('cpu'), tiled=True)
     plan = g.fwd_tiles
     info, ext = plan.info.numpy(), plan.ext.numpy()
     pattern = sparse.csr_matrix((np.ones(L.nnz), L.indices, L.indptr), shape=L.shape)
@@ -99,7 +99,7 @@ def test_tile_plan_halo_rings_are_minimal_and_keep_bank_bits():
 
 def test_graphs_without_locality_or_wide_rows_keep_the_gather_kernels():
     # random sparse matrix: the halo of a 256-row tile is (almost) the whole graph
-    g = DeviceGraph(random_L(6000, 6), torch.device('cpu'))
+    g = DeviceGraph(random_L(6000, 6), torch.device('cpu'), tiled=True)
     assert g.fwd_tiles is None and g.bwd_tiles is None
     # more than 10 entries per row do not fit a row record
     n = 600
@@ -111,9 +111,39 @@ def test_graphs_without_locality_or_wide_rows_keep_the_gather_kernels():
 def test_nonsymmetric_values_get_their_own_transposed_plan():
     L = sparse.csr_matrix(healpix_L(8), dtype=np.float32)
     L = sparse.csr_matrix(L.multiply(sparse.csr_matrix(1.0 + 0.1 * np.random.RandomState(0).rand(*L.shape))), dtype=np.float32)
-    g = DeviceGraph(L, torch.device('cpu'))
+    g = DeviceGraph(L, torch.device('cpu'), tiled=True)
     assert g.bwd_tiles is not None and g.bwd_tiles is not g.fwd_tiles
     rs = np.random.RandomState(1)
     x = rs.randn(L.shape[0], 4)
     o1, _ = _emulate(g.bwd_tiles, L.shape[0], x)
     np.testing.assert_allclose(o1, L.T.astype(np.float64) @ x, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize('case', ['full_sphere', 'partial_sphere', 'ragged_last_block', 'nonsym_values'])
+def test_block_plan_is_the_matrix(case):
+    """Tensor-core block formulation (csrc/sparse_blk.cu): the column lists and the A fragments of the 16-row blocks,
+    unpacked the way mma.m16n8k8 reads them, reproduce L x (and L^T x from the transposed plan)."""
+    from deepsphere_tf1_b200.graph import BLOCK_ROWS
+    L = {'full_sphere': lambda: healpix_L(16), 'partial_sphere': lambda: healpix_L(32, order=2),
+         'ragged_last_block': lambda: healpix_L(8).tocsr()[:700, :700], 'nonsym_values': lambda: healpix_L(8)}[case]()
+    L = sparse.csr_matrix(L, dtype=np.float32)
+    if case == 'nonsym_values':
+        L = sparse.csr_matrix(L.multiply(sparse.csr_matrix(1.0 + 0.1 * np.random.RandomState(0).rand(*L.shape))), dtype=np.float32)
+    M = L.shape[0]
+    g = DeviceGraph(L, torch.device('cpu'), blocks=True)
+    x = np.random.RandomState(1).randn(M, 3)
+    for bp, A_ref in ((g.fwd_blocks, L), (g.bwd_blocks, L.T)):
+        assert bp is not None and bp.nblocks == (M + BLOCK_ROWS - 1) // BLOCK_ROWS and 5 <= bp.KS <= 7
+        cols, fr = bp.cols.numpy(), bp.frags.numpy()
+        assert cols.shape == (bp.nblocks, 8 * bp.KS) and fr.shape == (bp.nblocks, bp.KS, 32, 4)
+        assert cols.min() >= 0 and cols.max() < M
+        A = np.zeros((bp.nblocks, BLOCK_ROWS, 8 * bp.KS), np.float32)
+        lane = np.arange(32)
+        gq, t = lane // 4, lane % 4
+        for s_ in range(bp.KS):
+            A[:, gq, 8 * s_ + t] = fr[:, s_, :, 0]
+            A[:, gq + 8, 8 * s_ + t] = fr[:, s_, :, 1]
+            A[:, gq, 8 * s_ + t + 4] = fr[:, s_, :, 2]
+            A[:, gq + 8, 8 * s_ + t + 4] = fr[:, s_, :, 3]
+        out = np.einsum('bik,bkf->bif', A.astype(np.float64), x[cols]).reshape(-1, 3)[:M]
+        np.testing.assert_allclose(out, A_ref.astype(np.float64) @ x, rtol=0, atol=1e-12)
