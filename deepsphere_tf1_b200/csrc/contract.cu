@@ -359,7 +359,8 @@ extern "C" int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const 
     Planar A{x0, xk, Fin, R * (long long)Fin};
     const int Q = K * Fin;
     if (g_use_tc.load(std::memory_order_relaxed) && Q > 16) {
-        const int rc = tc::contract_fwd_tc(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, workspace, s);
+        int rc = tc::contract_fwd_tc_cols(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, workspace, s);
+        if (rc == 1) rc = tc::contract_fwd_tc(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, workspace, s);
         if (rc != 1) return rc;                            // 1 = shape not supported on the tensor-core path
     }
     if (small_path(Q, Fout) && (((uintptr_t)Y & 15) == 0)) {

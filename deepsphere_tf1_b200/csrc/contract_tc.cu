@@ -558,7 +558,9 @@ size_t contract_workspace_bytes(int Fin, int K, int Fout)
     const size_t nb = (Q + 159) / 160;
     const size_t NB = ((Q + nb - 1) / nb + 15) / 16 * 16;
     const size_t bwd = 2 * nb * NB * (size_t)Fout * 4;
-    return (fwd > bwd ? fwd : bwd) + 1024;
+    size_t need = (fwd > bwd ? fwd : bwd) + 1024;
+    const size_t cols = colgemm_workspace_bytes(Fin, K);
+    return need > cols ? need : cols;
 }
 
 // Forward contraction on the tensor cores.  Returns 1 if the shape is not supported (caller falls back).

@@ -163,6 +163,10 @@ int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, 
 int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R, int Fin, int K, int Fout,
                          void* workspace, cudaStream_t s);
 size_t contract_workspace_bytes(int Fin, int K, int Fout);
+// forward contraction with the rows on the N side of the instruction (contract_tc2.cu)
+int contract_fwd_tc_cols(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
+                         double* bn_sums, void* workspace, cudaStream_t s);
+size_t colgemm_workspace_bytes(int Fin, int K);
 int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K,
                            int Fout, cudaStream_t s);
 
