@@ -879,7 +879,7 @@ extern "C" int dsb200_bn_relu_pool_sums(const float* out, const float* dout, con
     DSB_REQUIRE(F % 4 == 0 && F <= 1024, "bn_relu_pool_sums: F must be a multiple of 4, at most 1024");
     DSB_REQUIRE(aligned16(out, dout), "bn_relu_pool_sums: tensors must be 16-byte aligned");
     const int Fv = F / 4, rpb = 256 / Fv;
-    const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 4);
+    const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 8);
     bn_relu_pool_sums_kernel<<<grid, 256, 2 * (size_t)F * sizeof(float), STREAM>>>(out, dout, bias, sums_bwd, Rout, Fv);
     DSB_LAUNCH_CHECK();
 }

@@ -128,7 +128,7 @@ class _ChebStage(object):
         basis = ops.cheb_basis(self.graph, x, self.K)                      # models.py:1049-1061
         sums = None
         if self.bn and training:
-            sums = torch.zeros(2 * self.Fout, dtype=torch.float64, device=x.device)
+            sums = m._zeros(2 * self.Fout)
         y = ops.contract_fwd(x, basis, W, self.K, self.Fout, sums)         # models.py:1062-1078
         mean = rstd = None
         count = float(B * M * m.world_size)
@@ -230,7 +230,7 @@ class _ChebStage(object):
                 ops.fill(E[k, 0, Ml:], 0.0)
         sums = None
         if self.bn and training:
-            sums = torch.zeros(2 * self.Fout, dtype=torch.float64, device=x.device)
+            sums = m._zeros(2 * self.Fout)
         y = ops.contract_fwd(E[0], E[1:], W, K, self.Fout, sums)           # [1, Me, Fout], ghost rows = 0
         mean = rstd = None
         count = float(Ml * m.world_size)
@@ -265,10 +265,10 @@ class _ChebStage(object):
             b = m._P.views[self.scope + '/bias'] if self.has_bias else None
             two_pass = self.bn and training
             if two_pass and out is not None:
-                sums = ops.bn_relu_pool_sums(out, dout, b)
+                sums = ops.bn_relu_pool_sums(out, dout, b, sums=m._zeros(2 * self.Fout))
             else:
                 _, sums = ops.bn_act_pool_bwd(yo, mean, rstd, b, dout, self.p, self.pool, self.act, want_gz=not two_pass,
-                                              out=dyo)
+                                              out=dyo, sums=m._zeros(2 * self.Fout))
             if two_pass:
                 m._allreduce(sums)
             if self.has_bias:
@@ -310,9 +310,10 @@ class _ChebStage(object):
             b = m._P.views[self.scope + '/bias'] if self.has_bias else None
             two_pass = self.bn and training          # batch norm: sums first, then dy directly (gz never stored)
             if two_pass and out is not None:
-                dy, sums = None, ops.bn_relu_pool_sums(out, dout, b)       # pooled tensors only
+                dy, sums = None, ops.bn_relu_pool_sums(out, dout, b, sums=m._zeros(2 * self.Fout))   # pooled tensors only
             else:
-                dy, sums = ops.bn_act_pool_bwd(y, mean, rstd, b, dout, self.p, self.pool, self.act, want_gz=not two_pass)
+                dy, sums = ops.bn_act_pool_bwd(y, mean, rstd, b, dout, self.p, self.pool, self.act, want_gz=not two_pass,
+                                               sums=m._zeros(2 * self.Fout))
             if two_pass:
                 m._allreduce(sums)
             if self.has_bias:
@@ -864,6 +865,8 @@ class cgcnn(base_model):
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(0 if seed is None else int(seed))
         self._graph_exec = None
+        self._arena = torch.zeros(16384, dtype=torch.float64, device=self.device)
+        self._arena_off = None
 
     def _reset_variables(self):
         """`sess.run(op_init)`: back to the initial values (models.py:476-479)."""
@@ -913,6 +916,15 @@ class cgcnn(base_model):
             t = torch.from_numpy(np.ascontiguousarray(labels)).to(self.device, non_blocking=True)
         t = t.to(torch.float32 if self.regression else torch.int32)
         return t.contiguous()
+
+    def _zeros(self, n):
+        """n zeroed doubles for the per-feature sums of this step: slices of one arena that `_step_device` clears
+        with a single memset (ten separate fills per step otherwise).  Outside a training step: a fresh tensor."""
+        if self._arena_off is None or self._arena_off + n > self._arena.numel():
+            return torch.zeros(n, dtype=torch.float64, device=self.device)
+        t = self._arena[self._arena_off:self._arena_off + n]
+        self._arena_off += (n + 1) // 2 * 2
+        return t
 
     def _allreduce(self, t):
         if self.world_size > 1:
@@ -1035,9 +1047,14 @@ class cgcnn(base_model):
         P = self._P
         ops.fill(P.g, 0.0)
         self._loss.zero_()
-        logits, _ = self._forward(x, training=True, save=True)
-        dlogits = self._loss_fwd_bwd(logits, labels, True)
-        self._backward(dlogits)
+        self._arena.zero_()
+        self._arena_off = 0
+        try:
+            logits, _ = self._forward(x, training=True, save=True)
+            dlogits = self._loss_fwd_bwd(logits, labels, True)
+            self._backward(dlogits)
+        finally:
+            self._arena_off = None
         if self.world_size > 1:
             self._allreduce(P.g)                           # one flat NCCL all-reduce for every gradient
             ops.scale(self._loss, 1.0 / self.world_size)

@@ -157,12 +157,13 @@ def bn_act_pool_fwd(y, mean, rstd, bias, p, pool, act):
     return out
 
 
-def bn_act_pool_bwd(y, mean, rstd, bias, dout, p, pool, act, want_gz=True, out=None):
+def bn_act_pool_bwd(y, mean, rstd, bias, dout, p, pool, act, want_gz=True, out=None, sums=None):
     """gz = dLoss/d(normalised + bias) and the per-feature sums (sum gz, sum gz*xhat); with
     want_gz=False only the sums (pass 1 of the batch-norm backward)."""
     B, M, F = y.shape
     gz = (_new((B, M, F), y) if out is None else out) if want_gz else None
-    sums = torch.zeros(2 * F, dtype=torch.float64, device=y.device)
+    if sums is None:
+        sums = torch.zeros(2 * F, dtype=torch.float64, device=y.device)
     call('bn_act_pool_bwd', y, mean, rstd, bias, dout, gz, sums, B, M, F, p, POOL[pool], ACT[act])
     return gz, sums
 
@@ -171,10 +172,11 @@ def bn_relu_pool_sums_supported(F, p, pool, act):
     return act == 'relu' and (p == 1 or pool == 'max') and F % 4 == 0 and F <= 1024
 
 
-def bn_relu_pool_sums(out, dout, bias):
+def bn_relu_pool_sums(out, dout, bias, sums=None):
     """Pass 1 of the batch-norm backward for relu (+ max pool) from the pooled tensors only."""
     F = out.shape[-1]
-    sums = torch.zeros(2 * F, dtype=torch.float64, device=out.device)
+    if sums is None:
+        sums = torch.zeros(2 * F, dtype=torch.float64, device=out.device)
     call('bn_relu_pool_sums', out, dout, bias, sums, out.numel() // F, F)
     return sums
 
