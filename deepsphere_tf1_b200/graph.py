@@ -156,16 +156,66 @@ class BlockPlan(object):
         s8 = 8 * np.arange(KS)[:, None]
         frags = np.stack([A[:, g[None, :], s8 + t[None, :]], A[:, g[None, :] + 8, s8 + t[None, :]],
                           A[:, g[None, :], s8 + t[None, :] + 4], A[:, g[None, :] + 8, s8 + t[None, :] + 4]], axis=-1)
-        self.cols = torch.from_numpy(cols.astype(np.int32)).to(device)
-        self.frags = torch.from_numpy(np.ascontiguousarray(frags, dtype=np.float32)).to(device)
+        self.cols_np = cols.astype(np.int32)
+        self.frags_np = np.ascontiguousarray(frags, dtype=np.float32)
+        if device is not None:
+            self.cols = torch.from_numpy(self.cols_np).to(device)
+            self.frags = torch.from_numpy(self.frags_np).to(device)
         self.nblocks, self.KS = nb, KS
         self.valid = True
+
+
+STILE_ROWS = 128           # rows per staged tile (csrc/sparse_stile.cu) = 8 blocks
+STILE_MAX_ROWS = 340       # tile + ring-1 rows that fit shared memory for 4 samples, 2 CTAs per SM
+
+
+class StagedBlockPlan(object):
+    """Plan of the staged-tile + tensor-core-block sparse product (csrc/sparse_stile.cu): the blocks of `BlockPlan`
+    with LOCAL column indices inside their 128-row tile: tile rows 0..nt-1, then the tile's ring-1 halo rows in
+    ascending global order (`ext`)."""
+
+    def __init__(self, col, val, device):
+        self.valid = False
+        bp = BlockPlan(col, val, None)
+        if not bp.valid:
+            return
+        M = col.shape[0]
+        T = (M + STILE_ROWS - 1) // STILE_ROWS
+        cols = bp.cols_np
+        lcols = np.zeros(cols.shape, np.uint16)
+        tinfo = np.zeros((T, 4), np.int32)
+        exts, eoff, n1cap = [], 0, 0
+        bpt = STILE_ROWS // BLOCK_ROWS
+        for t in range(T):
+            r0, r1 = t * STILE_ROWS, min(M, (t + 1) * STILE_ROWS)
+            nt = r1 - r0
+            cb = cols[t * bpt:(t + 1) * bpt].astype(np.int64)
+            u = np.unique(cb)
+            ring = u[(u < r0) | (u >= r1)]
+            n1 = nt + len(ring)
+            if n1 > STILE_MAX_ROWS:
+                return
+            inside = (cb >= r0) & (cb < r1)
+            lcols[t * bpt:(t + 1) * bpt] = np.where(inside, cb - r0, nt + np.searchsorted(ring, cb)).astype(np.uint16)
+            tinfo[t] = (eoff, n1, 0, 0)
+            exts.append(ring.astype(np.int32))
+            eoff += len(ring)
+            n1cap = max(n1cap, n1)
+        self.tinfo = torch.from_numpy(tinfo).to(device)
+        self.ext = torch.from_numpy(np.concatenate(exts + [np.zeros(1, np.int32)])).to(device)
+        self.lcols = torch.from_numpy(lcols.view(np.int16)).to(device)
+        self.frags = torch.from_numpy(bp.frags_np).to(device)
+        self.ntiles, self.nblocks, self.KS, self.n1cap = T, bp.nblocks, bp.KS, n1cap
+        self.valid = True
+
+    def args(self):
+        return (self.tinfo, self.ext, self.lcols, self.frags, self.ntiles, self.nblocks, self.KS, self.n1cap)
 
 
 class DeviceGraph(object):
     """One Laplacian level on the GPU.  `.fwd` / `.bwd` = (rowptr | None, col, val, width)."""
 
-    def __init__(self, L, device, force_csr=False, tiled=False, LT=None, blocks=False):
+    def __init__(self, L, device, force_csr=False, tiled=False, LT=None, blocks=False, staged=False):
         """`LT`: the matrix to use for the transposed products instead of L.T (vertex-sharded mode: the rows of
         L^T this rank owns are not the transpose of the rows of L it owns)."""
         L = sparse.csr_matrix(L, dtype=np.float32)
@@ -184,9 +234,10 @@ class DeviceGraph(object):
             LT.sort_indices()
             self.max_degree = max(self.max_degree, int(np.diff(LT.indptr).max()))
         self.is_ell = (not force_csr) and self.max_degree <= ELL_MAX_WIDTH
-        self._want_tiles, self._want_blocks = tiled, blocks
+        self._want_tiles, self._want_blocks, self._want_staged = tiled, blocks, staged
         self.fwd_tiles = self.bwd_tiles = None
         self.fwd_blocks = self.bwd_blocks = None
+        self.fwd_staged = self.bwd_staged = None
         self.fwd = self._pack(L, 'fwd')
         if LT is None:
             LT = sparse.csr_matrix(L.T)
@@ -197,6 +248,7 @@ class DeviceGraph(object):
             self.bwd = self.fwd
             self.bwd_tiles = self.fwd_tiles
             self.bwd_blocks = self.fwd_blocks
+            self.bwd_staged = self.fwd_staged
         else:
             self.bwd = self._pack(LT, 'bwd')
 
@@ -214,6 +266,9 @@ class DeviceGraph(object):
             if self._want_blocks:
                 bp = BlockPlan(col, val, self.device)
                 setattr(self, which + '_blocks', bp if bp.valid else None)
+            if self._want_staged:
+                sp = StagedBlockPlan(col, val, self.device)
+                setattr(self, which + '_staged', sp if sp.valid else None)
             if self._want_tiles:
                 plan = TilePlan(col, val, self.device)
                 setattr(self, which + '_tiles', plan if plan.valid else None)

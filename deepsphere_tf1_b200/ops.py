@@ -26,8 +26,12 @@ def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, tra
     rowptr, col, val, width = graph.bwd if transpose else graph.fwd
     if out is None:
         out = _new((B, M, F), x)
-    bp = _blocks(graph, 'bwd' if transpose else 'fwd', B, F) if rows is None else None
-    if bp is not None:
+    which = 'bwd' if transpose else 'fwd'
+    sp = _staged(graph, which, B, F) if rows is None else None
+    bp = _blocks(graph, which, B, F) if rows is None and sp is None else None
+    if sp is not None:
+        call('spmm_stile', *sp.args(), B, M, F, x, y, z, out, alpha, beta, gamma)
+    elif bp is not None:
         call('spmm_blk', bp.cols, bp.frags, bp.nblocks, bp.KS, B, M, F, x, y, z, out, alpha, beta, gamma)
     elif rowptr is None:
         call('spmm_ell', col, val, width, B, M, F, x, y, z, out, alpha, beta, gamma)
@@ -39,6 +43,20 @@ def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, tra
 USE_BLOCKS = False        # tensor-core block formulation of the sparse product (csrc/sparse_blk.cu): correct, not yet faster
 BLOCKS_MIN_SAMPLES = 2    # below this the block records are not amortised: gather kernel
 USE_TILED = False         # shared-memory tiled recurrence (two orders per launch) when the graph has a tile plan
+
+
+USE_STAGED = False        # staged row tile + tensor-core blocks (csrc/sparse_stile.cu): correct, on par with the gather kernel at best
+STAGED_MIN_SAMPLES = 2
+
+
+def set_staged(on):
+    global USE_STAGED
+    USE_STAGED = bool(on)
+
+
+def _staged(graph, which, B, F):
+    sp = getattr(graph, which + '_staged', None)
+    return sp if (USE_STAGED and sp is not None and F % 16 == 0 and B >= STAGED_MIN_SAMPLES) else None
 
 
 def set_blocks(on):
@@ -84,7 +102,7 @@ def cheb_basis(graph, x, K):
     if plan is not None:
         call('cheb_basis_tiled', *plan.args(), B, M, F, K, x, basis)
         return basis
-    if _blocks(graph, 'fwd', B, F) is not None:
+    if _blocks(graph, 'fwd', B, F) is not None or _staged(graph, 'fwd', B, F) is not None:
         spmm(graph, x, out=basis[0])                                           # X1 = L X0
         for k in range(2, K):                                                  # Xk = 2 L X(k-1) - X(k-2)
             spmm(graph, basis[k - 2], x if k == 2 else basis[k - 3], None, out=basis[k - 1], alpha=2.0, beta=-1.0)
@@ -102,7 +120,7 @@ def cheb_basis_bwd(graph, G):
         S = _new((K, B, M, F), G)
         call('cheb_basis_bwd_tiled', *plan.args(), B, M, F, K, G, S)
         return S[0]
-    if _blocks(graph, 'bwd', B, F) is not None and K >= 2:
+    if (_blocks(graph, 'bwd', B, F) is not None or _staged(graph, 'bwd', B, F) is not None) and K >= 2:
         # A_(K-1) = G_(K-1);  A_k = G_k + c_k L^T A_(k+1) - A_(k+2), in place on the planes of G (see csrc/sparse.cu)
         for k in range(K - 2, -1, -1):
             a2 = G[k + 2] if k + 2 <= K - 1 else None

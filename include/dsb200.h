@@ -59,6 +59,16 @@ int dsb200_spmm_blk(const int32_t* blk_cols, const float* blk_frags, int nblocks
                     const float* x, const float* y, const float* z, float* out,
                     float alpha, float beta, float gamma, void* stream);
 
+/* staged row tile + tensor-core blocks (csrc/sparse_stile.cu): a CTA stages the x rows of a 128-row tile and of its
+ * ring-1 halo (cp.async) for a group of samples and multiplies the tile's eight 16-row blocks with mma.sync TF32
+ * (3xTF32).  tile_info int32[ntiles][4] = (first entry in tile_ext, rows of tile + halo, 0, 0); tile_ext = global ids
+ * of the halo rows; blk_lcols uint16[nblocks][8*ksteps] = LOCAL column (0..rows-1) of every block column;
+ * blk_frags as in dsb200_spmm_blk.  F % 16 == 0; out must not alias x (it may alias y or z). */
+int dsb200_spmm_stile(const int32_t* tile_info, const int32_t* tile_ext, const uint16_t* blk_lcols, const float* blk_frags,
+                      int ntiles, int nblocks, int ksteps, int n1cap, int B, int M, int F,
+                      const float* x, const float* y, const float* z, float* out,
+                      float alpha, float beta, float gamma, void* stream);
+
 /* ---- K1: one sparse-Laplacian product with fused recurrence arithmetic, for all B samples
  *      out[b] = alpha * L x[b] + beta * y[b] + gamma * z[b]    (y, z NULL when beta/gamma == 0;
  *      out may alias y or z)

@@ -19,9 +19,9 @@ def dev():
     return torch.device('cuda', 0)
 
 
-def _graph(L, dev, force_csr=False, tiled=False, blocks=False):
+def _graph(L, dev, force_csr=False, tiled=False, blocks=False, staged=False):
     from deepsphere_tf1_b200.graph import DeviceGraph
-    return DeviceGraph(L, dev, force_csr=force_csr, tiled=tiled, blocks=blocks)
+    return DeviceGraph(L, dev, force_csr=force_csr, tiled=tiled, blocks=blocks, staged=staged)
 
 
 def _oracle_basis(L, x, K):
@@ -153,10 +153,11 @@ def test_tiled_recurrence_steps(dev, F, graph):
     assert_close(o2, 2 * mul(Ld, mul(Ld, x)) - x.double(), RTOL, 'double step without T1 output')
 
 
+@pytest.mark.parametrize('path', ['blocks', 'staged'])
 @pytest.mark.parametrize('F', [8, 16, 32, 64, 24])
 @pytest.mark.parametrize('B', [2, 5, 16])
 @pytest.mark.parametrize('graph', ['full', 'patch', 'ragged', 'nonsym_values'])
-def test_block_mma_sparse_product(dev, F, B, graph):
+def test_block_mma_sparse_product(dev, F, B, graph, path):
     """Tensor-core block formulation (csrc/sparse_blk.cu, 3xTF32) against dense float64 products: general form with
     y and z, the transposed matrix, in-place accumulation -- within the fp32 bar."""
     from scipy import sparse
@@ -167,9 +168,15 @@ def test_block_mma_sparse_product(dev, F, B, graph):
     if graph == 'nonsym_values':
         L = sparse.csr_matrix(L.multiply(sparse.csr_matrix(1.0 + 0.1 * np.random.RandomState(0).rand(*L.shape))), dtype=np.float32)
     M = L.shape[0]
-    g = _graph(L, dev, blocks=True)
-    ops.set_blocks(True)
-    assert g.fwd_blocks is not None and ops._blocks(g, 'fwd', B, F) is not None
+    if path == 'staged' and F % 16:
+        pytest.skip('the staged kernel takes 16-feature slabs')
+    g = _graph(L, dev, blocks=path == 'blocks', staged=path == 'staged')
+    ops.set_blocks(path == 'blocks')
+    ops.set_staged(path == 'staged')
+    if path == 'blocks':
+        assert g.fwd_blocks is not None and ops._blocks(g, 'fwd', B, F) is not None
+    else:
+        assert g.fwd_staged is not None and g.bwd_staged is not None and ops._staged(g, 'fwd', B, F) is not None
     rs = np.random.RandomState(F + B)
     x, y, z = [torch.from_numpy(rs.randn(B, M, F).astype(np.float32)) for _ in range(3)]
     Ld = torch.from_numpy(L.toarray()).double()
@@ -184,6 +191,7 @@ def test_block_mma_sparse_product(dev, F, B, graph):
     G = torch.from_numpy(rs.randn(K, B, M, F).astype(np.float32)).to(dev)
     basis, dx = ops.cheb_basis(g, x.to(dev), K), ops.cheb_basis_bwd(g, G.clone())
     ops.set_blocks(False)
+    ops.set_staged(False)
     ref = ops.spmm(g, x.to(dev), y.to(dev), z.to(dev), alpha=0.5, beta=-1.5, gamma=0.25)
     assert_close(out, ref, 2e-6, 'block vs gather kernel')
     assert_close(basis, ops.cheb_basis(g, x.to(dev), K), 1e-5, 'basis')

@@ -147,3 +147,23 @@ def test_block_plan_is_the_matrix(case):
             A[:, gq + 8, 8 * s_ + t + 4] = fr[:, s_, :, 3]
         out = np.einsum('bik,bkf->bif', A.astype(np.float64), x[cols]).reshape(-1, 3)[:M]
         np.testing.assert_allclose(out, A_ref.astype(np.float64) @ x, rtol=0, atol=1e-12)
+
+
+def test_staged_block_plan_localises_the_block_columns():
+    """csrc/sparse_stile.cu: per 128-row tile the ring-1 halo list and the block columns as LOCAL indices."""
+    from deepsphere_tf1_b200.graph import STILE_ROWS
+    L = sparse.csr_matrix(healpix_L(16), dtype=np.float32)
+    M = L.shape[0]
+    g = DeviceGraph(L, torch.device('cpu'), blocks=True, staged=True)
+    sp, bp = g.fwd_staged, g.fwd_blocks
+    assert sp is not None and sp.ntiles == (M + STILE_ROWS - 1) // STILE_ROWS and sp.nblocks == bp.nblocks and sp.KS == bp.KS
+    tinfo, ext, lcols = sp.tinfo.numpy(), sp.ext.numpy(), sp.lcols.numpy().view(np.uint16).astype(np.int64)
+    cols = bp.cols.numpy()
+    for t in range(sp.ntiles):
+        eoff, n1 = tinfo[t, 0], tinfo[t, 1]
+        r0 = t * STILE_ROWS
+        nt = min(STILE_ROWS, M - r0)
+        rows = np.concatenate([np.arange(r0, r0 + nt), ext[eoff:eoff + n1 - nt]])       # global row of every local index
+        assert n1 <= sp.n1cap and np.all(np.diff(ext[eoff:eoff + n1 - nt]) > 0)
+        blk = slice(t * 8, min((t + 1) * 8, sp.nblocks))
+        np.testing.assert_array_equal(rows[lcols[blk]], cols[blk])

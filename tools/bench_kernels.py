@@ -57,7 +57,7 @@ def timeit(name, layer, nbytes, fn):
 
 for li in [int(v) for v in args.layers.split(',')]:
     i = li - 1
-    g = DeviceGraph(L[i], dev, tiled=True, blocks=True)
+    g = DeviceGraph(L[i], dev, tiled=True, blocks=True, staged=True)
     M, Fin, Fout, pool = g.M, Fins[i], bench.F[i], p[i]
     R = B * M
     X = 4 * R * Fin
@@ -67,11 +67,16 @@ for li in [int(v) for v in args.layers.split(',')]:
     out = torch.empty_like(x)
     W = torch.randn(Fin * K, Fout, device=dev) * 0.1
     ops.set_blocks(False)
+    ops.set_staged(False)
     timeit('spmm step (k>=2), gather', li, 3 * X + 8 * g.nnz, lambda: ops.spmm(g, x1, x, None, out=out, alpha=2.0, beta=-1.0))
     ops.set_blocks(True)
     if Fin % 8 == 0:
         timeit('spmm step (k>=2), block mma', li, 3 * X + 8 * g.nnz, lambda: ops.spmm(g, x1, x, None, out=out, alpha=2.0, beta=-1.0))
     ops.set_blocks(False)
+    ops.set_staged(True)
+    if Fin % 16 == 0 and g.fwd_staged is not None:
+        timeit('spmm step (k>=2), staged blocks', li, 3 * X + 8 * g.nnz, lambda: ops.spmm(g, x1, x, None, out=out, alpha=2.0, beta=-1.0))
+    ops.set_staged(False)
     xi, x1i, outi = x.view(1, M, B * Fin), x1.view(1, M, B * Fin), out.view(1, M, B * Fin)
     timeit('spmm step, interleaved', li, 3 * X + 8 * g.nnz, lambda: ops.spmm(g, x1i, xi, None, out=outi, alpha=2.0, beta=-1.0))
     if g.fwd_tiles is not None and Fin % 4 == 0:

@@ -6,8 +6,10 @@ from deepsphere_tf1_b200 import ops
 from deepsphere_tf1_b200.graph import DeviceGraph
 dev = torch.device('cuda', 0)
 L, p = bench.build_laplacians()
-g = DeviceGraph(L[1], dev, blocks=True)
-ops.set_blocks(True)
+import sys as _s
+g = DeviceGraph(L[1], dev, blocks='--blocks' in _s.argv, staged='--blocks' not in _s.argv)
+ops.set_blocks('--blocks' in _s.argv)
+ops.set_staged('--blocks' not in _s.argv)
 B, M, Fin = 16, g.M, 16
 x1, x0 = torch.randn(B, M, Fin, device=dev), torch.randn(B, M, Fin, device=dev)
 out = torch.empty_like(x1)
