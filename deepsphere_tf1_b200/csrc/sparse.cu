@@ -229,6 +229,83 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const float* v
     DSB_LAUNCH_CHECK();
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Whole recurrence of a SMALL level in one launch.  At the coarsest levels (M <= 341 vertices) a sample's 16-feature slab of
+// one order is at most 21 KB: a CTA keeps X_(k-1), X_(k-2) and X_k of (sample, slab) in shared memory and runs all K - 1
+// steps with a barrier in between -- K - 1 launches of a few microseconds each, all latency, become one.
+//   FWD : X_1 = L X_0,  X_k = 2 L X_(k-1) - X_(k-2)                       -> basis planes
+//   BWD : A_(K-1) = G_(K-1),  A_k = G_k + c_k L^T A_(k+1) - A_(k+2)      -> A_0 written over G_0   (c_k = 2, c_0 = 1)
+template <int W, bool BWD>
+__global__ void __launch_bounds__(256)
+cheb_small_kernel(const int32_t* __restrict__ col, const float* __restrict__ val, int M, int chunks, int K,
+                  const float4* x0, float4* planes, long long plane_stride)
+{
+    extern __shared__ float4 sp[];                              // [3][M][4]
+    const int slab = blockIdx.x, b = blockIdx.y;
+    const long long base = (long long)b * M * chunks + slab * 4;
+    const int nitems = M * 4;
+    float4* buf[3] = {sp, sp + (size_t)M * 4, sp + (size_t)2 * M * 4};
+    // plane index helpers: FWD order k = 0 is x0, k >= 1 is planes[k-1]; BWD order k is planes[k] (= G_k)
+    auto gptr = [&](int k) -> float4* { return BWD ? planes + (long long)k * plane_stride : (k == 0 ? const_cast<float4*>(x0) : planes + (long long)(k - 1) * plane_stride); };
+    {
+        const float4* src = gptr(BWD ? K - 1 : 0) + base;
+        for (int i = threadIdx.x; i < nitems; i += 256) buf[0][i] = src[(long long)(i >> 2) * chunks + (i & 3)];
+    }
+    __syncthreads();
+    int cur = 0;                                                // buf[cur] = newest order, buf[prev] = the one before
+    int prev = 2;
+    const int steps = K - 1;
+    for (int st = 0; st < steps; ++st) {
+        const int k = BWD ? K - 2 - st : st + 1;                // order produced by this step
+        const int nxt = 3 - cur - prev;
+        const float alpha = BWD ? (k >= 1 ? 2.f : 1.f) : (k == 1 ? 1.f : 2.f);
+        const bool has_prev = st > 0;                           // X_(k-2) / A_(k+2) exists
+        float4* dstg = gptr(BWD ? (k == 0 ? 0 : -1) : k);       // BWD stores only A_0
+        const float4* addg = BWD ? gptr(k) + base : nullptr;    // G_k
+        for (int i = threadIdx.x; i < nitems; i += 256) {
+            const int r = i >> 2, c = i & 3;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                const int cj = __ldg(col + r * W + j);
+                const float w = __ldg(val + r * W + j);
+                const float4 v = buf[cur][cj * 4 + c];
+                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+            }
+            float4 res = make_float4(alpha * acc.x, alpha * acc.y, alpha * acc.z, alpha * acc.w);
+            if (has_prev) { const float4 p2 = buf[prev][i]; res.x -= p2.x; res.y -= p2.y; res.z -= p2.z; res.w -= p2.w; }
+            if (BWD) { const float4 gk = addg[(long long)r * chunks + c]; res.x += gk.x; res.y += gk.y; res.z += gk.z; res.w += gk.w; }
+            buf[nxt][i] = res;
+            if (!BWD || k == 0) (dstg + base)[(long long)r * chunks + c] = res;
+        }
+        __syncthreads();
+        prev = cur;
+        cur = nxt;
+    }
+}
+
+// returns 1 if the level does not qualify
+static int cheb_small_launch(const int32_t* col, const float* val, int width, int B, int M, int F, int K, const float* x0, float* planes,
+                             bool bwd, cudaStream_t s)
+{
+    if (getenv("DSB200_NO_SMALL") || K < 2 || F % 16 || (width != 9 && width != 7)) return 1;
+    const size_t smem = (size_t)3 * M * 64;
+    if (smem > 64 * 1024 || M < 16) return 1;           // measured: wins at M = 256 (18.6 vs 25.9 us), loses at M = 1024 (59 vs 34 us: 64 CTAs only)
+    if ((((uintptr_t)x0 | (uintptr_t)planes) & 15) != 0) return 1;
+    const long long plane = (long long)B * M * (F / 4);
+    dim3 grid(F / 16, B);
+#define DSB_SMALL(WW, BB) do { \
+        static bool cfg = false; \
+        if (!cfg) { cudaError_t e = cudaFuncSetAttribute(cheb_small_kernel<WW, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+                    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; } cfg = true; } \
+        cheb_small_kernel<WW, BB><<<grid, 256, smem, s>>>(col, val, M, F / 4, K, (const float4*)x0, (float4*)planes, plane); } while (0)
+    if (width == 9) { if (bwd) DSB_SMALL(9, true); else DSB_SMALL(9, false); }
+    else { if (bwd) DSB_SMALL(7, true); else DSB_SMALL(7, false); }
+#undef DSB_SMALL
+    DSB_LAUNCH_CHECK();
+}
+
 }  // namespace dsb200
 
 using namespace dsb200;
@@ -260,6 +337,7 @@ extern "C" int dsb200_cheb_basis(const int32_t* rowptr, const int32_t* col, cons
     DSB_REQUIRE(basis, "cheb_basis: null basis");
     const long long plane = (long long)B * M * F;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!rowptr) { const int rs = cheb_small_launch(col, val, width, B, M, F, K, x0, basis, false, s); if (rs != 1) return rs; }
     // X1 = L X0
     int rc = spmm_launch(rowptr, col, val, width, B, M, F, x0, nullptr, nullptr, basis, 1.f, 0.f, 0.f, s);
     // Xk = 2 L X(k-1) - X(k-2)
@@ -282,6 +360,7 @@ extern "C" int dsb200_cheb_basis_bwd(const int32_t* rowptrT, const int32_t* colT
     if (K == 1) return 0;
     const long long plane = (long long)B * M * F;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!rowptrT) { const int rs = cheb_small_launch(colT, valT, width, B, M, F, K, nullptr, G, true, s); if (rs != 1) return rs; }
     int rc = 0;
     for (int k = K - 2; k >= 1 && rc == 0; --k) {
         float* gk = G + (long long)k * plane;
