@@ -272,6 +272,16 @@ int dsb200_scale(float* x, float a, long long n, void* stream);               /*
  * caller-supplied uniform [0,1) tensor; the same call applied to dout is the backward. */
 int dsb200_dropout(const float* x, const float* u, float keep, float* out, long long n, void* stream);
 
+/* ---- one-shot all-reduce of small double vectors over NVLink peer memory (csrc/peer_allreduce.cu; new -- replaces the
+ * NCCL launches of the SyncBN sums inside the data-parallel / vertex-sharded step).  Every rank creates one
+ * communication buffer and exports its IPC handle (64 bytes); the handles are exchanged by the host (torch.distributed
+ * all_gather) and opened on every peer.  HOST pointers: comm_out, handle, comms (array of `world` device pointers as
+ * mapped in this process, own buffer at index `rank`). */
+long long dsb200_peer_comm_bytes(void);
+int dsb200_peer_comm_create(void** comm_out, void* handle_out64);
+int dsb200_peer_comm_open(const void* handle64, void** comm_out);
+int dsb200_peer_allreduce_f64(void* const* comms, int rank, int world, double* data, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

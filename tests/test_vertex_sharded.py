@@ -107,3 +107,17 @@ def test_sharded_model_matches_single_device_model():
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-4000:]
     assert 'SHARDED PARITY OK' in r.stdout, r.stdout[-4000:]
+
+
+@pytest.mark.gpu
+def test_peer_memory_allreduce_matches_nccl():
+    """csrc/peer_allreduce.cu: eager calls and CUDA-graph replays against NCCL (tests/peer_worker.py under torchrun)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs at least 2 GPUs (gpurun --gpus 2)')
+    n = 4 if torch.cuda.device_count() >= 4 else 2
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n),
+           '--master-addr', '127.0.0.1', '--master-port', str(29900 + os.getpid() % 90),
+           os.path.join(ROOT, 'tests', 'peer_worker.py')]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-4000:]
+    assert 'PEER ALLREDUCE OK' in r.stdout, r.stdout[-4000:]
