@@ -231,6 +231,275 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const float* v
 
 
 // ------------------------------------------------------------------------------------------------------------------
+// Packed ELL: rec[j][m] = (col, val bits) of slot j of row m as ONE 8-byte record, slot-major ("transposed").  The
+// rows a warp works on are consecutive, so slot j of all of them is one contiguous 8*rpw-byte piece: ONE L1 wavefront
+// per slot and warp instead of the ~3 + ~3 of the row-major col[] / val[] arrays (rows 36 bytes apart).  At the 64- and
+// 128-byte feature rows of the cosmo layers the (col, val) loads were half of all L1 wavefronts of the gather kernel
+// (profiles/r01_spmm_rows_layer2_full.txt: L1/TEX 74 % busy, DRAM 38 %).
+__global__ void ell_pack_kernel(const int32_t* __restrict__ col, const float* __restrict__ val, int width, int M, int2* rec)
+{
+    const long long n = (long long)width * M;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i / M), m = (int)(i - (long long)j * M);
+        rec[i] = make_int2(col[(long long)m * width + j], __float_as_int(val[(long long)m * width + j]));
+    }
+}
+
+// Same tiling as spmm_rows_kernel (TR consecutive rows x column slab, LG lanes per row).  SB > 1: a tile spans SB
+// samples and a thread keeps the W records of its row in registers across them (W > 0 only).
+template <int PASSES, int W, int SB>
+__global__ void __launch_bounds__(256)
+spmm_rec_kernel(const int2* __restrict__ rec, int width, int B, int M, int chunks, int lg2, int TR, int CB,
+                const float4* __restrict__ x, const float4* y, const float4* z, float4* out,
+                float alpha, float beta, float gamma)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int LG = 1 << lg2, rpw = 32 >> lg2;
+    const int sub = lane >> lg2, lg = lane & (LG - 1);
+    const int rtiles = (M + TR - 1) / TR, ctiles = (chunks + CB - 1) / CB;
+    const int bgroups = (B + SB - 1) / SB;
+    const long long tiles = (long long)bgroups * rtiles * ctiles;
+    const int plane = M * chunks;                                  // float4 per sample (host checks it fits in 31 bits)
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int ct = (int)(t % ctiles);
+        const long long t2 = t / ctiles;
+        const int rt = (int)(t2 % rtiles), bg = (int)(t2 / rtiles);
+        const int coff = ct * CB + lg;
+        const int mend = min(M, (rt + 1) * TR);
+        bool on[PASSES];
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) on[p] = (coff + p * LG < chunks) && (lg + p * LG < CB);
+        for (int m = rt * TR + warp * rpw + sub; m < mend; m += 8 * rpw) {
+            if (W > 0) {
+                int c[W > 0 ? W : 1];
+                float wv[W > 0 ? W : 1];
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    const int2 r = __ldg(rec + (long long)j * M + m);
+                    c[j] = r.x * chunks + coff;
+                    wv[j] = __int_as_float(r.y);
+                }
+#pragma unroll
+                for (int s = 0; s < SB; ++s) {
+                    const int b = bg * SB + s;
+                    if (SB > 1 && b >= B) break;
+                    const float4* xb = x + (long long)b * plane;
+                    float4 v[W > 0 ? W : 1][PASSES];
+#pragma unroll
+                    for (int j = 0; j < W; ++j) {
+#pragma unroll
+                        for (int p = 0; p < PASSES; ++p)
+                            v[j][p] = on[p] ? __ldg(xb + c[j] + p * LG) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int p = 0; p < PASSES; ++p) {
+                        if (!on[p]) continue;
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int j = 0; j < W; ++j) {
+                            a.x = fmaf(wv[j], v[j][p].x, a.x); a.y = fmaf(wv[j], v[j][p].y, a.y);
+                            a.z = fmaf(wv[j], v[j][p].z, a.z); a.w = fmaf(wv[j], v[j][p].w, a.w);
+                        }
+                        const long long o = (long long)b * plane + m * chunks + coff + p * LG;
+                        float4 r = make_float4(a.x * alpha, a.y * alpha, a.z * alpha, a.w * alpha);
+                        if (y) { const float4 t4 = y[o]; r.x = fmaf(beta, t4.x, r.x); r.y = fmaf(beta, t4.y, r.y); r.z = fmaf(beta, t4.z, r.z); r.w = fmaf(beta, t4.w, r.w); }
+                        if (z) { const float4 t4 = z[o]; r.x = fmaf(gamma, t4.x, r.x); r.y = fmaf(gamma, t4.y, r.y); r.z = fmaf(gamma, t4.z, r.z); r.w = fmaf(gamma, t4.w, r.w); }
+                        out[o] = r;
+                    }
+                }
+            } else {
+                const float4* xb = x + (long long)bg * plane + coff;
+                float4 acc[PASSES];
+#pragma unroll
+                for (int p = 0; p < PASSES; ++p) acc[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                for (int j = 0; j < width; ++j) {
+                    const int2 r = __ldg(rec + (long long)j * M + m);
+                    const float wj = __int_as_float(r.y);
+                    const float4* xr = xb + r.x * chunks;
+#pragma unroll
+                    for (int p = 0; p < PASSES; ++p) {
+                        if (on[p]) {
+                            const float4 v = __ldg(xr + p * LG);
+                            acc[p].x = fmaf(wj, v.x, acc[p].x); acc[p].y = fmaf(wj, v.y, acc[p].y);
+                            acc[p].z = fmaf(wj, v.z, acc[p].z); acc[p].w = fmaf(wj, v.w, acc[p].w);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < PASSES; ++p) {
+                    if (on[p]) {
+                        const long long o = (long long)bg * plane + m * chunks + coff + p * LG;
+                        float4 r = make_float4(acc[p].x * alpha, acc[p].y * alpha, acc[p].z * alpha, acc[p].w * alpha);
+                        if (y) { const float4 t4 = y[o]; r.x = fmaf(beta, t4.x, r.x); r.y = fmaf(beta, t4.y, r.y); r.z = fmaf(beta, t4.z, r.z); r.w = fmaf(beta, t4.w, r.w); }
+                        if (z) { const float4 t4 = z[o]; r.x = fmaf(gamma, t4.x, r.x); r.y = fmaf(gamma, t4.y, r.y); r.z = fmaf(gamma, t4.z, r.z); r.w = fmaf(gamma, t4.w, r.w); }
+                        out[o] = r;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int2 ldg_nc_v2(const int2* p) {
+    int2 r; asm volatile("ld.global.nc.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p)); return r;
+}
+__device__ __forceinline__ float4 ldg_nc_v4(const float4* p) {
+    float4 r; asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p)); return r;
+}
+
+// Variant with explicit memory-level parallelism (whole feature row per lane group, LG = F/4 lanes, F = 4..128 a power of
+// two; ELL width W = 7 / 9).  The compiler schedules spmm_rows / spmm_rec for 32 registers, which leaves TWO gathers in
+// flight per thread and chains record load -> gather -> record load ...: several memory round trips per row.  Here
+//   MODE 0: the W records come straight from global memory, all W loads issued first, then all W gathers (volatile asm
+//           keeps the order), then y / z;
+//   MODE 1: the records of the row tile are staged in shared memory once per CTA tile (coalesced), re-used for SB samples;
+//           all W gathers in flight, the weights are re-read from shared memory at FMA time (registers = the W gathers);
+//   MODE 2: as MODE 1 but compiler-scheduled loads.
+// NB = CTAs per SM the register budget is set for.
+template <int W, int MODE, int NB>
+__global__ void __launch_bounds__(256, NB)
+spmm_mlp_kernel(const int2* __restrict__ rec, int B, int M, int lg2, int TR, int SB,
+                const float4* __restrict__ x, const float4* y, const float4* z, float4* out,
+                float alpha, float beta, float gamma)
+{
+    extern __shared__ int2 srec[];                                // MODE >= 1: [W][TR]
+    const int chunks = 1 << lg2;
+    const int rpp = 256 >> lg2;                                   // rows per pass
+    const int rl = threadIdx.x >> lg2, lg = threadIdx.x & (chunks - 1);
+    const int rtiles = (M + TR - 1) / TR, bgroups = (B + SB - 1) / SB;
+    const int plane = M << lg2;
+    for (int t = blockIdx.x; t < rtiles * bgroups; t += gridDim.x) {
+        const int rt = t % rtiles, bg = t / rtiles;
+        const int m0 = rt * TR, mend = min(M, m0 + TR);
+        if (MODE >= 1) {
+            __syncthreads();                                      // previous tile's readers are done
+            for (int i = threadIdx.x; i < W * TR; i += 256) {
+                const int j = i / TR, r = i - j * TR;
+                if (m0 + r < M) srec[i] = __ldg(rec + (long long)j * M + m0 + r);
+            }
+            __syncthreads();
+        }
+        for (int s = 0; s < SB; ++s) {
+            const int b = bg * SB + s;
+            if (b >= B) break;
+            const float4* xb = x + (long long)b * plane + lg;
+            for (int r = rl; m0 + r < mend; r += rpp) {
+                const int m = m0 + r;
+                const long long o = (long long)b * plane + (m << lg2) + lg;
+                float4 v[W];
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MODE == 0) {
+                    int2 rc[W];
+#pragma unroll
+                    for (int j = 0; j < W; ++j) rc[j] = ldg_nc_v2(rec + (long long)j * M + m);
+#pragma unroll
+                    for (int j = 0; j < W; ++j) v[j] = ldg_nc_v4(xb + (rc[j].x << lg2));
+#pragma unroll
+                    for (int j = 0; j < W; ++j) {
+                        const float w = __int_as_float(rc[j].y);
+                        a.x = fmaf(w, v[j].x, a.x); a.y = fmaf(w, v[j].y, a.y); a.z = fmaf(w, v[j].z, a.z); a.w = fmaf(w, v[j].w, a.w);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < W; ++j) {
+                        const int c = srec[j * TR + r].x;
+                        v[j] = (MODE == 1) ? ldg_nc_v4(xb + (c << lg2)) : __ldg(xb + (c << lg2));
+                    }
+#pragma unroll
+                    for (int j = 0; j < W; ++j) {
+                        const float w = __int_as_float(srec[j * TR + r].y);
+                        a.x = fmaf(w, v[j].x, a.x); a.y = fmaf(w, v[j].y, a.y); a.z = fmaf(w, v[j].z, a.z); a.w = fmaf(w, v[j].w, a.w);
+                    }
+                }
+                float4 res = make_float4(a.x * alpha, a.y * alpha, a.z * alpha, a.w * alpha);
+                if (y) { const float4 t4 = y[o]; res.x = fmaf(beta, t4.x, res.x); res.y = fmaf(beta, t4.y, res.y); res.z = fmaf(beta, t4.z, res.z); res.w = fmaf(beta, t4.w, res.w); }
+                if (z) { const float4 t4 = z[o]; res.x = fmaf(gamma, t4.x, res.x); res.y = fmaf(gamma, t4.y, res.y); res.z = fmaf(gamma, t4.z, res.z); res.w = fmaf(gamma, t4.w, res.w); }
+                out[o] = res;
+            }
+        }
+    }
+}
+
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+constexpr int kNotQualified = -1000;
+// returns kNotQualified when the shape does not qualify (caller falls back to the row-major kernels)
+static int spmm_rec_launch(const int2* rec, int width, int B, int M, int F, const float* x, const float* y, const float* z,
+                           float* out, float alpha, float beta, float gamma, cudaStream_t s)
+{
+    if (beta == 0.f) y = nullptr;
+    if (gamma == 0.f) z = nullptr;
+    const uintptr_t align = (uintptr_t)x | (uintptr_t)out | (uintptr_t)y | (uintptr_t)z;
+    if (F % 4 || (align & 15) || (long long)M * (F / 4) >= (1LL << 31)) return kNotQualified;
+    DSB_REQUIRE(x != out, "spmm: out must not alias x");
+    const int chunks = F / 4;
+    const int variant = env_int("DSB200_SPMM_VARIANT", 0);
+    if (variant > 0 && (width == 9 || width == 7) && chunks <= 32 && (chunks & (chunks - 1)) == 0) {
+        int l2 = 0;
+        while ((1 << l2) < chunks) ++l2;
+        int TR = env_int("DSB200_SPMM_TR", 128); if (TR < 16) TR = 128;
+        int SB = env_int("DSB200_SPMM_SB", 1); if (SB < 1) SB = 1;
+        while (SB > 1 && (long long)((B + SB - 1) / SB) * ((M + TR - 1) / TR) < 4LL * kNumSMs) SB >>= 1;
+        while (TR > 16 && (long long)((B + SB - 1) / SB) * ((M + TR - 1) / TR) < 4LL * kNumSMs) TR >>= 1;
+        const long long tiles = (long long)((B + SB - 1) / SB) * ((M + TR - 1) / TR);
+        const int mode = variant / 10, nb = variant % 10;
+        const long long cap = (long long)kNumSMs * nb;
+        const int grid = (int)(tiles < cap ? tiles : cap);
+        const size_t smem = mode >= 1 ? (size_t)width * TR * sizeof(int2) : 0;
+#define DSB_MLP(WW, MM, NN) spmm_mlp_kernel<WW, MM, NN><<<grid, 256, smem, s>>>(rec, B, M, l2, TR, SB, \
+            (const float4*)x, (const float4*)y, (const float4*)z, (float4*)out, alpha, beta, gamma)
+#define DSB_MLP_W(MM, NN) do { if (width == 9) DSB_MLP(9, MM, NN); else DSB_MLP(7, MM, NN); } while (0)
+        switch (variant) {
+            case 3: DSB_MLP_W(0, 3); break;
+            case 4: DSB_MLP_W(0, 4); break;
+            case 14: DSB_MLP_W(1, 4); break;
+            case 15: DSB_MLP_W(1, 5); break;
+            case 16: DSB_MLP_W(1, 6); break;
+            case 28: DSB_MLP_W(2, 8); break;
+            default: DSB_REQUIRE(false, "spmm: unknown DSB200_SPMM_VARIANT");
+        }
+#undef DSB_MLP_W
+#undef DSB_MLP
+        DSB_LAUNCH_CHECK();
+    }
+    int CB = chunks < 64 ? chunks : 64;
+    int lg2 = 0;
+    while ((1 << lg2) < CB && lg2 < 5) ++lg2;
+    const int passes = (CB + (1 << lg2) - 1) >> lg2;
+    int TR = 32768 / (CB * 16);
+    TR = TR < 32 ? 32 : TR > 128 ? 128 : TR;
+    { const int v = env_int("DSB200_SPMM_TR", 0); if (v > 0) TR = v; }
+    int SB = (width == 9 || width == 7) && passes == 1 ? env_int("DSB200_SPMM_SB", 1) : 1;
+    if (SB != 2 && SB != 4) SB = 1;
+    while (SB > 1 && (long long)((B + SB - 1) / SB) * ((M + TR - 1) / TR) * ((chunks + CB - 1) / CB) < 8LL * kNumSMs) SB >>= 1;
+    const int bgroups = (B + SB - 1) / SB;
+    while (TR > 16 && (long long)bgroups * ((M + TR - 1) / TR) * ((chunks + CB - 1) / CB) < 8LL * kNumSMs) TR >>= 1;
+    const long long tiles = (long long)bgroups * ((M + TR - 1) / TR) * ((chunks + CB - 1) / CB);
+    const long long cap = (long long)kNumSMs * 8;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+#define DSB_REC(PP, WW, SS) spmm_rec_kernel<PP, WW, SS><<<grid, 256, 0, s>>>(rec, width, B, M, chunks, lg2, TR, CB, \
+            (const float4*)x, (const float4*)y, (const float4*)z, (float4*)out, alpha, beta, gamma)
+    if (passes > 1) DSB_REC(2, 0, 1);                            // wide rows (F > 128): the unrolled form needs 128 registers
+    else if (width == 9) { if (SB == 4) DSB_REC(1, 9, 4); else if (SB == 2) DSB_REC(1, 9, 2); else DSB_REC(1, 9, 1); }
+    else if (width == 7) { if (SB == 4) DSB_REC(1, 7, 4); else if (SB == 2) DSB_REC(1, 7, 2); else DSB_REC(1, 7, 1); }
+    else DSB_REC(1, 0, 1);
+#undef DSB_REC
+    DSB_LAUNCH_CHECK();
+}
+
+// one product through the packed records when they are given and the shape qualifies, else the row-major kernels
+static int spmm_any(const int2* rec, const int32_t* rowptr, const int32_t* col, const float* val, int width, int B, int M, int F,
+                    const float* x, const float* y, const float* z, float* out, float alpha, float beta, float gamma, cudaStream_t s)
+{
+    if (rec && !rowptr) {
+        const int rc = spmm_rec_launch(rec, width, B, M, F, x, y, z, out, alpha, beta, gamma, s);
+        if (rc != kNotQualified) return rc;
+    }
+    return spmm_launch(rowptr, col, val, width, B, M, F, x, y, z, out, alpha, beta, gamma, s);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // Whole recurrence of a SMALL level in one launch.  At the coarsest levels (M <= 341 vertices) a sample's 16-feature slab of
 // one order is at most 21 KB: a CTA keeps X_(k-1), X_(k-2) and X_k of (sample, slab) in shared memory and runs all K - 1
 // steps with a barrier in between -- K - 1 launches of a few microseconds each, all latency, become one.
@@ -329,23 +598,22 @@ extern "C" int dsb200_spmm_csr(const int32_t* rowptr, const int32_t* col, const 
     return spmm_launch(rowptr, col, val, 0, B, M, F, x, y, z, out, alpha, beta, gamma, (cudaStream_t)stream);
 }
 
-extern "C" int dsb200_cheb_basis(const int32_t* rowptr, const int32_t* col, const float* val, int width,
-                                 int B, int M, int F, int K, const float* x0, float* basis, void* stream)
+static int cheb_basis_impl(const int2* rec, const int32_t* rowptr, const int32_t* col, const float* val, int width,
+                           int B, int M, int F, int K, const float* x0, float* basis, cudaStream_t s)
 {
     DSB_REQUIRE(K >= 1, "cheb_basis: K must be >= 1");
     if (K == 1) return 0;
     DSB_REQUIRE(basis, "cheb_basis: null basis");
     const long long plane = (long long)B * M * F;
-    cudaStream_t s = (cudaStream_t)stream;
     if (!rowptr) { const int rs = cheb_small_launch(col, val, width, B, M, F, K, x0, basis, false, s); if (rs != 1) return rs; }
     // X1 = L X0
-    int rc = spmm_launch(rowptr, col, val, width, B, M, F, x0, nullptr, nullptr, basis, 1.f, 0.f, 0.f, s);
+    int rc = spmm_any(rec, rowptr, col, val, width, B, M, F, x0, nullptr, nullptr, basis, 1.f, 0.f, 0.f, s);
     // Xk = 2 L X(k-1) - X(k-2)
     for (int k = 2; k < K && rc == 0; ++k) {
         const float* xm1 = basis + (long long)(k - 2) * plane;
         const float* xm2 = (k == 2) ? x0 : basis + (long long)(k - 3) * plane;
-        rc = spmm_launch(rowptr, col, val, width, B, M, F, xm1, xm2, nullptr, basis + (long long)(k - 1) * plane,
-                         2.f, -1.f, 0.f, s);
+        rc = spmm_any(rec, rowptr, col, val, width, B, M, F, xm1, xm2, nullptr, basis + (long long)(k - 1) * plane,
+                      2.f, -1.f, 0.f, s);
     }
     return rc;
 }
@@ -353,22 +621,63 @@ extern "C" int dsb200_cheb_basis(const int32_t* rowptr, const int32_t* col, cons
 // Adjoint of X1 = L X0, Xk = 2 L X(k-1) - X(k-2):  with A_k = dLoss/dX_k (total),
 //   A_(K-1) = G_(K-1);  A_k = G_k + 2 L^T A_(k+1) - A_(k+2)  (1 <= k <= K-2);
 //   A_0 = G_0 + L^T A_1 - A_2.
-extern "C" int dsb200_cheb_basis_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int width,
-                                     int B, int M, int F, int K, float* G, void* stream)
+static int cheb_basis_bwd_impl(const int2* recT, const int32_t* rowptrT, const int32_t* colT, const float* valT, int width,
+                               int B, int M, int F, int K, float* G, cudaStream_t s)
 {
     DSB_REQUIRE(K >= 1 && G, "cheb_basis_bwd: bad arguments");
     if (K == 1) return 0;
     const long long plane = (long long)B * M * F;
-    cudaStream_t s = (cudaStream_t)stream;
     if (!rowptrT) { const int rs = cheb_small_launch(colT, valT, width, B, M, F, K, nullptr, G, true, s); if (rs != 1) return rs; }
     int rc = 0;
     for (int k = K - 2; k >= 1 && rc == 0; --k) {
         float* gk = G + (long long)k * plane;
         const float* a1 = G + (long long)(k + 1) * plane;
         const float* a2 = (k + 2 <= K - 1) ? G + (long long)(k + 2) * plane : nullptr;
-        rc = spmm_launch(rowptrT, colT, valT, width, B, M, F, a1, gk, a2, gk, 2.f, 1.f, a2 ? -1.f : 0.f, s);
+        rc = spmm_any(recT, rowptrT, colT, valT, width, B, M, F, a1, gk, a2, gk, 2.f, 1.f, a2 ? -1.f : 0.f, s);
     }
     if (rc) return rc;
     const float* a2 = (K > 2) ? G + 2 * plane : nullptr;
-    return spmm_launch(rowptrT, colT, valT, width, B, M, F, G + plane, G, a2, G, 1.f, 1.f, a2 ? -1.f : 0.f, s);
+    return spmm_any(recT, rowptrT, colT, valT, width, B, M, F, G + plane, G, a2, G, 1.f, 1.f, a2 ? -1.f : 0.f, s);
+}
+
+extern "C" int dsb200_cheb_basis(const int32_t* rowptr, const int32_t* col, const float* val, int width,
+                                 int B, int M, int F, int K, const float* x0, float* basis, void* stream)
+{
+    return cheb_basis_impl(nullptr, rowptr, col, val, width, B, M, F, K, x0, basis, (cudaStream_t)stream);
+}
+
+extern "C" int dsb200_cheb_basis_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int width,
+                                     int B, int M, int F, int K, float* G, void* stream)
+{
+    return cheb_basis_bwd_impl(nullptr, rowptrT, colT, valT, width, B, M, F, K, G, (cudaStream_t)stream);
+}
+
+extern "C" int dsb200_ell_pack(const int32_t* col, const float* val, int width, int M, void* rec, void* stream)
+{
+    DSB_REQUIRE(col && val && rec && width > 0 && M > 0, "ell_pack: bad arguments");
+    ell_pack_kernel<<<grid_for((long long)width * M, 256, 8), 256, 0, (cudaStream_t)stream>>>(col, val, width, M, (int2*)rec);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_spmm_ellp(const void* rec, const int32_t* col, const float* val, int width, int B, int M, int F,
+                                const float* x, const float* y, const float* z, float* out,
+                                float alpha, float beta, float gamma, void* stream)
+{
+    DSB_REQUIRE(B > 0 && M > 0 && F > 0, "spmm: empty matrix");
+    DSB_REQUIRE(rec && col && val && x && out && width > 0, "spmm_ellp: bad arguments");
+    return spmm_any((const int2*)rec, nullptr, col, val, width, B, M, F, x, y, z, out, alpha, beta, gamma, (cudaStream_t)stream);
+}
+
+extern "C" int dsb200_cheb_basis_ellp(const void* rec, const int32_t* col, const float* val, int width,
+                                      int B, int M, int F, int K, const float* x0, float* basis, void* stream)
+{
+    DSB_REQUIRE(rec && col && val, "cheb_basis_ellp: bad arguments");
+    return cheb_basis_impl((const int2*)rec, nullptr, col, val, width, B, M, F, K, x0, basis, (cudaStream_t)stream);
+}
+
+extern "C" int dsb200_cheb_basis_bwd_ellp(const void* recT, const int32_t* colT, const float* valT, int width,
+                                          int B, int M, int F, int K, float* G, void* stream)
+{
+    DSB_REQUIRE(recT && colT && valT, "cheb_basis_bwd_ellp: bad arguments");
+    return cheb_basis_bwd_impl((const int2*)recT, nullptr, colT, valT, width, B, M, F, K, G, (cudaStream_t)stream);
 }

@@ -1,0 +1,239 @@
+// K1, bulk-asynchronous pipelined form:  out[b] = alpha * L x[b] + beta * y[b] + gamma * z[b]  on [B, M, F] tensors.
+// Same operator and call sites as dsb200_spmm_ell (reference deepsphere/models.py:1056-1061 and its autodiff).
+//
+// Why: the gather kernels (sparse.cu) are bound by dependent-load chains -- record -> neighbour row -> y, several memory
+// round trips per row with too few DRAM bytes in flight per SM (tools/exp_spmm_limits.py: 52 us at cosmo layer 2 even
+// when every gather hits L1, vs 38 us for a plain 3-stream kernel of the same size).  Here the COMPULSORY traffic is
+// decoupled from the arithmetic, as in a GEMM pipeline:
+//   * a work item = (row tile of TR consecutive rows, sample); the x rows of the tile, and the y / z rows, are contiguous
+//     in memory: one cp.async.bulk (TMA, 1-D) each into a shared-memory stage, completion on an mbarrier;
+//   * the tile's halo (rows referenced from outside the tile; host-built list, graph.py: PipePlan) follows with 16-byte
+//     cp.async -- about a third of a tile in HEALPix nested (Morton) order;
+//   * the tile's packed records (LOCAL column, value), 8 W TR bytes, are one more bulk copy per item (L2 hits: the B
+//     samples of a row tile are consecutive items);
+//   * S stages per CTA, filled by a dedicated producer warp; 2 CTAs per SM;
+//   * the 8 consumer warps read ONLY shared memory: W gathers of 16 bytes per lane from the staged rows, y / z from their stages, one
+//     coalesced 16-byte store per lane.  Arithmetic order identical to the gather kernels (bit-identical results).
+// F in {16, 32, 64} (NCH = 4, 8, 16 chunks per row), ELL width 7 / 9; other shapes keep the gather kernels.
+#include "common.cuh"
+#include <stdlib.h>
+
+namespace dsb200 {
+
+struct PipeArgs {
+    const int2* rec;        // [T][W][TR]  (local column, value bits); local column < TR: tile row, else TR + halo slot
+    const int32_t* ext;     // [T][HC]     global row of every halo slot (unused slots: the tile's first row)
+    const int32_t* nh;      // [T]         halo rows of the tile
+    const float4 *x, *y, *z;
+    float4* out;
+    int T, TR, HC, B, M, S;
+    int order;              // 0: CTA = contiguous item range, samples of a row tile consecutive; 1: contiguous range in memory
+                            // order (row tiles of a sample consecutive); 2: grid-strided in memory order
+    int ablate;             // timing experiments only (tools/exp_pipe_ablate.py): skip parts of the work
+    float alpha, beta, gamma;
+};
+
+__device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(saddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n .reg .pred p;\n W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra D;\n bra W;\n D:\n}"
+                 :: "r"(saddr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(saddr(dst)), "l"(src), "r"(bytes), "r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void cp16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+constexpr int kConsumerWarps = 8;
+constexpr int kHaloPerLane = 12;                                 // halo chunks per producer lane: HC * NCH <= 384
+constexpr int kPipeThreads = (kConsumerWarps + 1) * 32;          // + one producer warp
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(saddr(bar)) : "memory");
+}
+// the mbarrier receives one arrival when all cp.async issued so far by this thread have landed (counted at init: .noinc)
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(saddr(bar)) : "memory");
+}
+
+// Warp-specialised: warp 8 is the producer (it alone waits on global-memory latency: tile lists, bulk copies, halo
+// copies), warps 0..7 consume -- each owns TR/8 rows of every item and synchronises with nobody but the producer
+// (full[s] / empty[s] mbarriers), so the warps drift apart and hide each other's shared-memory latency.
+template <int W, int NCH, bool HASY, bool HASZ>
+__global__ void __launch_bounds__(kPipeThreads, 2)
+spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int TR = a.TR, HC = a.HC, S = a.S;
+    const uint32_t xbytes = (uint32_t)(TR + HC) * NCH * 16, tbytes = (uint32_t)TR * NCH * 16;
+    const uint32_t rbytes = (uint32_t)W * TR * 8;
+    const uint32_t ybase = xbytes, zbase = ybase + (HASY ? tbytes : 0), rbase = zbase + (HASZ ? tbytes : 0);
+    const uint32_t sbytes = rbase + rbytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * sbytes);
+    uint64_t* empty = full + S;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NBULK = 2 + (HASY ? 1 : 0) + (HASZ ? 1 : 0);
+
+    const long long nitems = (long long)a.T * a.B;
+    const long long c0 = nitems * blockIdx.x / gridDim.x, c1 = nitems * (blockIdx.x + 1) / gridDim.x;
+    const long long i0 = a.order == 2 ? blockIdx.x : c0, istep = a.order == 2 ? gridDim.x : 1;
+    const int n = a.order == 2 ? (int)((nitems - blockIdx.x + gridDim.x - 1) / gridDim.x) : (int)(c1 - c0);
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(full + s, 32 + NBULK); mbar_init(empty + s, kConsumerWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer ----------------
+        for (int it = 0; it < n; ++it) {
+            const int s = it % S, k = it / S;
+            const long long item = i0 + it * istep;
+            int rt, b;
+            if (a.order == 0) { rt = (int)(item / a.B); b = (int)(item - (long long)rt * a.B); }
+            else { b = (int)(item / a.T); rt = (int)(item - (long long)b * a.T); }
+            const int r0 = rt * TR, nt = min(TR, a.M - r0);
+            const int nhalo = (a.ablate & 2) ? 0 : __ldg(a.nh + rt) * NCH;
+            const int32_t* ext = a.ext + (long long)rt * HC;
+            int gr[kHaloPerLane];                                                 // halo chunks of this lane
+#pragma unroll
+            for (int q = 0; q < kHaloPerLane; ++q) { const int idx = lane + q * 32; gr[q] = idx < nhalo ? __ldg(ext + idx / NCH) : 0; }
+            if (k > 0) mbar_wait(empty + s, (uint32_t)(k - 1) & 1u);
+            unsigned char* st = smem + (size_t)s * sbytes;
+            const long long g0 = ((long long)b * a.M + r0) * NCH;                 // first chunk of the tile in the sample
+            const uint32_t nb = (uint32_t)nt * NCH * 16;
+            if (lane < NBULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (lane == 0) { mbar_expect_tx(full + s, nb); bulk_g2s(st, a.x + g0, nb, full + s); }
+            if (lane == 1) { mbar_expect_tx(full + s, rbytes); bulk_g2s(st + rbase, a.rec + (long long)rt * W * TR, rbytes, full + s); }
+            if (HASY && lane == 2) { mbar_expect_tx(full + s, nb); bulk_g2s(st + ybase, a.y + g0, nb, full + s); }
+            if (HASZ && lane == (HASY ? 3 : 2)) { mbar_expect_tx(full + s, nb); bulk_g2s(st + zbase, a.z + g0, nb, full + s); }
+            float4* xh = reinterpret_cast<float4*>(st) + TR * NCH;
+            const float4* xb = a.x + (long long)b * a.M * NCH;
+#pragma unroll
+            for (int q = 0; q < kHaloPerLane; ++q) {
+                const int idx = lane + q * 32;
+                if (idx < nhalo) cp16(xh + idx, xb + (long long)gr[q] * NCH + (idx % NCH));
+            }
+            cp_async_arrive(full + s);
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    constexpr int RPP = 32 / NCH;                                             // rows per warp pass
+    const int rpw = TR / kConsumerWarps;                                      // rows per warp (host: TR % (8 * RPP) == 0)
+    const int sub = lane / NCH, lg = lane - sub * NCH;
+    for (int it = 0; it < n; ++it) {
+        const int s = it % S, k = it / S;
+        const long long item = i0 + it * istep;
+        int rt, b;
+        if (a.order == 0) { rt = (int)(item / a.B); b = (int)(item - (long long)rt * a.B); }
+        else { b = (int)(item / a.T); rt = (int)(item - (long long)b * a.T); }
+        const int r0 = rt * TR, nt = min(TR, a.M - r0);
+        const unsigned char* st = smem + (size_t)s * sbytes;
+        const float4* xs = reinterpret_cast<const float4*>(st);
+        const float4* ys = reinterpret_cast<const float4*>(st + ybase);
+        const float4* zs = reinterpret_cast<const float4*>(st + zbase);
+        const int2* srec = reinterpret_cast<const int2*>(st + rbase);
+        float4* ob = a.out + ((long long)b * a.M + r0) * NCH;
+        mbar_wait(full + s, (uint32_t)k & 1u);
+        const int rend = min(nt, (warp + 1) * rpw);
+        for (int r = warp * rpw + sub; r < rend; r += RPP) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                if ((a.ablate & 1) && j > 0) break;
+                const int2 rc = srec[j * TR + r];
+                const float w = __int_as_float(rc.y);
+                const float4 v = xs[rc.x * NCH + lg];
+                acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+            }
+            float4 res = make_float4(acc.x * a.alpha, acc.y * a.alpha, acc.z * a.alpha, acc.w * a.alpha);
+            if (HASY) { const float4 t = ys[r * NCH + lg]; res.x = fmaf(a.beta, t.x, res.x); res.y = fmaf(a.beta, t.y, res.y); res.z = fmaf(a.beta, t.z, res.z); res.w = fmaf(a.beta, t.w, res.w); }
+            if (HASZ) { const float4 t = zs[r * NCH + lg]; res.x = fmaf(a.gamma, t.x, res.x); res.y = fmaf(a.gamma, t.y, res.y); res.z = fmaf(a.gamma, t.z, res.z); res.w = fmaf(a.gamma, t.w, res.w); }
+            if (!(a.ablate & 8)) ob[r * NCH + lg] = res;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+}
+
+static size_t pipe_smem(int W, int TR, int HC, int nch, int extra, int S) {
+    const size_t stage = (size_t)(TR + HC) * nch * 16 + (size_t)TR * nch * 16 * extra + (size_t)W * TR * 8;
+    return (size_t)S * stage + 2 * S * 8 + 64;
+}
+
+template <int W, int NCH>
+static int pipe_launch_t(const PipeArgs& a, int grid, size_t smem, cudaStream_t s)
+{
+#define DSB_PIPE(YY, ZZ) do { \
+        static bool cfg = false; \
+        if (!cfg) { cudaError_t e = cudaFuncSetAttribute(spmm_pipe_kernel<W, NCH, YY, ZZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024); \
+                    if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; } cfg = true; } \
+        spmm_pipe_kernel<W, NCH, YY, ZZ><<<grid, kPipeThreads, smem, s>>>(a); } while (0)
+    if (a.y && a.z) DSB_PIPE(true, true);
+    else if (a.y) DSB_PIPE(true, false);
+    else if (a.z) DSB_PIPE(false, true);
+    else DSB_PIPE(false, false);
+#undef DSB_PIPE
+    DSB_LAUNCH_CHECK();
+}
+
+}  // namespace dsb200
+
+using namespace dsb200;
+
+extern "C" int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, const int32_t* tile_nh,
+                                int ntiles, int TR, int HC, int width, int B, int M, int F,
+                                const float* x, const float* y, const float* z, float* out,
+                                float alpha, float beta, float gamma, void* stream)
+{
+    DSB_REQUIRE(B > 0 && M > 0 && F > 0, "spmm_pipe: empty matrix");
+    DSB_REQUIRE(tile_recs && tile_ext && tile_nh && x && out, "spmm_pipe: null pointer");
+    DSB_REQUIRE(x != out, "spmm_pipe: out must not alias x");
+    DSB_REQUIRE(width == 9 || width == 7, "spmm_pipe: ELL width must be 7 or 9");
+    DSB_REQUIRE(F == 16 || F == 32 || F == 64, "spmm_pipe: F must be 16, 32 or 64");
+    DSB_REQUIRE(TR > 0 && HC >= 0 && ntiles == (M + TR - 1) / TR, "spmm_pipe: tile plan does not match M");
+    DSB_REQUIRE(TR % (8 * (128 / F)) == 0 && HC * (F / 4) <= 32 * kHaloPerLane && (width * TR * 8) % 16 == 0, "spmm_pipe: unsupported tile shape");
+    if (beta == 0.f) y = nullptr;
+    if (gamma == 0.f) z = nullptr;
+    const uintptr_t align = (uintptr_t)x | (uintptr_t)out | (uintptr_t)y | (uintptr_t)z;
+    DSB_REQUIRE((align & 15) == 0, "spmm_pipe: pointers must be 16-byte aligned");
+    const int nch = F / 4, extra = (y ? 1 : 0) + (z ? 1 : 0);
+    int S = 4;
+    { const char* e = getenv("DSB200_PIPE_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= 4) S = atoi(e); }
+    while (S > 2 && pipe_smem(width, TR, HC, nch, extra, S) > 113 * 1024) --S;
+    const size_t smem = pipe_smem(width, TR, HC, nch, extra, S);
+    DSB_REQUIRE(smem <= 113 * 1024, "spmm_pipe: tile does not fit in shared memory");
+    PipeArgs a;
+    a.rec = (const int2*)tile_recs; a.ext = tile_ext; a.nh = tile_nh;
+    a.x = (const float4*)x; a.y = (const float4*)y; a.z = (const float4*)z; a.out = (float4*)out;
+    a.T = ntiles; a.TR = TR; a.HC = HC; a.B = B; a.M = M; a.S = S;
+    a.alpha = alpha; a.beta = beta; a.gamma = gamma;
+    { const char* e = getenv("DSB200_PIPE_ABLATE"); a.ablate = e ? atoi(e) : 0; }
+    { const char* e = getenv("DSB200_PIPE_ORDER"); a.order = e ? atoi(e) : 0; }
+    int ctas = 2;
+    { const char* e = getenv("DSB200_PIPE_CTAS"); if (e && atoi(e) == 1) ctas = 1; }
+    const long long nitems = (long long)ntiles * B;
+    const long long cap = (long long)ctas * kNumSMs;
+    const int grid = (int)(nitems < cap ? nitems : cap);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (width == 9) {
+        if (nch == 4) return pipe_launch_t<9, 4>(a, grid, smem, s);
+        if (nch == 8) return pipe_launch_t<9, 8>(a, grid, smem, s);
+        return pipe_launch_t<9, 16>(a, grid, smem, s);
+    }
+    if (nch == 4) return pipe_launch_t<7, 4>(a, grid, smem, s);
+    if (nch == 8) return pipe_launch_t<7, 8>(a, grid, smem, s);
+    return pipe_launch_t<7, 16>(a, grid, smem, s);
+}

@@ -6,6 +6,8 @@ fixed-width ELL (HEALPix 8-neighbour / icosahedral graphs: <= 9 / 7 entries per 
 (irregular kNN graphs), together with the same packing of L^T for the backward pass (L is
 symmetric only up to 1 ulp because of `D12 * W * D12`, reference utils.py:240).
 """
+import os
+
 import numpy as np
 import torch
 from scipy import sparse
@@ -103,6 +105,69 @@ class TilePlan(object):
 
     def args(self):
         return (self.info, self.recs, self.ext, self.ntiles, self.TR, self.n1cap, self.n2cap, self.width)
+
+
+PIPE_TILE_BYTES = 8192     # x bytes of one row tile of the pipelined kernel (csrc/sparse_pipe.cu): TR = 8192 / (4 F) rows
+PIPE_SMEM = 113 * 1024
+
+
+class PipePlan(object):
+    """Row tiles + ring-1 halo lists for the bulk-asynchronous pipelined sparse product (csrc/sparse_pipe.cu).
+
+    Tile t owns the consecutive rows [t*TR, (t+1)*TR).  LOCAL column of an entry: col - t*TR if the column lies in
+    the tile, else TR + (rank of the column among the tile's distinct outside columns, ascending).
+      rec int32[T, W, TR, 2] = (local column, value bits), slot-major per tile (padding rows / slots: (row, 0))
+      ext int32[T, HC]        = global row of every halo slot (unused slots: the tile's first row)
+      nh  int32[T]            = halo rows of the tile
+    Built from the ELL packing itself, so it works for any graph whose vertex order has locality; `valid` is False
+    when the halos are too large for shared memory (random vertex order): the gather kernels stay in charge."""
+
+    def __init__(self, col, val, device, TR):
+        M, W = col.shape
+        self.valid = False
+        if M == 0 or W not in (7, 9) or TR < 8:
+            return
+        T = (M + TR - 1) // TR
+        tile = (np.arange(M, dtype=np.int64) // TR)
+        c64 = col.astype(np.int64)
+        outside = (c64 // TR) != tile[:, None]
+        ri, si = np.nonzero(outside)
+        keys = tile[ri] * M + c64[ri, si]
+        uk, inv = np.unique(keys, return_inverse=True)
+        ut, ug = uk // M, uk % M
+        counts = np.bincount(ut, minlength=T).astype(np.int64)
+        HC = int(counts.max()) if len(uk) else 0
+        HC = max(8, (HC + 7) // 8 * 8)
+        if HC > 2 * TR:
+            return
+        start = np.cumsum(counts) - counts
+        rank = np.arange(len(uk), dtype=np.int64) - start[ut]
+        lcol = c64 - tile[:, None] * TR
+        lcol[ri, si] = TR + rank[inv]
+        ext = np.repeat((np.arange(T, dtype=np.int32) * TR)[:, None], HC, axis=1)
+        ext[ut, rank] = ug.astype(np.int32)
+        Mp = T * TR
+        rec = np.zeros((Mp, W, 2), dtype=np.int32)
+        rec[:, :, 0] = (np.arange(Mp) % TR)[:, None]                     # padding rows point at themselves
+        rec[:M, :, 0] = lcol
+        rec[:M, :, 1] = val.view(np.int32)
+        rec = np.ascontiguousarray(rec.reshape(T, TR, W, 2).transpose(0, 2, 1, 3))
+        self.rec_np, self.ext_np, self.nh_np = rec, ext, counts.astype(np.int32)
+        self.T, self.TR, self.HC, self.width, self.M = T, TR, HC, W, M
+        if device is not None:
+            self.rec = torch.from_numpy(rec).to(device)
+            self.ext = torch.from_numpy(np.ascontiguousarray(ext)).to(device)
+            self.nh = torch.from_numpy(self.nh_np).to(device)
+        self.valid = True
+
+    def fits(self, F, extra=2):
+        """Two stages of (x tile + halo, `extra` more tiles, records) fit in the CTA's shared memory, and the tile
+        shape is one the kernel's warp layout covers."""
+        stage = (self.TR + self.HC) * 4 * F + self.TR * 4 * F * extra + self.width * self.TR * 8
+        return (2 * stage + 128 <= PIPE_SMEM and self.TR % (8 * (128 // F)) == 0 and self.HC * (F // 4) <= 384)
+
+    def args(self):
+        return (self.rec, self.ext, self.nh, self.T, self.TR, self.HC, self.width)
 
 
 BLOCK_ROWS = 16            # rows per block of the tensor-core product (csrc/sparse_blk.cu): the M of mma.m16n8k8
@@ -238,6 +303,7 @@ class DeviceGraph(object):
         self.fwd_tiles = self.bwd_tiles = None
         self.fwd_blocks = self.bwd_blocks = None
         self.fwd_staged = self.bwd_staged = None
+        self.fwd_rec = self.bwd_rec = None
         self.fwd = self._pack(L, 'fwd')
         if LT is None:
             LT = sparse.csr_matrix(L.T)
@@ -246,6 +312,7 @@ class DeviceGraph(object):
                                   and np.array_equal(LT.indices, L.indices))
         if self.symmetric_pattern and np.array_equal(LT.data, L.data):
             self.bwd = self.fwd
+            self.bwd_rec = self.fwd_rec
             self.bwd_tiles = self.fwd_tiles
             self.bwd_blocks = self.fwd_blocks
             self.bwd_staged = self.fwd_staged
@@ -272,10 +339,32 @@ class DeviceGraph(object):
             if self._want_tiles:
                 plan = TilePlan(col, val, self.device)
                 setattr(self, which + '_tiles', plan if plan.valid else None)
+            # packed slot-major records rec[j, m] = (col, val bits): one contiguous piece per slot for the consecutive
+            # rows of a warp (csrc/sparse.cu: spmm_rec_kernel); same bits as dsb200_ell_pack produces on the device
+            rec = np.empty((width, self.M, 2), dtype=np.int32)
+            rec[:, :, 0] = col.T
+            rec[:, :, 1] = val.view(np.int32).T
+            setattr(self, which + '_rec', torch.from_numpy(rec).to(self.device))
             return (None, torch.from_numpy(col).to(self.device), torch.from_numpy(val).to(self.device), width)
         return (torch.from_numpy(A.indptr.astype(np.int32)).to(self.device),
                 torch.from_numpy(A.indices.astype(np.int32)).to(self.device),
                 torch.from_numpy(A.data.astype(np.float32)).to(self.device), 0)
+
+    def pipe_plan(self, which, F):
+        """PipePlan of L ('fwd') or L^T ('bwd') for F features per row (cached per tile size), or None."""
+        if not self.is_ell or F not in (16, 32, 64):
+            return None
+        TR = int(os.environ.get('DSB200_PIPE_TILE_BYTES', PIPE_TILE_BYTES)) // (4 * F)
+        if which == 'bwd' and self.bwd is self.fwd:
+            which = 'fwd'
+        key = (which, TR)
+        cache = self.__dict__.setdefault('_pipe_plans', {})
+        if key not in cache:
+            _, col, val, width = getattr(self, which)
+            plan = PipePlan(col.cpu().numpy(), val.cpu().numpy(), self.device, TR)
+            cache[key] = plan if plan.valid else None
+        plan = cache[key]
+        return plan if plan is not None and plan.fits(F) else None
 
     def bytes_stored(self):
         """Bytes one sparse product reads for the matrix (8 per stored entry)."""

@@ -27,17 +27,54 @@ def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, tra
     if out is None:
         out = _new((B, M, F), x)
     which = 'bwd' if transpose else 'fwd'
-    sp = _staged(graph, which, B, F) if rows is None else None
-    bp = _blocks(graph, which, B, F) if rows is None and sp is None else None
-    if sp is not None:
+    pp = _pipe(graph, which, B, M, F) if rows is None else None
+    sp = _staged(graph, which, B, F) if rows is None and pp is None else None
+    bp = _blocks(graph, which, B, F) if rows is None and sp is None and pp is None else None
+    if pp is not None:
+        call('spmm_pipe', *pp.args(), B, M, F, x, y, z, out, alpha, beta, gamma)
+    elif sp is not None:
         call('spmm_stile', *sp.args(), B, M, F, x, y, z, out, alpha, beta, gamma)
     elif bp is not None:
         call('spmm_blk', bp.cols, bp.frags, bp.nblocks, bp.KS, B, M, F, x, y, z, out, alpha, beta, gamma)
     elif rowptr is None:
-        call('spmm_ell', col, val, width, B, M, F, x, y, z, out, alpha, beta, gamma)
+        rec = _rec(graph, which) if rows is None else None         # the record stride is the graph's M
+        if rec is not None:
+            call('spmm_ellp', rec, col, val, width, B, M, F, x, y, z, out, alpha, beta, gamma)
+        else:
+            call('spmm_ell', col, val, width, B, M, F, x, y, z, out, alpha, beta, gamma)
     else:
         call('spmm_csr', rowptr, col, val, B, M, F, x, y, z, out, alpha, beta, gamma)
     return out
+
+
+USE_PIPE = True           # bulk-asynchronous pipelined sparse product (csrc/sparse_pipe.cu) where a tile plan exists
+PIPE_MIN_ITEMS = 4 * 296  # (row tiles x samples) below which the pipeline has nothing to overlap: gather kernels
+
+
+def set_pipe(on):
+    global USE_PIPE
+    USE_PIPE = bool(on)
+
+
+def _pipe(graph, which, B, M, F):
+    if not USE_PIPE or not hasattr(graph, 'pipe_plan'):
+        return None
+    plan = graph.pipe_plan(which, F)
+    if plan is None or plan.T * B < PIPE_MIN_ITEMS:
+        return None
+    return plan
+
+
+USE_RECORDS = True        # packed slot-major ELL records (csrc/sparse.cu: spmm_rec_kernel) instead of row-major col[] / val[]
+
+
+def set_records(on):
+    global USE_RECORDS
+    USE_RECORDS = bool(on)
+
+
+def _rec(graph, which):
+    return getattr(graph, which + '_rec', None) if USE_RECORDS else None
 
 
 USE_BLOCKS = False        # tensor-core block formulation of the sparse product (csrc/sparse_blk.cu): correct, not yet faster
@@ -102,13 +139,18 @@ def cheb_basis(graph, x, K):
     if plan is not None:
         call('cheb_basis_tiled', *plan.args(), B, M, F, K, x, basis)
         return basis
-    if _blocks(graph, 'fwd', B, F) is not None or _staged(graph, 'fwd', B, F) is not None:
+    if (_pipe(graph, 'fwd', B, M, F) is not None or _blocks(graph, 'fwd', B, F) is not None
+            or _staged(graph, 'fwd', B, F) is not None):
         spmm(graph, x, out=basis[0])                                           # X1 = L X0
         for k in range(2, K):                                                  # Xk = 2 L X(k-1) - X(k-2)
             spmm(graph, basis[k - 2], x if k == 2 else basis[k - 3], None, out=basis[k - 1], alpha=2.0, beta=-1.0)
         return basis
     rowptr, col, val, width = graph.fwd
-    call('cheb_basis', rowptr, col, val, width, B, M, F, K, x, basis)
+    rec = _rec(graph, 'fwd')
+    if rowptr is None and rec is not None:
+        call('cheb_basis_ellp', rec, col, val, width, B, M, F, K, x, basis)
+    else:
+        call('cheb_basis', rowptr, col, val, width, B, M, F, K, x, basis)
     return basis
 
 
@@ -120,7 +162,8 @@ def cheb_basis_bwd(graph, G):
         S = _new((K, B, M, F), G)
         call('cheb_basis_bwd_tiled', *plan.args(), B, M, F, K, G, S)
         return S[0]
-    if (_blocks(graph, 'bwd', B, F) is not None or _staged(graph, 'bwd', B, F) is not None) and K >= 2:
+    if (_pipe(graph, 'bwd', B, M, F) is not None or _blocks(graph, 'bwd', B, F) is not None
+            or _staged(graph, 'bwd', B, F) is not None) and K >= 2:
         # A_(K-1) = G_(K-1);  A_k = G_k + c_k L^T A_(k+1) - A_(k+2), in place on the planes of G (see csrc/sparse.cu)
         for k in range(K - 2, -1, -1):
             a2 = G[k + 2] if k + 2 <= K - 1 else None
@@ -128,7 +171,11 @@ def cheb_basis_bwd(graph, G):
                  gamma=-1.0 if a2 is not None else 0.0, transpose=True)
         return G[0]
     rowptr, col, val, width = graph.bwd
-    call('cheb_basis_bwd', rowptr, col, val, width, B, M, F, K, G)
+    rec = _rec(graph, 'bwd')
+    if rowptr is None and rec is not None:
+        call('cheb_basis_bwd_ellp', rec, col, val, width, B, M, F, K, G)
+    else:
+        call('cheb_basis_bwd', rowptr, col, val, width, B, M, F, K, G)
     return G[0]
 
 

@@ -91,6 +91,33 @@ int dsb200_cheb_basis(const int32_t* rowptr, const int32_t* col, const float* va
 int dsb200_cheb_basis_bwd(const int32_t* rowptrT, const int32_t* colT, const float* valT, int width,
                           int B, int M, int F, int K, float* G, void* stream);
 
+/* ---- K1 with PACKED ELL records (the default path of the host code).  rec int2[width][M]: rec[j*M + m] = (col, bit
+ * pattern of val) of slot j of row m -- slot-major, so the rows a warp works on read ONE contiguous piece per slot
+ * (one L1 wavefront instead of ~6 with the row-major col[] / val[] arrays).  dsb200_ell_pack builds it on the device
+ * from the row-major arrays; the *_ellp entry points take both (the row-major arrays serve the shapes the record
+ * kernel does not cover: F % 4 != 0, unaligned pointers, the one-launch recurrence of the coarsest levels).
+ * Same operators and call sites as dsb200_spmm_ell / dsb200_cheb_basis / dsb200_cheb_basis_bwd (models.py:1049-1061). */
+int dsb200_ell_pack(const int32_t* col, const float* val, int width, int M, void* rec, void* stream);
+int dsb200_spmm_ellp(const void* rec, const int32_t* col, const float* val, int width, int B, int M, int F,
+                     const float* x, const float* y, const float* z, float* out,
+                     float alpha, float beta, float gamma, void* stream);
+int dsb200_cheb_basis_ellp(const void* rec, const int32_t* col, const float* val, int width,
+                           int B, int M, int F, int K, const float* x0, float* basis, void* stream);
+int dsb200_cheb_basis_bwd_ellp(const void* recT, const int32_t* colT, const float* valT, int width,
+                               int B, int M, int F, int K, float* G, void* stream);
+
+/* ---- K1, bulk-asynchronous pipelined (csrc/sparse_pipe.cu; the default for F in {16, 32, 64}, ELL width 7 / 9, when the
+ * graph has a tile plan).  Same operator as dsb200_spmm_ell (models.py:1056-1061).  A work item = (row tile of TR
+ * consecutive rows, sample): the x / y / z rows of the tile arrive by cp.async.bulk (TMA) on an mbarrier, the halo rows by
+ * 16-byte cp.async, several items in flight per CTA; the arithmetic reads shared memory only.
+ * tile_recs int2[ntiles][width][TR] = (LOCAL column, value bits): local column < TR = row of the tile, else TR + halo slot;
+ * tile_ext int32[ntiles][HC] = global row of every halo slot; tile_nh int32[ntiles] = halo rows per tile
+ * (graph.py: PipePlan).  out must not alias x (it may alias y or z); pointers 16-byte aligned. */
+int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, const int32_t* tile_nh,
+                     int ntiles, int TR, int HC, int width, int B, int M, int F,
+                     const float* x, const float* y, const float* z, float* out,
+                     float alpha, float beta, float gamma, void* stream);
+
 /* ---- K1, shared-memory tiled: one or two recurrence steps per launch (csrc/sparse_tiled.cu)
  *      T1 = a1 * L x  + b1 * y + c1 * z  -> out1 (may be NULL in a two-step launch)
  *      T2 = a2 * L T1 + b2 * x + c2 * u  -> out2 (NULL: single step)

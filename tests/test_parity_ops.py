@@ -71,6 +71,86 @@ def test_spmm_general_form_and_aliasing(dev):
     assert oops is not None
 
 
+@pytest.mark.parametrize('sb', [1, 2, 4])
+@pytest.mark.parametrize('F', [4, 16, 32, 64, 132, 260])
+@pytest.mark.parametrize('graph', ['healpix', 'knn', 'nonsym'])
+def test_packed_record_spmm_is_bit_identical_to_row_major(dev, F, graph, sb, monkeypatch):
+    """Packed slot-major ELL records (spmm_rec_kernel, the default path) vs the row-major col[] / val[] kernel: same
+    products in the same order, so the results are bit-identical; dsb200_ell_pack reproduces the host packing."""
+    from deepsphere_tf1_b200 import ops
+    from deepsphere_tf1_b200._lib import call
+    L = {'healpix': lambda: healpix_L(16), 'knn': lambda: random_knn_L(700, 6), 'nonsym': lambda: random_L(1500, 9)}[graph]()
+    g = _graph(L, dev)
+    assert g.is_ell and g.fwd_rec is not None
+    if graph == 'healpix':
+        assert g.fwd[3] == 9
+    _, col, val, width = g.fwd
+    rec = torch.empty_like(g.fwd_rec)
+    call('ell_pack', col, val, width, g.M, rec)
+    assert torch.equal(rec, g.fwd_rec)
+    monkeypatch.setenv('DSB200_SPMM_SB', str(sb))
+    B, K = 5, 4
+    rs = np.random.RandomState(F + sb)
+    x, y, z = [torch.from_numpy(rs.randn(B, g.M, F).astype(np.float32)).to(dev) for _ in range(3)]
+    G = torch.from_numpy(rs.randn(K, B, g.M, F).astype(np.float32)).to(dev)
+    try:
+        ops.set_records(True)
+        out = ops.spmm(g, x, y, z, alpha=0.5, beta=-1.5, gamma=0.25)
+        outT = ops.spmm(g, x, y.clone(), None, alpha=2.0, beta=1.0, transpose=True)
+        basis = ops.cheb_basis(g, x, K)
+        dx = ops.cheb_basis_bwd(g, G.clone())
+        ops.set_records(False)
+        assert torch.equal(out, ops.spmm(g, x, y, z, alpha=0.5, beta=-1.5, gamma=0.25))
+        assert torch.equal(outT, ops.spmm(g, x, y.clone(), None, alpha=2.0, beta=1.0, transpose=True))
+        assert torch.equal(basis, ops.cheb_basis(g, x, K))
+        assert torch.equal(dx, ops.cheb_basis_bwd(g, G.clone()))
+    finally:
+        ops.set_records(True)
+    assert_close(basis, _oracle_basis(L, x.cpu(), K)[1:], RTOL, 'basis vs oracle')
+
+
+@pytest.mark.parametrize('F', [16, 32, 64])
+@pytest.mark.parametrize('B', [1, 5, 16])
+@pytest.mark.parametrize('graph', ['healpix16', 'patch64', 'ragged'])
+def test_pipelined_spmm_is_bit_identical_to_the_gather_kernel(dev, F, B, graph, monkeypatch):
+    """Bulk-asynchronous pipelined sparse product (csrc/sparse_pipe.cu, the default where a tile plan exists) vs the
+    gather kernel: identical arithmetic order, so identical bits -- general form, in-place adjoint form, whole recurrence
+    and its adjoint; and both within the fp32 bar of the oracle."""
+    from scipy import sparse
+    from deepsphere_tf1_b200 import ops
+    L = {'healpix16': lambda: healpix_L(16), 'patch64': lambda: healpix_L(64, order=2),
+         'ragged': lambda: sparse.coo_matrix(sparse.csr_matrix(healpix_L(16))[:3001, :3001])}[graph]()
+    g = _graph(L, dev)
+    monkeypatch.setattr(ops, 'PIPE_MIN_ITEMS', 1)
+    if F == 64:
+        assert ops._pipe(g, 'fwd', B, g.M, F) is None          # halo of a 32-row tile too large: gather kernel (still checked below)
+    else:
+        assert ops._pipe(g, 'fwd', B, g.M, F) is not None
+    K = 4
+    rs = np.random.RandomState(F + B)
+    x, y, z = [torch.from_numpy(rs.randn(B, g.M, F).astype(np.float32)).to(dev) for _ in range(3)]
+    G = torch.from_numpy(rs.randn(K, B, g.M, F).astype(np.float32)).to(dev)
+    try:
+        ops.set_pipe(True)
+        out = ops.spmm(g, x, y, z, alpha=0.5, beta=-1.5, gamma=0.25)
+        out1 = ops.spmm(g, x)
+        yt = y.clone()
+        ops.spmm(g, x, yt, z, out=yt, alpha=2.0, beta=1.0, gamma=-1.0, transpose=True)
+        basis = ops.cheb_basis(g, x, K)
+        dx = ops.cheb_basis_bwd(g, G.clone())
+        ops.set_pipe(False)
+        assert torch.equal(out, ops.spmm(g, x, y, z, alpha=0.5, beta=-1.5, gamma=0.25))
+        assert torch.equal(out1, ops.spmm(g, x))
+        yr = y.clone()
+        ops.spmm(g, x, yr, z, out=yr, alpha=2.0, beta=1.0, gamma=-1.0, transpose=True)
+        assert torch.equal(yt, yr)
+        assert torch.equal(basis, ops.cheb_basis(g, x, K))
+        assert torch.equal(dx, ops.cheb_basis_bwd(g, G.clone()))
+    finally:
+        ops.set_pipe(True)
+    assert_close(basis, _oracle_basis(L, x.cpu(), K)[1:], RTOL, 'basis vs oracle')
+
+
 @pytest.mark.parametrize('tensor_cores', [True, False])
 @pytest.mark.parametrize('shape', [(2, 192, 1, 16, 5), (2, 192, 16, 32, 5), (3, 100, 6, 16, 4), (1, 77, 3, 5, 3),
                                    (2, 64, 64, 64, 5), (2, 48, 32, 2, 5), (4, 33, 7, 9, 1), (2, 50, 96, 40, 4),

@@ -167,3 +167,41 @@ def test_staged_block_plan_localises_the_block_columns():
         assert n1 <= sp.n1cap and np.all(np.diff(ext[eoff:eoff + n1 - nt]) > 0)
         blk = slice(t * 8, min((t + 1) * 8, sp.nblocks))
         np.testing.assert_array_equal(rows[lcols[blk]], cols[blk])
+
+
+@pytest.mark.parametrize('TR', [32, 64, 128])
+@pytest.mark.parametrize('graph', ['healpix_full', 'healpix_patch', 'ragged'])
+def test_pipe_plan_local_gather_equals_the_global_product(graph, TR):
+    """PipePlan (csrc/sparse_pipe.cu): emulate the kernel's staging on the CPU -- tile rows followed by the halo rows of
+    `ext` -- and check that the local-column records reproduce L x exactly (same products, same order)."""
+    from scipy import sparse
+    from deepsphere_tf1_b200.graph import DeviceGraph, PipePlan
+    from helpers import healpix_L
+    L = {'healpix_full': lambda: healpix_L(8), 'healpix_patch': lambda: healpix_L(32, order=2),
+         'ragged': lambda: sparse.coo_matrix(sparse.csr_matrix(healpix_L(8))[:700, :700])}[graph]()
+    g = DeviceGraph(L, 'cpu')
+    _, col, val, width = g.fwd
+    col, val = col.numpy(), val.numpy()
+    plan = PipePlan(col, val, None, TR)
+    assert plan.valid and plan.width == width and plan.T == (g.M + TR - 1) // TR
+    rs = np.random.RandomState(TR)
+    x = rs.randn(g.M, 4).astype(np.float32)
+    ref = np.zeros_like(x)
+    for j in range(width):
+        ref = ref + val[:, j:j + 1] * x[col[:, j]]
+    out = np.zeros_like(x)
+    for t in range(plan.T):
+        r0, nt = t * TR, min(TR, g.M - t * TR)
+        nh = int(plan.nh_np[t])
+        assert nh <= plan.HC
+        stage = np.zeros((TR + plan.HC, 4), np.float32)
+        stage[:nt] = x[r0:r0 + nt]
+        stage[TR:TR + nh] = x[plan.ext_np[t, :nh]]
+        assert np.all((plan.ext_np[t, :nh] < r0) | (plan.ext_np[t, :nh] >= r0 + nt))
+        acc = np.zeros((nt, 4), np.float32)
+        for j in range(width):
+            lc = plan.rec_np[t, j, :nt, 0]
+            assert lc.max() < TR + max(nh, 1) and lc.min() >= 0
+            acc = acc + plan.rec_np[t, j, :nt, 1].view(np.float32)[:, None] * stage[lc]
+        out[r0:r0 + nt] = acc
+    assert np.array_equal(out, ref)
