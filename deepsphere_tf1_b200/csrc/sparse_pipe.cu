@@ -1,19 +1,26 @@
 // K1, bulk-asynchronous pipelined form:  out[b] = alpha * L x[b] + beta * y[b] + gamma * z[b]  on [B, M, F] tensors.
 // Same operator and call sites as dsb200_spmm_ell (reference deepsphere/models.py:1056-1061 and its autodiff).
 //
-// Why: the gather kernels (sparse.cu) are bound by dependent-load chains -- record -> neighbour row -> y, several memory
-// round trips per row with too few DRAM bytes in flight per SM (tools/exp_spmm_limits.py: 52 us at cosmo layer 2 even
-// when every gather hits L1, vs 38 us for a plain 3-stream kernel of the same size).  Here the COMPULSORY traffic is
-// decoupled from the arithmetic, as in a GEMM pipeline:
+// Why: the gather kernels (sparse.cu) are bound by the SM's load/store data pipe, not by HBM: 9 scattered 16-byte reads and
+// 18 record words per 16 output bytes are ~93 L1 wavefronts per 512 output bytes, each costing ~2 cycles when an instruction
+// needs several (tools/exp_spmm_limits.py: 52 us at cosmo layer 2 even when every gather hits L1; a plain 3-stream kernel
+// of the same size takes 33 us).  This kernel cuts the wavefronts per output by 3 and takes the compulsory traffic off the
+// load/store pipe:
 //   * a work item = (row tile of TR consecutive rows, sample); the x rows of the tile, and the y / z rows, are contiguous
 //     in memory: one cp.async.bulk (TMA, 1-D) each into a shared-memory stage, completion on an mbarrier;
 //   * the tile's halo (rows referenced from outside the tile; host-built list, graph.py: PipePlan) follows with 16-byte
-//     cp.async -- about a third of a tile in HEALPix nested (Morton) order;
-//   * the tile's packed records (LOCAL column, value), 8 W TR bytes, are one more bulk copy per item (L2 hits: the B
-//     samples of a row tile are consecutive items);
-//   * S stages per CTA, filled by a dedicated producer warp; 2 CTAs per SM;
-//   * the 8 consumer warps read ONLY shared memory: W gathers of 16 bytes per lane from the staged rows, y / z from their stages, one
-//     coalesced 16-byte store per lane.  Arithmetic order identical to the gather kernels (bit-identical results).
+//     cp.async -- about a third of a tile in HEALPix nested (Morton) order; items are taken grid-strided in memory order, so
+//     the halo rows are L2 hits on the tiles the neighbouring CTAs are loading;
+//   * the tile's records are one more bulk copy per item (L2 hits);
+//   * S = 3 stages per CTA, filled by FOUR producer warps, one per stream (a bulk copy costs its issuing warp ~0.3 us
+//     whatever its size); 2 CTAs per SM;
+//   * consumer warps read ONLY shared memory.  Dense-group form (default): a lane group owns 4 consecutive rows (a 2 x 2
+//     block of the sphere) and reads each of their <= 16 DISTINCT neighbour rows once (16 reads instead of 36), then applies
+//     the group's dense 4 x 16 weight block; column slots alternate in bank-line parity between neighbouring groups and odd
+//     groups store their rows pairwise swapped, so every shared-memory / global instruction of a warp touches both halves
+//     of its 128-byte lines (no bank conflicts at 64-byte rows).  Record form (one lane group per row, W gathers, the
+//     arithmetic order of the gather kernels: bit-identical results) is kept for ELL width 7 and as the reference.
+// Measured (tools/exp_timing_method.py, back to back over rotating operand sets): cosmo layer 2 60 -> 42 us, layer 3 35 -> 23 us.
 // F in {16, 32, 64} (NCH = 4, 8, 16 chunks per row), ELL width 7 / 9; other shapes keep the gather kernels.
 #include "common.cuh"
 #include <stdlib.h>
@@ -27,8 +34,10 @@ struct PipeArgs {
     const float4 *x, *y, *z;
     float4* out;
     int T, TR, HC, B, M, S;
-    int order;              // 0: CTA = contiguous item range, samples of a row tile consecutive; 1: contiguous range in memory
-                            // order (row tiles of a sample consecutive); 2: grid-strided in memory order
+    int order;              // item order.  2 (default): grid-strided in memory order -- at any time the CTAs work on one window of
+                            // consecutive row tiles of a sample, so halo rows are L2 hits on their neighbours' tiles (measured
+                            // best); 0: CTA = contiguous item range, samples of a row tile consecutive; 1: contiguous range in
+                            // memory order (experiments: DSB200_PIPE_ORDER)
     int ablate;             // timing experiments only (tools/exp_pipe_ablate.py): skip parts of the work
     float alpha, beta, gamma;
 };
@@ -54,9 +63,10 @@ __device__ __forceinline__ void cp16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
-constexpr int kConsumerWarps = 8;
-constexpr int kHaloPerLane = 12;                                 // halo chunks per producer lane: HC * NCH <= 384
-constexpr int kPipeThreads = (kConsumerWarps + 1) * 32;          // + one producer warp
+constexpr int kConsumerWarps = 8;                                // record form: one lane group per row
+constexpr int kProducerWarps = 4;                                // x + halo, records, y, z
+constexpr int kDenseWarps = 4;                                   // dense-group form: one lane group per 4 rows
+constexpr int kHaloPerLane = 16;                                 // halo chunks per producer lane: HC * NCH <= 512
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(saddr(bar)) : "memory");
@@ -69,10 +79,11 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
 // Warp-specialised: warp 8 is the producer (it alone waits on global-memory latency: tile lists, bulk copies, halo
 // copies), warps 0..7 consume -- each owns TR/8 rows of every item and synchronises with nobody but the producer
 // (full[s] / empty[s] mbarriers), so the warps drift apart and hide each other's shared-memory latency.
-template <int W, int NCH, bool HASY, bool HASZ>
-__global__ void __launch_bounds__(kPipeThreads, 2)
+template <int W, int NCH, bool HASY, bool HASZ, bool DENSE>
+__global__ void __launch_bounds__((DENSE ? kDenseWarps : kConsumerWarps) * 32 + kProducerWarps * 32, 2)
 spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
 {
+    constexpr int CW = DENSE ? kDenseWarps : kConsumerWarps;
     extern __shared__ __align__(128) unsigned char smem[];
     const int TR = a.TR, HC = a.HC, S = a.S;
     const uint32_t xbytes = (uint32_t)(TR + HC) * NCH * 16, tbytes = (uint32_t)TR * NCH * 16;
@@ -89,13 +100,32 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
     const long long i0 = a.order == 2 ? blockIdx.x : c0, istep = a.order == 2 ? gridDim.x : 1;
     const int n = a.order == 2 ? (int)((nitems - blockIdx.x + gridDim.x - 1) / gridDim.x) : (int)(c1 - c0);
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(full + s, 32 + NBULK); mbar_init(empty + s, kConsumerWarps); }
+        for (int s = 0; s < S; ++s) { mbar_init(full + s, 32 + NBULK); mbar_init(empty + s, CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == kConsumerWarps) {
-        // ---------------- producer ----------------
+    if (warp >= CW) {
+        // ---------------- producers ----------------
+        // One warp per stream (x + halo, records, y, z): a bulk copy costs its issuing warp ~0.3 us whatever its size
+        // (profiles/r01_tma_box_rate.txt), so four copies per item from ONE warp would cap a CTA at one item per 1.3 us.
+        const int role = warp - CW;                                           // 0: x + halo, 1: records, 2 / 3: y, z
+        if (role == 2 && !HASY && !HASZ) return;
+        if (role == 3 && !(HASY && HASZ)) return;
+        if (role != 0 && lane != 0) return;
+        // halo rows of the NEXT item are fetched (tile_ext, all HC slots: unused ones repeat the tile's first row) while
+        // this one waits for its stage: no global-memory latency between a stage falling empty and its refill
+        const int nhalo = (a.ablate & 2) ? 0 : HC * NCH;
+        auto tile_of = [&](int it) -> int {
+            const long long item = i0 + it * istep;
+            return a.order == 0 ? (int)(item / a.B) : (int)(item % a.T);
+        };
+        int gr[kHaloPerLane], grn[kHaloPerLane];
+        if (role == 0) {
+            const int32_t* ext = a.ext + (long long)tile_of(0) * HC;
+#pragma unroll
+            for (int q = 0; q < kHaloPerLane; ++q) { const int idx = lane + q * 32; grn[q] = idx < nhalo ? __ldg(ext + idx / NCH) : 0; }
+        }
         for (int it = 0; it < n; ++it) {
             const int s = it % S, k = it / S;
             const long long item = i0 + it * istep;
@@ -103,35 +133,115 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
             if (a.order == 0) { rt = (int)(item / a.B); b = (int)(item - (long long)rt * a.B); }
             else { b = (int)(item / a.T); rt = (int)(item - (long long)b * a.T); }
             const int r0 = rt * TR, nt = min(TR, a.M - r0);
-            const int nhalo = (a.ablate & 2) ? 0 : __ldg(a.nh + rt) * NCH;
-            const int32_t* ext = a.ext + (long long)rt * HC;
-            int gr[kHaloPerLane];                                                 // halo chunks of this lane
-#pragma unroll
-            for (int q = 0; q < kHaloPerLane; ++q) { const int idx = lane + q * 32; gr[q] = idx < nhalo ? __ldg(ext + idx / NCH) : 0; }
-            if (k > 0) mbar_wait(empty + s, (uint32_t)(k - 1) & 1u);
             unsigned char* st = smem + (size_t)s * sbytes;
             const long long g0 = ((long long)b * a.M + r0) * NCH;                 // first chunk of the tile in the sample
             const uint32_t nb = (uint32_t)nt * NCH * 16;
-            if (lane < NBULK) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (lane == 0) { mbar_expect_tx(full + s, nb); bulk_g2s(st, a.x + g0, nb, full + s); }
-            if (lane == 1) { mbar_expect_tx(full + s, rbytes); bulk_g2s(st + rbase, a.rec + (long long)rt * W * TR, rbytes, full + s); }
-            if (HASY && lane == 2) { mbar_expect_tx(full + s, nb); bulk_g2s(st + ybase, a.y + g0, nb, full + s); }
-            if (HASZ && lane == (HASY ? 3 : 2)) { mbar_expect_tx(full + s, nb); bulk_g2s(st + zbase, a.z + g0, nb, full + s); }
-            float4* xh = reinterpret_cast<float4*>(st) + TR * NCH;
-            const float4* xb = a.x + (long long)b * a.M * NCH;
+            if (role == 0) {
 #pragma unroll
-            for (int q = 0; q < kHaloPerLane; ++q) {
-                const int idx = lane + q * 32;
-                if (idx < nhalo) cp16(xh + idx, xb + (long long)gr[q] * NCH + (idx % NCH));
+                for (int q = 0; q < kHaloPerLane; ++q) gr[q] = grn[q];
+                if (it + 1 < n) {
+                    const int32_t* ext = a.ext + (long long)tile_of(it + 1) * HC;
+#pragma unroll
+                    for (int q = 0; q < kHaloPerLane; ++q) { const int idx = lane + q * 32; grn[q] = idx < nhalo ? __ldg(ext + idx / NCH) : 0; }
+                }
+                if (k > 0) mbar_wait(empty + s, (uint32_t)(k - 1) & 1u);
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of this stage -> async writes
+                    mbar_expect_tx(full + s, nb);
+                    bulk_g2s(st, a.x + g0, nb, full + s);
+                }
+                float4* xh = reinterpret_cast<float4*>(st) + TR * NCH;
+                const float4* xb = a.x + (long long)b * a.M * NCH;
+#pragma unroll
+                for (int q = 0; q < kHaloPerLane; ++q) {
+                    const int idx = lane + q * 32;
+                    if (idx < nhalo) cp16(xh + idx, xb + (long long)gr[q] * NCH + (idx % NCH));
+                }
+                cp_async_arrive(full + s);
+            } else {
+                if (k > 0) mbar_wait(empty + s, (uint32_t)(k - 1) & 1u);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                if (role == 1) {
+                    mbar_expect_tx(full + s, rbytes);
+                    bulk_g2s(st + rbase, a.rec + (long long)rt * W * TR, rbytes, full + s);
+                } else if (role == 2) {
+                    mbar_expect_tx(full + s, nb);
+                    if (HASY) bulk_g2s(st + ybase, a.y + g0, nb, full + s); else bulk_g2s(st + zbase, a.z + g0, nb, full + s);
+                } else {
+                    mbar_expect_tx(full + s, nb);
+                    bulk_g2s(st + zbase, a.z + g0, nb, full + s);
+                }
             }
-            cp_async_arrive(full + s);
+        }
+        return;
+    }
+
+    if (DENSE) {
+        // ---------------- consumers, dense-group form ----------------
+        // A group = 4 consecutive rows (a 2 x 2 block of the sphere in nested order) and the U <= 16 DISTINCT columns its
+        // 4 x W entries touch: a lane reads each distinct neighbour once (16 x 16 bytes instead of 36) and applies the
+        // group's dense 4 x 16 weight block (zeros where a row does not see a column).  Records per tile: [18][G] 16-byte
+        // pieces -- 16 weight pieces (row r ^ (g & 1), columns 4q..4q+3 at k = 4r + q) and 2 pieces of 8 uint16 local columns.
+        // The pairwise row swap of odd groups and the parity-alternating column slots (graph.py) keep the 64-byte segments
+        // of an instruction spread over both halves of the bank lines.
+        constexpr int GPW = 32 / NCH;                                         // groups per warp pass
+        const int G = TR / 4;
+        const int sub = lane / NCH, lg = lane - sub * NCH;
+        for (int it = 0; it < n; ++it) {
+            const int s = it % S, k = it / S;
+            const long long item = i0 + it * istep;
+            int rt, b;
+            if (a.order == 0) { rt = (int)(item / a.B); b = (int)(item - (long long)rt * a.B); }
+            else { b = (int)(item / a.T); rt = (int)(item - (long long)b * a.T); }
+            const int r0 = rt * TR, nt = min(TR, a.M - r0);
+            const unsigned char* st = smem + (size_t)s * sbytes;
+            const float4* xs = reinterpret_cast<const float4*>(st);
+            const float4* ys = reinterpret_cast<const float4*>(st + ybase);
+            const float4* zs = reinterpret_cast<const float4*>(st + zbase);
+            const float4* wrec = reinterpret_cast<const float4*>(st + rbase);   // [18][G]
+            float4* ob = a.out + ((long long)b * a.M + r0) * NCH;
+            mbar_wait(full + s, (uint32_t)k & 1u);
+            for (int g = warp * GPW + sub; g < G && 4 * g < nt; g += CW * GPW) {
+                if (a.ablate & 16) {
+                    for (int r = 0; r < 4; ++r) if (4 * g + r < nt && !(a.ablate & 8)) ob[(4 * g + r) * NCH + lg] = xs[(4 * g + r) * NCH + lg];
+                    continue;
+                }
+                const uint4 c0 = *reinterpret_cast<const uint4*>(wrec + 16 * G + g);
+                const uint4 c1 = *reinterpret_cast<const uint4*>(wrec + 17 * G + g);
+                const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                float4 v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    const int c = (u & 1) ? (int)(cw[u >> 1] >> 16) : (int)(cw[u >> 1] & 0xffffu);
+                    v[u] = xs[c * NCH + lg];
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 w = wrec[(4 * r + q) * G + g];
+                        acc.x = fmaf(w.x, v[4 * q].x, acc.x); acc.y = fmaf(w.x, v[4 * q].y, acc.y); acc.z = fmaf(w.x, v[4 * q].z, acc.z); acc.w = fmaf(w.x, v[4 * q].w, acc.w);
+                        acc.x = fmaf(w.y, v[4 * q + 1].x, acc.x); acc.y = fmaf(w.y, v[4 * q + 1].y, acc.y); acc.z = fmaf(w.y, v[4 * q + 1].z, acc.z); acc.w = fmaf(w.y, v[4 * q + 1].w, acc.w);
+                        acc.x = fmaf(w.z, v[4 * q + 2].x, acc.x); acc.y = fmaf(w.z, v[4 * q + 2].y, acc.y); acc.z = fmaf(w.z, v[4 * q + 2].z, acc.z); acc.w = fmaf(w.z, v[4 * q + 2].w, acc.w);
+                        acc.x = fmaf(w.w, v[4 * q + 3].x, acc.x); acc.y = fmaf(w.w, v[4 * q + 3].y, acc.y); acc.z = fmaf(w.w, v[4 * q + 3].z, acc.z); acc.w = fmaf(w.w, v[4 * q + 3].w, acc.w);
+                    }
+                    const int row = 4 * g + (r ^ (g & 1));                       // odd groups store their rows pairwise swapped
+                    float4 res = make_float4(acc.x * a.alpha, acc.y * a.alpha, acc.z * a.alpha, acc.w * a.alpha);
+                    if (HASY) { const float4 t = ys[row * NCH + lg]; res.x = fmaf(a.beta, t.x, res.x); res.y = fmaf(a.beta, t.y, res.y); res.z = fmaf(a.beta, t.z, res.z); res.w = fmaf(a.beta, t.w, res.w); }
+                    if (HASZ) { const float4 t = zs[row * NCH + lg]; res.x = fmaf(a.gamma, t.x, res.x); res.y = fmaf(a.gamma, t.y, res.y); res.z = fmaf(a.gamma, t.z, res.z); res.w = fmaf(a.gamma, t.w, res.w); }
+                    if (row < nt && !(a.ablate & 8)) ob[row * NCH + lg] = res;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);
         }
         return;
     }
 
     // ---------------- consumers ----------------
     constexpr int RPP = 32 / NCH;                                             // rows per warp pass
-    const int rpw = TR / kConsumerWarps;                                      // rows per warp (host: TR % (8 * RPP) == 0)
+    const int rpw = TR / CW;                                      // rows per warp (host: TR % (8 * RPP) == 0)
     const int sub = lane / NCH, lg = lane - sub * NCH;
     for (int it = 0; it < n; ++it) {
         const int s = it % S, k = it / S;
@@ -149,6 +259,7 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
         mbar_wait(full + s, (uint32_t)k & 1u);
         const int rend = min(nt, (warp + 1) * rpw);
         for (int r = warp * rpw + sub; r < rend; r += RPP) {
+            if (a.ablate & 16) { if (!(a.ablate & 8)) ob[r * NCH + lg] = xs[r * NCH + lg]; continue; }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
@@ -173,14 +284,15 @@ static size_t pipe_smem(int W, int TR, int HC, int nch, int extra, int S) {
     return (size_t)S * stage + 2 * S * 8 + 64;
 }
 
-template <int W, int NCH>
+template <int W, int NCH, bool DENSE>
 static int pipe_launch_t(const PipeArgs& a, int grid, size_t smem, cudaStream_t s)
 {
+    constexpr int threads = ((DENSE ? kDenseWarps : kConsumerWarps) + kProducerWarps) * 32;
 #define DSB_PIPE(YY, ZZ) do { \
         static bool cfg = false; \
-        if (!cfg) { cudaError_t e = cudaFuncSetAttribute(spmm_pipe_kernel<W, NCH, YY, ZZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024); \
+        if (!cfg) { cudaError_t e = cudaFuncSetAttribute(spmm_pipe_kernel<W, NCH, YY, ZZ, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024); \
                     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; } cfg = true; } \
-        spmm_pipe_kernel<W, NCH, YY, ZZ><<<grid, kPipeThreads, smem, s>>>(a); } while (0)
+        spmm_pipe_kernel<W, NCH, YY, ZZ, DENSE><<<grid, threads, smem, s>>>(a); } while (0)
     if (a.y && a.z) DSB_PIPE(true, true);
     else if (a.y) DSB_PIPE(true, false);
     else if (a.z) DSB_PIPE(false, true);
@@ -194,7 +306,7 @@ static int pipe_launch_t(const PipeArgs& a, int grid, size_t smem, cudaStream_t 
 using namespace dsb200;
 
 extern "C" int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, const int32_t* tile_nh,
-                                int ntiles, int TR, int HC, int width, int B, int M, int F,
+                                int ntiles, int TR, int HC, int width, int dense, int B, int M, int F,
                                 const float* x, const float* y, const float* z, float* out,
                                 float alpha, float beta, float gamma, void* stream)
 {
@@ -202,6 +314,7 @@ extern "C" int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, 
     DSB_REQUIRE(tile_recs && tile_ext && tile_nh && x && out, "spmm_pipe: null pointer");
     DSB_REQUIRE(x != out, "spmm_pipe: out must not alias x");
     DSB_REQUIRE(width == 9 || width == 7, "spmm_pipe: ELL width must be 7 or 9");
+    DSB_REQUIRE(!dense || width == 9, "spmm_pipe: dense-group records are 72 bytes per row (width 9 layout)");
     DSB_REQUIRE(F == 16 || F == 32 || F == 64, "spmm_pipe: F must be 16, 32 or 64");
     DSB_REQUIRE(TR > 0 && HC >= 0 && ntiles == (M + TR - 1) / TR, "spmm_pipe: tile plan does not match M");
     DSB_REQUIRE(TR % (8 * (128 / F)) == 0 && HC * (F / 4) <= 32 * kHaloPerLane && (width * TR * 8) % 16 == 0, "spmm_pipe: unsupported tile shape");
@@ -221,19 +334,24 @@ extern "C" int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, 
     a.T = ntiles; a.TR = TR; a.HC = HC; a.B = B; a.M = M; a.S = S;
     a.alpha = alpha; a.beta = beta; a.gamma = gamma;
     { const char* e = getenv("DSB200_PIPE_ABLATE"); a.ablate = e ? atoi(e) : 0; }
-    { const char* e = getenv("DSB200_PIPE_ORDER"); a.order = e ? atoi(e) : 0; }
+    { const char* e = getenv("DSB200_PIPE_ORDER"); a.order = e ? atoi(e) : 2; }
     int ctas = 2;
     { const char* e = getenv("DSB200_PIPE_CTAS"); if (e && atoi(e) == 1) ctas = 1; }
     const long long nitems = (long long)ntiles * B;
     const long long cap = (long long)ctas * kNumSMs;
     const int grid = (int)(nitems < cap ? nitems : cap);
     cudaStream_t s = (cudaStream_t)stream;
-    if (width == 9) {
-        if (nch == 4) return pipe_launch_t<9, 4>(a, grid, smem, s);
-        if (nch == 8) return pipe_launch_t<9, 8>(a, grid, smem, s);
-        return pipe_launch_t<9, 16>(a, grid, smem, s);
+    if (dense) {                                                  // the records do not depend on the ELL width (W = 9 is a dummy)
+        if (nch == 4) return pipe_launch_t<9, 4, true>(a, grid, smem, s);
+        if (nch == 8) return pipe_launch_t<9, 8, true>(a, grid, smem, s);
+        return pipe_launch_t<9, 16, true>(a, grid, smem, s);
     }
-    if (nch == 4) return pipe_launch_t<7, 4>(a, grid, smem, s);
-    if (nch == 8) return pipe_launch_t<7, 8>(a, grid, smem, s);
-    return pipe_launch_t<7, 16>(a, grid, smem, s);
+    if (width == 9) {
+        if (nch == 4) return pipe_launch_t<9, 4, false>(a, grid, smem, s);
+        if (nch == 8) return pipe_launch_t<9, 8, false>(a, grid, smem, s);
+        return pipe_launch_t<9, 16, false>(a, grid, smem, s);
+    }
+    if (nch == 4) return pipe_launch_t<7, 4, false>(a, grid, smem, s);
+    if (nch == 8) return pipe_launch_t<7, 8, false>(a, grid, smem, s);
+    return pipe_launch_t<7, 16, false>(a, grid, smem, s);
 }

@@ -153,21 +153,74 @@ class PipePlan(object):
         rec[:M, :, 1] = val.view(np.int32)
         rec = np.ascontiguousarray(rec.reshape(T, TR, W, 2).transpose(0, 2, 1, 3))
         self.rec_np, self.ext_np, self.nh_np = rec, ext, counts.astype(np.int32)
+        self.dense_np = self._dense_groups(lcol, val, M, Mp, T, TR, W)
         self.T, self.TR, self.HC, self.width, self.M = T, TR, HC, W, M
         if device is not None:
+            self.dense = torch.from_numpy(self.dense_np).to(device) if self.dense_np is not None else None
             self.rec = torch.from_numpy(rec).to(device)
             self.ext = torch.from_numpy(np.ascontiguousarray(ext)).to(device)
             self.nh = torch.from_numpy(self.nh_np).to(device)
         self.valid = True
 
+    @staticmethod
+    def _dense_groups(lcol, val, M, Mp, T, TR, W):
+        """Dense-group records (include/dsb200.h: dsb200_spmm_pipe, dense != 0), int32[T, 18, TR/4, 4], or None when
+        some group of 4 consecutive rows touches more than 16 distinct columns or the layout does not apply."""
+        if W != 9 or TR % 4 or TR + 2 * TR > 65535:
+            return None
+        G = TR // 4
+        lc = np.repeat((np.arange(Mp, dtype=np.int64) % TR)[:, None], W, axis=1)       # padding rows: own local row
+        lc[:M] = lcol
+        v = np.zeros((Mp, W), np.float32)
+        v[:M] = val
+        ng = Mp // 4
+        lcg = lc.reshape(ng, 4 * W)
+        order = np.argsort(lcg, axis=1, kind='stable')
+        srt = np.take_along_axis(lcg, order, axis=1)
+        first = np.ones_like(srt, dtype=bool)
+        first[:, 1:] = srt[:, 1:] != srt[:, :-1]
+        rank_sorted = np.cumsum(first, axis=1) - 1
+        if int(rank_sorted[:, -1].max()) + 1 > 16:
+            return None
+        rank = np.empty_like(rank_sorted)
+        np.put_along_axis(rank, order, rank_sorted, axis=1)
+        # Slot of every distinct column.  Shared-memory rows of 64 bytes (F = 16) sit in one HALF of a 128-byte bank line,
+        # chosen by the parity of the local column; the 8 groups a warp works on read slot u together, so slot u of group g
+        # gets a column of parity (u + g) & 1 where the group has at most 8 columns of each parity (always, inside the
+        # sphere: a 4 x 4 block): 4 + 4 segments per instruction, no bank conflict.  Other groups: ascending order.
+        gpar = (np.arange(ng) & 1)[:, None]
+        par = srt & 1
+        k_in_class = np.where(par == 1, np.cumsum(first & (par == 1), axis=1), np.cumsum(first & (par == 0), axis=1)) - 1
+        n_even = (first & (par == 0)).sum(axis=1)
+        n_odd = (first & (par == 1)).sum(axis=1)
+        balanced = ((n_even <= 8) & (n_odd <= 8))[:, None]
+        slot_sorted = np.where(balanced, 2 * k_in_class + (par ^ gpar), rank_sorted)
+        slot = np.empty_like(slot_sorted)
+        np.put_along_axis(slot, order, slot_sorted, axis=1)
+        cols = np.repeat(lcg[:, :1], 16, axis=1)                                      # unused slots: the group's first row
+        gi = np.repeat(np.arange(ng), 4 * W)
+        cols[gi, slot.ravel()] = lcg.ravel()
+        # row r of the stored block = row r ^ (g & 1) of the group: the y / z reads and the stores of an instruction then
+        # touch both halves of the bank lines / both 64-byte halves of the global lines (include/dsb200.h)
+        wd = np.zeros((ng, 4, 16), np.float32)
+        ri = np.tile(np.repeat(np.arange(4), W), ng) ^ np.repeat(np.arange(ng) & 1, 4 * W)
+        np.add.at(wd, (gi, ri, slot.ravel()), v.reshape(ng, 4 * W).ravel())
+        out = np.empty((T, 18, G, 4), np.int32)
+        out[:, :16] = wd.reshape(T, G, 16, 4).transpose(0, 2, 1, 3).view(np.int32)   # piece 4r + q = row r, columns 4q..4q+3
+        c16 = cols.astype(np.uint16).reshape(T, G, 2, 8)
+        out[:, 16:] = np.ascontiguousarray(c16.transpose(0, 2, 1, 3)).view(np.int32).reshape(T, 2, G, 4)
+        return np.ascontiguousarray(out)
+
     def fits(self, F, extra=2):
         """Two stages of (x tile + halo, `extra` more tiles, records) fit in the CTA's shared memory, and the tile
         shape is one the kernel's warp layout covers."""
         stage = (self.TR + self.HC) * 4 * F + self.TR * 4 * F * extra + self.width * self.TR * 8
-        return (2 * stage + 128 <= PIPE_SMEM and self.TR % (8 * (128 // F)) == 0 and self.HC * (F // 4) <= 384)
+        return (2 * stage + 128 <= PIPE_SMEM and self.TR % (8 * (128 // F)) == 0 and self.HC * (F // 4) <= 512)
 
-    def args(self):
-        return (self.rec, self.ext, self.nh, self.T, self.TR, self.HC, self.width)
+    def args(self, dense=False):
+        if dense and self.dense is not None:
+            return (self.dense, self.ext, self.nh, self.T, self.TR, self.HC, self.width, 1)
+        return (self.rec, self.ext, self.nh, self.T, self.TR, self.HC, self.width, 0)
 
 
 BLOCK_ROWS = 16            # rows per block of the tensor-core product (csrc/sparse_blk.cu): the M of mma.m16n8k8

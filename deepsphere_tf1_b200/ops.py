@@ -31,7 +31,7 @@ def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, tra
     sp = _staged(graph, which, B, F) if rows is None and pp is None else None
     bp = _blocks(graph, which, B, F) if rows is None and sp is None and pp is None else None
     if pp is not None:
-        call('spmm_pipe', *pp.args(), B, M, F, x, y, z, out, alpha, beta, gamma)
+        call('spmm_pipe', *pp.args(USE_DENSE_GROUPS), B, M, F, x, y, z, out, alpha, beta, gamma)
     elif sp is not None:
         call('spmm_stile', *sp.args(), B, M, F, x, y, z, out, alpha, beta, gamma)
     elif bp is not None:
@@ -48,12 +48,15 @@ def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, tra
 
 
 USE_PIPE = True           # bulk-asynchronous pipelined sparse product (csrc/sparse_pipe.cu) where a tile plan exists
+USE_DENSE_GROUPS = True   # pipelined kernel: 4-row groups with dense 4 x 16 weight blocks (each distinct neighbour read once)
 PIPE_MIN_ITEMS = 4 * 296  # (row tiles x samples) below which the pipeline has nothing to overlap: gather kernels
 
 
-def set_pipe(on):
-    global USE_PIPE
+def set_pipe(on, dense=None):
+    global USE_PIPE, USE_DENSE_GROUPS
     USE_PIPE = bool(on)
+    if dense is not None:
+        USE_DENSE_GROUPS = bool(dense)
 
 
 def _pipe(graph, which, B, M, F):

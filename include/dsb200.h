@@ -112,9 +112,13 @@ int dsb200_cheb_basis_bwd_ellp(const void* recT, const int32_t* colT, const floa
  * 16-byte cp.async, several items in flight per CTA; the arithmetic reads shared memory only.
  * tile_recs int2[ntiles][width][TR] = (LOCAL column, value bits): local column < TR = row of the tile, else TR + halo slot;
  * tile_ext int32[ntiles][HC] = global row of every halo slot; tile_nh int32[ntiles] = halo rows per tile
- * (graph.py: PipePlan).  out must not alias x (it may alias y or z); pointers 16-byte aligned. */
+ * (graph.py: PipePlan).  dense != 0: DENSE-GROUP records instead -- per tile [18][TR/4] 16-byte pieces: a group = 4
+ * consecutive rows and the <= 16 distinct local columns they touch; pieces 0..15 = the group's dense 4 x 16 weight block
+ * (row r ^ (g & 1) of group g, columns 4q..4q+3 at piece 4r + q), pieces 16, 17 = the 16 uint16 local columns.  Each distinct neighbour is read
+ * once per group (16 reads for 4 rows instead of 36); sums run in column order, so results equal the record form to
+ * rounding (~1e-7), not bit for bit.  out must not alias x (it may alias y or z); pointers 16-byte aligned. */
 int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, const int32_t* tile_nh,
-                     int ntiles, int TR, int HC, int width, int B, int M, int F,
+                     int ntiles, int TR, int HC, int width, int dense, int B, int M, int F,
                      const float* x, const float* y, const float* z, float* out,
                      float alpha, float beta, float gamma, void* stream);
 

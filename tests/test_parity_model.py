@@ -87,12 +87,16 @@ def _momentum():
     return dict(optimizer=lambda lr: optimizers.MomentumOptimizer(lr, 0.9)), optim_tf1.Momentum(0.9)
 
 
+@pytest.mark.parametrize('pipelined', [False, True])
 @pytest.mark.parametrize('fused_small', [True, False])
-def test_cosmo_like_fcn_statistics_head(fused_small):
+def test_cosmo_like_fcn_statistics_head(fused_small, pipelined, monkeypatch):
     """config 2 in miniature: partial sphere (order 2), K=5, max-pool 4, BN everywhere, last layer
     linear, statistics='mean', M=[]  (experiments/cosmo/experiment_deepsphere.py:39-47); with the
-    input layer on the fused never-materialise-y path (K*Fin = 5) and on the generic path."""
-    from deepsphere_tf1_b200 import utils
+    input layer on the fused never-materialise-y path (K*Fin = 5) and on the generic path; with the sparse
+    products of every level forced through the bulk-asynchronous pipelined kernel (csrc/sparse_pipe.cu, which
+    the size threshold would reserve for the large levels) and on the gather kernels."""
+    from deepsphere_tf1_b200 import ops, utils
+    monkeypatch.setattr(ops, 'PIPE_MIN_ITEMS', 1 if pipelined else 1 << 30)
     nsides = [32, 16, 8, 4, 4]
     idx = utils.nside2indexes(nsides, 2)
     L, p = utils.build_laplacians(nsides, indexes=idx, new=False)

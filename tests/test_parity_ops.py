@@ -109,29 +109,36 @@ def test_packed_record_spmm_is_bit_identical_to_row_major(dev, F, graph, sb, mon
     assert_close(basis, _oracle_basis(L, x.cpu(), K)[1:], RTOL, 'basis vs oracle')
 
 
+@pytest.mark.parametrize('dense', [False, True])
 @pytest.mark.parametrize('F', [16, 32, 64])
 @pytest.mark.parametrize('B', [1, 5, 16])
 @pytest.mark.parametrize('graph', ['healpix16', 'patch64', 'ragged'])
-def test_pipelined_spmm_is_bit_identical_to_the_gather_kernel(dev, F, B, graph, monkeypatch):
+def test_pipelined_spmm_equals_the_gather_kernel(dev, F, B, graph, dense, monkeypatch):
     """Bulk-asynchronous pipelined sparse product (csrc/sparse_pipe.cu, the default where a tile plan exists) vs the
-    gather kernel: identical arithmetic order, so identical bits -- general form, in-place adjoint form, whole recurrence
-    and its adjoint; and both within the fp32 bar of the oracle."""
+    gather kernel -- general form, in-place adjoint form, whole recurrence and its adjoint.  Record form: identical
+    arithmetic order, identical bits.  Dense-group form (4 rows x their <= 16 distinct columns): sums in column order,
+    equal to rounding.  Both within the fp32 bar of the oracle."""
     from scipy import sparse
     from deepsphere_tf1_b200 import ops
     L = {'healpix16': lambda: healpix_L(16), 'patch64': lambda: healpix_L(64, order=2),
          'ragged': lambda: sparse.coo_matrix(sparse.csr_matrix(healpix_L(16))[:3001, :3001])}[graph]()
     g = _graph(L, dev)
     monkeypatch.setattr(ops, 'PIPE_MIN_ITEMS', 1)
-    if F == 64:
-        assert ops._pipe(g, 'fwd', B, g.M, F) is None          # halo of a 32-row tile too large: gather kernel (still checked below)
-    else:
-        assert ops._pipe(g, 'fwd', B, g.M, F) is not None
+    plan = ops._pipe(g, 'fwd', B, g.M, F)
+    assert plan is not None and plan.dense is not None
+
+    def same(a, b, name):
+        if dense:
+            assert_close(a, b, 2e-6, name)
+        else:
+            assert torch.equal(a, b), name
+
     K = 4
     rs = np.random.RandomState(F + B)
     x, y, z = [torch.from_numpy(rs.randn(B, g.M, F).astype(np.float32)).to(dev) for _ in range(3)]
     G = torch.from_numpy(rs.randn(K, B, g.M, F).astype(np.float32)).to(dev)
     try:
-        ops.set_pipe(True)
+        ops.set_pipe(True, dense=dense)
         out = ops.spmm(g, x, y, z, alpha=0.5, beta=-1.5, gamma=0.25)
         out1 = ops.spmm(g, x)
         yt = y.clone()
@@ -139,15 +146,15 @@ def test_pipelined_spmm_is_bit_identical_to_the_gather_kernel(dev, F, B, graph, 
         basis = ops.cheb_basis(g, x, K)
         dx = ops.cheb_basis_bwd(g, G.clone())
         ops.set_pipe(False)
-        assert torch.equal(out, ops.spmm(g, x, y, z, alpha=0.5, beta=-1.5, gamma=0.25))
-        assert torch.equal(out1, ops.spmm(g, x))
+        same(out, ops.spmm(g, x, y, z, alpha=0.5, beta=-1.5, gamma=0.25), 'general form')
+        same(out1, ops.spmm(g, x), 'plain product')
         yr = y.clone()
         ops.spmm(g, x, yr, z, out=yr, alpha=2.0, beta=1.0, gamma=-1.0, transpose=True)
-        assert torch.equal(yt, yr)
-        assert torch.equal(basis, ops.cheb_basis(g, x, K))
-        assert torch.equal(dx, ops.cheb_basis_bwd(g, G.clone()))
+        same(yt, yr, 'in-place adjoint form')
+        same(basis, ops.cheb_basis(g, x, K), 'basis')
+        same(dx, ops.cheb_basis_bwd(g, G.clone()), 'adjoint recurrence')
     finally:
-        ops.set_pipe(True)
+        ops.set_pipe(True, dense=True)
     assert_close(basis, _oracle_basis(L, x.cpu(), K)[1:], RTOL, 'basis vs oracle')
 
 

@@ -204,4 +204,14 @@ def test_pipe_plan_local_gather_equals_the_global_product(graph, TR):
             assert lc.max() < TR + max(nh, 1) and lc.min() >= 0
             acc = acc + plan.rec_np[t, j, :nt, 1].view(np.float32)[:, None] * stage[lc]
         out[r0:r0 + nt] = acc
+        # dense-group records: 4 rows x <= 16 distinct columns, [18][G] 16-byte pieces per tile
+        d = plan.dense_np[t]
+        G = TR // 4
+        wd = d[:16].view(np.float32).reshape(4, 4, G, 4).transpose(2, 0, 1, 3).reshape(G, 4, 16)
+        cols = d[16:].view(np.uint16).reshape(2, G, 8).transpose(1, 0, 2).reshape(G, 16)
+        for gidx in range((nt + 3) // 4):
+            rows = slice(4 * gidx, min(4 * gidx + 4, nt))
+            dn = wd[gidx].astype(np.float64) @ stage[cols[gidx]].astype(np.float64)
+            dn = dn[np.arange(4) ^ (gidx & 1)]                       # stored row r = row r ^ (g & 1)
+            assert np.allclose(dn[:rows.stop - rows.start], acc[rows], rtol=0, atol=1e-5)
     assert np.array_equal(out, ref)

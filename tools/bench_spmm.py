@@ -51,8 +51,8 @@ for li in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else '1,2,3,4,5').s
     for form in ('fwd', 'adj'):
         nbytes = (3 if form == 'fwd' else 4) * X + 8 * g.nnz
         res = {}
-        for label, pipe in (('gather', False), ('pipelined', True)):
-            ops.set_pipe(pipe)
+        for label, pipe, dense in (('gather', False, False), ('pipelined', True, False), ('pipe+dense', True, True)):
+            ops.set_pipe(pipe, dense=dense)
             if pipe and ops._pipe(g, 'fwd', B, M, Fin) is None:
                 continue
             if form == 'fwd':
@@ -65,6 +65,7 @@ for li in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else '1,2,3,4,5').s
             t = timeit(fn)
             print('  {} {:<10s}: {:7.1f} us  {:6.1f} MB  {:6.0f} GB/s ({:4.1f}% of peak; roofline {:.1f} us)'.format(
                 form, label, t * 1e6, nbytes / 1e6, nbytes / t / 1e9, 100 * nbytes / t / 1e9 / peak, nbytes / peak / 1e3))
-        if len(res) == 2 and not torch.equal(res['gather'], res['pipelined']):
-            print('  MISMATCH', (res['gather'] - res['pipelined']).abs().max().item())
-ops.set_pipe(True)
+        for k in ('pipelined', 'pipe+dense'):
+            if k in res and not torch.equal(res['gather'], res[k]):
+                print('  {} differs from gather: max abs {:.2e}'.format(k, (res['gather'] - res[k]).abs().max().item()))
+ops.set_pipe(True, dense=True)

@@ -62,14 +62,14 @@ for li in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else '2,3').split('
     print('layer {}: B={} M={} Fin={}  {:.1f} MB per launch, roofline {:.1f} us; {} operand sets = {:.0f} MB'.format(
         li, B, M, Fin, nbytes / 1e6, nbytes / peak / 1e3, nsets, nsets * nbytes / 1e6))
     kernels = [('plain add', lambda i: torch.add(xs[i], ys[i], alpha=-1.0, out=os_[i]), None)]
-    for label, pipe in (('gather spmm', False), ('pipelined spmm', True)):
+    for label, pipe in (('gather spmm', (False, False)), ('pipelined spmm', (True, False)), ('pipe+dense spmm', (True, True))):
         kernels.append((label, lambda i: ops.spmm(g, xs[i], ys[i], None, out=os_[i], alpha=2.0, beta=-1.0), pipe))
     for label, fn, pipe in kernels:
         if pipe is not None:
-            ops.set_pipe(pipe)
+            ops.set_pipe(pipe[0], dense=pipe[1])
         a = per_launch(fn, False)
         b = per_launch(fn, True)
         c = back_to_back(fn, nsets)
         print('  {:<16s}: dirty flush {:6.1f} us ({:4.1f}%)   clean flush {:6.1f} us ({:4.1f}%)   back to back {:6.1f} us ({:4.1f}%)'.format(
             label, a * 1e6, 100 * nbytes / a / 1e9 / peak, b * 1e6, 100 * nbytes / b / 1e9 / peak, c * 1e6, 100 * nbytes / c / 1e9 / peak))
-ops.set_pipe(True)
+ops.set_pipe(True, dense=True)
