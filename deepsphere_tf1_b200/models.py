@@ -532,14 +532,20 @@ class base_model(object):
 
         times = []
         loss = float('nan')
+        def fetch():
+            d, l = next(train_iter)
+            if not isinstance(d, (np.ndarray, torch.Tensor)):
+                d = d.toarray()
+            return d, l
+
+        coming = fetch() if num_steps >= start_step else None
         for step in range(start_step, num_steps + 1):
             t_begin = perf_counter()
-            batch_data, batch_labels = next(train_iter)
-            if not isinstance(batch_data, (np.ndarray, torch.Tensor)):
-                batch_data = batch_data.toarray()
+            batch_data, batch_labels = coming
+            coming = fetch() if step < num_steps else None          # handed to train_step: its copy overlaps this step
             evaluate = (step % self.eval_frequency == 0) or (step == num_steps)
             t_begin_load = perf_counter()
-            learning_rate, loss_dev = self.train_step(batch_data, batch_labels)
+            learning_rate, loss_dev = self.train_step(batch_data, batch_labels, next_batch=coming)
             if evaluate or self.sync_every_step:
                 loss = float(loss_dev)                      # device -> host read of the step's loss
             t_end = perf_counter()
@@ -865,6 +871,8 @@ class cgcnn(base_model):
         self._gen = torch.Generator(device=self.device)
         self._gen.manual_seed(0 if seed is None else int(seed))
         self._graph_exec = None
+        self._prefetched = None
+        self._copy_stream = None
         self._peer = None
         self._arena = torch.zeros(16384, dtype=torch.float64, device=self.device)
         self._arena_off = None
@@ -1083,13 +1091,22 @@ class cgcnn(base_model):
         self.global_step = step + 1
         return lr
 
-    def train_step(self, batch_data, batch_labels):
+    def train_step(self, batch_data, batch_labels, next_batch=None):
         """One `sess.run([op_train, op_loss])` (models.py:535-536, 822-843).  Returns
-        (learning_rate, loss) with the loss still on the device (a 1-element tensor)."""
+        (learning_rate, loss) with the loss still on the device (a 1-element tensor).
+        `next_batch` = (data, labels) of the FOLLOWING step, if the caller has it (fit does): its host -> device copy is
+        enqueued on a copy stream right after this step's kernels, so it overlaps them (the feed_dict copy of the
+        reference, models.py:535, is 40 % of its step); the next call must then pass the same two objects."""
         if self._opt is None:
             raise RuntimeError('model was built without an optimizer')
-        x = self._to_device(batch_data)
-        labels = self._labels_to_device(batch_labels)
+        pre = self._prefetched
+        if pre is not None and pre[0] is batch_data and pre[1] is batch_labels:
+            x, labels = pre[2], pre[3]
+            torch.cuda.current_stream().wait_event(pre[4])
+        else:
+            x = self._to_device(batch_data)
+            labels = self._labels_to_device(batch_labels)
+        self._prefetched = None
         if x.shape[0] != self.batch_size:
             raise ValueError('batch of {} samples, model built for batch_size={}'.format(x.shape[0], self.batch_size))
         lr = self._advance_hyper()
@@ -1097,7 +1114,43 @@ class cgcnn(base_model):
             self._step_graphed(x, labels)
         else:
             self._step_device(x, labels)
+        if pre is not None and x is pre[2]:
+            pre[5].record()                                 # staging pair consumed (copied into the graph's inputs / used)
+        if next_batch is not None:
+            self._prefetch(next_batch[0], next_batch[1])
         return lr, self._loss
+
+    def _prefetch(self, batch_data, batch_labels):
+        """Start the host -> device copy of a coming batch on the copy stream into one of two staging pairs."""
+        if self.vertex_shard or batch_labels is None:
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = [None, None]
+            self._stage_i = 0
+        hx = batch_data if isinstance(batch_data, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(self._as_bmf(batch_data)))
+        hl = batch_labels if isinstance(batch_labels, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(batch_labels))
+        if hx.is_cuda or hx.dtype != torch.float32:
+            return
+        if hx.dim() == 2:
+            hx = hx.unsqueeze(2)
+        ldt = torch.float32 if self.regression else torch.int32
+        i = self._stage_i
+        self._stage_i ^= 1
+        st = self._stage[i]
+        if st is None or st[0].shape != hx.shape or st[1].shape != hl.shape:
+            st = (torch.empty(hx.shape, dtype=torch.float32, device=self.device),
+                  torch.empty(hl.shape, dtype=ldt, device=self.device),
+                  torch.cuda.Event(), torch.cuda.Event())          # (x, labels, ready, consumed)
+            st[3].record()
+            self._stage[i] = st
+        cs = self._copy_stream
+        cs.wait_event(st[3])                                # the step that last read this pair has taken its copy
+        with torch.cuda.stream(cs):
+            st[0].copy_(hx.contiguous(), non_blocking=True)
+            st[1].copy_(hl.to(ldt).contiguous(), non_blocking=True)
+            st[2].record(cs)
+        self._prefetched = (batch_data, batch_labels, st[0], st[1], st[2], st[3])
 
     def _capture(self, x, labels):
         self._gx = x.clone()

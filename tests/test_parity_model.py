@@ -200,6 +200,32 @@ def test_cuda_graph_replay_matches_eager():
     assert_close(graphed._P.w, eager._P.w, 1e-5, 'weights after graph replay')
 
 
+@pytest.mark.parametrize('graphed', [False, True])
+def test_prefetched_batches_train_exactly_like_plain_steps(graphed):
+    """train_step(next_batch=...) stages the following batch on a copy stream while the step runs (what fit does);
+    the weights after a few steps must equal those of plain train_step calls on the same batches."""
+    L = [healpix_L(4), healpix_L(2)]
+    kw = dict(F=[8, 4], K=[3, 3], p=[4, 1], batch_norm=[True, True], M=[], statistics='mean', cuda_graph=graphed)
+    _, plain = _pair(L, **kw)
+    _, pre = _pair(L, **kw)
+    rs = np.random.RandomState(5)
+    batches = [(torch.from_numpy(rs.randn(4, 192, 1).astype(np.float32)).pin_memory(),
+                torch.from_numpy(rs.randint(0, 4, size=4).astype(np.int32)).pin_memory()) for _ in range(5)]
+    for t, (x, labels) in enumerate(batches):
+        _, l1 = plain.train_step(x, labels)
+        _, l2 = pre.train_step(x, labels, next_batch=batches[t + 1] if t + 1 < len(batches) else None)
+        assert pre._prefetched is None or pre._prefetched[0] is batches[t + 1][0]
+        assert float(l1) == pytest.approx(float(l2), rel=1e-5)       # (atomic accumulation order differs run to run)
+    assert_close(pre._P.w, plain._P.w, 1e-5, 'weights after prefetched steps')
+    # a caller that passes a different batch than the one it announced just gets a plain copy
+    x, labels = batches[0]
+    pre.train_step(x, labels, next_batch=batches[1])
+    plain.train_step(x, labels)
+    pre.train_step(batches[2][0], batches[2][1])
+    plain.train_step(batches[2][0], batches[2][1])
+    assert_close(pre._P.w, plain._P.w, 1e-5, 'weights after an unannounced batch')
+
+
 def test_fit_predict_evaluate_api(tmp_path):
     """Reference-style end-to-end use: datasets in, tuples out (models.py:432-618, 343-430)."""
     from deepsphere_tf1_b200 import models, optimizers
