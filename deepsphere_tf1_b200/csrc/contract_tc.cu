@@ -346,6 +346,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
             const bool ok = row < p.R && !p.nostore;
             if (MODE == MODE_FWD) {
                 float* orow = p.out + row * p.Fout;
+                const bool wide8 = (p.Fout & 7) == 0 && (p.n0 & 7) == 0 && ((uintptr_t)p.out & 31) == 0;
                 for (int c0 = 0; c0 < p.Nreal; c0 += 32) {
                     float v[32];
                     {
@@ -367,7 +368,19 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
 #pragma unroll
                         for (int i = 16; i < 32; ++i) v[i] = 0.f;
                     }
-                    if (ok) {
+                    if (ok && wide8) {
+                        // a lane owns a whole output row: 32-byte stores halve the number of 128-byte lines (= load/store-pipe
+                        // wavefronts) a warp instruction touches per byte (32 lines either way)
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            const int c = p.n0 + c0 + i;
+                            if (c + 7 < p.Fout && c0 + i + 7 < p.Nreal) st8(orow + c, v + i);
+                            else {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) if (c + e < p.Fout && c0 + i + e < p.Nreal) orow[c + e] = v[i + e];
+                            }
+                        }
+                    } else if (ok) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const int c = p.n0 + c0 + i;

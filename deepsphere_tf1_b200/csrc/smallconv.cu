@@ -33,6 +33,12 @@ struct Planes {
 // was transposed to [M, B, Fin] before the recurrence (so that the sparse products gather B*Fin contiguous
 // floats per neighbour instead of Fin), row (b, m) = m*B + b.  Work items t enumerate pooled rows with the
 // sample index fastest in the interleaved case (coalesced basis reads); outputs keep the classic layout.
+// one 32-byte read-only load (sm_100+), src 32-byte aligned
+__device__ __forceinline__ void ldg8(const float* src, float* v) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "l"(src));
+}
+
 struct RowMap {
     int B, M, Mo, p, il;
     // B * M < 2^31 (checked by the launchers): 32-bit index arithmetic
@@ -306,6 +312,7 @@ smallconv_fwd_fast_kernel(Planes P, RowMap rm, const float* __restrict__ W, cons
     __syncthreads();
     const int Fg = Fout / 8;
     const long long total = Rout * Fg;
+    const bool wide = ((uintptr_t)out & 31) == 0;        // Fout % 8 == 0 here: every lane's piece is 32-byte aligned
     const float* cp[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) cp[q] = P.col(q);
@@ -340,9 +347,15 @@ smallconv_fwd_fast_kernel(Planes P, RowMap rm, const float* __restrict__ W, cons
         }
         float o[8];
         uint32_t a0 = 0, a1 = 0;
+        // (vector reads of the scale / shift and one 32-byte store per lane: the kernel is bound by load/store-pipe
+        // wavefronts -- a lane's output row piece lies in a different sample plane than its neighbours')
+        const float4 r0 = *reinterpret_cast<const float4*>(rs + f0), r1 = *reinterpret_cast<const float4*>(rs + f0 + 4);
+        const float4 c0 = *reinterpret_cast<const float4*>(cs + f0), c1 = *reinterpret_cast<const float4*>(cs + f0 + 4);
+        const float rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const float cc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
         for (int v = 0; v < 8; ++v) {
-            const float r = rs[f0 + v], c = cs[f0 + v];
+            const float r = rr[v], c = cc[v];
             float best = fmaf(y[0][v], r, c);
             uint32_t arg = 0;
 #pragma unroll
@@ -354,8 +367,13 @@ smallconv_fwd_fast_kernel(Planes P, RowMap rm, const float* __restrict__ W, cons
             if (v < 4) a0 |= arg << (8 * v); else a1 |= arg << (8 * (v - 4));
         }
         const long long ro = (long long)b * rm.Mo + mo;
-        st4(out + ro * Fout + f0, make_float4(o[0], o[1], o[2], o[3]));
-        st4(out + ro * Fout + f0 + 4, make_float4(o[4], o[5], o[6], o[7]));
+        if (wide) {
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         :: "l"(out + ro * Fout + f0), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+        } else {
+            st4(out + ro * Fout + f0, make_float4(o[0], o[1], o[2], o[3]));
+            st4(out + ro * Fout + f0 + 4, make_float4(o[4], o[5], o[6], o[7]));
+        }
         if (argmax) *reinterpret_cast<uint2*>(argmax + ro * Fout + f0) = make_uint2(a0, a1);
     }
 }
@@ -383,15 +401,22 @@ smallconv_bwd_fast_kernel(Planes P, RowMap rm, const float* __restrict__ bias, c
 #pragma unroll
     for (int v = 0; v < 8; ++v) { s1[v] = 0.f; s2[v] = 0.f; bs[v] = bias ? __ldg(bias + f0 + v) : 0.f; }
     const int Fin = P.Fin;
+    const bool wide = (((uintptr_t)dout | (uintptr_t)out) & 31) == 0;
     for (long long t = (long long)blockIdx.x * rows_per_block + rl; t < Rout; t += (long long)gridDim.x * rows_per_block) {
         int b, mo;
         rm.decode(t, b, mo);
         const long long ro = (long long)b * rm.Mo + mo;
-        const float4 d0 = ldg4(dout + ro * Fout + f0), d1 = ldg4(dout + ro * Fout + f0 + 4);
-        const float4 o0 = ldg4(out + ro * Fout + f0), o1 = ldg4(out + ro * Fout + f0 + 4);
+        float d[8], o[8];
+        if (wide) {                                      // one 32-byte load per lane and tensor: half the wavefronts
+            ldg8(dout + ro * Fout + f0, d);
+            ldg8(out + ro * Fout + f0, o);
+        } else {
+            const float4 d0 = ldg4(dout + ro * Fout + f0), d1 = ldg4(dout + ro * Fout + f0 + 4);
+            const float4 o0 = ldg4(out + ro * Fout + f0), o1 = ldg4(out + ro * Fout + f0 + 4);
+            d[0] = d0.x; d[1] = d0.y; d[2] = d0.z; d[3] = d0.w; d[4] = d1.x; d[5] = d1.y; d[6] = d1.z; d[7] = d1.w;
+            o[0] = o0.x; o[1] = o0.y; o[2] = o0.z; o[3] = o0.w; o[4] = o1.x; o[5] = o1.y; o[6] = o1.z; o[7] = o1.w;
+        }
         const uint2 ab = __ldg(reinterpret_cast<const uint2*>(argmax + ro * Fout + f0));
-        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        const float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
         float x[4][Q];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -457,23 +482,29 @@ __global__ void smallconv_bwd_finalize_kernel(const double* __restrict__ acc, co
     if (q == 0 && dbias) dbias[f] = (float)S1;
 }
 
-// out[m][b][f] = x[b][m][f]: tiles of TM vertices staged through shared memory, coalesced on both sides
+// out[m][b][f] = x[b][m][f]: tiles of TM vertices staged through shared memory, coalesced on both sides.  Index arithmetic by
+// shifts when B * F and F are powers of two (cosmo: 16, 1): the div / mod per element made this copy issue-bound (30 us for
+// 34 MB of traffic).
+template <bool POW2>
 __global__ void __launch_bounds__(256)
-interleave_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int M, int F, int TM)
+interleave_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int M, int F, int TM, int lgBF, int lgF)
 {
     extern __shared__ float tile[];                  // [B][TM*F + 1]
     const int m0 = blockIdx.x * TM;
     const int tm = min(TM, M - m0);
     const int w = tm * F, pitch = TM * F + 1;
-    for (int i = threadIdx.x; i < B * w; i += blockDim.x) {
-        const int b = i / w, r = i - b * w;
-        tile[b * pitch + r] = __ldg(x + ((long long)b * M + m0) * F + r);
+    for (int b = 0; b < B; ++b) {
+        const float* src = x + ((long long)b * M + m0) * F;
+        for (int r = threadIdx.x; r < w; r += blockDim.x) tile[b * pitch + r] = __ldg(src + r);
     }
     __syncthreads();
+    float* dst = out + (long long)m0 * B * F;
+    const int BF = B * F;
     for (int i = threadIdx.x; i < B * w; i += blockDim.x) {
-        const int m = i / (B * F), r = i - m * (B * F);
-        const int b = r / F, f = r - b * F;
-        out[(long long)m0 * B * F + i] = tile[b * pitch + m * F + f];
+        int m, b, f;
+        if (POW2) { m = i >> lgBF; const int r = i & (BF - 1); b = r >> lgF; f = r & (F - 1); }
+        else { m = i / BF; const int r = i - m * BF; b = r / F; f = r - b * F; }
+        dst[i] = tile[b * pitch + m * F + f];
     }
 }
 
@@ -597,11 +628,18 @@ extern "C" int dsb200_smallconv_bwd_finalize(const double* acc, const double* gr
 extern "C" int dsb200_interleave(const float* x, float* out, int B, int M, int F, void* stream)
 {
     DSB_REQUIRE(x && out && B > 0 && M > 0 && F > 0 && x != out, "interleave: bad arguments");
-    int TM = 8192 / (B * F);
+    int TM = 4096 / (B * F);                              // 16 KB tiles: several CTAs per SM
     if (TM < 1) TM = 1;
     if (TM > M) TM = M;
     const size_t smem = (size_t)B * (TM * F + 1) * sizeof(float);
     DSB_REQUIRE(smem <= 48 * 1024, "interleave: B*F too large");
-    interleave_kernel<<<(M + TM - 1) / TM, 256, smem, STREAM>>>(x, out, B, M, F, TM);
+    const int BF = B * F;
+    int lgBF = 0, lgF = 0;
+    while ((1 << lgBF) < BF) ++lgBF;
+    while ((1 << lgF) < F) ++lgF;
+    if ((1 << lgBF) == BF && (1 << lgF) == F)
+        interleave_kernel<true><<<(M + TM - 1) / TM, 256, smem, STREAM>>>(x, out, B, M, F, TM, lgBF, lgF);
+    else
+        interleave_kernel<false><<<(M + TM - 1) / TM, 256, smem, STREAM>>>(x, out, B, M, F, TM, 0, 0);
     DSB_LAUNCH_CHECK();
 }
