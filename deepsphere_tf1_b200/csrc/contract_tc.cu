@@ -74,6 +74,8 @@ constexpr int kWarpTma = 0, kWarpMma = 1, kWarpSplit0 = 2, kWarpEpi0 = 10;   // 
 struct alignas(64) RowGemmParams {
     CUtensorMap tmA0;          // plane 0 (x0, or dY for the data gradient)
     CUtensorMap tmAk;          // planes 1..K-1 (forward only)
+    CUtensorMap tmOut;         // (unused: a tensor-store epilogue was row-rate bound)
+    int epi_tma, epi_cols;     // data gradient: stage 128 rows x epi_cols (= Fin) of a plane in shared memory, 1-D bulk store
     const float* W;            // [Fin*K, Fout], row = fi*K + k
     const float* wpack;        // pre-split weights in the shared-memory image layout (pack_w_kernel), or NULL
     float* out;                // Y [R, Fout]  |  G [K][R][Fin]
@@ -179,6 +181,8 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* red = reinterpret_cast<float*>(tmem_slot + 2);           // [2][256] batch-norm partial sums
+    // data-gradient epilogue staging: [K planes][128 rows][epi_cols] fp32
+    uint8_t* epi = smem + ((((size_t)(reinterpret_cast<uint8_t*>(red + 2 * 256) - smem)) + 1023) & ~(size_t)1023);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full_tma + s, 1); mbar_init(full_mma + s, 128); mbar_init(empty + s, 1); }
@@ -335,7 +339,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
     } else {
         // ======================= epilogue =======================
         const int q = warp & 3;                                     // TMEM lane quarter of this warp
-        int ti = 0;
+        int ti = 0, ebox = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++ti) {
             const int a = p.acc_stages == 2 ? (ti & 1) : 0;
             const uint32_t use = (uint32_t)(p.acc_stages == 2 ? (ti >> 1) : ti);
@@ -401,6 +405,54 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
                         if (c0 + lane < p.Fout) { atomicAdd(red + c0 + lane, v[0]); atomicAdd(red + 256 + c0 + lane, w[0]); }
                     }
                 }
+            } else if (p.epi_tma) {
+                // A lane owns a row: written straight to global memory, every store instruction of the warp touches 32
+                // different 128-byte lines (26 / 33 us of the 99 / 83 us at cosmo layers 2 / 3 went into that).  The 128 rows of
+                // one output plane of a tile are CONTIGUOUS in global memory (planes are [R][Fin] row-major), so the four
+                // epilogue warps stage them row-major in shared memory and one lane stores the plane with a 1-D
+                // cp.async.bulk (no load/store-pipe wavefronts for global memory; a TMA TENSOR store was tried first and is
+                // limited to ~4 ns per box row).  A lane writes its four 16-byte chunks in an order rotated by its row index,
+                // which spreads the lanes of a quarter warp over the bank lines (conflict-free at 64-byte rows, 2-way at
+                // 128).  The warps share the issuing (a bulk copy costs its issuing warp ~0.3 us).  Per-plane fences and
+                // barriers made the epilogue the bottleneck (120 us), so all K planes of the tile are staged first.
+                const int bc = p.epi_cols;                              // = Fin = 16 (64-byte rows)
+                const uint32_t buf_bytes = (uint32_t)kTileM * (uint32_t)bc * 4u;      // one plane of the tile
+                const int ew = warp - kWarpEpi0, rloc = q * 32 + lane;
+                const int rot = (rloc >> 1) & 3;
+                const long long plane = p.R * (long long)p.Fin;
+                const long long rows_left = p.R - (long long)t * kTileM;
+                const uint32_t nbytes = (uint32_t)(rows_left < kTileM ? rows_left : kTileM) * (uint32_t)bc * 4u;
+                // all planes of the tile are staged, then stored: one fence and two barriers per tile
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // my stores of the previous tile
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                for (int c0 = 0; c0 + 16 <= p.Nreal; c0 += 16) {
+                    float hi[16], lo[16];
+                    tmem_ld16(tbase + c0, hi);
+                    tmem_ld16(tbase + p.Npad + c0, lo);
+                    tmem_ld_wait();
+                    const int kq = (p.n0 + c0) / bc;                    // Fin = 16: one round = one plane
+                    float4 v0 = make_float4(hi[0] + lo[0], hi[1] + lo[1], hi[2] + lo[2], hi[3] + lo[3]);
+                    float4 v1 = make_float4(hi[4] + lo[4], hi[5] + lo[5], hi[6] + lo[6], hi[7] + lo[7]);
+                    float4 v2 = make_float4(hi[8] + lo[8], hi[9] + lo[9], hi[10] + lo[10], hi[11] + lo[11]);
+                    float4 v3 = make_float4(hi[12] + lo[12], hi[13] + lo[13], hi[14] + lo[14], hi[15] + lo[15]);
+                    if (rot & 1) { const float4 tmp = v0; v0 = v1; v1 = v2; v2 = v3; v3 = tmp; }
+                    if (rot & 2) { float4 tmp = v0; v0 = v2; v2 = tmp; tmp = v1; v1 = v3; v3 = tmp; }
+                    float4* rowp = reinterpret_cast<float4*>(epi + (size_t)kq * buf_bytes + (size_t)rloc * bc * 4);
+                    rowp[(0 + rot) & 3] = v0;                           // instruction j carries chunk (j + rot) mod 4
+                    rowp[(1 + rot) & 3] = v1;
+                    rowp[(2 + rot) & 3] = v2;
+                    rowp[(3 + rot) & 3] = v3;
+                }
+                fence_proxy_async();
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (lane == 0 && !p.nostore) {
+                    for (int kq = ew; kq < p.K; kq += 4) {
+                        float* dst = p.out + kq * plane + (long long)t * kTileM * p.Fin;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                     :: "l"(dst), "r"(smem_u32(epi + (size_t)kq * buf_bytes)), "r"(nbytes) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             } else {
                 const long long plane = p.R * (long long)p.Fin;
                 const bool wide = (((uintptr_t)p.out | (uintptr_t)(plane * 4)) & 31) == 0;   // 32-byte stores possible
@@ -443,6 +495,8 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
             tc_fence_before();
             mbar_arrive(acc_empty + a);
         }
+        if (MODE == MODE_BWD_DATA && p.epi_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        (void)ebox;
         if (SUMS) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int e = threadIdx.x - kWarpEpi0 * 32; e < p.Fout; e += 128) {
@@ -468,18 +522,19 @@ static int env_int(const char* name, int dflt)
 }
 
 // Shared-memory plan; returns false if the shape does not fit the tensor-core path.
-static bool plan_rowgemm_n(int red_per_plane, int planes, int Npad, bool can_stream, int ctas, RowGemmPlan* pl);
+static bool plan_rowgemm_n(int red_per_plane, int planes, int Npad, bool can_stream, int ctas, RowGemmPlan* pl, size_t reserve);
 
 // Try `ctas` CTAs per SM first (independent pipelines hide the TMA -> split -> MMA -> epilogue latency chain of a
 // CTA), fall back to one.
-static bool plan_rowgemm(int red_per_plane, int planes, int Npad, bool can_stream, int ctas, RowGemmPlan* pl)
+// `reserve`: bytes kept free after the pipeline's own layout (epilogue staging of the data gradient)
+static bool plan_rowgemm(int red_per_plane, int planes, int Npad, bool can_stream, int ctas, RowGemmPlan* pl, size_t reserve = 0)
 {
     for (; ctas >= 1; --ctas)
-        if (plan_rowgemm_n(red_per_plane, planes, Npad, can_stream && ctas == 1, ctas, pl) && (ctas == 1 || pl->nstages >= 3)) return true;
+        if (plan_rowgemm_n(red_per_plane, planes, Npad, can_stream && ctas == 1, ctas, pl, reserve) && (ctas == 1 || pl->nstages >= 3)) return true;
     return false;
 }
 
-static bool plan_rowgemm_n(int red_per_plane, int planes, int Npad, bool can_stream, int ctas, RowGemmPlan* pl)
+static bool plan_rowgemm_n(int red_per_plane, int planes, int Npad, bool can_stream, int ctas, RowGemmPlan* pl, size_t reserve)
 {
     if (red_per_plane % 8) return false;
     pl->kc = red_per_plane % 32 == 0 ? 32 : red_per_plane % 16 == 0 ? 16 : 8;
@@ -490,7 +545,7 @@ static bool plan_rowgemm_n(int red_per_plane, int planes, int Npad, bool can_str
     pl->G = 32 / pl->kc;                                   // 16 KB of activations per stage
     if (pl->G > pl->nkb) pl->G = pl->nkb;
     pl->wbytes = (size_t)pl->nkb * 2 * Npad * pl->kc * 4;
-    const size_t fixed = 1024 /*align*/ + 3 * kMaxStages * 8 + 4 * 8 + 16 + 2 * 256 * 4 + 64;
+    const size_t fixed = 1024 /*align*/ + 3 * kMaxStages * 8 + 4 * 8 + 16 + 2 * 256 * 4 + 64 + reserve;
     const size_t budget = (size_t)(227 * 1024) / ctas - (ctas > 1 ? 1024 : 0);
     const size_t min_smem = (size_t)(227 * 1024) / (ctas + 1) + 1024;     // never more CTAs per SM than planned (TMEM)
     pl->ctas = ctas;
@@ -594,6 +649,7 @@ int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, 
     if (K > 1) { if (make_tmap_f32(&p.tmAk, xk, Fin, R, K - 1, pl.kc, kTileM, pl.swz, true)) return 1; }
     else p.tmAk = p.tmA0;
     p.W = W; p.out = Y; p.bn_sums = bn_sums; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
+    p.epi_tma = 0; p.epi_cols = 0; p.tmOut = p.tmA0;
     p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.G = pl.G; p.Npad = Npad; p.Nreal = Fout; p.n0 = 0; p.swz = pl.swz;
     p.nstages = pl.nstages; p.acc_stages = pl.acc_stages; p.wstream = pl.wstream;
     p.ntiles = (int)((R + kTileM - 1) / kTileM);
@@ -615,12 +671,22 @@ int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R,
     RowGemmPlan pl;
     int ctas = env_int("DSB200_RG_CTAS", 2);
     if (ctas > rowgemm_max_ctas<MODE_BWD_DATA, false>()) ctas = rowgemm_max_ctas<MODE_BWD_DATA, false>();
-    if (!plan_rowgemm(Fout, 1, NB, workspace != nullptr, ctas, &pl)) return 1;
+    // bulk-store epilogue (experiment, off by default: DSB200_RG_BULK_STORE=1): planes of 16 columns (cosmo layer 2), all K
+    // planes of a 128-row tile staged at once.  Measured at layer 2: 117 us against 99 us with direct 32-byte stores -- the
+    // staging alone costs 10 us and the single buffer makes every tile wait for the previous tile's stores to be read.
+    const int epi_cols = (Fin == 16 && nb == 1 && K <= 6 && (((uintptr_t)G) & 15) == 0 && env_int("DSB200_RG_BULK_STORE", 0)) ? Fin : 0;
+    const size_t reserve = epi_cols ? 1024 + (size_t)K * kTileM * epi_cols * 4 : 0;
+    bool epi_tma = epi_cols != 0;
+    if (!epi_tma || !plan_rowgemm(Fout, 1, NB, workspace != nullptr, ctas, &pl, reserve)) {
+        epi_tma = false;
+        if (!plan_rowgemm(Fout, 1, NB, workspace != nullptr, ctas, &pl)) return 1;
+    }
     for (int b = 0; b < nb; ++b) {
         RowGemmParams p;
         p.tmem_cols = pl.tmem_cols;
         if (make_tmap_f32(&p.tmA0, dY, Fout, R, 1, pl.kc, kTileM, pl.swz, false)) return 1;
         p.tmAk = p.tmA0;
+        p.epi_tma = epi_tma ? 1 : 0; p.epi_cols = epi_cols; p.tmOut = p.tmA0;
         p.W = W; p.out = G; p.bn_sums = nullptr; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
         p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.G = pl.G; p.Npad = NB; p.n0 = b * NB;
         p.Nreal = (Q - p.n0 < NB) ? (Q - p.n0) : NB;
