@@ -615,7 +615,7 @@ __device__ __forceinline__ float block_sum(float v, float* sh)
 
 __global__ void __launch_bounds__(256)
 softmax_ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, float* __restrict__ dlogits,
-                  float* loss_out, long long R, int C, float gscale)
+                  float* loss_out, long long R, int C, float gscale, const float* __restrict__ cw)
 {
     __shared__ float sh[8];
     float local = 0.f;
@@ -629,10 +629,11 @@ softmax_ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ 
         for (int c = 0; c < C; ++c) se += expf(__ldg(lp + c) - mx);
         const float lse = mx + logf(se);
         const int lab = __ldg(labels + r);
-        local += lse - __ldg(lp + lab);
+        const float wr = cw ? __ldg(cw + lab) : 1.f;                     // class weight of the row (models.py:795-802)
+        local = fmaf(wr, lse - __ldg(lp + lab), local);
         if (dlogits) {
             float* dp = dlogits + r * C;
-            const float k = gscale * invR;
+            const float k = gscale * invR * wr;
             for (int c = 0; c < C; ++c) dp[c] = (expf(__ldg(lp + c) - lse) - (c == lab ? 1.f : 0.f)) * k;
         }
     }
@@ -973,7 +974,15 @@ extern "C" int dsb200_softmax_ce(const float* logits, const int32_t* labels, flo
                                  long long R, int C, float grad_scale, void* stream)
 {
     DSB_REQUIRE(logits && labels && loss_out && R > 0 && C > 0, "softmax_ce: bad arguments");
-    softmax_ce_kernel<<<grid_for(R, 256, 4), 256, 0, STREAM>>>(logits, labels, dlogits, loss_out, R, C, grad_scale);
+    softmax_ce_kernel<<<grid_for(R, 256, 4), 256, 0, STREAM>>>(logits, labels, dlogits, loss_out, R, C, grad_scale, nullptr);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_softmax_ce_weighted(const float* logits, const int32_t* labels, const float* class_weights, float* dlogits,
+                                          float* loss_out, long long R, int C, float grad_scale, void* stream)
+{
+    DSB_REQUIRE(logits && labels && class_weights && loss_out && R > 0 && C > 0, "softmax_ce_weighted: bad arguments");
+    softmax_ce_kernel<<<grid_for(R, 256, 4), 256, 0, STREAM>>>(logits, labels, dlogits, loss_out, R, C, grad_scale, class_weights);
     DSB_LAUNCH_CHECK();
 }
 

@@ -16,8 +16,8 @@ Differences from the reference that a user sees (also listed in DESIGN.md):
   * `tf_dataset` may be any Python iterator of `(data, labels)` batches;
   * checkpoints are `torch.save` files `checkpoints/<dir_name>/model-<step>.pt` keyed by the
     reference's variable names (`conv1/weights`, `conv1/batch_normalization/moving_mean`, ...);
-  * `conv='monomials'`, `statistics='histogram'`, `dropFilt < 1`, `extra_loss`, `weighted`,
-    equiangular sampling: NotImplementedError (outside the hot path).
+  * `statistics='histogram'`, `dropFilt < 1`, `extra_loss`, equiangular sampling: NotImplementedError (outside the
+    hot path).  `conv='monomials'` and `weighted=True` are supported.
 """
 import glob
 import json
@@ -89,6 +89,9 @@ class _ParamStore(object):
         self.has_reg = bool(regularization) and n_weights > 0
 
 
+CLASS_WEIGHTS = (0.34130685, 318.47388343, 14.93759951)     # `weighted=True` (models.py:796)
+
+
 class _ChebStage(object):
     """filter -> [batch norm] -> [bias] -> [activation] -> [pool]   (models.py:1229-1243;
     decoder up-conv / de-conv / out-conv, models.py:1304-1341, with the unused parts off)."""
@@ -101,6 +104,9 @@ class _ChebStage(object):
         self.bn, self.has_bias, self.act = bn, bias, act
         self.p, self.pool = p, pool            # HEALPix pooling over p consecutive vertices
         self.keep = keep                       # icosahedral "pooling": keep the first `keep` vertices
+        self.mono = getattr(model, 'conv', 'chebyshev5') == 'monomials'       # basis x, Lx, L^2 x, ... (models.py:1085-1120)
+        if self.mono and self.sg is not None:
+            raise NotImplementedError("conv='monomials' is not available in the vertex-sharded mode")
         std = 1 / np.sqrt(Fin * (K + 0.5) / 2)                             # models.py:1080-1083
         model._P.add(scope + '/weights', (Fin * K, Fout), _truncated_normal(model._rs, (Fin * K, Fout), std), std)
         if bn:
@@ -125,7 +131,7 @@ class _ChebStage(object):
             return self._forward_small(x, W, training, save)
         if self.sg is not None and self.K > 1:
             return self._forward_sharded(x, W, training, save)
-        basis = ops.cheb_basis(self.graph, x, self.K)                      # models.py:1049-1061
+        basis = ops.cheb_basis(self.graph, x, self.K, self.mono)           # models.py:1049-1061 / 1094-1103
         sums = None
         if self.bn and training:
             sums = m._zeros(2 * self.Fout)
@@ -159,7 +165,7 @@ class _ChebStage(object):
         shape = (B, M, Fin)
         # sample-interleaved layout [M, B, Fin]: the sparse products gather B*Fin contiguous floats
         x = ops.interleave(x)
-        basis = ops.cheb_basis(self.graph, x.view(1, M, B * Fin), self.K)
+        basis = ops.cheb_basis(self.graph, x.view(1, M, B * Fin), self.K, self.mono)
         count = float(B * M * m.world_size)
         mean = rstd = gram = None
         if self.bn:
@@ -330,7 +336,7 @@ class _ChebStage(object):
             return None
         W = m._P.views[self.scope + '/weights']
         G = ops.contract_bwd_data(dy, W, self.K, Fin)
-        return ops.cheb_basis_bwd(self.graph, G)
+        return ops.cheb_basis_bwd(self.graph, G, self.mono)
 
 
 class _FcStage(object):
@@ -685,8 +691,9 @@ class cgcnn(base_model):
                              'layer if no fully connected layer follows.')
         if mask and not isinstance(mask, list):
             raise ValueError('Must provide a list of mask for training and validation.')
-        if conv != 'chebyshev5':
+        if conv not in ('chebyshev5', 'monomials'):                        # getattr(self, conv), models.py:1017
             raise NotImplementedError("conv='{}' is outside the ChebConv hot path".format(conv))
+        self.conv = conv
         if pool not in ('max', 'average'):
             raise AttributeError("'cgcnn' object has no attribute 'pool_{}'".format(pool))
         if activation not in ACT:
@@ -695,8 +702,9 @@ class cgcnn(base_model):
             if statistics == 'histogram':
                 raise NotImplementedError('the learned histogram layer is outside the hot path')
             raise ValueError('Unknown statistical layer {}'.format(statistics))
-        if dropFilt < 1 or extra_loss or weighted:
-            raise NotImplementedError('dropFilt / extra_loss / weighted are outside the hot path')
+        if dropFilt < 1 or extra_loss:
+            raise NotImplementedError('dropFilt / extra_loss are outside the hot path')
+        self.weighted = bool(weighted)
         if self.sampling == 'equiangular':
             raise NotImplementedError('equiangular sampling is outside the hot path')
         if np.dtype(dtype) != np.float32:
@@ -1048,7 +1056,14 @@ class cgcnn(base_model):
                                                                                        tuple(labels.shape)))
             d = ops.mse(pred, tgt, self._loss, gs, need_grad)
             return d.reshape(logits.shape) if need_grad else None
-        return ops.softmax_ce(logits, labels, self._loss, gs, need_grad)
+        cw = None
+        if self.weighted:                                  # models.py:795-802: hard-coded weights of 3 classes
+            if logits.shape[-1] != 3:
+                raise ValueError('weighted cross-entropy is defined for 3 classes (models.py:793-796)')
+            if getattr(self, '_class_w', None) is None:
+                self._class_w = torch.tensor(CLASS_WEIGHTS, dtype=torch.float32, device=self.device)
+            cw = self._class_w
+        return ops.softmax_ce(logits, labels, self._loss, gs, need_grad, cw)
 
     def _loss_only(self, logits, labels):
         self._loss.zero_()

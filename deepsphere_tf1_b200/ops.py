@@ -132,12 +132,17 @@ def cheb_tiled_step(graph, x, y=None, z=None, u=None, out1=None, out2=None, coef
     return out1, out2
 
 
-def cheb_basis(graph, x, K):
-    """Orders 1..K-1 of the Chebyshev basis of x (models.py:1049-1061) as [K-1, B, M, F]."""
+def cheb_basis(graph, x, K, monomial=False):
+    """Orders 1..K-1 of the Chebyshev basis of x (models.py:1049-1061) as [K-1, B, M, F]; `monomial`: the basis
+    x, Lx, L^2 x, ... of `cgcnn.monomials` instead (models.py:1094-1103)."""
     if K == 1:
         return None
     B, M, F = x.shape
     basis = _new((K - 1, B, M, F), x)
+    if monomial:
+        for k in range(1, K):                                                  # X_k = L X_(k-1)
+            spmm(graph, x if k == 1 else basis[k - 2], out=basis[k - 1])
+        return basis
     plan = _tiles(graph, 'fwd', F)
     if plan is not None:
         call('cheb_basis_tiled', *plan.args(), B, M, F, K, x, basis)
@@ -157,9 +162,14 @@ def cheb_basis(graph, x, K):
     return basis
 
 
-def cheb_basis_bwd(graph, G):
-    """Adjoint of the recurrence: G [K, B, M, F] -> dLoss/dx [B, M, F] (G is overwritten on the gather path)."""
+def cheb_basis_bwd(graph, G, monomial=False):
+    """Adjoint of the recurrence: G [K, B, M, F] -> dLoss/dx [B, M, F] (G is overwritten on the gather path).
+    `monomial`: adjoint of X_k = L X_(k-1), i.e. A_k = G_k + L^T A_(k+1)."""
     K, B, M, F = G.shape
+    if monomial:
+        for k in range(K - 2, -1, -1):
+            spmm(graph, G[k + 1], G[k], None, out=G[k], alpha=1.0, beta=1.0, transpose=True)
+        return G[0]
     plan = _tiles(graph, 'bwd', F)
     if plan is not None and K >= 2:
         S = _new((K, B, M, F), G)
@@ -343,11 +353,15 @@ def fc_bwd(x, W, y, dy, dW, db, act, need_dx=True):
     return dx
 
 
-def softmax_ce(logits, labels, loss_out, grad_scale=1.0, need_grad=True):
+def softmax_ce(logits, labels, loss_out, grad_scale=1.0, need_grad=True, class_weights=None):
+    """Mean sparse-softmax cross-entropy into loss_out (models.py:790-804); `class_weights` [C]: the `weighted` variant."""
     C = logits.shape[-1]
     R = logits.numel() // C
     dlogits = torch.empty_like(logits) if need_grad else None
-    call('softmax_ce', logits, labels, dlogits, loss_out, R, C, grad_scale)
+    if class_weights is not None:
+        call('softmax_ce_weighted', logits, labels, class_weights, dlogits, loss_out, R, C, grad_scale)
+    else:
+        call('softmax_ce', logits, labels, dlogits, loss_out, R, C, grad_scale)
     return dlogits
 
 

@@ -277,6 +277,10 @@ int dsb200_fc_bwd(const float* x, const float* W, const float* y, const float* d
  * MSE: pred/target [n]. */
 int dsb200_softmax_ce(const float* logits, const int32_t* labels, float* dlogits, float* loss_out,
                       long long R, int C, float grad_scale, void* stream);
+/* class-weighted variant (`weighted=True`, models.py:795-802): row r counts class_weights[labels[r]] times, the mean is
+ * still over R rows */
+int dsb200_softmax_ce_weighted(const float* logits, const int32_t* labels, const float* class_weights, float* dlogits,
+                               float* loss_out, long long R, int C, float grad_scale, void* stream);
 int dsb200_mse(const float* pred, const float* target, float* dpred, float* loss_out,
                long long n, float grad_scale, void* stream);
 /* softmax probabilities / argmax (models.py:750-763); probs or pred may be NULL */

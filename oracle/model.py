@@ -18,7 +18,7 @@ class OracleCgcnn:
     def __init__(self, L, F, K, p, batch_norm, M, num_feat_in=1, conv='chebyshev5', pool='max',
                  activation='relu', statistics=None, Fseg=None, regularization=0, dropout=1,
                  regression=False, dense=False, sampling='healpix', dtype=torch.float32, seed=2,
-                 finest_vertices=10 * 4 ** 5 + 2):
+                 finest_vertices=10 * 4 ** 5 + 2, weighted=False):
         if not len(L) == len(F) == len(K) == len(p) == len(batch_norm):          # models.py:937-940
             raise ValueError('Wrong specification of the convolutional layers')
         self.Ls = [ops.sparse_to_torch(l, dtype) for l in L]
@@ -26,7 +26,8 @@ class OracleCgcnn:
         self.F, self.K, self.p, self.batch_norm, self.M = F, K, p, batch_norm, M
         self.Fseg, self.regularization, self.dropout = Fseg, regularization, dropout
         self.regression, self.dense, self.sampling = regression, dense, sampling
-        self.conv = getattr(ops, conv)
+        self.conv = getattr(ops, conv)                                            # models.py:1017
+        self.weighted = weighted
         self.pool_kind, self.act, self.stat = pool, ops.ACTIVATIONS[activation], statistics
         self.dtype = dtype
         self.num_feat_in = num_feat_in
@@ -173,7 +174,7 @@ class OracleCgcnn:
     # ---- loss / gradients / step ----------------------------------------------------------
     def loss(self, logits, labels, P):
         wstd = [(P[k], self.std[k]) for k in self.params if k in self.std]
-        return ops.loss(logits, labels, self.regression, wstd, self.regularization)
+        return ops.loss(logits, labels, self.regression, wstd, self.regularization, self.weighted)
 
     def loss_and_grads(self, x, labels, training=True, drop_masks=None):
         """Forward + loss + autograd gradients w.r.t. every trainable variable."""

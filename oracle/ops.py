@@ -140,7 +140,10 @@ ACTIVATIONS = {
 }
 
 
-def loss(logits, labels, regression, weights_and_std, regularization):
+CLASS_WEIGHTS = (0.34130685, 318.47388343, 14.93759951)     # models.py:796 (hard-coded, 3 classes)
+
+
+def loss(logits, labels, regression, weights_and_std, regularization, weighted=False):
     """models.py:777-820 (cross-entropy / MSE + regularization * sum_i(l2_loss(W_i)/std_i^2)/sum_i size_i).
     `weights_and_std` = [(W_i, std_i)] in creation order (models.py:862-869)."""
     if regression:
@@ -149,6 +152,10 @@ def loss(logits, labels, regression, weights_and_std, regularization):
     else:
         C = logits.shape[-1]
         ce = TF.cross_entropy(logits.reshape(-1, C), labels.reshape(-1).long(), reduction='none')
+        if weighted:                                                       # models.py:795-802: one_hot(labels, 3) @ weights^T
+            if C != 3:
+                raise ValueError('weighted cross-entropy is defined for 3 classes')
+            ce = ce * torch.tensor(CLASS_WEIGHTS, dtype=ce.dtype)[labels.reshape(-1).long()]
         data_loss = ce.mean()
     n_weights = sum(int(np.prod(W.shape)) for W, _ in weights_and_std)
     reg = sum(((W ** 2).sum() / 2) / std ** 2 for W, std in weights_and_std) / n_weights

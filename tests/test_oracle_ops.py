@@ -73,3 +73,31 @@ def test_initial_loss_is_ln2_for_two_classes():
     labels = torch.arange(16) % 2
     _, ce = oops.loss(logits, labels, False, [(torch.ones(2, 2), 1.0)], 0.0)
     assert float(ce) == pytest.approx(np.log(2), rel=1e-6)
+
+
+def test_monomials_are_powers_of_L_on_eigenvectors():
+    """cgcnn.monomials (models.py:1085-1120): the k-th basis plane of an eigenvector v is lambda^k v."""
+    L = healpix_L(2)
+    lam, V = np.linalg.eigh(L.toarray().astype(np.float64))
+    Lt = oops.sparse_to_torch(L, torch.float64)
+    K = 5
+    for idx in (1, len(lam) - 1):
+        v = torch.from_numpy(V[:, idx]).reshape(1, -1, 1)
+        y = oops.monomials(v, Lt, torch.eye(K, dtype=torch.float64), K)          # y[..., k] = L^k v
+        for k in range(K):
+            assert torch.allclose(y[0, :, k], lam[idx] ** k * v[0, :, 0], atol=1e-6)   # (L is fp32, symmetric to 1 ulp)
+
+
+def test_weighted_cross_entropy_matches_its_definition():
+    """models.py:795-802: ce_r * (one_hot(label_r, 3) . weights), averaged over all rows."""
+    rs = np.random.RandomState(0)
+    logits = torch.from_numpy(rs.randn(7, 3))
+    labels = torch.from_numpy(rs.randint(0, 3, size=7))
+    w = np.array(oops.CLASS_WEIGHTS)
+    lse = torch.logsumexp(logits, dim=1)
+    ce = (lse - logits[torch.arange(7), labels]).numpy()
+    expect = float(np.mean(ce * w[labels.numpy()]))
+    got, _ = oops.loss(logits, labels, False, [(torch.zeros(1), 1.0)], 0.0, weighted=True)
+    assert float(got) == pytest.approx(expect, rel=1e-12)
+    with pytest.raises(ValueError):
+        oops.loss(torch.zeros(4, 5), torch.zeros(4, dtype=torch.long), False, [(torch.zeros(1), 1.0)], 0.0, weighted=True)

@@ -17,7 +17,7 @@ def _pair(L, sampling='healpix', seed=2, batch_size=4, finest=None, **kw):
     from deepsphere_tf1_b200 import models, optimizers
     from oracle.model import OracleCgcnn
     okw = {k: v for k, v in kw.items() if k in ('F', 'K', 'p', 'batch_norm', 'M', 'num_feat_in', 'pool', 'activation',
-                                                'statistics', 'Fseg', 'regularization', 'dropout', 'regression', 'dense')}
+                                                'statistics', 'Fseg', 'regularization', 'dropout', 'regression', 'dense', 'conv', 'weighted')}
     attrs = {'sampling': sampling}
     if finest is not None:
         okw['finest_vertices'] = finest
@@ -198,6 +198,39 @@ def test_cuda_graph_replay_matches_eager():
         _, l2 = graphed.train_step(x, labels)
         assert float(l1) == pytest.approx(float(l2), rel=1e-5)
     assert_close(graphed._P.w, eager._P.w, 1e-5, 'weights after graph replay')
+
+
+@pytest.mark.parametrize('pipelined', [False, True])
+def test_monomial_filters_classifier(pipelined, monkeypatch):
+    """conv='monomials' (models.py:1085-1120): basis x, Lx, L^2 x, ... instead of the Chebyshev recurrence; same weights
+    layout, same contraction.  Forward, every gradient (the adjoint A_k = G_k + L^T A_(k+1)) and three optimizer steps."""
+    from deepsphere_tf1_b200 import ops, utils
+    monkeypatch.setattr(ops, 'PIPE_MIN_ITEMS', 1 if pipelined else 1 << 30)
+    nsides = [16, 8, 4, 4]
+    L, p = utils.build_laplacians(nsides, new=False)
+    oracle, model = _pair(L, F=[16, 32, 8], K=[4, 3, 2], p=p, batch_norm=[True, True, False], M=[5], statistics='meanvar',
+                          conv='monomials', num_feat_in=2)
+    rs = np.random.RandomState(0)
+    x = rs.randn(4, L[0].shape[0], 2).astype(np.float32)
+    labels = np.random.RandomState(1).randint(0, 5, size=4).astype(np.int32)
+    _check_step(oracle, model, x, labels)
+
+
+def test_weighted_cross_entropy_dense_segmentation():
+    """weighted=True (models.py:795-802): per-pixel cross-entropy weighted by the hard-coded class weights of the climate
+    data set (3 classes), on a small encoder-decoder."""
+    L = [healpix_L(4), healpix_L(2), healpix_L(1)]
+    kw, opt = _momentum()
+    oracle, model = _pair(L, F=[8, 16, 16], K=[3, 3, 3], p=[4, 4, 1], batch_norm=[True, True, True], M=[], Fseg=3, dense=True,
+                          num_feat_in=4, pool='average', weighted=True, **kw)
+    rs = np.random.RandomState(0)
+    x = rs.randn(4, 192, 4).astype(np.float32)
+    labels = rs.choice(3, size=(4, 192), p=[0.9, 0.02, 0.08]).astype(np.int32)
+    _check_step(oracle, model, x, labels, opt=opt, rtol_after=2e-3)
+    # the weights are defined for 3 classes only
+    _, bad = _pair(L[:2], F=[8, 4], K=[3, 3], p=[4, 1], batch_norm=[True, True], M=[], statistics='mean', weighted=True)
+    with pytest.raises(ValueError):
+        bad.train_step(rs.randn(4, 192, 1).astype(np.float32), rs.randint(0, 4, size=4).astype(np.int32))
 
 
 @pytest.mark.parametrize('graphed', [False, True])

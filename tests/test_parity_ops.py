@@ -52,6 +52,28 @@ def test_cheb_basis_matches_oracle(dev, F, kind):
     assert_close(basis, _oracle_basis(L, x, K)[1:], RTOL, 'basis')
 
 
+@pytest.mark.parametrize('F', [3, 16])
+def test_monomial_basis_and_its_adjoint(dev, F):
+    """ops.cheb_basis(monomial=True): X_k = L X_(k-1) (models.py:1094-1103); its adjoint against the dense transpose."""
+    from deepsphere_tf1_b200 import ops
+    L = healpix_L(8)
+    g = _graph(L, dev)
+    K = 4
+    rs = np.random.RandomState(F)
+    x = torch.from_numpy(rs.randn(3, L.shape[0], F).astype(np.float32))
+    Ld = torch.from_numpy(L.toarray()).double()
+    planes = [x.double()]
+    for k in range(1, K):
+        planes.append(torch.einsum('ij,bjf->bif', Ld, planes[-1]))
+    basis = ops.cheb_basis(g, x.to(dev), K, monomial=True)
+    assert_close(basis, torch.stack(planes[1:]), RTOL, 'monomial basis')
+    G = torch.from_numpy(rs.randn(K, 3, L.shape[0], F).astype(np.float32))
+    A = G[K - 1].double()
+    for k in range(K - 2, -1, -1):
+        A = G[k].double() + torch.einsum('ji,bjf->bif', Ld, A)
+    assert_close(ops.cheb_basis_bwd(g, G.to(dev).clone(), monomial=True), A, RTOL, 'monomial adjoint')
+
+
 def test_spmm_general_form_and_aliasing(dev):
     from deepsphere_tf1_b200 import ops
     from oracle import ops as oops
@@ -460,6 +482,21 @@ def test_fc_losses_regulariser(dev):
     dp = ops.mse(hd.reshape(-1), t.to(dev).reshape(-1), loss)
     assert_close(loss, ((h.detach() - t) ** 2).mean().reshape(1), RTOL, 'mse')
     assert_close(dp.reshape(8, 7), 2 * (h.detach() - t) / 56, RTOL, 'dmse')
+
+
+def test_weighted_cross_entropy(dev):
+    from deepsphere_tf1_b200 import ops
+    from oracle import ops as oops
+    rs = np.random.RandomState(0)
+    logits = torch.from_numpy(rs.randn(2, 50, 3).astype(np.float32)).requires_grad_(True)
+    labels = torch.from_numpy(rs.randint(0, 3, size=(2, 50)).astype(np.int32))
+    ref, _ = oops.loss(logits, labels, False, [(torch.zeros(1), 1.0)], 0.0, weighted=True)
+    ref.backward()
+    loss = torch.zeros(1, device=dev)
+    cw = torch.tensor(oops.CLASS_WEIGHTS, dtype=torch.float32, device=dev)
+    d = ops.softmax_ce(logits.detach().to(dev), labels.to(dev), loss, 1.0, True, cw)
+    assert_close(loss, ref.detach().reshape(1), RTOL, 'weighted CE')
+    assert_close(d, logits.grad, RTOL, 'weighted CE gradient')
 
 
 @pytest.mark.parametrize('name', ['Adam', 'Momentum', 'SGD', 'RMSProp'])
