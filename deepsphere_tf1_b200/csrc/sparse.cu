@@ -6,7 +6,6 @@
 #include "common.cuh"
 #include <atomic>
 #include <stdlib.h>
-#include <stdlib.h>
 
 namespace dsb200 {
 
@@ -212,7 +211,6 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const float* v
         int TR = 32768 / (CB * 16);
         TR = TR < 32 ? 32 : TR > 128 ? 128 : TR;                   // 128-row tiles measured best on B200 (tools/sweep_spmm.py)
         if (const char* e = getenv("DSB200_SPMM_TR")) { const int v = atoi(e); if (v > 0) TR = v; }
-        if (const char* e = getenv("DSB200_SPMM_TR")) { const int v = atoi(e); if (v > 0) TR = v; }
         // keep enough tiles to fill the machine a few times over
         while (TR > 16 && (long long)B * ((M + TR - 1) / TR) * ((chunks + CB - 1) / CB) < 8LL * kNumSMs) TR >>= 1;
         if (passes <= 1) launch_rows<1>(rowptr, col, val, width, B, M, chunks, lg2, TR, CB, x, y, z, out, alpha, beta, gamma, s);
@@ -246,7 +244,10 @@ __global__ void ell_pack_kernel(const int32_t* __restrict__ col, const float* __
 }
 
 // Same tiling as spmm_rows_kernel (TR consecutive rows x column slab, LG lanes per row).  SB > 1: a tile spans SB
-// samples and a thread keeps the W records of its row in registers across them (W > 0 only).
+// samples and a thread keeps the W records of its row in registers across them (W > 0 only).  Variants with all W record
+// loads and all W gathers forced in flight, and with the tile's records staged in shared memory, were measured and
+// removed: every one of them lands on the same ~60 us at cosmo layer 2 (profiles/r01_exp_spmm_limits.txt) -- the limit is
+// the load/store pipe, which only the pipelined kernel (sparse_pipe.cu) relieves.
 template <int PASSES, int W, int SB>
 __global__ void __launch_bounds__(256)
 spmm_rec_kernel(const int2* __restrict__ rec, int width, int B, int M, int chunks, int lg2, int TR, int CB,
@@ -341,86 +342,6 @@ spmm_rec_kernel(const int2* __restrict__ rec, int width, int B, int M, int chunk
     }
 }
 
-__device__ __forceinline__ int2 ldg_nc_v2(const int2* p) {
-    int2 r; asm volatile("ld.global.nc.v2.s32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p)); return r;
-}
-__device__ __forceinline__ float4 ldg_nc_v4(const float4* p) {
-    float4 r; asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p)); return r;
-}
-
-// Variant with explicit memory-level parallelism (whole feature row per lane group, LG = F/4 lanes, F = 4..128 a power of
-// two; ELL width W = 7 / 9).  The compiler schedules spmm_rows / spmm_rec for 32 registers, which leaves TWO gathers in
-// flight per thread and chains record load -> gather -> record load ...: several memory round trips per row.  Here
-//   MODE 0: the W records come straight from global memory, all W loads issued first, then all W gathers (volatile asm
-//           keeps the order), then y / z;
-//   MODE 1: the records of the row tile are staged in shared memory once per CTA tile (coalesced), re-used for SB samples;
-//           all W gathers in flight, the weights are re-read from shared memory at FMA time (registers = the W gathers);
-//   MODE 2: as MODE 1 but compiler-scheduled loads.
-// NB = CTAs per SM the register budget is set for.
-template <int W, int MODE, int NB>
-__global__ void __launch_bounds__(256, NB)
-spmm_mlp_kernel(const int2* __restrict__ rec, int B, int M, int lg2, int TR, int SB,
-                const float4* __restrict__ x, const float4* y, const float4* z, float4* out,
-                float alpha, float beta, float gamma)
-{
-    extern __shared__ int2 srec[];                                // MODE >= 1: [W][TR]
-    const int chunks = 1 << lg2;
-    const int rpp = 256 >> lg2;                                   // rows per pass
-    const int rl = threadIdx.x >> lg2, lg = threadIdx.x & (chunks - 1);
-    const int rtiles = (M + TR - 1) / TR, bgroups = (B + SB - 1) / SB;
-    const int plane = M << lg2;
-    for (int t = blockIdx.x; t < rtiles * bgroups; t += gridDim.x) {
-        const int rt = t % rtiles, bg = t / rtiles;
-        const int m0 = rt * TR, mend = min(M, m0 + TR);
-        if (MODE >= 1) {
-            __syncthreads();                                      // previous tile's readers are done
-            for (int i = threadIdx.x; i < W * TR; i += 256) {
-                const int j = i / TR, r = i - j * TR;
-                if (m0 + r < M) srec[i] = __ldg(rec + (long long)j * M + m0 + r);
-            }
-            __syncthreads();
-        }
-        for (int s = 0; s < SB; ++s) {
-            const int b = bg * SB + s;
-            if (b >= B) break;
-            const float4* xb = x + (long long)b * plane + lg;
-            for (int r = rl; m0 + r < mend; r += rpp) {
-                const int m = m0 + r;
-                const long long o = (long long)b * plane + (m << lg2) + lg;
-                float4 v[W];
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (MODE == 0) {
-                    int2 rc[W];
-#pragma unroll
-                    for (int j = 0; j < W; ++j) rc[j] = ldg_nc_v2(rec + (long long)j * M + m);
-#pragma unroll
-                    for (int j = 0; j < W; ++j) v[j] = ldg_nc_v4(xb + (rc[j].x << lg2));
-#pragma unroll
-                    for (int j = 0; j < W; ++j) {
-                        const float w = __int_as_float(rc[j].y);
-                        a.x = fmaf(w, v[j].x, a.x); a.y = fmaf(w, v[j].y, a.y); a.z = fmaf(w, v[j].z, a.z); a.w = fmaf(w, v[j].w, a.w);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < W; ++j) {
-                        const int c = srec[j * TR + r].x;
-                        v[j] = (MODE == 1) ? ldg_nc_v4(xb + (c << lg2)) : __ldg(xb + (c << lg2));
-                    }
-#pragma unroll
-                    for (int j = 0; j < W; ++j) {
-                        const float w = __int_as_float(srec[j * TR + r].y);
-                        a.x = fmaf(w, v[j].x, a.x); a.y = fmaf(w, v[j].y, a.y); a.z = fmaf(w, v[j].z, a.z); a.w = fmaf(w, v[j].w, a.w);
-                    }
-                }
-                float4 res = make_float4(a.x * alpha, a.y * alpha, a.z * alpha, a.w * alpha);
-                if (y) { const float4 t4 = y[o]; res.x = fmaf(beta, t4.x, res.x); res.y = fmaf(beta, t4.y, res.y); res.z = fmaf(beta, t4.z, res.z); res.w = fmaf(beta, t4.w, res.w); }
-                if (z) { const float4 t4 = z[o]; res.x = fmaf(gamma, t4.x, res.x); res.y = fmaf(gamma, t4.y, res.y); res.z = fmaf(gamma, t4.z, res.z); res.w = fmaf(gamma, t4.w, res.w); }
-                out[o] = res;
-            }
-        }
-    }
-}
-
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
 constexpr int kNotQualified = -1000;
@@ -434,35 +355,6 @@ static int spmm_rec_launch(const int2* rec, int width, int B, int M, int F, cons
     if (F % 4 || (align & 15) || (long long)M * (F / 4) >= (1LL << 31)) return kNotQualified;
     DSB_REQUIRE(x != out, "spmm: out must not alias x");
     const int chunks = F / 4;
-    const int variant = env_int("DSB200_SPMM_VARIANT", 0);
-    if (variant > 0 && (width == 9 || width == 7) && chunks <= 32 && (chunks & (chunks - 1)) == 0) {
-        int l2 = 0;
-        while ((1 << l2) < chunks) ++l2;
-        int TR = env_int("DSB200_SPMM_TR", 128); if (TR < 16) TR = 128;
-        int SB = env_int("DSB200_SPMM_SB", 1); if (SB < 1) SB = 1;
-        while (SB > 1 && (long long)((B + SB - 1) / SB) * ((M + TR - 1) / TR) < 4LL * kNumSMs) SB >>= 1;
-        while (TR > 16 && (long long)((B + SB - 1) / SB) * ((M + TR - 1) / TR) < 4LL * kNumSMs) TR >>= 1;
-        const long long tiles = (long long)((B + SB - 1) / SB) * ((M + TR - 1) / TR);
-        const int mode = variant / 10, nb = variant % 10;
-        const long long cap = (long long)kNumSMs * nb;
-        const int grid = (int)(tiles < cap ? tiles : cap);
-        const size_t smem = mode >= 1 ? (size_t)width * TR * sizeof(int2) : 0;
-#define DSB_MLP(WW, MM, NN) spmm_mlp_kernel<WW, MM, NN><<<grid, 256, smem, s>>>(rec, B, M, l2, TR, SB, \
-            (const float4*)x, (const float4*)y, (const float4*)z, (float4*)out, alpha, beta, gamma)
-#define DSB_MLP_W(MM, NN) do { if (width == 9) DSB_MLP(9, MM, NN); else DSB_MLP(7, MM, NN); } while (0)
-        switch (variant) {
-            case 3: DSB_MLP_W(0, 3); break;
-            case 4: DSB_MLP_W(0, 4); break;
-            case 14: DSB_MLP_W(1, 4); break;
-            case 15: DSB_MLP_W(1, 5); break;
-            case 16: DSB_MLP_W(1, 6); break;
-            case 28: DSB_MLP_W(2, 8); break;
-            default: DSB_REQUIRE(false, "spmm: unknown DSB200_SPMM_VARIANT");
-        }
-#undef DSB_MLP_W
-#undef DSB_MLP
-        DSB_LAUNCH_CHECK();
-    }
     int CB = chunks < 64 ? chunks : 64;
     int lg2 = 0;
     while ((1 << lg2) < CB && lg2 < 5) ++lg2;

@@ -13,6 +13,8 @@ import bench  # noqa: E402
 from deepsphere_tf1_b200 import ops  # noqa: E402
 from deepsphere_tf1_b200.graph import DeviceGraph  # noqa: E402
 
+ops.set_pipe(False)          # this experiment is about the gather kernels
+
 torch.cuda.set_device(0)
 dev = torch.device('cuda', 0)
 L, p = bench.build_laplacians()
@@ -65,9 +67,8 @@ for li in [int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else '2,3').split('
             'random': torch.randint(0, M, (M, 9), device=dev)}
     for name, col in pats.items():
         repack(g, col)
-        for label, rec_on, var, sb in (('row-major', False, 0, 1), ('records', True, 0, 1), ('var28 SB4', True, 28, 4), ('var4', True, 4, 1)):
+        for label, rec_on, sb in (('row-major', False, 1), ('records', True, 1), ('records SB4', True, 4)):
             ops.set_records(rec_on)
-            os.environ['DSB200_SPMM_VARIANT'] = str(var)
             os.environ['DSB200_SPMM_SB'] = str(sb)
             t = timeit(lambda: ops.spmm(g, x1, x, None, out=out, alpha=2.0, beta=-1.0))
             print('  {:<22s} {:<10s}: {:7.1f} us ({:4.1f}%)'.format(name, label, t * 1e6, 100 * nbytes / t / 1e9 / peak))
