@@ -4,6 +4,8 @@ Every function takes / returns contiguous fp32 CUDA tensors in the reference's [
 layout and enqueues on torch's current stream.  The arithmetic lives in csrc/*.cu; PyTorch is
 used for device memory and streams, nothing else.  Reference call sites are cited per function.
 """
+import os
+
 import torch
 
 from ._consts import ACT, POOL, STAT, UNPOOL_REPEAT, UNPOOL_ZEROFILL  # noqa: F401
@@ -49,7 +51,8 @@ def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, tra
 
 USE_PIPE = True           # bulk-asynchronous pipelined sparse product (csrc/sparse_pipe.cu) where a tile plan exists
 USE_DENSE_GROUPS = True   # pipelined kernel: 4-row groups with dense 4 x 16 weight blocks (each distinct neighbour read once)
-PIPE_MIN_ITEMS = 4 * 296  # (row tiles x samples) below which the pipeline has nothing to overlap: gather kernels
+PIPE_MIN_ITEMS = int(os.environ.get('DSB200_PIPE_MIN_ITEMS', 4 * 296))  # (row tiles x samples) below which the pipeline has
+                                                                        # nothing to overlap: gather kernels
 
 
 def set_pipe(on, dense=None):
