@@ -613,6 +613,104 @@ __device__ __forceinline__ float block_sum(float v, float* sh)
     return v;                                               // valid in thread 0
 }
 
+// ---- learned histogram (cgcnn.learned_histogram, models.py:1166-1192; the `statistics='histogram'` head):
+//   hist[b, f, j] = scale * mean_m relu(1 - |x[b, m, f] - c[f, j]| * |w[f, j]|),   scale = bins / initial_range / 4
+// Block = (32 features) x (8 vertex lanes) of one sample: lanes read consecutive features (coalesced), every thread keeps
+// its `bins` partial sums in registers, the 8 vertex lanes are reduced through shared memory.
+constexpr int kHistBins = 32;                    // register budget: bins <= 32 (the reference hard-codes 20)
+
+__global__ void __launch_bounds__(256)
+hist_fwd_kernel(const float* __restrict__ x, const float* __restrict__ cen, const float* __restrict__ wid,
+                float* __restrict__ out, int M, int F, int bins, float scale_over_M)
+{
+    __shared__ float red[8][32][kHistBins + 1];
+    const int fl = threadIdx.x & 31, ml = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + fl, b = blockIdx.y;
+    float acc[kHistBins], c[kHistBins], w[kHistBins];
+#pragma unroll
+    for (int j = 0; j < kHistBins; ++j) {
+        acc[j] = 0.f;
+        c[j] = (f < F && j < bins) ? __ldg(cen + f * bins + j) : 0.f;
+        w[j] = (f < F && j < bins) ? fabsf(__ldg(wid + f * bins + j)) : 0.f;
+    }
+    if (f < F) {
+        const float* xb = x + (long long)b * M * F + f;
+        for (int m = ml; m < M; m += 8) {
+            const float v = __ldg(xb + (long long)m * F);
+#pragma unroll
+            for (int j = 0; j < kHistBins; ++j) acc[j] += fmaxf(1.f - fabsf(v - c[j]) * w[j], 0.f);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kHistBins; ++j) red[ml][fl][j] = acc[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * bins; i += 256) {
+        const int ff = i / bins, j = i - ff * bins;
+        if (blockIdx.x * 32 + ff < F) {
+            float t = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) t += red[q][ff][j];
+            out[((long long)b * F + blockIdx.x * 32 + ff) * bins + j] = t * scale_over_M;
+        }
+    }
+}
+
+// dx[b, m, f] = sum_j dh[b, f, j] * s * (active ? -sign(x - c) |w| : 0);  dc += dh s (active ? sign(x - c) |w| : 0);
+// dw += dh s (active ? -|x - c| sign(w) : 0);  active = 1 - |x - c| |w| > 0;  s = scale / M   (autodiff of 1187-1191)
+__global__ void __launch_bounds__(256)
+hist_bwd_kernel(const float* __restrict__ x, const float* __restrict__ cen, const float* __restrict__ wid,
+                const float* __restrict__ dh, float* __restrict__ dx, float* dcen, float* dwid,
+                int M, int F, int bins, float scale_over_M)
+{
+    __shared__ float red[8][32][kHistBins + 1];
+    const int fl = threadIdx.x & 31, ml = threadIdx.x >> 5;
+    const int f = blockIdx.x * 32 + fl, b = blockIdx.y;
+    float c[kHistBins], w[kHistBins], sw[kHistBins], g[kHistBins], dc[kHistBins], dw[kHistBins];
+#pragma unroll
+    for (int j = 0; j < kHistBins; ++j) {
+        const bool on = f < F && j < bins;
+        c[j] = on ? __ldg(cen + f * bins + j) : 0.f;
+        const float wr = on ? __ldg(wid + f * bins + j) : 0.f;
+        w[j] = fabsf(wr);
+        sw[j] = wr > 0.f ? 1.f : (wr < 0.f ? -1.f : 0.f);
+        g[j] = on ? __ldg(dh + ((long long)b * F + f) * bins + j) * scale_over_M : 0.f;
+        dc[j] = 0.f; dw[j] = 0.f;
+    }
+    if (f < F) {
+        const long long base = (long long)b * M * F + f;
+        for (int m = ml; m < M; m += 8) {
+            const float v = __ldg(x + base + (long long)m * F);
+            float d = 0.f;
+#pragma unroll
+            for (int j = 0; j < kHistBins; ++j) {
+                const float diff = v - c[j], ad = fabsf(diff);
+                const float sg = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+                const float ga = (1.f - ad * w[j] > 0.f) ? g[j] : 0.f;
+                d = fmaf(-sg * w[j], ga, d);
+                dc[j] = fmaf(sg * w[j], ga, dc[j]);
+                dw[j] = fmaf(-ad * sw[j], ga, dw[j]);
+            }
+            dx[base + (long long)m * F] = d;
+        }
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kHistBins; ++j) red[ml][fl][j] = pass ? dw[j] : dc[j];
+        __syncthreads();
+        float* dst = pass ? dwid : dcen;
+        for (int i = threadIdx.x; i < 32 * bins; i += 256) {
+            const int ff = i / bins, j = i - ff * bins;
+            if (blockIdx.x * 32 + ff < F) {
+                float t = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) t += red[q][ff][j];
+                atomicAdd(dst + (blockIdx.x * 32 + ff) * bins + j, t);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 softmax_ce_kernel(const float* __restrict__ logits, const int32_t* __restrict__ labels, float* __restrict__ dlogits,
                   float* loss_out, long long R, int C, float gscale, const float* __restrict__ cw)
@@ -967,6 +1065,25 @@ extern "C" int dsb200_fc_bwd(const float* x, const float* W, const float* y, con
     DSB_REQUIRE(act == DSB200_ACT_RELU || act == DSB200_ACT_IDENTITY, "fc_bwd: only relu / identity");
     if (dx) { fc_bwd_dx_kernel<<<(N * Min + 255) / 256, 256, 0, STREAM>>>(W, y, dy, dx, N, Min, Mout, act); count_launch(); }
     fc_bwd_dw_kernel<<<((Min + 1) * Mout + 255) / 256, 256, 0, STREAM>>>(x, y, dy, dW, db, N, Min, Mout, act);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_hist_fwd(const float* x, const float* centers, const float* widths, float* hist,
+                               int B, int M, int F, int bins, float scale, void* stream)
+{
+    DSB_REQUIRE(x && centers && widths && hist && B > 0 && M > 0 && F > 0, "hist_fwd: bad arguments");
+    DSB_REQUIRE(bins > 0 && bins <= kHistBins, "hist_fwd: at most 32 bins");
+    hist_fwd_kernel<<<dim3((F + 31) / 32, B), 256, 0, STREAM>>>(x, centers, widths, hist, M, F, bins, scale / (float)M);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_hist_bwd(const float* x, const float* centers, const float* widths, const float* dhist, float* dx,
+                               float* dcenters, float* dwidths, int B, int M, int F, int bins, float scale, void* stream)
+{
+    DSB_REQUIRE(x && centers && widths && dhist && dx && dcenters && dwidths && B > 0 && M > 0 && F > 0, "hist_bwd: bad arguments");
+    DSB_REQUIRE(bins > 0 && bins <= kHistBins, "hist_bwd: at most 32 bins");
+    hist_bwd_kernel<<<dim3((F + 31) / 32, B), 256, 0, STREAM>>>(x, centers, widths, dhist, dx, dcenters, dwidths, M, F, bins,
+                                                               scale / (float)M);
     DSB_LAUNCH_CHECK();
 }
 

@@ -16,8 +16,8 @@ Differences from the reference that a user sees (also listed in DESIGN.md):
   * `tf_dataset` may be any Python iterator of `(data, labels)` batches;
   * checkpoints are `torch.save` files `checkpoints/<dir_name>/model-<step>.pt` keyed by the
     reference's variable names (`conv1/weights`, `conv1/batch_normalization/moving_mean`, ...);
-  * `statistics='histogram'`, `dropFilt < 1`, `extra_loss`, equiangular sampling: NotImplementedError (outside the
-    hot path).  `conv='monomials'` and `weighted=True` are supported.
+  * `dropFilt < 1`, `extra_loss`, equiangular sampling: NotImplementedError (outside the hot path).
+    `conv='monomials'`, `weighted=True` and `statistics='histogram'` are supported.
 """
 import glob
 import json
@@ -698,9 +698,7 @@ class cgcnn(base_model):
             raise AttributeError("'cgcnn' object has no attribute 'pool_{}'".format(pool))
         if activation not in ACT:
             raise AttributeError("unknown activation '{}'".format(activation))
-        if statistics not in (None, 'mean', 'var', 'meanvar', 'max'):
-            if statistics == 'histogram':
-                raise NotImplementedError('the learned histogram layer is outside the hot path')
+        if statistics not in (None, 'mean', 'var', 'meanvar', 'max', 'histogram'):
             raise ValueError('Unknown statistical layer {}'.format(statistics))
         if dropFilt < 1 or extra_loss:
             raise NotImplementedError('dropFilt / extra_loss are outside the hot path')
@@ -831,8 +829,14 @@ class cgcnn(base_model):
             skipF.append(Fin)
         # statistics + fully connected head (models.py:1249-1285)
         self._fc = []
+        if self.statistics == 'histogram':                 # learned histogram: trainable centers / widths (models.py:1173-1185)
+            if self.vertex_shard:
+                raise NotImplementedError("statistics='histogram' is not available in the vertex-sharded mode")
+            nb, rg = ops.HIST_BINS, ops.HIST_RANGE
+            self._P.add('stat/centers', (1, 1, Fin, nb), np.tile(np.linspace(-rg, rg, nb, dtype=np.float32), (Fin, 1)))
+            self._P.add('stat/widths', (1, 1, Fin, nb), np.full((Fin, nb), 4 * rg / nb, np.float32))
         if self.M:
-            Min = {None: Mv * Fin, 'meanvar': 2 * Fin}.get(self.statistics, Fin)
+            Min = {None: Mv * Fin, 'meanvar': 2 * Fin, 'histogram': ops.HIST_BINS * Fin}.get(self.statistics, Fin)
             for i, Mo in enumerate(self.M[:-1]):
                 self._fc.append(_FcStage(self, 'fc{}'.format(i + 1), Min, Mo, True, act, self.dropout))
                 Min = Mo
@@ -975,7 +979,12 @@ class cgcnn(base_model):
         descriptor = x
         B = x.shape[0]
         self._stat_saved = None
-        if self.statistics is not None:
+        if self.statistics == 'histogram':
+            s = ops.hist_fwd(x, self._P.views['stat/centers'], self._P.views['stat/widths'])
+            if save:
+                self._stat_saved = (x,)
+            x = s
+        elif self.statistics is not None:
             s = ops.stat_fwd(x, self.statistics)
             if self.vertex_shard and self.world_size > 1:
                 # mean over the whole sphere = mean of the equally sized per-rank means
@@ -1033,7 +1042,11 @@ class cgcnn(base_model):
                         d = ops.unpool_bwd(dxin, arg, UNPOOL_REPEAT if kind == 'repeat' else UNPOOL_ZEROFILL)
         for fc in reversed(self._fc):
             d = fc.backward(d)
-        if self.statistics is not None:
+        if self.statistics == 'histogram':
+            P = self._P
+            d = ops.hist_bwd(self._stat_saved[0], P.views['stat/centers'], P.views['stat/widths'], d,
+                             P.gviews['stat/centers'], P.gviews['stat/widths'])
+        elif self.statistics is not None:
             d = ops.stat_bwd(self._stat_saved[0], d, self.statistics)
         elif self.M:
             d = d.reshape(self._stat_saved[0])

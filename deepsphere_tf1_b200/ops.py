@@ -342,6 +342,25 @@ def stat_bwd(x, dout, kind):
     return dx
 
 
+HIST_BINS, HIST_RANGE = 20, 2.0          # hard-coded in the reference (models.py:1166, 1264)
+
+
+def hist_fwd(x, centers, widths, bins=HIST_BINS, initial_range=HIST_RANGE):
+    """cgcnn.learned_histogram (models.py:1166-1192) -> [B, F*bins]."""
+    B, M, F = x.shape
+    out = _new((B, F * bins), x)
+    call('hist_fwd', x, centers, widths, out, B, M, F, bins, bins / initial_range / 4)
+    return out
+
+
+def hist_bwd(x, centers, widths, dout, dcenters, dwidths, bins=HIST_BINS, initial_range=HIST_RANGE):
+    """dx of the learned histogram; the gradients of the centers / widths are accumulated into dcenters / dwidths."""
+    B, M, F = x.shape
+    dx = _new((B, M, F), x)
+    call('hist_bwd', x, centers, widths, dout, dx, dcenters, dwidths, B, M, F, bins, bins / initial_range / 4)
+    return dx
+
+
 def fc_fwd(x, W, b, act):
     N, Min = x.shape
     y = _new((N, W.shape[1]), x)

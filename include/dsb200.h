@@ -286,6 +286,15 @@ int dsb200_mse(const float* pred, const float* target, float* dpred, float* loss
 /* softmax probabilities / argmax (models.py:750-763); probs or pred may be NULL */
 int dsb200_softmax_argmax(const float* logits, float* probs, int32_t* pred, long long R, int C, void* stream);
 
+/* ---- learned histogram head (cgcnn.learned_histogram, models.py:1166-1192; statistics='histogram', models.py:1263-1266)
+ *   hist[b, f, j] = scale * mean_m relu(1 - |x[b,m,f] - centers[f,j]| * |widths[f,j]|),  scale = bins / initial_range / 4
+ * x [B,M,F]; centers / widths [F, bins]; hist [B, F*bins] (feature-major, as the reference reshapes it); bins <= 32.
+ * Backward: dx [B,M,F] is written, dcenters / dwidths [F, bins] are ACCUMULATED (caller zeroes). */
+int dsb200_hist_fwd(const float* x, const float* centers, const float* widths, float* hist,
+                    int B, int M, int F, int bins, float scale, void* stream);
+int dsb200_hist_bwd(const float* x, const float* centers, const float* widths, const float* dhist, float* dx,
+                    float* dcenters, float* dwidths, int B, int M, int F, int bins, float scale, void* stream);
+
 /* ---- regularisation term  sum_i ||W_i||^2 / 2 / std_i^2  over a flat parameter buffer with a
  * per-element coefficient (models.py:806-808, 866): loss_out[0] += sum coef*w^2/2 and
  * g += coef * w */

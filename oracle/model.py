@@ -84,6 +84,11 @@ class OracleCgcnn:
             Min = Mv * Fin
         elif self.stat == 'meanvar':
             Min = 2 * Fin
+        elif self.stat == 'histogram':                       # models.py:1263-1266: 20 learned bins per feature
+            Min = 20 * Fin
+            c, w = ops.histogram_init(Fin, dtype=self.dtype)
+            self.params['stat/centers'] = c                  # trainable, not regularised (plain tf.Variable / get_variable)
+            self.params['stat/widths'] = w
         else:
             Min = Fin
         for i, Mo in enumerate(self.M[:-1]):
@@ -136,7 +141,10 @@ class OracleCgcnn:
             x = ops.pool(x, self.p[i], self.pool_kind, self.sampling)        # 1243
             pool_layers.append(x)                                            # 1245
         descriptor = x
-        x = ops.statistics(x, self.stat, bool(self.M))                       # 1249-1270
+        if self.stat == 'histogram':
+            x = ops.learned_histogram(x, P['stat/centers'], P['stat/widths'])  # 1263-1266
+        else:
+            x = ops.statistics(x, self.stat, bool(self.M))                   # 1249-1270
         for i, _ in enumerate(self.M[:-1]):                                  # 1275-1280
             sc = 'fc{}'.format(i + 1)
             x = self.act(ops.fc(x, P[sc + '/weights'], P[sc + '/bias']))

@@ -125,6 +125,23 @@ def statistics(x, kind, has_fc):
     raise ValueError('Unknown statistical layer {}'.format(kind))
 
 
+def learned_histogram(x, centers, widths, bins=20, initial_range=2):
+    """models.py:1166-1192; centers / widths are the trainable [1, 1, F, bins] variables `stat/centers`, `stat/widths`."""
+    N, M, F = x.shape
+    x4 = x.unsqueeze(3)                                                   # 1186
+    w = widths.reshape(1, 1, F, bins).abs()                               # 1188
+    dist = (x4 - centers.reshape(1, 1, F, bins)).abs()                    # 1189
+    hist = torch.relu(1 - dist * w).mean(dim=1) * (bins / initial_range / 4)   # 1190
+    return hist.reshape(N, bins * F)                                      # 1266
+
+
+def histogram_init(F, bins=20, initial_range=2, dtype=torch.float32):
+    """Initial values of `stat/centers` (linspace per feature, 1173-1179) and `stat/widths` (4 range / bins, 1181-1185)."""
+    centers = torch.linspace(-float(initial_range), float(initial_range), bins, dtype=dtype).repeat(F, 1).reshape(1, 1, F, bins)
+    widths = torch.full((1, 1, F, bins), 4 * initial_range / bins, dtype=dtype)
+    return centers, widths
+
+
 def fc(x, W, b=None):
     """models.py:1205-1212."""
     y = x @ W

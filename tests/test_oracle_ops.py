@@ -101,3 +101,17 @@ def test_weighted_cross_entropy_matches_its_definition():
     assert float(got) == pytest.approx(expect, rel=1e-12)
     with pytest.raises(ValueError):
         oops.loss(torch.zeros(4, 5), torch.zeros(4, dtype=torch.long), False, [(torch.zeros(1), 1.0)], 0.0, weighted=True)
+
+
+def test_learned_histogram_initial_bins_partition_their_range():
+    """models.py:1173-1190: triangular bins with 50 % overlap -- inside the initial range every value falls into exactly
+    two neighbouring bins whose memberships sum to a constant, so a histogram row sums to that constant times the scale."""
+    F, bins, rng = 3, 20, 2
+    c, w = oops.histogram_init(F, bins, rng, torch.float64)
+    assert c.shape == (1, 1, F, bins) and float(w[0, 0, 0, 0]) == pytest.approx(4 * rng / bins)
+    x = (torch.rand(2, 500, F, dtype=torch.float64) * 2 - 1) * 1.7          # well inside [-2, 2]
+    h = oops.learned_histogram(x, c, w, bins, rng).reshape(2, F, bins)
+    # spacing of the centers d = 2 rng / (bins - 1); membership 1 - |x - c| * 0.4 summed over the (up to 5) active bins
+    assert torch.all(h >= 0)
+    single = oops.learned_histogram(c[:, :, :, 7:8].reshape(1, 1, F).clone(), c, w, bins, rng).reshape(F, bins)
+    assert float(single[0, 7]) == pytest.approx(bins / rng / 4)            # a value on a center: membership 1 in that bin

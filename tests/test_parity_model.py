@@ -216,6 +216,21 @@ def test_monomial_filters_classifier(pipelined, monkeypatch):
     _check_step(oracle, model, x, labels)
 
 
+def test_learned_histogram_head():
+    """statistics='histogram' (models.py:1263-1266, 1166-1192): 20 learned bins per feature map in front of the fully
+    connected layers; the centers and widths train with the rest."""
+    from deepsphere_tf1_b200 import utils
+    nsides = [8, 4, 2, 2]
+    L, p = utils.build_laplacians(nsides, new=False)
+    oracle, model = _pair(L, F=[8, 16, 8], K=[3, 3, 3], p=p, batch_norm=[True, True, True], M=[12, 3], statistics='histogram',
+                          regularization=0.02)
+    assert 'stat/centers' in oracle.params and model._P.shapes['stat/widths'] == (1, 1, 8, 20)
+    rs = np.random.RandomState(0)
+    x = rs.randn(4, 768, 1).astype(np.float32)
+    labels = rs.randint(0, 3, size=4).astype(np.int32)
+    _check_step(oracle, model, x, labels)
+
+
 def test_weighted_cross_entropy_dense_segmentation():
     """weighted=True (models.py:795-802): per-pixel cross-entropy weighted by the hard-coded class weights of the climate
     data set (3 classes), on a small encoder-decoder."""

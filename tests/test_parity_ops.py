@@ -484,6 +484,31 @@ def test_fc_losses_regulariser(dev):
     assert_close(dp.reshape(8, 7), 2 * (h.detach() - t) / 56, RTOL, 'dmse')
 
 
+@pytest.mark.parametrize('shape', [(3, 50, 7), (2, 256, 64), (1, 9, 40)])
+def test_learned_histogram_forward_backward(dev, shape):
+    """dsb200_hist_fwd / bwd vs torch autograd of the restated cgcnn.learned_histogram (models.py:1166-1192)."""
+    from deepsphere_tf1_b200 import ops
+    from oracle import ops as oops
+    B, M, F = shape
+    rs = np.random.RandomState(M)
+    x = torch.from_numpy((rs.randn(B, M, F) * 1.5).astype(np.float32)).requires_grad_(True)
+    c0, w0 = oops.histogram_init(F)
+    c = (c0 + torch.from_numpy(rs.randn(1, 1, F, 20).astype(np.float32)) * 0.05).requires_grad_(True)
+    w = (w0 * torch.from_numpy(rs.choice([-1.0, 1.0], size=(1, 1, F, 20)).astype(np.float32))
+         * (1 + 0.1 * torch.from_numpy(rs.randn(1, 1, F, 20).astype(np.float32)))).requires_grad_(True)
+    ref = oops.learned_histogram(x, c, w)
+    dh = torch.from_numpy(rs.randn(B, F * 20).astype(np.float32))
+    ref.backward(dh)
+    cd, wd = c.detach().reshape(F, 20).to(dev).contiguous(), w.detach().reshape(F, 20).to(dev).contiguous()
+    out = ops.hist_fwd(x.detach().to(dev), cd, wd)
+    assert_close(out, ref.detach(), RTOL, 'histogram')
+    dc, dw = torch.zeros_like(cd), torch.zeros_like(wd)
+    dx = ops.hist_bwd(x.detach().to(dev), cd, wd, dh.to(dev), dc, dw)
+    assert_close(dx, x.grad, RTOL, 'dx')
+    assert_close(dc, c.grad.reshape(F, 20), RTOL, 'dcenters')
+    assert_close(dw, w.grad.reshape(F, 20), RTOL, 'dwidths')
+
+
 def test_weighted_cross_entropy(dev):
     from deepsphere_tf1_b200 import ops
     from oracle import ops as oops
