@@ -150,8 +150,12 @@ def build_laplacians(nsides, indexes=None, use_4=False, sampling='healpix', std=
                 laplacian = healpix_laplacian(nside=nside, indexes=index, use_4=use_4, std=sigma,
                                               full=mat, new=new, n_neighbors=n_neighbors)
             elif sampling == 'icosahedron':
-                from .graphs import icosahedron_laplacian
-                laplacian = icosahedron_laplacian(order=nside)
+                # utils.py:370-376 builds the mesh and its kNN weights inside the PyGSP fork (SphereIcosahedron), which
+                # is not available; models.cgcnn takes the Laplacians of an icosahedral hierarchy directly (L=[...],
+                # p = vertex counts of the coarser levels) and implements its pooling / unpooling (models.py:1137-1138,
+                # 1356-1358), see tests/test_parity_model.py::test_climate_like_icosahedral_segmentation
+                raise NotImplementedError('icosahedral graphs need the PyGSP fork (SphereIcosahedron); '
+                                          'build the Laplacians elsewhere and pass them to models.cgcnn(L=..., p=...)')
             elif sampling == 'equiangular':
                 raise NotImplementedError('equiangular sampling needs the PyGSP fork (out of scope)')
             else:
