@@ -8,6 +8,7 @@
 // FP32 FFMA register-tiled kernels (exact-precision path); the tcgen05 path lives in
 // contract_tc.cu.
 #include "common.cuh"
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include <atomic>
 
@@ -349,6 +350,12 @@ extern "C" long long dsb200_contract_workspace_bytes(int Fin, int K, int Fout)
     return (long long)tc::contract_workspace_bytes(Fin, K, Fout);
 }
 
+namespace dsb200 {
+int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
+                     double* bn_sums, cudaStream_t s);                      // contract_mma.cu
+static bool fwd_mma_enabled() { const char* e = getenv("DSB200_FWD_MMA"); return e ? atoi(e) != 0 : true; }   // default on
+}  // namespace dsb200
+
 extern "C" int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const float* W, float* Y,
                                         long long R, int Fin, int K, int Fout, double* bn_sums, void* workspace,
                                         void* stream)
@@ -358,6 +365,10 @@ extern "C" int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const 
     cudaStream_t s = (cudaStream_t)stream;
     Planar A{x0, xk, Fin, R * (long long)Fin};
     const int Q = K * Fin;
+    if (g_use_tc.load(std::memory_order_relaxed) && fwd_mma_enabled()) {
+        const int rc = contract_fwd_mma(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, s);   // narrow layers (Fin 16 -> Fout 32)
+        if (rc != 1) return rc;
+    }
     if (g_use_tc.load(std::memory_order_relaxed) && Q > 16) {
         int rc = tc::contract_fwd_tc_cols(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, workspace, s);
         if (rc == 1) rc = tc::contract_fwd_tc(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, workspace, s);
