@@ -353,6 +353,9 @@ extern "C" long long dsb200_contract_workspace_bytes(int Fin, int K, int Fout)
 namespace dsb200 {
 int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
                      double* bn_sums, cudaStream_t s);                      // contract_mma.cu
+int contract_wgrad_mma(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K, int Fout,
+                       cudaStream_t s);                                     // contract_mma.cu
+static bool wgrad_mma_enabled() { const char* e = getenv("DSB200_WGRAD_MMA"); return e ? atoi(e) != 0 : true; }   // default on
 static bool fwd_mma_enabled() { const char* e = getenv("DSB200_FWD_MMA"); return e ? atoi(e) != 0 : true; }   // default on
 }  // namespace dsb200
 
@@ -410,6 +413,10 @@ extern "C" int dsb200_cheb_contract_bwd_weight(const float* x0, const float* xk,
     cudaStream_t s = (cudaStream_t)stream;
     Planar A{x0, xk, Fin, R * (long long)Fin};
     const int Q = K * Fin;
+    if (g_use_tc.load(std::memory_order_relaxed) && wgrad_mma_enabled()) {
+        const int rc = contract_wgrad_mma(x0, xk, dY, dW, R, Fin, K, Fout, s);       // narrow layers (Fin 16 -> Fout 32)
+        if (rc != 1) return rc;
+    }
     if (g_use_tc.load(std::memory_order_relaxed) && Q > 16) {
         const int rc = tc::contract_bwd_weight_tc(x0, xk, dY, dW, R, Fin, K, Fout, s);
         if (rc != 1) return rc;

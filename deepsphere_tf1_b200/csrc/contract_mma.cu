@@ -318,6 +318,162 @@ rowgemm_mma_pipe_kernel(const float* __restrict__ x0, const float* __restrict__ 
     }
 }
 
+// ---- weight gradient of the same narrow layer:  dW[fi*K + k, fo] += sum_r X_k[r, fi] dY[r, fo]   (autodiff of models.py:1077).
+// The reduction runs over the ROWS, so in mma.m16n8k8 terms M = the 16 input features of a plane, N = the 32 output features
+// (4 column tiles), k = 8 rows per instruction.  One CTA per SM (the K x 16 accumulator registers of a warp need the whole
+// register file): 3 producer warps bring 128-row stages -- K plane tiles of X and the dY tile, all contiguous in memory -- by
+// 1-D bulk copies into a 3-stage ring; each of the 8 consumer warps owns 16 rows of every stage for ALL planes (the dY
+// fragments are read once per row step and shared by the K planes), splits both operands hi / lo in registers (3xTF32) and keeps
+// its partial dW in registers until the end: warps -> shared memory -> one red.global.add per element and CTA.
+// Fragment permutations: A's m index g / g+8 <-> features 4(g/2) + g%2 / + 2 (a lane reads one float4 of a row and uses two of
+// its components), B's n index v of column tile j <-> output feature 4v + j (a lane reads one float4 of dY and uses component j
+// for tile j), k index t / t+4 <-> rows t / t+4 of the 8-row step.
+constexpr int kWgRows = 128, kWgStages = 3, kWgConsumers = 8, kWgProducers = 3;
+constexpr int kWgThreads = (kWgConsumers + kWgProducers) * 32;
+
+template <int K>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_mma_pipe_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ dY,
+                      float* __restrict__ dW, long long R)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int kXTile = kWgRows * kMmaFin * 4, kYTile = kWgRows * kMmaFout * 4, kStage = K * kXTile + kYTile;
+    float* sred = reinterpret_cast<float*>(smem + kWgStages * kStage);                  // [K*16][32]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sred + K * kMmaFin * kMmaFout);
+    uint64_t* empty = full + kWgStages;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & 3, g = lane >> 2;
+    for (int i = threadIdx.x; i < K * kMmaFin * kMmaFout; i += kWgThreads) sred[i] = 0.f;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kWgStages; ++s) { mp_bar_init(full + s, kWgProducers); mp_bar_init(empty + s, kWgConsumers); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long plane = R * kMmaFin;
+    const long long nblk = (R + kWgRows - 1) / kWgRows;
+    const long long b0 = nblk * blockIdx.x / gridDim.x, b1 = nblk * (blockIdx.x + 1) / gridDim.x;
+    const int nst = (int)(b1 - b0);
+
+    if (warp >= kWgConsumers) {
+        const int pw = warp - kWgConsumers;
+        if (lane == 0) {
+            for (int it = 0; it < nst; ++it) {
+                const int s = it % kWgStages, u = it / kWgStages;
+                if (u > 0) mp_bar_wait(empty + s, (uint32_t)(u - 1) & 1u);
+                const long long row0 = (b0 + it) * kWgRows;
+                const uint32_t rows = (uint32_t)(R - row0 < kWgRows ? R - row0 : kWgRows);
+                unsigned char* st = smem + (size_t)s * kStage;
+                uint32_t bytes = 0;
+                for (int c = pw; c <= K; c += kWgProducers) bytes += rows * (c < K ? kMmaFin : kMmaFout) * 4;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mp_bar_expect_tx(full + s, bytes);
+                for (int c = pw; c <= K; c += kWgProducers) {
+                    if (c < K) mp_bulk_g2s(st + c * kXTile, (c == 0 ? x0 : xk + (long long)(c - 1) * plane) + row0 * kMmaFin, rows * kMmaFin * 4, full + s);
+                    else mp_bulk_g2s(st + K * kXTile, dY + row0 * kMmaFout, rows * kMmaFout * 4, full + s);
+                }
+            }
+        }
+        return;
+    }
+
+    float acc[K][4][4];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[k][j][e] = 0.f;
+    const bool odd = (g & 1) != 0;
+    for (int it = 0; it < nst; ++it) {
+        const int s = it % kWgStages, u = it / kWgStages;
+        const long long row0 = (b0 + it) * kWgRows;
+        const unsigned char* st = smem + (size_t)s * kStage;
+        const float4* Ys = reinterpret_cast<const float4*>(st + K * kXTile);            // [128][8]
+        mp_bar_wait(full + s, (uint32_t)u & 1u);
+#pragma unroll
+        for (int step = 0; step < 2; ++step) {
+            const int r0 = warp * 16 + step * 8 + t, r1 = r0 + 4;                       // rows of this lane in the stage
+            const bool ok0 = row0 + r0 < R, ok1 = row0 + r1 < R;                        // (stale shared memory past R)
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 y0 = ok0 ? Ys[r0 * 8 + g] : zero4, y1 = ok1 ? Ys[r1 * 8 + g] : zero4;
+            const float yv0[4] = {y0.x, y0.y, y0.z, y0.w}, yv1[4] = {y1.x, y1.y, y1.z, y1.w};
+            uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t h0 = __float_as_uint(yv0[j]) & 0xffffe000u, h1 = __float_as_uint(yv1[j]) & 0xffffe000u;
+                bh[j][0] = h0; bh[j][1] = h1;
+                bl[j][0] = __float_as_uint(yv0[j] - __uint_as_float(h0));
+                bl[j][1] = __float_as_uint(yv1[j] - __uint_as_float(h1));
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float4* Xs = reinterpret_cast<const float4*>(st + k * kXTile);    // [128][4]
+                const float4 a0 = ok0 ? Xs[r0 * 4 + (g >> 1)] : zero4, a1 = ok1 ? Xs[r1 * 4 + (g >> 1)] : zero4;
+                const float f[4] = {odd ? a0.y : a0.x, odd ? a0.w : a0.z, odd ? a1.y : a1.x, odd ? a1.w : a1.z};
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t hb = __float_as_uint(f[e]) & 0xffffe000u;
+                    ah[e] = hb;
+                    al[e] = __float_as_uint(f[e] - __uint_as_float(hb));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    mma_tf32_16x8x8(acc[k][j], al, bh[j][0], bh[j][1]);
+                    mma_tf32_16x8x8(acc[k][j], ah, bl[j][0], bl[j][1]);
+                    mma_tf32_16x8x8(acc[k][j], ah, bh[j][0], bh[j][1]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mp_bar_arrive(empty + s);
+    }
+    // partial dW of this warp -> shared memory -> global
+    const int fA = 4 * (g >> 1) + (g & 1);
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int fi = fA + ((e & 2) ? 2 : 0);                                   // c2, c3: m index g + 8
+                const int fo = 4 * (2 * t + (e & 1)) + j;
+                atomicAdd(sred + (fi * K + k) * kMmaFout + fo, acc[k][j][e]);
+            }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int i = threadIdx.x; i < K * kMmaFin * kMmaFout; i += kWgConsumers * 32)
+        asm volatile("red.global.add.f32 [%0], %1;" :: "l"(dW + i), "f"(sred[i]) : "memory");
+}
+
+template <int K>
+static int wgrad_mma_launch(const float* x0, const float* xk, const float* dY, float* dW, long long R, cudaStream_t s)
+{
+    const long long nblk = (R + kWgRows - 1) / kWgRows;
+    const int grid = (int)(nblk < kNumSMs ? nblk : kNumSMs);
+    const size_t smem = (size_t)kWgStages * (K * kWgRows * kMmaFin * 4 + kWgRows * kMmaFout * 4) + (size_t)K * kMmaFin * kMmaFout * 4
+                        + 2 * kWgStages * 8 + 64;
+    static bool cfg = false;
+    if (!cfg) {
+        cudaError_t ce = cudaFuncSetAttribute(wgrad_mma_pipe_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return (int)ce; }
+        cfg = true;
+    }
+    wgrad_mma_pipe_kernel<K><<<grid, kWgThreads, smem, s>>>(x0, xk, dY, dW, R);
+    DSB_LAUNCH_CHECK();
+}
+
+// returns 1 when the shape does not qualify
+int contract_wgrad_mma(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K, int Fout,
+                       cudaStream_t s)
+{
+    if (Fin != kMmaFin || Fout != kMmaFout || R < kWgRows) return 1;
+    if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)dY) & 15) != 0) return 1;
+    if (K == 5) return wgrad_mma_launch<5>(x0, xk, dY, dW, R, s);
+    if (K == 4) return wgrad_mma_launch<4>(x0, xk, dY, dW, R, s);
+    if (K == 3) return wgrad_mma_launch<3>(x0, xk, dY, dW, R, s);
+    return 1;
+}
+
 // returns 1 when the shape does not qualify
 int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
                      double* bn_sums, cudaStream_t s)
