@@ -466,6 +466,9 @@ static int wgrad_mma_launch(const float* x0, const float* xk, const float* dY, f
 int contract_wgrad_mma(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K, int Fout,
                        cudaStream_t s)
 {
+    // Wider layers (Fin 32 / 64 -> Fout 64) were tried with the consumer warps split over the output features (191 us at cosmo
+    // layer 3 against 70 us): with row pitches of 128 / 256 bytes the four rows a fragment load touches fall on the same banks
+    // (4-way conflicts on every operand read) -- they need a swizzled staging, which a 1-D bulk copy cannot write.
     if (Fin != kMmaFin || Fout != kMmaFout || R < kWgRows) return 1;
     if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)dY) & 15) != 0) return 1;
     if (K == 5) return wgrad_mma_launch<5>(x0, xk, dY, dW, R, s);
