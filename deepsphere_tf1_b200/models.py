@@ -1169,15 +1169,27 @@ class cgcnn(base_model):
         if st is None or st[0].shape != hx.shape or st[1].shape != hl.shape:
             st = (torch.empty(hx.shape, dtype=torch.float32, device=self.device),
                   torch.empty(hl.shape, dtype=ldt, device=self.device),
-                  torch.cuda.Event(), torch.cuda.Event())          # (x, labels, ready, consumed)
+                  torch.cuda.Event(), torch.cuda.Event(),          # (x, labels, ready, consumed,
+                  torch.empty(hx.shape, dtype=torch.float32).pin_memory(),     #  pinned x, pinned labels, copied)
+                  torch.empty(hl.shape, dtype=ldt).pin_memory(), torch.cuda.Event())
             st[3].record()
+            st[6].record()
             self._stage[i] = st
         cs = self._copy_stream
+        hl = hl.to(ldt)
+        if not (hx.is_pinned() and hl.is_pinned()):
+            # pageable batches (numpy arrays of the reference's dataset protocol): through this pair's pinned buffers, so that
+            # the device copy is a real asynchronous DMA; the previous DMA out of them (two steps ago) must have finished
+            st[6].synchronize()
+            st[4].copy_(hx)
+            st[5].copy_(hl)
+            hx, hl = st[4], st[5]
         cs.wait_event(st[3])                                # the step that last read this pair has taken its copy
         with torch.cuda.stream(cs):
             st[0].copy_(hx.contiguous(), non_blocking=True)
-            st[1].copy_(hl.to(ldt).contiguous(), non_blocking=True)
+            st[1].copy_(hl.contiguous(), non_blocking=True)
             st[2].record(cs)
+            st[6].record(cs)
         self._prefetched = (batch_data, batch_labels, st[0], st[1], st[2], st[3])
 
     def _capture(self, x, labels):

@@ -265,6 +265,14 @@ def test_prefetched_batches_train_exactly_like_plain_steps(graphed):
         assert pre._prefetched is None or pre._prefetched[0] is batches[t + 1][0]
         assert float(l1) == pytest.approx(float(l2), rel=1e-5)       # (atomic accumulation order differs run to run)
     assert_close(pre._P.w, plain._P.w, 1e-5, 'weights after prefetched steps')
+    # pageable numpy batches (the reference's dataset protocol) go through the pinned staging buffers
+    _, plain2 = _pair(L, **kw)
+    _, pre2 = _pair(L, **kw)
+    nb = [(b[0].numpy().copy(), b[1].numpy().copy()) for b in batches]
+    for t, (x, labels) in enumerate(nb):
+        plain2.train_step(x, labels)
+        pre2.train_step(x, labels, next_batch=nb[t + 1] if t + 1 < len(nb) else None)
+    assert_close(pre2._P.w, plain2._P.w, 1e-5, 'weights after prefetched numpy batches')
     # a caller that passes a different batch than the one it announced just gets a plain copy
     x, labels = batches[0]
     pre.train_step(x, labels, next_batch=batches[1])
