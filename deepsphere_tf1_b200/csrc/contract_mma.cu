@@ -174,14 +174,16 @@ __device__ __forceinline__ void mp_bulk_g2s(void* dst, const void* src, uint32_t
                  :: "r"(mp_saddr(dst)), "l"(src), "r"(bytes), "r"(mp_saddr(bar)) : "memory");
 }
 
-constexpr int kMpRows = 256, kMpStages = 4, kMpThreads = 9 * 32;
-constexpr int kMpStageBytes = kMpRows * kMmaFin * 4;          // 16 KB
+constexpr int kMpThreads = 9 * 32;
 
-template <bool SUMS>
-__global__ void __maxnreg__(112)
-rowgemm_mma_pipe_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ W,
-                        float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K)
+// MTW = row tiles of 16 per warp (2: 32 rows, two CTAs per SM; 4: 64 rows, one CTA per SM -- the weight fragments are then read
+// half as often per row), kMpStages stages of 8 * 16 * MTW rows.
+template <bool SUMS, int MTW, int kMpStages>
+__device__ __forceinline__ void
+rowgemm_mma_pipe_body(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ W,
+                      float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K)
 {
+    constexpr int kMpRows = 8 * 16 * MTW, kMpStageBytes = kMpRows * kMmaFin * 4;
     extern __shared__ __align__(128) unsigned char smem[];
     float4* sW = reinterpret_cast<float4*>(smem + kMpStages * kMpStageBytes);           // [K][2][4][32]
     float* red = reinterpret_cast<float*>(sW + kMmaMaxK * 2 * 4 * 32);
@@ -234,10 +236,10 @@ rowgemm_mma_pipe_kernel(const float* __restrict__ x0, const float* __restrict__ 
     for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
     int it = 0;
     for (long long blk = b0; blk < b1; ++blk) {
-        const long long row0 = blk * kMpRows + warp * 32;
-        float acc[2][4][4];
+        const long long row0 = blk * kMpRows + warp * (16 * MTW);
+        float acc[MTW][4][4];
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int m = 0; m < MTW; ++m)
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -245,18 +247,18 @@ rowgemm_mma_pipe_kernel(const float* __restrict__ x0, const float* __restrict__ 
         for (int k = 0; k < K; ++k, ++it) {
             const int s = it % kMpStages, u = it / kMpStages;
             mp_bar_wait(full + s, (uint32_t)u & 1u);
-            const float4* A = reinterpret_cast<const float4*>(smem + (size_t)s * kMpStageBytes) + (warp * 32) * 4 + t;
-            float4 v[2][2];
+            const float4* A = reinterpret_cast<const float4*>(smem + (size_t)s * kMpStageBytes) + (warp * (16 * MTW)) * 4 + t;
+            float4 v[MTW][2];
 #pragma unroll
-            for (int m = 0; m < 2; ++m)
+            for (int m = 0; m < MTW; ++m)
 #pragma unroll
                 for (int h = 0; h < 2; ++h)                               // rows past R: zeros (the stage holds stale data there)
                     v[m][h] = (row0 + 16 * m + 8 * h + g < R) ? A[(16 * m + 8 * h + g) * 4] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int s2i = 0; s2i < 2; ++s2i) {
-                uint32_t ah[2][4], al[2][4];
+                uint32_t ah[MTW][4], al[MTW][4];
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
+                for (int m = 0; m < MTW; ++m) {
                     const float f0 = s2i ? v[m][0].z : v[m][0].x, f1 = s2i ? v[m][1].z : v[m][1].x;
                     const float f2 = s2i ? v[m][0].w : v[m][0].y, f3 = s2i ? v[m][1].w : v[m][1].y;
                     const float f[4] = {f0, f1, f2, f3};
@@ -274,7 +276,7 @@ rowgemm_mma_pipe_kernel(const float* __restrict__ x0, const float* __restrict__ 
                     const uint32_t bh0 = __float_as_uint(wf.x), bh1 = __float_as_uint(wf.y);
                     const uint32_t bl0 = __float_as_uint(wf.z), bl1 = __float_as_uint(wf.w);
 #pragma unroll
-                    for (int m = 0; m < 2; ++m) {
+                    for (int m = 0; m < MTW; ++m) {
                         mma_tf32_16x8x8(acc[m][j], al[m], bh0, bh1);
                         mma_tf32_16x8x8(acc[m][j], ah[m], bl0, bl1);
                         mma_tf32_16x8x8(acc[m][j], ah[m], bh0, bh1);
@@ -285,7 +287,7 @@ rowgemm_mma_pipe_kernel(const float* __restrict__ x0, const float* __restrict__ 
             if (lane == 0) mp_bar_arrive(empty + s);
         }
 #pragma unroll
-        for (int m = 0; m < 2; ++m)
+        for (int m = 0; m < MTW; ++m)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const long long r = row0 + 16 * m + 8 * h + g;
@@ -316,6 +318,22 @@ rowgemm_mma_pipe_kernel(const float* __restrict__ x0, const float* __restrict__ 
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x < 2 * kMmaFout) atomicAdd(bn_sums + threadIdx.x, (double)red[threadIdx.x]);
     }
+}
+
+template <bool SUMS>
+__global__ void __maxnreg__(112)
+rowgemm_mma_pipe_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ W,
+                        float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K)
+{
+    rowgemm_mma_pipe_body<SUMS, 2, 4>(x0, xk, W, Y, bn_sums, R, K);
+}
+
+template <bool SUMS>
+__global__ void __launch_bounds__(kMpThreads, 1)
+rowgemm_mma_pipe64_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ W,
+                          float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K)
+{
+    rowgemm_mma_pipe_body<SUMS, 4, 5>(x0, xk, W, Y, bn_sums, R, K);
 }
 
 // ---- weight gradient of the same narrow layer:  dW[fi*K + k, fo] += sum_r X_k[r, fi] dY[r, fo]   (autodiff of models.py:1077).
@@ -485,15 +503,33 @@ int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y,
     if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y) & 15) != 0) return 1;
     const long long cap = 2LL * kNumSMs;
     const char* e = getenv("DSB200_FWD_MMA");
-    if (e && atoi(e) == 2) {                                         // register version (experiment)
+    const int variant = e ? atoi(e) : 3;                             // 3 (default): 64 rows per warp, one CTA per SM (100.6 us with
+                                                                     // the sums at cosmo layer 2); 1: 32 rows, two CTAs (105.8 us)
+    if (variant == 2) {                                              // register version (experiment)
         const long long nblk = (R + 31) / 32;
         const int grid = (int)((nblk + 7) / 8 < cap ? (nblk + 7) / 8 : cap);
         rowgemm_mma_kernel<<<grid, 256, 0, s>>>(x0, xk, W, Y, bn_sums, R, K);
         DSB_LAUNCH_CHECK();
     }
-    const long long nblk = (R + kMpRows - 1) / kMpRows;
+    const size_t fixed = (size_t)kMmaMaxK * 2 * 4 * 32 * 16 + 2 * kMmaFout * 4 + 2 * 8 * 8 + 64;
+    if (variant == 3) {                                              // 64 rows per warp, one CTA per SM
+        const long long nb64 = (R + 511) / 512;
+        const int grid64 = (int)(nb64 < kNumSMs ? nb64 : kNumSMs);
+        const size_t smem64 = (size_t)5 * 512 * kMmaFin * 4 + fixed;
+        static bool cfg64 = false;
+        if (!cfg64) {
+            cudaError_t ce = cudaFuncSetAttribute(rowgemm_mma_pipe64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (ce == cudaSuccess) ce = cudaFuncSetAttribute(rowgemm_mma_pipe64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return (int)ce; }
+            cfg64 = true;
+        }
+        if (bn_sums) rowgemm_mma_pipe64_kernel<true><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K);
+        else rowgemm_mma_pipe64_kernel<false><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K);
+        DSB_LAUNCH_CHECK();
+    }
+    const long long nblk = (R + 255) / 256;
     const int grid = (int)(nblk < cap ? nblk : cap);
-    const size_t smem = (size_t)kMpStages * kMpStageBytes + (size_t)kMmaMaxK * 2 * 4 * 32 * 16 + 2 * kMmaFout * 4 + 2 * kMpStages * 8 + 64;
+    const size_t smem = (size_t)4 * 256 * kMmaFin * 4 + fixed;
     static bool cfg = false;
     if (!cfg) {
         cudaError_t ce = cudaFuncSetAttribute(rowgemm_mma_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
