@@ -16,8 +16,8 @@ Differences from the reference that a user sees (also listed in DESIGN.md):
   * `tf_dataset` may be any Python iterator of `(data, labels)` batches;
   * checkpoints are `torch.save` files `checkpoints/<dir_name>/model-<step>.pt` keyed by the
     reference's variable names (`conv1/weights`, `conv1/batch_normalization/moving_mean`, ...);
-  * `dropFilt < 1`, `extra_loss`, equiangular sampling: NotImplementedError (outside the hot path).
-    `conv='monomials'`, `weighted=True` and `statistics='histogram'` are supported.
+  * `extra_loss`, equiangular sampling: NotImplementedError (outside the hot path).
+    `conv='monomials'`, `weighted=True`, `statistics='histogram'` and `dropFilt < 1` are supported.
 """
 import glob
 import json
@@ -115,7 +115,10 @@ class _ChebStage(object):
             model._P.add(scope + '/bias', (1, 1, Fout), np.zeros(Fout, np.float32))
         self.post = bn or bias or act != 'identity' or p > 1
         # tiny reduction depth (K*Fin <= 8) on the input layer: never materialise y (csrc/smallconv.cu)
-        self.small = bool(first and self.post and model.fused_small and self.sg is None
+        self.drop = float(getattr(model, 'dropFilt', 1.0))                    # filter dropout (models.py:1068-1076)
+        if self.drop < 1 and self.sg is not None:
+            raise NotImplementedError('dropFilt < 1 is not available in the vertex-sharded mode')
+        self.small = bool(first and self.post and model.fused_small and self.sg is None and self.drop >= 1
                           and ops.smallconv_supported(Fin, K, Fout))
         self.saved = None
 
@@ -132,6 +135,13 @@ class _ChebStage(object):
         if self.sg is not None and self.K > 1:
             return self._forward_sharded(x, W, training, save)
         basis = ops.cheb_basis(self.graph, x, self.K, self.mono)           # models.py:1049-1061 / 1094-1103
+        umask = None
+        if training and self.drop < 1:
+            # W * (dropout(ones[Fin, Fout], keep) * keep): a {0, 1} mask shared by the K orders of a filter (1068-1076)
+            u = m._dropout_uniform(self.scope + '/filt', W.new_empty(self.Fin, 1, self.Fout))
+            umask = u.expand(self.Fin, self.K, self.Fout).contiguous().view(self.Fin * self.K, self.Fout)
+            W = ops.dropout(W, umask, self.drop)               # u < keep ? W / keep : 0
+            ops.scale(W, self.drop)
         sums = None
         if self.bn and training:
             sums = m._zeros(2 * self.Fout)
@@ -154,7 +164,7 @@ class _ChebStage(object):
         if save:
             # the pooled output feeds pass 1 of the batch-norm backward (it is the next layer's input anyway)
             lean = self.post and self.bn and training and ops.bn_relu_pool_sums_supported(self.Fout, self.p, self.pool, self.act)
-            self.saved = (x, basis, y, mean, rstd, count, training, out if lean else None)
+            self.saved = (x, basis, y, mean, rstd, count, training, out if lean else None, umask, W if umask is not None else None)
         if self.keep is not None and self.keep != out.shape[1]:
             out = ops.vertex_resize(out, self.keep, 0.0)                   # x[:, :p, :]  (models.py:1138,1157)
         return out
@@ -306,7 +316,7 @@ class _ChebStage(object):
             if need_dx:
                 raise RuntimeError('the fused input layer does not produce an input gradient')
             return self._backward_small(dout)
-        x, basis, y, mean, rstd, count, training, out = self.saved
+        x, basis, y, mean, rstd, count, training, out, umask, Wmasked = self.saved
         self.saved = None
         B, M, Fin = x.shape
         if self.keep is not None and dout.shape[1] != M // self.p:
@@ -331,10 +341,17 @@ class _ChebStage(object):
                     ops.scale(gb, 1.0 / m.world_size)            # the flat all-reduce sums it back
             if two_pass:
                 dy = ops.bn_act_pool_bwd_dy(y, mean, rstd, b, dout, sums, count, self.p, self.pool, self.act)
-        ops.contract_bwd_weight(x, basis, dy, m._P.gviews[self.scope + '/weights'], self.K)
+        gW = m._P.gviews[self.scope + '/weights']
+        if umask is None:
+            ops.contract_bwd_weight(x, basis, dy, gW, self.K)
+        else:                                                # gradient w.r.t. the masked weights, times the mask
+            tmp = torch.zeros_like(gW)
+            ops.contract_bwd_weight(x, basis, dy, tmp, self.K)
+            tmp = ops.dropout(tmp, umask, self.drop)
+            ops.axpy(tmp, gW, self.drop)                     # gW += keep * (u < keep ? tmp / keep : 0)
         if not need_dx:
             return None
-        W = m._P.views[self.scope + '/weights']
+        W = Wmasked if umask is not None else m._P.views[self.scope + '/weights']
         G = ops.contract_bwd_data(dy, W, self.K, Fin)
         return ops.cheb_basis_bwd(self.graph, G, self.mono)
 
@@ -700,8 +717,9 @@ class cgcnn(base_model):
             raise AttributeError("unknown activation '{}'".format(activation))
         if statistics not in (None, 'mean', 'var', 'meanvar', 'max', 'histogram'):
             raise ValueError('Unknown statistical layer {}'.format(statistics))
-        if dropFilt < 1 or extra_loss:
-            raise NotImplementedError('dropFilt / extra_loss are outside the hot path')
+        if extra_loss:
+            raise NotImplementedError('extra_loss (triplet loss) is outside the hot path')
+        self.dropFilt = float(dropFilt)
         self.weighted = bool(weighted)
         if self.sampling == 'equiangular':
             raise NotImplementedError('equiangular sampling is outside the hot path')

@@ -124,14 +124,15 @@ class OracleCgcnn:
         new_state[mm], new_state[mv] = nm, nv
         return y
 
-    def forward(self, x, P, training, new_state=None, drop_masks=None):
+    def forward(self, x, P, training, new_state=None, drop_masks=None, filt_masks=None):
         """`_inference` (+ `_decoder` for dense nets with pooling).  Returns (logits, descriptor)."""
         new_state = {} if new_state is None else new_state
         n = len(self.p)
         pool_layers = [x]                                                    # models.py:1221-1222
         for i in range(n):
             sc = 'conv{}'.format(i + 1)
-            x = self.conv(x, self.Ls[i], P[sc + '/weights'], self.K[i])      # 1229
+            fm = filt_masks.get(sc) if (filt_masks and training) else None   # filter dropout: explicit masks (RNG is not parity)
+            x = self.conv(x, self.Ls[i], P[sc + '/weights'], self.K[i], fm)  # 1229
             if i == n - 1 and len(self.M) == 0:                              # 1232-1234
                 break
             if self.batch_norm[i]:
@@ -184,11 +185,11 @@ class OracleCgcnn:
         wstd = [(P[k], self.std[k]) for k in self.params if k in self.std]
         return ops.loss(logits, labels, self.regression, wstd, self.regularization, self.weighted)
 
-    def loss_and_grads(self, x, labels, training=True, drop_masks=None):
+    def loss_and_grads(self, x, labels, training=True, drop_masks=None, filt_masks=None):
         """Forward + loss + autograd gradients w.r.t. every trainable variable."""
         P = {k: v.clone().requires_grad_(True) for k, v in self.params.items()}
         new_state = {}
-        logits, _ = self.forward(x, P, training, new_state, drop_masks)
+        logits, _ = self.forward(x, P, training, new_state, drop_masks, filt_masks)
         total, data_loss = self.loss(logits, labels, P)
         grads = torch.autograd.grad(total, list(P.values()), allow_unused=True)
         grads = {k: (g if g is not None else torch.zeros_like(P[k])) for k, g in zip(P, grads)}

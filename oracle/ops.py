@@ -20,10 +20,20 @@ def sparse_to_torch(L, dtype=torch.float32):
     return torch.sparse_coo_tensor(idx, val, L.shape).coalesce().to_sparse_csr()
 
 
-def chebyshev5(x, L, W, K):
-    """models.py:1039-1078.  x [N, M, Fin], L torch sparse [M, M], W [Fin*K, Fout]."""
+def drop_filters(W, Fin, K, mask):
+    """models.py:1068-1076 / 1110-1118: W [Fin*K, Fout] times a {0, 1} mask [Fin, Fout] shared by the K orders (the reference
+    draws it as tf.nn.dropout(ones, keep) * keep while training; ones otherwise)."""
+    if mask is None:
+        return W
+    Fout = W.shape[1]
+    return (W.reshape(Fin, K, Fout) * mask.reshape(Fin, 1, Fout).to(W.dtype)).reshape(Fin * K, Fout)
+
+
+def chebyshev5(x, L, W, K, mask=None):
+    """models.py:1039-1078.  x [N, M, Fin], L torch sparse [M, M], W [Fin*K, Fout]; mask: filter dropout."""
     N, M, Fin = x.shape
     Fout = W.shape[1]
+    W = drop_filters(W, Fin, K, mask)
     x0 = x.permute(1, 2, 0)                                   # M x Fin x N        (1049)
     x0 = x0.reshape(M, Fin * N)                               # M x Fin*N          (1050)
     xs = x0.unsqueeze(0)                                      # 1 x M x Fin*N      (1051)
@@ -41,10 +51,11 @@ def chebyshev5(x, L, W, K):
     return y.reshape(N, M, Fout)                              #                    (1078)
 
 
-def monomials(x, L, W, K):
+def monomials(x, L, W, K, mask=None):
     """models.py:1085-1120 (monomial basis x, Lx, L^2x, ...)."""
     N, M, Fin = x.shape
     Fout = W.shape[1]
+    W = drop_filters(W, Fin, K, mask)
     x0 = x.permute(1, 2, 0).reshape(M, Fin * N)
     xs = x0.unsqueeze(0)
     for k in range(1, K):

@@ -231,6 +231,51 @@ def test_learned_histogram_head():
     _check_step(oracle, model, x, labels)
 
 
+@pytest.mark.parametrize('conv', ['chebyshev5', 'monomials'])
+def test_filter_dropout(conv):
+    """dropFilt < 1 (models.py:1068-1076, 1110-1118): while training, W is multiplied by a {0, 1} mask [Fin, Fout] shared by the
+    K orders.  The product draws the mask on the device; the oracle gets the same masks: logits, loss and every gradient agree,
+    and inference uses the full filters."""
+    from deepsphere_tf1_b200 import utils
+    nsides = [8, 4, 2, 2]
+    L, p = utils.build_laplacians(nsides, new=False)
+    keep = 0.6
+    oracle, model = _pair(L, F=[8, 16, 8], K=[3, 3, 3], p=p, batch_norm=[True, False, True], M=[4], statistics='mean', conv=conv,
+                          dropFilt=keep, num_feat_in=2)
+    rs = np.random.RandomState(0)
+    x = rs.randn(4, 768, 2).astype(np.float32)
+    labels = rs.randint(0, 4, size=4).astype(np.int32)
+    xd, ld = model._to_device(x), model._labels_to_device(labels)
+    model._P.g.zero_()
+    model._loss.zero_()
+    logits, _ = model._forward(xd, training=True, save=True)
+    masks = {}
+    for i in range(3):
+        u = model._dropout_u['conv{}/filt'.format(i + 1)]
+        m = (u[:, 0, :] < keep).float().cpu()
+        assert 0 < m.mean() < 1
+        masks['conv{}'.format(i + 1)] = m
+    total, logits_ref, grads, _ = oracle.loss_and_grads(torch.from_numpy(x), torch.from_numpy(labels), training=True, filt_masks=masks)
+    assert_close(logits, logits_ref.reshape(logits.shape), RTOL, 'logits')
+    model._backward(model._loss_fwd_bwd(logits, ld, True))
+    assert_close(model._loss, total.reshape(1), RTOL, 'loss')
+    gmax = max(float(g.abs().max()) for g in grads.values())
+    for name, g in grads.items():
+        assert_close(model._P.gviews[name].reshape(-1), g.reshape(-1), 2 * RTOL, 'grad ' + name, floor=1e-3 * gmax)
+        if name.endswith('/weights') and name.startswith('conv'):
+            mk = masks[name[:5]]
+            Fin, Fout = mk.shape
+            gw = model._P.gviews[name].cpu().reshape(Fin, -1, Fout)
+            dropped = (mk == 0)[:, None, :].expand_as(gw)
+            assert float(gw[dropped].abs().max()) == 0.0                # dropped filters get no gradient
+    # inference: full filters (the moving statistics were updated by the training forward on both sides)
+    for k, v in oracle.state.items():
+        model.set_var(k, v.numpy())
+    ref, _ = oracle.predict_logits(torch.from_numpy(x))
+    out, _ = model._forward(xd, training=False, save=False)
+    assert_close(out, ref.reshape(out.shape), 5e-4, 'eval logits')
+
+
 def test_weighted_cross_entropy_dense_segmentation():
     """weighted=True (models.py:795-802): per-pixel cross-entropy weighted by the hard-coded class weights of the climate
     data set (3 classes), on a small encoder-decoder."""
