@@ -107,7 +107,8 @@ class _ChebStage(object):
         self.mono = getattr(model, 'conv', 'chebyshev5') == 'monomials'       # basis x, Lx, L^2 x, ... (models.py:1085-1120)
         if self.mono and self.sg is not None:
             raise NotImplementedError("conv='monomials' is not available in the vertex-sharded mode")
-        std = 1 / np.sqrt(Fin * (K + 0.5) / 2)                             # models.py:1080-1083
+        # chebyshev5: Xavier-like std (models.py:1080-1083); monomials: `_weight_variable` default 0.1 (models.py:1108, 862)
+        std = 0.1 if self.mono else 1 / np.sqrt(Fin * (K + 0.5) / 2)
         model._P.add(scope + '/weights', (Fin * K, Fout), _truncated_normal(model._rs, (Fin * K, Fout), std), std)
         if bn:
             model._add_bn(scope, Fout)
@@ -410,7 +411,7 @@ class base_model(object):
             end = min(begin + bs, size)
             host_labels = None
             if cache:
-                batch_data, host_labels = next(data_iter)
+                batch_data, host_labels = self._with_batch_axis(*next(data_iter))
                 batch_data = self._as_bmf(np.asarray(batch_data))
             else:
                 tmp = data[begin:end]
@@ -429,6 +430,20 @@ class base_model(object):
     def _as_bmf(a):
         a = np.asarray(a, dtype=np.float32)
         return a[:, :, None] if a.ndim == 2 else a
+
+    def _with_batch_axis(self, data, labels=None):
+        """`LabeledDataset.iter(1)` yields un-batched samples ([M] or [M, F], scalar label) like the reference
+        (data.py:58-60); restore the batch axis so that batch_size == 1 (the vertex-sharded mode) goes through fit /
+        predict(cache=True)."""
+        if self.batch_size != 1 or isinstance(data, torch.Tensor):
+            return data, labels
+        a = np.asarray(data)
+        M0 = self.L[0].shape[0]
+        if a.ndim == 1 or (a.ndim == 2 and a.shape[0] == M0 and M0 != 1):
+            a = a[None]
+            if labels is not None:
+                labels = np.asarray(labels)[None]
+        return a, labels
 
     def get_descriptor(self, data, sess=None, cache=True):
         """Output of the last convolutional stage for every sample (models.py:77-111)."""
@@ -528,17 +543,24 @@ class base_model(object):
         t_cpu, t_wall = process_time(), time.time()
         ckpt_dir = self._get_path('checkpoints')
         start_step = 1
-        if restore and self._restore_latest():
+        # Data parallel (torchrun): rank 0 alone resets / writes the run directories; the others wait at a barrier before
+        # they look at the checkpoint directory, so that every rank takes the same decision.
+        restored = restore and self._latest_checkpoint() is not None
+        if not restored and self.rank == 0:
+            shutil.rmtree(self._get_path('summaries'), ignore_errors=True)
+            shutil.rmtree(ckpt_dir, ignore_errors=True)
+            os.makedirs(ckpt_dir, exist_ok=True)
+        self._barrier()
+        if restored and self._restore_latest():
             start_step = self.global_step + 1
             print('training from last checkpoint')
         else:
             print('training from scratch')
-            shutil.rmtree(self._get_path('summaries'), ignore_errors=True)
-            shutil.rmtree(ckpt_dir, ignore_errors=True)
-            os.makedirs(ckpt_dir)
             self._reset_variables()
-        os.makedirs(self._get_path('summaries'), exist_ok=True)
-        summary = open(os.path.join(self._get_path('summaries'), 'scalars.jsonl'), 'a')
+        summary = None
+        if self.rank == 0:
+            os.makedirs(self._get_path('summaries'), exist_ok=True)
+            summary = open(os.path.join(self._get_path('summaries'), 'scalars.jsonl'), 'a')
 
         accuracies_validation, losses_validation, losses_training = [], [], []
         num_steps = int(self.num_epochs * train_dataset.N / self.batch_size)
@@ -559,7 +581,7 @@ class base_model(object):
             d, l = next(train_iter)
             if not isinstance(d, (np.ndarray, torch.Tensor)):
                 d = d.toarray()
-            return d, l
+            return self._with_batch_axis(d, l)
 
         coming = fetch() if num_steps >= start_step else None
         for step in range(start_step, num_steps + 1):
@@ -593,18 +615,26 @@ class base_model(object):
                 print('  validation {}'.format(string))
                 print('  CPU time: {:.0f}s, wall time: {:.0f}s, perf_time_load: {:.3f}s, perf_time: {:.3f}s'.format(
                     process_time() - t_cpu, time.time() - t_wall, t_end - t_begin_load, times[-1]))
-            summary.write(json.dumps(record) + '\n')
-            summary.flush()
+            if summary is not None:
+                summary.write(json.dumps(record) + '\n')
+                summary.flush()
             self.save_checkpoint(step)
+            self._barrier()                                  # nobody reads a checkpoint rank 0 is still writing
 
         if verbose and not self.regression and accuracies_validation:
             print('validation accuracy: best = {:.2f}, mean = {:.2f}'.format(
                 max(accuracies_validation), np.mean(accuracies_validation[-10:])))
-        summary.close()
+        if summary is not None:
+            summary.close()
         if verbose and times:
             print('time per batch: mean = {:.5f}, var = {:.5f}'.format(np.mean(times), np.var(times)))
         t_step = (time.time() - t_wall) / max(num_steps, 1)
         return accuracies_validation, losses_validation, losses_training, t_step, (np.mean(times) if times else 0.0)
+
+    def _barrier(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.pg)
 
     def get_var(self, name):
         """Value of a variable by its reference name, from the latest checkpoint if one exists

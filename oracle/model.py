@@ -52,7 +52,10 @@ class OracleCgcnn:
         self.std[scope + '/weights'] = std
 
     def _cheb(self, scope, Fin, Fout, K):
-        self._weights(scope, (Fin * K, Fout), 1 / np.sqrt(Fin * (K + 0.5) / 2))   # models.py:1080-1083
+        if self.conv is ops.monomials:
+            self._weights(scope, (Fin * K, Fout), 0.1)                            # models.py:1108 -> 862 (default stddev)
+        else:
+            self._weights(scope, (Fin * K, Fout), 1 / np.sqrt(Fin * (K + 0.5) / 2))   # models.py:1080-1083
 
     def _bias(self, scope, F):
         self.params[scope + '/bias'] = torch.zeros(1, 1, F, dtype=self.dtype)

@@ -48,3 +48,20 @@ def test_constructor_errors_match_the_reference():
         models.cgcnn(L, F=[4, 4], K=[3, 3], p=[4, 4], batch_norm=[True, True], M=[], **common)
     with pytest.raises(ValueError, match='Unknown statistical'):
         models.cgcnn(L, F=[4, 4], K=[3, 3], p=[4, 1], batch_norm=[True, True], M=[], statistics='median', **common)
+
+
+def test_integration_stub_matches_the_header():
+    """The ctypes stub printed in INTEGRATION.md declares as many arguments as include/dsb200.h does (an argument short
+    shifts the stream handle into the workspace slot)."""
+    import re
+    from deepsphere_tf1_b200 import _lib
+    text = open(os.path.join(os.path.dirname(_lib.HEADER), '..', 'INTEGRATION.md')).read()
+    found = re.findall(r'lib\.(dsb200_\w+)\.argtypes = \[([^\]]*)\]', text)
+    assert len(found) >= 2
+    for name, args in found:
+        n = len([a for a in args.split(',') if a.strip()])
+        assert n == len(_lib.PROTOS[name][1]), (name, n, len(_lib.PROTOS[name][1]))
+    for name, args in re.findall(r'lib\.(dsb200_\w+)\(([^)]*)\)', text):
+        if name in _lib.PROTOS and name != 'dsb200_last_error':
+            n = len([a for a in args.split(',') if a.strip()])
+            assert n == len(_lib.PROTOS[name][1]), ('call of ' + name, n, len(_lib.PROTOS[name][1]))
