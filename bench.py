@@ -206,6 +206,67 @@ def spmm_roofline(model, B, iters=60, nsets=6):
             'single_launch_after_rewriting_512MB_us': float(np.median(singles))}
 
 
+def parity_check(L, p, world, rank, dev, tol=1e-4):
+    """ONE training step of the benchmark's own configuration (cosmo config 2, global batch 16, M = 262,144) on the CUDA
+    path and on the CPU oracle from identical weights and inputs: logits, loss and every gradient.  With N ranks the
+    global batch of 16 is split 16/N per rank, so that the check also covers SyncBN, the Gram
+    all-reduce of the fused input layer and the flat gradient all-reduce; the oracle always sees the 16 samples.
+    Returns the dict of the JSON line's `parity` key (rank 0) -- the run fails above `tol`."""
+    import torch
+    import torch.distributed as dist
+    from deepsphere_tf1_b200 import models, ops, optimizers
+    Bg = 16
+    Bl = Bg // world
+    m = models.cgcnn(L=L, p=p, F=F, K=[KCHEB] * 6, batch_norm=[True] * 6, M=[], statistics='mean', num_epochs=1,
+                     batch_size=Bl, eval_frequency=10 ** 9, seed=2, verbose=False, cuda_graph=False,
+                     scheduler=lambda step: 2e-4, optimizer=lambda lr: optimizers.AdamOptimizer(lr, epsilon=1e-8),
+                     dir_name='_bench_parity', device=dev)
+    x, labels = synthetic_batch(Bg, 7)
+    xs, ls = x[rank * Bl:(rank + 1) * Bl], labels[rank * Bl:(rank + 1) * Bl]
+    xd, ld = m._to_device(xs), m._labels_to_device(ls)
+    ops.fill(m._P.g, 0.0)
+    m._loss.zero_()
+    m._arena.zero_()
+    logits, _ = m._forward(xd, training=True, save=True)
+    dlogits = m._loss_fwd_bwd(logits, ld, True)
+    m._backward(dlogits)
+    if world > 1:
+        m._allreduce(m._P.g)
+        ops.scale(m._loss, 1.0 / world)
+        m._allreduce(m._loss)
+        gathered = [torch.empty_like(logits) for _ in range(world)]
+        dist.all_gather(gathered, logits)
+        logits = torch.cat(gathered, dim=0)
+    torch.cuda.synchronize()
+    if rank != 0:
+        return None
+    import warnings
+    from oracle.model import OracleCgcnn
+    warnings.filterwarnings('ignore')
+    torch.set_num_threads(os.cpu_count())
+    o = OracleCgcnn(L, F=F, K=[KCHEB] * 6, p=p, batch_norm=[True] * 6, M=[], statistics='mean')
+    for name, v in o.params.items():
+        o.params[name] = m._P.views[name].detach().cpu().reshape(v.shape).clone()
+    total, ologits, grads, _ = o.loss_and_grads(torch.from_numpy(x), torch.from_numpy(labels), True)
+
+    def rel(a, b, floor=0.0):
+        a, b = a.detach().double().cpu().numpy().reshape(-1), b.detach().double().cpu().numpy().reshape(-1)
+        return float(np.abs(a - b).max() / max(np.abs(b).max(), floor, 1e-30))
+    gmax = max(float(g.abs().max()) for g in grads.values())
+    worst, worst_name = 0.0, ''
+    for name, g in grads.items():
+        e = rel(m._P.gviews[name], g, floor=1e-3 * gmax)
+        if e > worst:
+            worst, worst_name = e, name
+    out = {'loss_rel': abs(float(m._loss) - float(total)) / max(abs(float(total)), 1e-30),
+           'max_logit_rel': rel(logits, ologits), 'max_grad_rel': worst, 'worst_gradient': worst_name,
+           'loss': float(m._loss), 'oracle_loss': float(total), 'global_batch': Bg, 'ranks': world, 'tolerance': tol,
+           'what': 'one training step of the benchmark configuration (M=262,144, batch 16 split over the ranks): CUDA path '
+                   'vs CPU oracle from identical weights; errors relative to the largest expected magnitude'}
+    out['ok'] = bool(out['loss_rel'] <= tol and out['max_logit_rel'] <= tol and out['max_grad_rel'] <= tol)
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -293,6 +354,8 @@ def run_gpu(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = float(tt[0]), float(tt[1])
 
+    parity = None if args.no_parity else parity_check(L, p, world, rank, dev)
+
     # kernels per step, counted by the library itself on one eager (non-graph) step
     c0 = _lib.kernel_launches()
     model._advance_hyper()
@@ -300,6 +363,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
     per_step = _lib.kernel_launches() - c0
 
+    exit_code = 0
     if rank == 0:
         roof = spmm_roofline(model, B_local)
         cpu = None
@@ -324,9 +388,14 @@ def run_gpu(args):
                     'api': 'train_step(pinned host batch, next_batch=...): the following batch is copied on a copy stream '
                            'while the step runs (as fit() does); loss read back every step'},
             'gpu_launches': int(per_step * args.steps),
-            'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'final_loss': last_loss,
+            'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'parity': parity, 'final_loss': last_loss,
         }
         print(json.dumps(out))
+        if parity is not None and not parity['ok']:
+            sys.stderr.write('PARITY FAILED: {}\n'.format(json.dumps(parity)))
+            exit_code = 3
+    if world == 1 and exit_code:
+        sys.exit(exit_code)
     if world > 1:
         # Captured CUDA graphs hold NCCL work; tearing the process group down under them can block
         # (seen with NCCL 2.28 / torch 2.11).  Release the graph, meet at a barrier, flush and leave.
@@ -335,7 +404,7 @@ def run_gpu(args):
         dist.barrier()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        os._exit(exit_code)
 
 
 def main():
@@ -347,6 +416,7 @@ def main():
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
     ap.add_argument('--no-graph', action='store_true', help='issue every launch from Python instead of one CUDA graph')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-parity', action='store_true', help='skip the full-size CUDA-vs-oracle check of one training step')
     ap.add_argument('--recompute-lmax', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -14,6 +14,17 @@ void count_launch(int n = 1);     // host-side tally of kernel launches issued b
 #define DSB_LAUNCH_CHECK() \
     do { ::dsb200::count_launch(); cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) { ::dsb200::set_error(cudaGetErrorString(e__)); return (int)e__; } return 0; } while (0)
 
+// Tuning knobs: read from the environment ONCE per process (first use), never per launch.  Knobs that switch parts of the
+// work off or dump debug data (timing experiments: wrong results) exist only in -DDSB200_EXPERIMENTS builds.
+int env_int_raw(const char* name, int dflt);
+#define DSB_ENV_INT(name, dflt) \
+    ([&]() -> int { static const int v__ = ::dsb200::env_int_raw(name, -2147483647); return v__ == -2147483647 ? (int)(dflt) : v__; }())
+#ifdef DSB200_EXPERIMENTS
+#define DSB_EXPERIMENT_INT(name, dflt) DSB_ENV_INT(name, dflt)
+#else
+#define DSB_EXPERIMENT_INT(name, dflt) (dflt)
+#endif
+
 constexpr int kNumSMs = 148;       // B200: 2 dies x 74 SMs
 
 static inline int grid_for(long long work_items, int threads, int ctas_per_sm = 8) {

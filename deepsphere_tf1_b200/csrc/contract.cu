@@ -355,8 +355,8 @@ int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y,
                      double* bn_sums, cudaStream_t s);                      // contract_mma.cu
 int contract_wgrad_mma(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K, int Fout,
                        cudaStream_t s);                                     // contract_mma.cu
-static bool wgrad_mma_enabled() { const char* e = getenv("DSB200_WGRAD_MMA"); return e ? atoi(e) != 0 : true; }   // default on
-static bool fwd_mma_enabled() { const char* e = getenv("DSB200_FWD_MMA"); return e ? atoi(e) != 0 : true; }   // default on
+static bool wgrad_mma_enabled() { return DSB_ENV_INT("DSB200_WGRAD_MMA", 1) != 0; }   // default on
+static bool fwd_mma_enabled() { return DSB_ENV_INT("DSB200_FWD_MMA", 3) != 0; }   // default on
 }  // namespace dsb200
 
 extern "C" int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const float* W, float* Y,

@@ -502,8 +502,7 @@ int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y,
     if (Fin != kMmaFin || Fout != kMmaFout || K < 1 || K > kMmaMaxK) return 1;
     if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y) & 15) != 0) return 1;
     const long long cap = 2LL * kNumSMs;
-    const char* e = getenv("DSB200_FWD_MMA");
-    const int variant = e ? atoi(e) : 3;                             // 3 (default): 64 rows per warp, one CTA per SM (100.6 us with
+    const int variant = DSB_ENV_INT("DSB200_FWD_MMA", 3);                            // 3 (default): 64 rows per warp, one CTA per SM (100.6 us with
                                                                      // the sums at cosmo layer 2); 1: 32 rows, two CTAs (105.8 us)
     if (variant == 2) {                                              // register version (experiment)
         const long long nblk = (R + 31) / 32;

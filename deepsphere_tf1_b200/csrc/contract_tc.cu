@@ -515,11 +515,7 @@ struct RowGemmPlan {
     size_t smem, wbytes;
 };
 
-static int env_int(const char* name, int dflt)
-{
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
-}
+#define env_int(name, dflt) DSB_ENV_INT(name, dflt)
 
 // Shared-memory plan; returns false if the shape does not fit the tensor-core path.
 static bool plan_rowgemm_n(int red_per_plane, int planes, int Npad, bool can_stream, int ctas, RowGemmPlan* pl, size_t reserve);
@@ -606,8 +602,12 @@ static int launch_rowgemm(RowGemmParams& p, size_t smem, int ctas, float* image,
         configured = true;
     }
     p.wpack = image;
-    p.nostore = env_int("DSB200_RG_NOSTORE", 0);
+    p.nostore = DSB_EXPERIMENT_INT("DSB200_RG_NOSTORE", 0);
+#ifdef DSB200_EXPERIMENTS
     { const char* d = getenv("DSB200_RG_DBG"); p.dbg = (d && *d) ? (long long*)strtoull(d, nullptr, 0) : nullptr; }
+#else
+    p.dbg = nullptr;
+#endif
     if (image) {
         const int total = p.nkb * 2 * p.Npad * p.kc;
         pack_w_kernel<MODE><<<(total + 255) / 256, 256, 0, s>>>(p, image);

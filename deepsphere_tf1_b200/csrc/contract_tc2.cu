@@ -225,12 +225,12 @@ size_t colgemm_workspace_bytes(int Fin, int K) { return (size_t)K * Fin * kImgRo
 int contract_fwd_tc_cols(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
                          double* bn_sums, void* workspace, cudaStream_t s)
 {
-    if (getenv("DSB200_NO_COLGEMM")) return 1;
+    if (DSB_ENV_INT("DSB200_NO_COLGEMM", 0)) return 1;
     if (!workspace || R < kTileN || R > 0x7fffff00LL || Fout > 64 || (Fout & 3) || (Fin & 15)) return 1;
     // Measured (tools/sweep_gemm.py): 77 vs 90 us at cosmo layer 3 (Fin = 32), but 181 vs 136 us at layer 2 (Fin = 16, Fout = 32:
     // half of the 128 accumulator lanes and half of the epilogue warps idle, and TMA delivers 64-byte rows no faster than ~4 ns
     // each per SM).  DSB200_CG_ALL=1 forces this kernel wherever the shape fits.
-    if (Fin < 32 && !getenv("DSB200_CG_ALL")) return 1;
+    if (Fin < 32 && !DSB_ENV_INT("DSB200_CG_ALL", 0)) return 1;
     if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y | (uintptr_t)workspace) & 15) != 0) return 1;
     ColGemmParams p;
     p.kc = 16; p.swz = 2;
@@ -240,7 +240,7 @@ int contract_fwd_tc_cols(const float* x0, const float* xk, const float* W, float
     const size_t stage = 2 * (size_t)kTileN * p.kc * 4;
     const size_t fixed = 1024 + 3 * kCgStagesMax * 8 + 4 * 8 + 16 + 64;
     int ctas = 1;
-    if (const char* e = getenv("DSB200_CG_CTAS")) ctas = atoi(e) == 2 ? 2 : 1;
+    { const int e = DSB_ENV_INT("DSB200_CG_CTAS", 0); if (e) ctas = e == 2 ? 2 : 1; }
     size_t budget = (size_t)(227 * 1024) / ctas - (ctas > 1 ? 1024 : 0);
     if (ctas == 2 && wbytes + fixed + 2 * stage > budget) { ctas = 1; budget = 227 * 1024; }
     if (wbytes + fixed + (ctas == 2 ? 2 : 3) * stage > budget) return 1;

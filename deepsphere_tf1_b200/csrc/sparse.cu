@@ -13,6 +13,11 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static thread_local char g_err[256] = "";
+int env_int_raw(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 void set_error(const char* msg) {
     int i = 0;
     for (; msg[i] && i < 255; ++i) g_err[i] = msg[i];
@@ -203,14 +208,14 @@ static int spmm_launch(const int32_t* rowptr, const int32_t* col, const float* v
     if (vec == 4) {
         const int chunks = F / 4;
         int CB = chunks < 64 ? chunks : 64;                        // column slab: at most 1 KB of a row
-        if (const char* e = getenv("DSB200_SPMM_CB")) { const int v = atoi(e); if (v > 0 && v < CB) CB = v; }
+        { const int v = DSB_ENV_INT("DSB200_SPMM_CB", 0); if (v > 0 && v < CB) CB = v; }
         int lg2 = 0;
         while ((1 << lg2) < CB && lg2 < 5) ++lg2;
         const int passes = (CB + (1 << lg2) - 1) >> lg2;           // 1 or 2
         // rows per tile: ~64 KB of x per tile (it has to live in L1 next to its halo), 32..512 rows
         int TR = 32768 / (CB * 16);
         TR = TR < 32 ? 32 : TR > 128 ? 128 : TR;                   // 128-row tiles measured best on B200 (tools/sweep_spmm.py)
-        if (const char* e = getenv("DSB200_SPMM_TR")) { const int v = atoi(e); if (v > 0) TR = v; }
+        { const int v = DSB_ENV_INT("DSB200_SPMM_TR", 0); if (v > 0) TR = v; }
         // keep enough tiles to fill the machine a few times over
         while (TR > 16 && (long long)B * ((M + TR - 1) / TR) * ((chunks + CB - 1) / CB) < 8LL * kNumSMs) TR >>= 1;
         if (passes <= 1) launch_rows<1>(rowptr, col, val, width, B, M, chunks, lg2, TR, CB, x, y, z, out, alpha, beta, gamma, s);
@@ -342,7 +347,7 @@ spmm_rec_kernel(const int2* __restrict__ rec, int width, int B, int M, int chunk
     }
 }
 
-static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+#define env_int(name, dflt) DSB_ENV_INT(name, dflt)
 
 constexpr int kNotQualified = -1000;
 // returns kNotQualified when the shape does not qualify (caller falls back to the row-major kernels)
@@ -450,7 +455,7 @@ cheb_small_kernel(const int32_t* __restrict__ col, const float* __restrict__ val
 static int cheb_small_launch(const int32_t* col, const float* val, int width, int B, int M, int F, int K, const float* x0, float* planes,
                              bool bwd, cudaStream_t s)
 {
-    if (getenv("DSB200_NO_SMALL") || K < 2 || F % 16 || (width != 9 && width != 7)) return 1;
+    if (DSB_ENV_INT("DSB200_NO_SMALL", 0) || K < 2 || F % 16 || (width != 9 && width != 7)) return 1;
     const size_t smem = (size_t)3 * M * 64;
     if (smem > 64 * 1024 || M < 16) return 1;           // measured: wins at M = 256 (18.6 vs 25.9 us), loses at M = 1024 (59 vs 34 us: 64 CTAs only)
     if ((((uintptr_t)x0 | (uintptr_t)planes) & 15) != 0) return 1;

@@ -27,6 +27,12 @@
 
 namespace dsb200 {
 
+#ifdef DSB200_EXPERIMENTS
+#define PIPE_ABLATE(a) ((a).ablate)
+#else
+#define PIPE_ABLATE(a) 0
+#endif
+
 struct PipeArgs {
     const int2* rec;        // [T][W][TR]  (local column, value bits); local column < TR: tile row, else TR + halo slot
     const int32_t* ext;     // [T][HC]     global row of every halo slot (unused slots: the tile's first row)
@@ -115,7 +121,7 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
         if (role != 0 && lane != 0) return;
         // halo rows of the NEXT item are fetched (tile_ext, all HC slots: unused ones repeat the tile's first row) while
         // this one waits for its stage: no global-memory latency between a stage falling empty and its refill
-        const int nhalo = (a.ablate & 2) ? 0 : HC * NCH;
+        const int nhalo = (PIPE_ABLATE(a) & 2) ? 0 : HC * NCH;
         auto tile_of = [&](int it) -> int {
             const long long item = i0 + it * istep;
             return a.order == 0 ? (int)(item / a.B) : (int)(item % a.T);
@@ -202,8 +208,8 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
             float4* ob = a.out + ((long long)b * a.M + r0) * NCH;
             mbar_wait(full + s, (uint32_t)k & 1u);
             for (int g = warp * GPW + sub; g < G && 4 * g < nt; g += CW * GPW) {
-                if (a.ablate & 16) {
-                    for (int r = 0; r < 4; ++r) if (4 * g + r < nt && !(a.ablate & 8)) ob[(4 * g + r) * NCH + lg] = xs[(4 * g + r) * NCH + lg];
+                if (PIPE_ABLATE(a) & 16) {
+                    for (int r = 0; r < 4; ++r) if (4 * g + r < nt && !(PIPE_ABLATE(a) & 8)) ob[(4 * g + r) * NCH + lg] = xs[(4 * g + r) * NCH + lg];
                     continue;
                 }
                 const uint4 c0 = *reinterpret_cast<const uint4*>(wrec + 16 * G + g);
@@ -230,7 +236,7 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
                     float4 res = make_float4(acc.x * a.alpha, acc.y * a.alpha, acc.z * a.alpha, acc.w * a.alpha);
                     if (HASY) { const float4 t = ys[row * NCH + lg]; res.x = fmaf(a.beta, t.x, res.x); res.y = fmaf(a.beta, t.y, res.y); res.z = fmaf(a.beta, t.z, res.z); res.w = fmaf(a.beta, t.w, res.w); }
                     if (HASZ) { const float4 t = zs[row * NCH + lg]; res.x = fmaf(a.gamma, t.x, res.x); res.y = fmaf(a.gamma, t.y, res.y); res.z = fmaf(a.gamma, t.z, res.z); res.w = fmaf(a.gamma, t.w, res.w); }
-                    if (row < nt && !(a.ablate & 8)) ob[row * NCH + lg] = res;
+                    if (row < nt && !(PIPE_ABLATE(a) & 8)) ob[row * NCH + lg] = res;
                 }
             }
             __syncwarp();
@@ -259,11 +265,11 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
         mbar_wait(full + s, (uint32_t)k & 1u);
         const int rend = min(nt, (warp + 1) * rpw);
         for (int r = warp * rpw + sub; r < rend; r += RPP) {
-            if (a.ablate & 16) { if (!(a.ablate & 8)) ob[r * NCH + lg] = xs[r * NCH + lg]; continue; }
+            if (PIPE_ABLATE(a) & 16) { if (!(PIPE_ABLATE(a) & 8)) ob[r * NCH + lg] = xs[r * NCH + lg]; continue; }
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
-                if ((a.ablate & 1) && j > 0) break;
+                if ((PIPE_ABLATE(a) & 1) && j > 0) break;
                 const int2 rc = srec[j * TR + r];
                 const float w = __int_as_float(rc.y);
                 const float4 v = xs[rc.x * NCH + lg];
@@ -272,7 +278,7 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
             float4 res = make_float4(acc.x * a.alpha, acc.y * a.alpha, acc.z * a.alpha, acc.w * a.alpha);
             if (HASY) { const float4 t = ys[r * NCH + lg]; res.x = fmaf(a.beta, t.x, res.x); res.y = fmaf(a.beta, t.y, res.y); res.z = fmaf(a.beta, t.z, res.z); res.w = fmaf(a.beta, t.w, res.w); }
             if (HASZ) { const float4 t = zs[r * NCH + lg]; res.x = fmaf(a.gamma, t.x, res.x); res.y = fmaf(a.gamma, t.y, res.y); res.z = fmaf(a.gamma, t.z, res.z); res.w = fmaf(a.gamma, t.w, res.w); }
-            if (!(a.ablate & 8)) ob[r * NCH + lg] = res;
+            if (!(PIPE_ABLATE(a) & 8)) ob[r * NCH + lg] = res;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
@@ -324,7 +330,7 @@ extern "C" int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, 
     DSB_REQUIRE((align & 15) == 0, "spmm_pipe: pointers must be 16-byte aligned");
     const int nch = F / 4, extra = (y ? 1 : 0) + (z ? 1 : 0);
     int S = 4;
-    { const char* e = getenv("DSB200_PIPE_STAGES"); if (e && atoi(e) >= 2 && atoi(e) <= 4) S = atoi(e); }
+    { const int e = DSB_ENV_INT("DSB200_PIPE_STAGES", 0); if (e >= 2 && e <= 4) S = e; }
     while (S > 2 && pipe_smem(width, TR, HC, nch, extra, S) > 113 * 1024) --S;
     const size_t smem = pipe_smem(width, TR, HC, nch, extra, S);
     DSB_REQUIRE(smem <= 113 * 1024, "spmm_pipe: tile does not fit in shared memory");
@@ -333,10 +339,10 @@ extern "C" int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, 
     a.x = (const float4*)x; a.y = (const float4*)y; a.z = (const float4*)z; a.out = (float4*)out;
     a.T = ntiles; a.TR = TR; a.HC = HC; a.B = B; a.M = M; a.S = S;
     a.alpha = alpha; a.beta = beta; a.gamma = gamma;
-    { const char* e = getenv("DSB200_PIPE_ABLATE"); a.ablate = e ? atoi(e) : 0; }
-    { const char* e = getenv("DSB200_PIPE_ORDER"); a.order = e ? atoi(e) : 2; }
+    a.ablate = DSB_EXPERIMENT_INT("DSB200_PIPE_ABLATE", 0);
+    a.order = DSB_ENV_INT("DSB200_PIPE_ORDER", 2);
     int ctas = 2;
-    { const char* e = getenv("DSB200_PIPE_CTAS"); if (e && atoi(e) == 1) ctas = 1; }
+    if (DSB_ENV_INT("DSB200_PIPE_CTAS", 2) == 1) ctas = 1;
     const long long nitems = (long long)ntiles * B;
     const long long cap = (long long)ctas * kNumSMs;
     const int grid = (int)(nitems < cap ? nitems : cap);

@@ -13,98 +13,6 @@ import torch
 from scipy import sparse
 
 ELL_MAX_WIDTH = 16
-TILE_SLOTS = 10            # neighbour slots of a row record of the tiled kernels (csrc/sparse_tiled.cu: RowRec)
-TILE_ROWS = 256            # rows per tile: 16 x 16 pixels in HEALPix nested order
-TILE_SMEM_ROWS = 1700      # (tile + ring 1) + (tile + ring 1 + ring 2) local rows that fit shared memory with >= 2 CTAs per SM
-
-
-def _bucket_slots(rows, base):
-    """Local slots for halo rows that keep the low 3 bits of the global id: local = base + 8*q + (g & 7).
-    Returns (local ids, size of the region, a multiple of 8)."""
-    if len(rows) == 0:
-        return np.zeros(0, np.int64), 0
-    b = (rows & 7).astype(np.int64)
-    order = np.argsort(b, kind='stable')
-    cnt = np.bincount(b, minlength=8)
-    start = np.concatenate([[0], np.cumsum(cnt)[:-1]])
-    pos = np.empty(len(rows), np.int64)
-    pos[order] = np.arange(len(rows)) - start[b[order]]
-    return base + 8 * pos + b, 8 * int(cnt.max())
-
-
-class TilePlan(object):
-    """Row tiles with two halo rings for the shared-memory tiled recurrence kernels (csrc/sparse_tiled.cu).
-
-    Tile t owns the consecutive rows [t*TR, (t+1)*TR).  Ring 1 = rows referenced by the tile's rows that lie
-    outside the tile, ring 2 = rows referenced by ring 1 outside tile + ring 1.
-    LOCAL indices: tile rows 0..nt-1 (offset in the tile); ring 1 in [ntp, n1), ring 2 in [n1, n2) with
-    ntp = nt rounded up to 8.  A halo row keeps the low 3 bits of its global id in its local index (8 vertices that
-    are neighbours on the sphere then sit in 8 different shared-memory bank groups); unused slots are holes.
-    Every local row < n1 has a record of 16 words -- 10 fp32 values, 5 words of uint16 local columns, 1 pad --
-    stored word-major per tile ([16][n1]) so that consecutive threads read consecutive words.  Holes have zero
-    values and point at themselves; `ext` gives the global row of every local index >= nt (holes: the tile's
-    first row, a harmless load)."""
-
-    def __init__(self, col, val, device, TR=TILE_ROWS):
-        M, W = col.shape
-        self.valid = False
-        if W > TILE_SLOTS or M == 0:
-            return
-        T = (M + TR - 1) // TR
-        info = np.zeros((T, 4), np.int32)
-        recs, exts = [], []
-        woff = eoff = 0
-        n1cap = n2cap = 0
-        for t in range(T):
-            r0, r1 = t * TR, min(M, (t + 1) * TR)
-            nt = r1 - r0
-            ntp = (nt + 7) // 8 * 8
-            c_t = col[r0:r1]
-            u = np.unique(c_t)
-            ring1 = u[(u < r0) | (u >= r1)]
-            u2 = np.unique(col[ring1])
-            u2 = u2[(u2 < r0) | (u2 >= r1)]
-            ring2 = np.setdiff1d(u2, ring1, assume_unique=True)
-            l1, s1 = _bucket_slots(ring1, ntp)
-            n1 = ntp + s1
-            l2, s2 = _bucket_slots(ring2, n1)
-            n2 = n1 + s2
-            if n1 + n2 > TILE_SMEM_ROWS or n2 > 65535:
-                return                                   # vertex order without locality: keep the gather kernels
-            # global -> local lookup over tile + rings
-            gid = np.concatenate([np.arange(r0, r1), ring1, ring2]).astype(np.int64)
-            lid = np.concatenate([np.arange(nt), l1, l2]).astype(np.int64)
-            order = np.argsort(gid)
-            gid_s, lid_s = gid[order], lid[order]
-            rows_g = np.concatenate([np.arange(r0, r1), ring1])            # real rows that get a record
-            rows_l = np.concatenate([np.arange(nt), l1]).astype(np.int64)
-            cg = col[rows_g].astype(np.int64)
-            pos = np.searchsorted(gid_s, cg)
-            assert np.array_equal(gid_s[pos], cg)
-            words = np.zeros((16, n1), np.uint32)
-            lc = np.repeat(np.arange(n1, dtype=np.uint32)[:, None], TILE_SLOTS, axis=1)   # holes / unused slots: own index
-            lc[rows_l, :W] = lid_s[pos].astype(np.uint32)
-            v = np.zeros((n1, TILE_SLOTS), np.float32)
-            v[rows_l, :W] = val[rows_g]
-            words[:TILE_SLOTS] = v.view(np.uint32).T
-            words[TILE_SLOTS:TILE_SLOTS + 5] = (lc[:, 0::2] | (lc[:, 1::2] << 16)).T
-            ext = np.full(n2 - nt, r0, np.int32)
-            ext[l1 - nt] = ring1
-            ext[l2 - nt] = ring2
-            recs.append(words.ravel())
-            exts.append(ext)
-            info[t] = (woff, n1, n2, eoff)
-            woff += 16 * n1
-            eoff += n2 - nt
-            n1cap, n2cap = max(n1cap, n1), max(n2cap, n2)
-        self.info = torch.from_numpy(info).to(device)
-        self.recs = torch.from_numpy(np.concatenate(recs).view(np.int32)).to(device)
-        self.ext = torch.from_numpy(np.concatenate(exts + [np.zeros(1, np.int32)])).to(device)
-        self.ntiles, self.TR, self.n1cap, self.n2cap, self.width = T, TR, n1cap, n2cap, W
-        self.valid = True
-
-    def args(self):
-        return (self.info, self.recs, self.ext, self.ntiles, self.TR, self.n1cap, self.n2cap, self.width)
 
 
 PIPE_TILE_BYTES = 8192     # x bytes of one row tile of the pipelined kernel (csrc/sparse_pipe.cu): TR = 8192 / (4 F) rows
@@ -223,117 +131,10 @@ class PipePlan(object):
         return (self.rec, self.ext, self.nh, self.T, self.TR, self.HC, self.width, 0)
 
 
-BLOCK_ROWS = 16            # rows per block of the tensor-core product (csrc/sparse_blk.cu): the M of mma.m16n8k8
-BLOCK_MAX_ROWS = 4 << 20   # no block plan above this many rows (2.7 KB per block)
-
-
-class BlockPlan(object):
-    """Dense [16 x 8*KS] blocks of L for the tensor-core sparse product (csrc/sparse_blk.cu).
-
-    Block b = rows [16 b, 16 b + 16).  `cols[b]` lists its distinct columns in ascending order, padded with the
-    block's first row; `frags[b]` holds the block's values in mma.m16n8k8 A-fragment order:
-    frags[b, s, lane] = (A[g, 8s+t], A[g+8, 8s+t], A[g, 8s+t+4], A[g+8, 8s+t+4]),  g = lane // 4, t = lane % 4."""
-
-    def __init__(self, col, val, device):
-        M, W = col.shape
-        self.valid = False
-        if M == 0 or M > BLOCK_MAX_ROWS:
-            return
-        nb = (M + BLOCK_ROWS - 1) // BLOCK_ROWS
-        Mp = nb * BLOCK_ROWS
-        c = np.empty((Mp, W), np.int64)
-        v = np.zeros((Mp, W), np.float32)
-        c[:M], v[:M] = col, val
-        if Mp > M:                                            # ragged last block: empty rows
-            c[M:] = (nb - 1) * BLOCK_ROWS
-        first = (np.arange(nb, dtype=np.int64) * BLOCK_ROWS)[:, None]
-        cb = np.where(v.reshape(nb, -1) != 0, c.reshape(nb, -1), first)       # unused slots point at the block itself
-        order = np.argsort(cb, axis=1, kind='stable')
-        srt = np.take_along_axis(cb, order, axis=1)
-        new = np.ones(srt.shape, bool)
-        new[:, 1:] = srt[:, 1:] != srt[:, :-1]
-        pos_sorted = np.cumsum(new, axis=1) - 1                                # union index of every sorted entry
-        nu = pos_sorted[:, -1] + 1
-        KS = int((nu.max() + 7) // 8)
-        KS = max(KS, 5)
-        if KS > 7:
-            return                                            # too many distinct columns per block: keep the gather kernels
-        K8 = 8 * KS
-        pos = np.empty_like(pos_sorted)
-        np.put_along_axis(pos, order, pos_sorted, axis=1)                      # union index of every original entry
-        cols = np.repeat(first, K8, axis=1)
-        bi = np.repeat(np.arange(nb), srt.shape[1]).reshape(srt.shape)
-        cols[bi[new], pos_sorted[new]] = srt[new]
-        A = np.zeros((nb, BLOCK_ROWS, K8), np.float32)
-        vb = v.reshape(nb, -1)
-        ri = np.tile(np.repeat(np.arange(BLOCK_ROWS), W), (nb, 1))
-        nz = vb != 0
-        A[bi[nz], ri[nz], pos[nz]] = vb[nz]
-        lane = np.arange(32)
-        g, t = lane // 4, lane % 4
-        s8 = 8 * np.arange(KS)[:, None]
-        frags = np.stack([A[:, g[None, :], s8 + t[None, :]], A[:, g[None, :] + 8, s8 + t[None, :]],
-                          A[:, g[None, :], s8 + t[None, :] + 4], A[:, g[None, :] + 8, s8 + t[None, :] + 4]], axis=-1)
-        self.cols_np = cols.astype(np.int32)
-        self.frags_np = np.ascontiguousarray(frags, dtype=np.float32)
-        if device is not None:
-            self.cols = torch.from_numpy(self.cols_np).to(device)
-            self.frags = torch.from_numpy(self.frags_np).to(device)
-        self.nblocks, self.KS = nb, KS
-        self.valid = True
-
-
-STILE_ROWS = 128           # rows per staged tile (csrc/sparse_stile.cu) = 8 blocks
-STILE_MAX_ROWS = 340       # tile + ring-1 rows that fit shared memory for 4 samples, 2 CTAs per SM
-
-
-class StagedBlockPlan(object):
-    """Plan of the staged-tile + tensor-core-block sparse product (csrc/sparse_stile.cu): the blocks of `BlockPlan`
-    with LOCAL column indices inside their 128-row tile: tile rows 0..nt-1, then the tile's ring-1 halo rows in
-    ascending global order (`ext`)."""
-
-    def __init__(self, col, val, device):
-        self.valid = False
-        bp = BlockPlan(col, val, None)
-        if not bp.valid:
-            return
-        M = col.shape[0]
-        T = (M + STILE_ROWS - 1) // STILE_ROWS
-        cols = bp.cols_np
-        lcols = np.zeros(cols.shape, np.uint16)
-        tinfo = np.zeros((T, 4), np.int32)
-        exts, eoff, n1cap = [], 0, 0
-        bpt = STILE_ROWS // BLOCK_ROWS
-        for t in range(T):
-            r0, r1 = t * STILE_ROWS, min(M, (t + 1) * STILE_ROWS)
-            nt = r1 - r0
-            cb = cols[t * bpt:(t + 1) * bpt].astype(np.int64)
-            u = np.unique(cb)
-            ring = u[(u < r0) | (u >= r1)]
-            n1 = nt + len(ring)
-            if n1 > STILE_MAX_ROWS:
-                return
-            inside = (cb >= r0) & (cb < r1)
-            lcols[t * bpt:(t + 1) * bpt] = np.where(inside, cb - r0, nt + np.searchsorted(ring, cb)).astype(np.uint16)
-            tinfo[t] = (eoff, n1, 0, 0)
-            exts.append(ring.astype(np.int32))
-            eoff += len(ring)
-            n1cap = max(n1cap, n1)
-        self.tinfo = torch.from_numpy(tinfo).to(device)
-        self.ext = torch.from_numpy(np.concatenate(exts + [np.zeros(1, np.int32)])).to(device)
-        self.lcols = torch.from_numpy(lcols.view(np.int16)).to(device)
-        self.frags = torch.from_numpy(bp.frags_np).to(device)
-        self.ntiles, self.nblocks, self.KS, self.n1cap = T, bp.nblocks, bp.KS, n1cap
-        self.valid = True
-
-    def args(self):
-        return (self.tinfo, self.ext, self.lcols, self.frags, self.ntiles, self.nblocks, self.KS, self.n1cap)
-
-
 class DeviceGraph(object):
     """One Laplacian level on the GPU.  `.fwd` / `.bwd` = (rowptr | None, col, val, width)."""
 
-    def __init__(self, L, device, force_csr=False, tiled=False, LT=None, blocks=False, staged=False):
+    def __init__(self, L, device, force_csr=False, LT=None):
         """`LT`: the matrix to use for the transposed products instead of L.T (vertex-sharded mode: the rows of
         L^T this rank owns are not the transpose of the rows of L it owns)."""
         L = sparse.csr_matrix(L, dtype=np.float32)
@@ -352,10 +153,6 @@ class DeviceGraph(object):
             LT.sort_indices()
             self.max_degree = max(self.max_degree, int(np.diff(LT.indptr).max()))
         self.is_ell = (not force_csr) and self.max_degree <= ELL_MAX_WIDTH
-        self._want_tiles, self._want_blocks, self._want_staged = tiled, blocks, staged
-        self.fwd_tiles = self.bwd_tiles = None
-        self.fwd_blocks = self.bwd_blocks = None
-        self.fwd_staged = self.bwd_staged = None
         self.fwd_rec = self.bwd_rec = None
         self.fwd = self._pack(L, 'fwd')
         if LT is None:
@@ -366,9 +163,6 @@ class DeviceGraph(object):
         if self.symmetric_pattern and np.array_equal(LT.data, L.data):
             self.bwd = self.fwd
             self.bwd_rec = self.fwd_rec
-            self.bwd_tiles = self.fwd_tiles
-            self.bwd_blocks = self.fwd_blocks
-            self.bwd_staged = self.fwd_staged
         else:
             self.bwd = self._pack(LT, 'bwd')
 
@@ -383,15 +177,6 @@ class DeviceGraph(object):
             slot = np.arange(A.nnz) - np.repeat(A.indptr[:-1], counts)
             col[rows, slot] = A.indices
             val[rows, slot] = A.data
-            if self._want_blocks:
-                bp = BlockPlan(col, val, self.device)
-                setattr(self, which + '_blocks', bp if bp.valid else None)
-            if self._want_staged:
-                sp = StagedBlockPlan(col, val, self.device)
-                setattr(self, which + '_staged', sp if sp.valid else None)
-            if self._want_tiles:
-                plan = TilePlan(col, val, self.device)
-                setattr(self, which + '_tiles', plan if plan.valid else None)
             # packed slot-major records rec[j, m] = (col, val bits): one contiguous piece per slot for the consecutive
             # rows of a warp (csrc/sparse.cu: spmm_rec_kernel); same bits as dsb200_ell_pack produces on the device
             rec = np.empty((width, self.M, 2), dtype=np.int32)
@@ -479,6 +264,6 @@ class ShardedGraph(object):
                 self.send[q] = mine.astype(np.int32)
         self.device = device
         if device is not None:
-            self.graph = DeviceGraph(self.L_local, device, tiled=False, LT=self.LT_local)
+            self.graph = DeviceGraph(self.L_local, device, LT=self.LT_local)
             self.M = self.Me
             self.send_dev = {q: torch.from_numpy(v).to(device) for q, v in self.send.items()}

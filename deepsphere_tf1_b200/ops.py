@@ -30,14 +30,8 @@ def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, tra
         out = _new((B, M, F), x)
     which = 'bwd' if transpose else 'fwd'
     pp = _pipe(graph, which, B, M, F) if rows is None else None
-    sp = _staged(graph, which, B, F) if rows is None and pp is None else None
-    bp = _blocks(graph, which, B, F) if rows is None and sp is None and pp is None else None
     if pp is not None:
         call('spmm_pipe', *pp.args(USE_DENSE_GROUPS), B, M, F, x, y, z, out, alpha, beta, gamma)
-    elif sp is not None:
-        call('spmm_stile', *sp.args(), B, M, F, x, y, z, out, alpha, beta, gamma)
-    elif bp is not None:
-        call('spmm_blk', bp.cols, bp.frags, bp.nblocks, bp.KS, B, M, F, x, y, z, out, alpha, beta, gamma)
     elif rowptr is None:
         rec = _rec(graph, which) if rows is None else None         # the record stride is the graph's M
         if rec is not None:
@@ -83,58 +77,6 @@ def _rec(graph, which):
     return getattr(graph, which + '_rec', None) if USE_RECORDS else None
 
 
-USE_BLOCKS = False        # tensor-core block formulation of the sparse product (csrc/sparse_blk.cu): correct, not yet faster
-BLOCKS_MIN_SAMPLES = 2    # below this the block records are not amortised: gather kernel
-USE_TILED = False         # shared-memory tiled recurrence (two orders per launch) when the graph has a tile plan
-
-
-USE_STAGED = False        # staged row tile + tensor-core blocks (csrc/sparse_stile.cu): correct, on par with the gather kernel at best
-STAGED_MIN_SAMPLES = 2
-
-
-def set_staged(on):
-    global USE_STAGED
-    USE_STAGED = bool(on)
-
-
-def _staged(graph, which, B, F):
-    sp = getattr(graph, which + '_staged', None)
-    return sp if (USE_STAGED and sp is not None and F % 16 == 0 and B >= STAGED_MIN_SAMPLES) else None
-
-
-def set_blocks(on):
-    global USE_BLOCKS
-    USE_BLOCKS = bool(on)
-
-
-def _blocks(graph, which, B, F):
-    bp = getattr(graph, which + '_blocks', None)
-    return bp if (USE_BLOCKS and bp is not None and F % 8 == 0 and B >= BLOCKS_MIN_SAMPLES) else None
-
-
-def set_tiled(on):
-    global USE_TILED
-    USE_TILED = bool(on)
-
-
-def _tiles(graph, which, F):
-    plan = getattr(graph, which + '_tiles', None)
-    return plan if (USE_TILED and plan is not None and F % 4 == 0) else None
-
-
-def cheb_tiled_step(graph, x, y=None, z=None, u=None, out1=None, out2=None, coef1=(1.0, 0.0, 0.0), coef2=None,
-                    transpose=False):
-    """T1 = a1 L x + b1 y + c1 z -> out1;  with coef2: T2 = a2 L T1 + b2 x + c2 u -> out2  (one launch)."""
-    B, M, F = x.shape
-    plan = getattr(graph, ('bwd' if transpose else 'fwd') + '_tiles')
-    if plan is None:
-        raise RuntimeError('this graph has no tile plan')
-    a2, b2, c2 = coef2 if coef2 is not None else (0.0, 0.0, 0.0)
-    call('cheb_tiled_step', *plan.args(), B, M, F, x, y, z, u, out1, out2 if coef2 is not None else None,
-         coef1[0], coef1[1], coef1[2], a2, b2, c2)
-    return out1, out2
-
-
 def cheb_basis(graph, x, K, monomial=False):
     """Orders 1..K-1 of the Chebyshev basis of x (models.py:1049-1061) as [K-1, B, M, F]; `monomial`: the basis
     x, Lx, L^2 x, ... of `cgcnn.monomials` instead (models.py:1094-1103)."""
@@ -146,12 +88,7 @@ def cheb_basis(graph, x, K, monomial=False):
         for k in range(1, K):                                                  # X_k = L X_(k-1)
             spmm(graph, x if k == 1 else basis[k - 2], out=basis[k - 1])
         return basis
-    plan = _tiles(graph, 'fwd', F)
-    if plan is not None:
-        call('cheb_basis_tiled', *plan.args(), B, M, F, K, x, basis)
-        return basis
-    if (_pipe(graph, 'fwd', B, M, F) is not None or _blocks(graph, 'fwd', B, F) is not None
-            or _staged(graph, 'fwd', B, F) is not None):
+    if _pipe(graph, 'fwd', B, M, F) is not None:
         spmm(graph, x, out=basis[0])                                           # X1 = L X0
         for k in range(2, K):                                                  # Xk = 2 L X(k-1) - X(k-2)
             spmm(graph, basis[k - 2], x if k == 2 else basis[k - 3], None, out=basis[k - 1], alpha=2.0, beta=-1.0)
@@ -173,13 +110,7 @@ def cheb_basis_bwd(graph, G, monomial=False):
         for k in range(K - 2, -1, -1):
             spmm(graph, G[k + 1], G[k], None, out=G[k], alpha=1.0, beta=1.0, transpose=True)
         return G[0]
-    plan = _tiles(graph, 'bwd', F)
-    if plan is not None and K >= 2:
-        S = _new((K, B, M, F), G)
-        call('cheb_basis_bwd_tiled', *plan.args(), B, M, F, K, G, S)
-        return S[0]
-    if (_pipe(graph, 'bwd', B, M, F) is not None or _blocks(graph, 'bwd', B, F) is not None
-            or _staged(graph, 'bwd', B, F) is not None) and K >= 2:
+    if _pipe(graph, 'bwd', B, M, F) is not None and K >= 2:
         # A_(K-1) = G_(K-1);  A_k = G_k + c_k L^T A_(k+1) - A_(k+2), in place on the planes of G (see csrc/sparse.cu)
         for k in range(K - 2, -1, -1):
             a2 = G[k + 2] if k + 2 <= K - 1 else None

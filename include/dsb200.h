@@ -51,24 +51,6 @@ const char* dsb200_last_error(void);
 /* number of CUDA kernels this library has launched in this process (all threads) */
 long long dsb200_kernel_launches(void);
 
-/* the same product on the tensor cores (csrc/sparse_blk.cu): 16 consecutive rows and their at most 8*ksteps distinct
- * columns are one dense [16 x 8*ksteps] block of L, multiplied with mma.sync TF32 (3xTF32 split: fp32-level accuracy).
- * blk_cols int32[nblocks][8*ksteps] = the column list of every block (padding: the block's first row, zero weights);
- * blk_frags float[nblocks][ksteps][32][4] = the block in m16n8k8 A-fragment order.  F % 8 == 0, ksteps in 5..7. */
-int dsb200_spmm_blk(const int32_t* blk_cols, const float* blk_frags, int nblocks, int ksteps, int B, int M, int F,
-                    const float* x, const float* y, const float* z, float* out,
-                    float alpha, float beta, float gamma, void* stream);
-
-/* staged row tile + tensor-core blocks (csrc/sparse_stile.cu): a CTA stages the x rows of a 128-row tile and of its
- * ring-1 halo (cp.async) for a group of samples and multiplies the tile's eight 16-row blocks with mma.sync TF32
- * (3xTF32).  tile_info int32[ntiles][4] = (first entry in tile_ext, rows of tile + halo, 0, 0); tile_ext = global ids
- * of the halo rows; blk_lcols uint16[nblocks][8*ksteps] = LOCAL column (0..rows-1) of every block column;
- * blk_frags as in dsb200_spmm_blk.  F % 16 == 0; out must not alias x (it may alias y or z). */
-int dsb200_spmm_stile(const int32_t* tile_info, const int32_t* tile_ext, const uint16_t* blk_lcols, const float* blk_frags,
-                      int ntiles, int nblocks, int ksteps, int n1cap, int B, int M, int F,
-                      const float* x, const float* y, const float* z, float* out,
-                      float alpha, float beta, float gamma, void* stream);
-
 /* ---- K1: one sparse-Laplacian product with fused recurrence arithmetic, for all B samples
  *      out[b] = alpha * L x[b] + beta * y[b] + gamma * z[b]    (y, z NULL when beta/gamma == 0;
  *      out may alias y or z)
@@ -121,28 +103,6 @@ int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, const int32
                      int ntiles, int TR, int HC, int width, int dense, int B, int M, int F,
                      const float* x, const float* y, const float* z, float* out,
                      float alpha, float beta, float gamma, void* stream);
-
-/* ---- K1, shared-memory tiled: one or two recurrence steps per launch (csrc/sparse_tiled.cu)
- *      T1 = a1 * L x  + b1 * y + c1 * z  -> out1 (may be NULL in a two-step launch)
- *      T2 = a2 * L T1 + b2 * x + c2 * u  -> out2 (NULL: single step)
- * The tile plan (graph.py: TilePlan) is built once per Laplacian from its ELL packing: tile_info int32[ntiles][4]
- * = (first record, rows of tile + ring 1, rows incl. ring 2, first ext entry); tile_recs = 64-byte records
- * (10 fp32 values, 10 uint16 local columns) of the tile + ring-1 rows; tile_ext = global ids of the halo rows.
- * F % 4 == 0; outputs must not alias x (nor y / z in a two-step launch).  Replaces the same TF ops as
- * dsb200_spmm_ell (models.py:1056-1061), two at a time. */
-int dsb200_cheb_tiled_step(const int32_t* tile_info, const void* tile_recs, const int32_t* tile_ext,
-                           int ntiles, int TR, int n1cap, int n2cap, int width, int B, int M, int F,
-                           const float* x, const float* y, const float* z, const float* u,
-                           float* out1, float* out2, float a1, float b1, float c1, float a2, float b2, float c2,
-                           void* stream);
-/* all orders 1..K-1 of the basis, two per launch (same result as dsb200_cheb_basis) */
-int dsb200_cheb_basis_tiled(const int32_t* tile_info, const void* tile_recs, const int32_t* tile_ext,
-                            int ntiles, int TR, int n1cap, int n2cap, int width, int B, int M, int F, int K,
-                            const float* x0, float* basis, void* stream);
-/* adjoint recurrence with the tile plan of L^T: G [K][B,M,F] read only, S [K][B,M,F] scratch, result S[0] */
-int dsb200_cheb_basis_bwd_tiled(const int32_t* tile_info, const void* tile_recs, const int32_t* tile_ext,
-                                int ntiles, int TR, int n1cap, int n2cap, int width, int B, int M, int F, int K,
-                                const float* G, float* S, void* stream);
 
 /* ---- K2: dense contraction over (fin, k)  (tf.matmul, models.py:1062-1078)
  *   Y[r, fo] = sum_{k, fi} X_k[r, fi] * W[fi*K + k, fo],   r < R = B*M

@@ -19,9 +19,9 @@ def dev():
     return torch.device('cuda', 0)
 
 
-def _graph(L, dev, force_csr=False, tiled=False, blocks=False, staged=False):
+def _graph(L, dev, force_csr=False):
     from deepsphere_tf1_b200.graph import DeviceGraph
-    return DeviceGraph(L, dev, force_csr=force_csr, tiled=tiled, blocks=blocks, staged=staged)
+    return DeviceGraph(L, dev, force_csr=force_csr)
 
 
 def _oracle_basis(L, x, K):
@@ -224,109 +224,6 @@ def _contraction_case(dev, shape):
     dW = torch.zeros(Fin * K, Fout, device=dev)
     ops.contract_bwd_weight(x0, xk, dy.to(dev), dW, K)
     assert_close(dW, dW_ref, RTOL, 'dW')
-
-
-@pytest.mark.parametrize('F', [4, 8, 16, 32, 64, 24])
-@pytest.mark.parametrize('graph', ['full', 'patch', 'ragged', 'nonsym_values'])
-def test_tiled_recurrence_steps(dev, F, graph):
-    """Shared-memory tiled kernel (csrc/sparse_tiled.cu): single and fused double steps in their general form
-    against dense float64 products, on graphs with several tiles, a single tile, a ragged last tile and
-    non-symmetric values (separate plan for L^T)."""
-    from scipy import sparse
-    from deepsphere_tf1_b200 import ops
-    L = {'full': lambda: healpix_L(16), 'patch': lambda: healpix_L(32, order=2), 'ragged': lambda: healpix_L(8).tocsr()[:700, :700],
-         'nonsym_values': lambda: healpix_L(8)}[graph]()
-    L = sparse.csr_matrix(L, dtype=np.float32)
-    if graph == 'nonsym_values':
-        L = sparse.csr_matrix(L.multiply(sparse.csr_matrix(1.0 + 0.1 * np.random.RandomState(0).rand(*L.shape))), dtype=np.float32)
-    M = L.shape[0]
-    g = _graph(L, dev, tiled=True)
-    assert g.fwd_tiles is not None and g.bwd_tiles is not None
-    B = 3
-    rs = np.random.RandomState(F)
-    x, y, z, u = [torch.from_numpy(rs.randn(B, M, F).astype(np.float32)) for _ in range(4)]
-    Ld = torch.from_numpy(L.toarray()).double()
-    mul = lambda A, t: torch.einsum('ij,bjf->bif', A, t.double())
-    xd, yd, zd, ud = [t.to(dev) for t in (x, y, z, u)]
-    o1 = torch.empty_like(xd)
-    ops.cheb_tiled_step(g, xd, yd, zd, out1=o1, coef1=(0.5, -1.5, 0.25))
-    assert_close(o1, 0.5 * mul(Ld, x) - 1.5 * y.double() + 0.25 * z.double(), RTOL, 'single step')
-    o1, o2 = torch.empty_like(xd), torch.empty_like(xd)
-    ops.cheb_tiled_step(g, xd, yd, zd, ud, o1, o2, coef1=(2.0, 1.0, -1.0), coef2=(2.0, -1.0, 1.0), transpose=True)
-    t1 = 2 * mul(Ld.t(), x) + y.double() - z.double()
-    assert_close(o1, t1, RTOL, 'double step, T1')
-    assert_close(o2, 2 * mul(Ld.t(), t1) - x.double() + u.double(), RTOL, 'double step, T2')
-    # T1 not stored, no y / z / u
-    o2.zero_()
-    ops.cheb_tiled_step(g, xd, out2=o2, coef1=(1.0, 0.0, 0.0), coef2=(2.0, -1.0, 0.0))
-    assert_close(o2, 2 * mul(Ld, mul(Ld, x)) - x.double(), RTOL, 'double step without T1 output')
-
-
-@pytest.mark.parametrize('path', ['blocks', 'staged'])
-@pytest.mark.parametrize('F', [8, 16, 32, 64, 24])
-@pytest.mark.parametrize('B', [2, 5, 16])
-@pytest.mark.parametrize('graph', ['full', 'patch', 'ragged', 'nonsym_values'])
-def test_block_mma_sparse_product(dev, F, B, graph, path):
-    """Tensor-core block formulation (csrc/sparse_blk.cu, 3xTF32) against dense float64 products: general form with
-    y and z, the transposed matrix, in-place accumulation -- within the fp32 bar."""
-    from scipy import sparse
-    from deepsphere_tf1_b200 import ops
-    L = {'full': lambda: healpix_L(16), 'patch': lambda: healpix_L(32, order=2), 'ragged': lambda: healpix_L(8).tocsr()[:700, :700],
-         'nonsym_values': lambda: healpix_L(8)}[graph]()
-    L = sparse.csr_matrix(L, dtype=np.float32)
-    if graph == 'nonsym_values':
-        L = sparse.csr_matrix(L.multiply(sparse.csr_matrix(1.0 + 0.1 * np.random.RandomState(0).rand(*L.shape))), dtype=np.float32)
-    M = L.shape[0]
-    if path == 'staged' and F % 16:
-        pytest.skip('the staged kernel takes 16-feature slabs')
-    g = _graph(L, dev, blocks=path == 'blocks', staged=path == 'staged')
-    ops.set_blocks(path == 'blocks')
-    ops.set_staged(path == 'staged')
-    if path == 'blocks':
-        assert g.fwd_blocks is not None and ops._blocks(g, 'fwd', B, F) is not None
-    else:
-        assert g.fwd_staged is not None and g.bwd_staged is not None and ops._staged(g, 'fwd', B, F) is not None
-    rs = np.random.RandomState(F + B)
-    x, y, z = [torch.from_numpy(rs.randn(B, M, F).astype(np.float32)) for _ in range(3)]
-    Ld = torch.from_numpy(L.toarray()).double()
-    mul = lambda A, t: torch.einsum('ij,bjf->bif', A, t.double())
-    out = ops.spmm(g, x.to(dev), y.to(dev), z.to(dev), alpha=0.5, beta=-1.5, gamma=0.25)
-    assert_close(out, 0.5 * mul(Ld, x) - 1.5 * y.double() + 0.25 * z.double(), 2e-6, 'block product')
-    yd = y.to(dev).clone()
-    ops.spmm(g, x.to(dev), yd, None, out=yd, alpha=2.0, beta=1.0, transpose=True)
-    assert_close(yd, 2 * mul(Ld.t(), x) + y.double(), 2e-6, 'transposed, in place on y')
-    # the whole basis and the adjoint through the block path, against the gather kernels
-    K = 4
-    G = torch.from_numpy(rs.randn(K, B, M, F).astype(np.float32)).to(dev)
-    basis, dx = ops.cheb_basis(g, x.to(dev), K), ops.cheb_basis_bwd(g, G.clone())
-    ops.set_blocks(False)
-    ops.set_staged(False)
-    ref = ops.spmm(g, x.to(dev), y.to(dev), z.to(dev), alpha=0.5, beta=-1.5, gamma=0.25)
-    assert_close(out, ref, 2e-6, 'block vs gather kernel')
-    assert_close(basis, ops.cheb_basis(g, x.to(dev), K), 1e-5, 'basis')
-    assert_close(dx, ops.cheb_basis_bwd(g, G.clone()), 1e-5, 'adjoint')
-
-
-@pytest.mark.parametrize('K', [2, 3, 4, 5, 6])
-def test_tiled_basis_and_adjoint_equal_the_gather_path(dev, K):
-    from deepsphere_tf1_b200 import ops
-    L = healpix_L(16)
-    g = _graph(L, dev, tiled=True)
-    rs = np.random.RandomState(K)
-    x = torch.from_numpy(rs.randn(2, L.shape[0], 16).astype(np.float32)).to(dev)
-    G = torch.from_numpy(rs.randn(K, 2, L.shape[0], 16).astype(np.float32)).to(dev)
-    try:
-        ops.set_tiled(True)
-        basis = ops.cheb_basis(g, x, K)
-        dx = ops.cheb_basis_bwd(g, G.clone())
-        ops.set_tiled(False)
-        basis_ref = ops.cheb_basis(g, x, K)
-        dx_ref = ops.cheb_basis_bwd(g, G.clone())
-    finally:
-        ops.set_tiled(False)
-    assert_close(basis, basis_ref, 1e-5, 'basis')
-    assert_close(dx, dx_ref, 1e-5, 'adjoint')
-    assert_close(basis, _oracle_basis(L, x.cpu(), K)[1:], RTOL, 'basis vs oracle')
 
 
 @pytest.mark.parametrize('kind', ['ell', 'csr', 'nonsym'])

@@ -57,7 +57,7 @@ def timeit(name, layer, nbytes, fn):
 
 for li in [int(v) for v in args.layers.split(',')]:
     i = li - 1
-    g = DeviceGraph(L[i], dev, tiled=True, blocks=True, staged=True)
+    g = DeviceGraph(L[i], dev)
     M, Fin, Fout, pool = g.M, Fins[i], bench.F[i], p[i]
     R = B * M
     X = 4 * R * Fin
@@ -66,30 +66,9 @@ for li in [int(v) for v in args.layers.split(',')]:
     x1 = torch.randn(B, M, Fin, device=dev)
     out = torch.empty_like(x)
     W = torch.randn(Fin * K, Fout, device=dev) * 0.1
-    ops.set_blocks(False)
-    ops.set_staged(False)
-    timeit('spmm step (k>=2), gather', li, 3 * X + 8 * g.nnz, lambda: ops.spmm(g, x1, x, None, out=out, alpha=2.0, beta=-1.0))
-    ops.set_blocks(True)
-    if Fin % 8 == 0:
-        timeit('spmm step (k>=2), block mma', li, 3 * X + 8 * g.nnz, lambda: ops.spmm(g, x1, x, None, out=out, alpha=2.0, beta=-1.0))
-    ops.set_blocks(False)
-    ops.set_staged(True)
-    if Fin % 16 == 0 and g.fwd_staged is not None:
-        timeit('spmm step (k>=2), staged blocks', li, 3 * X + 8 * g.nnz, lambda: ops.spmm(g, x1, x, None, out=out, alpha=2.0, beta=-1.0))
-    ops.set_staged(False)
+    timeit('spmm step (k>=2)', li, 3 * X + 8 * g.nnz, lambda: ops.spmm(g, x1, x, None, out=out, alpha=2.0, beta=-1.0))
     xi, x1i, outi = x.view(1, M, B * Fin), x1.view(1, M, B * Fin), out.view(1, M, B * Fin)
     timeit('spmm step, interleaved', li, 3 * X + 8 * g.nnz, lambda: ops.spmm(g, x1i, xi, None, out=outi, alpha=2.0, beta=-1.0))
-    if g.fwd_tiles is not None and Fin % 4 == 0:
-        out2 = torch.empty_like(x)
-        timeit('tiled single step (k>=2)', li, 3 * X + 8 * g.nnz,
-               lambda: ops.cheb_tiled_step(g, x1, x, out1=out, coef1=(2.0, -1.0, 0.0)))
-        timeit('tiled pair (k, k+1), k>=2', li, 4 * X + 8 * g.nnz,
-               lambda: ops.cheb_tiled_step(g, x1, x, out1=out, out2=out2, coef1=(2.0, -1.0, 0.0), coef2=(2.0, -1.0, 0.0)))
-        if li == 1:
-            o1i, o2i = out.view(1, M, B * Fin), out2.view(1, M, B * Fin)
-            timeit('tiled pair, interleaved', li, 4 * X + 8 * g.nnz,
-                   lambda: ops.cheb_tiled_step(g, x1i, xi, out1=o1i, out2=o2i, coef1=(2.0, -1.0, 0.0), coef2=(2.0, -1.0, 0.0)))
-        del out2
     basis = ops.cheb_basis(g, x, K)
     timeit('cheb_basis (4 steps)', li, (2 + 3 * 3) * X + 4 * 8 * g.nnz, lambda: ops.cheb_basis(g, x, K))
     sums = torch.zeros(2 * Fout, dtype=torch.float64, device=dev)

@@ -16,7 +16,6 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--layer', type=int, default=2)
 ap.add_argument('--batch', type=int, default=16)
 ap.add_argument('--interleave', action='store_true')
-ap.add_argument('--tiled', action='store_true', help='shared-memory tiled kernel: one single step and one fused pair')
 args = ap.parse_args()
 torch.cuda.set_device(0)
 dev = torch.device('cuda', 0)
@@ -31,11 +30,6 @@ flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
 out2 = torch.empty_like(x1)
 for _ in range(3):
     ops.fill(flush, 0.0)
-    if args.tiled:
-        ops.cheb_tiled_step(g, x1, x0, out1=out, coef1=(2.0, -1.0, 0.0))
-        ops.fill(flush, 0.0)
-        ops.cheb_tiled_step(g, x1, x0, out1=out, out2=out2, coef1=(2.0, -1.0, 0.0), coef2=(2.0, -1.0, 0.0))
-    else:
-        ops.spmm(g, x1, x0, None, out=out, alpha=2.0, beta=-1.0)
+    ops.spmm(g, x1, x0, None, out=out, alpha=2.0, beta=-1.0)
 torch.cuda.synchronize()
 print('ok', shape)
