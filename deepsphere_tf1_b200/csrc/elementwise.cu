@@ -567,7 +567,17 @@ fc_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W, const fl
 
 __device__ __forceinline__ float fc_dz(float yv, float dyv, int act)
 {
-    return (act == DSB200_ACT_RELU) ? (yv > 0.f ? dyv : 0.f) : dyv;
+    // derivative of the activation expressed through its OUTPUT y (the fc layers keep y only)
+    switch (act) {
+        case DSB200_ACT_RELU: return yv > 0.f ? dyv : 0.f;
+        case DSB200_ACT_ELU: return yv > 0.f ? dyv : dyv * (yv + 1.f);                 // exp(z) = y + 1 for z <= 0
+        case DSB200_ACT_TANH: return dyv * (1.f - yv * yv);
+        case DSB200_ACT_SIGMOID: return dyv * yv * (1.f - yv);
+        case DSB200_ACT_LEAKY_RELU: return yv > 0.f ? dyv : 0.2f * dyv;
+        case DSB200_ACT_SOFTPLUS: return dyv * (1.f - expf(-yv));                      // sigmoid(z) = 1 - exp(-softplus(z))
+        case DSB200_ACT_RELU6: return (yv > 0.f && yv < 6.f) ? dyv : 0.f;
+        default: return dyv;
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1062,7 +1072,6 @@ extern "C" int dsb200_fc_bwd(const float* x, const float* W, const float* y, con
                              float* db, int N, int Min, int Mout, int act, void* stream)
 {
     DSB_REQUIRE(x && W && y && dy && dW && N > 0 && Min > 0 && Mout > 0, "fc_bwd: bad arguments");
-    DSB_REQUIRE(act == DSB200_ACT_RELU || act == DSB200_ACT_IDENTITY, "fc_bwd: only relu / identity");
     if (dx) { fc_bwd_dx_kernel<<<(N * Min + 255) / 256, 256, 0, STREAM>>>(W, y, dy, dx, N, Min, Mout, act); count_launch(); }
     fc_bwd_dw_kernel<<<((Min + 1) * Mout + 255) / 256, 256, 0, STREAM>>>(x, y, dy, dW, db, N, Min, Mout, act);
     DSB_LAUNCH_CHECK();

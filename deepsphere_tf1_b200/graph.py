@@ -131,10 +131,98 @@ class PipePlan(object):
         return (self.rec, self.ext, self.nh, self.T, self.TR, self.HC, self.width, 0)
 
 
+STENCIL_T = 16             # a fused-recurrence tile = 16 x 16 pixels = 256 consecutive NESTED indices (csrc/cheb_tile.cu)
+STENCIL_W = 12             # floats per stencil record: 9 weights (dy, dx row-major) + 3 of padding (three 16-byte pieces)
+
+
+class StencilPlan(object):
+    """Tile plan of the fused Chebyshev recurrence (csrc/cheb_tile.cu): all K - 1 sparse products of a layer in ONE launch.
+
+    HEALPix NESTED order is Morton order inside a base face, so T*T consecutive indices are a T x T square of pixels and
+    the 8-neighbour Laplacian is a 3 x 3 stencil with per-pixel weights on it.  For a recurrence of S = K - 1 steps a tile
+    is staged in shared memory with an S-ring halo as a flat (T + 2S)^2 image; step s is then computed on the image
+    shrunk by s + 1 rings, every neighbour read from shared memory, nothing but the results touching HBM.
+      p2v int32[nt, P, P]      vertex shown at every image position (P = T + 2S; row = iy, column = ix), -1 = none
+      wts float32[nt, P-2, P-2, 12]  the 3 x 3 weights of L (or L^T) at every position that is ever computed:
+                                entry 3 (dy + 1) + (dx + 1) multiplies the value at (row + dy, column + dx)
+    The flat image crosses face boundaries with healpix's own face tables; around the 8 vertices of the base tessellation
+    where only three faces meet no flat image exists.  The plan is therefore VERIFIED against the matrix itself: every
+    stored entry of every row that is computed must sit at one of the 9 image positions around its row.  `valid` is False
+    otherwise (or when the vertex order is not whole aligned tiles), and the per-step kernels stay in charge."""
+
+    def __init__(self, col, val, nside, ids, S, device, T=STENCIL_T):
+        from . import healpix as hp
+        self.valid = False
+        M, W = col.shape
+        T2 = T * T
+        if M == 0 or M % T2 or S < 1 or S > 7 or nside < T:
+            return
+        ids = np.arange(M, dtype=np.int64) if ids is None else np.asarray(ids, dtype=np.int64)
+        if len(ids) != M:
+            return
+        nt = M // T2
+        blocks = ids.reshape(nt, T2)
+        base = blocks[:, 0]
+        if np.any(base % T2) or np.any(blocks != base[:, None] + np.arange(T2)):
+            return
+        npface = int(nside) * int(nside)
+        if int(ids.max()) >= 12 * npface:
+            return
+        ix0, iy0, face = hp.nest2xyf(nside, base)
+        P = T + 2 * S
+        off = np.arange(P, dtype=np.int64) - S
+        x = (ix0[:, None, None] + off[None, None, :]) + np.zeros((1, P, 1), np.int64)          # [nt, row, column]
+        y = (iy0[:, None, None] + off[None, :, None]) + np.zeros((1, 1, P), np.int64)
+        f = np.broadcast_to(face[:, None, None], x.shape)
+        code = np.full(x.shape, 4, dtype=np.int64)
+        lo, hi = x < 0, x >= nside
+        x = np.where(lo, x + nside, np.where(hi, x - nside, x))
+        code += hi.astype(np.int64) - lo.astype(np.int64)
+        lo, hi = y < 0, y >= nside
+        y = np.where(lo, y + nside, np.where(hi, y - nside, y))
+        code += 3 * (hi.astype(np.int64) - lo.astype(np.int64))
+        nf = hp._FACE_NB[code, f]
+        bits = hp._SWAP[code, f >> 2]
+        x = np.where(bits & 1, nside - x - 1, x)
+        y = np.where(bits & 2, nside - y - 1, y)
+        swap = (bits & 4) != 0
+        x, y = np.where(swap, y, x), np.where(swap, x, y)
+        nested = np.where(nf >= 0, hp.xyf2nest(nside, x, y, np.maximum(nf, 0)), -1)
+        # nested pixel number -> vertex (position in `ids`)
+        order = np.argsort(ids, kind='stable')
+        sid = ids[order]
+        pos = np.clip(np.searchsorted(sid, nested), 0, M - 1)
+        p2v = np.where((nested >= 0) & (sid[pos] == nested), order[pos], -1).astype(np.int64)
+        # 3 x 3 weights on the computed region [1, P-1)^2, verified against the matrix
+        Q = P - 2
+        ctr = p2v[:, 1:P - 1, 1:P - 1]
+        have = ctr >= 0
+        vc = np.where(have, ctr, 0)
+        cols = col[vc].astype(np.int64)                                     # [nt, Q, Q, W]
+        vals = np.where(have[..., None], val[vc], np.float32(0))
+        wts = np.zeros((nt, Q, Q, STENCIL_W), np.float32)
+        matched = np.zeros(cols.shape, bool)
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                nb = p2v[:, 1 + dy:P - 1 + dy, 1 + dx:P - 1 + dx]
+                hit = (cols == nb[..., None]) & (nb[..., None] >= 0) & ~matched
+                wts[..., 3 * (dy + 1) + (dx + 1)] = np.where(hit, vals, np.float32(0)).sum(axis=-1, dtype=np.float32)
+                matched |= hit
+        if np.any((vals != 0) & ~matched):
+            return                                                          # some neighbour is not on the flat image
+        self.p2v_np = np.ascontiguousarray(p2v.astype(np.int32))
+        self.wts_np = np.ascontiguousarray(wts)
+        self.nt, self.T, self.S, self.P, self.M = nt, T, S, P, M
+        if device is not None:
+            self.p2v = torch.from_numpy(self.p2v_np).to(device)
+            self.wts = torch.from_numpy(self.wts_np).to(device)
+        self.valid = True
+
+
 class DeviceGraph(object):
     """One Laplacian level on the GPU.  `.fwd` / `.bwd` = (rowptr | None, col, val, width)."""
 
-    def __init__(self, L, device, force_csr=False, LT=None):
+    def __init__(self, L, device, force_csr=False, LT=None, nested=None):
         """`LT`: the matrix to use for the transposed products instead of L.T (vertex-sharded mode: the rows of
         L^T this rank owns are not the transpose of the rows of L it owns)."""
         L = sparse.csr_matrix(L, dtype=np.float32)
@@ -143,6 +231,8 @@ class DeviceGraph(object):
         if L.shape[0] != L.shape[1]:
             raise ValueError('Laplacian must be square')
         self.M = L.shape[0]
+        # `nested` = (nside, nested pixel number of every vertex | None): HEALPix geometry for the fused tile recurrence
+        self.nested = nested
         self.nnz = int(L.nnz)
         self.device = device
         counts = np.diff(L.indptr)
@@ -203,6 +293,21 @@ class DeviceGraph(object):
             cache[key] = plan if plan.valid else None
         plan = cache[key]
         return plan if plan is not None and plan.fits(F) else None
+
+    def stencil_plan(self, which, S):
+        """StencilPlan of L ('fwd') or L^T ('bwd') for a recurrence of S steps (cached), or None."""
+        if not self.is_ell or self.nested is None:
+            return None
+        if which == 'bwd' and self.bwd is self.fwd:
+            which = 'fwd'
+        cache = self.__dict__.setdefault('_stencil_plans', {})
+        key = (which, S)
+        if key not in cache:
+            _, col, val, width = getattr(self, which)
+            nside, ids = self.nested
+            plan = StencilPlan(col.cpu().numpy(), val.cpu().numpy(), nside, ids, S, self.device)
+            cache[key] = plan if plan.valid else None
+        return cache[key]
 
     def bytes_stored(self):
         """Bytes one sparse product reads for the matrix (8 per stored entry)."""

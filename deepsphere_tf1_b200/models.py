@@ -367,8 +367,6 @@ class _FcStage(object):
         model._P.add(scope + '/weights', (Min, Mout), _truncated_normal(model._rs, (Min, Mout), std), std)
         if bias:
             model._P.add(scope + '/bias', (Mout,), np.zeros(Mout, np.float32))
-        if act not in ('relu', 'identity'):
-            raise NotImplementedError('fully connected layers support relu / identity activations')
 
     def forward(self, x, training, save):
         m = self.m
@@ -839,7 +837,10 @@ class cgcnn(base_model):
         if self.vertex_shard:
             self._graphs[i] = ShardedGraph(self.L[i], self.rank, self.world_size, self.device)
         else:
-            self._graphs[i] = DeviceGraph(self.L[i], self.device)
+            # HEALPix geometry of the level (nside, nested pixel numbers) when `deepsphere` built the graphs: lets the
+            # fused tile recurrence (csrc/cheb_tile.cu) address the vertices as pixel squares
+            nested = getattr(self, '_nested', None)
+            self._graphs[i] = DeviceGraph(self.L[i], self.device, nested=nested[i] if nested else None)
         return self._graphs[i]
 
     def _build_program(self, seed):
@@ -1292,4 +1293,7 @@ class deepsphere(cgcnn):
             self.ratio = nsides[0][1] / nsides[0][0] if isinstance(nsides[0], tuple) else 1.
         self.nsides = nsides
         self.pygsp_graphs = [None] * len(nsides)
+        if sampling == 'healpix' and not full:
+            idx = indexes if indexes is not None else [None] * len(nsides)
+            self._nested = [(int(n), idx[i]) for i, n in enumerate(nsides[:len(L)])]
         super(deepsphere, self).__init__(L=L, p=p, **kwargs)

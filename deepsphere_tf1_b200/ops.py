@@ -77,6 +77,33 @@ def _rec(graph, which):
     return getattr(graph, which + '_rec', None) if USE_RECORDS else None
 
 
+USE_TILE = True           # fused tile recurrence (csrc/cheb_tile.cu): all K - 1 sparse products of a layer in one launch
+TILE_MIN_ITEMS = int(os.environ.get('DSB200_TILE_MIN_ITEMS', 64))     # (tile, sample, 16-feature chunk) items below which the
+                                                                      # one-launch gather recurrence of the coarse levels stays
+
+
+def set_tile(on):
+    global USE_TILE
+    USE_TILE = bool(on)
+
+
+TILE_BWD_MAX_ITEMS = int(os.environ.get('DSB200_TILE_BWD_MAX_ITEMS', 1024))   # adjoint form: above this many items the per-step
+                                                                              # pipelined kernels are faster (tools/bench_tile.py:
+                                                                              # the G_k planes come straight from L2 / HBM there)
+
+
+def _tile(graph, which, K, B, F):
+    if not USE_TILE or K < 2 or K > 8 or F % 16 or not hasattr(graph, 'stencil_plan'):
+        return None
+    plan = graph.stencil_plan(which, K - 1)
+    if plan is None:
+        return None
+    items = plan.nt * B * (F // 16)
+    if items < TILE_MIN_ITEMS or (which == 'bwd' and items > TILE_BWD_MAX_ITEMS):
+        return None
+    return plan
+
+
 def cheb_basis(graph, x, K, monomial=False):
     """Orders 1..K-1 of the Chebyshev basis of x (models.py:1049-1061) as [K-1, B, M, F]; `monomial`: the basis
     x, Lx, L^2 x, ... of `cgcnn.monomials` instead (models.py:1094-1103)."""
@@ -84,6 +111,10 @@ def cheb_basis(graph, x, K, monomial=False):
         return None
     B, M, F = x.shape
     basis = _new((K - 1, B, M, F), x)
+    tp = _tile(graph, 'fwd', K, B, F)
+    if tp is not None:
+        call('cheb_tile', tp.p2v, tp.wts, tp.nt, tp.T, K - 1, B, M, F, 0, 1 if monomial else 0, x, basis)
+        return basis
     if monomial:
         for k in range(1, K):                                                  # X_k = L X_(k-1)
             spmm(graph, x if k == 1 else basis[k - 2], out=basis[k - 1])
@@ -106,6 +137,11 @@ def cheb_basis_bwd(graph, G, monomial=False):
     """Adjoint of the recurrence: G [K, B, M, F] -> dLoss/dx [B, M, F] (G is overwritten on the gather path).
     `monomial`: adjoint of X_k = L X_(k-1), i.e. A_k = G_k + L^T A_(k+1)."""
     K, B, M, F = G.shape
+    tp = _tile(graph, 'bwd', K, B, F)
+    if tp is not None:
+        dx = _new((B, M, F), G)
+        call('cheb_tile', tp.p2v, tp.wts, tp.nt, tp.T, K - 1, B, M, F, 1, 1 if monomial else 0, G, dx)
+        return dx
     if monomial:
         for k in range(K - 2, -1, -1):
             spmm(graph, G[k + 1], G[k], None, out=G[k], alpha=1.0, beta=1.0, transpose=True)

@@ -104,6 +104,19 @@ int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, const int32
                      const float* x, const float* y, const float* z, float* out,
                      float alpha, float beta, float gamma, void* stream);
 
+/* ---- K1 fused: ALL K - 1 sparse products of a layer in one launch (csrc/cheb_tile.cu; HEALPix NESTED graphs whose vertex
+ * list is whole 256-pixel tiles: the cosmo patches).  Replaces the K - 1 tf.sparse_tensor_dense_matmul calls of
+ * cgcnn.chebyshev5 (models.py:1056-1061) -- or of cgcnn.monomials (models.py:1099-1102) when monomial != 0 -- and, with
+ * backward != 0, the TF autodiff of those lines.  S = K - 1 in 1..7, T = 16, M = ntiles * 256, F % 16 == 0.
+ *   tile_p2v int32[ntiles][P][P], P = T + 2 S: vertex shown at every position of the tile's flat image (-1 = none);
+ *   tile_w  float[ntiles][P-2][P-2][12]: the 3 x 3 weights of L (backward: of L^T) around every computed position, entry
+ *           3 (dy + 1) + (dx + 1) multiplies the value at (row + dy, column + dx); entries 9..11 are padding
+ *   (graph.py: StencilPlan builds and verifies both from the ELL arrays).
+ * forward : x = X_0 [B][M][F],            out = orders 1..K-1 [K-1][B][M][F]   (same result as dsb200_cheb_basis)
+ * backward: x = G [K][B][M][F] (read only), out = dLoss/dX_0 [B][M][F]          (same result as dsb200_cheb_basis_bwd) */
+int dsb200_cheb_tile(const int32_t* tile_p2v, const float* tile_w, int ntiles, int T, int S, int B, int M, int F,
+                     int backward, int monomial, const float* x, float* out, void* stream);
+
 /* ---- K2: dense contraction over (fin, k)  (tf.matmul, models.py:1062-1078)
  *   Y[r, fo] = sum_{k, fi} X_k[r, fi] * W[fi*K + k, fo],   r < R = B*M
  * x0 = order 0 [R,Fin], xk = orders 1..K-1 [K-1][R][Fin] (may be NULL when K == 1).

@@ -26,3 +26,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope='session')
+def dev():
+    """cuda:0 with libdsb200 loaded (GPU tests only)."""
+    import torch
+    from deepsphere_tf1_b200 import _lib
+    _lib.LIB.load()
+    return torch.device('cuda', 0)

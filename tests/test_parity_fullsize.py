@@ -121,3 +121,40 @@ def test_contraction_directions_at_benchmark_size(dev, shape):
     y2 = ops.contract_fwd(x0, xk, Wd, K, Fout, None)
     for _ in range(10):
         assert torch.equal(ops.contract_fwd(x0, xk, Wd, K, Fout, None), y2)
+
+
+@pytest.mark.parametrize('level', [0, 1, 2])
+def test_fused_tile_recurrence_at_benchmark_size(dev, level, monkeypatch):
+    """csrc/cheb_tile.cu at cosmo layers 1 (sample-interleaved [1, 262144, 16]), 2 ([16, 65536, 16]) and 3 ([16, 16384, 32]):
+    forward basis and adjoint against float64 on the CPU, and bit-stable over repeated launches."""
+    from deepsphere_tf1_b200 import ops, utils
+    from deepsphere_tf1_b200.graph import DeviceGraph
+    nside = [1024, 512, 256][level]
+    B, F = [(1, 16), (16, 16), (16, 32)][level]
+    K = 5
+    L = healpix_L(nside, order=2)
+    ids = utils.nside2indexes([nside], 2)[0]
+    g = DeviceGraph(L, dev, nested=(nside, ids))
+    monkeypatch.setattr(ops, 'TILE_BWD_MAX_ITEMS', 1 << 30)
+    assert ops._tile(g, 'fwd', K, B, F) is not None, 'the fused tile kernel must be the one that runs at this size'
+    L64 = sparse.csr_matrix(L, dtype=np.float64)
+    rs = np.random.RandomState(level)
+    x = torch.from_numpy(rs.randn(B, g.M, F).astype(np.float32))
+    planes = [x.double(), _apply(L64, x)]
+    for k in range(2, K):
+        planes.append(2 * _apply(L64, planes[-1]) - planes[-2])
+    xd = x.to(dev)
+    basis = ops.cheb_basis(g, xd, K)
+    assert_close(basis, torch.stack(planes[1:]), RTOL, 'basis')
+    G = torch.from_numpy(rs.randn(K, B, g.M, F).astype(np.float32))
+    LT = L64.T.tocsr()
+    a2, a1 = None, G[K - 1].double()
+    for k in range(K - 2, -1, -1):
+        a = G[k].double() + (2.0 if k >= 1 else 1.0) * _apply(LT, a1) - (a2 if a2 is not None else 0)
+        a2, a1 = a1, a
+    Gd = G.to(dev)
+    dx = ops.cheb_basis_bwd(g, Gd)
+    assert_close(dx, a1, RTOL, 'adjoint recurrence')
+    for _ in range(20):
+        assert torch.equal(ops.cheb_basis(g, xd, K), basis)
+        assert torch.equal(ops.cheb_basis_bwd(g, Gd), dx)

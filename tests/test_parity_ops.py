@@ -441,3 +441,41 @@ def test_optimizers_follow_tf1_update_rules(dev, name):
         hyper = torch.tensor(prod.hyper(lr, t), dtype=torch.float32, device=dev)
         ops.optimizer_step(prod.kind, wd, g.to(dev), slots[0] if slots else None, slots[1] if len(slots) > 1 else None, hyper)
     assert_close(wd, params['w'], RTOL, name)
+
+
+@pytest.mark.parametrize('monomial', [False, True])
+@pytest.mark.parametrize('K', [2, 4, 5])
+@pytest.mark.parametrize('B,F', [(1, 16), (3, 32), (16, 16), (2, 64)])
+@pytest.mark.parametrize('graph', [(64, 2), (128, 2), (64, 1)])
+def test_fused_tile_recurrence(dev, graph, B, F, K, monomial, monkeypatch):
+    """csrc/cheb_tile.cu (all K - 1 sparse products of a layer in one launch, 16 x 16 pixel tiles with a (K - 1)-ring halo in
+    shared memory): forward basis and adjoint against the per-step kernels and the oracle recurrence."""
+    from deepsphere_tf1_b200 import ops, utils
+    from deepsphere_tf1_b200.graph import DeviceGraph
+    nside, order = graph
+    L = healpix_L(nside, order)
+    ids = utils.nside2indexes([nside], order)[0]
+    g = DeviceGraph(L, dev, nested=(nside, ids))
+    monkeypatch.setattr(ops, 'TILE_MIN_ITEMS', 1)
+    monkeypatch.setattr(ops, 'TILE_BWD_MAX_ITEMS', 1 << 30)
+    assert ops._tile(g, 'fwd', K, B, F) is not None and ops._tile(g, 'bwd', K, B, F) is not None
+    rs = np.random.RandomState(K + F)
+    x = torch.from_numpy(rs.randn(B, g.M, F).astype(np.float32)).to(dev)
+    G = torch.from_numpy(rs.randn(K, B, g.M, F).astype(np.float32)).to(dev)
+    basis = ops.cheb_basis(g, x, K, monomial)
+    dx = ops.cheb_basis_bwd(g, G.clone(), monomial)
+    try:
+        ops.set_tile(False)
+        basis_ref = ops.cheb_basis(g, x, K, monomial)
+        dx_ref = ops.cheb_basis_bwd(g, G.clone(), monomial)
+    finally:
+        ops.set_tile(True)
+    assert_close(basis, basis_ref, 2e-6, 'basis vs per-step kernels')
+    assert_close(dx, dx_ref, 2e-6, 'adjoint vs per-step kernels')
+    if not monomial:
+        assert_close(basis, _oracle_basis(L, x.cpu(), K)[1:], RTOL, 'basis vs oracle')
+    # the adjoint identity <G, T x> = <T^T G, x> over all K planes, in float64
+    planes = torch.cat([x[None], basis]).double()
+    lhs = float((G.double() * planes).sum())
+    rhs = float((dx.double() * x.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), float(planes.abs().max()) * float(G.abs().max())), (lhs, rhs)
