@@ -255,18 +255,31 @@ def parity_check(L, p, world, rank, dev, tol=1e-4):
         a, b = a.detach().double().cpu().numpy().reshape(-1), b.detach().double().cpu().numpy().reshape(-1)
         return float(np.abs(a - b).max() / max(np.abs(b).max(), floor, 1e-30))
     gmax = max(float(g.abs().max()) for g in grads.values())
-    worst, worst_name = 0.0, ''
+    # what float32 arithmetic can deliver at this size: the same oracle evaluated in float32 on the CPU against its float64
+    # evaluation.  The gradients of layers 1-3 sum 4-17 M terms that cancel to ~1e-4 of their magnitude (everything behind a
+    # batch-norm layer has zero mean), so ANY float32 evaluation -- TF1's included -- is 1e-3..1e-2 off on them.
+    o32 = OracleCgcnn(L, F=F, K=[KCHEB] * 6, p=p, batch_norm=[True] * 6, M=[], statistics='mean')
+    for name, v in o32.params.items():
+        o32.params[name] = m._P.views[name].detach().cpu().reshape(v.shape).clone()
+    _, _, grads32, _ = o32.loss_and_grads(torch.from_numpy(x), torch.from_numpy(labels), True)
+    per_var, worst, worst_name, grads_ok = {}, 0.0, '', True
     for name, g in grads.items():
         e = rel(m._P.gviews[name], g, floor=1e-3 * gmax)
+        e32 = rel(grads32[name], g, floor=1e-3 * gmax)
+        per_var[name] = {'cuda_vs_f64': e, 'cpu_f32_vs_f64': e32}
+        grads_ok = grads_ok and e <= max(tol, 2.0 * e32)
         if e > worst:
             worst, worst_name = e, name
     out = {'loss_rel': abs(float(m._loss) - float(total)) / max(abs(float(total)), 1e-30),
            'max_logit_rel': rel(logits, ologits), 'max_grad_rel': worst, 'worst_gradient': worst_name,
+           'max_grad_rel_of_cpu_float32_oracle': max(v['cpu_f32_vs_f64'] for v in per_var.values()),
+           'gradients': per_var,
            'loss': float(m._loss), 'oracle_loss': float(total), 'global_batch': Bg, 'ranks': world, 'tolerance': tol,
            'what': 'one training step of the benchmark configuration (M=262,144, batch 16 split over the ranks): CUDA path '
                    '(fp32) vs CPU oracle evaluated in float64 from identical weights; errors relative to the largest '
-                   'expected magnitude of each tensor'}
-    out['ok'] = bool(out['loss_rel'] <= tol and out['max_logit_rel'] <= tol and out['max_grad_rel'] <= tol)
+                   'expected magnitude of each tensor.  ok = loss and logits within the tolerance, every gradient within '
+                   'max(tolerance, 2 x the error of the float32 CPU evaluation of the same oracle)'}
+    out['ok'] = bool(out['loss_rel'] <= tol and out['max_logit_rel'] <= tol and grads_ok)
     return out
 
 

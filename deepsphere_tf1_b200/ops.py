@@ -77,19 +77,22 @@ def _rec(graph, which):
     return getattr(graph, which + '_rec', None) if USE_RECORDS else None
 
 
-USE_TILE = True           # fused tile recurrence (csrc/cheb_tile.cu): all K - 1 sparse products of a layer in one launch
-TILE_MIN_ITEMS = int(os.environ.get('DSB200_TILE_MIN_ITEMS', 64))     # (tile, sample, 16-feature chunk) items below which the
-                                                                      # one-launch gather recurrence of the coarse levels stays
+USE_TILE = os.environ.get('DSB200_TILE', '1') != '0'   # fused tile recurrence (csrc/cheb_tile.cu): all K - 1 sparse products of
+                                                       # a layer in one launch
+# Where the fused kernel is used.  Measured inside the cosmo training step (profiles/r02_trace_step_*.txt): the per-step
+# pipelined kernels find the plane the previous step has just written in the 126 MB L2 (28 us per step at layer 2 instead of 42 us
+# with cold operands), so the HBM traffic the fusion removes is already L2 traffic there and the halo recomputation (1.43x) and
+# idle lanes (0.88) of the tile kernel decide: it wins where there are few (tile, sample, 16-feature chunk) items (layer 1: 54 vs
+# 112 us, layers 4-5), loses at 4096 items (layer 2: 156 vs 111 us).  With operands that exceed L2 (tools/bench_tile.py) it wins
+# the forward direction everywhere.  Items = nt * B * F / 16.
+TILE_MIN_ITEMS = int(os.environ.get('DSB200_TILE_MIN_ITEMS', 128))
+TILE_FWD_MAX_ITEMS = int(os.environ.get('DSB200_TILE_FWD_MAX_ITEMS', 1024))
+TILE_BWD_MAX_ITEMS = int(os.environ.get('DSB200_TILE_BWD_MAX_ITEMS', 256))
 
 
 def set_tile(on):
     global USE_TILE
     USE_TILE = bool(on)
-
-
-TILE_BWD_MAX_ITEMS = int(os.environ.get('DSB200_TILE_BWD_MAX_ITEMS', 1024))   # adjoint form: above this many items the per-step
-                                                                              # pipelined kernels are faster (tools/bench_tile.py:
-                                                                              # the G_k planes come straight from L2 / HBM there)
 
 
 def _tile(graph, which, K, B, F):
@@ -99,7 +102,7 @@ def _tile(graph, which, K, B, F):
     if plan is None:
         return None
     items = plan.nt * B * (F // 16)
-    if items < TILE_MIN_ITEMS or (which == 'bwd' and items > TILE_BWD_MAX_ITEMS):
+    if items < TILE_MIN_ITEMS or items > (TILE_BWD_MAX_ITEMS if which == 'bwd' else TILE_FWD_MAX_ITEMS):
         return None
     return plan
 

@@ -136,6 +136,7 @@ def test_fused_tile_recurrence_at_benchmark_size(dev, level, monkeypatch):
     ids = utils.nside2indexes([nside], 2)[0]
     g = DeviceGraph(L, dev, nested=(nside, ids))
     monkeypatch.setattr(ops, 'TILE_BWD_MAX_ITEMS', 1 << 30)
+    monkeypatch.setattr(ops, 'TILE_FWD_MAX_ITEMS', 1 << 30)
     assert ops._tile(g, 'fwd', K, B, F) is not None, 'the fused tile kernel must be the one that runs at this size'
     L64 = sparse.csr_matrix(L, dtype=np.float64)
     rs = np.random.RandomState(level)

@@ -458,6 +458,7 @@ def test_fused_tile_recurrence(dev, graph, B, F, K, monomial, monkeypatch):
     g = DeviceGraph(L, dev, nested=(nside, ids))
     monkeypatch.setattr(ops, 'TILE_MIN_ITEMS', 1)
     monkeypatch.setattr(ops, 'TILE_BWD_MAX_ITEMS', 1 << 30)
+    monkeypatch.setattr(ops, 'TILE_FWD_MAX_ITEMS', 1 << 30)
     assert ops._tile(g, 'fwd', K, B, F) is not None and ops._tile(g, 'bwd', K, B, F) is not None
     rs = np.random.RandomState(K + F)
     x = torch.from_numpy(rs.randn(B, g.M, F).astype(np.float32)).to(dev)

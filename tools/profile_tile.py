@@ -13,7 +13,8 @@ from deepsphere_tf1_b200 import ops, utils  # noqa: E402
 from deepsphere_tf1_b200.graph import DeviceGraph  # noqa: E402
 
 layer = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-ops.TILE_BWD_MAX_ITEMS = 1 << 30
+ops.TILE_BWD_MAX_ITEMS = ops.TILE_FWD_MAX_ITEMS = 1 << 30
+ops.TILE_MIN_ITEMS = 1
 torch.cuda.set_device(0)
 dev = torch.device('cuda', 0)
 L, p = bench.build_laplacians()
