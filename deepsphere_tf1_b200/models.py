@@ -1281,10 +1281,10 @@ class cgcnn(base_model):
 
 class deepsphere(cgcnn):
     """Spherical CNN front-end: Laplacians and pooling factors from a list of nsides
-    (reference `deepsphere`, models.py:1784-1839).  `new=True` (the PyGSP-fork kNN graph) is
-    not available: the default here is the in-repo 8-neighbour graph, `new=False`."""
+    (reference `deepsphere`, models.py:1784-1839).  `new=True` (the upstream default) builds the kNN graph of the PyGSP
+    fork's `SphereHealpix` (graphs.py); `new=False` the in-repo 8-neighbour graph that the cosmo experiments use."""
 
-    def __init__(self, nsides, indexes=None, use_4=False, sampling='healpix', std=None, full=False, new=False,
+    def __init__(self, nsides, indexes=None, use_4=False, sampling='healpix', std=None, full=False, new=True,
                  n_neighbors=8, lmax=None, **kwargs):
         L, p = utils.build_laplacians(nsides, indexes=indexes, use_4=use_4, sampling=sampling,
                                       std=std, full=full, new=new, n_neighbors=n_neighbors, lmax=lmax)
@@ -1293,7 +1293,7 @@ class deepsphere(cgcnn):
             self.ratio = nsides[0][1] / nsides[0][0] if isinstance(nsides[0], tuple) else 1.
         self.nsides = nsides
         self.pygsp_graphs = [None] * len(nsides)
-        if sampling == 'healpix' and not full:
+        if sampling == 'healpix' and not full and not new:
             idx = indexes if indexes is not None else [None] * len(nsides)
             self._nested = [(int(n), idx[i]) for i, n in enumerate(nsides[:len(L)])]
         super(deepsphere, self).__init__(L=L, p=p, **kwargs)

@@ -12,7 +12,7 @@ operations on the COO triplets instead of per-pixel healpy calls and sparse-spar
 
 Float32 results are bit-identical to the reference code run on the same numpy (checked in
 tests/test_graph_golden.py against fixtures produced by the reference's own utils.py).
-The icosahedral and irregular (kNN) graphs live in `graphs.py`.
+The icosahedral, kNN-HEALPix (`new=True`) and irregular station graphs live in `graphs.py`.
 """
 import numpy as np
 from scipy import sparse
@@ -90,12 +90,14 @@ def build_laplacian(W, lap_type='normalized', dtype=np.float32):
 
 
 def healpix_laplacian(nside=16, nest=True, lap_type='normalized', indexes=None, dtype=np.float32,
-                      use_4=False, std=None, full=False, new=False, n_neighbors=8):
-    """HEALPix Laplacian.  Only the in-repo 8-neighbour graph (`new=False`) exists here; the
-    reference's `new=True` delegates to an external PyGSP fork (utils.py:331-334)."""
+                      use_4=False, std=None, full=False, new=True, n_neighbors=8):
+    """HEALPix Laplacian (utils.py:320-342).  `new=True` (the upstream default): the kNN graph of the PyGSP fork's
+    `SphereHealpix`, restated in graphs.py; `new=False`: the in-repo 8-neighbour graph."""
     if new:
-        raise NotImplementedError('new=True needs the PyGSP fork graph (SphereHealpix); '
-                                  'use new=False, the in-repo 8-neighbour graph')
+        if not nest:
+            raise NotImplementedError()
+        from . import graphs
+        return graphs.healpix_nn_laplacian(nside, indexes=indexes, n_neighbors=n_neighbors, lap_type=lap_type, dtype=dtype)
     if use_4:
         raise NotImplementedError()     # as upstream (utils.py:268-270)
     W = healpix_weightmatrix(nside=nside, nest=nest, indexes=indexes, dtype=dtype, std=std, full=full)
@@ -121,7 +123,7 @@ def estimate_lmax(laplacian):
 
 
 def build_laplacians(nsides, indexes=None, use_4=False, sampling='healpix', std=None, full=False,
-                     new=False, n_neighbors=8, lmax=None):
+                     new=True, n_neighbors=8, lmax=None):
     """List of rescaled Laplacians (COO, float32) and pooling factors from a list of nsides.
 
     `lmax` (optional list, one value per level actually built) skips the eigenvalue solve.
@@ -150,12 +152,8 @@ def build_laplacians(nsides, indexes=None, use_4=False, sampling='healpix', std=
                 laplacian = healpix_laplacian(nside=nside, indexes=index, use_4=use_4, std=sigma,
                                               full=mat, new=new, n_neighbors=n_neighbors)
             elif sampling == 'icosahedron':
-                # utils.py:370-376 builds the mesh and its kNN weights inside the PyGSP fork (SphereIcosahedron), which
-                # is not available; models.cgcnn takes the Laplacians of an icosahedral hierarchy directly (L=[...],
-                # p = vertex counts of the coarser levels) and implements its pooling / unpooling (models.py:1137-1138,
-                # 1356-1358), see tests/test_parity_model.py::test_climate_like_icosahedral_segmentation
-                raise NotImplementedError('icosahedral graphs need the PyGSP fork (SphereIcosahedron); '
-                                          'build the Laplacians elsewhere and pass them to models.cgcnn(L=..., p=...)')
+                from . import graphs
+                laplacian = graphs.icosahedron_laplacian(order=nside, indexes=index)    # utils.py:370-376, 412
             elif sampling == 'equiangular':
                 raise NotImplementedError('equiangular sampling needs the PyGSP fork (out of scope)')
             else:

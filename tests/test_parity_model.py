@@ -359,3 +359,39 @@ def test_fit_predict_evaluate_api(tmp_path):
     import shutil
     shutil.rmtree(model._get_path('checkpoints'), ignore_errors=True)
     shutil.rmtree(model._get_path('summaries'), ignore_errors=True)
+
+
+def test_climate_encoder_decoder_on_the_real_icosahedral_meshes():
+    """config 3 through the reference's own entry point: `deepsphere(sampling='icosahedron', nsides=[5, 5, 4, 3, 3])` builds the
+    level-5 / 4 / 3 meshes (graphs.py, pinned to the reference's SphereIcosahedron) and their combinatorial Laplacians
+    (utils.py:370-376, 412); prefix-slice pooling, pad-with-ones unpooling up to the hard-coded 10,242 vertices, weighted CE."""
+    from deepsphere_tf1_b200 import models, optimizers
+    from oracle.model import OracleCgcnn
+    from oracle import optim_tf1
+    kw = dict(F=[8, 16, 16, 16], K=[4] * 4, batch_norm=[True] * 4, M=[], num_feat_in=4, pool='average', dense=True, Fseg=3,
+              weighted=True)
+    model = models.deepsphere(nsides=[5, 5, 4, 3, 3], sampling='icosahedron', num_epochs=1, batch_size=2, eval_frequency=10,
+                              dir_name='_test_parity', verbose=False, scheduler=lambda step: 1e-2,
+                              optimizer=lambda lr: optimizers.MomentumOptimizer(lr, 0.9), **kw)
+    assert [l.shape[0] for l in model.L] == [10242, 10242, 2562, 642] and model.p == [10242, 2562, 642, 642]
+    oracle = OracleCgcnn(model.L, p=model.p, sampling='icosahedron', **kw)
+    copy_weights(oracle, model)
+    rs = np.random.RandomState(9)
+    x = rs.randn(2, 10242, 4).astype(np.float32)
+    labels = rs.choice(3, size=(2, 10242), p=[0.9, 0.02, 0.08]).astype(np.int32)
+    _check_step(oracle, model, x, labels, opt=optim_tf1.Momentum(0.9))
+
+
+def test_default_healpix_graph_is_the_knn_graph():
+    """`deepsphere(nsides)` without `new=`: the upstream default new=True (models.py:1827) -> kNN graph, 11-wide ELL rows."""
+    from deepsphere_tf1_b200 import models, optimizers
+    from oracle.model import OracleCgcnn
+    kw = dict(F=[8, 4], K=[4, 3], batch_norm=[True, True], M=[5], statistics='meanvar')
+    model = models.deepsphere(nsides=[8, 4, 2], num_epochs=1, batch_size=3, eval_frequency=10, dir_name='_test_parity',
+                              verbose=False, scheduler=lambda step: 1e-2,
+                              optimizer=lambda lr: optimizers.AdamOptimizer(lr, epsilon=1e-8), **kw)
+    assert np.diff(model.L[0].tocsr().indptr).max() > 9
+    oracle = OracleCgcnn(model.L, p=model.p, **kw)
+    copy_weights(oracle, model)
+    rs = np.random.RandomState(10)
+    _check_step(oracle, model, rs.randn(3, 768, 1).astype(np.float32), rs.randint(0, 5, size=3).astype(np.int32))
