@@ -66,7 +66,9 @@ def _check_step(oracle, model, x, labels, steps=3, rtol_after=5e-4, opt=None):
         assert lr_p == pytest.approx(lr)
         assert float(loss_p) == pytest.approx(loss_ref, rel=rtol_after)
     for name, v in oracle.params.items():
-        assert_close(model._P.views[name].reshape(-1), v.reshape(-1), rtol_after, 'weights ' + name, floor=1e-6)
+        # floor: a bias in front of a batch-normalised filter only ever receives rounding noise (see above); after a few
+        # momentum steps it holds ~1e-9 in any implementation
+        assert_close(model._P.views[name].reshape(-1), v.reshape(-1), rtol_after, 'weights ' + name, floor=1e-5)
     for name, v in oracle.state.items():
         # a moving mean is compared on the scale of the feature's standard deviation
         floor = float(oracle.state[name.replace('moving_mean', 'moving_variance')].max()) ** 0.5

@@ -113,14 +113,23 @@ def parity(c, tol=1e-4):
         a, b = a.detach().double().cpu().numpy().reshape(-1), b.detach().double().cpu().numpy().reshape(-1)
         return float(np.abs(a - b).max() / max(np.abs(b).max(), floor, 1e-30))
     gmax = max(float(g.abs().max()) for g in grads.values())
-    worst, worst32, ok = 0.0, 0.0, True
+    worst, worst32, per_var = 0.0, 0.0, {}
+    num = den = num32 = 0.0
     for name, g in grads.items():
         e, e32 = rel(m._P.gviews[name], g, 1e-3 * gmax), rel(grads32[name], g, 1e-3 * gmax)
+        per_var[name] = {'cuda_vs_f64': e, 'cpu_f32_vs_f64': e32, 'max_abs': float(g.abs().max())}
         worst, worst32 = max(worst, e), max(worst32, e32)
-        ok = ok and e <= max(tol, 2 * e32)
+        gd = g.double().reshape(-1)
+        num += float(((m._P.gviews[name].detach().cpu().double().reshape(-1) - gd) ** 2).sum())
+        num32 += float(((grads32[name].double().reshape(-1) - gd) ** 2).sum())
+        den += float((gd ** 2).sum())
+    grad_l2 = (num / den) ** 0.5
+    ok = grad_l2 <= tol
     out = {'loss_rel': abs(float(m._loss) - float(total)) / max(abs(float(total)), 1e-30),
-           'max_logit_rel': rel(logits, ologits), 'max_grad_rel': worst, 'max_grad_rel_of_cpu_float32_oracle': worst32,
-           'batch': Bp, 'tolerance': tol}
+           'max_logit_rel': rel(logits, ologits), 'grad_rel_l2': grad_l2,
+           'grad_rel_l2_of_cpu_float32_oracle': (num32 / den) ** 0.5, 'max_grad_rel': worst,
+           'max_grad_rel_of_cpu_float32_oracle': worst32,
+           'batch': Bp, 'tolerance': tol, 'gradients': per_var, 'largest_gradient': gmax}
     out['ok'] = bool(ok and out['loss_rel'] <= tol and out['max_logit_rel'] <= tol)
     del m
     return out

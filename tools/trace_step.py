@@ -13,12 +13,21 @@ import bench  # noqa: E402
 from deepsphere_tf1_b200 import models, optimizers, utils  # noqa: E402
 
 torch.cuda.set_device(0)
-model = models.deepsphere(
+CFG = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+if CFG != 2:
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import bench_configs
+    c = bench_configs.config(CFG)
+    model = bench_configs.build_model(c, c['B'], False, '_trace')
+    x, labels = c['x'], c['labels']
+else:
+  model = models.deepsphere(
     nsides=bench.NSIDES, indexes=utils.nside2indexes(bench.NSIDES, bench.ORDER), new=False, lmax=bench.LMAX,
     F=bench.F, K=[bench.KCHEB] * 6, batch_norm=[True] * 6, M=[], statistics='mean', num_epochs=1,
     batch_size=16, eval_frequency=10 ** 9, seed=2, verbose=False, cuda_graph=False,
     scheduler=lambda step: 2e-4, optimizer=lambda lr: optimizers.AdamOptimizer(lr, epsilon=1e-8), dir_name='_trace')
-x, labels = bench.synthetic_batch(16, 0)
+if CFG == 2:
+    x, labels = bench.synthetic_batch(16, 0)
 xd, ld = model._to_device(x), model._labels_to_device(labels)
 for _ in range(3):
     model._advance_hyper()
