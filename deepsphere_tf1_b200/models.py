@@ -999,12 +999,19 @@ class cgcnn(base_model):
     def _allreduce(self, t):
         if self.world_size > 1:
             import torch.distributed as dist
-            if self._peer is None and os.environ.get('DSB200_PEER_ALLREDUCE', '0') == '1':   # opt-in: measured gain 0.5 % at 2 GPUs
+            # small fp64 vectors (SyncBN sums): one single-CTA kernel over NVLink peer memory instead of an NCCL launch
+            # (csrc/peer_allreduce.cu; ~10 us instead of ~17-30 us per call, 13 calls per cosmo step).  Default on where CUDA IPC
+            # between the ranks works (one node); DSB200_PEER_ALLREDUCE=0 keeps everything on NCCL.
+            if self._peer is None and os.environ.get('DSB200_PEER_ALLREDUCE', '1') == '1':
                 from .peer import PeerAllReduce
                 try:
                     self._peer = PeerAllReduce(self.pg)
+                    if not self._peer.enabled:
+                        self._peer = False
                 except Exception:                         # no IPC / not one node: NCCL only
                     self._peer = False
+            elif self._peer is None:
+                self._peer = False
             if self._peer and self._peer.allreduce(t):    # small fp64 vectors: one kernel over NVLink peer memory
                 return
             dist.all_reduce(t, group=self.pg)
