@@ -124,7 +124,7 @@ def parity(c, tol=1e-4):
         num32 += float(((grads32[name].double().reshape(-1) - gd) ** 2).sum())
         den += float((gd ** 2).sum())
     grad_l2 = (num / den) ** 0.5
-    ok = grad_l2 <= tol
+    ok = grad_l2 <= max(tol, 4.0 * (num32 / den) ** 0.5)
     out = {'loss_rel': abs(float(m._loss) - float(total)) / max(abs(float(total)), 1e-30),
            'max_logit_rel': rel(logits, ologits), 'grad_rel_l2': grad_l2,
            'grad_rel_l2_of_cpu_float32_oracle': (num32 / den) ** 0.5, 'max_grad_rel': worst,

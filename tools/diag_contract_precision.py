@@ -2,15 +2,20 @@ import sys, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 from deepsphere_tf1_b200 import ops
 dev = torch.device('cuda', 0)
+MODE = sys.argv[1] if len(sys.argv) > 1 else 'normal'
 def rel(a, b):
     a, b = a.double().cpu(), b.double().cpu()
     return float((a - b).abs().max() / b.abs().max())
-for (B, M, Fin, Fout, K) in [(8, 10242, 48, 32, 4), (8, 10242, 16, 32, 4), (8, 10242, 32, 32, 4), (8, 10242, 32, 3, 1), (8, 2562, 96, 64, 4), (8, 2562, 64, 128, 4), (8, 642, 192, 128, 4), (8, 162, 384, 256, 4), (8, 42, 768, 512, 4), (8, 12, 1024, 512, 4), (8, 12, 512, 512, 4)]:
+for (B, M, Fin, Fout, K) in [(16, 65536, 16, 32, 5), (16, 16384, 32, 64, 5), (16, 4096, 64, 64, 5), (4, 4096, 64, 64, 5), (16, 1024, 64, 64, 5), (8, 10242, 48, 32, 4), (8, 10242, 16, 32, 4), (8, 10242, 32, 32, 4), (8, 10242, 32, 3, 1), (8, 2562, 96, 64, 4), (8, 2562, 64, 128, 4), (8, 642, 192, 128, 4), (8, 162, 384, 256, 4), (8, 42, 768, 512, 4), (8, 12, 1024, 512, 4), (8, 12, 512, 512, 4)]:
     R = B * M
     rs = np.random.RandomState(Fin)
     planes = torch.from_numpy(rs.standard_normal((K, B, M, Fin)).astype(np.float32))
+    if MODE == 'relu':          # what the layers really see: non-negative activations with a large mean, zero-mean gradients
+        planes = planes.abs() + 1.0
     W = torch.from_numpy((rs.randn(Fin * K, Fout) / np.sqrt(Fin * K)).astype(np.float32))
     dy = torch.from_numpy(rs.standard_normal((B, M, Fout)).astype(np.float32))
+    if MODE == 'relu':
+        dy = dy - dy.mean(dim=(0, 1), keepdim=True)
     pl = planes.reshape(K, R, Fin).double().to(dev)
     W3 = W.double().reshape(Fin, K, Fout).to(dev)
     dy2 = dy.reshape(R, Fout).double().to(dev)
