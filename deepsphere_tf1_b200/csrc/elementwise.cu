@@ -844,6 +844,15 @@ __global__ void __launch_bounds__(256) axpy_kernel(const float* __restrict__ x, 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = fmaf(a, __ldg(x + i), y[i]);
 }
 
+// out[i] = a[i] * x[i * F + ch]: one feature channel of the input batch as a per-vertex mask (masked regression loss,
+// reference deepsphere/models.py:785-787: `predictions * data[..., -2]`, `labels * data[..., -1]`)
+__global__ void __launch_bounds__(256) mul_channel_kernel(const float* __restrict__ a, const float* __restrict__ x, int F, int ch,
+                                                          float* __restrict__ out, long long n)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = a[i] * __ldg(x + i * F + ch);
+}
+
 __global__ void __launch_bounds__(256) scale_kernel(float* x, float a, long long n)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -1155,6 +1164,13 @@ extern "C" int dsb200_axpy(const float* x, float* y, float a, long long n, void*
 {
     DSB_REQUIRE(x && y && n > 0, "axpy: bad arguments");
     axpy_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(x, y, a, n);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_mul_channel(const float* a, const float* x, int F, int ch, float* out, long long n, void* stream)
+{
+    DSB_REQUIRE(a && x && out && n > 0 && F > 0 && ch >= 0 && ch < F, "mul_channel: bad arguments");
+    mul_channel_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(a, x, F, ch, out, n);
     DSB_LAUNCH_CHECK();
 }
 

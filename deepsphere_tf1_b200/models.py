@@ -778,8 +778,11 @@ class cgcnn(base_model):
                 raise NotImplementedError('vertex_shard=True supports one sample per step, HEALPix pooling, '
                                           "statistics='mean', no fully connected layers, no decoder")
         if mask:
+            # models.py:1030-1032: only the PRESENCE of the attribute switches the masked loss on (models.py:785-787): the last two
+            # input features are the masks of the predictions and of the labels
             self.train_mask, self.val_mask = mask[0], mask[1]
-            raise NotImplementedError('masked regression is outside the hot path')
+            if not (regression and dense):
+                raise ValueError('masks apply to the dense regression loss (models.py:785-787)')
 
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         import torch.distributed as dist
@@ -1027,6 +1030,7 @@ class cgcnn(base_model):
     # ------------------------------------------------------------------ the layer program
     def _forward(self, x, training, save):
         """`_inference` (+ `_decoder`): returns (logits, descriptor) (models.py:1219-1344)."""
+        self._input = x                                    # the masked loss reads its last two channels
         skips = [x]
         for st in self._encoder:
             x = st.forward(x, training, save)
@@ -1123,7 +1127,13 @@ class cgcnn(base_model):
             if pred.numel() != tgt.numel():
                 raise ValueError('regression: logits {} do not match labels {}'.format(tuple(logits.shape),
                                                                                        tuple(labels.shape)))
+            masked = hasattr(self, 'train_mask')
+            if masked:                                     # predictions * data[..., -2], labels * data[..., -1]
+                xin = self._input
+                pred, tgt = ops.mul_channel(pred, xin, -2), ops.mul_channel(tgt.contiguous(), xin, -1)
             d = ops.mse(pred, tgt, self._loss, gs, need_grad)
+            if masked and need_grad:
+                d = ops.mul_channel(d, xin, -2)
             return d.reshape(logits.shape) if need_grad else None
         cw = None
         if self.weighted:                                  # models.py:795-802: hard-coded weights of 3 classes

@@ -388,6 +388,14 @@ def axpy(x, y, a=1.0):
     call('axpy', x, y, float(a), x.numel())
 
 
+def mul_channel(a, x, ch):
+    """a * x[..., ch] for a [B, M] (or flat) and x [B, M, F] (masked regression, models.py:785-787)."""
+    F = x.shape[-1]
+    out = torch.empty_like(a)
+    call('mul_channel', a, x, F, ch % F, out, a.numel())
+    return out
+
+
 def scale(x, a):
     call('scale', x, float(a), x.numel())
 

@@ -285,6 +285,8 @@ int dsb200_optimizer_step(int kind, float* w, const float* g, float* s1, float* 
 int dsb200_fill(float* x, float v, long long n, void* stream);
 int dsb200_axpy(const float* x, float* y, float a, long long n, void* stream); /* y += a*x */
 int dsb200_scale(float* x, float a, long long n, void* stream);               /* x *= a */
+/* out[i] = a[i] * x[i*F + ch], i < n: a feature channel of the input batch as a mask (masked MSE, models.py:785-787) */
+int dsb200_mul_channel(const float* a, const float* x, int F, int ch, float* out, long long n, void* stream);
 /* tf.nn.dropout on the fc layers (models.py:1279-1280): out = u < keep ? x / keep : 0 with u a
  * caller-supplied uniform [0,1) tensor; the same call applied to dout is the backward. */
 int dsb200_dropout(const float* x, const float* u, float keep, float* out, long long n, void* stream);

@@ -109,11 +109,13 @@ def estimate_lmax(laplacian, v0=None):
     return 1.02 * sparse.linalg.eigsh(laplacian, k=1, which='LM', return_eigenvectors=False, v0=v0)[0]
 
 
-def build_laplacians(nsides, indexes=None, std=None, full=False, lmax=None):
+def build_laplacians(nsides, indexes=None, std=None, full=False, lmax=None, new=False):
     """deepsphere/utils.py:388-431 for sampling='healpix', new=False.
 
     `lmax` (optional list, one per built level) replaces the ARPACK call so that a test can
     hand the same value to the oracle and to the product."""
+    if new:
+        raise NotImplementedError('the oracle restates the in-repo graph (new=False); the kNN graph lives in the PyGSP fork')
     L = []
     p = []
     if indexes is None:

@@ -18,7 +18,7 @@ class OracleCgcnn:
     def __init__(self, L, F, K, p, batch_norm, M, num_feat_in=1, conv='chebyshev5', pool='max',
                  activation='relu', statistics=None, Fseg=None, regularization=0, dropout=1,
                  regression=False, dense=False, sampling='healpix', dtype=torch.float32, seed=2,
-                 finest_vertices=10 * 4 ** 5 + 2, weighted=False):
+                 finest_vertices=10 * 4 ** 5 + 2, weighted=False, masked=False):
         if not len(L) == len(F) == len(K) == len(p) == len(batch_norm):          # models.py:937-940
             raise ValueError('Wrong specification of the convolutional layers')
         self.Ls = [ops.sparse_to_torch(l, dtype) for l in L]
@@ -28,6 +28,7 @@ class OracleCgcnn:
         self.regression, self.dense, self.sampling = regression, dense, sampling
         self.conv = getattr(ops, conv)                                            # models.py:1017
         self.weighted = weighted
+        self.masked = masked                        # a `mask` argument was given: masked MSE (models.py:785-787, 1030-1032)
         self.pool_kind, self.act, self.stat = pool, ops.ACTIVATIONS[activation], statistics
         self.dtype = dtype
         self.num_feat_in = num_feat_in
@@ -184,16 +185,17 @@ class OracleCgcnn:
         return self.conv(x, self.Ls[-n], P['outconv/weights'], 1)             # 1340-1341
 
     # ---- loss / gradients / step ----------------------------------------------------------
-    def loss(self, logits, labels, P):
+    def loss(self, logits, labels, P, data=None):
         wstd = [(P[k], self.std[k]) for k in self.params if k in self.std]
-        return ops.loss(logits, labels, self.regression, wstd, self.regularization, self.weighted)
+        return ops.loss(logits, labels, self.regression, wstd, self.regularization, self.weighted,
+                        data if self.masked else None)
 
     def loss_and_grads(self, x, labels, training=True, drop_masks=None, filt_masks=None):
         """Forward + loss + autograd gradients w.r.t. every trainable variable."""
         P = {k: v.clone().requires_grad_(True) for k, v in self.params.items()}
         new_state = {}
         logits, _ = self.forward(x, P, training, new_state, drop_masks, filt_masks)
-        total, data_loss = self.loss(logits, labels, P)
+        total, data_loss = self.loss(logits, labels, P, x)
         grads = torch.autograd.grad(total, list(P.values()), allow_unused=True)
         grads = {k: (g if g is not None else torch.zeros_like(P[k])) for k, g in zip(P, grads)}
         return total.detach(), logits.detach(), grads, new_state

@@ -171,11 +171,14 @@ ACTIVATIONS = {
 CLASS_WEIGHTS = (0.34130685, 318.47388343, 14.93759951)     # models.py:796 (hard-coded, 3 classes)
 
 
-def loss(logits, labels, regression, weights_and_std, regularization, weighted=False):
+def loss(logits, labels, regression, weights_and_std, regularization, weighted=False, mask_data=None):
     """models.py:777-820 (cross-entropy / MSE + regularization * sum_i(l2_loss(W_i)/std_i^2)/sum_i size_i).
     `weights_and_std` = [(W_i, std_i)] in creation order (models.py:862-869)."""
     if regression:
         predictions = logits.squeeze()
+        if mask_data is not None:                                          # models.py:785-787 (`hasattr(self, 'train_mask')`)
+            predictions = predictions * mask_data[..., -2]
+            labels = labels * mask_data[..., -1]
         data_loss = ((labels - predictions) ** 2).mean()                   # tf.losses.mean_squared_error
     else:
         C = logits.shape[-1]

@@ -87,13 +87,13 @@ def test_ds_index(mod):
 def test_build_laplacians_pipeline(mod):
     """Whole pipeline incl. the ARPACK lmax (start-vector dependent -> 1e-5 tolerance)."""
     nsides = [32, 16, 8, 4, 4]
-    Ls, p = mod.build_laplacians(nsides, indexes=mod.nside2indexes(nsides, 2))
+    Ls, p = mod.build_laplacians(nsides, indexes=mod.nside2indexes(nsides, 2), new=False)
     np.testing.assert_array_equal(np.array(p), G['bl_p'])
     assert len(Ls) == int(G['bl_n'])
     for i, L in enumerate(Ls):
         assert L.format == 'coo' and L.dtype == np.float32
         assert_same(L, 'bl_L%d' % i, exact=False, rtol=2e-5)
-    Ls, p = mod.build_laplacians([4, 2, 1])
+    Ls, p = mod.build_laplacians([4, 2, 1], new=False)
     np.testing.assert_array_equal(np.array(p), G['blfull_p'])
     for i, L in enumerate(Ls):
         assert_same(L, 'blfull_L%d' % i, exact=False, rtol=2e-5)
@@ -104,7 +104,7 @@ def test_build_laplacians_product_equals_oracle_with_same_lmax():
     idx = putils.nside2indexes(nsides, 1)
     lmax = [np.float32(1.9), np.float32(1.85), np.float32(1.8)]
     La, pa = ograph.build_laplacians(nsides, indexes=idx, lmax=lmax)
-    Lb, pb = putils.build_laplacians(nsides, indexes=idx, lmax=lmax)
+    Lb, pb = putils.build_laplacians(nsides, indexes=idx, lmax=lmax, new=False)
     assert pa == pb == [4, 4, 1]
     for A, B in zip(La, Lb):
         for u, v in zip(parts(A), parts(B)):

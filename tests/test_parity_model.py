@@ -397,3 +397,18 @@ def test_default_healpix_graph_is_the_knn_graph():
     copy_weights(oracle, model)
     rs = np.random.RandomState(10)
     _check_step(oracle, model, rs.randn(3, 768, 1).astype(np.float32), rs.randint(0, 5, size=3).astype(np.int32))
+
+
+def test_masked_dense_regression():
+    """`mask=[train, val]` (models.py:1030-1032): the masked MSE of models.py:785-787 -- predictions * data[..., -2],
+    labels * data[..., -1] -- on a GHCN-like dense regression net."""
+    L = [random_knn_L(300, 8, seed=3)] * 3
+    kw, opt = _momentum()
+    oracle, model = _pair(L, F=[12, 12, 1], K=[3, 3, 3], p=[1, 1, 1], batch_norm=[True, True, True], M=[], num_feat_in=4,
+                          regression=True, dense=True, mask=[None, None], **kw)
+    oracle.masked = True
+    rs = np.random.RandomState(12)
+    x = rs.randn(4, 300, 4).astype(np.float32)
+    x[..., -2:] = (rs.rand(4, 300, 2) > 0.3).astype(np.float32)
+    labels = rs.randn(4, 300).astype(np.float32)
+    _check_step(oracle, model, x, labels, opt=opt)
