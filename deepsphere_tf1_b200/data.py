@@ -123,3 +123,61 @@ class GaussianNoise(object):
             s = s.reshape([size[0]] + [1] * (len(size) - 1))
             return s * noise + self.loc
         return noise + self.loc
+
+
+class DeviceDataset(LabeledDataset):
+    """The same dataset protocol with the samples RESIDENT IN HBM and batches assembled by one kernel (csrc/input.cu):
+    `.iter(batch_size)` yields `(data, labels)` as CUDA tensors, which `fit` / `train_step` consume without a host -> device copy
+    (the reference's host-side batch assembly + feed_dict is ~40 % of its training step, experiments/cosmo/demo.ipynb:1003).
+    Sample order, shuffling (host numpy permutation, as upstream), noise-level ramp and labels are those of
+    LabeledDataset / LabeledDatasetWithNoise; the noise itself comes from a counter-based device generator (Philox4x32-10), so
+    its values differ from numpy's Mersenne Twister stream while its distribution and the ramp are the same.
+
+    Arguments as LabeledDatasetWithNoise (`end_level=0` / `nit=0` with `start_level=end_level=0` gives the noise-free
+    LabeledDataset), plus `device` and `seed`."""
+
+    def __init__(self, X, label, shuffle=True, start_level=0, end_level=0, nit=0, all_level=False, scale=1., loc=0.0,
+                 device=None, seed=1):
+        import torch
+        super().__init__(X=X, label=label, shuffle=shuffle, transform=None)
+        self._nit, self._sl, self._el = nit, start_level, end_level
+        self._all_level, self._scale, self._loc = all_level, float(scale), float(loc)
+        if self._loc != 0.0:
+            raise NotImplementedError('a noise offset (loc) is not part of the device pipeline')
+        self._device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self._Xd = torch.from_numpy(np.ascontiguousarray(self._X)).to(self._device)
+        lab = np.ascontiguousarray(self._label)
+        self._int_labels = lab.dtype.kind in 'iub'
+        self._ld = torch.from_numpy(lab.astype(np.int32 if self._int_labels else np.float32)).to(self._device)
+        self._seed = int(seed)
+        self._calls = 0
+        self._rs = np.random.RandomState(self._seed)
+
+    noise_level = LabeledDatasetWithNoise.noise_level
+
+    def __iter__(self, batch_size=1):
+        import torch
+        from ._lib import call
+        row_len = int(np.prod(self._X.shape[1:]))
+        lab_len = int(np.prod(self._label.shape[1:])) if self._label.ndim > 1 else 1
+        nb = max(batch_size, 1)
+        for it, sel in enumerate(self._batches(batch_size)):
+            idx = torch.from_numpy(np.atleast_1d(np.asarray(sel)).astype(np.int32)).to(self._device, non_blocking=True)
+            out = torch.empty((nb,) + self._X.shape[1:], dtype=torch.float32, device=self._device)
+            level = float(self.noise_level(it)) * self._scale
+            sscale = None
+            if self._all_level and level != 0.0:           # GaussianNoise(all_level=True): a random level for the last quarter
+                s = self._rs.rand(nb).astype(np.float32)
+                s[:int(nb / 4 * 3)] = 1
+                sscale = torch.from_numpy(s).to(self._device, non_blocking=True)
+            # every call draws from its own block of the counter space
+            call('gather_noise', self._Xd, idx, nb, row_len, level, sscale, self._seed, self._calls << 40, out)
+            self._calls += 1
+            if self._int_labels:
+                lab = torch.empty((nb,) + self._label.shape[1:], dtype=torch.int32, device=self._device)
+                call('gather_labels', self._ld, idx, nb, lab_len, lab)
+            else:
+                lab = self._ld[idx.long()]
+            if batch_size == 1:                            # the reference yields un-batched samples for batch_size 1
+                out, lab = out[0], lab[0]
+            yield out, lab

@@ -433,7 +433,14 @@ class base_model(object):
         """`LabeledDataset.iter(1)` yields un-batched samples ([M] or [M, F], scalar label) like the reference
         (data.py:58-60); restore the batch axis so that batch_size == 1 (the vertex-sharded mode) goes through fit /
         predict(cache=True)."""
-        if self.batch_size != 1 or isinstance(data, torch.Tensor):
+        if self.batch_size != 1:
+            return data, labels
+        if isinstance(data, torch.Tensor):                 # device-resident datasets (data.DeviceDataset)
+            M0 = self.L[0].shape[0]
+            if data.dim() == 1 or (data.dim() == 2 and data.shape[0] == M0 and M0 != 1):
+                data = data.unsqueeze(0)
+                if labels is not None:
+                    labels = labels.unsqueeze(0)
             return data, labels
         a = np.asarray(data)
         M0 = self.L[0].shape[0]

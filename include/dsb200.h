@@ -291,6 +291,16 @@ int dsb200_mul_channel(const float* a, const float* x, int F, int ch, float* out
  * caller-supplied uniform [0,1) tensor; the same call applied to dout is the backward. */
 int dsb200_dropout(const float* x, const float* u, float keep, float* out, long long n, void* stream);
 
+/* ---- device-side input pipeline (csrc/input.cu; replaces the host batch assembly of deepsphere/data.py:39-147 + feed_dict,
+ * models.py:535).  out[b, j] = X[idx[b], j] + level * sample_scale[b] * N(0, 1), j < row_len: gather of the batch's samples from
+ * the HBM-resident dataset plus Gaussian noise (LabeledDatasetWithNoise / GaussianNoise, data.py:95-166) from a counter-based
+ * generator (Philox4x32-10, Box-Muller): the number at (b, j) depends only on (seed, offset, b, j).  sample_scale may be NULL
+ * (all ones; the `all_level` option of GaussianNoise draws it per sample).  level == 0: a plain gather. */
+int dsb200_gather_noise(const float* X, const int32_t* idx, int nb, long long row_len, float level,
+                        const float* sample_scale, long long seed, long long offset, float* out, void* stream);
+/* out[b, j] = labels[idx[b], j] (int32; row_len = 1 for one label per sample, M for dense labels) */
+int dsb200_gather_labels(const int32_t* labels, const int32_t* idx, int nb, long long row_len, int32_t* out, void* stream);
+
 /* ---- one-shot all-reduce of small double vectors over NVLink peer memory (csrc/peer_allreduce.cu; new -- replaces the
  * NCCL launches of the SyncBN sums inside the data-parallel / vertex-sharded step).  Every rank creates one
  * communication buffer and exports its IPC handle (64 bytes); the handles are exchanged by the host (torch.distributed
