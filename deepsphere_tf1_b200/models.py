@@ -562,10 +562,12 @@ class base_model(object):
         else:
             print('training from scratch')
             self._reset_variables()
-        summary = None
+        summary = writer = None
         if self.rank == 0:
             os.makedirs(self._get_path('summaries'), exist_ok=True)
             summary = open(os.path.join(self._get_path('summaries'), 'scalars.jsonl'), 'a')
+            from .summary import FileWriter                  # TensorBoard event file (tf.summary.FileWriter, models.py:463)
+            writer = FileWriter(self._get_path('summaries'))
 
         accuracies_validation, losses_validation, losses_training = [], [], []
         num_steps = int(self.num_epochs * train_dataset.N / self.batch_size)
@@ -616,6 +618,26 @@ class base_model(object):
                 accuracies_validation.append(accuracy)
             losses_validation.append(vloss)
             record.update({'validation/accuracy': float(np.mean(accuracy)), 'validation/loss': float(vloss)})
+            if writer is not None:                           # the tags of models.py:575-603, 815-819, 838, 868
+                sc = {'loss/total': loss, 'learning_rate': learning_rate, 'validation/loss': float(vloss)}
+                if self.regression:
+                    sc.update({'validation/exp_variance': float(accuracy), 'validation/r2': float(f1),
+                               'validation/mae': float(metrics[0]), 'validation/mre': float(metrics[1])})
+                elif self.dense:
+                    AP, class_acc = metrics
+                    names = ('BG', 'TC', 'AR')
+                    sc['validation/accuracy'] = float(accuracy)
+                    sc.update({'validation/accuracy_' + n: float(class_acc[i]) for i, n in enumerate(names)})
+                    sc.update({'validation/f1_' + n: float(f1[i]) for i, n in enumerate(names)})
+                    sc.update({'validation/AP_' + n: float(AP[i]) for i, n in enumerate(names)})
+                else:
+                    sc.update({'validation/accuracy': float(accuracy), 'validation/f1': float(f1)})
+                hist = {}
+                for name in self._P.views:                   # tf.summary.histogram(var.op.name, var) and its gradient
+                    hist[name] = self._P.views[name].detach().cpu().numpy()
+                    hist[name + '/gradients'] = self._P.gviews[name].detach().cpu().numpy()
+                writer.add_summary(step, sc, hist)
+                writer.flush()
             if verbose:
                 print('  validation {}'.format(string))
                 print('  CPU time: {:.0f}s, wall time: {:.0f}s, perf_time_load: {:.3f}s, perf_time: {:.3f}s'.format(
@@ -631,6 +653,7 @@ class base_model(object):
                 max(accuracies_validation), np.mean(accuracies_validation[-10:])))
         if summary is not None:
             summary.close()
+            writer.close()
         if verbose and times:
             print('time per batch: mean = {:.5f}, var = {:.5f}'.format(np.mean(times), np.var(times)))
         t_step = (time.time() - t_wall) / max(num_steps, 1)

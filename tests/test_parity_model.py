@@ -351,6 +351,32 @@ def test_fit_predict_evaluate_api(tmp_path):
     np.testing.assert_array_equal(pred, pred2)
     string, accuracy, f1, loss2, metrics = model.evaluate(x[32:].reshape(8, 192, 1), labels[32:], sess=model)
     assert 'accuracy' in string and loss2 == pytest.approx(loss) and accuracy >= 75
+    # TensorBoard event file with the reference's tags (models.py:575-603, 815-819, 868), one record per evaluation
+    import glob
+    from deepsphere_tf1_b200 import summary
+    files = glob.glob(model._get_path('summaries') + '/events.out.tfevents.*')
+    assert len(files) == 1
+    ev = summary.read_events(files[0])
+    assert [e[0] for e in ev] == [16, 32, 48]
+    for tag in ('loss/total', 'learning_rate', 'validation/accuracy', 'validation/f1', 'validation/loss', 'conv1/weights',
+                'conv1/weights/gradients', 'conv1/bias'):
+        assert tag in ev[-1][1], tag
+    assert ev[-1][1]['validation/loss'] == pytest.approx(loss_val[-1], rel=1e-5)
+    # the evaluation string against the same metrics computed from the ORACLE's predictions (models.py:421-427)
+    import sklearn.metrics
+    from oracle.model import OracleCgcnn
+    oracle = OracleCgcnn(model.L, F=[8, 2], K=[3, 3], p=model.p, batch_norm=[True, True], M=[], statistics='mean')
+    for name in oracle.params:
+        oracle.params[name] = torch.from_numpy(model.get_var(name)).reshape(oracle.params[name].shape)
+    for name in oracle.state:
+        oracle.state[name] = torch.from_numpy(model.get_var(name))
+    ologits, _ = oracle.predict_logits(torch.from_numpy(x[32:].reshape(8, 192, 1)))
+    opred = ologits.argmax(-1).numpy()
+    oloss, _ = oracle.loss(ologits, torch.from_numpy(labels[32:]), oracle.params)
+    expect = 'accuracy: {:.2f} ({:d} / {:d}), f1 (weighted): {:.2f}, loss: {:.2e}'.format(
+        100 * sklearn.metrics.accuracy_score(labels[32:], opred), int((opred == labels[32:]).sum()), 8,
+        100 * sklearn.metrics.f1_score(labels[32:], opred, average='weighted'), float(oloss))
+    assert string.split('\n')[0] == expect
     # a fresh model restores the latest checkpoint when no session is given (models.py:851-860)
     again = models.deepsphere(nsides=[4, 2, 2], F=[8, 2], K=[3, 3], batch_norm=[True, True], M=[], statistics='mean',
                               num_epochs=12, batch_size=8, eval_frequency=16, seed=5, verbose=False,

@@ -1,0 +1,42 @@
+"""TensorBoard event files written without TensorFlow (deepsphere_tf1_b200/summary.py): record framing with masked CRC-32C,
+hand-encoded Event / Summary / HistogramProto, read back by the module's own parser."""
+import struct
+
+import numpy as np
+import pytest
+
+from deepsphere_tf1_b200 import summary
+
+
+def test_crc32c_known_answers():
+    assert summary._crc32c(b'123456789') == 0xE3069283                      # the standard check value of CRC-32C (Castagnoli)
+    assert summary._crc32c(b'') == 0
+    assert summary._crc32c(bytes(32)) == 0x8A9136AA                         # RFC 3720 B.4: 32 bytes of zeros
+
+
+def test_event_file_round_trip(tmp_path):
+    w = summary.FileWriter(str(tmp_path))
+    rs = np.random.RandomState(0)
+    vals = rs.randn(1000) * 0.1
+    w.add_summary(200, {'loss/total': 0.6931, 'learning_rate': 2e-4, 'validation/accuracy': 87.5}, {'conv1/weights': vals})
+    w.add_summary(400, {'loss/total': 0.25})
+    w.close()
+    raw = open(w.path, 'rb').read()
+    (n,) = struct.unpack('<Q', raw[:8])
+    assert raw[12:12 + n].endswith(b'brain.Event:2')                         # the file-version record TensorBoard expects first
+    ev = summary.read_events(w.path)
+    assert [e[0] for e in ev] == [200, 400]
+    assert ev[0][1]['loss/total'] == pytest.approx(0.6931, rel=1e-6) and ev[0][1]['validation/accuracy'] == pytest.approx(87.5)
+    h = ev[0][1]['conv1/weights']
+    assert h['num'] == 1000 and h['min'] == pytest.approx(vals.min()) and h['max'] == pytest.approx(vals.max())
+    assert h['sum'] == pytest.approx(vals.sum()) and h['sum_squares'] == pytest.approx((vals ** 2).sum())
+    assert sum(h['bucket']) == 1000 and len(h['bucket']) == len(h['bucket_limit'])
+    lim = np.array(h['bucket_limit'])
+    assert np.all(np.diff(lim) > 0) and lim[-1] >= vals.max()
+    # a flipped byte is detected
+    bad = bytearray(raw)
+    bad[40] ^= 1
+    p2 = tmp_path / 'bad'
+    p2.write_bytes(bytes(bad))
+    with pytest.raises(ValueError):
+        summary.read_events(str(p2))
