@@ -256,6 +256,34 @@ class DeviceGraph(object):
         else:
             self.bwd = self._pack(LT, 'bwd')
 
+    @classmethod
+    def from_ell(cls, col, val, nnz, device, nested=None):
+        """A graph whose ELL arrays (int32 [M, w] / fp32 [M, w], ascending columns, padding = (row, 0)) already live on the
+        device (graph_build.py).  The transposed values come from `dsb200_ell_transpose` (symmetric pattern required)."""
+        from ._lib import call
+        self = cls.__new__(cls)
+        M, width = col.shape
+        self.M, self.nnz, self.device, self.nested = int(M), int(nnz), device, nested
+        self.max_degree, self.is_ell = int(width), True
+        self.fwd = (None, col, val, int(width))
+        valT = torch.empty_like(val)
+        missing = torch.zeros(1, dtype=torch.int32, device=col.device)
+        call('ell_transpose', col, val, M, width, valT, missing)
+        if int(missing.item()):
+            raise ValueError('from_ell: the sparsity pattern is not symmetric')
+        self.symmetric_pattern = True
+        rec = torch.empty((width, M, 2), dtype=torch.int32, device=col.device)
+        call('ell_pack', col, val, width, M, rec)
+        self.fwd_rec = rec
+        if torch.equal(valT, val):
+            self.bwd, self.bwd_rec = self.fwd, self.fwd_rec
+        else:
+            self.bwd = (None, col, valT, int(width))
+            recT = torch.empty_like(rec)
+            call('ell_pack', col, valT, width, M, recT)
+            self.bwd_rec = recT
+        return self
+
     def _pack(self, A, which='fwd'):
         if self.is_ell:
             width = max(self.max_degree, int(np.diff(A.indptr).max()))

@@ -867,8 +867,11 @@ class cgcnn(base_model):
             if Lj.shape == self.L[i].shape and Lj.nnz == self.L[i].nnz and (Lj != self.L[i]).nnz == 0:
                 self._graphs[i] = g
                 return g
+        pre = getattr(self, '_prebuilt_graphs', None)
         if self.vertex_shard:
             self._graphs[i] = ShardedGraph(self.L[i], self.rank, self.world_size, self.device)
+        elif pre is not None and pre[i] is not None and pre[i].device == self.device:
+            self._graphs[i] = pre[i]                          # built on the device by graph_build.py
         else:
             # HEALPix geometry of the level (nside, nested pixel numbers) when `deepsphere` built the graphs: lets the
             # fused tile recurrence (csrc/cheb_tile.cu) address the vertices as pixel squares
@@ -1332,9 +1335,22 @@ class deepsphere(cgcnn):
     fork's `SphereHealpix` (graphs.py); `new=False` the in-repo 8-neighbour graph that the cosmo experiments use."""
 
     def __init__(self, nsides, indexes=None, use_4=False, sampling='healpix', std=None, full=False, new=True,
-                 n_neighbors=8, lmax=None, **kwargs):
-        L, p = utils.build_laplacians(nsides, indexes=indexes, use_4=use_4, sampling=sampling,
-                                      std=std, full=full, new=new, n_neighbors=n_neighbors, lmax=lmax)
+                 n_neighbors=8, lmax=None, device_build=None, **kwargs):
+        # `device_build`: build the in-repo 8-neighbour graphs (new=False) with the CUDA builder (graph_build.py: same bits as
+        # the numpy path for the same lmax, lmax itself by Lanczos instead of ARPACK); default: levels of 2^16 vertices and more
+        on_device = (sampling == 'healpix' and not new and not use_4 and not kwargs.get('vertex_shard', False)
+                     and not (full if not isinstance(full, list) else any(full)) and torch.cuda.is_available())
+        if device_build is None:
+            device_build = on_device and max(int(n if not isinstance(n, tuple) else n[0]) for n in nsides) >= 128 \
+                and (indexes is None or max(len(ix) for ix in indexes if ix is not None) >= (1 << 16))
+        if device_build and on_device:
+            from . import graph_build
+            dev = kwargs.get('device')
+            L, p, graphs = graph_build.build_laplacians(nsides, indexes=indexes, device=dev, std=std, lmax=lmax)
+            self._prebuilt_graphs = graphs
+        else:
+            L, p = utils.build_laplacians(nsides, indexes=indexes, use_4=use_4, sampling=sampling,
+                                          std=std, full=full, new=new, n_neighbors=n_neighbors, lmax=lmax)
         self.sampling = sampling
         if sampling == 'equiangular':
             self.ratio = nsides[0][1] / nsides[0][0] if isinstance(nsides[0], tuple) else 1.

@@ -291,6 +291,33 @@ int dsb200_mul_channel(const float* a, const float* x, int F, int ch, float* out
  * caller-supplied uniform [0,1) tensor; the same call applied to dout is the backward. */
 int dsb200_dropout(const float* x, const float* u, float keep, float* out, long long n, void* stream);
 
+/* ---- device-side HEALPix graph / Laplacian construction (csrc/healpix_build.cu; replaces the host path of
+ * deepsphere/utils.py:25-133, 231-242, 379-385 and healpy's pix2vec / get_all_neighbours, utils.py:56, 63).  The kernels follow
+ * the numpy path operation by operation (explicitly rounded float32 / float64 arithmetic), the host does the three array
+ * operations in between whose rounding belongs to numpy's libm (graph_build.py): mean -> kernel width, exp -> weights, power ->
+ * d^-1/2.  ids (int64[M]) = NESTED pixel of every vertex or NULL (vertex v = pixel v); inverse (int32[12 nside^2]) = vertex of
+ * every pixel (-1 = none) or NULL with ids == NULL.
+ *   hpx_coords      coords float[M][3] = float32(pix2vec(nside, pixel, nest=True))
+ *   hpx_neighbours  nb int32[M][8] = vertex of the SW, W, NW, N, NE, E, SE, S neighbour (-1 = none), d2 float[M][8] = squared
+ *                   chord distance ((dx^2 + dy^2) + dz^2 in float32 (0 where nb < 0)
+ *   hpx_sort_degree w float[M][8] (weights, host-computed) -> per row the entries in ascending column order (scol, sw; -1 / 0
+ *                   beyond cnt[v]) and deg[v] = their sequential float32 sum (scipy: canonical CSR, W.sum(1))
+ *   hpx_laplacian   ELL rows (col int32[M][width], val float[M][width], padding = (row, 0)) of I - (d12_i w_ij) d12_j
+ *                   (normalized != 0; d12 = deg^-1/2 from the host) or D - W (normalized == 0), diagonal at its sorted place
+ *   ell_rescale     val <- val / half_lmax, diagonal - 1          (rescale_L, utils.py:379-385)
+ *   ell_transpose   valT = values of the transposed matrix on the same (symmetric) pattern; *missing counts entries whose
+ *                   transposed partner is absent */
+int dsb200_hpx_coords(int nside, const long long* ids, long long M, float* coords, void* stream);
+int dsb200_hpx_neighbours(int nside, const long long* ids, const int32_t* inverse, long long M, const float* coords,
+                          int32_t* nb, float* d2, void* stream);
+int dsb200_hpx_sort_degree(const int32_t* nb, const float* w, long long M, int32_t* scol, float* sw, int32_t* cnt,
+                           float* deg, void* stream);
+int dsb200_hpx_laplacian(const int32_t* scol, const float* sw, const int32_t* cnt, const float* d12, const float* deg,
+                         long long M, int width, int normalized, int32_t* col, float* val, void* stream);
+int dsb200_ell_rescale(const int32_t* col, float* val, long long M, int width, float half_lmax, void* stream);
+int dsb200_ell_transpose(const int32_t* col, const float* val, long long M, int width, float* valT, int32_t* missing,
+                         void* stream);
+
 /* ---- device-side input pipeline (csrc/input.cu; replaces the host batch assembly of deepsphere/data.py:39-147 + feed_dict,
  * models.py:535).  out[b, j] = X[idx[b], j] + level * sample_scale[b] * N(0, 1), j < row_len: gather of the batch's samples from
  * the HBM-resident dataset plus Gaussian noise (LabeledDatasetWithNoise / GaussianNoise, data.py:95-166) from a counter-based
