@@ -8,10 +8,11 @@
 //   hpx_neighbours  8 neighbours (SW, W, NW, N, NE, E, SE, S; -1 = none or outside the vertex set) and the squared chord
 //                   distances ((dx^2 + dy^2) + dz^2 in float32                                              (utils.py:63-103)
 //   [host: kernel width = mean of the distances, weights = exp(-d^2 / (2 width))]                          (utils.py:107-111)
-//   hpx_sort_degree entries of every row in ascending column order (scipy's canonical CSR) and the degree as their sequential sum
+//   hpx_sort_degree entries of every row in ascending column order (scipy's canonical CSR) and the degree summed in the order of
+//                   scipy's W.sum(1) (np.add.reduceat: first entry + sequential sum of the rest)
 //   [host: d^-1/2 = power(d, -0.5)]                                                                        (utils.py:238)
 //   hpx_laplacian   I - (d_i^-1/2 w_ij) d_j^-1/2 as ELL rows (diagonal at its sorted place, padding = (row, 0))
-//   ell_rescale     L / (lmax / 2) - I                                                                     (utils.py:383-385)
+//   ell_rescale     L * recip - I, recip = float32(1 / (lmax / 2)): scipy evaluates `L /= s` as `data *= 1.0 / s` (utils.py:383-385)
 //   ell_transpose   values of L^T on the same pattern ((d_i w) d_j is symmetric only to one ulp)
 #include "common.cuh"
 
@@ -148,8 +149,16 @@ hpx_sort_degree_kernel(const int* __restrict__ nb, const float* __restrict__ w, 
         if (m > 0 && c[m - 1] == c[j]) x[m - 1] = __fadd_rn(x[m - 1], x[j]);
         else { c[m] = c[j]; x[m] = x[j]; ++m; }
     }
+    // W.sum(1) of scipy's CSR = np.add.reduceat over the row: the first entry plus the sequential sum of the others
     float s = 0.f;
-    for (int j = 0; j < m; ++j) s = __fadd_rn(s, x[j]);
+    if (m > 0) {
+        s = x[0];
+        if (m > 1) {
+            float tail = x[1];
+            for (int j = 2; j < m; ++j) tail = __fadd_rn(tail, x[j]);
+            s = __fadd_rn(s, tail);
+        }
+    }
     for (int j = 0; j < 8; ++j) { scol[8 * v + j] = j < m ? c[j] : -1; sw[8 * v + j] = j < m ? x[j] : 0.f; }
     cnt[v] = m;
     deg[v] = s;
@@ -185,13 +194,13 @@ hpx_laplacian_kernel(const int* __restrict__ scol, const float* __restrict__ sw,
 }
 
 __global__ void __launch_bounds__(256)
-ell_rescale_kernel(const int* __restrict__ col, float* __restrict__ val, long long M, int width, float s)
+ell_rescale_kernel(const int* __restrict__ col, float* __restrict__ val, long long M, int width, float recip)
 {
     const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= M) return;
     bool diag_done = false;
     for (int j = 0; j < width; ++j) {
-        float x = __fdiv_rn(val[v * width + j], s);
+        float x = __fmul_rn(val[v * width + j], recip);
         if (!diag_done && col[v * width + j] == v) { x = __fsub_rn(x, 1.f); diag_done = true; }   // first (row, .) slot = the diagonal
         else if (col[v * width + j] == v) x = 0.f;                                                 // padding
         val[v * width + j] = x;
@@ -263,10 +272,10 @@ extern "C" int dsb200_hpx_laplacian(const int32_t* scol, const float* sw, const 
     DSB_LAUNCH_CHECK();
 }
 
-extern "C" int dsb200_ell_rescale(const int32_t* col, float* val, long long M, int width, float half_lmax, void* stream)
+extern "C" int dsb200_ell_rescale(const int32_t* col, float* val, long long M, int width, float recip, void* stream)
 {
-    DSB_REQUIRE(col && val && M > 0 && width > 0 && half_lmax > 0.f, "ell_rescale: bad arguments");
-    ell_rescale_kernel<<<HPX_GRID(M)>>>(col, val, M, width, half_lmax);
+    DSB_REQUIRE(col && val && M > 0 && width > 0 && recip > 0.f, "ell_rescale: bad arguments");
+    ell_rescale_kernel<<<HPX_GRID(M)>>>(col, val, M, width, recip);
     DSB_LAUNCH_CHECK();
 }
 

@@ -18,41 +18,37 @@ from ._lib import call
 from .graph import DeviceGraph
 
 
-def lanczos_lmax(graph, steps=64, tol=1e-7, seed=0):
-    """Largest eigenvalue of the symmetric ELL matrix of `graph` (fwd) by Lanczos with full re-orthogonalisation; the sparse
-    products run through libdsb200, the vector algebra through torch (set-up plumbing, not the hot path)."""
+def lanczos_lmax(graph, steps=320, tol=2e-6, seed=0):
+    """Largest eigenvalue of the symmetric ELL matrix of `graph` (fwd) by Lanczos with full re-orthogonalisation (two passes of
+    classical Gram-Schmidt against all previous vectors); stops when the residual bound |beta_k s_k| of the largest Ritz pair
+    falls under tol * lambda, or after `steps` steps (the Ritz value approaches lambda_max from below: the spectrum of a grid
+    Laplacian is dense at its upper end, and the factor 1.02 of utils.py:423 absorbs what is left).  The sparse products run
+    through libdsb200, the vector algebra through torch (set-up plumbing, not the hot path)."""
     from . import ops
     M = graph.M
     dev = graph.fwd[1].device
+    steps = int(min(steps, M, max(16, (6 << 30) // (4 * M))))         # at most 6 GB of Lanczos vectors
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
+    Q = torch.empty((steps + 1, M), dtype=torch.float32, device=dev)
     q = torch.randn(M, generator=gen, device=dev, dtype=torch.float32)
-    q /= q.norm()
-    Q = [q]
+    Q[0] = q / q.norm()
     alphas, betas = [], []
-    prev = None
-    last = None
-    for k in range(min(steps, M)):
-        w = ops.spmm(graph, Q[-1].view(1, M, 1)).view(M).double()
-        a = float(torch.dot(w, Q[-1].double()))
-        alphas.append(a)
-        w = w - a * Q[-1].double()
-        if prev is not None:
-            w = w - betas[-1] * prev.double()
-        for qq in Q:                                         # full re-orthogonalisation (float64 accumulation)
-            w = w - torch.dot(w, qq.double()) * qq.double()
+    lam = None
+    for k in range(steps):
+        w = ops.spmm(graph, Q[k].view(1, M, 1)).view(M)
+        alphas.append(float(torch.dot(w.double(), Q[k].double())))
+        for _ in range(2):
+            w = w - Q[:k + 1].t() @ (Q[:k + 1] @ w)
+        b = float(w.double().norm())
         T = np.diag(alphas) + np.diag(betas, 1) + np.diag(betas, -1)
-        lam = float(np.linalg.eigvalsh(T)[-1])
-        b = float(w.norm())
-        if last is not None and abs(lam - last) <= tol * abs(lam) and k >= 8:
-            return lam
-        last = lam
-        if b < 1e-12:
-            return lam
+        ev, evec = np.linalg.eigh(T)
+        lam = float(ev[-1])
+        if b < 1e-10 or (k >= 4 and abs(b * evec[-1, -1]) <= tol * abs(lam)):
+            break
         betas.append(b)
-        prev = Q[-1]
-        Q.append((w / b).float())
-    return last
+        Q[k + 1] = w / b
+    return lam
 
 
 def healpix_level(nside, indexes=None, device=None, lap_type='normalized', std=None, lmax=None, rescale=True, with_scipy=True):
@@ -102,8 +98,8 @@ def healpix_level(nside, indexes=None, device=None, lap_type='normalized', std=N
     if rescale:
         if lmax is None:
             lmax = np.float32(1.02 * lanczos_lmax(g))
-        call('ell_rescale', col, val, M, width, float(np.float32(lmax) / np.float32(2) if isinstance(lmax, np.floating)
-                                                       else np.float32(lmax / 2)))
+        recip = 1.0 / (lmax / 2)                             # scipy: `L /= s` is `L.data *= 1.0 / s`, with lmax's own scalar type
+        call('ell_rescale', col, val, M, width, float(np.float32(recip)))
         g = DeviceGraph.from_ell(col, val, nnz, device, nested=(nside, indexes if ids is not None else None))
     L = None
     if with_scipy:

@@ -304,7 +304,8 @@ int dsb200_dropout(const float* x, const float* u, float keep, float* out, long 
  *                   beyond cnt[v]) and deg[v] = their sequential float32 sum (scipy: canonical CSR, W.sum(1))
  *   hpx_laplacian   ELL rows (col int32[M][width], val float[M][width], padding = (row, 0)) of I - (d12_i w_ij) d12_j
  *                   (normalized != 0; d12 = deg^-1/2 from the host) or D - W (normalized == 0), diagonal at its sorted place
- *   ell_rescale     val <- val / half_lmax, diagonal - 1          (rescale_L, utils.py:379-385)
+ *   ell_rescale     val <- val * recip, diagonal - 1; recip = float32(1.0 / (lmax / 2)) -- scipy evaluates the `L /= lmax / 2`
+ *                   of rescale_L (utils.py:379-385) as a multiplication by the reciprocal
  *   ell_transpose   valT = values of the transposed matrix on the same (symmetric) pattern; *missing counts entries whose
  *                   transposed partner is absent */
 int dsb200_hpx_coords(int nside, const long long* ids, long long M, float* coords, void* stream);
@@ -314,7 +315,7 @@ int dsb200_hpx_sort_degree(const int32_t* nb, const float* w, long long M, int32
                            float* deg, void* stream);
 int dsb200_hpx_laplacian(const int32_t* scol, const float* sw, const int32_t* cnt, const float* d12, const float* deg,
                          long long M, int width, int normalized, int32_t* col, float* val, void* stream);
-int dsb200_ell_rescale(const int32_t* col, float* val, long long M, int width, float half_lmax, void* stream);
+int dsb200_ell_rescale(const int32_t* col, float* val, long long M, int width, float recip, void* stream);
 int dsb200_ell_transpose(const int32_t* col, const float* val, long long M, int width, float* valT, int32_t* missing,
                          void* stream);
 

@@ -63,7 +63,8 @@ def test_lanczos_lmax_agrees_with_arpack(dev, nside, order):
     Lu = utils.build_laplacian(W, 'normalized')
     expect = utils.estimate_lmax(Lu)
     g, _, lmax = graph_build.healpix_level(nside, indexes, dev, with_scipy=False)
-    assert float(lmax) == pytest.approx(float(expect), rel=1e-5)
+    # the Ritz value approaches the largest eigenvalue from below
+    assert float(expect) * (1 - 2e-5) <= float(lmax) <= float(expect) * (1 + 2e-6)
 
 
 def test_build_laplacians_through_the_model_front_end(dev):
