@@ -387,7 +387,7 @@ class ShardedGraph(object):
             n = int((owner == q).sum())
             if n:
                 self.recv[q] = (int(np.searchsorted(owner, q)), n)
-        self.send = {}
+        self.send, self.send_off = {}, {}
         for q in range(world):
             if q == rank:
                 continue
@@ -395,8 +395,19 @@ class ShardedGraph(object):
             mine = g[(g >= lo) & (g < hi)] - lo
             if len(mine):
                 self.send[q] = mine.astype(np.int32)
+                self.send_off[q] = int(np.searchsorted(g, lo))        # where my rows start in rank q's ghost block
         self.device = device
         if device is not None:
             self.graph = DeviceGraph(self.L_local, device, LT=self.LT_local)
             self.M = self.Me
             self.send_dev = {q: torch.from_numpy(v).to(device) for q, v in self.send.items()}
+            # one-kernel exchange over peer memory (csrc/peer_halo.cu): neighbour table and the concatenated row lists
+            meta, first = [len(self.send), len(self.recv)], 0
+            for q in sorted(self.send):
+                meta += [q, len(self.send[q]), self.send_off[q], first]
+                first += len(self.send[q])
+            meta += sorted(self.recv)
+            self.halo_meta = torch.tensor(meta, dtype=torch.int32, device=device)
+            idx = np.concatenate([self.send[q] for q in sorted(self.send)]) if self.send else np.zeros(1, np.int32)
+            self.halo_idx = torch.from_numpy(idx.astype(np.int32)).to(device)
+            self.halo_max_rows = max([len(v) for v in self.send.values()] + [0])

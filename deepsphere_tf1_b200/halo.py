@@ -10,11 +10,17 @@ import torch
 import torch.distributed as dist
 
 
-def exchange(sg, t, group=None, gather=None):
-    """Fill the ghost rows of t ([1, Me, F] or [Me, F], contiguous) from their owners, in place."""
-    if sg.world == 1 or (not sg.send and not sg.recv):
+def exchange(sg, t, group=None, gather=None, peer=None):
+    """Fill the ghost rows of t ([1, Me, F] or [Me, F], contiguous) from their owners, in place.  `peer` (peer.PeerHalo): one
+    kernel over NVLink peer memory instead of NCCL send / recv pairs; every rank must then call it for every exchange (the
+    mailboxes count the calls), also ranks without neighbours."""
+    if sg.world == 1:
         return t
     rows = t.view(sg.Me, -1)
+    if peer is not None and peer.exchange(sg, rows):
+        return t
+    if not sg.send and not sg.recv:
+        return t
     F = rows.shape[1]
     ops_, keep = [], []
     for q, (off, n) in sorted(sg.recv.items()):

@@ -236,12 +236,12 @@ class _ChebStage(object):
             raise ValueError('the vertex-sharded mode takes one sample per step')
         E = torch.empty((K, 1, sg.Me, Fin), dtype=torch.float32, device=x.device)
         ops.vertex_resize(x, sg.Me, 0.0, out=E[0])
-        halo.exchange(sg, E[0], m.pg)
+        halo.exchange(sg, E[0], m.pg, peer=m._peer_halo)
         for k in range(1, K):
             ops.spmm(g, E[k - 1], E[k - 2] if k >= 2 else None, None, out=E[k], alpha=1.0 if k == 1 else 2.0,
                      beta=0.0 if k == 1 else -1.0, rows=Ml)
             if k < K - 1:
-                halo.exchange(sg, E[k], m.pg)
+                halo.exchange(sg, E[k], m.pg, peer=m._peer_halo)
         if sg.H:
             for k in range(K):
                 ops.fill(E[k, 0, Ml:], 0.0)
@@ -303,7 +303,7 @@ class _ChebStage(object):
         W = m._P.views[self.scope + '/weights']
         G = ops.contract_bwd_data(dy, W, K, Fin)                           # [K, 1, Me, Fin]
         for k in range(K - 2, -1, -1):                                     # adjoint recurrence (csrc/sparse.cu)
-            halo.exchange(sg, G[k + 1], m.pg)
+            halo.exchange(sg, G[k + 1], m.pg, peer=m._peer_halo)
             a2 = G[k + 2] if k + 2 <= K - 1 else None
             ops.spmm(g, G[k + 1], G[k], a2, out=G[k], alpha=2.0 if k >= 1 else 1.0, beta=1.0,
                      gamma=-1.0 if a2 is not None else 0.0, transpose=True, rows=Ml)
@@ -971,6 +971,16 @@ class cgcnn(base_model):
         self._prefetched = None
         self._copy_stream = None
         self._peer = None
+        self._peer_halo = None
+        if self.vertex_shard and self.world_size > 1 and os.environ.get('DSB200_PEER_HALO', '1') == '1':
+            # one-kernel halo exchange over NVLink peer memory (csrc/peer_halo.cu); NCCL send / recv when CUDA IPC is unavailable
+            cap = max([st.sg.H * st.Fin for st in self._encoder if st.sg is not None] + [4])
+            try:
+                from .peer import PeerHalo
+                ph = PeerHalo(cap, self.pg)
+                self._peer_halo = ph if ph.enabled else None
+            except Exception:
+                self._peer_halo = None
         self._arena = torch.zeros(16384, dtype=torch.float64, device=self.device)
         self._arena_off = None
 

@@ -291,6 +291,16 @@ int dsb200_mul_channel(const float* a, const float* x, int F, int ch, float* out
  * caller-supplied uniform [0,1) tensor; the same call applied to dout is the backward. */
 int dsb200_dropout(const float* x, const float* u, float keep, float* out, long long n, void* stream);
 
+/* ---- halo exchange of the vertex-sharded mode over NVLink peer memory (csrc/peer_halo.cu; new).  Every rank owns a mailbox
+ * (dsb200_peer_halo_create, `capacity` floats per half) that its peers open with dsb200_peer_comm_open.  One exchange = one
+ * kernel: push the boundary rows into the neighbours' mailboxes, publish a sequence number, wait for the neighbours', copy the
+ * mailbox into the ghost rows rows[Ml .. Ml + H).  meta int32 (device): [0] sends, [1] receives, per send (peer, rows, first ghost
+ * row at the peer, first entry in idx), per receive (peer); idx int32 (device): owned rows to send, per neighbour ascending.
+ * HOST pointers: comm_out, handle, comms.  16-byte pieces when F % 4 == 0 and rows is 16-byte aligned, single floats otherwise. */
+int dsb200_peer_halo_create(long long capacity, void** comm_out, void* handle_out64);
+int dsb200_peer_halo_exchange(void* const* comms, int rank, int world, float* rows, int F, int Ml, int H,
+                              const int32_t* meta, const int32_t* idx, int max_rows, void* stream);
+
 /* ---- device-side HEALPix graph / Laplacian construction (csrc/healpix_build.cu; replaces the host path of
  * deepsphere/utils.py:25-133, 231-242, 379-385 and healpy's pix2vec / get_all_neighbours, utils.py:56, 63).  The kernels follow
  * the numpy path operation by operation (explicitly rounded float32 / float64 arithmetic), the host does the three array
