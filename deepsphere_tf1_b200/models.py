@@ -1348,7 +1348,7 @@ class deepsphere(cgcnn):
                  n_neighbors=8, lmax=None, device_build=None, **kwargs):
         # `device_build`: build the in-repo 8-neighbour graphs (new=False) with the CUDA builder (graph_build.py: same bits as
         # the numpy path for the same lmax, lmax itself by Lanczos instead of ARPACK); default: levels of 2^16 vertices and more
-        on_device = (sampling == 'healpix' and not new and not use_4 and not kwargs.get('vertex_shard', False)
+        on_device = (sampling == 'healpix' and not new and not use_4
                      and not (full if not isinstance(full, list) else any(full)) and torch.cuda.is_available())
         if device_build is None:
             device_build = on_device and max(int(n if not isinstance(n, tuple) else n[0]) for n in nsides) >= 128 \
@@ -1357,7 +1357,9 @@ class deepsphere(cgcnn):
             from . import graph_build
             dev = kwargs.get('device')
             L, p, graphs = graph_build.build_laplacians(nsides, indexes=indexes, device=dev, std=std, lmax=lmax)
-            self._prebuilt_graphs = graphs
+            # vertex-sharded mode: every rank keeps its own vertex range only (graph.ShardedGraph, cut from the scipy matrices)
+            self._prebuilt_graphs = None if kwargs.get('vertex_shard', False) else graphs
+            del graphs
         else:
             L, p = utils.build_laplacians(nsides, indexes=indexes, use_4=use_4, sampling=sampling,
                                           std=std, full=full, new=new, n_neighbors=n_neighbors, lmax=lmax)

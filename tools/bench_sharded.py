@@ -22,6 +22,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--nside', type=int, default=256)
 ap.add_argument('--steps', type=int, default=10)
 ap.add_argument('--warmup', type=int, default=3)
+ap.add_argument('--lmax', action='store_true', help='skip the eigenvalue solves (1.57 for every level): start-up only')
 ap.add_argument('--graph', action='store_true', help='replay the step (kernels + NCCL send/recv) as one CUDA graph')
 args = ap.parse_args()
 rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
@@ -34,7 +35,7 @@ m = models.deepsphere(nsides=nsides, new=False, F=[16, 32, 64, 64, 64, 1], K=[5]
                       statistics='mean', regression=True, num_epochs=1, batch_size=1, eval_frequency=10 ** 9, seed=0,
                       verbose=False, vertex_shard=world > 1, fused_small=world == 1, cuda_graph=args.graph,
                       scheduler=lambda step: 2e-4, optimizer=lambda lr: optimizers.AdamOptimizer(lr, epsilon=1e-8),
-                      dir_name='_bench_sharded')
+                      dir_name='_bench_sharded', lmax=[1.57] * 6 if args.lmax else None)
 t_build = time.time() - t0
 npix = 12 * args.nside ** 2
 rs = np.random.RandomState(0)
