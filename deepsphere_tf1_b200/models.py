@@ -972,8 +972,10 @@ class cgcnn(base_model):
         self._copy_stream = None
         self._peer = None
         self._peer_halo = None
-        if self.vertex_shard and self.world_size > 1 and os.environ.get('DSB200_PEER_HALO', '1') == '1':
-            # one-kernel halo exchange over NVLink peer memory (csrc/peer_halo.cu); NCCL send / recv when CUDA IPC is unavailable
+        if self.vertex_shard and self.world_size > 1 and os.environ.get('DSB200_PEER_HALO', '0') == '1':
+            # opt-in: one-kernel halo exchange over NVLink peer memory (csrc/peer_halo.cu).  Measured on 2 GPUs inside the step's
+            # CUDA graph it is no faster than NCCL's grouped send / recv (2.75 vs 2.48 ms at Nside 512): the ~57 rank
+            # synchronisations of a sharded step cost their dependency chain, not the transport
             cap = max([st.sg.H * st.Fin for st in self._encoder if st.sg is not None] + [4])
             try:
                 from .peer import PeerHalo
