@@ -60,3 +60,13 @@ def assert_close(actual, expected, rtol, name='', floor=0.0):
     scale = max(np.abs(e).max(), floor, 1e-30)
     err = np.abs(a - e).max() / scale
     assert err <= rtol, '{}: max error {:.3e} relative to max |expected| {:.3e} (rtol {})'.format(name, err, scale, rtol)
+
+
+def free_port():
+    """A TCP port nobody listens on (for torchrun's rendezvous)."""
+    import socket
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port

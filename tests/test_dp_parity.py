@@ -9,6 +9,8 @@ import pytest
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from helpers import free_port  # noqa: E402
 
 
 @pytest.mark.gpu
@@ -17,7 +19,7 @@ def test_data_parallel_model_matches_single_gpu_model():
         pytest.skip('needs at least 2 GPUs (gpurun --gpus 2)')
     n = 4 if torch.cuda.device_count() >= 4 else 2
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n),
-           '--master-addr', '127.0.0.1', '--master-port', str(29300 + os.getpid() % 150),
+           '--master-addr', '127.0.0.1', '--master-port', str(free_port()),
            os.path.join(ROOT, 'tests', 'dp_worker.py')]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-4000:]

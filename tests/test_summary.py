@@ -40,3 +40,25 @@ def test_event_file_round_trip(tmp_path):
     p2.write_bytes(bytes(bad))
     with pytest.raises(ValueError):
         summary.read_events(str(p2))
+
+
+def test_tensorboard_reads_the_event_file(tmp_path):
+    """The files are for TensorBoard: its own loader (record checksums, Event / Summary protos, the scalar and histogram
+    plugins' data-compat layer) must accept them and return the values."""
+    efl = pytest.importorskip('tensorboard.backend.event_processing.event_file_loader')
+    from tensorboard.util import tensor_util
+    w = summary.FileWriter(str(tmp_path))
+    vals = np.linspace(-1, 1, 101)
+    w.add_summary(7, {'loss/total': 0.125, 'validation/accuracy': 93.75}, {'conv1/weights': vals})
+    w.close()
+    events = list(efl.EventFileLoader(w.path).Load())
+    assert events[0].file_version == 'brain.Event:2'
+    ev = events[1]
+    assert ev.step == 7
+    got = {v.tag: v for v in ev.summary.value}
+    assert got['loss/total'].metadata.plugin_data.plugin_name == 'scalars'
+    assert float(tensor_util.make_ndarray(got['loss/total'].tensor)) == 0.125
+    assert float(tensor_util.make_ndarray(got['validation/accuracy'].tensor)) == 93.75
+    assert got['conv1/weights'].metadata.plugin_data.plugin_name == 'histograms'
+    h = tensor_util.make_ndarray(got['conv1/weights'].tensor)          # [buckets, (left, right, count)]
+    assert h.shape[1] == 3 and h[:, 2].sum() == 101

@@ -17,6 +17,8 @@ import torch.multiprocessing as mp
 from scipy import sparse
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+from helpers import free_port  # noqa: E402
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 
@@ -102,7 +104,7 @@ def test_sharded_model_matches_single_device_model():
     n = min(4, torch.cuda.device_count())
     n = 4 if n >= 4 else 2
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n),
-           '--master-addr', '127.0.0.1', '--master-port', str(29500 + os.getpid() % 400),
+           '--master-addr', '127.0.0.1', '--master-port', str(free_port()),
            os.path.join(ROOT, 'tests', 'sharded_worker.py')]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-4000:]
@@ -116,7 +118,7 @@ def test_peer_memory_allreduce_matches_nccl():
         pytest.skip('needs at least 2 GPUs (gpurun --gpus 2)')
     n = 4 if torch.cuda.device_count() >= 4 else 2
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n),
-           '--master-addr', '127.0.0.1', '--master-port', str(29900 + os.getpid() % 90),
+           '--master-addr', '127.0.0.1', '--master-port', str(free_port()),
            os.path.join(ROOT, 'tests', 'peer_worker.py')]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-4000:]
