@@ -703,6 +703,58 @@ class base_model(object):
             if key in sd:
                 s.copy_(sd[key])
 
+    # TensorFlow checkpoints (tf.train.Saver files of the reference, models.py:723, 847-860): same variable names
+    def tf_variables(self):
+        """{TF variable name: array} as `tf.train.Saver` would store them: trainable variables, batch-norm moving statistics,
+        `training/global_step`, and the Adam / Momentum / RMSProp slots under TF's slot names."""
+        out = {name: self._P.views[name].detach().cpu().numpy().reshape(self._P.shapes[name]) for name in self._P.views}
+        out.update({k: v.detach().cpu().numpy() for k, v in self._state.items()})
+        out['training/global_step'] = np.asarray(self.global_step, dtype=np.int64)
+        for s, slot in enumerate(self._slots):
+            suffix = self._opt.tf_slot_names[s] if hasattr(self._opt, 'tf_slot_names') else 'slot{}'.format(s)
+            for name, shape, off, n, std, init in self._P.specs:
+                out['{}/{}'.format(name, suffix)] = slot[off:off + n].detach().cpu().numpy().reshape(shape)
+        return out
+
+    def save_tf_checkpoint(self, prefix):
+        from . import tf_checkpoint
+        tf_checkpoint.write_checkpoint(prefix, self.tf_variables())
+
+    def load_tf_checkpoint(self, prefix, strict=True):
+        """Restore from a TensorFlow V2 checkpoint written by the reference (`checkpoints/<dir_name>/model-<step>`) or by
+        `save_tf_checkpoint`.  Returns the names found in the file that this model does not use."""
+        from . import tf_checkpoint
+        ck = tf_checkpoint.read_checkpoint(prefix)
+        used = set()
+        for name, view in self._P.views.items():
+            if name not in ck:
+                if strict:
+                    raise KeyError('checkpoint {} has no variable {}'.format(prefix, name))
+                continue
+            if int(np.prod(ck[name].shape)) != view.numel():
+                raise ValueError('{}: checkpoint shape {} does not match {}'.format(name, ck[name].shape, tuple(view.shape)))
+            view.copy_(torch.from_numpy(np.ascontiguousarray(ck[name], dtype=np.float32)).reshape(view.shape))
+            used.add(name)
+        for k in self._state:
+            if k in ck:
+                self._state[k].copy_(torch.from_numpy(np.ascontiguousarray(ck[k], dtype=np.float32)))
+                used.add(k)
+            elif strict:
+                raise KeyError('checkpoint {} has no variable {}'.format(prefix, k))
+        for key in ('training/global_step', 'global_step'):
+            if key in ck:
+                self.global_step = int(ck[key])
+                used.add(key)
+        for s, slot in enumerate(self._slots):
+            suffix = self._opt.tf_slot_names[s] if hasattr(self._opt, 'tf_slot_names') else 'slot{}'.format(s)
+            for name, shape, off, n, std, init in self._P.specs:
+                key = '{}/{}'.format(name, suffix)
+                if key in ck:
+                    slot[off:off + n].copy_(torch.from_numpy(np.ascontiguousarray(ck[key], dtype=np.float32)).reshape(-1))
+                    used.add(key)
+        self._graph_exec = None
+        return sorted(set(ck) - used)
+
     def save_checkpoint(self, step):
         if self.rank != 0:
             return
@@ -722,7 +774,13 @@ class base_model(object):
     def _restore_latest(self):
         f = self._latest_checkpoint()
         if f is None:
-            return False
+            # a run directory written by the reference itself: TensorFlow checkpoint files
+            from . import tf_checkpoint
+            prefix = tf_checkpoint.latest_checkpoint(self._get_path('checkpoints'))
+            if prefix is None:
+                return False
+            self.load_tf_checkpoint(prefix, strict=False)
+            return True
         self.load_state_dict(torch.load(f, map_location='cpu'))
         return True
 

@@ -42,6 +42,7 @@ class GradientDescentOptimizer(_Optimizer):
 
 class MomentumOptimizer(_Optimizer):
     kind, slots = OPT_MOMENTUM, 1
+    tf_slot_names = ('Momentum',)                 # names of the slot variables in a tf.train.Saver checkpoint
 
     def __init__(self, learning_rate, momentum=0.9, use_nesterov=False):
         if use_nesterov:
@@ -54,6 +55,7 @@ class MomentumOptimizer(_Optimizer):
 
 class AdamOptimizer(_Optimizer):
     kind, slots = OPT_ADAM, 2
+    tf_slot_names = ('Adam', 'Adam_1')            # first / second moment
 
     def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
         self.learning_rate, self.beta1, self.beta2, self.epsilon = learning_rate, beta1, beta2, epsilon
@@ -65,6 +67,7 @@ class AdamOptimizer(_Optimizer):
 
 class RMSPropOptimizer(_Optimizer):
     kind, slots, slot1_init = OPT_RMSPROP, 2, 1.0
+    tf_slot_names = ('RMSProp', 'RMSProp_1')      # mean square, momentum
 
     def __init__(self, learning_rate, decay=0.9, momentum=0.0, epsilon=1e-10):
         self.learning_rate, self.decay, self.momentum, self.epsilon = learning_rate, decay, momentum, epsilon
