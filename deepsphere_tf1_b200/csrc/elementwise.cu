@@ -7,6 +7,7 @@
 //   softmax cross-entropy / MSE / L2 regulariser      (models.py:777-820)
 //   optimizers with TF1 update rules                  (models.py:822-843)
 #include "common.cuh"
+#include "bf16.cuh"
 #include <float.h>
 
 namespace dsb200 {
@@ -45,10 +46,10 @@ __global__ void sums_to_float_kernel(const double* __restrict__ s, float* out, i
 // ------------------------------------------------------------------------------------------
 // normalise -> + bias -> activation -> pool over p consecutive vertices.
 // One thread owns VEC features of one pooled (sample, vertex) row.
-template <int VEC, int ACT>
+template <int VEC, int ACT, typename T>
 __global__ void __launch_bounds__(256)
-bn_act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
-                       const float* __restrict__ bias, float* __restrict__ out,
+bn_act_pool_fwd_kernel(const T* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ bias, T* __restrict__ out,
                        long long Rout, int Fv, int p, int pool, int act)
 {
     const long long total = Rout * Fv;
@@ -65,13 +66,13 @@ bn_act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
             bs[v] = bias ? __ldg(bias + f0 + v) : 0.f;
             acc[v] = (pool == DSB200_POOL_MAX) ? -FLT_MAX : 0.f;
         }
-        const float* yp = y + (ro * p) * F + f0;
+        const T* yp = y + (ro * p) * F + f0;
         for (int j = 0; j < p; ++j) {
             float t[VEC];
             if (VEC == 4) { const float4 q = ldg4(yp + (long long)j * F); t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w; }
             else {
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) t[v] = __ldg(yp + (long long)j * F + v);
+                for (int v = 0; v < VEC; ++v) t[v] = ldg1(yp + (long long)j * F + v);
             }
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
@@ -84,11 +85,11 @@ bn_act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
 #pragma unroll
             for (int v = 0; v < VEC; ++v) acc[v] *= inv;
         }
-        float* op = out + ro * F + f0;
+        T* op = out + ro * F + f0;
         if (VEC == 4) st4(op, make_float4(acc[0], acc[1], acc[2], acc[3]));
         else {
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) op[v] = acc[v];
+            for (int v = 0; v < VEC; ++v) st1(op + v, acc[v]);
         }
     }
 }
@@ -96,10 +97,10 @@ bn_act_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
 // Lean forward for the combination every DeepSphere encoder layer uses (batch norm, relu, max pool over P children,
 // F % 4 == 0), same arithmetic as the general kernel.  One thread = one float4 feature group of one pooled row, its P
 // loads issued back to back; the per-feature parameters sit in shared memory.
-template <int P>
+template <int P, typename T>
 __global__ void __launch_bounds__(256)
-bn_relu_max_fwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
-                       const float* __restrict__ bias, float* __restrict__ out, long long total, int Fv)
+bn_relu_max_fwd_kernel(const T* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ bias, T* __restrict__ out, long long total, int Fv)
 {
     extern __shared__ float par[];                          // [3][F]: mean, rstd, bias
     const int F = Fv * 4;
@@ -113,7 +114,7 @@ bn_relu_max_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
     if (g >= total) return;
     const long long ro = g / Fv;
     const int f0 = (int)(g - ro * Fv) * 4;
-    const float* yp = y + (ro * P) * F + f0;
+    const T* yp = y + (ro * P) * F + f0;
     float4 q[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) q[j] = ldg4(yp + (long long)j * F);
@@ -134,25 +135,25 @@ bn_relu_max_fwd_kernel(const float* __restrict__ y, const float* __restrict__ me
 //   MODE 0: write gz and accumulate the sums          (no batch norm: gz is already dy)
 //   MODE 1: accumulate the sums only                  (batch norm, pass 1: nothing is written)
 //   MODE 2: write dy = rstd (gz - S1/n - xhat S2/n)   (batch norm, pass 2: gz is recomputed, never stored)
-template <int VEC> __device__ __forceinline__ void load_vec(const float* p, float* v) {
+template <int VEC, typename T> __device__ __forceinline__ void load_vec(const T* p, float* v) {
     if (VEC == 4) { const float4 q = ldg4(p); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
     else {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) v[i] = __ldg(p + i);
+        for (int i = 0; i < VEC; ++i) v[i] = ldg1(p + i);
     }
 }
-template <int VEC> __device__ __forceinline__ void store_vec(float* p, const float* v) {
+template <int VEC, typename T> __device__ __forceinline__ void store_vec(T* p, const float* v) {
     if (VEC == 4) st4(p, make_float4(v[0], v[1], v[2], v[3]));
     else {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) p[i] = v[i];
+        for (int i = 0; i < VEC; ++i) st1(p + i, v[i]);
     }
 }
 
-template <int VEC, int MODE, int ACT>
+template <int VEC, int MODE, int ACT, typename T>
 __global__ void __launch_bounds__(256)
-bn_act_pool_bwd_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
-                       const float* __restrict__ bias, const float* __restrict__ dout, float* __restrict__ gz,
+bn_act_pool_bwd_kernel(const T* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                       const float* __restrict__ bias, const T* __restrict__ dout, T* __restrict__ gz,
                        double* __restrict__ sums_bwd, double count, long long Rout, int Fv, int p, int pool, int act)
 {
     extern __shared__ float red[];                          // [2][F]
@@ -179,8 +180,8 @@ bn_act_pool_bwd_kernel(const float* __restrict__ y, const float* __restrict__ me
         for (long long ro = (long long)blockIdx.x * rows_per_block + rl; ro < Rout; ro += (long long)gridDim.x * rows_per_block) {
             float d[VEC];
             load_vec<VEC>(dout + ro * F + f0, d);
-            const float* yp = y + (ro * p) * F + f0;
-            float* gp = MODE != 1 ? gz + (ro * p) * F + f0 : nullptr;
+            const T* yp = y + (ro * p) * F + f0;
+            T* gp = MODE != 1 ? gz + (ro * p) * F + f0 : nullptr;
             const bool is_max = pool == DSB200_POOL_MAX && p > 1;
             const float inv = is_max ? 1.f : 1.f / (float)p;
             if (p <= PC) {
@@ -274,8 +275,9 @@ bn_act_pool_bwd_kernel(const float* __restrict__ y, const float* __restrict__ me
 //   sum gz       = sum_{pooled rows} [out > 0] dout
 //   sum gz*xhat  = sum_{pooled rows} [out > 0] dout (out - bias)
 // read from the two POOLED tensors (2 * Y/P bytes instead of Y + Y/P).
+template <typename T>
 __global__ void __launch_bounds__(256)
-bn_relu_pool_sums_kernel(const float* __restrict__ out, const float* __restrict__ dout, const float* __restrict__ bias,
+bn_relu_pool_sums_kernel(const T* __restrict__ out, const T* __restrict__ dout, const float* __restrict__ bias,
                          double* __restrict__ sums_bwd, long long Rout, int Fv)
 {
     extern __shared__ float red[];                          // [2][F]
@@ -318,10 +320,10 @@ bn_relu_pool_sums_kernel(const float* __restrict__ out, const float* __restrict_
 
 // Pass 2: dy = rstd (gz - S1/n - xhat S2/n); one thread = one float4 feature group of one pooled row and its
 // P children.  The arg-max is recomputed from y (first maximum wins, as in the forward pass).
-template <int P>
+template <int P, typename T>
 __global__ void __launch_bounds__(256)
-bn_relu_max_bwd_dy_kernel(const float* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
-                          const float* __restrict__ bias, const float* __restrict__ dout, float* __restrict__ dy,
+bn_relu_max_bwd_dy_kernel(const T* __restrict__ y, const float* __restrict__ mean, const float* __restrict__ rstd,
+                          const float* __restrict__ bias, const T* __restrict__ dout, T* __restrict__ dy,
                           const double* __restrict__ sums_bwd, double count, long long total, int Fv)
 {
     extern __shared__ float par[];                          // [5][F]: mean, rstd, bias, S1/n, S2/n
@@ -345,8 +347,8 @@ bn_relu_max_bwd_dy_kernel(const float* __restrict__ y, const float* __restrict__
     const float m1[4] = {a4.x, a4.y, a4.z, a4.w}, m2[4] = {b4.x, b4.y, b4.z, b4.w};
     const float4 d4 = ldg4(dout + ro * F + f0);
     const float d[4] = {d4.x, d4.y, d4.z, d4.w};
-    const float* yp = y + (ro * P) * F + f0;
-    float* op = dy + (ro * P) * F + f0;
+    const T* yp = y + (ro * P) * F + f0;
+    T* op = dy + (ro * P) * F + f0;
     float xh[P][4];
 #pragma unroll
     for (int j = 0; j < P; ++j) {
@@ -868,6 +870,15 @@ dropout_kernel(const float* __restrict__ x, const float* __restrict__ u, float k
         out[i] = (__ldg(u + i) < keep) ? __ldg(x + i) * inv : 0.f;
 }
 
+// storage-type conversion of an activation tensor (BF16 mode: operators without a bf16 kernel run in fp32 between two casts)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ x, TO* __restrict__ out, long long n4, long long n)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) st4(out + 4 * i, ldg4(x + 4 * i));
+    if (blockIdx.x == 0 && threadIdx.x < (int)(n - 4 * n4)) st1(out + 4 * n4 + threadIdx.x, ldg1(x + 4 * n4 + threadIdx.x));
+}
+
 static inline bool aligned16(const void* a, const void* b = nullptr, const void* c = nullptr)
 {
     return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
@@ -901,8 +912,9 @@ extern "C" int dsb200_sums_to_float(const double* sums, float* out, int n, void*
     DSB_LAUNCH_CHECK();
 }
 
-extern "C" int dsb200_bn_act_pool_fwd(const float* y, const float* mean, const float* rstd, const float* bias,
-                                      float* out, int B, int M, int F, int p, int pool, int act, void* stream)
+template <typename T>
+static int bn_act_pool_fwd_launch(const T* y, const float* mean, const float* rstd, const float* bias,
+                                  T* out, int B, int M, int F, int p, int pool, int act, void* stream)
 {
     DSB_REQUIRE(y && out && B > 0 && M > 0 && F > 0 && p >= 1, "bn_act_pool_fwd: bad arguments");
     DSB_REQUIRE(M % p == 0, "bn_act_pool_fwd: M must be a multiple of p");
@@ -914,13 +926,13 @@ extern "C" int dsb200_bn_act_pool_fwd(const float* y, const float* mean, const f
         const long long blocks = (total + 255) / 256;
         if (blocks <= 0x7fffffffLL) {
             const size_t sm = 3 * (size_t)F * sizeof(float);
-#define DSB_LEAN(PP) bn_relu_max_fwd_kernel<PP><<<(unsigned)blocks, 256, sm, STREAM>>>(y, mean, rstd, bias, out, total, F / 4)
+#define DSB_LEAN(PP) bn_relu_max_fwd_kernel<PP, T><<<(unsigned)blocks, 256, sm, STREAM>>>(y, mean, rstd, bias, out, total, F / 4)
             if (p == 1) DSB_LEAN(1); else if (p == 2) DSB_LEAN(2); else DSB_LEAN(4);
 #undef DSB_LEAN
             DSB_LAUNCH_CHECK();
         }
     }
-#define DSB_FWD(V, A, G) bn_act_pool_fwd_kernel<V, A><<<G, 256, 0, STREAM>>>(y, mean, rstd, bias, out, Rout, F / V, p, pool, act)
+#define DSB_FWD(V, A, G) bn_act_pool_fwd_kernel<V, A, T><<<G, 256, 0, STREAM>>>(y, mean, rstd, bias, out, Rout, F / V, p, pool, act)
     if (F % 4 == 0 && aligned16(y, out)) {
         const int g = grid_for(Rout * (F / 4), 256);
         if (act == DSB200_ACT_RELU) DSB_FWD(4, DSB200_ACT_RELU, g);
@@ -934,9 +946,21 @@ extern "C" int dsb200_bn_act_pool_fwd(const float* y, const float* mean, const f
     DSB_LAUNCH_CHECK();
 }
 
-template <int MODE>
-static int bn_act_pool_bwd_launch(const float* y, const float* mean, const float* rstd, const float* bias,
-                                  const float* dout, float* gz, double* sums_bwd, double count,
+extern "C" int dsb200_bn_act_pool_fwd(const float* y, const float* mean, const float* rstd, const float* bias,
+                                      float* out, int B, int M, int F, int p, int pool, int act, void* stream)
+{
+    return bn_act_pool_fwd_launch<float>(y, mean, rstd, bias, out, B, M, F, p, pool, act, stream);
+}
+
+extern "C" int dsb200_bn_act_pool_fwd_bf16(const void* y, const float* mean, const float* rstd, const float* bias,
+                                           void* out, int B, int M, int F, int p, int pool, int act, void* stream)
+{
+    return bn_act_pool_fwd_launch<bf16>((const bf16*)y, mean, rstd, bias, (bf16*)out, B, M, F, p, pool, act, stream);
+}
+
+template <int MODE, typename T>
+static int bn_act_pool_bwd_launch(const T* y, const float* mean, const float* rstd, const float* bias,
+                                  const T* dout, T* gz, double* sums_bwd, double count,
                                   int B, int M, int F, int p, int pool, int act, cudaStream_t st)
 {
     DSB_REQUIRE(y && dout && sums_bwd && B > 0 && M > 0 && F > 0 && p >= 1, "bn_act_pool_bwd: bad arguments");
@@ -951,13 +975,13 @@ static int bn_act_pool_bwd_launch(const float* y, const float* mean, const float
         const long long blocks = (total + 255) / 256;
         if (blocks <= 0x7fffffffLL) {
             const size_t sm = 5 * (size_t)F * sizeof(float);
-#define DSB_DY(PP) bn_relu_max_bwd_dy_kernel<PP><<<(unsigned)blocks, 256, sm, st>>>(y, mean, rstd, bias, dout, gz, sums_bwd, count, total, F / 4)
+#define DSB_DY(PP) bn_relu_max_bwd_dy_kernel<PP, T><<<(unsigned)blocks, 256, sm, st>>>(y, mean, rstd, bias, dout, gz, sums_bwd, count, total, F / 4)
             if (p == 1) DSB_DY(1); else if (p == 2) DSB_DY(2); else DSB_DY(4);
 #undef DSB_DY
             DSB_LAUNCH_CHECK();
         }
     }
-#define DSB_BWD(V, A) bn_act_pool_bwd_kernel<V, MODE, A><<<grid, 256, smem, st>>>(y, mean, rstd, bias, dout, gz, sums_bwd, count, Rout, F / V, p, pool, act)
+#define DSB_BWD(V, A) bn_act_pool_bwd_kernel<V, MODE, A, T><<<grid, 256, smem, st>>>(y, mean, rstd, bias, dout, gz, sums_bwd, count, Rout, F / V, p, pool, act)
     if (F % 4 == 0 && F / 4 <= 256 && a16) {
         const int Fv = F / 4, rpb = 256 / Fv;
         const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 8);
@@ -978,8 +1002,16 @@ extern "C" int dsb200_bn_act_pool_bwd(const float* y, const float* mean, const f
                                       const float* dout, float* gz, double* sums_bwd,
                                       int B, int M, int F, int p, int pool, int act, void* stream)
 {
-    if (gz) return bn_act_pool_bwd_launch<0>(y, mean, rstd, bias, dout, gz, sums_bwd, 1.0, B, M, F, p, pool, act, STREAM);
-    return bn_act_pool_bwd_launch<1>(y, mean, rstd, bias, dout, nullptr, sums_bwd, 1.0, B, M, F, p, pool, act, STREAM);
+    if (gz) return bn_act_pool_bwd_launch<0, float>(y, mean, rstd, bias, dout, gz, sums_bwd, 1.0, B, M, F, p, pool, act, STREAM);
+    return bn_act_pool_bwd_launch<1, float>(y, mean, rstd, bias, dout, nullptr, sums_bwd, 1.0, B, M, F, p, pool, act, STREAM);
+}
+
+extern "C" int dsb200_bn_act_pool_bwd_bf16(const void* y, const float* mean, const float* rstd, const float* bias,
+                                           const void* dout, void* gz, double* sums_bwd,
+                                           int B, int M, int F, int p, int pool, int act, void* stream)
+{
+    if (gz) return bn_act_pool_bwd_launch<0, bf16>((const bf16*)y, mean, rstd, bias, (const bf16*)dout, (bf16*)gz, sums_bwd, 1.0, B, M, F, p, pool, act, STREAM);
+    return bn_act_pool_bwd_launch<1, bf16>((const bf16*)y, mean, rstd, bias, (const bf16*)dout, nullptr, sums_bwd, 1.0, B, M, F, p, pool, act, STREAM);
 }
 
 extern "C" int dsb200_bn_act_pool_bwd_dy(const float* y, const float* mean, const float* rstd, const float* bias,
@@ -987,19 +1019,40 @@ extern "C" int dsb200_bn_act_pool_bwd_dy(const float* y, const float* mean, cons
                                          int B, int M, int F, int p, int pool, int act, void* stream)
 {
     DSB_REQUIRE(mean && rstd && dy && count > 0, "bn_act_pool_bwd_dy: bad arguments");
-    return bn_act_pool_bwd_launch<2>(y, mean, rstd, bias, dout, dy, const_cast<double*>(sums_bwd), count, B, M, F, p, pool, act, STREAM);
+    return bn_act_pool_bwd_launch<2, float>(y, mean, rstd, bias, dout, dy, const_cast<double*>(sums_bwd), count, B, M, F, p, pool, act, STREAM);
 }
 
-extern "C" int dsb200_bn_relu_pool_sums(const float* out, const float* dout, const float* bias, double* sums_bwd,
-                                        long long Rout, int F, void* stream)
+extern "C" int dsb200_bn_act_pool_bwd_dy_bf16(const void* y, const float* mean, const float* rstd, const float* bias,
+                                              const void* dout, const double* sums_bwd, double count, void* dy,
+                                              int B, int M, int F, int p, int pool, int act, void* stream)
+{
+    DSB_REQUIRE(mean && rstd && dy && count > 0, "bn_act_pool_bwd_dy: bad arguments");
+    return bn_act_pool_bwd_launch<2, bf16>((const bf16*)y, mean, rstd, bias, (const bf16*)dout, (bf16*)dy, const_cast<double*>(sums_bwd), count, B, M, F, p, pool, act, STREAM);
+}
+
+template <typename T>
+static int bn_relu_pool_sums_launch(const T* out, const T* dout, const float* bias, double* sums_bwd,
+                                    long long Rout, int F, void* stream)
 {
     DSB_REQUIRE(out && dout && sums_bwd && Rout > 0 && F > 0, "bn_relu_pool_sums: bad arguments");
     DSB_REQUIRE(F % 4 == 0 && F <= 1024, "bn_relu_pool_sums: F must be a multiple of 4, at most 1024");
     DSB_REQUIRE(aligned16(out, dout), "bn_relu_pool_sums: tensors must be 16-byte aligned");
     const int Fv = F / 4, rpb = 256 / Fv;
     const int grid = grid_for((Rout + rpb - 1) / rpb * 256, 256, 8);
-    bn_relu_pool_sums_kernel<<<grid, 256, 2 * (size_t)F * sizeof(float), STREAM>>>(out, dout, bias, sums_bwd, Rout, Fv);
+    bn_relu_pool_sums_kernel<T><<<grid, 256, 2 * (size_t)F * sizeof(float), STREAM>>>(out, dout, bias, sums_bwd, Rout, Fv);
     DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_bn_relu_pool_sums(const float* out, const float* dout, const float* bias, double* sums_bwd,
+                                        long long Rout, int F, void* stream)
+{
+    return bn_relu_pool_sums_launch<float>(out, dout, bias, sums_bwd, Rout, F, stream);
+}
+
+extern "C" int dsb200_bn_relu_pool_sums_bf16(const void* out, const void* dout, const float* bias, double* sums_bwd,
+                                             long long Rout, int F, void* stream)
+{
+    return bn_relu_pool_sums_launch<bf16>((const bf16*)out, (const bf16*)dout, bias, sums_bwd, Rout, F, stream);
 }
 
 extern "C" int dsb200_bn_bwd_apply(const float* y, const float* mean, const float* rstd, const double* sums_bwd,
@@ -1186,5 +1239,21 @@ extern "C" int dsb200_dropout(const float* x, const float* u, float keep, float*
     DSB_REQUIRE(x && u && out && n > 0 && keep > 0.f && keep <= 1.f, "dropout: bad arguments");
     DSB_REQUIRE(x != out, "dropout: out must not alias x");
     dropout_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(x, u, keep, out, n);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_cast_f32_to_bf16(const float* x, void* out, long long n, void* stream)
+{
+    DSB_REQUIRE(x && out && n > 0, "cast: bad arguments");
+    DSB_REQUIRE(aligned16(x) && (((uintptr_t)out) & 7) == 0, "cast: tensors must be 16-byte aligned");
+    cast_kernel<float, bf16><<<grid_for(n / 4 + 1, 256), 256, 0, STREAM>>>(x, (bf16*)out, n / 4, n);
+    DSB_LAUNCH_CHECK();
+}
+
+extern "C" int dsb200_cast_bf16_to_f32(const void* x, float* out, long long n, void* stream)
+{
+    DSB_REQUIRE(x && out && n > 0, "cast: bad arguments");
+    DSB_REQUIRE(aligned16(out) && (((uintptr_t)x) & 7) == 0, "cast: tensors must be 16-byte aligned");
+    cast_kernel<bf16, float><<<grid_for(n / 4 + 1, 256), 256, 0, STREAM>>>((const bf16*)x, out, n / 4, n);
     DSB_LAUNCH_CHECK();
 }

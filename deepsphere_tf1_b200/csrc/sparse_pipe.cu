@@ -23,6 +23,7 @@
 // Measured (tools/exp_timing_method.py, back to back over rotating operand sets): cosmo layer 2 60 -> 42 us, layer 3 35 -> 23 us.
 // F in {16, 32, 64} (NCH = 4, 8, 16 chunks per row), ELL width 7 / 9; other shapes keep the gather kernels.
 #include "common.cuh"
+#include "bf16.cuh"
 #include <stdlib.h>
 
 namespace dsb200 {
@@ -85,14 +86,25 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
 // Warp-specialised: warp 8 is the producer (it alone waits on global-memory latency: tile lists, bulk copies, halo
 // copies), warps 0..7 consume -- each owns TR/8 rows of every item and synchronises with nobody but the producer
 // (full[s] / empty[s] mbarriers), so the warps drift apart and hide each other's shared-memory latency.
-template <int W, int NCH, bool HASY, bool HASZ, bool DENSE>
+// BF16: the tensors hold bfloat16 (csrc/bf16.cuh).  NCH stays the number of LANES per row (4 features each, now 8 bytes);
+// the producers move CPR = NCH / 2 16-byte chunks per row; the arithmetic is fp32, the result is rounded once on the store.
+template <bool BF16> struct PipeVec { typedef float4 type; };
+template <> struct PipeVec<true> { typedef uint2 type; };
+__device__ __forceinline__ float4 pv_load(const float4* p) { return *p; }
+__device__ __forceinline__ float4 pv_load(const uint2* p) { return unpack_bf16x4(*p); }
+__device__ __forceinline__ void pv_store(float4* p, float4 v) { *p = v; }
+__device__ __forceinline__ void pv_store(uint2* p, float4 v) { *p = pack_bf16x4(v); }
+
+template <int W, int NCH, bool HASY, bool HASZ, bool DENSE, bool BF16>
 __global__ void __launch_bounds__((DENSE ? kDenseWarps : kConsumerWarps) * 32 + kProducerWarps * 32, 2)
 spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
 {
     constexpr int CW = DENSE ? kDenseWarps : kConsumerWarps;
+    constexpr int CPR = BF16 ? NCH / 2 : NCH;                      // 16-byte chunks per row
+    typedef typename PipeVec<BF16>::type V;                        // what a lane reads / writes: its 4 features
     extern __shared__ __align__(128) unsigned char smem[];
     const int TR = a.TR, HC = a.HC, S = a.S;
-    const uint32_t xbytes = (uint32_t)(TR + HC) * NCH * 16, tbytes = (uint32_t)TR * NCH * 16;
+    const uint32_t xbytes = (uint32_t)(TR + HC) * CPR * 16, tbytes = (uint32_t)TR * CPR * 16;
     const uint32_t rbytes = (uint32_t)W * TR * 8;
     const uint32_t ybase = xbytes, zbase = ybase + (HASY ? tbytes : 0), rbase = zbase + (HASZ ? tbytes : 0);
     const uint32_t sbytes = rbase + rbytes;
@@ -121,7 +133,7 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
         if (role != 0 && lane != 0) return;
         // halo rows of the NEXT item are fetched (tile_ext, all HC slots: unused ones repeat the tile's first row) while
         // this one waits for its stage: no global-memory latency between a stage falling empty and its refill
-        const int nhalo = (PIPE_ABLATE(a) & 2) ? 0 : HC * NCH;
+        const int nhalo = (PIPE_ABLATE(a) & 2) ? 0 : HC * CPR;
         auto tile_of = [&](int it) -> int {
             const long long item = i0 + it * istep;
             return a.order == 0 ? (int)(item / a.B) : (int)(item % a.T);
@@ -130,7 +142,7 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
         if (role == 0) {
             const int32_t* ext = a.ext + (long long)tile_of(0) * HC;
 #pragma unroll
-            for (int q = 0; q < kHaloPerLane; ++q) { const int idx = lane + q * 32; grn[q] = idx < nhalo ? __ldg(ext + idx / NCH) : 0; }
+            for (int q = 0; q < kHaloPerLane; ++q) { const int idx = lane + q * 32; grn[q] = idx < nhalo ? __ldg(ext + idx / CPR) : 0; }
         }
         for (int it = 0; it < n; ++it) {
             const int s = it % S, k = it / S;
@@ -140,15 +152,15 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
             else { b = (int)(item / a.T); rt = (int)(item - (long long)b * a.T); }
             const int r0 = rt * TR, nt = min(TR, a.M - r0);
             unsigned char* st = smem + (size_t)s * sbytes;
-            const long long g0 = ((long long)b * a.M + r0) * NCH;                 // first chunk of the tile in the sample
-            const uint32_t nb = (uint32_t)nt * NCH * 16;
+            const long long g0 = ((long long)b * a.M + r0) * CPR;                 // first chunk of the tile in the sample
+            const uint32_t nb = (uint32_t)nt * CPR * 16;
             if (role == 0) {
 #pragma unroll
                 for (int q = 0; q < kHaloPerLane; ++q) gr[q] = grn[q];
                 if (it + 1 < n) {
                     const int32_t* ext = a.ext + (long long)tile_of(it + 1) * HC;
 #pragma unroll
-                    for (int q = 0; q < kHaloPerLane; ++q) { const int idx = lane + q * 32; grn[q] = idx < nhalo ? __ldg(ext + idx / NCH) : 0; }
+                    for (int q = 0; q < kHaloPerLane; ++q) { const int idx = lane + q * 32; grn[q] = idx < nhalo ? __ldg(ext + idx / CPR) : 0; }
                 }
                 if (k > 0) mbar_wait(empty + s, (uint32_t)(k - 1) & 1u);
                 if (lane == 0) {
@@ -156,12 +168,12 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
                     mbar_expect_tx(full + s, nb);
                     bulk_g2s(st, a.x + g0, nb, full + s);
                 }
-                float4* xh = reinterpret_cast<float4*>(st) + TR * NCH;
-                const float4* xb = a.x + (long long)b * a.M * NCH;
+                float4* xh = reinterpret_cast<float4*>(st) + TR * CPR;
+                const float4* xb = a.x + (long long)b * a.M * CPR;
 #pragma unroll
                 for (int q = 0; q < kHaloPerLane; ++q) {
                     const int idx = lane + q * 32;
-                    if (idx < nhalo) cp16(xh + idx, xb + (long long)gr[q] * NCH + (idx % NCH));
+                    if (idx < nhalo) cp16(xh + idx, xb + (long long)gr[q] * CPR + (idx % CPR));
                 }
                 cp_async_arrive(full + s);
             } else {
@@ -201,11 +213,11 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
             else { b = (int)(item / a.T); rt = (int)(item - (long long)b * a.T); }
             const int r0 = rt * TR, nt = min(TR, a.M - r0);
             const unsigned char* st = smem + (size_t)s * sbytes;
-            const float4* xs = reinterpret_cast<const float4*>(st);
-            const float4* ys = reinterpret_cast<const float4*>(st + ybase);
-            const float4* zs = reinterpret_cast<const float4*>(st + zbase);
+            const V* xs = reinterpret_cast<const V*>(st);
+            const V* ys = reinterpret_cast<const V*>(st + ybase);
+            const V* zs = reinterpret_cast<const V*>(st + zbase);
             const float4* wrec = reinterpret_cast<const float4*>(st + rbase);   // [18][G]
-            float4* ob = a.out + ((long long)b * a.M + r0) * NCH;
+            V* ob = reinterpret_cast<V*>(a.out) + ((long long)b * a.M + r0) * NCH;
             mbar_wait(full + s, (uint32_t)k & 1u);
             for (int g = warp * GPW + sub; g < G && 4 * g < nt; g += CW * GPW) {
                 if (PIPE_ABLATE(a) & 16) {
@@ -219,7 +231,7 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
                     const int c = (u & 1) ? (int)(cw[u >> 1] >> 16) : (int)(cw[u >> 1] & 0xffffu);
-                    v[u] = xs[c * NCH + lg];
+                    v[u] = pv_load(xs + c * NCH + lg);
                 }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -234,9 +246,9 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
                     }
                     const int row = 4 * g + (r ^ (g & 1));                       // odd groups store their rows pairwise swapped
                     float4 res = make_float4(acc.x * a.alpha, acc.y * a.alpha, acc.z * a.alpha, acc.w * a.alpha);
-                    if (HASY) { const float4 t = ys[row * NCH + lg]; res.x = fmaf(a.beta, t.x, res.x); res.y = fmaf(a.beta, t.y, res.y); res.z = fmaf(a.beta, t.z, res.z); res.w = fmaf(a.beta, t.w, res.w); }
-                    if (HASZ) { const float4 t = zs[row * NCH + lg]; res.x = fmaf(a.gamma, t.x, res.x); res.y = fmaf(a.gamma, t.y, res.y); res.z = fmaf(a.gamma, t.z, res.z); res.w = fmaf(a.gamma, t.w, res.w); }
-                    if (row < nt && !(PIPE_ABLATE(a) & 8)) ob[row * NCH + lg] = res;
+                    if (HASY) { const float4 t = pv_load(ys + row * NCH + lg); res.x = fmaf(a.beta, t.x, res.x); res.y = fmaf(a.beta, t.y, res.y); res.z = fmaf(a.beta, t.z, res.z); res.w = fmaf(a.beta, t.w, res.w); }
+                    if (HASZ) { const float4 t = pv_load(zs + row * NCH + lg); res.x = fmaf(a.gamma, t.x, res.x); res.y = fmaf(a.gamma, t.y, res.y); res.z = fmaf(a.gamma, t.z, res.z); res.w = fmaf(a.gamma, t.w, res.w); }
+                    if (row < nt && !(PIPE_ABLATE(a) & 8)) pv_store(ob + row * NCH + lg, res);
                 }
             }
             __syncwarp();
@@ -257,11 +269,11 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
         else { b = (int)(item / a.T); rt = (int)(item - (long long)b * a.T); }
         const int r0 = rt * TR, nt = min(TR, a.M - r0);
         const unsigned char* st = smem + (size_t)s * sbytes;
-        const float4* xs = reinterpret_cast<const float4*>(st);
-        const float4* ys = reinterpret_cast<const float4*>(st + ybase);
-        const float4* zs = reinterpret_cast<const float4*>(st + zbase);
+        const V* xs = reinterpret_cast<const V*>(st);
+        const V* ys = reinterpret_cast<const V*>(st + ybase);
+        const V* zs = reinterpret_cast<const V*>(st + zbase);
         const int2* srec = reinterpret_cast<const int2*>(st + rbase);
-        float4* ob = a.out + ((long long)b * a.M + r0) * NCH;
+        V* ob = reinterpret_cast<V*>(a.out) + ((long long)b * a.M + r0) * NCH;
         mbar_wait(full + s, (uint32_t)k & 1u);
         const int rend = min(nt, (warp + 1) * rpw);
         for (int r = warp * rpw + sub; r < rend; r += RPP) {
@@ -272,13 +284,13 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
                 if ((PIPE_ABLATE(a) & 1) && j > 0) break;
                 const int2 rc = srec[j * TR + r];
                 const float w = __int_as_float(rc.y);
-                const float4 v = xs[rc.x * NCH + lg];
+                const float4 v = pv_load(xs + rc.x * NCH + lg);
                 acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
             }
             float4 res = make_float4(acc.x * a.alpha, acc.y * a.alpha, acc.z * a.alpha, acc.w * a.alpha);
-            if (HASY) { const float4 t = ys[r * NCH + lg]; res.x = fmaf(a.beta, t.x, res.x); res.y = fmaf(a.beta, t.y, res.y); res.z = fmaf(a.beta, t.z, res.z); res.w = fmaf(a.beta, t.w, res.w); }
-            if (HASZ) { const float4 t = zs[r * NCH + lg]; res.x = fmaf(a.gamma, t.x, res.x); res.y = fmaf(a.gamma, t.y, res.y); res.z = fmaf(a.gamma, t.z, res.z); res.w = fmaf(a.gamma, t.w, res.w); }
-            if (!(PIPE_ABLATE(a) & 8)) ob[r * NCH + lg] = res;
+            if (HASY) { const float4 t = pv_load(ys + r * NCH + lg); res.x = fmaf(a.beta, t.x, res.x); res.y = fmaf(a.beta, t.y, res.y); res.z = fmaf(a.beta, t.z, res.z); res.w = fmaf(a.beta, t.w, res.w); }
+            if (HASZ) { const float4 t = pv_load(zs + r * NCH + lg); res.x = fmaf(a.gamma, t.x, res.x); res.y = fmaf(a.gamma, t.y, res.y); res.z = fmaf(a.gamma, t.z, res.z); res.w = fmaf(a.gamma, t.w, res.w); }
+            if (!(PIPE_ABLATE(a) & 8)) pv_store(ob + r * NCH + lg, res);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
@@ -290,15 +302,15 @@ static size_t pipe_smem(int W, int TR, int HC, int nch, int extra, int S) {
     return (size_t)S * stage + 2 * S * 8 + 64;
 }
 
-template <int W, int NCH, bool DENSE>
+template <int W, int NCH, bool DENSE, bool BF16>
 static int pipe_launch_t(const PipeArgs& a, int grid, size_t smem, cudaStream_t s)
 {
     constexpr int threads = ((DENSE ? kDenseWarps : kConsumerWarps) + kProducerWarps) * 32;
 #define DSB_PIPE(YY, ZZ) do { \
         static bool cfg = false; \
-        if (!cfg) { cudaError_t e = cudaFuncSetAttribute(spmm_pipe_kernel<W, NCH, YY, ZZ, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024); \
+        if (!cfg) { cudaError_t e = cudaFuncSetAttribute(spmm_pipe_kernel<W, NCH, YY, ZZ, DENSE, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024); \
                     if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; } cfg = true; } \
-        spmm_pipe_kernel<W, NCH, YY, ZZ, DENSE><<<grid, threads, smem, s>>>(a); } while (0)
+        spmm_pipe_kernel<W, NCH, YY, ZZ, DENSE, BF16><<<grid, threads, smem, s>>>(a); } while (0)
     if (a.y && a.z) DSB_PIPE(true, true);
     else if (a.y) DSB_PIPE(true, false);
     else if (a.z) DSB_PIPE(false, true);
@@ -311,10 +323,11 @@ static int pipe_launch_t(const PipeArgs& a, int grid, size_t smem, cudaStream_t 
 
 using namespace dsb200;
 
-extern "C" int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, const int32_t* tile_nh,
-                                int ntiles, int TR, int HC, int width, int dense, int B, int M, int F,
-                                const float* x, const float* y, const float* z, float* out,
-                                float alpha, float beta, float gamma, void* stream)
+template <bool BF16>
+static int spmm_pipe_entry(const void* tile_recs, const int32_t* tile_ext, const int32_t* tile_nh,
+                           int ntiles, int TR, int HC, int width, int dense, int B, int M, int F,
+                           const void* x, const void* y, const void* z, void* out,
+                           float alpha, float beta, float gamma, void* stream)
 {
     DSB_REQUIRE(B > 0 && M > 0 && F > 0, "spmm_pipe: empty matrix");
     DSB_REQUIRE(tile_recs && tile_ext && tile_nh && x && out, "spmm_pipe: null pointer");
@@ -323,16 +336,17 @@ extern "C" int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, 
     DSB_REQUIRE(!dense || width == 9, "spmm_pipe: dense-group records are 72 bytes per row (width 9 layout)");
     DSB_REQUIRE(F == 16 || F == 32 || F == 64, "spmm_pipe: F must be 16, 32 or 64");
     DSB_REQUIRE(TR > 0 && HC >= 0 && ntiles == (M + TR - 1) / TR, "spmm_pipe: tile plan does not match M");
-    DSB_REQUIRE(TR % (8 * (128 / F)) == 0 && HC * (F / 4) <= 32 * kHaloPerLane && (width * TR * 8) % 16 == 0, "spmm_pipe: unsupported tile shape");
+    const int nch = F / 4, cpr = BF16 ? nch / 2 : nch;          // lanes per row, 16-byte chunks per row
+    DSB_REQUIRE(TR % (8 * (128 / F)) == 0 && HC * cpr <= 32 * kHaloPerLane && (width * TR * 8) % 16 == 0, "spmm_pipe: unsupported tile shape");
     if (beta == 0.f) y = nullptr;
     if (gamma == 0.f) z = nullptr;
     const uintptr_t align = (uintptr_t)x | (uintptr_t)out | (uintptr_t)y | (uintptr_t)z;
     DSB_REQUIRE((align & 15) == 0, "spmm_pipe: pointers must be 16-byte aligned");
-    const int nch = F / 4, extra = (y ? 1 : 0) + (z ? 1 : 0);
+    const int extra = (y ? 1 : 0) + (z ? 1 : 0);
     int S = 4;
     { const int e = DSB_ENV_INT("DSB200_PIPE_STAGES", 0); if (e >= 2 && e <= 4) S = e; }
-    while (S > 2 && pipe_smem(width, TR, HC, nch, extra, S) > 113 * 1024) --S;
-    const size_t smem = pipe_smem(width, TR, HC, nch, extra, S);
+    while (S > 2 && pipe_smem(width, TR, HC, cpr, extra, S) > 113 * 1024) --S;
+    const size_t smem = pipe_smem(width, TR, HC, cpr, extra, S);
     DSB_REQUIRE(smem <= 113 * 1024, "spmm_pipe: tile does not fit in shared memory");
     PipeArgs a;
     a.rec = (const int2*)tile_recs; a.ext = tile_ext; a.nh = tile_nh;
@@ -348,16 +362,33 @@ extern "C" int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, 
     const int grid = (int)(nitems < cap ? nitems : cap);
     cudaStream_t s = (cudaStream_t)stream;
     if (dense) {                                                  // the records do not depend on the ELL width (W = 9 is a dummy)
-        if (nch == 4) return pipe_launch_t<9, 4, true>(a, grid, smem, s);
-        if (nch == 8) return pipe_launch_t<9, 8, true>(a, grid, smem, s);
-        return pipe_launch_t<9, 16, true>(a, grid, smem, s);
+        if (nch == 4) return pipe_launch_t<9, 4, true, BF16>(a, grid, smem, s);
+        if (nch == 8) return pipe_launch_t<9, 8, true, BF16>(a, grid, smem, s);
+        return pipe_launch_t<9, 16, true, BF16>(a, grid, smem, s);
     }
     if (width == 9) {
-        if (nch == 4) return pipe_launch_t<9, 4, false>(a, grid, smem, s);
-        if (nch == 8) return pipe_launch_t<9, 8, false>(a, grid, smem, s);
-        return pipe_launch_t<9, 16, false>(a, grid, smem, s);
+        if (nch == 4) return pipe_launch_t<9, 4, false, BF16>(a, grid, smem, s);
+        if (nch == 8) return pipe_launch_t<9, 8, false, BF16>(a, grid, smem, s);
+        return pipe_launch_t<9, 16, false, BF16>(a, grid, smem, s);
     }
-    if (nch == 4) return pipe_launch_t<7, 4, false>(a, grid, smem, s);
-    if (nch == 8) return pipe_launch_t<7, 8, false>(a, grid, smem, s);
-    return pipe_launch_t<7, 16, false>(a, grid, smem, s);
+    if (nch == 4) return pipe_launch_t<7, 4, false, BF16>(a, grid, smem, s);
+    if (nch == 8) return pipe_launch_t<7, 8, false, BF16>(a, grid, smem, s);
+    return pipe_launch_t<7, 16, false, BF16>(a, grid, smem, s);
+}
+
+extern "C" int dsb200_spmm_pipe(const void* tile_recs, const int32_t* tile_ext, const int32_t* tile_nh,
+                                int ntiles, int TR, int HC, int width, int dense, int B, int M, int F,
+                                const float* x, const float* y, const float* z, float* out,
+                                float alpha, float beta, float gamma, void* stream)
+{
+    return spmm_pipe_entry<false>(tile_recs, tile_ext, tile_nh, ntiles, TR, HC, width, dense, B, M, F, x, y, z, out, alpha, beta, gamma, stream);
+}
+
+// the same operator on bfloat16 tensors (BF16 mode); the tile plan is the one of rows of 2 F bytes (graph.pipe_plan(.., esize=2))
+extern "C" int dsb200_spmm_pipe_bf16(const void* tile_recs, const int32_t* tile_ext, const int32_t* tile_nh,
+                                     int ntiles, int TR, int HC, int width, int dense, int B, int M, int F,
+                                     const void* x, const void* y, const void* z, void* out,
+                                     float alpha, float beta, float gamma, void* stream)
+{
+    return spmm_pipe_entry<true>(tile_recs, tile_ext, tile_nh, ntiles, TR, HC, width, dense, B, M, F, x, y, z, out, alpha, beta, gamma, stream);
 }

@@ -119,11 +119,12 @@ class PipePlan(object):
         out[:, 16:] = np.ascontiguousarray(c16.transpose(0, 2, 1, 3)).view(np.int32).reshape(T, 2, G, 4)
         return np.ascontiguousarray(out)
 
-    def fits(self, F, extra=2):
+    def fits(self, F, extra=2, esize=4):
         """Two stages of (x tile + halo, `extra` more tiles, records) fit in the CTA's shared memory, and the tile
-        shape is one the kernel's warp layout covers."""
-        stage = (self.TR + self.HC) * 4 * F + self.TR * 4 * F * extra + self.width * self.TR * 8
-        return (2 * stage + 128 <= PIPE_SMEM and self.TR % (8 * (128 // F)) == 0 and self.HC * (F // 4) <= 512)
+        shape is one the kernel's warp layout covers.  `esize`: bytes per element (2 in the BF16 mode)."""
+        rb = esize * F
+        stage = (self.TR + self.HC) * rb + self.TR * rb * extra + self.width * self.TR * 8
+        return (2 * stage + 128 <= PIPE_SMEM and self.TR % (8 * (128 // F)) == 0 and self.HC * (rb // 16) <= 512)
 
     def args(self, dense=False):
         if dense and self.dense is not None:
@@ -306,11 +307,11 @@ class DeviceGraph(object):
                 torch.from_numpy(A.indices.astype(np.int32)).to(self.device),
                 torch.from_numpy(A.data.astype(np.float32)).to(self.device), 0)
 
-    def pipe_plan(self, which, F):
-        """PipePlan of L ('fwd') or L^T ('bwd') for F features per row (cached per tile size), or None."""
+    def pipe_plan(self, which, F, esize=4):
+        """PipePlan of L ('fwd') or L^T ('bwd') for F features of `esize` bytes per row (cached per tile size), or None."""
         if not self.is_ell or F not in (16, 32, 64):
             return None
-        TR = int(os.environ.get('DSB200_PIPE_TILE_BYTES', PIPE_TILE_BYTES)) // (4 * F)
+        TR = int(os.environ.get('DSB200_PIPE_TILE_BYTES', PIPE_TILE_BYTES)) // (esize * F)
         if which == 'bwd' and self.bwd is self.fwd:
             which = 'fwd'
         key = (which, TR)
@@ -320,7 +321,7 @@ class DeviceGraph(object):
             plan = PipePlan(col.cpu().numpy(), val.cpu().numpy(), self.device, TR)
             cache[key] = plan if plan.valid else None
         plan = cache[key]
-        return plan if plan is not None and plan.fits(F) else None
+        return plan if plan is not None and plan.fits(F, esize=esize) else None
 
     def stencil_plan(self, which, S):
         """StencilPlan of L ('fwd') or L^T ('bwd') for a recurrence of S steps (cached), or None."""

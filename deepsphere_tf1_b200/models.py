@@ -121,6 +121,9 @@ class _ChebStage(object):
             raise NotImplementedError('dropFilt < 1 is not available in the vertex-sharded mode')
         self.small = bool(first and self.post and model.fused_small and self.sg is None and self.drop >= 1
                           and ops.smallconv_supported(Fin, K, Fout))
+        # BF16 mode: this layer reads, keeps and writes bfloat16 activations (the fused input layer and the vertex-sharded
+        # layers stay fp32; tensors are converted where the two kinds of layer meet)
+        self.bf16 = bool(getattr(model, 'act_dtype', torch.float32) == torch.bfloat16 and not self.small and self.sg is None)
         self.saved = None
 
     def forward(self, x, training, save):
@@ -131,6 +134,7 @@ class _ChebStage(object):
             raise ValueError('{}: input [{}, {}] does not fit the Laplacian ({} vertices) / weights ({} features)'
                              .format(self.scope, M, Fin, Mg, self.Fin))
         W = m._P.views[self.scope + '/weights']
+        x = ops.to_bf16(x) if self.bf16 else ops.to_f32(x)
         if self.small:
             return self._forward_small(x, W, training, save)
         if self.sg is not None and self.K > 1:
@@ -167,7 +171,7 @@ class _ChebStage(object):
             lean = self.post and self.bn and training and ops.bn_relu_pool_sums_supported(self.Fout, self.p, self.pool, self.act)
             self.saved = (x, basis, y, mean, rstd, count, training, out if lean else None, umask, W if umask is not None else None)
         if self.keep is not None and self.keep != out.shape[1]:
-            out = ops.vertex_resize(out, self.keep, 0.0)                   # x[:, :p, :]  (models.py:1138,1157)
+            out = ops.vertex_resize(ops.to_f32(out), self.keep, 0.0)       # x[:, :p, :]  (models.py:1138,1157)
         return out
 
     def _forward_small(self, x, W, training, save):
@@ -204,6 +208,7 @@ class _ChebStage(object):
         m = self.m
         x, basis, gram, mean, rstd, count, training, shape, out, arg = self.saved
         self.saved = None
+        dout = ops.to_f32(dout)
         B, M, Fin = shape
         if self.keep is not None and dout.shape[1] != M // self.p:
             dout = ops.vertex_resize(dout, M // self.p, 0.0)
@@ -274,6 +279,7 @@ class _ChebStage(object):
         m, sg, g, K = self.m, self.sg, self.graph, self.K
         E, y, mean, rstd, count, training, out = self.saved
         self.saved = None
+        dout = ops.to_f32(dout)
         Ml, Fin = sg.Ml, self.Fin
         yo = y[:, :Ml]
         if self.post:
@@ -321,7 +327,8 @@ class _ChebStage(object):
         self.saved = None
         B, M, Fin = x.shape
         if self.keep is not None and dout.shape[1] != M // self.p:
-            dout = ops.vertex_resize(dout, M // self.p, 0.0)               # adjoint of the slice
+            dout = ops.vertex_resize(ops.to_f32(dout), M // self.p, 0.0)   # adjoint of the slice
+        dout = ops.to_bf16(dout) if self.bf16 else ops.to_f32(dout)
         dy = dout
         if self.post:
             b = m._P.views[self.scope + '/bias'] if self.has_bias else None
@@ -839,8 +846,15 @@ class cgcnn(base_model):
         self.weighted = bool(weighted)
         if self.sampling == 'equiangular':
             raise NotImplementedError('equiangular sampling is outside the hot path')
-        if np.dtype(dtype) != np.float32:
-            raise NotImplementedError('only float32 Laplacians are supported')
+        # dtype: upstream it only casts the Laplacians (models.py:1047).  Here 'bfloat16' selects the BF16 mode of the ChebConv
+        # layers (activations stored as bfloat16, fp32 arithmetic and accumulation; include/dsb200.h, "BF16 mode"); the
+        # Laplacians, the weights and the statistics stay float32 either way.
+        if (isinstance(dtype, str) and dtype in ('bfloat16', 'bf16')) or dtype is torch.bfloat16:
+            self.act_dtype = torch.bfloat16
+        elif np.dtype(dtype) == np.float32:
+            self.act_dtype = torch.float32
+        else:
+            raise NotImplementedError("dtype must be float32 or 'bfloat16'")
         if not torch.cuda.is_available():
             raise RuntimeError('deepsphere_tf1_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
 
@@ -1139,6 +1153,7 @@ class cgcnn(base_model):
             x = st.forward(x, training, save)
             if st.post:
                 skips.append(x)
+        x = ops.to_f32(x)                                  # BF16 mode: everything outside the ChebConv layers is fp32
         descriptor = x
         B = x.shape[0]
         self._stat_saved = None
@@ -1166,6 +1181,7 @@ class cgcnn(base_model):
             for up, de, j in self._decoder:
                 if up is not None:
                     (kind, arg), stage = up
+                    x = ops.to_f32(x)
                     if kind == 'pad':
                         xin = ops.vertex_resize(x, arg, 1.0)                 # tf.pad(..., constant_values=1)
                     else:
@@ -1175,9 +1191,9 @@ class cgcnn(base_model):
                                          'for segmentation task')
                     stage.prev_M = x.shape[1]
                     x = stage.forward(xin, training, save)
-                    x = ops.concat_f(x, skips[j])
+                    x = ops.concat_f(ops.to_f32(x), ops.to_f32(skips[j]))
                 x = de.forward(x, training, save)
-            x = self._outconv.forward(x, training, save)
+            x = ops.to_f32(self._outconv.forward(x, training, save))
         return x, descriptor
 
     def _backward(self, dlogits):
@@ -1192,17 +1208,18 @@ class cgcnn(base_model):
                 if up is not None:
                     (kind, arg), stage = up
                     Fa = stage.Fout
-                    da, db = ops.split_f(d, Fa)
+                    da, db = ops.split_f(ops.to_f32(d), Fa)
                     if j in skip_grads:
                         ops.axpy(db, skip_grads[j], 1.0)
                     else:
                         skip_grads[j] = db
-                    dxin = stage.backward(da)
+                    dxin = ops.to_f32(stage.backward(da))
                     if kind == 'pad':
                         Mprev = stage.prev_M
                         d = ops.vertex_resize(dxin, Mprev, 0.0) if dxin.shape[1] != Mprev else dxin
                     else:
                         d = ops.unpool_bwd(dxin, arg, UNPOOL_REPEAT if kind == 'repeat' else UNPOOL_ZEROFILL)
+        d = ops.to_f32(d)
         for fc in reversed(self._fc):
             d = fc.backward(d)
         if self.statistics == 'histogram':
@@ -1217,6 +1234,7 @@ class cgcnn(base_model):
         for k in range(n_enc - 1, -1, -1):
             st = self._encoder[k]
             if st.post and (k + 1) in skip_grads:
+                d = ops.to_f32(d)
                 ops.axpy(skip_grads.pop(k + 1), d, 1.0)
             d = st.backward(d, need_dx=k > 0)
         return d

@@ -12,8 +12,36 @@ from ._consts import ACT, POOL, STAT, UNPOOL_REPEAT, UNPOOL_ZEROFILL  # noqa: F4
 from ._lib import call
 
 
-def _new(shape, like, dtype=torch.float32):
-    return torch.empty(shape, dtype=dtype, device=like.device)
+BF16 = torch.bfloat16
+
+
+def _new(shape, like, dtype=None):
+    return torch.empty(shape, dtype=like.dtype if dtype is None else dtype, device=like.device)
+
+
+# ---- BF16 mode (cgcnn(..., dtype='bfloat16'); include/dsb200.h, "BF16 mode").  The ChebConv operators below take bfloat16
+# activations natively where a bf16 kernel covers the shape; everywhere else the tensor is converted with these two kernels
+# and the fp32 operator runs (models.py casts at the boundaries of the ChebConv chain, so the other operators only see fp32).
+def to_f32(x):
+    if x is None or x.dtype == torch.float32:
+        return x
+    out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    call('cast_bf16_to_f32', x, out, x.numel())
+    return out
+
+
+def to_bf16(x, out=None):
+    if x is None or (x.dtype == BF16 and out is None):
+        return x
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    call('cast_f32_to_bf16', x, out, x.numel())
+    return out
+
+
+def _lib_int(name, *args):
+    from ._lib import LIB
+    return int(getattr(LIB.load(), 'dsb200_' + name)(*args))
 
 
 def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, transpose=False, rows=None):
@@ -26,9 +54,18 @@ def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, tra
             raise ValueError('rows= needs a single sample')
         M = rows
     rowptr, col, val, width = graph.bwd if transpose else graph.fwd
+    which = 'bwd' if transpose else 'fwd'
+    if x.dtype == BF16:
+        pp = _pipe(graph, which, B, M, F, esize=2, min_items=1) if rows is None else None
+        if pp is None:                                   # no bf16 gather kernels: fp32 operator between two casts
+            res = spmm(graph, to_f32(x), to_f32(y), to_f32(z), None, alpha, beta, gamma, transpose, rows)
+            return to_bf16(res, out)
+        if out is None:
+            out = _new((B, M, F), x)
+        call('spmm_pipe_bf16', *pp.args(USE_DENSE_GROUPS), B, M, F, x, y, z, out, alpha, beta, gamma)
+        return out
     if out is None:
         out = _new((B, M, F), x)
-    which = 'bwd' if transpose else 'fwd'
     pp = _pipe(graph, which, B, M, F) if rows is None else None
     if pp is not None:
         call('spmm_pipe', *pp.args(USE_DENSE_GROUPS), B, M, F, x, y, z, out, alpha, beta, gamma)
@@ -56,11 +93,11 @@ def set_pipe(on, dense=None):
         USE_DENSE_GROUPS = bool(dense)
 
 
-def _pipe(graph, which, B, M, F):
+def _pipe(graph, which, B, M, F, esize=4, min_items=None):
     if not USE_PIPE or not hasattr(graph, 'pipe_plan'):
         return None
-    plan = graph.pipe_plan(which, F)
-    if plan is None or plan.T * B < PIPE_MIN_ITEMS:
+    plan = graph.pipe_plan(which, F, esize)
+    if plan is None or plan.T * B < (PIPE_MIN_ITEMS if min_items is None else min_items):
         return None
     return plan
 
@@ -113,6 +150,16 @@ def cheb_basis(graph, x, K, monomial=False):
     if K == 1:
         return None
     B, M, F = x.shape
+    if x.dtype == BF16:
+        if _pipe(graph, 'fwd', B, M, F, esize=2, min_items=1) is None:
+            return to_bf16(cheb_basis(graph, to_f32(x), K, monomial))
+        basis = _new((K - 1, B, M, F), x)
+        for k in range(1, K):
+            if monomial or k == 1:
+                spmm(graph, x if k == 1 else basis[k - 2], out=basis[k - 1])
+            else:
+                spmm(graph, basis[k - 2], x if k == 2 else basis[k - 3], None, out=basis[k - 1], alpha=2.0, beta=-1.0)
+        return basis
     basis = _new((K - 1, B, M, F), x)
     tp = _tile(graph, 'fwd', K, B, F)
     if tp is not None:
@@ -140,6 +187,14 @@ def cheb_basis_bwd(graph, G, monomial=False):
     """Adjoint of the recurrence: G [K, B, M, F] -> dLoss/dx [B, M, F] (G is overwritten on the gather path).
     `monomial`: adjoint of X_k = L X_(k-1), i.e. A_k = G_k + L^T A_(k+1)."""
     K, B, M, F = G.shape
+    if G.dtype == BF16:
+        if K >= 2 and _pipe(graph, 'bwd', B, M, F, esize=2, min_items=1) is None:
+            return to_bf16(cheb_basis_bwd(graph, to_f32(G), monomial))
+        for k in range(K - 2, -1, -1):
+            a2 = G[k + 2] if (k + 2 <= K - 1 and not monomial) else None
+            spmm(graph, G[k + 1], G[k], a2, out=G[k], alpha=2.0 if (k >= 1 and not monomial) else 1.0, beta=1.0,
+                 gamma=-1.0 if a2 is not None else 0.0, transpose=True)
+        return G[0]
     tp = _tile(graph, 'bwd', K, B, F)
     if tp is not None:
         dx = _new((B, M, F), G)
@@ -173,9 +228,19 @@ def _workspace(Fin, K, Fout, device):
     return torch.empty(n, dtype=torch.uint8, device=device)
 
 
+def _workspace_bf16(R, Fin, K, Fout, device):
+    return torch.empty(_lib_int('contract_workspace_bytes_bf16', R, Fin, K, Fout), dtype=torch.uint8, device=device)
+
+
 def contract_fwd(x, basis, W, K, Fout, bn_sums=None):
     """Y = [X_0 .. X_{K-1}] . W  (tf.matmul, models.py:1062-1078), optional batch-norm sums."""
     B, M, Fin = x.shape
+    if x.dtype == BF16:
+        if not _lib_int('contract_bf16_supported', 0, B * M, Fin, K, Fout):
+            return to_bf16(contract_fwd(to_f32(x), to_f32(basis), W, K, Fout, bn_sums))
+        y = _new((B, M, Fout), x)
+        call('cheb_contract_fwd_bf16', x, basis, W, y, B * M, Fin, K, Fout, bn_sums, _workspace_bf16(B * M, Fin, K, Fout, x.device))
+        return y
     y = _new((B, M, Fout), x)
     call('cheb_contract_fwd', x, basis, W, y, B * M, Fin, K, Fout, bn_sums, _workspace(Fin, K, Fout, x.device))
     return y
@@ -183,6 +248,12 @@ def contract_fwd(x, basis, W, K, Fout, bn_sums=None):
 
 def contract_bwd_data(dy, W, K, Fin):
     B, M, Fout = dy.shape
+    if dy.dtype == BF16:
+        if not _lib_int('contract_bf16_supported', 1, B * M, Fin, K, Fout):
+            return to_bf16(contract_bwd_data(to_f32(dy), W, K, Fin))
+        G = _new((K, B, M, Fin), dy)
+        call('cheb_contract_bwd_data_bf16', dy, W, G, B * M, Fin, K, Fout, _workspace_bf16(B * M, Fin, K, Fout, dy.device))
+        return G
     G = _new((K, B, M, Fin), dy)
     call('cheb_contract_bwd_data', dy, W, G, B * M, Fin, K, Fout, _workspace(Fin, K, Fout, dy.device))
     return G
@@ -190,7 +261,16 @@ def contract_bwd_data(dy, W, K, Fin):
 
 def contract_bwd_weight(x, basis, dy, dW, K):
     B, M, Fin = x.shape
+    if x.dtype == BF16:
+        if _lib_int('contract_bf16_supported', 2, B * M, Fin, K, dy.shape[2]):
+            call('cheb_contract_bwd_weight_bf16', x, basis, dy, dW, B * M, Fin, K, dy.shape[2])
+            return
+        x, basis, dy = to_f32(x), to_f32(basis), to_f32(dy)
     call('cheb_contract_bwd_weight', x, basis, dy, dW, B * M, Fin, K, dy.shape[2])
+
+
+def _sfx(t):
+    return '_bf16' if t.dtype == BF16 else ''
 
 
 def bn_finalize(sums, count, F, mean, rstd, moving_mean=None, moving_var=None, eps=1e-5, momentum=0.9):
@@ -204,7 +284,7 @@ def bn_from_moving(moving_mean, moving_var, mean, rstd, eps=1e-5):
 def bn_act_pool_fwd(y, mean, rstd, bias, p, pool, act):
     B, M, F = y.shape
     out = _new((B, M // p, F), y)
-    call('bn_act_pool_fwd', y, mean, rstd, bias, out, B, M, F, p, POOL[pool], ACT[act])
+    call('bn_act_pool_fwd' + _sfx(y), y, mean, rstd, bias, out, B, M, F, p, POOL[pool], ACT[act])
     return out
 
 
@@ -215,7 +295,7 @@ def bn_act_pool_bwd(y, mean, rstd, bias, dout, p, pool, act, want_gz=True, out=N
     gz = (_new((B, M, F), y) if out is None else out) if want_gz else None
     if sums is None:
         sums = torch.zeros(2 * F, dtype=torch.float64, device=y.device)
-    call('bn_act_pool_bwd', y, mean, rstd, bias, dout, gz, sums, B, M, F, p, POOL[pool], ACT[act])
+    call('bn_act_pool_bwd' + _sfx(y), y, mean, rstd, bias, dout, gz, sums, B, M, F, p, POOL[pool], ACT[act])
     return gz, sums
 
 
@@ -228,7 +308,7 @@ def bn_relu_pool_sums(out, dout, bias, sums=None):
     F = out.shape[-1]
     if sums is None:
         sums = torch.zeros(2 * F, dtype=torch.float64, device=out.device)
-    call('bn_relu_pool_sums', out, dout, bias, sums, out.numel() // F, F)
+    call('bn_relu_pool_sums' + _sfx(out), out, dout, bias, sums, out.numel() // F, F)
     return sums
 
 
@@ -244,7 +324,7 @@ def bn_act_pool_bwd_dy(y, mean, rstd, bias, dout, sums, count, p, pool, act, out
     """Pass 2 of the batch-norm backward: dy from y, dout and the (all-reduced) sums."""
     B, M, F = y.shape
     dy = _new((B, M, F), y) if out is None else out
-    call('bn_act_pool_bwd_dy', y, mean, rstd, bias, dout, sums, float(count), dy, B, M, F, p, POOL[pool], ACT[act])
+    call('bn_act_pool_bwd_dy' + _sfx(y), y, mean, rstd, bias, dout, sums, float(count), dy, B, M, F, p, POOL[pool], ACT[act])
     return dy
 
 

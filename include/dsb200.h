@@ -349,6 +349,43 @@ int dsb200_peer_comm_create(void** comm_out, void* handle_out64);
 int dsb200_peer_comm_open(const void* handle64, void** comm_out);
 int dsb200_peer_allreduce_f64(void* const* comms, int rank, int world, double* data, int n, void* stream);
 
+/* ---- BF16 mode (north star: "FP32 ... (1e-2 in BF16)"; cgcnn(..., dtype='bfloat16')).  Activations -- layer inputs and
+ * outputs, the Chebyshev planes, Y, and every activation gradient -- are STORED as bfloat16 (void* = __nv_bfloat16*); all
+ * arithmetic and accumulation is fp32, one rounding (to nearest even) per stored element.  Weights, batch-norm statistics
+ * and weight gradients stay fp32.  Same operators and reference call sites as the fp32 entry points of the same name. */
+/* K1 (models.py:1056-1061), csrc/sparse_pipe.cu; the tile plan is the one for rows of 2 F bytes (TR = 8192 / (2 F)) */
+int dsb200_spmm_pipe_bf16(const void* tile_recs, const int32_t* tile_ext, const int32_t* tile_nh,
+                          int ntiles, int TR, int HC, int width, int dense, int B, int M, int F,
+                          const void* x, const void* y, const void* z, void* out,
+                          float alpha, float beta, float gamma, void* stream);
+/* K2 (models.py:1062-1078 and its autodiff), csrc/contract_bf16.cu: tcgen05.mma kind::f16 (BF16 x BF16 -> FP32 in TMEM) fed by
+ * TMA tensor copies, no operand split.  Shapes: dsb200_contract_bf16_supported(dir = 0 forward / 1 data gradient / 2 weight
+ * gradient, ...) != 0; other shapes: cast to fp32 and use the fp32 entry points.  workspace: device scratch of
+ * dsb200_contract_workspace_bytes_bf16(R, Fin, K, Fout) bytes (the packed bf16 weight image), required.
+ * bn_sums: statistics of the STORED (rounded) Y. */
+int dsb200_contract_bf16_supported(int dir, long long R, int Fin, int K, int Fout);
+long long dsb200_contract_workspace_bytes_bf16(long long R, int Fin, int K, int Fout);
+int dsb200_cheb_contract_fwd_bf16(const void* x0, const void* xk, const float* W, void* Y,
+                                  long long R, int Fin, int K, int Fout, double* bn_sums, void* workspace, void* stream);
+int dsb200_cheb_contract_bwd_data_bf16(const void* dY, const float* W, void* G,
+                                       long long R, int Fin, int K, int Fout, void* workspace, void* stream);
+int dsb200_cheb_contract_bwd_weight_bf16(const void* x0, const void* xk, const void* dY, float* dW,
+                                         long long R, int Fin, int K, int Fout, void* stream);
+/* K3 / K4 (models.py:1194-1203, 1122-1163, 1235-1243): the batch-norm / bias / activation / pooling chain on bf16 tensors */
+int dsb200_bn_act_pool_fwd_bf16(const void* y, const float* mean, const float* rstd, const float* bias,
+                                void* out, int B, int M, int F, int p, int pool, int act, void* stream);
+int dsb200_bn_act_pool_bwd_bf16(const void* y, const float* mean, const float* rstd, const float* bias,
+                                const void* dout, void* gz, double* sums_bwd,
+                                int B, int M, int F, int p, int pool, int act, void* stream);
+int dsb200_bn_act_pool_bwd_dy_bf16(const void* y, const float* mean, const float* rstd, const float* bias,
+                                   const void* dout, const double* sums_bwd, double count, void* dy,
+                                   int B, int M, int F, int p, int pool, int act, void* stream);
+int dsb200_bn_relu_pool_sums_bf16(const void* out, const void* dout, const float* bias, double* sums_bwd,
+                                  long long Rout, int F, void* stream);
+/* storage conversion (operators without a bf16 kernel run in fp32 between two of these) */
+int dsb200_cast_f32_to_bf16(const float* x, void* out, long long n, void* stream);
+int dsb200_cast_bf16_to_f32(const void* x, float* out, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
