@@ -151,7 +151,7 @@ def run_reference(args):
     }))
 
 
-def spmm_roofline(model, B, iters=60, nsets=6):
+def spmm_roofline(model, B, iters=60, nsets=6, bf16=False):
     """The ChebConv recurrence step X_k = 2 L X_{k-1} - X_{k-2} at the layer with the largest
     feature slab (layer 2: M=65,536, Fin=16), timed alone with CUDA events on the launching stream:
     `iters` launches back to back over `nsets` rotating operand sets (6 x 201 MB, ten times the 126 MB
@@ -164,10 +164,11 @@ def spmm_roofline(model, B, iters=60, nsets=6):
     g = model._graphs[1]
     M, Fin = g.M, F[0]
     dev = model.device
-    xs = [torch.randn(B, M, Fin, device=dev) for _ in range(nsets)]
-    ys = [torch.randn(B, M, Fin, device=dev) for _ in range(nsets)]
-    outs = [torch.empty(B, M, Fin, device=dev) for _ in range(nsets)]
-    bytes_alg = 3 * B * M * Fin * 4 + 8 * g.nnz
+    dt, es = (torch.bfloat16, 2) if bf16 else (torch.float32, 4)
+    xs = [torch.randn(B, M, Fin, device=dev).to(dt) for _ in range(nsets)]
+    ys = [torch.randn(B, M, Fin, device=dev).to(dt) for _ in range(nsets)]
+    outs = [torch.empty(B, M, Fin, device=dev, dtype=dt) for _ in range(nsets)]
+    bytes_alg = 3 * B * M * Fin * es + 8 * g.nnz
     for i in range(nsets):
         ops.spmm(g, xs[i], ys[i], None, out=outs[i], alpha=2.0, beta=-1.0)
     torch.cuda.synchronize()
@@ -178,6 +179,14 @@ def spmm_roofline(model, B, iters=60, nsets=6):
     e1.record()
     e1.synchronize()
     t = e0.elapsed_time(e1) * 1e-3 / iters
+    if bf16:
+        peak, how = peaks()
+        ach = bytes_alg / t / 1e9
+        return {'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak, 'traffic': None,
+                'kernel': 'spmm_pipe_kernel<9,4,true,false,true,BF16> (ChebConv recurrence step, layer 2: B={} M={} Fin={}, bfloat16)'.format(B, M, Fin),
+                'algorithmic_bytes_per_launch': bytes_alg, 'avg_launch_us': t * 1e6, 'peak_source': how,
+                'timing': '{} launches back to back over {} rotating operand sets, CUDA events (the {} MB of the sets exceed L2 '
+                          'about five times)'.format(iters, nsets, nsets * 3 * B * M * Fin * es // 1000000)}
     # for comparison, the round's earlier method: single launches, each after a 512 MB buffer has been rewritten
     flush = torch.empty(512 * 1024 * 1024 // 4, device=dev)
     singles = []
@@ -206,7 +215,7 @@ def spmm_roofline(model, B, iters=60, nsets=6):
             'single_launch_after_rewriting_512MB_us': float(np.median(singles))}
 
 
-def parity_check(L, p, world, rank, dev, tol=1e-4):
+def parity_check(L, p, world, rank, dev, tol=1e-4, with_bf16=True):
     """ONE training step of the benchmark's own configuration (cosmo config 2, global batch 16, M = 262,144) on the CUDA
     path and on the CPU oracle from identical weights and inputs: logits, loss and every gradient.  With N ranks the
     global batch of 16 is split 16/N per rank, so that the check also covers SyncBN, the Gram
@@ -217,27 +226,35 @@ def parity_check(L, p, world, rank, dev, tol=1e-4):
     from deepsphere_tf1_b200 import models, ops, optimizers
     Bg = 16
     Bl = Bg // world
-    m = models.cgcnn(L=L, p=p, F=F, K=[KCHEB] * 6, batch_norm=[True] * 6, M=[], statistics='mean', num_epochs=1,
-                     batch_size=Bl, eval_frequency=10 ** 9, seed=2, verbose=False, cuda_graph=False,
-                     scheduler=lambda step: 2e-4, optimizer=lambda lr: optimizers.AdamOptimizer(lr, epsilon=1e-8),
-                     dir_name='_bench_parity', device=dev)
     x, labels = synthetic_batch(Bg, 7)
     xs, ls = x[rank * Bl:(rank + 1) * Bl], labels[rank * Bl:(rank + 1) * Bl]
-    xd, ld = m._to_device(xs), m._labels_to_device(ls)
-    ops.fill(m._P.g, 0.0)
-    m._loss.zero_()
-    m._arena.zero_()
-    logits, _ = m._forward(xd, training=True, save=True)
-    dlogits = m._loss_fwd_bwd(logits, ld, True)
-    m._backward(dlogits)
-    if world > 1:
-        m._allreduce(m._P.g)
-        ops.scale(m._loss, 1.0 / world)
-        m._allreduce(m._loss)
-        gathered = [torch.empty_like(logits) for _ in range(world)]
-        dist.all_gather(gathered, logits)
-        logits = torch.cat(gathered, dim=0)
-    torch.cuda.synchronize()
+
+    def cuda_step(dtype):
+        m = models.cgcnn(L=L, p=p, F=F, K=[KCHEB] * 6, batch_norm=[True] * 6, M=[], statistics='mean', num_epochs=1,
+                         batch_size=Bl, eval_frequency=10 ** 9, seed=2, verbose=False, cuda_graph=False, dtype=dtype,
+                         scheduler=lambda step: 2e-4, optimizer=lambda lr: optimizers.AdamOptimizer(lr, epsilon=1e-8),
+                         dir_name='_bench_parity', device=dev)
+        xd, ld = m._to_device(xs), m._labels_to_device(ls)
+        ops.fill(m._P.g, 0.0)
+        m._loss.zero_()
+        m._arena.zero_()
+        logits, _ = m._forward(xd, training=True, save=True)
+        dlogits = m._loss_fwd_bwd(logits, ld, True)
+        m._backward(dlogits)
+        if world > 1:
+            m._allreduce(m._P.g)
+            ops.scale(m._loss, 1.0 / world)
+            m._allreduce(m._loss)
+            gathered = [torch.empty_like(logits) for _ in range(world)]
+            dist.all_gather(gathered, logits)
+            logits = torch.cat(gathered, dim=0)
+        torch.cuda.synchronize()
+        return m, logits
+
+    m, logits = cuda_step(np.float32)
+    mb = logitsb = None
+    if with_bf16:
+        mb, logitsb = cuda_step('bfloat16')              # same seed: identical initial weights
     if rank != 0:
         return None
     import warnings
@@ -295,6 +312,29 @@ def parity_check(L, p, world, rank, dev, tol=1e-4):
                    'equals the float64 product of its own inputs to 1e-6 x its condition number).  Per-tensor max-norm errors '
                    'are listed beside those of the float32 CPU oracle'}
     out['ok'] = bool(out['loss_rel'] <= tol and out['max_logit_rel'] <= tol and grads_ok)
+    if mb is not None:
+        # BF16 mode (dtype='bfloat16': layers 2-6 on bfloat16 activations) against the same float64 oracle.  Forward: 1e-2 (north
+        # star).  Gradients: BF16 storage flips arg-max / ReLU decisions, so they are held to the deviation of the CPU oracle
+        # evaluated with the same tensors rounded to bfloat16 (oracle.ops.STORE) -- the noise floor of BF16 storage itself.
+        oe = OracleCgcnn(L, F=F, K=[KCHEB] * 6, p=p, batch_norm=[True] * 6, M=[], statistics='mean')
+        oe.bf16_layers = {2, 3, 4, 5, 6}
+        for name, v in oe.params.items():
+            oe.params[name] = m._P.views[name].detach().cpu().reshape(v.shape).clone()
+        tote, logitse, gradse, _ = oe.loss_and_grads(torch.from_numpy(x), torch.from_numpy(labels), True)
+        nb = ne = 0.0
+        for name, g in grads.items():
+            gd = g.double().reshape(-1)
+            nb += float(((mb._P.gviews[name].detach().cpu().double().reshape(-1) - gd) ** 2).sum())
+            ne += float(((gradse[name].double().reshape(-1) - gd) ** 2).sum())
+        b = {'loss_rel': abs(float(mb._loss) - float(total)) / max(abs(float(total)), 1e-30),
+             'max_logit_rel': rel(logitsb, ologits), 'grad_rel_l2': (nb / den) ** 0.5,
+             'grad_rel_l2_of_bf16_storage_oracle': (ne / den) ** 0.5,
+             'max_logit_rel_of_bf16_storage_oracle': rel(logitse, ologits), 'tolerance': 1e-2,
+             'what': 'the same step with dtype=bfloat16 vs the float64 oracle; ok = loss_rel and max_logit_rel within 1e-2, '
+                     'grad_rel_l2 within max(1e-2, 3 x that of the CPU oracle with BF16 storage emulation)'}
+        b['ok'] = bool(b['loss_rel'] <= 1e-2 and b['max_logit_rel'] <= 1e-2 and
+                       b['grad_rel_l2'] <= max(1e-2, 3.0 * b['grad_rel_l2_of_bf16_storage_oracle']))
+        out['bf16'] = b
     return out
 
 
@@ -396,7 +436,57 @@ def run_gpu(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = float(tt[0]), float(tt[1])
 
-    parity = None if args.no_parity else parity_check(L, p, world, rank, dev)
+    parity = None if args.no_parity else parity_check(L, p, world, rank, dev, with_bf16=not args.no_bf16)
+
+    # ---------------- BF16 mode: the same step with dtype='bfloat16' (a second line of evidence, never the headline)
+    bf16 = None
+    if not args.no_bf16:
+        mb = models.deepsphere(
+            nsides=NSIDES, indexes=utils.nside2indexes(NSIDES, ORDER), new=False, lmax=None if args.recompute_lmax else LMAX,
+            F=F, K=[KCHEB] * 6, batch_norm=[True] * 6, M=[], statistics='mean', num_epochs=1, dtype='bfloat16',
+            batch_size=B_local, eval_frequency=10 ** 9, seed=2, verbose=False, cuda_graph=not args.no_graph,
+            scheduler=lambda step: optimizers.exponential_decay(2e-4, step, decay_steps=1, decay_rate=0.999),
+            optimizer=lambda lr: optimizers.AdamOptimizer(lr, epsilon=1e-8), dir_name='_bench_bf16')
+        for _ in range(warm):
+            _, lossb = mb.train_step(x_pin, l_pin, next_batch=nxt)
+            float(lossb)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            _, lossb = mb.train_step(x_pin, l_pin, next_batch=nxt)
+            lastb = float(lossb)
+        e1.record()
+        barrier()
+        tb_e2e = e0.elapsed_time(e1) * 1e-3
+        if mb.cuda_graph:
+            mb._gx.copy_(xd)
+            mb._gl.copy_(ld)
+            stepb = lambda: mb._step_graph_resident()              # noqa: E731
+        else:
+            stepb = lambda: mb._step_device(xd, ld)                # noqa: E731
+        for _ in range(warm):
+            mb._advance_hyper()
+            stepb()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            mb._advance_hyper()
+            stepb()
+        e1.record()
+        barrier()
+        tb = torch.tensor([e0.elapsed_time(e1) * 1e-3, tb_e2e], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        bf16 = {'dtype': 'bf16', 'value': B_global * args.steps / float(tb[0]), 'unit': 'samples/s',
+                'ms_per_step': float(tb[0]) / args.steps * 1e3,
+                'e2e': {'value': B_global * args.steps / float(tb[1]), 'unit': 'samples/s', 'ms_per_step': float(tb[1]) / args.steps * 1e3},
+                'final_loss': lastb,
+                'what': "the same training step with cgcnn(dtype='bfloat16'): layers 2-6 store activations, Chebyshev planes and "
+                        'activation gradients as bfloat16 (fp32 arithmetic / accumulation, fp32 weights and statistics; tcgen05 '
+                        'kind::f16 contractions); parity in parity.bf16'}
+        if rank == 0:
+            bf16["roofline"] = spmm_roofline(mb, B_local, nsets=12, bf16=True)
+        del mb
 
     # kernels per step, counted by the library itself on one eager (non-graph) step
     c0 = _lib.kernel_launches()
@@ -431,9 +521,10 @@ def run_gpu(args):
                            'while the step runs (as fit() does); loss read back every step'},
             'gpu_launches': int(per_step * args.steps),
             'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'parity': parity, 'final_loss': last_loss,
+            'bf16_mode': bf16,
         }
         print(json.dumps(out))
-        if parity is not None and not parity['ok']:
+        if parity is not None and not (parity['ok'] and parity.get('bf16', {'ok': True})['ok']):
             sys.stderr.write('PARITY FAILED: {}\n'.format(json.dumps(parity)))
             exit_code = 3
     if world == 1 and exit_code:
@@ -460,6 +551,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--parity-only', action='store_true', help='only the full-size CUDA-vs-oracle check (no timing)')
     ap.add_argument('--no-parity', action='store_true', help='skip the full-size CUDA-vs-oracle check of one training step')
+    ap.add_argument('--no-bf16', action='store_true', help="skip the second measurement with dtype='bfloat16' (key bf16_mode)")
     ap.add_argument('--recompute-lmax', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

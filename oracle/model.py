@@ -33,6 +33,7 @@ class OracleCgcnn:
         self.dtype = dtype
         self.num_feat_in = num_feat_in
         self.finest_vertices = finest_vertices      # hard-coded level-5 size at models.py:1300
+        self.bf16_layers = set()                    # encoder layers (1-based) evaluated with BF16 storage emulation (ops.STORE)
         self.params = {}        # trainable, creation order
         self.std = {}           # name -> init stddev for regularised weights (models.py:866)
         self.state = {}         # BN moving statistics
@@ -136,7 +137,11 @@ class OracleCgcnn:
         for i in range(n):
             sc = 'conv{}'.format(i + 1)
             fm = filt_masks.get(sc) if (filt_masks and training) else None   # filter dropout: explicit masks (RNG is not parity)
-            x = self.conv(x, self.Ls[i], P[sc + '/weights'], self.K[i], fm)  # 1229
+            ops.STORE = True if (i + 1) in self.bf16_layers else None
+            try:
+                x = self.conv(x, self.Ls[i], P[sc + '/weights'], self.K[i], fm)  # 1229
+            finally:
+                ops.STORE = None
             if i == n - 1 and len(self.M) == 0:                              # 1232-1234
                 break
             if self.batch_norm[i]:
@@ -144,6 +149,8 @@ class OracleCgcnn:
             x = ops.bias(x, P[sc + '/bias'])                                 # 1238
             x = self.act(x)                                                  # 1239
             x = ops.pool(x, self.p[i], self.pool_kind, self.sampling)        # 1243
+            if (i + 1) in self.bf16_layers:
+                x = ops._RoundBf16.apply(x)                                  # the product stores this layer's output as bfloat16
             pool_layers.append(x)                                            # 1245
         descriptor = x
         if self.stat == 'histogram':

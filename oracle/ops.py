@@ -11,6 +11,42 @@ import torch
 import torch.nn.functional as TF
 
 
+# ---- emulation of the BF16 storage mode of the product (cgcnn(dtype='bfloat16')): where the product STORES an activation
+# (layer input, Chebyshev planes, the contraction's output, the pooled output) or its gradient as bfloat16, the oracle rounds
+# the same tensor -- and, in the backward pass, its gradient -- to bfloat16 (round to nearest even) and keeps computing in
+# its own dtype.  STORE is None (no rounding) unless OracleCgcnn.bf16_layers names the layer being evaluated.  This is the
+# noise floor of BF16 storage itself, against which the CUDA kernels are held (tests/test_bf16.py).
+STORE = None
+
+
+class _RoundBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+class _RoundBf16Fwd(torch.autograd.Function):          # weights: the contraction reads them rounded, their gradient stays fp32
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _st(t):
+    return t if STORE is None else _RoundBf16.apply(t)
+
+
+def _stw(t):
+    return t if STORE is None else _RoundBf16Fwd.apply(t)
+
+
 def sparse_to_torch(L, dtype=torch.float32):
     """models.py:1044-1047: COO triplets -> SparseTensor, reordered row-major, cast to dtype."""
     L = L.tocoo()
@@ -35,19 +71,19 @@ def chebyshev5(x, L, W, K, mask=None):
     Fout = W.shape[1]
     W = drop_filters(W, Fin, K, mask)
     x0 = x.permute(1, 2, 0)                                   # M x Fin x N        (1049)
-    x0 = x0.reshape(M, Fin * N)                               # M x Fin*N          (1050)
+    x0 = _st(x0.reshape(M, Fin * N))                          # M x Fin*N          (1050)
     xs = x0.unsqueeze(0)                                      # 1 x M x Fin*N      (1051)
     if K > 1:
-        x1 = torch.sparse.mm(L, x0)                           #                    (1056)
+        x1 = _st(torch.sparse.mm(L, x0))                      #                    (1056)
         xs = torch.cat([xs, x1.unsqueeze(0)], dim=0)          #                    (1057)
     for k in range(2, K):
-        x2 = 2 * torch.sparse.mm(L, x1) - x0                  #                    (1059)
+        x2 = _st(2 * torch.sparse.mm(L, x1) - x0)             #                    (1059)
         xs = torch.cat([xs, x2.unsqueeze(0)], dim=0)
         x0, x1 = x1, x2                                       #                    (1061)
     xs = xs.reshape(K, M, Fin, N)                             #                    (1062)
     xs = xs.permute(3, 1, 2, 0)                               # N x M x Fin x K    (1063)
     xs = xs.reshape(N * M, Fin * K)                           #                    (1064)
-    y = xs @ W                                                #                    (1077)
+    y = _st(xs @ _stw(W))                                     #                    (1077)
     return y.reshape(N, M, Fout)                              #                    (1078)
 
 
