@@ -200,8 +200,14 @@ def test_bf16_cosmo_like_model_against_the_oracles(dev):
     t64, l64, g64, _ = o64.loss_and_grads(torch.from_numpy(x).double(), torch.from_numpy(labels))
     tem, lem, gem, _ = oem.loss_and_grads(torch.from_numpy(x), torch.from_numpy(labels))
     logits, loss, g = _grads_cuda(model, x, labels.astype(np.int32))
-    assert_close(logits.reshape(l64.shape), l64, RT_FWD, 'logits')
-    assert abs(loss - float(t64)) <= RT_FWD * abs(float(t64))
+    # the logits of this miniature are means over 64 vertices only (max |logit| ~ 0.5, the activations behind them are O(1)): held
+    # to 1e-2 or, where BF16 storage itself costs more, to 3x the deviation of the BF16-storage oracle
+    lscale = float(l64.abs().max())
+    lfloor = float((lem.double() - l64).abs().max()) / lscale
+    lerr = float((logits.reshape(l64.shape) - l64).abs().max()) / lscale
+    print('logits error vs float64: CUDA bf16 {:.3e}, BF16-storage oracle {:.3e}'.format(lerr, lfloor))
+    assert lerr <= max(RT_FWD, 3 * lfloor), (lerr, lfloor)
+    assert abs(loss - float(t64)) <= max(RT_FWD, 3 * abs(float(tem) - float(t64)) / abs(float(t64))) * abs(float(t64))
     floor = _flat_err(gem, g64)                                       # what BF16 storage costs in ANY implementation
     err = _flat_err(g, g64)
     print('flat gradient error vs float64: CUDA bf16 {:.3e}, BF16-storage oracle {:.3e}'.format(err, floor))
@@ -229,8 +235,9 @@ def test_bf16_encoder_decoder_and_fc_models_run_and_stay_close_to_fp32(dev):
     """Everything outside the ChebConv layers is fp32 between casts: a U-Net (unpool, concat, dense loss) and an fc head in
     dtype='bfloat16' against the same models in float32."""
     from deepsphere_tf1_b200 import models, optimizers, utils
-    nsides = [8, 4, 2]
+    nsides = [8, 4, 2, 2]
     L, p = utils.build_laplacians(nsides, indexes=utils.nside2indexes(nsides, 0), new=False)
+    assert [l.shape[0] for l in L] == [768, 192, 48] and p == [4, 4, 1]
     rs = np.random.RandomState(1)
     common = dict(num_epochs=1, batch_size=2, eval_frequency=10, dir_name='_test_bf16b', verbose=False, seed=3,
                   optimizer=lambda lr: optimizers.MomentumOptimizer(lr, 0.9), scheduler=lambda s: 1e-2)

@@ -25,6 +25,7 @@ else:
     nsides=bench.NSIDES, indexes=utils.nside2indexes(bench.NSIDES, bench.ORDER), new=False, lmax=bench.LMAX,
     F=bench.F, K=[bench.KCHEB] * 6, batch_norm=[True] * 6, M=[], statistics='mean', num_epochs=1,
     batch_size=16, eval_frequency=10 ** 9, seed=2, verbose=False, cuda_graph=False,
+    dtype='bfloat16' if os.environ.get('DSB200_TRACE_DTYPE', 'f32') == 'bf16' else 'float32',
     scheduler=lambda step: 2e-4, optimizer=lambda lr: optimizers.AdamOptimizer(lr, epsilon=1e-8), dir_name='_trace')
 if CFG == 2:
     x, labels = bench.synthetic_batch(16, 0)
