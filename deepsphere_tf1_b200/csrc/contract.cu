@@ -352,7 +352,7 @@ extern "C" long long dsb200_contract_workspace_bytes(int Fin, int K, int Fout)
 
 namespace dsb200 {
 int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
-                     double* bn_sums, cudaStream_t s);                      // contract_mma.cu
+                     double* bn_sums, cudaStream_t s, float* Ypool = nullptr);   // contract_mma.cu
 int contract_wgrad_mma(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K, int Fout,
                        cudaStream_t s);                                     // contract_mma.cu
 static bool wgrad_mma_enabled() { return DSB_ENV_INT("DSB200_WGRAD_MMA", 1) != 0; }   // default on
@@ -387,6 +387,43 @@ extern "C" int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const 
         contract_kernel<false><<<grid, 256, 0, s>>>(A, W, Y, R, Fin, K, Fout, Q, Fout, bn_sums);
     }
     DSB_LAUNCH_CHECK();
+}
+
+// Forward contraction with the HEALPix max-pool over 4 consecutive vertices fused into the epilogue: Ypool [R/4, Fout] =
+// max over every 4 consecutive rows of Y; Y itself is written only when the caller needs it (training: the batch-norm backward
+// reads it) and may be NULL (inference).  Tensor-core kernels only: 1 -> the caller uses the unfused operators.
+static int contract_fwd_pool4(const float* x0, const float* xk, const float* W, float* Y, float* Ypool, long long R, int Fin, int K,
+                              int Fout, double* bn_sums, void* workspace, cudaStream_t s)
+{
+    if (!g_use_tc.load(std::memory_order_relaxed) || (R & 3)) return 1;
+    if (fwd_mma_enabled()) {
+        const int rc = contract_fwd_mma(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, s, Ypool);
+        if (rc != 1) return rc;
+    }
+    if (K * Fin <= 16 || !workspace) return 1;
+    int rc = tc::contract_fwd_tc_cols(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, workspace, s, Ypool);
+    if (rc == 1) rc = tc::contract_fwd_tc(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, workspace, s, Ypool);
+    return rc;
+}
+
+extern "C" int dsb200_cheb_contract_fwd_pool4(const float* x0, const float* xk, const float* W, float* Y, float* Ypool,
+                                              long long R, int Fin, int K, int Fout, double* bn_sums, void* workspace, void* stream)
+{
+    DSB_REQUIRE(R > 0 && Fin > 0 && K > 0 && Fout > 0, "contract_fwd_pool4: bad shape");
+    DSB_REQUIRE(x0 && W && Ypool && (K == 1 || xk), "contract_fwd_pool4: null pointer");
+    const int rc = contract_fwd_pool4(x0, xk, W, Y, Ypool, R, Fin, K, Fout, bn_sums, workspace, (cudaStream_t)stream);
+    DSB_REQUIRE(rc != 1, "contract_fwd_pool4: no tensor-core kernel takes this shape (see dsb200_contract_pool4_supported)");
+    return rc;
+}
+
+// 1 when dsb200_cheb_contract_fwd_pool4 takes the shape (the conditions of the three tensor-core forward kernels)
+extern "C" int dsb200_contract_pool4_supported(long long R, int Fin, int K, int Fout)
+{
+    if (!g_use_tc.load(std::memory_order_relaxed) || (R & 3) || R < 256 || R > 0x7fffff00LL) return 0;
+    if (fwd_mma_enabled() && Fin == 16 && Fout == 32 && K >= 1 && K <= 8) return 1;
+    if (K * Fin <= 16) return 0;
+    if ((Fin & 7) || Fout > 256) return 0;
+    return tc::contract_fwd_tc_query(R, Fin, K, Fout);
 }
 
 extern "C" int dsb200_cheb_contract_bwd_data(const float* dY, const float* W, float* G,

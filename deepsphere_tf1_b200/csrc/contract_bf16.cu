@@ -60,7 +60,8 @@ struct alignas(64) RowGemmBfParams {
     CUtensorMap tmAk;          // planes 1..K-1, rank 3 (forward only)
     const float* W;            // [Fin*K, Fout], row = fi*K + k
     const uint8_t* wimage;     // packed bf16 weights in the shared-memory image layout (pack_w_bf16_kernel)
-    bf16* out;                 // Y [R, Fout]  |  G [K][R][Fin]
+    bf16* out;                 // Y [R, Fout] (forward: may be NULL when only the pooled output is wanted)  |  G [K][R][Fin]
+    bf16* pool_out;            // forward only, may be NULL: max over every 4 consecutive rows of Y, [R/4, Fout]
     double* bn_sums;           // forward only, may be NULL
     long long Rp;              // packed rows = R / rp
     int Fin, K, Fout, rp;
@@ -245,6 +246,7 @@ rowgemm_bf16_kernel(const __grid_constant__ RowGemmBfParams p)
                 if (MODE == BF_FWD) {
                     bf16* orow = p.out + prow * p.Nreal;
                     const bool wide = (p.Nreal & 15) == 0 && (((uintptr_t)p.out) & 31) == 0;
+                    const bool sty = p.out != nullptr;
                     for (int c0 = 0; c0 < p.Nreal; c0 += 32) {
                         float v[32];
                         tmem_ld16(tbase + c0, v);
@@ -257,10 +259,10 @@ rowgemm_bf16_kernel(const __grid_constant__ RowGemmBfParams p)
                         uint32_t w[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-                        if (ok && wide) {
+                        if (ok && sty && wide) {
                             st_b32x8(orow + c0, w);
                             if (c0 + 16 < p.Nreal) st_b32x8(orow + c0 + 16, w + 8);
-                        } else if (ok) {
+                        } else if (ok && sty) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i)
                                 if (c0 + i < p.Nreal) st1(orow + c0 + i, (i & 1) ? bf16_hi(w[i >> 1]) : bf16_lo(w[i >> 1]));
@@ -276,6 +278,36 @@ rowgemm_bf16_kernel(const __grid_constant__ RowGemmBfParams p)
                                 const int f = (c0 + lane) % p.Fout;
                                 atomicAdd(red + f, v[0]);
                                 atomicAdd(red + 256 + f, sq[0]);
+                            }
+                        }
+                    }
+                    if (p.pool_out) {
+                        // HEALPix max-pool over 4 consecutive rows, fused: batch norm without scale / shift, the bias and
+                        // every activation of the library are non-decreasing per feature, so pooling the raw y first gives the same
+                        // result (models.py:1235-1243) and the normalise / activate pass runs on a quarter of the rows.  A packed
+                        // row holds rp consecutive rows: maximum over its rp column groups, then over the 4 / rp neighbouring lanes.
+                        const int lpg = 4 / p.rp;
+                        for (int f0 = 0; f0 < p.Fout; f0 += 16) {
+                            float m[16];
+                            tmem_ld16(tbase + f0, m);
+                            tmem_ld_wait();
+                            for (int h = 1; h < p.rp; ++h) {
+                                float u[16];
+                                tmem_ld16(tbase + h * p.Fout + f0, u);
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) m[i] = fmaxf(m[i], u[i]);
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], 1));
+                                if (lpg == 4) m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], 2));
+                            }
+                            if (ok && (lane & (lpg - 1)) == 0) {
+                                uint32_t w[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(m[2 * i], m[2 * i + 1]);   // rounding is monotone: = max of the stored y
+                                st_b32x8(p.pool_out + (prow / lpg) * p.Fout + f0, w);
                             }
                         }
                     }
@@ -383,13 +415,15 @@ static void fill_params(RowGemmBfParams& p, const RowGemmBfPlan& pl, long long R
     p.ntiles = (int)((p.Rp + (long long)pl.TM * kBM - 1) / ((long long)pl.TM * kBM));
 }
 
-int contract_fwd_bf16(const bf16* x0, const bf16* xk, const float* W, bf16* Y, long long R, int Fin, int K, int Fout,
-                      double* bn_sums, void* workspace, cudaStream_t s, bool query)
+int contract_fwd_bf16(const bf16* x0, const bf16* xk, const float* W, bf16* Y, bf16* Ypool, long long R, int Fin, int K, int Fout,
+                      double* bn_sums, void* workspace, cudaStream_t s, bool query, bool pool)
 {
     if (R > 0x7fffff00LL || Fout > 256 || K < 1) return 1;
     RowGemmBfPlan pl;
     if (!plan_rowgemm_bf16(BF_FWD, R, Fin, K, Fout, &pl)) return 1;
+    if (pool && ((Fout & 15) || (R & 3) || pl.rp > 2)) return 1;
     if (query) return 0;
+    if ((((uintptr_t)Ypool) & 31) != 0 || (!Y && !Ypool)) return 1;
     if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y | (uintptr_t)workspace) & 15) != 0 || !workspace) return 1;
     RowGemmBfParams p;
     fill_params(p, pl, R, Fin, K, Fout);
@@ -406,7 +440,7 @@ int contract_fwd_bf16(const bf16* x0, const bf16* xk, const float* W, bf16* Y, l
         const cuuint32_t box[3] = {(cuuint32_t)pl.kc, (cuuint32_t)(pl.TM * kBM), (cuuint32_t)(K - 1)};
         if (make_tmap_bf16(&p.tmAk, xk, 3, dims, strides, box, pl.swz)) return 1;
     } else p.tmAk = p.tmA0;
-    p.W = W; p.out = Y; p.bn_sums = bn_sums;
+    p.W = W; p.out = Y; p.pool_out = Ypool; p.bn_sums = bn_sums;
     if (!bn_sums) return launch_rowgemm_bf16<BF_FWD, false>(p, pl.smem, (uint8_t*)workspace, s);
     return launch_rowgemm_bf16<BF_FWD, true>(p, pl.smem, (uint8_t*)workspace, s);
 }
@@ -428,7 +462,7 @@ int contract_bwd_data_bf16(const bf16* dY, const float* W, bf16* G, long long R,
     const cuuint32_t box[2] = {(cuuint32_t)pl.kc, (cuuint32_t)(pl.TM * kBM)};
     if (make_tmap_bf16(&p.tmA0, dY, 2, dims, strides, box, pl.swz)) return 1;
     p.tmAk = p.tmA0;
-    p.W = W; p.out = G; p.bn_sums = nullptr;
+    p.W = W; p.out = G; p.pool_out = nullptr; p.bn_sums = nullptr;
     return launch_rowgemm_bf16<BF_BWD_DATA, false>(p, pl.smem, (uint8_t*)workspace, s);
 }
 
@@ -672,7 +706,8 @@ using namespace dsb200;
 // 1 when the bf16 tensor-core kernel of direction `dir` (0 forward, 1 data gradient, 2 weight gradient) takes this shape
 extern "C" int dsb200_contract_bf16_supported(int dir, long long R, int Fin, int K, int Fout)
 {
-    if (dir == 0) return tc::contract_fwd_bf16(nullptr, nullptr, nullptr, nullptr, R, Fin, K, Fout, nullptr, nullptr, 0, true) == 0;
+    if (dir == 0) return tc::contract_fwd_bf16(nullptr, nullptr, nullptr, nullptr, nullptr, R, Fin, K, Fout, nullptr, nullptr, 0, true, false) == 0;
+    if (dir == 3) return tc::contract_fwd_bf16(nullptr, nullptr, nullptr, nullptr, nullptr, R, Fin, K, Fout, nullptr, nullptr, 0, true, true) == 0;
     if (dir == 1) return tc::contract_bwd_data_bf16(nullptr, nullptr, nullptr, R, Fin, K, Fout, nullptr, 0, true) == 0;
     return tc::contract_bwd_weight_bf16(nullptr, nullptr, nullptr, nullptr, R, Fin, K, Fout, 0, true) == 0;
 }
@@ -686,9 +721,19 @@ extern "C" int dsb200_cheb_contract_fwd_bf16(const void* x0, const void* xk, con
                                              int K, int Fout, double* bn_sums, void* workspace, void* stream)
 {
     DSB_REQUIRE(x0 && W && y && R > 0 && (K == 1 || xk), "cheb_contract_fwd_bf16: bad arguments");
-    const int rc = tc::contract_fwd_bf16((const bf16*)x0, (const bf16*)xk, W, (bf16*)y, R, Fin, K, Fout, bn_sums, workspace,
-                                         (cudaStream_t)stream, false);
+    const int rc = tc::contract_fwd_bf16((const bf16*)x0, (const bf16*)xk, W, (bf16*)y, nullptr, R, Fin, K, Fout, bn_sums, workspace,
+                                         (cudaStream_t)stream, false, false);
     DSB_REQUIRE(rc != 1, "cheb_contract_fwd_bf16: unsupported shape / alignment (see dsb200_contract_bf16_supported)");
+    return rc;
+}
+
+extern "C" int dsb200_cheb_contract_fwd_pool4_bf16(const void* x0, const void* xk, const float* W, void* y, void* ypool, long long R,
+                                                   int Fin, int K, int Fout, double* bn_sums, void* workspace, void* stream)
+{
+    DSB_REQUIRE(x0 && W && ypool && R > 0 && (K == 1 || xk), "cheb_contract_fwd_pool4_bf16: bad arguments");
+    const int rc = tc::contract_fwd_bf16((const bf16*)x0, (const bf16*)xk, W, (bf16*)y, (bf16*)ypool, R, Fin, K, Fout, bn_sums,
+                                         workspace, (cudaStream_t)stream, false, true);
+    DSB_REQUIRE(rc != 1, "cheb_contract_fwd_pool4_bf16: unsupported shape / alignment (dsb200_contract_bf16_supported(3, ...))");
     return rc;
 }
 

@@ -181,7 +181,7 @@ constexpr int kMpThreads = 9 * 32;
 template <bool SUMS, int MTW, int kMpStages>
 __device__ __forceinline__ void
 rowgemm_mma_pipe_body(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ W,
-                      float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K)
+                      float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K, float* __restrict__ Ypool)
 {
     constexpr int kMpRows = 8 * 16 * MTW, kMpStageBytes = kMpRows * kMmaFin * 4;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -294,7 +294,17 @@ rowgemm_mma_pipe_body(const float* __restrict__ x0, const float* __restrict__ xk
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
                     const float4 o = make_float4(acc[m][2 * p][2 * h], acc[m][2 * p][2 * h + 1], acc[m][2 * p + 1][2 * h], acc[m][2 * p + 1][2 * h + 1]);
-                    if (r < R) *reinterpret_cast<float4*>(Y + r * kMmaFout + 16 * p + 4 * t) = o;
+                    if (Y != nullptr && r < R) *reinterpret_cast<float4*>(Y + r * kMmaFout + 16 * p + 4 * t) = o;
+                    if (Ypool != nullptr) {
+                        // max-pool over 4 consecutive rows (g, g^1, g^2, g^3 = lanes 4 and 8 apart), on the raw y: it commutes with the
+                        // batch norm / bias / activation that follow (non-decreasing per feature, models.py:1235-1243)
+                        float4 q = o;
+                        q.x = fmaxf(q.x, __shfl_xor_sync(0xffffffffu, q.x, 4)); q.y = fmaxf(q.y, __shfl_xor_sync(0xffffffffu, q.y, 4));
+                        q.z = fmaxf(q.z, __shfl_xor_sync(0xffffffffu, q.z, 4)); q.w = fmaxf(q.w, __shfl_xor_sync(0xffffffffu, q.w, 4));
+                        q.x = fmaxf(q.x, __shfl_xor_sync(0xffffffffu, q.x, 8)); q.y = fmaxf(q.y, __shfl_xor_sync(0xffffffffu, q.y, 8));
+                        q.z = fmaxf(q.z, __shfl_xor_sync(0xffffffffu, q.z, 8)); q.w = fmaxf(q.w, __shfl_xor_sync(0xffffffffu, q.w, 8));
+                        if ((g & 3) == 0 && r < R) *reinterpret_cast<float4*>(Ypool + (r >> 2) * kMmaFout + 16 * p + 4 * t) = q;
+                    }
                     if (!SUMS) continue;
                     // rows past R are exact zeros: the sums need no predicate
                     s1[4 * p] += o.x; s1[4 * p + 1] += o.y; s1[4 * p + 2] += o.z; s1[4 * p + 3] += o.w;
@@ -323,17 +333,17 @@ rowgemm_mma_pipe_body(const float* __restrict__ x0, const float* __restrict__ xk
 template <bool SUMS>
 __global__ void __maxnreg__(112)
 rowgemm_mma_pipe_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ W,
-                        float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K)
+                        float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K, float* __restrict__ Ypool)
 {
-    rowgemm_mma_pipe_body<SUMS, 2, 4>(x0, xk, W, Y, bn_sums, R, K);
+    rowgemm_mma_pipe_body<SUMS, 2, 4>(x0, xk, W, Y, bn_sums, R, K, Ypool);
 }
 
 template <bool SUMS>
 __global__ void __launch_bounds__(kMpThreads, 1)
 rowgemm_mma_pipe64_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ W,
-                          float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K)
+                          float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K, float* __restrict__ Ypool)
 {
-    rowgemm_mma_pipe_body<SUMS, 4, 5>(x0, xk, W, Y, bn_sums, R, K);
+    rowgemm_mma_pipe_body<SUMS, 4, 5>(x0, xk, W, Y, bn_sums, R, K, Ypool);
 }
 
 // ---- weight gradient of the same narrow layer:  dW[fi*K + k, fo] += sum_r X_k[r, fi] dY[r, fo]   (autodiff of models.py:1077).
@@ -497,13 +507,15 @@ int contract_wgrad_mma(const float* x0, const float* xk, const float* dY, float*
 
 // returns 1 when the shape does not qualify
 int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
-                     double* bn_sums, cudaStream_t s)
+                     double* bn_sums, cudaStream_t s, float* Ypool)
 {
     if (Fin != kMmaFin || Fout != kMmaFout || K < 1 || K > kMmaMaxK) return 1;
-    if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y) & 15) != 0) return 1;
+    if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y | (uintptr_t)Ypool) & 15) != 0) return 1;
+    if (Ypool && (R & 3)) return 1;
     const long long cap = 2LL * kNumSMs;
-    const int variant = DSB_ENV_INT("DSB200_FWD_MMA", 3);                            // 3 (default): 64 rows per warp, one CTA per SM (100.6 us with
+    int variant = DSB_ENV_INT("DSB200_FWD_MMA", 3);                  // 3 (default): 64 rows per warp, one CTA per SM (100.6 us with
                                                                      // the sums at cosmo layer 2); 1: 32 rows, two CTAs (105.8 us)
+    if (Ypool && variant == 2) variant = 3;                          // the register experiment has no pooled epilogue
     if (variant == 2) {                                              // register version (experiment)
         const long long nblk = (R + 31) / 32;
         const int grid = (int)((nblk + 7) / 8 < cap ? (nblk + 7) / 8 : cap);
@@ -522,8 +534,8 @@ int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y,
             if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return (int)ce; }
             cfg64 = true;
         }
-        if (bn_sums) rowgemm_mma_pipe64_kernel<true><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K);
-        else rowgemm_mma_pipe64_kernel<false><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K);
+        if (bn_sums) rowgemm_mma_pipe64_kernel<true><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+        else rowgemm_mma_pipe64_kernel<false><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
         DSB_LAUNCH_CHECK();
     }
     const long long nblk = (R + 255) / 256;
@@ -536,8 +548,8 @@ int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y,
         if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return (int)ce; }
         cfg = true;
     }
-    if (bn_sums) rowgemm_mma_pipe_kernel<true><<<grid, kMpThreads, smem, s>>>(x0, xk, W, Y, bn_sums, R, K);
-    else rowgemm_mma_pipe_kernel<false><<<grid, kMpThreads, smem, s>>>(x0, xk, W, Y, bn_sums, R, K);
+    if (bn_sums) rowgemm_mma_pipe_kernel<true><<<grid, kMpThreads, smem, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+    else rowgemm_mma_pipe_kernel<false><<<grid, kMpThreads, smem, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
     DSB_LAUNCH_CHECK();
 }
 

@@ -78,7 +78,8 @@ struct alignas(64) RowGemmParams {
     int epi_tma, epi_cols;     // data gradient: stage 128 rows x epi_cols (= Fin) of a plane in shared memory, 1-D bulk store
     const float* W;            // [Fin*K, Fout], row = fi*K + k
     const float* wpack;        // pre-split weights in the shared-memory image layout (pack_w_kernel), or NULL
-    float* out;                // Y [R, Fout]  |  G [K][R][Fin]
+    float* out;                // Y [R, Fout] (forward: may be NULL when only the pooled output is wanted)  |  G [K][R][Fin]
+    float* pool_out;           // forward only, may be NULL: max over every 4 consecutive rows of Y, [R/4, Fout]
     double* bn_sums;           // forward only, may be NULL
     long long R;
     int Fin, K, Fout;
@@ -350,6 +351,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
             const bool ok = row < p.R && !p.nostore;
             if (MODE == MODE_FWD) {
                 float* orow = p.out + row * p.Fout;
+                const bool sty = p.out != nullptr;
                 const bool wide8 = (p.Fout & 7) == 0 && (p.n0 & 7) == 0 && ((uintptr_t)p.out & 31) == 0;
                 for (int c0 = 0; c0 < p.Nreal; c0 += 32) {
                     float v[32];
@@ -372,7 +374,32 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
 #pragma unroll
                         for (int i = 16; i < 32; ++i) v[i] = 0.f;
                     }
-                    if (ok && wide8) {
+                    if (p.pool_out) {
+                        // HEALPix max-pool over 4 consecutive rows = 4 neighbouring lanes, on the raw y: batch norm without scale /
+                        // shift, the bias and the activations are non-decreasing per feature, so the pooling commutes with them
+                        // (models.py:1235-1243); the normalise / activate pass then reads a quarter of the rows
+                        float m[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            m[i] = fmaxf(v[i], __shfl_xor_sync(0xffffffffu, v[i], 1));
+                            m[i] = fmaxf(m[i], __shfl_xor_sync(0xffffffffu, m[i], 2));
+                        }
+                        if (ok && (lane & 3) == 0) {
+                            float* prow = p.pool_out + (row >> 2) * p.Fout;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const int c = p.n0 + c0 + i;
+                                if (c + 3 < p.Fout && (p.Fout & 3) == 0) st4(prow + c, make_float4(m[i], m[i + 1], m[i + 2], m[i + 3]));
+                                else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) if (c + e < p.Fout && c0 + i + e < p.Nreal) prow[c + e] = m[i + e];
+                                }
+                            }
+                        }
+                    }
+                    if (!sty) {
+                        // only the pooled output is wanted (inference)
+                    } else if (ok && wide8) {
                         // a lane owns a whole output row: 32-byte stores halve the number of 128-byte lines (= load/store-pipe
                         // wavefronts) a warp instruction touches per byte (32 lines either way)
 #pragma unroll
@@ -633,10 +660,11 @@ size_t contract_workspace_bytes(int Fin, int K, int Fout)
 
 // Forward contraction on the tensor cores.  Returns 1 if the shape is not supported (caller falls back).
 int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
-                    double* bn_sums, void* workspace, cudaStream_t s)
+                    double* bn_sums, void* workspace, cudaStream_t s, float* Ypool)
 {
     if (R < kTileM || R > 0x7fffff00LL || Fout > 256) return 1;
-    if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y | (uintptr_t)workspace) & 15) != 0) return 1;
+    if ((((uintptr_t)x0 | (uintptr_t)xk | (uintptr_t)Y | (uintptr_t)workspace | (uintptr_t)Ypool) & 15) != 0) return 1;
+    if (Ypool && (R & 3)) return 1;
     const int Npad = (Fout + 15) / 16 * 16;
     RowGemmPlan pl;
     int ctas = env_int("DSB200_RG_CTAS", 2);
@@ -648,7 +676,7 @@ int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, 
     if (make_tmap_f32(&p.tmA0, x0, Fin, R, 1, pl.kc, kTileM, pl.swz, false)) return 1;
     if (K > 1) { if (make_tmap_f32(&p.tmAk, xk, Fin, R, K - 1, pl.kc, kTileM, pl.swz, true)) return 1; }
     else p.tmAk = p.tmA0;
-    p.W = W; p.out = Y; p.bn_sums = bn_sums; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
+    p.W = W; p.out = Y; p.pool_out = Ypool; p.bn_sums = bn_sums; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
     p.epi_tma = 0; p.epi_cols = 0; p.tmOut = p.tmA0;
     p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.G = pl.G; p.Npad = Npad; p.Nreal = Fout; p.n0 = 0; p.swz = pl.swz;
     p.nstages = pl.nstages; p.acc_stages = pl.acc_stages; p.wstream = pl.wstream;
@@ -656,6 +684,17 @@ int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, 
     float* image = (float*)workspace;
     if (!bn_sums) return launch_rowgemm<MODE_FWD, false>(p, pl.smem, pl.ctas, image, s);
     return launch_rowgemm<MODE_FWD, true>(p, pl.smem, pl.ctas, image, s);
+}
+
+// 1 when contract_fwd_tc takes the shape (alignment aside)
+int contract_fwd_tc_query(long long R, int Fin, int K, int Fout)
+{
+    if (R < kTileM || R > 0x7fffff00LL || Fout > 256) return 0;
+    RowGemmPlan pl;
+    int ctas = env_int("DSB200_RG_CTAS", 2);
+    const int rmax = rowgemm_max_ctas<MODE_FWD, true>();
+    if (ctas > rmax) ctas = rmax;
+    return plan_rowgemm(Fin, K, (Fout + 15) / 16 * 16, true, ctas, &pl) ? 1 : 0;
 }
 
 // Data gradient on the tensor cores: G[k][r][fi] = sum_fo dY[r, fo] W[fi*K + k, fo].
@@ -687,7 +726,7 @@ int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R,
         if (make_tmap_f32(&p.tmA0, dY, Fout, R, 1, pl.kc, kTileM, pl.swz, false)) return 1;
         p.tmAk = p.tmA0;
         p.epi_tma = epi_tma ? 1 : 0; p.epi_cols = epi_cols; p.tmOut = p.tmA0;
-        p.W = W; p.out = G; p.bn_sums = nullptr; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
+        p.W = W; p.out = G; p.pool_out = nullptr; p.bn_sums = nullptr; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
         p.kc = pl.kc; p.nchunk = pl.nchunk; p.nkb = pl.nkb; p.G = pl.G; p.Npad = NB; p.n0 = b * NB;
         p.Nreal = (Q - p.n0 < NB) ? (Q - p.n0) : NB;
         p.swz = pl.swz; p.nstages = pl.nstages; p.acc_stages = pl.acc_stages; p.wstream = pl.wstream;

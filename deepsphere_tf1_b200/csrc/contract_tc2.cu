@@ -26,7 +26,8 @@ constexpr int kCgStagesMax = 8;
 struct alignas(64) ColGemmParams {
     CUtensorMap tmA0, tmAk;    // plane 0 / planes 1..K-1, boxes of 256 rows x kc columns
     const float* wimg;         // weight image [nkb][128][kc], K-major swizzled (colgemm_pack_kernel)
-    float* out;                // Y [R, Fout]
+    float* out;                // Y [R, Fout] (may be NULL when only the pooled output is wanted)
+    float* pool_out;           // may be NULL: max over every 4 consecutive rows of Y, [R/4, Fout]
     double* bn_sums;           // may be NULL
     long long R;
     int Fin, K, Fout, kc, nchunk, nkb, swz, nstages, ntiles;
@@ -191,6 +192,7 @@ colgemm_tc_kernel(const __grid_constant__ ColGemmParams p)
                     tmem_ld16(tbase + c0, v);
                     tmem_ld16(tbase + c0 + 16, v + 16);
                     tmem_ld_wait();
+                    float pm = 0.f;
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
                         // hi + lo of both rows; the even lane keeps row c0+i, the odd lane row c0+i+1
@@ -199,8 +201,20 @@ colgemm_tc_kernel(const __grid_constant__ ColGemmParams p)
                         const float mine = odd ? o : e;
                         const long long r = row0 + c0 + i + odd;
                         if (fo < p.Fout && r < p.R) {
-                            p.out[r * p.Fout + fo] = mine;
+                            if (p.out) p.out[r * p.Fout + fo] = mine;
                             if (SUMS) { s1 += mine; s2 = fmaf(mine, mine, s2); }
+                        }
+                        if (p.pool_out) {
+                            // max-pool over the 4 consecutive rows c0+i-2 .. c0+i+1 (i = 2 mod 4): this lane holds two of them (in
+                            // `pm` and `mine`), its partner the other two; the pooling commutes with the batch norm / bias /
+                            // activation that follow (all non-decreasing per feature, models.py:1235-1243)
+                            if ((i & 2) == 0) pm = mine;
+                            else {
+                                float m4 = fmaxf(pm, mine);
+                                m4 = fmaxf(m4, __shfl_xor_sync(0xffffffffu, m4, 1));
+                                const long long rg = row0 + c0 + i - 2;
+                                if (!odd && fo < p.Fout && rg < p.R) p.pool_out[(rg >> 2) * p.Fout + fo] = m4;
+                            }
                         }
                     }
                 }
@@ -223,9 +237,10 @@ size_t colgemm_workspace_bytes(int Fin, int K) { return (size_t)K * Fin * kImgRo
 
 // Returns 1 when the shape is not supported (the caller uses the row-GEMM).
 int contract_fwd_tc_cols(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
-                         double* bn_sums, void* workspace, cudaStream_t s)
+                         double* bn_sums, void* workspace, cudaStream_t s, float* Ypool)
 {
     if (DSB_ENV_INT("DSB200_NO_COLGEMM", 0)) return 1;
+    if (Ypool && (R & 3)) return 1;
     if (!workspace || R < kTileN || R > 0x7fffff00LL || Fout > 64 || (Fout & 3) || (Fin & 15)) return 1;
     // Measured (tools/sweep_gemm.py): 77 vs 90 us at cosmo layer 3 (Fin = 32), but 181 vs 136 us at layer 2 (Fin = 16, Fout = 32:
     // half of the 128 accumulator lanes and half of the epilogue warps idle, and TMA delivers 64-byte rows no faster than ~4 ns
@@ -254,7 +269,7 @@ int contract_fwd_tc_cols(const float* x0, const float* xk, const float* W, float
     if (make_tmap_f32(&p.tmA0, x0, Fin, R, 1, p.kc, kTileN, p.swz, false)) return 1;
     if (K > 1) { if (make_tmap_f32(&p.tmAk, xk, Fin, R, K - 1, p.kc, kTileN, p.swz, true)) return 1; }
     else p.tmAk = p.tmA0;
-    p.wimg = (const float*)workspace; p.out = Y; p.bn_sums = bn_sums; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
+    p.wimg = (const float*)workspace; p.out = Y; p.pool_out = Ypool; p.bn_sums = bn_sums; p.R = R; p.Fin = Fin; p.K = K; p.Fout = Fout;
     p.ntiles = (int)((R + kTileN - 1) / kTileN);
     static bool configured = false;
     if (!configured) {

@@ -158,14 +158,16 @@ int make_tmap_f32(CUtensorMap* out, const float* base, long long cols, long long
                   int box_cols, int box_rows, int swz, bool rank3);
 
 // tensor-core contraction entry points (contract_tc.cu); return 1 when the shape is not supported
+// Ypool (may be NULL): max over every 4 consecutive rows of Y, [R/4, Fout]; Y may then be NULL (inference)
 int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
-                    double* bn_sums, void* workspace, cudaStream_t s);
+                    double* bn_sums, void* workspace, cudaStream_t s, float* Ypool = nullptr);
+int contract_fwd_tc_query(long long R, int Fin, int K, int Fout);
 int contract_bwd_data_tc(const float* dY, const float* W, float* G, long long R, int Fin, int K, int Fout,
                          void* workspace, cudaStream_t s);
 size_t contract_workspace_bytes(int Fin, int K, int Fout);
 // forward contraction with the rows on the N side of the instruction (contract_tc2.cu)
 int contract_fwd_tc_cols(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
-                         double* bn_sums, void* workspace, cudaStream_t s);
+                         double* bn_sums, void* workspace, cudaStream_t s, float* Ypool = nullptr);
 size_t colgemm_workspace_bytes(int Fin, int K);
 int contract_bwd_weight_tc(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K,
                            int Fout, cudaStream_t s);

@@ -150,7 +150,15 @@ class _ChebStage(object):
         sums = None
         if self.bn and training:
             sums = m._zeros(2 * self.Fout)
-        y = ops.contract_fwd(x, basis, W, self.K, self.Fout, sums)         # models.py:1062-1078
+        # HEALPix max-pool over 4 vertices fused into the contraction's epilogue where a tensor-core kernel takes the shape: the
+        # pooling commutes with batch norm (no scale / shift), bias and a non-decreasing activation
+        fuse_pool = (self.post and self.p == 4 and self.pool == 'max' and self.act in ops.POOL4_ACTS
+                     and ops.contract_pool4_supported(x, self.K, self.Fout))
+        ypool = None
+        if fuse_pool:
+            y, ypool = ops.contract_fwd_pool4(x, basis, W, self.K, self.Fout, sums, want_y=save)
+        else:
+            y = ops.contract_fwd(x, basis, W, self.K, self.Fout, sums)     # models.py:1062-1078
         mean = rstd = None
         count = float(B * M * m.world_size)
         if self.bn:
@@ -165,7 +173,10 @@ class _ChebStage(object):
         out = y
         if self.post:
             b = m._P.views[self.scope + '/bias'] if self.has_bias else None
-            out = ops.bn_act_pool_fwd(y, mean, rstd, b, self.p, self.pool, self.act)
+            if ypool is not None:
+                out = ops.bn_act_pool_fwd(ypool, mean, rstd, b, 1, self.pool, self.act)     # a quarter of the rows
+            else:
+                out = ops.bn_act_pool_fwd(y, mean, rstd, b, self.p, self.pool, self.act)
         if save:
             # the pooled output feeds pass 1 of the batch-norm backward (it is the next layer's input anyway)
             lean = self.post and self.bn and training and ops.bn_relu_pool_sums_supported(self.Fout, self.p, self.pool, self.act)

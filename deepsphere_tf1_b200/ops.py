@@ -246,6 +246,33 @@ def contract_fwd(x, basis, W, K, Fout, bn_sums=None):
     return y
 
 
+POOL4_ACTS = ('relu', 'identity', 'leaky_relu', 'relu6')   # non-decreasing in floating point too: pooling first is bit-identical
+USE_POOL4 = os.environ.get('DSB200_POOL4', '1') != '0'
+
+
+def contract_pool4_supported(x, K, Fout):
+    """The forward contraction can emit the max over every 4 consecutive vertices itself."""
+    B, M, Fin = x.shape
+    if not USE_POOL4 or M % 4:
+        return False
+    if x.dtype == BF16:
+        return bool(_lib_int('contract_bf16_supported', 3, B * M, Fin, K, Fout))
+    return bool(_lib_int('contract_pool4_supported', B * M, Fin, K, Fout))
+
+
+def contract_fwd_pool4(x, basis, W, K, Fout, bn_sums=None, want_y=True):
+    """(Y or None, max over 4 consecutive vertices of Y [B, M/4, Fout]) in one launch: the HEALPix max-pool fused into the
+    contraction's epilogue (models.py:1062-1078 + 1139-1142).  want_y=False (inference): Y is never written."""
+    B, M, Fin = x.shape
+    y = _new((B, M, Fout), x) if want_y else None
+    yp = _new((B, M // 4, Fout), x)
+    if x.dtype == BF16:
+        call('cheb_contract_fwd_pool4_bf16', x, basis, W, y, yp, B * M, Fin, K, Fout, bn_sums, _workspace_bf16(B * M, Fin, K, Fout, x.device))
+    else:
+        call('cheb_contract_fwd_pool4', x, basis, W, y, yp, B * M, Fin, K, Fout, bn_sums, _workspace(Fin, K, Fout, x.device))
+    return y, yp
+
+
 def contract_bwd_data(dy, W, K, Fin):
     B, M, Fout = dy.shape
     if dy.dtype == BF16:

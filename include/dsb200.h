@@ -128,6 +128,15 @@ int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const float* W, f
 /* dX_k[r, fi] = sum_fo dY[r, fo] * W[fi*K + k, fo]  -> G [K][R][Fin]  (autodiff of 1077) */
 int dsb200_cheb_contract_bwd_data(const float* dY, const float* W, float* G,
                                   long long R, int Fin, int K, int Fout, void* workspace, void* stream);
+/* The same contraction with the HEALPix max-pool over 4 consecutive vertices (models.py:1139-1142 with p = 4) fused into the
+ * epilogue: Ypool [R/4, Fout] = max over every 4 consecutive rows of Y.  tf.layers.batch_normalization without scale /
+ * shift (models.py:1197), the bias and every activation of the library are non-decreasing per feature, so
+ * pool(act(bn(y) + b)) = act(bn(pool(y)) + b): the normalise / activate pass (dsb200_bn_act_pool_fwd with p = 1) then reads a
+ * quarter of the rows.  Y may be NULL (inference: the un-pooled tensor is never written); bn_sums as above, over ALL rows.
+ * Tensor-core kernels only: dsb200_contract_pool4_supported(R, Fin, K, Fout) != 0. */
+int dsb200_cheb_contract_fwd_pool4(const float* x0, const float* xk, const float* W, float* Y, float* Ypool,
+                                   long long R, int Fin, int K, int Fout, double* bn_sums, void* workspace, void* stream);
+int dsb200_contract_pool4_supported(long long R, int Fin, int K, int Fout);
 /* `workspace` (device, 16-byte aligned, dsb200_contract_workspace_bytes(Fin, K, Fout) bytes, may be NULL):
  * scratch for the TF32 hi / lo split weight image of the tensor-core path; without it every CTA splits
  * the weights itself (slower for small layers). */
@@ -367,6 +376,9 @@ int dsb200_contract_bf16_supported(int dir, long long R, int Fin, int K, int Fou
 long long dsb200_contract_workspace_bytes_bf16(long long R, int Fin, int K, int Fout);
 int dsb200_cheb_contract_fwd_bf16(const void* x0, const void* xk, const float* W, void* Y,
                                   long long R, int Fin, int K, int Fout, double* bn_sums, void* workspace, void* stream);
+/* forward with the fused 4-vertex max-pool (see dsb200_cheb_contract_fwd_pool4): dsb200_contract_bf16_supported(3, ...) != 0 */
+int dsb200_cheb_contract_fwd_pool4_bf16(const void* x0, const void* xk, const float* W, void* Y, void* Ypool,
+                                        long long R, int Fin, int K, int Fout, double* bn_sums, void* workspace, void* stream);
 int dsb200_cheb_contract_bwd_data_bf16(const void* dY, const float* W, void* G,
                                        long long R, int Fin, int K, int Fout, void* workspace, void* stream);
 int dsb200_cheb_contract_bwd_weight_bf16(const void* x0, const void* xk, const void* dY, float* dW,

@@ -480,3 +480,33 @@ def test_fused_tile_recurrence(dev, graph, B, F, K, monomial, monkeypatch):
     lhs = float((G.double() * planes).sum())
     rhs = float((dx.double() * x.double()).sum())
     assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), float(planes.abs().max()) * float(G.abs().max())), (lhs, rhs)
+
+
+@pytest.mark.parametrize('bf16', [False, True])
+@pytest.mark.parametrize('B,M,Fin,K,Fout', [(2, 1024, 16, 5, 32), (3, 512, 32, 5, 64), (2, 256, 64, 5, 64), (1, 4096, 16, 3, 32),
+                                            (2, 1028, 32, 4, 32), (16, 65536, 16, 5, 32)])
+def test_contraction_with_the_max_pool_fused_into_the_epilogue(dev, B, M, Fin, K, Fout, bf16):
+    """dsb200_cheb_contract_fwd_pool4(_bf16): Y, the batch-norm sums and the max over every 4 consecutive vertices in one launch
+     -- bit-identical to the contraction followed by the pooling, with and without the un-pooled output."""
+    from deepsphere_tf1_b200 import ops
+    gen = torch.Generator().manual_seed(M + Fin)
+    dt = torch.bfloat16 if bf16 else torch.float32
+    x = torch.randn(K, B, M, Fin, generator=gen).to(dev).to(dt)
+    W = (torch.randn(Fin * K, Fout, generator=gen) * 0.2).to(dev)
+    x0, xk = x[0], x[1:]
+    if not ops.contract_pool4_supported(x0, K, Fout):
+        pytest.skip('no tensor-core kernel with a pooled epilogue for this shape')
+    s_ref = torch.zeros(2 * Fout, dtype=torch.float64, device=dev)
+    y_ref = ops.contract_fwd(x0, xk, W, K, Fout, s_ref)
+    p_ref = y_ref.view(B, M // 4, 4, Fout).max(dim=2).values
+    s1 = torch.zeros(2 * Fout, dtype=torch.float64, device=dev)
+    y, yp = ops.contract_fwd_pool4(x0, xk, W, K, Fout, s1, want_y=True)
+    assert torch.equal(y, y_ref) and torch.equal(yp, p_ref)
+    assert_close(s1, s_ref, 1e-12 if not bf16 else 1e-9, 'sums')
+    y2, yp2 = ops.contract_fwd_pool4(x0, xk, W, K, Fout, None, want_y=False)
+    assert y2 is None and torch.equal(yp2, p_ref)
+    # pooling first == pooling last through batch norm + bias + relu (what models.py does with the pooled tensor)
+    mean = (torch.randn(Fout, generator=gen) * 0.1).to(dev)
+    rstd = (torch.rand(Fout, generator=gen) + 0.5).to(dev)
+    bias = (torch.randn(Fout, generator=gen) * 0.1).to(dev)
+    assert torch.equal(ops.bn_act_pool_fwd(yp, mean, rstd, bias, 1, 'max', 'relu'), ops.bn_act_pool_fwd(y_ref, mean, rstd, bias, 4, 'max', 'relu'))
