@@ -124,7 +124,7 @@ __device__ __forceinline__ void warp_column_sums32(float (&v)[32], int lane)
     }
 }
 
-template <int MODE, bool SUMS>
+template <int MODE, bool SUMS, bool POOL>
 __global__ void __launch_bounds__(kBfThreads, 1)
 rowgemm_bf16_kernel(const __grid_constant__ RowGemmBfParams p)
 {
@@ -246,7 +246,7 @@ rowgemm_bf16_kernel(const __grid_constant__ RowGemmBfParams p)
                 if (MODE == BF_FWD) {
                     bf16* orow = p.out + prow * p.Nreal;
                     const bool wide = (p.Nreal & 15) == 0 && (((uintptr_t)p.out) & 31) == 0;
-                    const bool sty = p.out != nullptr;
+                    const bool sty = !POOL || p.out != nullptr;
                     for (int c0 = 0; c0 < p.Nreal; c0 += 32) {
                         float v[32];
                         tmem_ld16(tbase + c0, v);
@@ -281,7 +281,7 @@ rowgemm_bf16_kernel(const __grid_constant__ RowGemmBfParams p)
                             }
                         }
                     }
-                    if (p.pool_out) {
+                    if (POOL) {
                         // HEALPix max-pool over 4 consecutive rows, fused: batch norm without scale / shift, the bias and
                         // every activation of the library are non-decreasing per feature, so pooling the raw y first gives the same
                         // result (models.py:1235-1243) and the normalise / activate pass runs on a quarter of the rows.  A packed
@@ -388,12 +388,12 @@ static bool plan_rowgemm_bf16(int mode, long long R, int red, int planes, int nc
     return true;
 }
 
-template <int MODE, bool SUMS>
+template <int MODE, bool SUMS, bool POOL>
 static int launch_rowgemm_bf16(RowGemmBfParams& p, size_t smem, uint8_t* image, cudaStream_t s)
 {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rowgemm_bf16_kernel<MODE, SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(rowgemm_bf16_kernel<MODE, SUMS, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
@@ -402,7 +402,7 @@ static int launch_rowgemm_bf16(RowGemmBfParams& p, size_t smem, uint8_t* image, 
     pack_w_bf16_kernel<MODE><<<(total + 255) / 256, 256, 0, s>>>(p, image);
     count_launch();
     const int grid = p.ntiles < kNumSMs ? p.ntiles : kNumSMs;
-    rowgemm_bf16_kernel<MODE, SUMS><<<grid, kBfThreads, smem, s>>>(p);
+    rowgemm_bf16_kernel<MODE, SUMS, POOL><<<grid, kBfThreads, smem, s>>>(p);
     DSB_LAUNCH_CHECK();
 }
 
@@ -441,8 +441,12 @@ int contract_fwd_bf16(const bf16* x0, const bf16* xk, const float* W, bf16* Y, b
         if (make_tmap_bf16(&p.tmAk, xk, 3, dims, strides, box, pl.swz)) return 1;
     } else p.tmAk = p.tmA0;
     p.W = W; p.out = Y; p.pool_out = Ypool; p.bn_sums = bn_sums;
-    if (!bn_sums) return launch_rowgemm_bf16<BF_FWD, false>(p, pl.smem, (uint8_t*)workspace, s);
-    return launch_rowgemm_bf16<BF_FWD, true>(p, pl.smem, (uint8_t*)workspace, s);
+    if (Ypool) {
+        if (!bn_sums) return launch_rowgemm_bf16<BF_FWD, false, true>(p, pl.smem, (uint8_t*)workspace, s);
+        return launch_rowgemm_bf16<BF_FWD, true, true>(p, pl.smem, (uint8_t*)workspace, s);
+    }
+    if (!bn_sums) return launch_rowgemm_bf16<BF_FWD, false, false>(p, pl.smem, (uint8_t*)workspace, s);
+    return launch_rowgemm_bf16<BF_FWD, true, false>(p, pl.smem, (uint8_t*)workspace, s);
 }
 
 int contract_bwd_data_bf16(const bf16* dY, const float* W, bf16* G, long long R, int Fin, int K, int Fout,
@@ -463,7 +467,7 @@ int contract_bwd_data_bf16(const bf16* dY, const float* W, bf16* G, long long R,
     if (make_tmap_bf16(&p.tmA0, dY, 2, dims, strides, box, pl.swz)) return 1;
     p.tmAk = p.tmA0;
     p.W = W; p.out = G; p.pool_out = nullptr; p.bn_sums = nullptr;
-    return launch_rowgemm_bf16<BF_BWD_DATA, false>(p, pl.smem, (uint8_t*)workspace, s);
+    return launch_rowgemm_bf16<BF_BWD_DATA, false, false>(p, pl.smem, (uint8_t*)workspace, s);
 }
 
 size_t contract_workspace_bytes_bf16(long long R, int Fin, int K, int Fout)

@@ -178,7 +178,7 @@ constexpr int kMpThreads = 9 * 32;
 
 // MTW = row tiles of 16 per warp (2: 32 rows, two CTAs per SM; 4: 64 rows, one CTA per SM -- the weight fragments are then read
 // half as often per row), kMpStages stages of 8 * 16 * MTW rows.
-template <bool SUMS, int MTW, int kMpStages>
+template <bool SUMS, int MTW, int kMpStages, bool POOL>
 __device__ __forceinline__ void
 rowgemm_mma_pipe_body(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ W,
                       float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K, float* __restrict__ Ypool)
@@ -294,8 +294,8 @@ rowgemm_mma_pipe_body(const float* __restrict__ x0, const float* __restrict__ xk
 #pragma unroll
                 for (int p = 0; p < 2; ++p) {
                     const float4 o = make_float4(acc[m][2 * p][2 * h], acc[m][2 * p][2 * h + 1], acc[m][2 * p + 1][2 * h], acc[m][2 * p + 1][2 * h + 1]);
-                    if (Y != nullptr && r < R) *reinterpret_cast<float4*>(Y + r * kMmaFout + 16 * p + 4 * t) = o;
-                    if (Ypool != nullptr) {
+                    if ((!POOL || Y != nullptr) && r < R) *reinterpret_cast<float4*>(Y + r * kMmaFout + 16 * p + 4 * t) = o;
+                    if (POOL) {
                         // max-pool over 4 consecutive rows (g, g^1, g^2, g^3 = lanes 4 and 8 apart), on the raw y: it commutes with the
                         // batch norm / bias / activation that follow (non-decreasing per feature, models.py:1235-1243)
                         float4 q = o;
@@ -330,20 +330,20 @@ rowgemm_mma_pipe_body(const float* __restrict__ x0, const float* __restrict__ xk
     }
 }
 
-template <bool SUMS>
+template <bool SUMS, bool POOL>
 __global__ void __maxnreg__(112)
 rowgemm_mma_pipe_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ W,
                         float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K, float* __restrict__ Ypool)
 {
-    rowgemm_mma_pipe_body<SUMS, 2, 4>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+    rowgemm_mma_pipe_body<SUMS, 2, 4, POOL>(x0, xk, W, Y, bn_sums, R, K, Ypool);
 }
 
-template <bool SUMS>
+template <bool SUMS, bool POOL>
 __global__ void __launch_bounds__(kMpThreads, 1)
 rowgemm_mma_pipe64_kernel(const float* __restrict__ x0, const float* __restrict__ xk, const float* __restrict__ W,
                           float* __restrict__ Y, double* __restrict__ bn_sums, long long R, int K, float* __restrict__ Ypool)
 {
-    rowgemm_mma_pipe_body<SUMS, 4, 5>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+    rowgemm_mma_pipe_body<SUMS, 4, 5, POOL>(x0, xk, W, Y, bn_sums, R, K, Ypool);
 }
 
 // ---- weight gradient of the same narrow layer:  dW[fi*K + k, fo] += sum_r X_k[r, fi] dY[r, fo]   (autodiff of models.py:1077).
@@ -529,13 +529,18 @@ int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y,
         const size_t smem64 = (size_t)5 * 512 * kMmaFin * 4 + fixed;
         static bool cfg64 = false;
         if (!cfg64) {
-            cudaError_t ce = cudaFuncSetAttribute(rowgemm_mma_pipe64_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-            if (ce == cudaSuccess) ce = cudaFuncSetAttribute(rowgemm_mma_pipe64_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            cudaError_t ce = cudaFuncSetAttribute(rowgemm_mma_pipe64_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (ce == cudaSuccess) ce = cudaFuncSetAttribute(rowgemm_mma_pipe64_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (ce == cudaSuccess) ce = cudaFuncSetAttribute(rowgemm_mma_pipe64_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (ce == cudaSuccess) ce = cudaFuncSetAttribute(rowgemm_mma_pipe64_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
             if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return (int)ce; }
             cfg64 = true;
         }
-        if (bn_sums) rowgemm_mma_pipe64_kernel<true><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
-        else rowgemm_mma_pipe64_kernel<false><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+        if (Ypool) {
+            if (bn_sums) rowgemm_mma_pipe64_kernel<true, true><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+            else rowgemm_mma_pipe64_kernel<false, true><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+        } else if (bn_sums) rowgemm_mma_pipe64_kernel<true, false><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+        else rowgemm_mma_pipe64_kernel<false, false><<<grid64, kMpThreads, smem64, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
         DSB_LAUNCH_CHECK();
     }
     const long long nblk = (R + 255) / 256;
@@ -543,13 +548,18 @@ int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y,
     const size_t smem = (size_t)4 * 256 * kMmaFin * 4 + fixed;
     static bool cfg = false;
     if (!cfg) {
-        cudaError_t ce = cudaFuncSetAttribute(rowgemm_mma_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(rowgemm_mma_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaError_t ce = cudaFuncSetAttribute(rowgemm_mma_pipe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(rowgemm_mma_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(rowgemm_mma_pipe_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(rowgemm_mma_pipe_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
         if (ce != cudaSuccess) { set_error(cudaGetErrorString(ce)); return (int)ce; }
         cfg = true;
     }
-    if (bn_sums) rowgemm_mma_pipe_kernel<true><<<grid, kMpThreads, smem, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
-    else rowgemm_mma_pipe_kernel<false><<<grid, kMpThreads, smem, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+    if (Ypool) {
+        if (bn_sums) rowgemm_mma_pipe_kernel<true, true><<<grid, kMpThreads, smem, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+        else rowgemm_mma_pipe_kernel<false, true><<<grid, kMpThreads, smem, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+    } else if (bn_sums) rowgemm_mma_pipe_kernel<true, false><<<grid, kMpThreads, smem, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
+    else rowgemm_mma_pipe_kernel<false, false><<<grid, kMpThreads, smem, s>>>(x0, xk, W, Y, bn_sums, R, K, Ypool);
     DSB_LAUNCH_CHECK();
 }
 

@@ -155,7 +155,9 @@ __device__ __forceinline__ void warp_column_sums(float (&v)[32], int lane)
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 #define RG_DBG(slot, ev) do { if (p.dbg && blockIdx.x == 0 && (slot) < 256) p.dbg[(slot) * 8 + (ev)] = gtimer(); } while (0)
 
-template <int MODE, bool SUMS>
+// POOL: forward only, the epilogue also emits the max over every 4 consecutive rows (a separate instance, so that the training
+// kernels -- which keep the pooling in the batch-norm pass, see models.py -- are compiled exactly as before)
+template <int MODE, bool SUMS, bool POOL = false>
 __global__ void __launch_bounds__(kRgThreads, 2)
 rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
 {
@@ -351,7 +353,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
             const bool ok = row < p.R && !p.nostore;
             if (MODE == MODE_FWD) {
                 float* orow = p.out + row * p.Fout;
-                const bool sty = p.out != nullptr;
+                const bool sty = !POOL || p.out != nullptr;
                 const bool wide8 = (p.Fout & 7) == 0 && (p.n0 & 7) == 0 && ((uintptr_t)p.out & 31) == 0;
                 for (int c0 = 0; c0 < p.Nreal; c0 += 32) {
                     float v[32];
@@ -374,7 +376,7 @@ rowgemm_tc_kernel(const __grid_constant__ RowGemmParams p)
 #pragma unroll
                         for (int i = 16; i < 32; ++i) v[i] = 0.f;
                     }
-                    if (p.pool_out) {
+                    if (POOL) {
                         // HEALPix max-pool over 4 consecutive rows = 4 neighbouring lanes, on the raw y: batch norm without scale /
                         // shift, the bias and the activations are non-decreasing per feature, so the pooling commutes with them
                         // (models.py:1235-1243); the normalise / activate pass then reads a quarter of the rows
@@ -619,12 +621,12 @@ static int rowgemm_max_ctas()
     return cached;
 }
 
-template <int MODE, bool SUMS>
+template <int MODE, bool SUMS, bool POOL = false>
 static int launch_rowgemm(RowGemmParams& p, size_t smem, int ctas, float* image, cudaStream_t s)
 {
     static bool configured = false;                // per template instance
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(rowgemm_tc_kernel<MODE, SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(rowgemm_tc_kernel<MODE, SUMS, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
@@ -642,7 +644,7 @@ static int launch_rowgemm(RowGemmParams& p, size_t smem, int ctas, float* image,
     }
     const int slots = kNumSMs * ctas;
     const int grid = p.ntiles < slots ? p.ntiles : slots;
-    rowgemm_tc_kernel<MODE, SUMS><<<grid, kRgThreads, smem, s>>>(p);
+    rowgemm_tc_kernel<MODE, SUMS, POOL><<<grid, kRgThreads, smem, s>>>(p);
     DSB_LAUNCH_CHECK();
 }
 
@@ -682,6 +684,10 @@ int contract_fwd_tc(const float* x0, const float* xk, const float* W, float* Y, 
     p.nstages = pl.nstages; p.acc_stages = pl.acc_stages; p.wstream = pl.wstream;
     p.ntiles = (int)((R + kTileM - 1) / kTileM);
     float* image = (float*)workspace;
+    if (Ypool) {
+        if (!bn_sums) return launch_rowgemm<MODE_FWD, false, true>(p, pl.smem, pl.ctas, image, s);
+        return launch_rowgemm<MODE_FWD, true, true>(p, pl.smem, pl.ctas, image, s);
+    }
     if (!bn_sums) return launch_rowgemm<MODE_FWD, false>(p, pl.smem, pl.ctas, image, s);
     return launch_rowgemm<MODE_FWD, true>(p, pl.smem, pl.ctas, image, s);
 }

@@ -57,7 +57,7 @@ colgemm_pack_kernel(const float* __restrict__ W, float* __restrict__ image, int 
     }
 }
 
-template <bool SUMS>
+template <bool SUMS, bool POOL>
 __global__ void __launch_bounds__(kCgThreads, 2)
 colgemm_tc_kernel(const __grid_constant__ ColGemmParams p)
 {
@@ -201,10 +201,10 @@ colgemm_tc_kernel(const __grid_constant__ ColGemmParams p)
                         const float mine = odd ? o : e;
                         const long long r = row0 + c0 + i + odd;
                         if (fo < p.Fout && r < p.R) {
-                            if (p.out) p.out[r * p.Fout + fo] = mine;
+                            if (!POOL || p.out) p.out[r * p.Fout + fo] = mine;
                             if (SUMS) { s1 += mine; s2 = fmaf(mine, mine, s2); }
                         }
-                        if (p.pool_out) {
+                        if (POOL) {
                             // max-pool over the 4 consecutive rows c0+i-2 .. c0+i+1 (i = 2 mod 4): this lane holds two of them (in
                             // `pm` and `mine`), its partner the other two; the pooling commutes with the batch norm / bias /
                             // activation that follow (all non-decreasing per feature, models.py:1235-1243)
@@ -273,8 +273,10 @@ int contract_fwd_tc_cols(const float* x0, const float* xk, const float* W, float
     p.ntiles = (int)((R + kTileN - 1) / kTileN);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(colgemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(colgemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(colgemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(colgemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(colgemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(colgemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
@@ -283,8 +285,11 @@ int contract_fwd_tc_cols(const float* x0, const float* xk, const float* W, float
     count_launch();
     const int slots = kNumSMs * ctas;
     const int grid = p.ntiles < slots ? p.ntiles : slots;
-    if (bn_sums) colgemm_tc_kernel<true><<<grid, kCgThreads, smem, s>>>(p);
-    else colgemm_tc_kernel<false><<<grid, kCgThreads, smem, s>>>(p);
+    if (Ypool) {
+        if (bn_sums) colgemm_tc_kernel<true, true><<<grid, kCgThreads, smem, s>>>(p);
+        else colgemm_tc_kernel<false, true><<<grid, kCgThreads, smem, s>>>(p);
+    } else if (bn_sums) colgemm_tc_kernel<true, false><<<grid, kCgThreads, smem, s>>>(p);
+    else colgemm_tc_kernel<false, false><<<grid, kCgThreads, smem, s>>>(p);
     DSB_LAUNCH_CHECK();
 }
 

@@ -151,9 +151,12 @@ class _ChebStage(object):
         if self.bn and training:
             sums = m._zeros(2 * self.Fout)
         # HEALPix max-pool over 4 vertices fused into the contraction's epilogue where a tensor-core kernel takes the shape: the
-        # pooling commutes with batch norm (no scale / shift), bias and a non-decreasing activation
+        # pooling commutes with batch norm (no scale / shift), bias and a non-decreasing activation.  Used when the
+        # un-pooled tensor is not needed afterwards (inference: it is never written).  While training, the batch-norm backward
+        # needs y anyway and the epilogues of these kernels are what bounds them: measured inside the cosmo step, the pooled
+        # epilogue costs the three forward kernels +35 us and saves 18 us of the normalise pass (profiles/r02_trace_step_pool4.txt)
         fuse_pool = (self.post and self.p == 4 and self.pool == 'max' and self.act in ops.POOL4_ACTS
-                     and ops.contract_pool4_supported(x, self.K, self.Fout))
+                     and (not save or ops.POOL4_TRAIN) and ops.contract_pool4_supported(x, self.K, self.Fout))
         ypool = None
         if fuse_pool:
             y, ypool = ops.contract_fwd_pool4(x, basis, W, self.K, self.Fout, sums, want_y=save)

@@ -248,6 +248,7 @@ def contract_fwd(x, basis, W, K, Fout, bn_sums=None):
 
 POOL4_ACTS = ('relu', 'identity', 'leaky_relu', 'relu6')   # non-decreasing in floating point too: pooling first is bit-identical
 USE_POOL4 = os.environ.get('DSB200_POOL4', '1') != '0'
+POOL4_TRAIN = os.environ.get('DSB200_POOL4_TRAIN', '0') == '1'   # also while training (slower: see models._ChebStage.forward)
 
 
 def contract_pool4_supported(x, K, Fout):

