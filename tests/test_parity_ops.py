@@ -502,7 +502,7 @@ def test_contraction_with_the_max_pool_fused_into_the_epilogue(dev, B, M, Fin, K
     s1 = torch.zeros(2 * Fout, dtype=torch.float64, device=dev)
     y, yp = ops.contract_fwd_pool4(x0, xk, W, K, Fout, s1, want_y=True)
     assert torch.equal(y, y_ref) and torch.equal(yp, p_ref)
-    assert_close(s1, s_ref, 1e-12 if not bf16 else 1e-9, 'sums')
+    assert_close(s1, s_ref, 1e-6, 'sums')                             # float partial sums, added in launch-dependent order
     y2, yp2 = ops.contract_fwd_pool4(x0, xk, W, K, Fout, None, want_y=False)
     assert y2 is None and torch.equal(yp2, p_ref)
     # pooling first == pooling last through batch norm + bias + relu (what models.py does with the pooled tensor)
