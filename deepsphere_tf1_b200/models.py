@@ -16,7 +16,8 @@ Differences from the reference that a user sees (also listed in DESIGN.md):
   * `tf_dataset` may be any Python iterator of `(data, labels)` batches;
   * checkpoints are `torch.save` files `checkpoints/<dir_name>/model-<step>.pt` keyed by the
     reference's variable names (`conv1/weights`, `conv1/batch_normalization/moving_mean`, ...);
-  * `extra_loss`, equiangular sampling: NotImplementedError (outside the hot path).
+  * `extra_loss` (triplet loss): NotImplementedError -- upstream passes the rank-3 descriptor to a rank-2 loss (models.py:768-769,
+    1247), it cannot run as committed; equiangular grids: square, power-of-two side, on the in-repo 8-neighbour graph;
     `conv='monomials'`, `weighted=True`, `statistics='histogram'` and `dropFilt < 1` are supported.
 """
 import glob
@@ -859,7 +860,16 @@ class cgcnn(base_model):
         self.dropFilt = float(dropFilt)
         self.weighted = bool(weighted)
         if self.sampling == 'equiangular':
-            raise NotImplementedError('equiangular sampling is outside the hot path')
+            # 2-D pooling of the (colatitude, longitude) grid with a sqrt(p) x sqrt(p) window (models.py:1131-1136, 1150-1155).
+            # Here the vertices of every level are kept in Z (Morton) order of their grid position, so that a window is p
+            # CONSECUTIVE vertices and every kernel of the HEALPix path (pooling, fused epilogues, tile plans) applies unchanged;
+            # inputs, dense outputs and descriptors are permuted at the boundary (`_equi_gather`).
+            if getattr(self, 'ratio', 1.) != 1.:
+                raise NotImplementedError('equiangular grids with different bandwidths in latitude and longitude')
+            if vertex_shard:
+                raise NotImplementedError('vertex_shard=True is a HEALPix mode')
+            if dense and pool == 'max' and (np.asarray(p) > 1).any():
+                raise NotImplementedError('unpooling max with equiangular sampling is not yet implemented')   # models.py:1367
         # dtype: upstream it only casts the Laplacians (models.py:1047).  Here 'bfloat16' selects the BF16 mode of the ChebConv
         # layers (activations stored as bfloat16, fp32 arithmetic and accumulation; include/dsb200.h, "BF16 mode"); the
         # Laplacians, the weights and the statistics stay float32 either way.
@@ -944,6 +954,37 @@ class cgcnn(base_model):
             self._bn_buf[scope] = (torch.empty(F, device=self.device), torch.empty(F, device=self.device))
         return self._bn_buf[scope]
 
+    def _equi_perm(self, M):
+        """(perm, inv) of a square equiangular grid of M vertices: perm[k] = row-major index of the k-th vertex in Z (Morton)
+        order; inv[perm[k]] = k.  Cached per size, with int32 device copies."""
+        cache = self.__dict__.setdefault('_equi_perms', {})
+        if M not in cache:
+            n = int(round(M ** 0.5))
+            if n * n != M or n & (n - 1):
+                raise NotImplementedError('equiangular grids need a power-of-two side (got {} vertices)'.format(M))
+            k = np.arange(M, dtype=np.int64)
+            i = np.zeros(M, np.int64)
+            j = np.zeros(M, np.int64)
+            for b in range(max(1, n.bit_length() - 1)):
+                j |= ((k >> (2 * b)) & 1) << b
+                i |= ((k >> (2 * b + 1)) & 1) << b
+            perm = i * n + j
+            inv = np.empty(M, np.int64)
+            inv[perm] = k
+            cache[M] = (perm, inv, {})
+        return cache[M]
+
+    def _equi_gather(self, x, inverse=False):
+        """x [B, M, F] -> out[b, k] = x[b, perm[k]] (row-major -> Z order) or, inverse, out[b, v] = x[b, inv[v]] (back)."""
+        B, M, F = x.shape
+        perm, inv, dev = self._equi_perm(M)
+        key = (B, bool(inverse))
+        if key not in dev:
+            src = inv if inverse else perm
+            idx = (np.arange(B, dtype=np.int64)[:, None] * M + src[None, :]).reshape(-1)
+            dev[key] = torch.from_numpy(idx.astype(np.int32)).to(self.device)
+        return ops.gather_rows(x.reshape(B * M, F), dev[key]).view(B, M, F)
+
     def _graph_for(self, i):
         """Device copy of Laplacian level i; identical consecutive levels share one copy."""
         if i in self._graphs:
@@ -962,7 +1003,11 @@ class cgcnn(base_model):
             # HEALPix geometry of the level (nside, nested pixel numbers) when `deepsphere` built the graphs: lets the
             # fused tile recurrence (csrc/cheb_tile.cu) address the vertices as pixel squares
             nested = getattr(self, '_nested', None)
-            self._graphs[i] = DeviceGraph(self.L[i], self.device, nested=nested[i] if nested else None)
+            Li = self.L[i]
+            if self.sampling == 'equiangular':               # vertices in Z order (see __init__)
+                perm = self._equi_perm(Li.shape[0])[0]
+                Li = Li.tocsr()[perm][:, perm].tocoo()
+            self._graphs[i] = DeviceGraph(Li, self.device, nested=nested[i] if nested else None)
         return self._graphs[i]
 
     def _build_program(self, seed):
@@ -1162,6 +1207,9 @@ class cgcnn(base_model):
     def _forward(self, x, training, save):
         """`_inference` (+ `_decoder`): returns (logits, descriptor) (models.py:1219-1344)."""
         self._input = x                                    # the masked loss reads its last two channels
+        equi = self.sampling == 'equiangular'
+        if equi:
+            x = self._equi_gather(ops.to_f32(x))
         skips = [x]
         for st in self._encoder:
             x = st.forward(x, training, save)
@@ -1169,6 +1217,10 @@ class cgcnn(base_model):
                 skips.append(x)
         x = ops.to_f32(x)                                  # BF16 mode: everything outside the ChebConv layers is fp32
         descriptor = x
+        if equi:
+            descriptor = self._equi_gather(x, inverse=True)     # the reference's vertex order
+            if not self._has_decoder:
+                x = descriptor                                  # ... also for the statistics / the flattened head
         B = x.shape[0]
         self._stat_saved = None
         if self.statistics == 'histogram':
@@ -1208,6 +1260,8 @@ class cgcnn(base_model):
                     x = ops.concat_f(ops.to_f32(x), ops.to_f32(skips[j]))
                 x = de.forward(x, training, save)
             x = ops.to_f32(self._outconv.forward(x, training, save))
+            if equi:
+                x = self._equi_gather(x, inverse=True)
         return x, descriptor
 
     def _backward(self, dlogits):
@@ -1215,7 +1269,10 @@ class cgcnn(base_model):
         n_enc = len(self._encoder)
         skip_grads = {}                                    # encoder skip index -> gradient from the decoder
         d = dlogits
+        equi = self.sampling == 'equiangular'
         if self._has_decoder:
+            if equi:
+                d = self._equi_gather(d.contiguous())
             d = self._outconv.backward(d)
             for up, de, j in reversed(self._decoder):
                 d = de.backward(d)
@@ -1244,6 +1301,8 @@ class cgcnn(base_model):
             d = ops.stat_bwd(self._stat_saved[0], d, self.statistics)
         elif self.M:
             d = d.reshape(self._stat_saved[0])
+        if equi and not self._has_decoder:
+            d = self._equi_gather(ops.to_f32(d).contiguous())    # adjoint of the un-permutation in _forward
         # encoder: stage k produced skips[k + 1] (when it has a post chain)
         for k in range(n_enc - 1, -1, -1):
             st = self._encoder[k]

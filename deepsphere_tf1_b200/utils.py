@@ -104,6 +104,53 @@ def healpix_laplacian(nside=16, nest=True, lap_type='normalized', indexes=None, 
     return build_laplacian(W, lap_type=lap_type)
 
 
+def equiangular_weightmatrix(bw=64, indexes=None, dtype=np.float32):
+    """8-neighbour graph of the SOFT equiangular grid of bandwidth bw (2bw x 2bw vertices, row-major in (colatitude, longitude)),
+    weights 1 / squared chord distance (upstream utils.py:136-229, the only equiangular graph that is fully in the reference's
+    repository; its neighbour functions wrap the longitude and cross the poles by half a turn).  Vectorised; same float32
+    arithmetic and the same entry order as upstream (neighbours SW, W, NW, N, NE, E, SE, S), so the CSR matrix is bit-identical."""
+    if indexes is not None:
+        raise NotImplementedError('equiangular_weightmatrix: partial grids are not supported (upstream builds a full-size matrix)')
+    n = 2 * bw
+    npix = n * n
+    beta = np.pi * (2 * np.arange(n) + 1) / (4. * bw)          # SOFT
+    alpha = np.arange(n) * np.pi / bw
+    theta, phi = np.meshgrid(beta, alpha, indexing='ij')
+    ct, st, cp, sp = np.cos(theta), np.sin(theta), np.cos(phi), np.sin(phi)
+    coords = np.vstack([(st * cp).flatten(), (st * sp).flatten(), ct.flatten()]).transpose()
+    coords = np.asarray(coords, dtype=dtype)
+    ind = np.arange(npix, dtype=np.int64)
+
+    def south(x):
+        return np.where(x >= npix - n, (x + bw) % n + npix - n, x + n)
+
+    def north(x):
+        return np.where(x < n, (x + bw) % n, x - n)
+
+    def west(x):
+        return np.where(x % n == 0, x + n, x) - 1
+
+    def east(x):
+        return np.where(x % n == n - 1, x - n, x) + 1
+
+    w, e = west(ind), east(ind)
+    nb = np.stack([south(w), w, north(w), north(ind), north(e), e, south(e), south(ind)], axis=1)
+    col_index = nb.reshape(-1)
+    row_index = np.repeat(ind, 8)
+    distances = np.sum((coords[row_index] - coords[col_index])**2, axis=1)
+    weights = 1 / distances
+    return sparse.csr_matrix((weights, (row_index, col_index)), shape=(npix, npix), dtype=dtype)
+
+
+def equiangular_laplacian(bw=16, lap_type='normalized', indexes=None, dtype=np.float32, use_4=False):
+    """Laplacian of the equiangular graph.  Upstream (utils.py:344-361) takes it from the absent PyGSP fork's
+    SphereEquiangular(bandwidth, sampling='SOFT'), whose neighbourhood and weights are not pinned anywhere in the reference;
+    this is the in-repository construction its commented-out lines name: equiangular_weightmatrix + build_laplacian."""
+    if use_4:
+        raise NotImplementedError()
+    return build_laplacian(equiangular_weightmatrix(bw=bw, indexes=indexes, dtype=dtype), lap_type=lap_type)
+
+
 def rescale_L(L, lmax=2, scale=1):
     """Rescale the Laplacian eigenvalues to [-scale, scale]:  L / (lmax/2) - I."""
     M, M = L.shape
@@ -140,6 +187,8 @@ def build_laplacians(nsides, indexes=None, use_4=False, sampling='healpix', std=
     built = 0
     for i, (nside, index, sigma, mat) in enumerate(zip(nsides, indexes, std, full)):
         if isinstance(nside, tuple):
+            if sampling == 'equiangular' and nside[0] != nside[1]:
+                raise NotImplementedError('equiangular grids with different bandwidths in latitude and longitude')
             nside = nside[0]
         if i > 0 and sampling != 'icosahedron':
             p.append((nside_last // nside)**2)
@@ -155,7 +204,7 @@ def build_laplacians(nsides, indexes=None, use_4=False, sampling='healpix', std=
                 from . import graphs
                 laplacian = graphs.icosahedron_laplacian(order=nside, indexes=index)    # utils.py:370-376, 412
             elif sampling == 'equiangular':
-                raise NotImplementedError('equiangular sampling needs the PyGSP fork (out of scope)')
+                laplacian = equiangular_laplacian(bw=nside, indexes=index, use_4=use_4)       # utils.py:415-416
             else:
                 raise ValueError('Unknown sampling: ' + sampling)
             lm = estimate_lmax(laplacian) if lmax is None else lmax[built]

@@ -129,7 +129,12 @@ def pool(x, p, kind, sampling):
     SAME padding, M divisible by p); icosahedron = keep the first p vertices."""
     if p > 1:
         if sampling == 'equiangular':
-            raise NotImplementedError('equiangular pooling is out of scope (SURVEY section 2)')
+            # models.py:1131-1136, 1150-1155: the vertices as a [sqrt(M/ratio), sqrt(M*ratio)] grid (ratio = 1 here), 2-D pooling
+            # with a sqrt(p) x sqrt(p) window, SAME padding (sizes divisible by the window)
+            N, M, F = x.shape
+            H, s = int(round(M ** 0.5)), int(round(p ** 0.5))
+            xr = x.reshape(N, H // s, s, H // s, s, F)
+            return (xr.amax(dim=(2, 4)) if kind == 'max' else xr.mean(dim=(2, 4))).reshape(N, -1, F)
         if sampling == 'icosahedron':
             return x[:, :p, :]
         N, M, F = x.shape
@@ -143,8 +148,10 @@ def unpool(x, p, kind, sampling):
     p vertices with the constant 1; max: healpix puts the value first and p-1 zeros."""
     N, M, F = x.shape
     if kind == 'average':
-        if sampling == 'equiangular':
-            raise NotImplementedError('equiangular unpooling is out of scope')
+        if sampling == 'equiangular':                                                  # (1348-1355): repeat_elements on both axes
+            H, s = int(round(M ** 0.5)), int(round(p ** 0.5))
+            xr = x.reshape(N, H, H, F).repeat_interleave(s, dim=1).repeat_interleave(s, dim=2)
+            return xr.reshape(N, -1, F)
         if sampling == 'icosahedron':
             return TF.pad(x, (0, 0, 0, int(p - M)), mode='constant', value=1.0)   # (1358)
         return x.unsqueeze(2).repeat(1, 1, p, 1).reshape(N, M * p, F)             # (1363-1364)

@@ -117,6 +117,11 @@ def main():
     L = utils.build_laplacian(W, 'normalized')
     Lr = utils.rescale_L(L.copy(), lmax=np.float32(1.93))
     out.update(_csr_parts(Lr, 'rescale4'))
+    # equiangular (SOFT) 8-neighbour graph, the only equiangular construction that is fully in the reference's repository
+    for bw in (2, 4, 8):
+        W = utils.equiangular_weightmatrix(bw=bw, dtype=np.float32)
+        out.update(_csr_parts(W, 'equi%d_W' % bw))
+        out.update(_csr_parts(utils.build_laplacian(W, lap_type='normalized'), 'equi%d_Lnorm' % bw))
     np.savez_compressed(os.path.join(HERE, 'graph_golden.npz'), **out)
 
     # dataset protocol (deepsphere/data.py): deterministic (shuffle=False) iterators

@@ -182,6 +182,23 @@ def main():
     x = rs.randn(4, 48, 1).astype(np.float32)
     run_case(ref_models, 'dropouts', out, kw, x, rs.randint(0, 2, 4), True, sphere=sphere)
 
+    # I. equiangular conventions: 2-D pooling of the (colatitude, longitude) grid with a sqrt(p) x sqrt(p) window and the
+    #    repeat_elements unpooling (models.py:1131-1136, 1150-1155, 1348-1355), on the reference's own in-repository equiangular
+    #    graph (utils.equiangular_weightmatrix + build_laplacian; the fork's SphereEquiangular is absent)
+    def equi_L(bw):
+        Lq = ref_utils.build_laplacian(ref_utils.equiangular_weightmatrix(bw=bw, dtype=np.float32), 'normalized')
+        return sparse.coo_matrix(ref_utils.rescale_L(sparse.csr_matrix(Lq), lmax=np.float32(2.0)), dtype=np.float32)
+    Ls = [equi_L(8), equi_L(4), equi_L(2)]
+    kw = dict(F=[4, 6, 3], K=[3, 3, 2], batch_norm=[True, True, False], M=[], pool='max', statistics='mean', num_feat_in=2)
+    x = rs.randn(2, 256, 2).astype(np.float32)
+
+    # (run_case builds the model through cgcnn.__new__: give the class the attribute deepsphere.__init__ would set)
+    ref_models.cgcnn.ratio = 1.
+    run_case(ref_models, 'equi_max', out, kw, x, rs.randint(0, 3, 2), True, L=Ls, p=[4, 4, 1], sampling='equiangular')
+    kw = dict(F=[4, 5, 3], K=[3, 2, 2], batch_norm=[True, False, True], M=[], pool='average', dense=True, Fseg=3, num_feat_in=2)
+    Ls = [equi_L(8), equi_L(4), equi_L(4)]
+    run_case(ref_models, 'equi_dense', out, kw, x, rs.randint(0, 3, (2, 256)), True, L=Ls, p=[4, 1, 1], sampling='equiangular')
+
     np.savez_compressed(os.path.join(HERE, 'ops_golden.npz'), **out)
     print('wrote', os.path.join(HERE, 'ops_golden.npz'), os.path.getsize(os.path.join(HERE, 'ops_golden.npz')), 'bytes')
 

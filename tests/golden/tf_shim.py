@@ -406,12 +406,27 @@ def _pool_windows(x, ksize, strides, padding, fill):
     return x.reshape(N, Hp // p, p, Wd, C), H, p
 
 
+def _pool2d(x, ksize, strides, padding, kind):
+    """NHWC, square window s x s with stride s over H and W, sizes divisible by s (the reference's equiangular pooling,
+    models.py:1131-1136, 1150-1155: ksize=[1, p**0.5, p**0.5, 1])."""
+    assert padding == 'SAME' and list(ksize) == list(strides) and ksize[0] == ksize[3] == 1 and ksize[1] == ksize[2]
+    s = int(ksize[1])
+    N, H, Wd, C = x.shape
+    assert H % s == 0 and Wd % s == 0
+    w = x.reshape(N, H // s, s, Wd // s, s, C)
+    return w.amax(dim=(2, 4)) if kind == 'max' else w.mean(dim=(2, 4))
+
+
 def _max_pool(x, ksize, strides, padding):
+    if ksize[2] != 1:
+        return _pool2d(x, ksize, strides, padding, 'max')
     w, _, _ = _pool_windows(x, ksize, strides, padding, float('-inf'))
     return w.max(dim=2).values
 
 
 def _avg_pool(x, ksize, strides, padding):
+    if ksize[2] != 1:
+        return _pool2d(x, ksize, strides, padding, 'avg')
     w, H, p = _pool_windows(x, ksize, strides, padding, 0.0)
     n = torch.full((w.shape[1],), float(p))
     if H % p:
@@ -490,4 +505,11 @@ def install():
     for n in names:
         sys.modules[n] = types.ModuleType(n)
     sys.modules[names[-1]].triplet_semihard_loss = None
+    # tensorflow.keras.backend.repeat_elements (equiangular unpooling, models.py:1349-1355)
+    keras = types.ModuleType('tensorflow.keras')
+    keras.backend = types.ModuleType('tensorflow.keras.backend')
+    keras.backend.repeat_elements = lambda t, rep, axis: torch.repeat_interleave(t, int(rep), dim=axis)
+    me.keras = keras
+    sys.modules['tensorflow.keras'] = keras
+    sys.modules['tensorflow.keras.backend'] = keras.backend
     return me

@@ -166,3 +166,37 @@ def test_cosmo_patch_is_a_square_grid():
     deg = np.diff(W.indptr)
     assert (deg == 3).sum() == 4 and (deg == 5).sum() == 4 * (n - 2) and (deg == 8).sum() == (n - 2)**2
     assert abs(W - W.T).max() < 1e-7
+
+
+@pytest.mark.parametrize('bw', [2, 4, 8])
+def test_equiangular_graph_bit_exact(bw):
+    """utils.equiangular_weightmatrix (vectorised) against the reference's own loop (upstream utils.py:136-229)."""
+    W = putils.equiangular_weightmatrix(bw=bw, dtype=np.float32)
+    assert_same(W, 'equi%d_W' % bw)
+    assert_same(putils.build_laplacian(W, 'normalized'), 'equi%d_Lnorm' % bw)
+    n = 2 * bw
+    A = sparse.csr_matrix(W)
+    assert A.shape == (n * n, n * n) and (abs(A - A.T) > 1e-6 * abs(A).max()).nnz == 0      # the neighbour relation is symmetric
+    if bw >= 4:                                                     # (bw = 1 is degenerate: coincident neighbours, infinite weights)
+        L, p = putils.build_laplacians([bw, bw // 2, bw // 2], sampling='equiangular')
+        assert p == [4, 1] and [l.shape[0] for l in L] == [n * n, n * n // 4]
+
+
+def test_equiangular_z_order_makes_2d_windows_consecutive():
+    """models.cgcnn._equi_perm: in Z order every sqrt(p) x sqrt(p) window of the grid is p consecutive vertices, at every level."""
+    from deepsphere_tf1_b200 import models
+    m = models.cgcnn.__new__(models.cgcnn)
+    for n in (2, 4, 16):
+        perm, inv, _ = m._equi_perm(n * n)
+        assert sorted(perm) == list(range(n * n)) and (inv[perm] == np.arange(n * n)).all()
+        i, j = perm // n, perm % n
+        for s in (2, 4):
+            if s > n:
+                continue
+            blk = (i // s) * (n // s) + (j // s)
+            g = blk.reshape(-1, s * s)
+            assert (g == g[:, :1]).all()
+            # ... and the windows themselves are in the Z order of the coarser grid
+            pc, _, _ = m._equi_perm((n // s) ** 2) if n // s > 1 else (np.zeros(1, np.int64), None, None)
+            if n // s > 1:
+                assert (g[:, 0] == pc).all()

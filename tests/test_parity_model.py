@@ -439,3 +439,32 @@ def test_masked_dense_regression():
     x[..., -2:] = (rs.rand(4, 300, 2) > 0.3).astype(np.float32)
     labels = rs.randn(4, 300).astype(np.float32)
     _check_step(oracle, model, x, labels, opt=opt)
+
+
+@pytest.mark.parametrize('head', ['mean', 'flatten_fc', 'dense'])
+def test_equiangular_grid_2d_pooling(head):
+    """sampling='equiangular' (models.py:1131-1136, 1150-1155, 1348-1355): 2-D pooling / unpooling of the (colatitude, longitude)
+    grid.  The product keeps the vertices in Z order and pools consecutive vertices; inputs, descriptors, the flattened head
+    and dense outputs are in the reference's row-major order, which this test pins against the oracle."""
+    from deepsphere_tf1_b200 import utils
+    L, p = utils.build_laplacians([8, 4, 2, 2], sampling='equiangular')
+    assert p == [4, 4, 1] and [l.shape[0] for l in L] == [256, 64, 16]
+    rs = np.random.RandomState(5)
+    x = rs.randn(3, 256, 2).astype(np.float32)
+    if head == 'dense':
+        kw = dict(F=[6, 8, 4], K=[3, 3, 2], p=p, batch_norm=[True, True, False], M=[], pool='average', dense=True, Fseg=3,
+                  num_feat_in=2)
+        labels = rs.randint(0, 3, size=(3, 256)).astype(np.int32)
+        mom, opt = _momentum()
+        kw.update(mom)
+    elif head == 'flatten_fc':
+        kw = dict(F=[6, 8], K=[3, 3], p=p[:2], batch_norm=[True, True], M=[12, 3], pool='max', statistics=None, num_feat_in=2)
+        labels = rs.randint(0, 3, size=3).astype(np.int32)
+        opt = None
+        L = L[:2]
+    else:
+        kw = dict(F=[6, 8, 3], K=[3, 3, 2], p=p, batch_norm=[True, True, False], M=[], pool='max', statistics='mean', num_feat_in=2)
+        labels = rs.randint(0, 3, size=3).astype(np.int32)
+        opt = None
+    oracle, model = _pair(L, sampling='equiangular', batch_size=3, **kw)
+    _check_step(oracle, model, x, labels.astype(np.int64) if head != 'dense' else labels.astype(np.int64), opt=opt)
