@@ -5,8 +5,8 @@
 //   dW[fi*K + k, fo] = sum_r X_k[r, fi] * dY[r, fo]
 // Rows are (sample, vertex) pairs of the [B, M, F] layout; the K Chebyshev orders are K
 // separate [R, Fin] planes (never concatenated / transposed as the reference does at 1062-1064).
-// FP32 FFMA register-tiled kernels (exact-precision path); the tcgen05 path lives in
-// contract_tc.cu.
+// This file: the dispatch of the three entry points and the small-reduction kernels of the input layer.  The tensor-core
+// kernels live in contract_tc.cu / contract_tc2.cu / contract_mma.cu, the general fp32 FFMA GEMM (any shape) in contract_ffma.cu.
 #include "common.cuh"
 #include <stdlib.h>
 #include "tc_common.cuh"
@@ -14,8 +14,6 @@
 
 namespace dsb200 {
 
-constexpr int BM = 128, BN = 64, BK = 16;      // CTA tile; 256 threads, 8x4 outputs per thread
-constexpr int PADM = BM + 4, PADN = BN + 4;
 
 // Planar operand: logical column q of a [R, P*Fw] matrix lives in plane q / Fw (plane 0 at p0,
 // planes >= 1 at pk + (plane-1)*R*Fw) at column q % Fw.
@@ -28,165 +26,6 @@ struct Planar {
         return plane == 0 ? p0 : pk + (long long)(plane - 1) * plane_stride;
     }
 };
-
-// C[r, n] = sum_q A[r, q] * Bm[q, n]
-//  FWD : A planar (X_k, Fw = Fin, Q = K*Fin, q = k*Fin + fi); Bm[q, n] = W[(fi*K + k)*Fout + n];
-//        C = Y [R, Fout]; optional batch-norm sums in the epilogue.
-//  BWD : A = dY [R, Fout] (Q = Fout); n = k*Fin + fi; Bm[q, n] = W[(fi*K + k)*Fout + q];
-//        C planar (G_k [R, Fin]).
-template <bool BWD>
-__global__ void __launch_bounds__(256)
-contract_kernel(Planar A, const float* __restrict__ W, float* __restrict__ Cout,
-                long long R, int Fin, int K, int Fout, int Q, int N, double* __restrict__ bn_sums)
-{
-    __shared__ __align__(16) float As[BK][PADM];
-    __shared__ __align__(16) float Bs[BK][PADN];
-    __shared__ float red[2][BN];
-
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;              // 16 x 16 threads
-    const long long r0 = (long long)blockIdx.x * BM;
-    const int n0 = blockIdx.y * BN;
-    const int Aw = A.Fw;                                   // width of one A plane
-
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    const bool a_vec = (Aw % 4 == 0);
-    for (int q0 = 0; q0 < Q; q0 += BK) {
-        // ---- A tile: BM rows x BK columns -> As[kk][row]
-        if (a_vec) {
-            // 512 float4 per tile: thread loads 2 (rows i and i+64)
-            const int kq = (tid & 3) * 4;
-            const int q = q0 + kq;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = (tid >> 2) + h * 64;
-                const long long r = r0 + i;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < R && q < Q) {
-                    const int plane = q / Aw, f = q - plane * Aw;
-                    v = ldg4(A.at(plane) + r * Aw + f);
-                }
-                As[kq + 0][i] = v.x; As[kq + 1][i] = v.y; As[kq + 2][i] = v.z; As[kq + 3][i] = v.w;
-            }
-        } else {
-            const int kk = tid & 15;
-            const int q = q0 + kk;
-            int plane = 0, f = 0;
-            if (q < Q) { plane = q / Aw; f = q - plane * Aw; }
-            const float* ap = A.at(plane);
-#pragma unroll
-            for (int h = 0; h < 8; ++h) {
-                const int i = (tid >> 4) + h * 16;
-                const long long r = r0 + i;
-                As[kk][i] = (r < R && q < Q) ? __ldg(ap + r * Aw + f) : 0.f;
-            }
-        }
-        // ---- B tile: BK x BN -> Bs[kk][n]
-        {
-            const int kk = tid >> 4;
-            const int nn = (tid & 15) * 4;
-            const int q = q0 + kk;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (q < Q) {
-                if (!BWD) {
-                    const int k = q / Fin, fi = q - k * Fin;
-                    const float* wp = W + ((long long)fi * K + k) * Fout + n0 + nn;
-                    if ((Fout % 4 == 0) && n0 + nn + 3 < N) {
-                        const float4 t = ldg4(wp);
-                        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) if (n0 + nn + j < N) v[j] = __ldg(wp + j);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int n = n0 + nn + j;
-                        if (n < N) {
-                            const int k = n / Fin, fi = n - k * Fin;
-                            v[j] = __ldg(W + ((long long)fi * K + k) * Fout + q);
-                        }
-                    }
-                }
-            }
-            *reinterpret_cast<float4*>(&Bs[kk][nn]) = make_float4(v[0], v[1], v[2], v[3]);
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < BK; ++kk) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-
-    // ---- epilogue
-    const int nbase = n0 + tx * 4;
-    if (!BWD) {
-        const bool vec = (Fout % 4 == 0) && (nbase + 3 < N);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const long long r = r0 + ty * 8 + i;
-            if (r >= R) continue;
-            float* cp = Cout + r * Fout + nbase;
-            if (vec) st4(cp, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-            else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) if (nbase + j < N) cp[j] = acc[i][j];
-            }
-        }
-        if (bn_sums) {                                     // uniform branch
-            if (tid < BN) { red[0][tid] = 0.f; red[1][tid] = 0.f; }
-            __syncthreads();
-            float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (r0 + ty * 8 + i < R) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { s[j] += acc[i][j]; ss[j] = fmaf(acc[i][j], acc[i][j], ss[j]); }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { atomicAdd(&red[0][tx * 4 + j], s[j]); atomicAdd(&red[1][tx * 4 + j], ss[j]); }
-            __syncthreads();
-            if (tid < BN && n0 + tid < N) {
-                atomicAdd(bn_sums + n0 + tid, (double)red[0][tid]);
-                atomicAdd(bn_sums + N + n0 + tid, (double)red[1][tid]);
-            }
-        }
-    } else {
-        // n = k*Fin + fi  ->  plane k, column fi of G
-        const bool vec = (Fin % 4 == 0) && (nbase + 3 < N);
-        const long long plane_stride = R * (long long)Fin;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const long long r = r0 + ty * 8 + i;
-            if (r >= R) continue;
-            if (vec) {
-                const int k = nbase / Fin, fi = nbase - k * Fin;
-                st4(Cout + k * plane_stride + r * Fin + fi, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int n = nbase + j;
-                    if (n < N) { const int k = n / Fin, fi = n - k * Fin; Cout[k * plane_stride + r * Fin + fi] = acc[i][j]; }
-                }
-            }
-        }
-    }
-}
 
 // Small reduction depth (Q = K*Fin <= 16, e.g. the first layer Fin = 1): one thread produces 4
 // output columns of one row straight from global memory; W sits in shared memory.  The kernel is
@@ -272,70 +111,6 @@ contract_small_bwd_weight_kernel(Planar A, const float* __restrict__ dY, float* 
     }
 }
 
-// dW tile kernel: rows of the output are q = k*Fin + fi, columns fo; the reduction runs over the
-// (vertex, sample) rows r, split across blockIdx.z; partial tiles are merged with atomics.
-constexpr int WM = 64, WN = 64, WK = 16;
-__global__ void __launch_bounds__(256)
-contract_bwd_weight_kernel(Planar A, const float* __restrict__ dY, float* __restrict__ dW,
-                           long long R, int Fin, int K, int Fout, int Q, long long rows_per_split)
-{
-    __shared__ __align__(16) float As[WK][WM + 4];
-    __shared__ __align__(16) float Bs[WK][WN + 4];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int q0 = blockIdx.x * WM, n0 = blockIdx.y * WN;
-    const long long rbeg = (long long)blockIdx.z * rows_per_split;
-    long long rend = rbeg + rows_per_split;
-    if (rend > R) rend = R;
-
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    const int li = tid & 63, lk = tid >> 6;               // 64 columns x 4 rows per pass
-    const int qa = q0 + li;
-    int plane = 0, fa = 0;
-    if (qa < Q) { plane = qa / Fin; fa = qa - plane * Fin; }
-    const float* ap = A.at(plane);
-    const int nb = n0 + li;
-
-    for (long long rr = rbeg; rr < rend; rr += WK) {
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const int kk = lk + h * 4;
-            const long long r = rr + kk;
-            const bool ok = r < rend;
-            As[kk][li] = (ok && qa < Q) ? __ldg(ap + r * Fin + fa) : 0.f;
-            Bs[kk][li] = (ok && nb < Fout) ? __ldg(dY + r * Fout + nb) : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < WK; ++kk) {
-            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-            const float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
-            const float av[4] = {a.x, a.y, a.z, a.w};
-            const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int q = q0 + ty * 4 + i;
-        if (q >= Q) continue;
-        const int k = q / Fin, fi = q - k * Fin;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int n = n0 + tx * 4 + j;
-            if (n < Fout) atomicAdd(dW + ((long long)fi * K + k) * Fout + n, acc[i][j]);
-        }
-    }
-}
-
 // tensor-core (tcgen05) path on by default; dsb200_set_tensor_cores(0) forces the FP32 FFMA kernels
 static std::atomic<int> g_use_tc{1};
 
@@ -355,6 +130,11 @@ int contract_fwd_mma(const float* x0, const float* xk, const float* W, float* Y,
                      double* bn_sums, cudaStream_t s, float* Ypool = nullptr);   // contract_mma.cu
 int contract_wgrad_mma(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K, int Fout,
                        cudaStream_t s);                                     // contract_mma.cu
+int contract_fwd_ffma(const float* x0, const float* xk, const float* W, float* Y, long long R, int Fin, int K, int Fout,
+                      double* bn_sums, cudaStream_t s);                     // contract_ffma.cu
+int contract_bwd_data_ffma(const float* dY, const float* W, float* G, long long R, int Fin, int K, int Fout, cudaStream_t s);
+int contract_bwd_weight_ffma(const float* x0, const float* xk, const float* dY, float* dW, long long R, int Fin, int K, int Fout,
+                             cudaStream_t s);
 static bool wgrad_mma_enabled() { return DSB_ENV_INT("DSB200_WGRAD_MMA", 1) != 0; }   // default on
 static bool fwd_mma_enabled() { return DSB_ENV_INT("DSB200_FWD_MMA", 3) != 0; }   // default on
 }  // namespace dsb200
@@ -383,8 +163,7 @@ extern "C" int dsb200_cheb_contract_fwd(const float* x0, const float* xk, const 
         const size_t smem = (size_t)(Q * Fout + 2 * Fout) * sizeof(float);
         contract_small_fwd_kernel<<<grid, 256, smem, s>>>(A, W, Y, R, Fin, K, Fout, Q, bn_sums);
     } else {
-        dim3 grid((unsigned)((R + BM - 1) / BM), (unsigned)((Fout + BN - 1) / BN));
-        contract_kernel<false><<<grid, 256, 0, s>>>(A, W, Y, R, Fin, K, Fout, Q, Fout, bn_sums);
+        return contract_fwd_ffma(x0, xk, W, Y, R, Fin, K, Fout, bn_sums, s);
     }
     DSB_LAUNCH_CHECK();
 }
@@ -435,11 +214,7 @@ extern "C" int dsb200_cheb_contract_bwd_data(const float* dY, const float* W, fl
         const int rc = tc::contract_bwd_data_tc(dY, W, G, R, Fin, K, Fout, workspace, (cudaStream_t)stream);
         if (rc != 1) return rc;
     }
-    Planar A{dY, nullptr, Fout, 0};
-    const int N = K * Fin;
-    dim3 grid((unsigned)((R + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
-    contract_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(A, W, G, R, Fin, K, Fout, Fout, N, nullptr);
-    DSB_LAUNCH_CHECK();
+    return contract_bwd_data_ffma(dY, W, G, R, Fin, K, Fout, (cudaStream_t)stream);
 }
 
 extern "C" int dsb200_cheb_contract_bwd_weight(const float* x0, const float* xk, const float* dY, float* dW,
@@ -465,17 +240,7 @@ extern "C" int dsb200_cheb_contract_bwd_weight(const float* x0, const float* xk,
         if (Q <= 8) contract_small_bwd_weight_kernel<8><<<grid, 256, smem, s>>>(A, dY, dW, R, Fin, K, Fout, Q);
         else contract_small_bwd_weight_kernel<16><<<grid, 256, smem, s>>>(A, dY, dW, R, Fin, K, Fout, Q);
     } else {
-        const int tq = (Q + WM - 1) / WM, tn = (Fout + WN - 1) / WN;
-        long long splits = (4LL * kNumSMs + (long long)tq * tn - 1) / ((long long)tq * tn);
-        const long long max_splits = (R + 4 * WK - 1) / (4 * WK);
-        if (splits > max_splits) splits = max_splits;
-        if (splits < 1) splits = 1;
-        if (splits > 65535) splits = 65535;
-        long long rows_per_split = (R + splits - 1) / splits;
-        rows_per_split = (rows_per_split + WK - 1) / WK * WK;
-        splits = (R + rows_per_split - 1) / rows_per_split;
-        dim3 grid((unsigned)tq, (unsigned)tn, (unsigned)splits);
-        contract_bwd_weight_kernel<<<grid, 256, 0, s>>>(A, dY, dW, R, Fin, K, Fout, Q, rows_per_split);
+        return contract_bwd_weight_ffma(x0, xk, dY, dW, R, Fin, K, Fout, s);
     }
     DSB_LAUNCH_CHECK();
 }
