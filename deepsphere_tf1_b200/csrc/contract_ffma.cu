@@ -5,7 +5,7 @@
 //   BWD_DATA dX_k[r, fi]     = sum_fo dY[r, fo] W[fi*K + k, fo]
 //   WGRAD    dW[fi*K+k, fo] += sum_r X_k[r, fi] dY[r, fo]
 // written as C[m, n] = sum_t A(m, t) B(t, n) with loaders that address the planar operands in place (the K orders are K separate
-// [R, Fin] planes, never concatenated).  CTA tile 128 x (16 TN) x 8, 256 threads, 8 x TN outputs per thread; the next k-tile is
+// [R, Fin] planes, never concatenated).  CTA tile 128 x (16 TN) x 16, 256 threads, 8 x TN outputs per thread; the next k-tile is
 // fetched into registers while the current one is multiplied out of shared memory (one barrier per k-tile).  Exact fp32
 // arithmetic (no TF32), any shape, vector loads where the shape allows.  Replaces the 128 x 64 / 64 x 64 single-buffered kernels
 // of round 1 (20 % of the FFMA peak on the GHCN layers, profiles/r02_trace_step_cfg5.txt).
@@ -13,7 +13,7 @@
 
 namespace dsb200 {
 
-constexpr int GM = 128, GK = 8, GPAD = 4;
+constexpr int GM = 128, GK = 16, GPAD = 4;
 enum { G_FWD = 0, G_BWD = 1, G_WGRAD = 2 };
 
 struct GemmArgs {
@@ -48,10 +48,12 @@ __device__ __forceinline__ void load_a4(const GemmArgs& g, long long m, long lon
             v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
         } else {
             int kk = k, ff = fi;
+            const float* p = plane_of(g, kk) + m * g.Fin + ff;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (q + j < (int)tend) v[j] = __ldg(plane_of(g, kk) + m * g.Fin + ff);
-                if (++ff == g.Fin) { ff = 0; ++kk; }
+                if (q + j < (int)tend) v[j] = __ldg(p);
+                ++p;
+                if (++ff == g.Fin) { ff = 0; ++kk; p = plane_of(g, kk) + m * g.Fin; }
             }
         }
     } else if (MODE == G_BWD) {                  // m = row r, t = fo
@@ -71,10 +73,12 @@ __device__ __forceinline__ void load_a4(const GemmArgs& g, long long m, long lon
             v[0] = w.x; v[1] = w.y; v[2] = w.z; v[3] = w.w;
         } else {
             int kk = k, ff = fi;
+            const float* p = plane_of(g, kk) + t * g.Fin + ff;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                if (q + j < (int)g.M) v[j] = __ldg(plane_of(g, kk) + t * g.Fin + ff);
-                if (++ff == g.Fin) { ff = 0; ++kk; }
+                if (q + j < (int)g.M) v[j] = __ldg(p);
+                ++p;
+                if (++ff == g.Fin) { ff = 0; ++kk; p = plane_of(g, kk) + t * g.Fin; }
             }
         }
     }
@@ -117,11 +121,12 @@ __device__ __forceinline__ void load_b4(const GemmArgs& g, long long t, long lon
 
 // TN = output columns per thread: the CTA tile is 128 x (16 * TN)
 template <int MODE, int TN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 sgemm_kernel(const GemmArgs g)
 {
     constexpr int GN = 16 * TN;
-    constexpr int BLOADS = (GK * GN + 1023) / 1024;        // float4 groups of the B tile per thread (1 for GN <= 128)
+    constexpr int ALOADS = GM * GK / 1024;                 // float4 groups of the A tile per thread
+    constexpr int BLOADS = (GK * GN + 1023) / 1024;        // float4 groups of the B tile per thread
     __shared__ __align__(16) float As[2][GK][GM + GPAD];
     __shared__ __align__(16) float Bs[2][GK][GN + GPAD];
     __shared__ float red[2][GN];
@@ -143,23 +148,28 @@ sgemm_kernel(const GemmArgs g)
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
     // ---- tile loaders: global -> registers, registers -> shared memory (As[kk][m], Bs[kk][n])
-    float ra[4], rb[BLOADS][4];
-    const bool b_active = tid * 4 < GK * GN || BLOADS > 1;
+    float ra[ALOADS][4], rb[BLOADS][4];
     auto fetch = [&](long long t0) {
-        if (MODE == G_WGRAD) load_a4<MODE>(g, m0 + (tid & 31) * 4, t0 + (tid >> 5), tend, ra);           // 4 consecutive q of one row
-        else load_a4<MODE>(g, m0 + (tid >> 1), t0 + (tid & 1) * 4, tend, ra);                             // 4 consecutive t of one row
+#pragma unroll
+        for (int l = 0; l < ALOADS; ++l) {
+            if (MODE == G_WGRAD) load_a4<MODE>(g, m0 + (tid & 31) * 4, t0 + (tid >> 5) + 8 * l, tend, ra[l]);   // 4 consecutive q of one row
+            else load_a4<MODE>(g, m0 + (tid >> 1), t0 + (tid & 1) * 4 + 8 * l, tend, ra[l]);                     // 4 consecutive t of one row
+        }
 #pragma unroll
         for (int l = 0; l < BLOADS; ++l) {
             const int e = tid + l * 256;
-            if (MODE == G_BWD) { if (e * 4 < GK * GN) load_b4<MODE>(g, t0 + (e & 1) * 4, tend, n0 + (e >> 1), rb[l]); }
+            if (MODE == G_BWD) { if (e * 4 < GK * GN) load_b4<MODE>(g, t0 + (e & 3) * 4, tend, n0 + (e >> 2), rb[l]); }
             else { if (e * 4 < GK * GN) load_b4<MODE>(g, t0 + e / (GN / 4), tend, n0 + (e % (GN / 4)) * 4, rb[l]); }
         }
     };
     auto stash = [&](int buf) {
-        if (MODE == G_WGRAD) *reinterpret_cast<float4*>(&As[buf][tid >> 5][(tid & 31) * 4]) = make_float4(ra[0], ra[1], ra[2], ra[3]);
-        else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) As[buf][(tid & 1) * 4 + j][tid >> 1] = ra[j];
+        for (int l = 0; l < ALOADS; ++l) {
+            if (MODE == G_WGRAD) *reinterpret_cast<float4*>(&As[buf][(tid >> 5) + 8 * l][(tid & 31) * 4]) = make_float4(ra[l][0], ra[l][1], ra[l][2], ra[l][3]);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) As[buf][(tid & 1) * 4 + 8 * l + j][tid >> 1] = ra[l][j];
+            }
         }
 #pragma unroll
         for (int l = 0; l < BLOADS; ++l) {
@@ -167,11 +177,10 @@ sgemm_kernel(const GemmArgs g)
             if (e * 4 >= GK * GN) continue;
             if (MODE == G_BWD) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) Bs[buf][(e & 1) * 4 + j][e >> 1] = rb[l][j];
+                for (int j = 0; j < 4; ++j) Bs[buf][(e & 3) * 4 + j][e >> 2] = rb[l][j];
             } else *reinterpret_cast<float4*>(&Bs[buf][e / (GN / 4)][(e % (GN / 4)) * 4]) = make_float4(rb[l][0], rb[l][1], rb[l][2], rb[l][3]);
         }
     };
-    (void)b_active;
 
     int buf = 0;
     fetch(tbeg);
@@ -250,10 +259,13 @@ sgemm_kernel(const GemmArgs g)
         for (int i = 0; i < 8; ++i) {
             const long long r = m0 + ty * 8 + i;
             if (r >= g.M) continue;
+            int k = nb / g.Fin, fi = nb - k * g.Fin;
+            float* cp = g.c + k * plane + r * g.Fin + fi;
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
-                const int n = nb + j;
-                if (n < g.N) { const int k = n / g.Fin, fi = n - k * g.Fin; g.c[k * plane + r * g.Fin + fi] = acc[i][j]; }
+                if (nb + j < g.N) *cp = acc[i][j];
+                ++cp;
+                if (++fi == g.Fin) { fi = 0; cp += plane - g.Fin; }
             }
         }
     } else {
