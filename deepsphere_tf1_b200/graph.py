@@ -351,9 +351,15 @@ class ShardedGraph(object):
     and Me = Ml + H columns: the owned vertices first, then the H ghost vertices (1-ring halo) sorted by global id,
     i.e. grouped by owner.  It is stored square (Me x Me, empty ghost rows) so that the kernels of the single-GPU
     path run unchanged on [1, Me, F] tensors whose last H rows are ghosts.  `send[q]` lists the owned rows rank q
-    needs (ascending), `recv[q]` = (first ghost slot, count) of the ghosts owned by q."""
+    needs (ascending), `recv[q]` = (first ghost slot, count) of the ghosts owned by q.
 
-    def __init__(self, L, rank, world, device):
+    `rings` > 1: the halo holds every vertex within `rings` edges of the owned range, and the local matrix also has the rows of
+    the ghosts of rings 1 .. rings-1 (all their columns are local).  ONE exchange then feeds `rings` consecutive sparse products
+    computed on all local rows: after product j the values are valid on the owned vertices and on rings 1 .. rings-j (the outer
+    rings hold finite garbage that no valid row reads) -- a whole Chebyshev recurrence of order K = rings + 1 per exchange,
+    instead of one exchange per product."""
+
+    def __init__(self, L, rank, world, device, rings=1):
         L = sparse.csr_matrix(L, dtype=np.float32)
         L.sum_duplicates()
         M = L.shape[0]
@@ -362,24 +368,45 @@ class ShardedGraph(object):
         Ml = M // world
         LT = sparse.csr_matrix(L.T)
         self.M_global, self.Ml, self.rank, self.world = M, Ml, rank, world
+        self.rings = int(rings)
 
-        def ghosts_of(q):
+        def ghosts_of(q, want_ring=False):
+            """Vertices within `rings` edges (of L or L^T) of rank q's range, ascending global id (+ their ring number)."""
             lo, hi = q * Ml, (q + 1) * Ml
             c = np.union1d(L[lo:hi].indices, LT[lo:hi].indices)
-            return c[(c < lo) | (c >= hi)]
+            found = c[(c < lo) | (c >= hi)]
+            ring = np.ones(len(found), np.int32)
+            frontier = found
+            for j in range(2, self.rings + 1):
+                if not len(frontier):
+                    break
+                c = np.union1d(L[frontier].indices, LT[frontier].indices)
+                c = c[(c < lo) | (c >= hi)]
+                new = np.setdiff1d(c, found, assume_unique=True)
+                found = np.concatenate([found, new])
+                ring = np.concatenate([ring, np.full(len(new), j, np.int32)])
+                frontier = new
+            order = np.argsort(found, kind='stable')
+            return (found[order], ring[order]) if want_ring else found[order]
 
         lo, hi = rank * Ml, (rank + 1) * Ml
-        ghosts = ghosts_of(rank)
+        ghosts, ghost_ring = ghosts_of(rank, True)
         H = len(ghosts)
         self.H, self.Me = H, Ml + H
-        self.ghost_ids = ghosts
+        self.ghost_ids, self.ghost_ring = ghosts, ghost_ring
+        inner = np.nonzero(ghost_ring < self.rings)[0]           # ghosts that get a matrix row (none for rings == 1)
 
         def localise(A):
-            rows = A[lo:hi].tocoo()
+            rowsel = np.concatenate([np.arange(lo, hi, dtype=np.int64), ghosts[inner].astype(np.int64)])
+            lrow = np.concatenate([np.arange(Ml, dtype=np.int64), Ml + inner.astype(np.int64)])
+            rows = A[rowsel].tocoo()
             c = rows.col.astype(np.int64)
             own = (c >= lo) & (c < hi)
-            lc = np.where(own, c - lo, Ml + np.searchsorted(ghosts, c))
-            return sparse.csr_matrix((rows.data, (rows.row, lc)), shape=(self.Me, self.Me), dtype=np.float32)
+            pos = np.minimum(np.searchsorted(ghosts, c), max(H - 1, 0))
+            local = own | ((ghosts[pos] == c) if H else own)
+            assert local.all(), 'a row inside the halo references a vertex outside of it'
+            lc = np.where(own, c - lo, Ml + pos)
+            return sparse.csr_matrix((rows.data, (lrow[rows.row], lc)), shape=(self.Me, self.Me), dtype=np.float32)
 
         self.L_local, self.LT_local = localise(L), localise(LT)
         owner = ghosts // Ml

@@ -257,10 +257,11 @@ class _ChebStage(object):
         E = torch.empty((K, 1, sg.Me, Fin), dtype=torch.float32, device=x.device)
         ops.vertex_resize(x, sg.Me, 0.0, out=E[0])
         halo.exchange(sg, E[0], m.pg, peer=m._peer_halo)
+        wide = sg.rings >= K - 1 and sg.rings > 1      # the halo covers the whole recurrence: no further exchange, all local rows
         for k in range(1, K):
             ops.spmm(g, E[k - 1], E[k - 2] if k >= 2 else None, None, out=E[k], alpha=1.0 if k == 1 else 2.0,
-                     beta=0.0 if k == 1 else -1.0, rows=Ml)
-            if k < K - 1:
+                     beta=0.0 if k == 1 else -1.0, rows=None if wide else Ml)
+            if k < K - 1 and not wide:
                 halo.exchange(sg, E[k], m.pg, peer=m._peer_halo)
         if sg.H:
             for k in range(K):
@@ -322,12 +323,20 @@ class _ChebStage(object):
         if not need_dx:
             return None
         W = m._P.views[self.scope + '/weights']
+        wide = sg.rings >= K - 1 and sg.rings > 1
+        if wide:
+            # dy on the whole halo (one exchange), G_k = dy W_k^T on all local rows, then the adjoint recurrence without further
+            # exchanges: A_k is valid on the owned vertices and the rings 1 .. k, A_0 on the owned ones
+            if not dy.is_contiguous():
+                dy = dy.contiguous()
+            halo.exchange(sg, dy, m.pg, peer=m._peer_halo)
         G = ops.contract_bwd_data(dy, W, K, Fin)                           # [K, 1, Me, Fin]
         for k in range(K - 2, -1, -1):                                     # adjoint recurrence (csrc/sparse.cu)
-            halo.exchange(sg, G[k + 1], m.pg, peer=m._peer_halo)
+            if not wide:
+                halo.exchange(sg, G[k + 1], m.pg, peer=m._peer_halo)
             a2 = G[k + 2] if k + 2 <= K - 1 else None
             ops.spmm(g, G[k + 1], G[k], a2, out=G[k], alpha=2.0 if k >= 1 else 1.0, beta=1.0,
-                     gamma=-1.0 if a2 is not None else 0.0, transpose=True, rows=Ml)
+                     gamma=-1.0 if a2 is not None else 0.0, transpose=True, rows=None if wide else Ml)
         return G[0][:, :Ml]
 
     def backward(self, dout, need_dx=True):
@@ -996,7 +1005,10 @@ class cgcnn(base_model):
                 return g
         pre = getattr(self, '_prebuilt_graphs', None)
         if self.vertex_shard:
-            self._graphs[i] = ShardedGraph(self.L[i], self.rank, self.world_size, self.device)
+            # (K - 1)-ring halos: one exchange per layer and direction instead of one per sparse product (graph.ShardedGraph);
+            # DSB200_SHARD_RINGS=1 restores the 1-ring halo with an exchange before every product
+            rings = int(os.environ.get('DSB200_SHARD_RINGS', 0)) or max(1, max(self.K) - 1)
+            self._graphs[i] = ShardedGraph(self.L[i], self.rank, self.world_size, self.device, rings=rings)
         elif pre is not None and pre[i] is not None and pre[i].device == self.device:
             self._graphs[i] = pre[i]                          # built on the device by graph_build.py
         else:
@@ -1107,7 +1119,7 @@ class cgcnn(base_model):
             # opt-in: one-kernel halo exchange over NVLink peer memory (csrc/peer_halo.cu).  Measured on 2 GPUs inside the step's
             # CUDA graph it is no faster than NCCL's grouped send / recv (2.75 vs 2.48 ms at Nside 512): the ~57 rank
             # synchronisations of a sharded step cost their dependency chain, not the transport
-            cap = max([st.sg.H * st.Fin for st in self._encoder if st.sg is not None] + [4])
+            cap = max([st.sg.H * max(st.Fin, st.Fout) for st in self._encoder if st.sg is not None] + [4])
             try:
                 from .peer import PeerHalo
                 ph = PeerHalo(cap, self.pg)

@@ -80,6 +80,65 @@ def test_halo_exchange_reproduces_the_global_recurrence(tmp_path, world, nonsym)
         assert np.all(np.diff(g) > 0) and not np.any((g >= r * Ml) & (g < (r + 1) * Ml))
 
 
+def _wide_worker(rank, world, port, nonsym, out):
+    """(K - 1)-ring halo: ONE exchange per recurrence, every product on all local rows (graph.ShardedGraph(rings=K-1))."""
+    from deepsphere_tf1_b200 import halo
+    from deepsphere_tf1_b200.graph import ShardedGraph
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    L = _graph(nonsym)
+    K, F = 5, 3
+    sg = ShardedGraph(L, rank, world, None, rings=K - 1)
+    M, Ml = L.shape[0], sg.Ml
+    lo = rank * Ml
+    gather = lambda rows, idx: rows[torch.from_numpy(idx.astype(np.int64))].contiguous()
+    x = np.random.RandomState(0).randn(M, F)
+    G = np.random.RandomState(1).randn(K, M, F)
+    A, AT = sg.L_local.astype(np.float64), sg.LT_local.astype(np.float64)
+    e = torch.zeros(sg.Me, F, dtype=torch.float64)
+    e[:Ml] = torch.from_numpy(x[lo:lo + Ml])
+    halo.exchange(sg, e, gather=gather)                                   # the only exchange of the forward recurrence
+    planes = [e.numpy(), A @ e.numpy()]
+    for k in range(2, K):
+        planes.append(2 * (A @ planes[-1]) - planes[-2])
+    g = torch.zeros(K, sg.Me, F, dtype=torch.float64)
+    g[:, :Ml] = torch.from_numpy(G[:, lo:lo + Ml])
+    for k in range(K):
+        halo.exchange(sg, g[k], gather=gather)                            # (the model exchanges dy once and derives the G_k locally)
+    a = [None] * K
+    a[K - 1] = g[K - 1].numpy()
+    for k in range(K - 2, -1, -1):
+        a[k] = g[k].numpy() + (2.0 if k >= 1 else 1.0) * (AT @ a[k + 1]) - (a[k + 2] if k + 2 <= K - 1 else 0.0)
+    torch.save((torch.from_numpy(np.stack([p[:Ml] for p in planes])), torch.from_numpy(a[0][:Ml]),
+                torch.from_numpy(sg.ghost_ids), torch.from_numpy(sg.ghost_ring)), '{}.{}'.format(out, rank))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,nonsym', [(2, False), (4, True)])
+def test_wide_halo_needs_one_exchange_per_recurrence(tmp_path, world, nonsym):
+    out = str(tmp_path / 'wide')
+    mp.spawn(_wide_worker, args=(world, 31000 + (os.getpid() * 11 + world) % 2000, nonsym, out), nprocs=world, join=True)
+    L = _graph(nonsym).astype(np.float64)
+    M, K, F = L.shape[0], 5, 3
+    x = np.random.RandomState(0).randn(M, F)
+    G = np.random.RandomState(1).randn(K, M, F)
+    ref = [x, L @ x]
+    for k in range(2, K):
+        ref.append(2 * (L @ ref[-1]) - ref[-2])
+    ref = np.stack(ref)
+    A = [None] * K
+    A[K - 1] = G[K - 1]
+    for k in range(K - 2, -1, -1):
+        A[k] = G[k] + (2.0 if k >= 1 else 1.0) * (L.T @ A[k + 1]) - (A[k + 2] if k + 2 <= K - 1 else 0.0)
+    Ml = M // world
+    for r in range(world):
+        planes, a0, ghosts, ring = torch.load('{}.{}'.format(out, r))
+        np.testing.assert_allclose(planes.numpy(), ref[:, r * Ml:(r + 1) * Ml], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(a0.numpy(), A[0][r * Ml:(r + 1) * Ml], rtol=0, atol=1e-9)
+        assert np.all(np.diff(ghosts.numpy()) > 0) and ring.numpy().min() == 1 and ring.numpy().max() <= K - 1
+
+
 def test_partition_plan_is_consistent_across_ranks():
     from deepsphere_tf1_b200.graph import ShardedGraph
     L = _graph(False)
@@ -93,6 +152,14 @@ def test_partition_plan_is_consistent_across_ranks():
             # what r sends to q is exactly the ghost segment of q that r owns, in the same order
             np.testing.assert_array_equal(sgs[q].ghost_ids[off:off + n], idx + r * a.Ml)
         assert a.L_local.shape == (a.Me, a.Me) and a.L_local[a.Ml:].nnz == 0
+    # wide halos: the same plan invariants, rows for the inner rings only
+    sgs = [ShardedGraph(L, r, world, None, rings=3) for r in range(world)]
+    for r, a in enumerate(sgs):
+        for q, idx in a.send.items():
+            off, n = sgs[q].recv[r]
+            np.testing.assert_array_equal(sgs[q].ghost_ids[off:off + n], idx + r * a.Ml)
+        rows_with_entries = np.unique(a.L_local[a.Ml:].tocoo().row)
+        assert set(rows_with_entries) <= set(np.nonzero(a.ghost_ring < 3)[0])
     with pytest.raises(ValueError):
         ShardedGraph(L, 0, 5, None)
 
