@@ -15,12 +15,13 @@ from deepsphere_tf1_b200 import models, ops, optimizers, utils  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--steps', type=int, default=2000)
 ap.add_argument('--flush', action='store_true', help='rewrite a 512 MB buffer between steps (cold L2, like under ncu)')
+ap.add_argument('--dtype', default='float32', choices=['float32', 'bfloat16'])
 args = ap.parse_args()
 torch.cuda.set_device(0)
 model = models.deepsphere(
     nsides=bench.NSIDES, indexes=utils.nside2indexes(bench.NSIDES, bench.ORDER), new=False, lmax=bench.LMAX,
     F=bench.F, K=[bench.KCHEB] * 6, batch_norm=[True] * 6, M=[], statistics='mean', num_epochs=1,
-    batch_size=16, eval_frequency=10 ** 9, seed=2, verbose=False, cuda_graph=False,
+    batch_size=16, eval_frequency=10 ** 9, seed=2, verbose=False, cuda_graph=False, dtype=args.dtype,
     scheduler=lambda step: optimizers.exponential_decay(2e-4, step, 1, 0.999),
     optimizer=lambda lr: optimizers.AdamOptimizer(lr, epsilon=1e-8), dir_name='_stress')
 x, labels = bench.synthetic_batch(16, 100)
