@@ -67,6 +67,51 @@ def healpix_weightmatrix(nside=16, nest=True, indexes=None, dtype=np.float32, st
     return sparse.csr_matrix((weights, (row_index, col_index)), shape=(npix, npix), dtype=dtype)
 
 
+def build_matrix_4_neighboors(nside, indexes, nest=True, dtype=np.float32):
+    """4-neighbour grid graph of a HEALPix patch (upstream utils.py:484-591, `use_4=True`).  The patch is one base pixel of the
+    coarser resolution `order`, i.e. the nested pixels 0 .. (nside / order)^2 - 1: a square in Z (Morton) order.  Upstream walks
+    the digits of every index; here the whole edge list is built with array operations, in upstream's ORDER of entries (per pixel:
+    the two neighbours inside its 2 x 2 block, then per level the -x / +x and the -y / +y crossings it tests) because the kernel
+    width is the mean over that list.  Gaussian weights exp(-d^2 / (3 mean d^2)) on float64 coordinates."""
+    assert nest
+    idx = np.asarray(indexes, dtype=np.int64)
+    order = nside // int(round(((int(idx.max()) + 1)) ** 0.5))         # hp.npix2nside(12 * (max + 1))
+    npix = hp.nside2npix(nside) // hp.nside2npix(order)
+    assert set(idx.tolist()) == set(range(npix))
+    x, y, z = hp.pix2vec(nside, idx, nest=True)
+    coords = np.vstack([x, y, z]).transpose()
+    d = idx % 4
+    base = idx - d
+    cols = [base + np.array([1, 3, 0, 2])[d], base + np.array([2, 0, 3, 1])[d]]
+    valid = [np.ones(len(idx), bool), np.ones(len(idx), bool)]
+    levels = int(np.log2(nside) - np.log2(order) - 1)
+    digits = []
+    for it in range(levels):
+        digits.append((idx // 4 ** it) % 4)                         # digits of the levels 0 .. it (d3 upstream)
+        d2 = (idx // 4 ** (it + 1)) % 4
+        D = np.stack(digits)
+
+        def all_in(a, b):
+            return ((D == a) | (D == b)).all(axis=0)
+        in13, in23, in02, in01 = all_in(1, 3), all_in(2, 3), all_in(0, 2), all_in(0, 1)
+        shift = 4 ** (it + 1) - sum(4 ** j for j in range(it + 1))
+        # first / second test of upstream's branch for d2 = 0, 1, 2, 3
+        colA = idx + np.array([shift, -shift, -2 * shift, -2 * shift])[d2]
+        okA = np.choose(d2, [in13, in02, in01, in01])
+        colB = idx + np.array([2 * shift, 2 * shift, shift, -shift])[d2]
+        okB = np.choose(d2, [in23, in23, in13, in02])
+        cols += [colA, colB]
+        valid += [okA, okB]
+    C = np.stack(cols, axis=1)
+    V = np.stack(valid, axis=1)
+    row_index = np.repeat(idx, C.shape[1])[V.reshape(-1)]
+    col_index = C.reshape(-1)[V.reshape(-1)]
+    distances = np.sum((coords[row_index] - coords[col_index]) ** 2, axis=1)
+    kernel_width = np.mean(distances)
+    weights = np.exp(-distances / (3 * kernel_width))
+    return sparse.csr_matrix((weights, (row_index, col_index)), shape=(npix, npix), dtype=dtype)
+
+
 def build_laplacian(W, lap_type='normalized', dtype=np.float32):
     """Combinatorial `D - W` or normalised `I - D^-1/2 W D^-1/2` Laplacian of a weight matrix."""
     d = np.ravel(W.sum(1))
@@ -99,7 +144,8 @@ def healpix_laplacian(nside=16, nest=True, lap_type='normalized', indexes=None, 
         from . import graphs
         return graphs.healpix_nn_laplacian(nside, indexes=indexes, n_neighbors=n_neighbors, lap_type=lap_type, dtype=dtype)
     if use_4:
-        raise NotImplementedError()     # as upstream (utils.py:268-270)
+        W = build_matrix_4_neighboors(nside, indexes, nest=nest, dtype=dtype)          # utils.py:336-337
+        return build_laplacian(W, lap_type=lap_type)
     W = healpix_weightmatrix(nside=nside, nest=nest, indexes=indexes, dtype=dtype, std=std, full=full)
     return build_laplacian(W, lap_type=lap_type)
 

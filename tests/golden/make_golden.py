@@ -30,6 +30,7 @@ def _install_shims():
     hp = types.ModuleType('healpy')
     hp.pix2vec = ohp.pix2vec
     hp.nside2npix = ohp.nside2npix
+    hp.npix2nside = lambda npix: int(round((npix / 12) ** 0.5))
     hp.pixelfunc = types.ModuleType('healpy.pixelfunc')
     hp.pixelfunc.get_all_neighbours = ohp.get_all_neighbours
     sys.modules['healpy'] = hp
@@ -117,6 +118,11 @@ def main():
     L = utils.build_laplacian(W, 'normalized')
     Lr = utils.rescale_L(L.copy(), lmax=np.float32(1.93))
     out.update(_csr_parts(Lr, 'rescale4'))
+    # 4-neighbour grid graph of a patch (use_4=True, utils.py:484-591)
+    for nside, order in ((8, 2), (16, 1), (32, 2)):
+        idx4 = utils.nside2indexes([nside], order)[0]
+        W = utils.build_matrix_4_neighboors(nside, idx4, nest=True, dtype=np.float32)
+        out.update(_csr_parts(W, 'four%d_%d_W' % (nside, order)))
     # equiangular (SOFT) 8-neighbour graph, the only equiangular construction that is fully in the reference's repository
     for bw in (2, 4, 8):
         W = utils.equiangular_weightmatrix(bw=bw, dtype=np.float32)

@@ -200,3 +200,19 @@ def test_equiangular_z_order_makes_2d_windows_consecutive():
             pc, _, _ = m._equi_perm((n // s) ** 2) if n // s > 1 else (np.zeros(1, np.int64), None, None)
             if n // s > 1:
                 assert (g[:, 0] == pc).all()
+
+
+@pytest.mark.parametrize('nside,order', [(8, 2), (16, 1), (32, 2)])
+def test_four_neighbour_patch_graph_bit_exact(nside, order):
+    """utils.build_matrix_4_neighboors (use_4=True; array operations) against the reference's digit-walking loop
+    (upstream utils.py:484-591): the 4-connected grid of a nested-order patch, Gaussian weights with width 3 x mean d^2."""
+    idx = putils.nside2indexes([nside], order)[0]
+    W = putils.build_matrix_4_neighboors(nside, idx)
+    assert_same(W, 'four%d_%d_W' % (nside, order))
+    A = sparse.csr_matrix(W)
+    n = int(round(len(idx) ** 0.5))
+    deg = np.diff(A.indptr)
+    assert deg.min() == 2 and deg.max() == 4 and (deg == 2).sum() == 4 and A.nnz == 4 * n * (n - 1)     # an n x n grid
+    L, p = putils.build_laplacians([nside, nside // 2, nside // 2], indexes=putils.nside2indexes([nside, nside // 2, nside // 2], order),
+                                   use_4=True, new=False)
+    assert p == [4, 1] and L[0].shape[0] == len(idx)

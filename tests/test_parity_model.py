@@ -468,3 +468,17 @@ def test_equiangular_grid_2d_pooling(head):
         opt = None
     oracle, model = _pair(L, sampling='equiangular', batch_size=3, **kw)
     _check_step(oracle, model, x, labels.astype(np.int64) if head != 'dense' else labels.astype(np.int64), opt=opt)
+
+
+def test_use_4_neighbour_graph_model():
+    """`use_4=True` (utils.py:336-337, 484-591): the 4-neighbour patch graph (ELL width 5) through the whole model."""
+    from deepsphere_tf1_b200 import utils
+    nsides = [16, 8, 4, 4]
+    idx = utils.nside2indexes(nsides, 1)
+    L, p = utils.build_laplacians(nsides, indexes=idx, use_4=True, new=False)
+    assert p == [4, 4, 1] and [l.shape[0] for l in L] == [256, 64, 16]
+    oracle, model = _pair(L, F=[8, 16, 3], K=[4, 4, 3], p=p, batch_norm=[True, True, False], M=[], statistics='mean', num_feat_in=2)
+    rs = np.random.RandomState(9)
+    x = rs.randn(4, 256, 2).astype(np.float32)
+    labels = rs.randint(0, 3, size=4).astype(np.int32)
+    _check_step(oracle, model, x, labels)
