@@ -17,7 +17,9 @@ pinned host -> device copy of a batch and its labels on a copy stream overlappin
 device -> host read of the loss, every step); `roofline` = the ChebConv
 recurrence SpMM step timed alone with CUDA events (back to back over operand sets >> L2) against the
 measured HBM copy bandwidth; `cpu_baseline` = the oracle (restated reference) timed on this box's
-host cores.
+host cores; `parity` = one step of this very configuration against the float64 oracle (fp32 path, and
+`parity.bf16` for the BF16 mode; the run exits 3 if it fails); `bf16_mode` = the same measurement with
+dtype='bfloat16' (a second line of evidence: the headline `dtype` stays f32).
 """
 import argparse
 import json

@@ -18,7 +18,10 @@ Differences from the reference that a user sees (also listed in DESIGN.md):
     reference's variable names (`conv1/weights`, `conv1/batch_normalization/moving_mean`, ...);
   * `extra_loss` (triplet loss): NotImplementedError -- upstream passes the rank-3 descriptor to a rank-2 loss (models.py:768-769,
     1247), it cannot run as committed; equiangular grids: square, power-of-two side, on the in-repo 8-neighbour graph;
-    `conv='monomials'`, `weighted=True`, `statistics='histogram'` and `dropFilt < 1` are supported.
+    `conv='monomials'`, `weighted=True`, `statistics='histogram'` and `dropFilt < 1` (SURVEY 8f.3) are supported;
+  * `dtype='bfloat16'` (upstream's `dtype` only casts the Laplacians): the ChebConv layers keep their activations, Chebyshev
+    planes and activation gradients as bfloat16 (fp32 arithmetic, fp32 weights / statistics); everything else stays float32;
+  * TensorFlow checkpoints of the reference can be read / written directly (`load_tf_checkpoint` / `save_tf_checkpoint`).
 """
 import glob
 import json
