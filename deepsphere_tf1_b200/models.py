@@ -17,7 +17,8 @@ Differences from the reference that a user sees (also listed in DESIGN.md):
   * checkpoints are `torch.save` files `checkpoints/<dir_name>/model-<step>.pt` keyed by the
     reference's variable names (`conv1/weights`, `conv1/batch_normalization/moving_mean`, ...);
   * `extra_loss` (triplet loss): NotImplementedError -- upstream passes the rank-3 descriptor to a rank-2 loss (models.py:768-769,
-    1247), it cannot run as committed; equiangular grids: square, power-of-two side, on the in-repo 8-neighbour graph;
+    1247), it cannot run as committed; equiangular grids: any rows x columns the pooling windows divide (`ratio`), on the
+    in-repo 8-neighbour graph;
     `conv='monomials'`, `weighted=True`, `statistics='histogram'` and `dropFilt < 1` (SURVEY 8f.3) are supported;
   * `dtype='bfloat16'` (upstream's `dtype` only casts the Laplacians): the ChebConv layers keep their activations, Chebyshev
     planes and activation gradients as bfloat16 (fp32 arithmetic, fp32 weights / statistics); everything else stays float32;
@@ -876,8 +877,16 @@ class cgcnn(base_model):
             # Here the vertices of every level are kept in Z (Morton) order of their grid position, so that a window is p
             # CONSECUTIVE vertices and every kernel of the HEALPix path (pooling, fused epilogues, tile plans) applies unchanged;
             # inputs, dense outputs and descriptors are permuted at the boundary (`_equi_gather`).
-            if getattr(self, 'ratio', 1.) != 1.:
-                raise NotImplementedError('equiangular grids with different bandwidths in latitude and longitude')
+            # `ratio` = columns / rows of the grid (an attribute, as upstream: deepsphere.__init__ sets it, models.py:1832-1836).
+            # Every level that is pooled by p needs sides divisible by sqrt(p) at that point of the chain.
+            rows = int(round((L[0].shape[0] / float(getattr(self, 'ratio', 1.))) ** 0.5))
+            cols = L[0].shape[0] // max(rows, 1)
+            for pi in (p[:-1] if len(M) == 0 else p):          # the last layer of a model without fc head does not pool
+                s = int(round(pi ** 0.5))
+                if s * s != pi or rows % s or cols % s:
+                    raise ValueError('equiangular pooling by {} needs a square window that divides the {} x {} grid'
+                                     .format(pi, rows, cols))
+                rows, cols = rows // s, cols // s
             if vertex_shard:
                 raise NotImplementedError('vertex_shard=True is a HEALPix mode')
             if dense and pool == 'max' and (np.asarray(p) > 1).any():
@@ -967,22 +976,19 @@ class cgcnn(base_model):
         return self._bn_buf[scope]
 
     def _equi_perm(self, M):
-        """(perm, inv) of a square equiangular grid of M vertices: perm[k] = row-major index of the k-th vertex in Z (Morton)
-        order; inv[perm[k]] = k.  Cached per size, with int32 device copies."""
+        """(perm, inv) of an equiangular grid of M vertices, [sqrt(M / ratio), sqrt(M * ratio)] as upstream reshapes it
+        (models.py:1134): perm[k] = row-major index of the k-th vertex in the blocked Z order of
+        utils.equiangular_block_order (plain Morton order on a square power-of-two grid); inv[perm[k]] = k.  Cached per size,
+        with int32 device copies."""
         cache = self.__dict__.setdefault('_equi_perms', {})
         if M not in cache:
-            n = int(round(M ** 0.5))
-            if n * n != M or n & (n - 1):
-                raise NotImplementedError('equiangular grids need a power-of-two side (got {} vertices)'.format(M))
-            k = np.arange(M, dtype=np.int64)
-            i = np.zeros(M, np.int64)
-            j = np.zeros(M, np.int64)
-            for b in range(max(1, n.bit_length() - 1)):
-                j |= ((k >> (2 * b)) & 1) << b
-                i |= ((k >> (2 * b + 1)) & 1) << b
-            perm = i * n + j
+            ratio = float(getattr(self, 'ratio', 1.))
+            rows, cols = int(round((M / ratio) ** 0.5)), int(round((M * ratio) ** 0.5))
+            if rows * cols != M:
+                raise ValueError('{} vertices are not a grid with {} times as many columns as rows'.format(M, ratio))
+            perm = utils.equiangular_block_order(rows, cols)
             inv = np.empty(M, np.int64)
-            inv[perm] = k
+            inv[perm] = np.arange(M, dtype=np.int64)
             cache[M] = (perm, inv, {})
         return cache[M]
 

@@ -154,13 +154,17 @@ def equiangular_weightmatrix(bw=64, indexes=None, dtype=np.float32):
     """8-neighbour graph of the SOFT equiangular grid of bandwidth bw (2bw x 2bw vertices, row-major in (colatitude, longitude)),
     weights 1 / squared chord distance (upstream utils.py:136-229, the only equiangular graph that is fully in the reference's
     repository; its neighbour functions wrap the longitude and cross the poles by half a turn).  Vectorised; same float32
-    arithmetic and the same entry order as upstream (neighbours SW, W, NW, N, NE, E, SE, S), so the CSR matrix is bit-identical."""
+    arithmetic and the same entry order as upstream (neighbours SW, W, NW, N, NE, E, SE, S), so the CSR matrix is bit-identical.
+    `bw` may be a pair (bw_colatitude, bw_longitude): the same construction on the 2 bw[0] x 2 bw[1] grid (upstream passes such
+    pairs to the absent fork's SphereEquiangular, utils.py:401-416; this rectangular form is an extension with nothing upstream
+    to be pinned to -- for equal bandwidths it is the square grid above, bit for bit)."""
     if indexes is not None:
         raise NotImplementedError('equiangular_weightmatrix: partial grids are not supported (upstream builds a full-size matrix)')
-    n = 2 * bw
-    npix = n * n
-    beta = np.pi * (2 * np.arange(n) + 1) / (4. * bw)          # SOFT
-    alpha = np.arange(n) * np.pi / bw
+    bw_lat, bw_lon = (int(bw[0]), int(bw[1])) if isinstance(bw, (tuple, list)) else (int(bw), int(bw))
+    nr, n = 2 * bw_lat, 2 * bw_lon                             # rows (colatitude), columns (longitude)
+    npix = nr * n
+    beta = np.pi * (2 * np.arange(nr) + 1) / (4. * bw_lat)     # SOFT
+    alpha = np.arange(n) * np.pi / bw_lon
     theta, phi = np.meshgrid(beta, alpha, indexing='ij')
     ct, st, cp, sp = np.cos(theta), np.sin(theta), np.cos(phi), np.sin(phi)
     coords = np.vstack([(st * cp).flatten(), (st * sp).flatten(), ct.flatten()]).transpose()
@@ -168,10 +172,10 @@ def equiangular_weightmatrix(bw=64, indexes=None, dtype=np.float32):
     ind = np.arange(npix, dtype=np.int64)
 
     def south(x):
-        return np.where(x >= npix - n, (x + bw) % n + npix - n, x + n)
+        return np.where(x >= npix - n, (x + bw_lon) % n + npix - n, x + n)
 
     def north(x):
-        return np.where(x < n, (x + bw) % n, x - n)
+        return np.where(x < n, (x + bw_lon) % n, x - n)
 
     def west(x):
         return np.where(x % n == 0, x + n, x) - 1
@@ -186,6 +190,30 @@ def equiangular_weightmatrix(bw=64, indexes=None, dtype=np.float32):
     distances = np.sum((coords[row_index] - coords[col_index])**2, axis=1)
     weights = 1 / distances
     return sparse.csr_matrix((weights, (row_index, col_index)), shape=(npix, npix), dtype=dtype)
+
+
+def equiangular_block_order(rows, cols, depth=None):
+    """Vertex order of a rows x cols equiangular grid in which every aligned 2^s x 2^s window (s <= depth) is 4^s CONSECUTIVE
+    vertices, so that the 2-D pooling / unpooling of models.py:1131-1136, 1150-1155, 1348-1355 becomes the 1-D pooling over
+    consecutive vertices of the HEALPix kernels: the grid is cut into 2^depth x 2^depth blocks, blocks in row-major order,
+    Z (Morton) order inside a block.  Returns perm with perm[k] = row-major index of the k-th vertex.  depth defaults to the
+    largest one both sides allow; the order induced on the grid pooled by 2^s is the same construction with depth - s."""
+    rows, cols = int(rows), int(cols)
+    dmax = 0
+    while rows % (2 << dmax) == 0 and cols % (2 << dmax) == 0:
+        dmax += 1
+    depth = dmax if depth is None else int(depth)
+    if depth > dmax:
+        raise ValueError('a {} x {} grid cannot be pooled {} times by 2 x 2'.format(rows, cols, depth))
+    k = np.arange(rows * cols, dtype=np.int64)
+    blk, within = k >> (2 * depth), k & ((1 << (2 * depth)) - 1)
+    bi, bj = np.divmod(blk, cols >> depth)
+    wi = np.zeros_like(k)
+    wj = np.zeros_like(k)
+    for b in range(depth):
+        wj |= ((within >> (2 * b)) & 1) << b
+        wi |= ((within >> (2 * b + 1)) & 1) << b
+    return ((bi << depth) + wi) * cols + (bj << depth) + wj
 
 
 def equiangular_laplacian(bw=16, lap_type='normalized', indexes=None, dtype=np.float32, use_4=False):
@@ -232,9 +260,8 @@ def build_laplacians(nsides, indexes=None, use_4=False, sampling='healpix', std=
     nside_last = -1
     built = 0
     for i, (nside, index, sigma, mat) in enumerate(zip(nsides, indexes, std, full)):
-        if isinstance(nside, tuple):
-            if sampling == 'equiangular' and nside[0] != nside[1]:
-                raise NotImplementedError('equiangular grids with different bandwidths in latitude and longitude')
+        bw = nside
+        if isinstance(nside, tuple):                           # equiangular: (bandwidth in colatitude, in longitude), utils.py:401-403
             nside = nside[0]
         if i > 0 and sampling != 'icosahedron':
             p.append((nside_last // nside)**2)
@@ -250,7 +277,7 @@ def build_laplacians(nsides, indexes=None, use_4=False, sampling='healpix', std=
                 from . import graphs
                 laplacian = graphs.icosahedron_laplacian(order=nside, indexes=index)    # utils.py:370-376, 412
             elif sampling == 'equiangular':
-                laplacian = equiangular_laplacian(bw=nside, indexes=index, use_4=use_4)       # utils.py:415-416
+                laplacian = equiangular_laplacian(bw=bw, indexes=index, use_4=use_4)          # utils.py:415-416
             else:
                 raise ValueError('Unknown sampling: ' + sampling)
             lm = estimate_lmax(laplacian) if lmax is None else lmax[built]

@@ -18,7 +18,7 @@ class OracleCgcnn:
     def __init__(self, L, F, K, p, batch_norm, M, num_feat_in=1, conv='chebyshev5', pool='max',
                  activation='relu', statistics=None, Fseg=None, regularization=0, dropout=1,
                  regression=False, dense=False, sampling='healpix', dtype=torch.float32, seed=2,
-                 finest_vertices=10 * 4 ** 5 + 2, weighted=False, masked=False):
+                 finest_vertices=10 * 4 ** 5 + 2, weighted=False, masked=False, ratio=1.):
         if not len(L) == len(F) == len(K) == len(p) == len(batch_norm):          # models.py:937-940
             raise ValueError('Wrong specification of the convolutional layers')
         self.Ls = [ops.sparse_to_torch(l, dtype) for l in L]
@@ -28,6 +28,7 @@ class OracleCgcnn:
         self.regression, self.dense, self.sampling = regression, dense, sampling
         self.conv = getattr(ops, conv)                                            # models.py:1017
         self.weighted = weighted
+        self.ratio = ratio                          # equiangular grids: columns / rows (deepsphere.__init__, models.py:1832-1836)
         self.masked = masked                        # a `mask` argument was given: masked MSE (models.py:785-787, 1030-1032)
         self.pool_kind, self.act, self.stat = pool, ops.ACTIVATIONS[activation], statistics
         self.dtype = dtype
@@ -148,7 +149,7 @@ class OracleCgcnn:
                 x = self._bn_apply(x, sc, training, new_state)              # 1235-1236
             x = ops.bias(x, P[sc + '/bias'])                                 # 1238
             x = self.act(x)                                                  # 1239
-            x = ops.pool(x, self.p[i], self.pool_kind, self.sampling)        # 1243
+            x = ops.pool(x, self.p[i], self.pool_kind, self.sampling, self.ratio)        # 1243
             if (i + 1) in self.bf16_layers:
                 x = ops._RoundBf16.apply(x)                                  # the product stores this layer's output as bfloat16
             pool_layers.append(x)                                            # 1245
@@ -178,7 +179,7 @@ class OracleCgcnn:
                     p = self.p[-i - 1] if i + 1 <= n else self.finest_vertices
                 else:
                     p = self.p[-i]
-                x = ops.unpool(x, p, self.pool_kind, self.sampling)           # 1304
+                x = ops.unpool(x, p, self.pool_kind, self.sampling, self.ratio)           # 1304
                 sc = 'upconv{}'.format(j)
                 x = self.conv(x, self.Ls[-i], P[sc + '/weights'], self.K[-i])  # 1307
                 x = ops.bias(x, P[sc + '/bias'])                              # 1308

@@ -124,16 +124,16 @@ def batch_normalization(x, moving_mean, moving_var, training, momentum=0.9, eps=
     return y, new_mean, new_var
 
 
-def pool(x, p, kind, sampling):
+def pool(x, p, kind, sampling, ratio=1.):
     """models.py:1128-1163: healpix = max/avg over p consecutive vertices (ksize [1,p,1,1],
     SAME padding, M divisible by p); icosahedron = keep the first p vertices."""
     if p > 1:
         if sampling == 'equiangular':
-            # models.py:1131-1136, 1150-1155: the vertices as a [sqrt(M/ratio), sqrt(M*ratio)] grid (ratio = 1 here), 2-D pooling
-            # with a sqrt(p) x sqrt(p) window, SAME padding (sizes divisible by the window)
+            # models.py:1131-1136, 1150-1155: the vertices as a [sqrt(M/ratio), sqrt(M*ratio)] grid, 2-D pooling with a
+            # sqrt(p) x sqrt(p) window, SAME padding (sizes divisible by the window)
             N, M, F = x.shape
-            H, s = int(round(M ** 0.5)), int(round(p ** 0.5))
-            xr = x.reshape(N, H // s, s, H // s, s, F)
+            H, W, s = int(round((M / ratio) ** 0.5)), int(round((M * ratio) ** 0.5)), int(round(p ** 0.5))
+            xr = x.reshape(N, H // s, s, W // s, s, F)
             return (xr.amax(dim=(2, 4)) if kind == 'max' else xr.mean(dim=(2, 4))).reshape(N, -1, F)
         if sampling == 'icosahedron':
             return x[:, :p, :]
@@ -143,14 +143,14 @@ def pool(x, p, kind, sampling):
     return x
 
 
-def unpool(x, p, kind, sampling):
+def unpool(x, p, kind, sampling, ratio=1.):
     """models.py:1347-1375.  average: healpix repeats each vertex p times, icosahedron pads to
     p vertices with the constant 1; max: healpix puts the value first and p-1 zeros."""
     N, M, F = x.shape
     if kind == 'average':
         if sampling == 'equiangular':                                                  # (1348-1355): repeat_elements on both axes
-            H, s = int(round(M ** 0.5)), int(round(p ** 0.5))
-            xr = x.reshape(N, H, H, F).repeat_interleave(s, dim=1).repeat_interleave(s, dim=2)
+            H, W, s = int(round((M / ratio) ** 0.5)), int(round((M * ratio) ** 0.5)), int(round(p ** 0.5))
+            xr = x.reshape(N, H, W, F).repeat_interleave(s, dim=1).repeat_interleave(s, dim=2)
             return xr.reshape(N, -1, F)
         if sampling == 'icosahedron':
             return TF.pad(x, (0, 0, 0, int(p - M)), mode='constant', value=1.0)   # (1358)

@@ -78,7 +78,7 @@ def run_case(ref_models, name, out, kw, x, labels, training, sphere=None, L=None
     rec = {}
     cfg = dict(kw)
     cfg.update(sampling=model.sampling if hasattr(model, 'sampling') else sampling, p=[int(v) for v in model.p],
-               training=bool(training), n_levels=len(model.L))
+               training=bool(training), n_levels=len(model.L), ratio=float(getattr(model, 'ratio', 1.)))
     rec['config'] = np.array(json.dumps(cfg))
     for i, Li in enumerate(model.L):
         Li = Li.tocoo()
@@ -199,6 +199,30 @@ def main():
     Ls = [equi_L(8), equi_L(4), equi_L(4)]
     run_case(ref_models, 'equi_dense', out, kw, x, rs.randint(0, 3, (2, 256)), True, L=Ls, p=[4, 1, 1], sampling='equiangular')
 
+    # J. rectangular equiangular grids (`ratio` = columns / rows, set by deepsphere.__init__ from a pair of bandwidths,
+    #    models.py:1832-1836; the reshape of models.py:1134, 1153, 1353): an 8 x 12 grid (ratio 1.5, the aspect of the climate
+    #    data's 768 x 1152 grid) pooled twice, and its encoder-decoder.  Only the operator code is exercised: random symmetric
+    #    matrices stand for the Laplacians (the rectangular graph comes from the absent fork's SphereEquiangular)
+    ref_models.cgcnn.ratio = 1.5
+    Ls = [random_graph(96, 4, 31), random_graph(24, 4, 32), random_graph(6, 3, 33)]
+    kw = dict(F=[4, 6, 3], K=[3, 3, 2], batch_norm=[True, True, False], M=[], pool='max', statistics='mean', num_feat_in=2)
+    x = rs.randn(3, 96, 2).astype(np.float32)
+    run_case(ref_models, 'equi_rect_max', out, kw, x, rs.randint(0, 3, 3), True, L=Ls, p=[4, 4, 1], sampling='equiangular')
+    kw = dict(F=[4, 5, 3], K=[3, 2, 2], batch_norm=[True, False, True], M=[], pool='average', dense=True, Fseg=3, num_feat_in=2)
+    Ls = [random_graph(96, 4, 34), random_graph(24, 4, 35), random_graph(24, 4, 36)]
+    run_case(ref_models, 'equi_rect_dense', out, kw, x, rs.randint(0, 3, (3, 96)), True, L=Ls, p=[4, 1, 1], sampling='equiangular')
+    ref_models.cgcnn.ratio = 1.
+
+    # Cases that go through the reference's build_laplacians carry an ARPACK lmax (random start vector, utils.py:423): a
+    # regeneration moves them by ~1e-7.  Keep the committed vectors of the cases that already exist and only add new ones
+    # (--all rewrites everything).
+    path = os.path.join(HERE, 'ops_golden.npz')
+    if os.path.exists(path) and '--all' not in sys.argv:
+        old = np.load(path, allow_pickle=False)
+        have = {k.split('::')[0] for k in old.files}
+        out = {k: v for k, v in out.items() if k.split('::')[0] not in have}
+        print('kept', sorted(have), 'added', sorted({k.split('::')[0] for k in out}))
+        out.update({k: old[k] for k in old.files})
     np.savez_compressed(os.path.join(HERE, 'ops_golden.npz'), **out)
     print('wrote', os.path.join(HERE, 'ops_golden.npz'), os.path.getsize(os.path.join(HERE, 'ops_golden.npz')), 'bytes')
 

@@ -84,3 +84,44 @@ def test_station_graph_of_the_ghcn_experiment():
     assert W.shape == (300, 300) and abs(W - W.T).max() == 0
     L = graphs.sphere_knn_laplacian(lon, lat, 10)
     np.testing.assert_allclose(np.asarray(L.sum(axis=1)).ravel(), 0, atol=1e-4)      # combinatorial: rows sum to zero
+
+
+@pytest.mark.parametrize('rows,cols', [(8, 8), (8, 12), (6, 9), (24, 36), (4, 32)])
+def test_equiangular_block_order_makes_2d_windows_consecutive(rows, cols):
+    """The product pools p CONSECUTIVE vertices; on an equiangular grid the reference pools sqrt(p) x sqrt(p) windows of the
+    [rows, cols] reshape (models.py:1131-1136).  utils.equiangular_block_order is the vertex order that makes the two the same,
+    level after level: checked here against the oracle's 2-D pooling / unpooling for every depth the grid allows."""
+    import torch
+    from deepsphere_tf1_b200 import utils
+    from oracle import ops as oops
+    perm = utils.equiangular_block_order(rows, cols)
+    assert sorted(perm.tolist()) == list(range(rows * cols))
+    ratio = cols / rows
+    rs = np.random.RandomState(rows * 100 + cols)
+    x = torch.from_numpy(rs.randn(2, rows * cols, 3).astype(np.float32))
+    r, c, xz = rows, cols, x[:, perm]
+    while r % 2 == 0 and c % 2 == 0:
+        for kind in ('max', 'average'):
+            want = oops.pool(x, 4, kind, 'equiangular', ratio)                      # row-major in, row-major out
+            got = xz.reshape(2, -1, 4, 3)
+            got = got.max(dim=2).values if kind == 'max' else got.mean(dim=2)        # what the HEALPix kernels do
+            coarse = utils.equiangular_block_order(r // 2, c // 2)
+            assert torch.allclose(got, want[:, coarse], atol=1e-6), (r, c, kind)
+        # unpooling: repeat each vertex 4 times in the block order == repeat_elements on both axes (models.py:1348-1355)
+        up = oops.unpool(want, 4, 'average', 'equiangular', ratio)
+        assert torch.equal(want[:, coarse].repeat_interleave(4, dim=1), up[:, utils.equiangular_block_order(r, c)])
+        x, xz, r, c = want, want[:, coarse], r // 2, c // 2
+    with pytest.raises(ValueError):
+        utils.equiangular_block_order(rows, cols, depth=10)
+
+
+def test_rectangular_equiangular_graph():
+    """Pair of bandwidths (utils.py:401-403): the in-repo 8-neighbour construction on the 2 bw[0] x 2 bw[1] grid; equal bandwidths
+    give the square graph bit for bit (which the golden vectors pin to the reference's own function)."""
+    from deepsphere_tf1_b200 import utils
+    W = utils.equiangular_weightmatrix((4, 6))
+    assert W.shape == (96, 96) and (np.diff(W.indptr) == 8).all() and np.isfinite(W.data).all()
+    assert abs(W - W.T).max() < 1e-5 * W.max()
+    assert (utils.equiangular_weightmatrix(4) != utils.equiangular_weightmatrix((4, 4))).nnz == 0
+    L, p = utils.build_laplacians([(8, 12), (4, 6), (2, 3), (2, 3)], sampling='equiangular')
+    assert p == [4, 4, 1] and [l.shape[0] for l in L] == [384, 96, 24]

@@ -60,7 +60,7 @@ class Case(object):
 
 
 def build_oracle(c):
-    o = OracleCgcnn(c.L, p=c.cfg['p'], sampling=c.cfg['sampling'], **c.model_kwargs())
+    o = OracleCgcnn(c.L, p=c.cfg['p'], sampling=c.cfg['sampling'], ratio=c.cfg.get('ratio', 1.), **c.model_kwargs())
     assert list(o.params.keys()) == c.var_names                         # the reference's variable names and creation order
     for k in c.var_names:
         v = torch.from_numpy(c['var/' + k])
@@ -119,7 +119,7 @@ def build_product(c, dev):
     kw = c.model_kwargs()
     cls = models.cgcnn
     if c.cfg['sampling'] != 'healpix':
-        cls = type('cgcnn_' + c.cfg['sampling'], (models.cgcnn,), {'sampling': c.cfg['sampling']})
+        cls = type('cgcnn_' + c.cfg['sampling'], (models.cgcnn,), {'sampling': c.cfg['sampling'], 'ratio': c.cfg.get('ratio', 1.)})
     m = cls(L=c.L, p=c.cfg['p'], num_epochs=1, scheduler=lambda step: 1e-3,
             optimizer=lambda lr: optimizers.GradientDescentOptimizer(lr), batch_size=c.x.shape[0], dir_name='_golden',
             verbose=False, device=dev, **kw)

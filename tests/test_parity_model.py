@@ -470,6 +470,27 @@ def test_equiangular_grid_2d_pooling(head):
     _check_step(oracle, model, x, labels.astype(np.int64) if head != 'dense' else labels.astype(np.int64), opt=opt)
 
 
+def test_rectangular_equiangular_grid_through_the_front_end():
+    """deepsphere(nsides=[(bw_colatitude, bw_longitude), ...], sampling='equiangular'): `ratio` = columns / rows
+    (models.py:1832-1836) drives the reshape of the 2-D pooling (models.py:1134).  16 x 24 grid, ratio 1.5 (the aspect of the
+    climate data's 768 x 1152 grid), pooled twice; the vertices go through the blocked Z order of
+    utils.equiangular_block_order.  (The operator code is pinned to the reference by the golden cases equi_rect_*.)"""
+    from deepsphere_tf1_b200 import models, optimizers
+    from oracle.model import OracleCgcnn
+    nsides = [(8, 12), (4, 6), (2, 3), (2, 3)]
+    kw = dict(F=[6, 8, 3], K=[3, 3, 2], batch_norm=[True, True, False], M=[], pool='max', statistics='mean', num_feat_in=2)
+    model = models.deepsphere(nsides=nsides, sampling='equiangular', num_epochs=1, batch_size=3, eval_frequency=10,
+                              dir_name='_test_parity', verbose=False,
+                              optimizer=lambda lr: optimizers.AdamOptimizer(lr, epsilon=1e-8),
+                              scheduler=lambda step: optimizers.exponential_decay(2e-3, step, 10, 0.9), **kw)
+    assert model.ratio == 1.5 and list(model.p) == [4, 4, 1] and [l.shape[0] for l in model.L] == [384, 96, 24]
+    oracle = OracleCgcnn(model.L, p=model.p, sampling='equiangular', ratio=model.ratio, seed=2, **kw)
+    copy_weights(oracle, model)
+    rs = np.random.RandomState(6)
+    x = rs.randn(3, 384, 2).astype(np.float32)
+    _check_step(oracle, model, x, rs.randint(0, 3, size=3).astype(np.int64))
+
+
 def test_use_4_neighbour_graph_model():
     """`use_4=True` (utils.py:336-337, 484-591): the 4-neighbour patch graph (ELL width 5) through the whole model."""
     from deepsphere_tf1_b200 import utils
