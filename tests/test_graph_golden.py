@@ -117,6 +117,35 @@ def test_healpy_docstring_example():
     want = [11, 7, 3, -1, 0, 5, 8, -1]
     assert list(ohp.get_all_neighbours(1, 4)) == want
     assert list(php.get_all_neighbours(1, 4)) == want
+    # second example of the same docstring: hp.get_all_neighbours(1, np.pi / 2, np.pi / 2) -- the pixel at (theta, phi) =
+    # (pi / 2, pi / 2) is base pixel 5
+    want = [8, 4, 0, -1, 1, 6, 9, -1]
+    assert list(ohp.get_all_neighbours(1, 5)) == want
+    assert list(php.get_all_neighbours(1, 5)) == want
+
+
+def test_published_pixel_centres():
+    """Known answers that do not come from this repository (healpy itself is absent):
+    (1) the 12 base pixels (Gorski et al. 2005, fig. 4: z = 2/3, 0, -2/3; phi = pi/4 + k pi/2 in the caps, k pi/2 on the equator;
+        at Nside = 1 the NESTED and RING numbers coincide);
+    (2) Nside = 2, children of base pixel 0 in NESTED order (south, east, west, north) from the ring formulas of the same
+        paper: z = 1 - i^2 / (3 Nside^2) in the cap, 4/3 - 2 i / (3 Nside) in the belt;
+    (3) the (theta, phi) pairs of healpy's own `pix2ang` docstring (`hp.pix2ang(16, [1440, 427, 1520, 0, 3068])`, RING
+        numbers): the pixel SET is the same in both schemes, so each pair must be the centre of exactly one nested pixel."""
+    for mod in (ohp, php):
+        v = np.array(mod.pix2vec(1, np.arange(12) if mod is php else range(12)), dtype=np.float64)
+        z = np.repeat([2 / 3, 0.0, -2 / 3], 4)
+        phi = np.concatenate([np.pi / 4 + np.arange(4) * np.pi / 2, np.arange(4) * np.pi / 2, np.pi / 4 + np.arange(4) * np.pi / 2])
+        np.testing.assert_allclose(v[2], z, atol=1e-15)
+        np.testing.assert_allclose(np.arctan2(v[1], v[0]) % (2 * np.pi), phi, atol=1e-15)
+        v = np.array(mod.pix2vec(2, np.arange(4) if mod is php else range(4)), dtype=np.float64)
+        np.testing.assert_allclose(v[2], [1 / 3, 2 / 3, 2 / 3, 11 / 12], atol=1e-15)
+        np.testing.assert_allclose(np.arctan2(v[1], v[0]), [np.pi / 4, 3 * np.pi / 8, np.pi / 8, np.pi / 4], atol=1e-15)
+    v = np.array(php.pix2vec(16, np.arange(3072)))
+    theta, phi = np.arccos(v[2]), np.arctan2(v[1], v[0]) % (2 * np.pi)
+    for t, f in zip([1.52911759, 0.78550497, 1.57079633, 0.05103658, 3.09055608], [0., 0.78539816, 1.61988371, 0.78539816, 5.49778714]):
+        hit = (np.abs(theta - t) < 2e-8) & (np.abs((phi - f + np.pi) % (2 * np.pi) - np.pi) < 2e-8)
+        assert hit.sum() == 1, (t, f)
 
 
 @pytest.mark.parametrize('nside', [1, 2, 4, 8, 16])
