@@ -329,6 +329,30 @@ def test_prefetched_batches_train_exactly_like_plain_steps(graphed):
     assert_close(pre._P.w, plain._P.w, 1e-5, 'weights after an unannounced batch')
 
 
+@pytest.mark.parametrize('shard', [False, True])
+def test_fit_with_one_sample_per_step(shard):
+    """batch_size = 1 (the only batch size of the vertex-sharded mode): `LabeledDataset.iter(1)` yields un-batched samples like
+    the reference (data.py:58-60); fit / predict(cache=True) restore the batch axis.  `shard`: the vertex-sharded layer program
+    on a single rank (no ghosts, no exchange)."""
+    from deepsphere_tf1_b200 import models, optimizers
+    from deepsphere_tf1_b200.data import LabeledDataset
+    rs = np.random.RandomState(3)
+    n = 12
+    labels = rs.randint(0, 2, size=n)
+    x = rs.randn(n, 192).astype(np.float32) + labels[:, None] * 1.5
+    train, val = LabeledDataset(x[:8], labels[:8]), LabeledDataset(x[8:], labels[8:], shuffle=False)
+    model = models.deepsphere(nsides=[4, 2, 2], new=False, F=[8, 2], K=[3, 3], batch_norm=[True, True], M=[], statistics='mean',
+                              num_epochs=2, batch_size=1, eval_frequency=8, seed=1, verbose=False, vertex_shard=shard,
+                              scheduler=lambda step: 1e-2, optimizer=lambda lr: optimizers.AdamOptimizer(lr),
+                              dir_name='_test_fit_b1')
+    acc, loss_val, loss_train, t_step, t_batch = model.fit(train, val, restore=False, verbose=False)
+    assert len(acc) == len(loss_val) == len(loss_train) == 2 and np.isfinite(loss_train).all() and np.isfinite(loss_val).all()
+    pred, loss = model.predict(val, sess=model, cache=True)              # labels come from the dataset
+    assert pred.shape == (4,) and np.isfinite(loss)
+    pred2 = model.predict(x[8:].reshape(4, 192, 1), sess=model)
+    np.testing.assert_array_equal(pred, pred2)
+
+
 def test_fit_predict_evaluate_api(tmp_path):
     """Reference-style end-to-end use: datasets in, tuples out (models.py:432-618, 343-430)."""
     from deepsphere_tf1_b200 import models, optimizers
