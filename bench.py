@@ -12,9 +12,9 @@ experiments/cosmo/experiment_deepsphere.py:39-47,94-98 at order 2: HEALPix Nside
 statistics='mean', batch 16 per GPU, synthetic maps ~ N(0, 1+3.5^2), fp32.
 
 Prints ONE JSON line (rank 0).  `value` = samples/s with the batch resident in HBM; `e2e` = the
-same through the public API (`model.train_step(host batch, next_batch=...)`, the call fit() makes:
-pinned host -> device copy of a batch and its labels on a copy stream overlapping the step's kernels,
-device -> host read of the loss, every step); `roofline` = the ChebConv
+same through the public API (`model.train_step(host batch, next_batch=...)` + `model.loss_handle()`, the loop fit()
+runs: pinned host -> device copy of a batch and its labels on a copy stream overlapping the step's kernels,
+device -> host read of every step's loss, one step behind); `roofline` = the ChebConv
 recurrence SpMM step timed alone with CUDA events (back to back over operand sets >> L2) against the
 measured HBM copy bandwidth; `cpu_baseline` = the oracle (restated reference) timed on this box's
 host cores; `parity` = one step of this very configuration against the float64 oracle (fp32 path, and
@@ -340,6 +340,22 @@ def parity_check(L, p, world, rank, dev, tol=1e-4, with_bf16=True):
     return out
 
 
+def e2e_loop(model, x_pin, l_pin, nxt, steps):
+    """The inner loop of fit() (models.py: train_step + loss_handle): every step copies a full batch host -> device (on the copy
+    stream, overlapping the step) and reads its loss back to the host -- one step behind, i.e. the host waits for the loss of
+    step i - 1 after it has enqueued step i, and for the last one before the timed region ends.  `steps` losses are read."""
+    pending, last = None, float('nan')
+    for _ in range(steps):
+        model.train_step(x_pin, l_pin, next_batch=nxt)
+        handle = model.loss_handle()
+        if pending is not None:
+            last = pending.value()
+        pending = handle
+    if pending is not None:
+        last = pending.value()
+    return last
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -400,9 +416,7 @@ def run_gpu(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        _, loss = model.train_step(x_pin, l_pin, next_batch=nxt)
-        last_loss = float(loss)
+    last_loss = e2e_loop(model, x_pin, l_pin, nxt, args.steps)
     e1.record()
     barrier()
     t_e2e = e0.elapsed_time(e1) * 1e-3
@@ -454,9 +468,7 @@ def run_gpu(args):
             float(lossb)
         barrier()
         e0.record()
-        for _ in range(args.steps):
-            _, lossb = mb.train_step(x_pin, l_pin, next_batch=nxt)
-            lastb = float(lossb)
+        lastb = e2e_loop(mb, x_pin, l_pin, nxt, args.steps)
         e1.record()
         barrier()
         tb_e2e = e0.elapsed_time(e1) * 1e-3
@@ -519,8 +531,10 @@ def run_gpu(args):
             'e2e': {'value': B_global * args.steps / t_e2e, 'unit': 'samples/s',
                     'h2d_bytes_per_step': int(x_pin.numel() * 4 + l_pin.numel() * 4 + 32), 'd2h_bytes_per_step': 4,
                     'ms_per_step': t_e2e / args.steps * 1e3,
-                    'api': 'train_step(pinned host batch, next_batch=...): the following batch is copied on a copy stream '
-                           'while the step runs (as fit() does); loss read back every step'},
+                    'api': 'the loop of fit(): train_step(pinned host batch, next_batch=...) copies the following batch on a copy '
+                           'stream while the step runs; the loss of EVERY step is read back to the host through '
+                           'model.loss_handle(), one step behind (the host waits for the loss of step i - 1 after enqueuing step '
+                           'i, and for the last one inside the timed region)'},
             'gpu_launches': int(per_step * args.steps),
             'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu, 'parity': parity, 'final_loss': last_loss,
             'bf16_mode': bf16,

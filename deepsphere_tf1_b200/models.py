@@ -427,6 +427,17 @@ class _FcStage(object):
         return ops.fc_bwd(x, W, y, dout, m._P.gviews[self.scope + '/weights'], db, self.act, need_dx)
 
 
+class _LossHandle(object):
+    """Loss of one training step on its way to the host (`cgcnn.loss_handle`)."""
+
+    def __init__(self, host, event, slot):
+        self._host, self._event, self._slot = host, event, slot
+
+    def value(self):
+        self._event.synchronize()
+        return float(self._host[self._slot])
+
+
 class base_model(object):
     """Run loops shared by all models (reference `base_model`, models.py:68-879)."""
 
@@ -619,6 +630,8 @@ class base_model(object):
 
         times = []
         loss = float('nan')
+        pending = None
+
         def fetch():
             d, l = next(train_iter)
             if not isinstance(d, (np.ndarray, torch.Tensor)):
@@ -633,8 +646,15 @@ class base_model(object):
             evaluate = (step % self.eval_frequency == 0) or (step == num_steps)
             t_begin_load = perf_counter()
             learning_rate, loss_dev = self.train_step(batch_data, batch_labels, next_batch=coming)
-            if evaluate or self.sync_every_step:
+            if evaluate:
                 loss = float(loss_dev)                      # device -> host read of the step's loss
+                pending = None
+            elif self.sync_every_step:
+                # the loss of every step reaches the host, one step behind: wait for step i - 1 now that step i is enqueued
+                handle = self.loss_handle()
+                if pending is not None:
+                    loss = pending.value()
+                pending = handle
             t_end = perf_counter()
             times.append(t_end - t_begin)
             if not evaluate:
@@ -835,7 +855,8 @@ class cgcnn(base_model):
     statistics choices, Fseg, regularization, dropout, batch_size, eval_frequency, regression,
     dense, dir_name.  Extra keyword arguments: `device` (default current CUDA device), `seed`,
     `process_group` (torch.distributed group for data parallelism; default: the world group if
-    initialised), `cuda_graph` (replay the training step as one CUDA graph), `sync_every_step`.
+    initialised), `cuda_graph` (replay the training step as one CUDA graph), `sync_every_step` (fit reads the loss of every step,
+    one step behind, instead of only at the evaluation steps).
     """
 
     def __init__(self, L, F, K, p, batch_norm, M,
@@ -1428,6 +1449,21 @@ class cgcnn(base_model):
         if next_batch is not None:
             self._prefetch(next_batch[0], next_batch[1])
         return lr, self._loss
+
+    def loss_handle(self):
+        """Start the device -> host copy of the loss of the step just enqueued (4 bytes into one of two pinned slots, on the
+        compute stream, before the next step clears the accumulator) and return a handle whose `.value()` waits for that copy
+        only.  fit() reads the loss of step i - 1 through such a handle AFTER it has enqueued step i, so the host never leaves
+        the GPU without work between two steps (the `sess.run` of the reference returns the loss synchronously,
+        models.py:535-536: there the device idles while Python prepares the next feed)."""
+        if getattr(self, '_loss_slots', None) is None:
+            self._loss_slots = (torch.zeros(2, dtype=torch.float32).pin_memory(), [torch.cuda.Event(), torch.cuda.Event()], [0])
+        host, events, turn = self._loss_slots
+        i = turn[0]
+        turn[0] ^= 1
+        host[i:i + 1].copy_(self._loss, non_blocking=True)
+        events[i].record()
+        return _LossHandle(host, events[i], i)
 
     def _prefetch(self, batch_data, batch_labels):
         """Start the host -> device copy of a coming batch on the copy stream into one of two staging pairs."""

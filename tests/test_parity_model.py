@@ -329,6 +329,34 @@ def test_prefetched_batches_train_exactly_like_plain_steps(graphed):
     assert_close(pre._P.w, plain._P.w, 1e-5, 'weights after an unannounced batch')
 
 
+@pytest.mark.parametrize('graphed', [False, True])
+def test_loss_handle_delivers_the_loss_of_every_step(graphed):
+    """`loss_handle()` (what fit() and bench.py's e2e loop read): the loss of step i, copied into a pinned slot before step
+    i + 1 clears the accumulator, read one step behind -- the same numbers as synchronous reads, in the same order."""
+    L = [healpix_L(4), healpix_L(2)]
+    kw = dict(F=[8, 4], K=[3, 3], p=[4, 1], batch_norm=[True, True], M=[], statistics='mean', cuda_graph=graphed)
+    _, m = _pair(L, **kw)
+    rs = np.random.RandomState(8)
+    batches = [(torch.from_numpy(rs.randn(4, 192, 1).astype(np.float32)).pin_memory(),
+                torch.from_numpy(rs.randint(0, 4, size=4).astype(np.int32)).pin_memory()) for _ in range(6)]
+    sync, lagged, pending = [], [], None
+    for t, (x, labels) in enumerate(batches):
+        _, loss = m.train_step(x, labels, next_batch=batches[t + 1] if t + 1 < len(batches) else None)
+        handle = m.loss_handle()
+        if t % 2 == 0:
+            sync.append(float(loss))              # a synchronous read in between must not disturb the slots
+        else:
+            sync.append(None)
+        if pending is not None:
+            lagged.append(pending.value())
+        pending = handle
+    lagged.append(pending.value())
+    assert len(lagged) == len(batches) and len(set(lagged)) == len(batches)
+    for a, b in zip(sync, lagged):
+        assert a is None or a == b
+    assert lagged[-1] == float(m._loss)
+
+
 @pytest.mark.parametrize('shard', [False, True])
 def test_fit_with_one_sample_per_step(shard):
     """batch_size = 1 (the only batch size of the vertex-sharded mode): `LabeledDataset.iter(1)` yields un-batched samples like

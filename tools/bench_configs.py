@@ -200,8 +200,7 @@ def run(n, steps, warm=3):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        last = float(model.train_step(x_pin, l_pin, next_batch=nxt)[1])
+    last = bench.e2e_loop(model, x_pin, l_pin, nxt, steps)
     e1.record()
     torch.cuda.synchronize()
     t_e2e = e0.elapsed_time(e1) * 1e-3
