@@ -60,6 +60,12 @@ def synthetic_batch(B, seed):
     return x, labels
 
 
+def bench_config(global_batch):
+    """`config` of the JSON line, the same for both arms (--impl b200 / reference)."""
+    return {'workload': WORKLOAD, 'global_batch': global_batch,
+            'l2': 'no flush between steps: one step streams > 2 GB of activations per GPU at batch 16, >> 126 MB L2'}
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -137,16 +143,21 @@ def run_reference(args):
         return
     L, p = build_laplacians(args.recompute_lmax)
     B = 16
-    steps = max(1, min(args.steps, 5))
-    times, cores = cpu_reference_steps(L, p, B, steps, 1)
+    # K steps and W warm-ups as asked (a step of 16 samples takes ~1.3 s on the GPU box's 16 cores); capped so that the run
+    # always ends within a few minutes
+    steps, warm = max(1, min(args.steps, 60)), max(1, min(args.warmup, 5))
+    world = max(1, args.gpus)
+    times, cores = cpu_reference_steps(L, p, B, steps, warm)
     ms = float(np.mean(times)) * 1e3
     v = B / (ms / 1e3)
-    sample = '{} full training steps of batch {} (after 1 warm-up), torch-CPU oracle, {} threads'.format(steps, B, cores)
+    sample = ('{} full training steps of {} samples each (after {} warm-up) of the same workload, torch-CPU oracle, {} threads; '
+              'samples/s does not depend on how many such batches make the global batch').format(steps, B, warm, cores)
     print(json.dumps({
-        'impl': 'reference', 'metric': 'train samples/s', 'value': v, 'unit': 'samples/s', 'n_gpus': 0,
-        'steps': steps, 'warmup': 1, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'impl': 'reference', 'metric': 'train samples/s', 'value': v, 'unit': 'samples/s', 'n_gpus': world,
+        'steps': steps, 'warmup': warm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': args.scaling,
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'global_batch': B, 'parallelism': 'host CPU, {} threads'.format(cores)},
+        'config': bench_config(B * world if args.scaling == 'weak' else B),
+        'details': {'parallelism': 'host CPU of rank 0, {} threads; no GPU is used'.format(cores)},
         'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -523,11 +534,9 @@ def run_gpu(args):
             'n_gpus': world, 'steps': args.steps, 'warmup': warm,
             'ms_per_step': t_dev / args.steps * 1e3, 'higher_is_better': True, 'scaling': args.scaling,
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'global_batch': B_global, 'local_batch': B_local,
-                       'parallelism': 'dp{} (SyncBN + one flat NCCL gradient all-reduce)'.format(world),
-                       'cuda_graph': bool(model.cuda_graph),
-                       'l2': 'no flush between steps: one step streams > 2 GB of activations per GPU at batch 16, '
-                             '>> 126 MB L2'},
+            'config': bench_config(B_global),
+            'details': {'local_batch': B_local, 'cuda_graph': bool(model.cuda_graph),
+                        'parallelism': 'dp{} (SyncBN + one flat NCCL gradient all-reduce)'.format(world)},
             'e2e': {'value': B_global * args.steps / t_e2e, 'unit': 'samples/s',
                     'h2d_bytes_per_step': int(x_pin.numel() * 4 + l_pin.numel() * 4 + 32), 'd2h_bytes_per_step': 4,
                     'ms_per_step': t_e2e / args.steps * 1e3,
