@@ -82,6 +82,8 @@ def test_model_restores_from_tensorflow_checkpoint(dev, tmp_path):
     assert unused == [] and b.global_step == 3
     assert torch.equal(a._P.w, b._P.w) and all(torch.equal(a._state[k], b._state[k]) for k in a._state)
     la, lb = float(a.train_step(x, lab)[1]), float(b.train_step(x, lab)[1])
-    assert la == lb                                                         # same weights AND same Adam moments
+    # same weights AND same Adam moments; not bit for bit: the batch-norm sums are accumulated with atomics, whose order (hence
+    # the last bit of a mean) differs from launch to launch
+    assert la == pytest.approx(lb, rel=1e-6)
     # the weight gradients are summed with red.global.add: the order differs from launch to launch, not the moments they meet
     assert torch.allclose(a._P.w, b._P.w, rtol=0, atol=1e-6)
