@@ -84,6 +84,7 @@ def test_model_restores_from_tensorflow_checkpoint(dev, tmp_path):
     la, lb = float(a.train_step(x, lab)[1]), float(b.train_step(x, lab)[1])
     # same weights AND same Adam moments; not bit for bit: the batch-norm sums are accumulated with atomics, whose order (hence
     # the last bit of a mean) differs from launch to launch
-    assert la == pytest.approx(lb, rel=1e-6)
-    # the weight gradients are summed with red.global.add: the order differs from launch to launch, not the moments they meet
-    assert torch.allclose(a._P.w, b._P.w, rtol=0, atol=1e-6)
+    assert la == pytest.approx(lb, rel=1e-5), (la, lb)
+    # the weight gradients are summed with red.global.add: the order differs from launch to launch, not the moments they meet.  One
+    # Adam step moves a weight by ~lr = 1e-2: a lost or misplaced moment shows at 1e-3, the summation order at 1e-7
+    assert torch.allclose(a._P.w, b._P.w, rtol=0, atol=1e-5), float((a._P.w - b._P.w).abs().max())
