@@ -644,11 +644,18 @@ class base_model(object):
             batch_data, batch_labels = coming
             coming = fetch() if step < num_steps else None          # handed to train_step: its copy overlaps this step
             evaluate = (step % self.eval_frequency == 0) or (step == num_steps)
+            trace = None
+            if evaluate and self.profile and self.rank == 0:
+                from .summary import StepTrace               # tf.RunOptions(FULL_TRACE) + RunMetadata, models.py:514-519
+                trace = StepTrace()
+                trace.start()
             t_begin_load = perf_counter()
             learning_rate, loss_dev = self.train_step(batch_data, batch_labels, next_batch=coming)
             if evaluate:
                 loss = float(loss_dev)                      # device -> host read of the step's loss
                 pending = None
+                if trace is not None:
+                    trace.stop()
             elif self.sync_every_step:
                 # the loss of every step reaches the host, one step behind: wait for step i - 1 now that step i is enqueued
                 handle = self.loss_handle()
@@ -691,6 +698,8 @@ class base_model(object):
                 for name in self._P.views:                   # tf.summary.histogram(var.op.name, var) and its gradient
                     hist[name] = self._P.views[name].detach().cpu().numpy()
                     hist[name + '/gradients'] = self._P.gviews[name].detach().cpu().numpy()
+                if trace is not None:                        # writer.add_run_metadata(run_metadata, 'step%d'), models.py:604-605
+                    sc['profile/step_kernel_us'] = trace.write(self._get_path('summaries'), step)
                 writer.add_summary(step, sc, hist)
                 writer.flush()
             if verbose:
@@ -856,7 +865,9 @@ class cgcnn(base_model):
     dense, dir_name.  Extra keyword arguments: `device` (default current CUDA device), `seed`,
     `process_group` (torch.distributed group for data parallelism; default: the world group if
     initialised), `cuda_graph` (replay the training step as one CUDA graph), `sync_every_step` (fit reads the loss of every step,
-    one step behind, instead of only at the evaluation steps).
+    one step behind, instead of only at the evaluation steps).  `profile=True` traces the training step of every evaluation as
+    upstream (models.py:514-519, 604-605): `summaries/<dir_name>/trace-step<N>.json` (Chrome trace) and `kernels-step<N>.txt`
+    (summary.StepTrace); `debug` (the TF debugger session, models.py:471-472) has no counterpart and is ignored.
     """
 
     def __init__(self, L, F, K, p, batch_norm, M,

@@ -113,6 +113,58 @@ class FileWriter(object):
         self._f.close()
 
 
+class StepTrace(object):
+    """`profile=True` (deepsphere/models.py:514-519, 604-605): the reference runs the training step of every evaluation with
+    `tf.RunOptions(trace_level=FULL_TRACE)` and hands the `RunMetadata` to the summary writer.  Here the same step runs under
+    torch.profiler (CUPTI activity records; the kernels of a CUDA-graph replay are traced like eager launches) and what is kept
+    is the device timeline: `trace-step<N>.json` (Chrome trace format: chrome://tracing, Perfetto, TensorBoard's profile
+    plugin) and `kernels-step<N>.txt` (time and launch count per kernel, largest first) in the summary directory.  Numbers taken
+    under the profiler are attribution, not measurements: the step time that `fit` returns excludes nothing and is slower on
+    traced steps, exactly as upstream."""
+
+    def __init__(self):
+        from torch.profiler import profile, ProfilerActivity
+        self._prof = profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA])
+        self._on = False
+
+    def start(self):
+        self._prof.__enter__()
+        self._on = True
+
+    def stop(self):
+        import torch
+        if self._on:
+            torch.cuda.synchronize()
+            self._prof.__exit__(None, None, None)
+            self._on = False
+
+    def kernels(self):
+        """[(kernel name, microseconds, launches)] of the traced region, largest first."""
+        tot = {}
+        for ev in self._prof.events():
+            if ev.device_type.name != 'CUDA' or not ev.name:
+                continue
+            name = ev.name.replace('(anonymous namespace)::', '').replace('void ', '').replace('dsb200::', '').split('(')[0]
+            d = tot.setdefault(name, [0.0, 0])
+            d[0] += ev.device_time if hasattr(ev, 'device_time') else ev.cuda_time
+            d[1] += 1
+        return sorted(((n, v[0], v[1]) for n, v in tot.items()), key=lambda r: -r[1])
+
+    def write(self, logdir, step):
+        """Write both files; returns the kernel time of the traced step in microseconds."""
+        self.stop()
+        os.makedirs(logdir, exist_ok=True)
+        self._prof.export_chrome_trace(os.path.join(logdir, 'trace-step{}.json'.format(step)))
+        rows = self.kernels()
+        total = sum(r[1] for r in rows)
+        with open(os.path.join(logdir, 'kernels-step{}.txt'.format(step)), 'w') as f:
+            f.write('{:>10s} {:>5s} {:>6s}  kernel\n'.format('us', 'n', 'share'))
+            for name, us, n in rows:
+                f.write('{:10.1f} {:5d} {:5.1f}%  {}\n'.format(us, n, 100 * us / max(total, 1e-30), name[:120]))
+            f.write('{:10.1f} total kernel time of the step\n'.format(total))
+        return total
+
+
 # ---------------------------------------------------------------------------------------------- reader (tests, tooling)
 def _read_varint(buf, i):
     n = shift = 0

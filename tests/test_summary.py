@@ -1,5 +1,6 @@
 """TensorBoard event files written without TensorFlow (deepsphere_tf1_b200/summary.py): record framing with masked CRC-32C,
 hand-encoded Event / Summary / HistogramProto, read back by the module's own parser."""
+import os
 import struct
 
 import numpy as np
@@ -62,3 +63,33 @@ def test_tensorboard_reads_the_event_file(tmp_path):
     assert got['conv1/weights'].metadata.plugin_data.plugin_name == 'histograms'
     h = tensor_util.make_ndarray(got['conv1/weights'].tensor)          # [buckets, (left, right, count)]
     assert h.shape[1] == 3 and h[:, 2].sum() == 101
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('graph', [False, True])
+def test_fit_with_profile_writes_the_device_trace(graph):
+    """`profile=True` (models.py:514-519, 604-605): the training step of every evaluation is traced; the summary directory holds
+    its timeline and per-kernel table, and the event file the kernel time of that step."""
+    import glob
+    import json
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from deepsphere_tf1_b200 import models, optimizers
+    from deepsphere_tf1_b200.data import LabeledDataset
+    rs = np.random.RandomState(0)
+    x, labels = rs.randn(16, 192).astype(np.float32), rs.randint(0, 2, size=16)
+    train, val = LabeledDataset(x, labels), LabeledDataset(x[:8], labels[:8], shuffle=False)
+    model = models.deepsphere(nsides=[4, 2, 2], new=False, F=[8, 2], K=[3, 3], batch_norm=[True, True], M=[], statistics='mean',
+                              num_epochs=4, batch_size=8, eval_frequency=4, seed=1, verbose=False, profile=True, cuda_graph=graph,
+                              scheduler=lambda step: 1e-2, optimizer=lambda lr: optimizers.AdamOptimizer(lr),
+                              dir_name='_test_profile')
+    model.fit(train, val, restore=False, verbose=False)
+    logdir = model._get_path('summaries')
+    assert sorted(os.path.basename(f) for f in glob.glob(logdir + '/trace-step*.json')) == ['trace-step4.json', 'trace-step8.json']
+    table = open(logdir + '/kernels-step8.txt').read()
+    assert 'optimizer_kernel' in table and 'total kernel time of the step' in table      # this library's kernels, by name
+    trace = json.load(open(logdir + '/trace-step8.json'))
+    assert any('optimizer_kernel' in str(e.get('name', '')) for e in trace['traceEvents'])
+    ev = summary.read_events(glob.glob(logdir + '/events.out.tfevents.*')[0])
+    assert [e[0] for e in ev] == [4, 8] and ev[-1][1]['profile/step_kernel_us'] > 0
