@@ -596,7 +596,7 @@ class base_model(object):
         start_step = 1
         # Data parallel (torchrun): rank 0 alone resets / writes the run directories; the others wait at a barrier before
         # they look at the checkpoint directory, so that every rank takes the same decision.
-        restored = restore and self._latest_checkpoint() is not None
+        restored = restore and self._has_checkpoint()         # own .pt files, or a run directory written by the reference (TF files)
         if not restored and self.rank == 0:
             shutil.rmtree(self._get_path('summaries'), ignore_errors=True)
             shutil.rmtree(ckpt_dir, ignore_errors=True)
@@ -834,6 +834,12 @@ class base_model(object):
         if not files:
             return None
         return max(files, key=lambda f: int(f.split('-')[-1][:-3]))
+
+    def _has_checkpoint(self):
+        if self._latest_checkpoint() is not None:
+            return True
+        from . import tf_checkpoint
+        return tf_checkpoint.latest_checkpoint(self._get_path('checkpoints')) is not None
 
     def _restore_latest(self):
         f = self._latest_checkpoint()

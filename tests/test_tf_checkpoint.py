@@ -88,3 +88,19 @@ def test_model_restores_from_tensorflow_checkpoint(dev, tmp_path):
     # the weight gradients are summed with red.global.add: the order differs from launch to launch, not the moments they meet.  One
     # Adam step moves a weight by ~lr = 1e-2: a lost or misplaced moment shows at 1e-3, the summation order at 1e-7
     assert torch.allclose(a._P.w, b._P.w, rtol=0, atol=1e-5), float((a._P.w - b._P.w).abs().max())
+    # a run directory written by the reference holds TensorFlow files only: predict() without a session restores it
+    # (models.py:851-860), fit(restore=True) continues from its step (models.py:452-457) and leaves the files alone
+    import os
+    import shutil
+    from deepsphere_tf1_b200.data import LabeledDataset
+    c = models.deepsphere(seed=3, dir_name='_tfck_c', **kw)
+    d = c._get_path('checkpoints')
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    b.save_tf_checkpoint(os.path.join(d, 'model-4'))
+    np.testing.assert_array_equal(c.predict(x), b.predict(x, sess=b))
+    assert c.global_step == 4
+    xs, ls = rs.randn(24, 192).astype(np.float32), rs.randint(0, 2, 24)
+    c.fit(LabeledDataset(xs, ls, shuffle=False), LabeledDataset(xs[:4], ls[:4], shuffle=False), restore=True, verbose=False)
+    assert c.global_step == 6 and os.path.exists(os.path.join(d, 'model-4.index')) and os.path.exists(os.path.join(d, 'model-6.pt'))
+    shutil.rmtree(d, ignore_errors=True)
