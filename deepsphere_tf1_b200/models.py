@@ -648,7 +648,8 @@ class base_model(object):
             if evaluate and self.profile and self.rank == 0:
                 from .summary import StepTrace               # tf.RunOptions(FULL_TRACE) + RunMetadata, models.py:514-519
                 trace = StepTrace()
-                trace.start()
+                self._trace_eager = True                    # launch by launch instead of one graph replay: the host side of
+                trace.start()                               # every kernel is part of the trace, as in a FULL_TRACE run
             t_begin_load = perf_counter()
             learning_rate, loss_dev = self.train_step(batch_data, batch_labels, next_batch=coming)
             if evaluate:
@@ -656,6 +657,7 @@ class base_model(object):
                 pending = None
                 if trace is not None:
                     trace.stop()
+                    self._trace_eager = False
             elif self.sync_every_step:
                 # the loss of every step reaches the host, one step behind: wait for step i - 1 now that step i is enqueued
                 handle = self.loss_handle()
@@ -955,6 +957,7 @@ class cgcnn(base_model):
         self.restore, self.tf_dataset = restore, tf_dataset
         self.num_feat_in = num_feat_in
         self.cuda_graph, self.sync_every_step = cuda_graph, sync_every_step
+        self._trace_eager = False
         self.fused_small = fused_small
         self.vertex_shard = bool(vertex_shard)
         if self.vertex_shard:
@@ -1457,10 +1460,10 @@ class cgcnn(base_model):
         if x.shape[0] != self.batch_size:
             raise ValueError('batch of {} samples, model built for batch_size={}'.format(x.shape[0], self.batch_size))
         lr = self._advance_hyper()
-        if self.cuda_graph:
+        if self.cuda_graph and not self._trace_eager:
             self._step_graphed(x, labels)
         else:
-            self._step_device(x, labels)
+            self._step_device(x, labels)                    # also the traced steps of fit(profile=True): every launch visible
         if pre is not None and x is pre[2]:
             pre[5].record()                                 # staging pair consumed (copied into the graph's inputs / used)
         if next_batch is not None:
