@@ -77,6 +77,8 @@ def run_case(ref_models, name, out, kw, x, labels, training, sphere=None, L=None
         tf_shim.nn.softmax = real_softmax
     rec = {}
     cfg = dict(kw)
+    if 'mask' in cfg:
+        cfg['mask'] = True                                                       # only the presence of the argument matters
     cfg.update(sampling=model.sampling if hasattr(model, 'sampling') else sampling, p=[int(v) for v in model.p],
                training=bool(training), n_levels=len(model.L), ratio=float(getattr(model, 'ratio', 1.)))
     rec['config'] = np.array(json.dumps(cfg))
@@ -212,6 +214,38 @@ def main():
     Ls = [random_graph(96, 4, 34), random_graph(24, 4, 35), random_graph(24, 4, 36)]
     run_case(ref_models, 'equi_rect_dense', out, kw, x, rs.randint(0, 3, (3, 96)), True, L=Ls, p=[4, 1, 1], sampling='equiangular')
     ref_models.cgcnn.ratio = 1.
+
+    # K. the GHCN stacks (experiments/ghcn/GHCN_train.py:7-60): the same irregular graph at every layer, no pooling (p = 1), the
+    #    combinatorial Laplacian passed UN-rescaled, dense regression / global regression through a fully connected output,
+    #    and the masked dense loss (`mask=[train, val]`: only its presence matters, models.py:785-787, 1030-1032 -- the last two
+    #    input channels are the masks of the predictions and of the labels)
+    def knn_like(n, deg, seed):
+        g = np.random.RandomState(seed)
+        rows = np.repeat(np.arange(n), deg)
+        cols = (rows + 1 + g.randint(0, n - 1, size=n * deg)) % n             # no self loops
+        W = sparse.coo_matrix((g.rand(n * deg).astype(np.float32), (rows, cols)), shape=(n, n)).tocsr()
+        W = W.maximum(W.T)
+        d = np.asarray(W.sum(axis=1)).ravel()
+        return sparse.coo_matrix(sparse.diags(d) - W, dtype=np.float32)        # L = D - W, spectrum in [0, 2 max d]
+    Lg = knn_like(60, 3, 41)
+    Lg = sparse.coo_matrix(Lg / np.float32(4.0), dtype=np.float32)             # keep T_k(L) x of order one without rescale_L
+    kw = dict(F=[5, 6, 6, 1], K=[3, 3, 3, 3], batch_norm=[True] * 4, M=[], statistics=None, regression=True, dense=True,
+              num_feat_in=3)
+    x = rs.randn(4, 60, 3).astype(np.float32)
+    run_case(ref_models, 'ghcn_dense', out, kw, x, rs.randn(4, 60).astype(np.float32), True, L=[Lg] * 4, p=[1, 1, 1, 1])
+    kw = dict(F=[5, 6, 6], K=[3, 3, 3], batch_norm=[True] * 3, M=[1], statistics='mean', regression=True, num_feat_in=3)
+    run_case(ref_models, 'ghcn_global', out, kw, x, rs.randn(4).astype(np.float32), True, L=[Lg] * 3, p=[1, 1, 1])
+    kw = dict(F=[5, 6, 1], K=[3, 3, 3], batch_norm=[True] * 3, M=[], statistics=None, regression=True, dense=True,
+              num_feat_in=5, mask=[np.ones(60), np.ones(60)])
+    xm = rs.randn(4, 60, 5).astype(np.float32)
+    xm[..., -2:] = (rs.rand(4, 60, 2) < 0.7).astype(np.float32)
+    run_case(ref_models, 'ghcn_masked', out, kw, xm, rs.randn(4, 60).astype(np.float32), True, L=[Lg] * 3, p=[1, 1, 1])
+
+    # L. one layer pooling by 16 (Nside 4 -> 1)
+    sphere = dict(nsides=[4, 1, 1], new=False)
+    kw = dict(F=[3, 4], K=[3, 2], batch_norm=[True, True], M=[], statistics='mean', pool='max')
+    x = rs.randn(2, 192, 1).astype(np.float32)
+    run_case(ref_models, 'pool16', out, kw, x, rs.randint(0, 4, 2), True, sphere=sphere)
 
     # Cases that go through the reference's build_laplacians carry an ARPACK lmax (random start vector, utils.py:423): a
     # regeneration moves them by ~1e-7.  Keep the committed vectors of the cases that already exist and only add new ones

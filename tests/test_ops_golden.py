@@ -60,7 +60,8 @@ class Case(object):
 
 
 def build_oracle(c):
-    o = OracleCgcnn(c.L, p=c.cfg['p'], sampling=c.cfg['sampling'], ratio=c.cfg.get('ratio', 1.), **c.model_kwargs())
+    o = OracleCgcnn(c.L, p=c.cfg['p'], sampling=c.cfg['sampling'], ratio=c.cfg.get('ratio', 1.), masked=bool(c.cfg.get('mask')),
+                    **c.model_kwargs())
     assert list(o.params.keys()) == c.var_names                         # the reference's variable names and creation order
     for k in c.var_names:
         v = torch.from_numpy(c['var/' + k])
@@ -117,6 +118,8 @@ def test_monomial_regulariser_uses_default_stddev():
 def build_product(c, dev):
     from deepsphere_tf1_b200 import models, optimizers
     kw = c.model_kwargs()
+    if c.cfg.get('mask'):                               # only the presence of the argument matters (models.py:1030-1032, 785-787)
+        kw['mask'] = [np.ones(c.L[0].shape[0]), np.ones(c.L[0].shape[0])]
     cls = models.cgcnn
     if c.cfg['sampling'] != 'healpix':
         cls = type('cgcnn_' + c.cfg['sampling'], (models.cgcnn,), {'sampling': c.cfg['sampling'], 'ratio': c.cfg.get('ratio', 1.)})
