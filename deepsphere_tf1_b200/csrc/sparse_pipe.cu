@@ -46,6 +46,8 @@ struct PipeArgs {
                             // best); 0: CTA = contiguous item range, samples of a row tile consecutive; 1: contiguous range in
                             // memory order (experiments: DSB200_PIPE_ORDER)
     int ablate;             // timing experiments only (tools/exp_pipe_ablate.py): skip parts of the work
+    int rev;                // walk the items from the END of memory to its start (same items, same results): a launch that starts
+                            // where its producer stopped finds that producer's last ~100 MB in L2 (ops.py: zigzag recurrence)
     float alpha, beta, gamma;
 };
 
@@ -117,6 +119,11 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
     const long long c0 = nitems * blockIdx.x / gridDim.x, c1 = nitems * (blockIdx.x + 1) / gridDim.x;
     const long long i0 = a.order == 2 ? blockIdx.x : c0, istep = a.order == 2 ? gridDim.x : 1;
     const int n = a.order == 2 ? (int)((nitems - blockIdx.x + gridDim.x - 1) / gridDim.x) : (int)(c1 - c0);
+    const bool rev = a.rev != 0;
+    auto item_at = [&](int it) -> long long {
+        const long long fwd = i0 + it * istep;
+        return rev ? nitems - 1 - fwd : fwd;
+    };
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(full + s, 32 + NBULK); mbar_init(empty + s, CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -135,7 +142,7 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
         // this one waits for its stage: no global-memory latency between a stage falling empty and its refill
         const int nhalo = (PIPE_ABLATE(a) & 2) ? 0 : HC * CPR;
         auto tile_of = [&](int it) -> int {
-            const long long item = i0 + it * istep;
+            const long long item = item_at(it);
             return a.order == 0 ? (int)(item / a.B) : (int)(item % a.T);
         };
         int gr[kHaloPerLane], grn[kHaloPerLane];
@@ -146,7 +153,7 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
         }
         for (int it = 0; it < n; ++it) {
             const int s = it % S, k = it / S;
-            const long long item = i0 + it * istep;
+            const long long item = item_at(it);
             int rt, b;
             if (a.order == 0) { rt = (int)(item / a.B); b = (int)(item - (long long)rt * a.B); }
             else { b = (int)(item / a.T); rt = (int)(item - (long long)b * a.T); }
@@ -207,7 +214,7 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
         const int sub = lane / NCH, lg = lane - sub * NCH;
         for (int it = 0; it < n; ++it) {
             const int s = it % S, k = it / S;
-            const long long item = i0 + it * istep;
+            const long long item = item_at(it);
             int rt, b;
             if (a.order == 0) { rt = (int)(item / a.B); b = (int)(item - (long long)rt * a.B); }
             else { b = (int)(item / a.T); rt = (int)(item - (long long)b * a.T); }
@@ -263,7 +270,7 @@ spmm_pipe_kernel(const __grid_constant__ PipeArgs a)
     const int sub = lane / NCH, lg = lane - sub * NCH;
     for (int it = 0; it < n; ++it) {
         const int s = it % S, k = it / S;
-        const long long item = i0 + it * istep;
+        const long long item = item_at(it);
         int rt, b;
         if (a.order == 0) { rt = (int)(item / a.B); b = (int)(item - (long long)rt * a.B); }
         else { b = (int)(item / a.T); rt = (int)(item - (long long)b * a.T); }
@@ -333,6 +340,8 @@ static int spmm_pipe_entry(const void* tile_recs, const int32_t* tile_ext, const
     DSB_REQUIRE(tile_recs && tile_ext && tile_nh && x && out, "spmm_pipe: null pointer");
     DSB_REQUIRE(x != out, "spmm_pipe: out must not alias x");
     DSB_REQUIRE(width == 9 || width == 7, "spmm_pipe: ELL width must be 7 or 9");
+    const int reverse = (dense >> 1) & 1;                       // bit 1 of `dense`: walk the items from the end of memory
+    dense &= 1;
     DSB_REQUIRE(!dense || width == 9, "spmm_pipe: dense-group records are 72 bytes per row (width 9 layout)");
     DSB_REQUIRE(F == 16 || F == 32 || F == 64, "spmm_pipe: F must be 16, 32 or 64");
     DSB_REQUIRE(TR > 0 && HC >= 0 && ntiles == (M + TR - 1) / TR, "spmm_pipe: tile plan does not match M");
@@ -355,6 +364,7 @@ static int spmm_pipe_entry(const void* tile_recs, const int32_t* tile_ext, const
     a.alpha = alpha; a.beta = beta; a.gamma = gamma;
     a.ablate = DSB_EXPERIMENT_INT("DSB200_PIPE_ABLATE", 0);
     a.order = DSB_ENV_INT("DSB200_PIPE_ORDER", 2);
+    a.rev = reverse;
     int ctas = 2;
     if (DSB_ENV_INT("DSB200_PIPE_CTAS", 2) == 1) ctas = 1;
     const long long nitems = (long long)ntiles * B;

@@ -77,7 +77,10 @@ class PipePlan(object):
         if W != 9 or TR % 4 or TR + 2 * TR > 65535:
             return None
         G = TR // 4
-        lc = np.repeat((np.arange(Mp, dtype=np.int64) % TR)[:, None], W, axis=1)       # padding rows: own local row
+        # Padding rows (>= M, weights 0) point at the FIRST row of their group, never at themselves: the kernel stages only
+        # the tile's M - t*TR real rows, and a group that mixes real and padding rows would otherwise multiply whatever the
+        # shared-memory stage held before (uninitialised in a CTA's first item: possibly NaN bits) by 0.0 into its real rows.
+        lc = np.repeat(((np.arange(Mp, dtype=np.int64) // 4 * 4) % TR)[:, None], W, axis=1)
         lc[:M] = lcol
         v = np.zeros((Mp, W), np.float32)
         v[:M] = val
@@ -126,10 +129,13 @@ class PipePlan(object):
         stage = (self.TR + self.HC) * rb + self.TR * rb * extra + self.width * self.TR * 8
         return (2 * stage + 128 <= PIPE_SMEM and self.TR % (8 * (128 // F)) == 0 and self.HC * (rb // 16) <= 512)
 
-    def args(self, dense=False):
+    def args(self, dense=False, reverse=False):
+        """Leading arguments of dsb200_spmm_pipe; the last one carries the flags: bit 0 = dense-group records, bit 1 = walk the
+        items from the end of memory to its start."""
+        rev = 2 if reverse else 0
         if dense and self.dense is not None:
-            return (self.dense, self.ext, self.nh, self.T, self.TR, self.HC, self.width, 1)
-        return (self.rec, self.ext, self.nh, self.T, self.TR, self.HC, self.width, 0)
+            return (self.dense, self.ext, self.nh, self.T, self.TR, self.HC, self.width, 1 | rev)
+        return (self.rec, self.ext, self.nh, self.T, self.TR, self.HC, self.width, rev)
 
 
 STENCIL_T = 16             # a fused-recurrence tile = 16 x 16 pixels = 256 consecutive NESTED indices (csrc/cheb_tile.cu)

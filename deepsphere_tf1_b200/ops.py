@@ -44,10 +44,10 @@ def _lib_int(name, *args):
     return int(getattr(LIB.load(), 'dsb200_' + name)(*args))
 
 
-def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, transpose=False, rows=None):
+def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, transpose=False, rows=None, reverse=False):
     """out = alpha * L x + beta * y + gamma * z  (tf.sparse_tensor_dense_matmul, models.py:1056,1059).
     `rows`: compute only the first `rows` rows (vertex-sharded mode, one sample: the trailing ghost rows of x are
-    inputs only)."""
+    inputs only).  `reverse` (pipelined kernel only; same result): walk memory from its end to its start (`ZIGZAG`)."""
     B, M, F = x.shape
     if rows is not None:
         if B != 1:
@@ -58,17 +58,17 @@ def spmm(graph, x, y=None, z=None, out=None, alpha=1.0, beta=0.0, gamma=0.0, tra
     if x.dtype == BF16:
         pp = _pipe(graph, which, B, M, F, esize=2, min_items=1) if rows is None else None
         if pp is None:                                   # no bf16 gather kernels: fp32 operator between two casts
-            res = spmm(graph, to_f32(x), to_f32(y), to_f32(z), None, alpha, beta, gamma, transpose, rows)
+            res = spmm(graph, to_f32(x), to_f32(y), to_f32(z), None, alpha, beta, gamma, transpose, rows, reverse)
             return to_bf16(res, out)
         if out is None:
             out = _new((B, M, F), x)
-        call('spmm_pipe_bf16', *pp.args(USE_DENSE_GROUPS), B, M, F, x, y, z, out, alpha, beta, gamma)
+        call('spmm_pipe_bf16', *pp.args(USE_DENSE_GROUPS, reverse), B, M, F, x, y, z, out, alpha, beta, gamma)
         return out
     if out is None:
         out = _new((B, M, F), x)
     pp = _pipe(graph, which, B, M, F) if rows is None else None
     if pp is not None:
-        call('spmm_pipe', *pp.args(USE_DENSE_GROUPS), B, M, F, x, y, z, out, alpha, beta, gamma)
+        call('spmm_pipe', *pp.args(USE_DENSE_GROUPS, reverse), B, M, F, x, y, z, out, alpha, beta, gamma)
     elif rowptr is None:
         rec = _rec(graph, which) if rows is None else None         # the record stride is the graph's M
         if rec is not None:
@@ -84,6 +84,24 @@ USE_PIPE = True           # bulk-asynchronous pipelined sparse product (csrc/spa
 USE_DENSE_GROUPS = True   # pipelined kernel: 4-row groups with dense 4 x 16 weight blocks (each distinct neighbour read once)
 PIPE_MIN_ITEMS = int(os.environ.get('DSB200_PIPE_MIN_ITEMS', 4 * 296))  # (row tiles x samples) below which the pipeline has
                                                                         # nothing to overlap: gather kernels
+
+
+# Zigzag recurrence: consecutive sparse products of a layer sweep memory in opposite directions, so that each one starts on the
+# rows its predecessor touched last (still in the 126 MB L2) instead of the rows it touched first (evicted long ago: one step at
+# the large levels moves 200-270 MB).  The last forward step runs end -> start because the contraction that follows walks
+# start -> end; the first adjoint step runs end -> start because the data-gradient contraction before it stopped at the end.
+# 0: every step start -> end.  (Results do not depend on the order: every item writes its own rows.)
+ZIGZAG = int(os.environ.get('DSB200_ZIGZAG', 0))
+
+
+def _rev_fwd(k, K):
+    """Direction of forward step k (1..K-1): step K-1 reversed, alternating below it (ZIGZAG = 2: the other parity)."""
+    return bool(ZIGZAG) and ((K - 1 - k) % 2 == 0) == (ZIGZAG == 1)
+
+
+def _rev_bwd(k, K):
+    """Direction of adjoint step k (K-2..0): step K-2 (the first to run) reversed, alternating after it."""
+    return bool(ZIGZAG) and ((K - 2 - k) % 2 == 0) == (ZIGZAG == 1)
 
 
 def set_pipe(on, dense=None):
@@ -156,9 +174,10 @@ def cheb_basis(graph, x, K, monomial=False):
         basis = _new((K - 1, B, M, F), x)
         for k in range(1, K):
             if monomial or k == 1:
-                spmm(graph, x if k == 1 else basis[k - 2], out=basis[k - 1])
+                spmm(graph, x if k == 1 else basis[k - 2], out=basis[k - 1], reverse=_rev_fwd(k, K))
             else:
-                spmm(graph, basis[k - 2], x if k == 2 else basis[k - 3], None, out=basis[k - 1], alpha=2.0, beta=-1.0)
+                spmm(graph, basis[k - 2], x if k == 2 else basis[k - 3], None, out=basis[k - 1], alpha=2.0, beta=-1.0,
+                     reverse=_rev_fwd(k, K))
         return basis
     basis = _new((K - 1, B, M, F), x)
     tp = _tile(graph, 'fwd', K, B, F)
@@ -170,9 +189,10 @@ def cheb_basis(graph, x, K, monomial=False):
             spmm(graph, x if k == 1 else basis[k - 2], out=basis[k - 1])
         return basis
     if _pipe(graph, 'fwd', B, M, F) is not None:
-        spmm(graph, x, out=basis[0])                                           # X1 = L X0
+        spmm(graph, x, out=basis[0], reverse=_rev_fwd(1, K))                   # X1 = L X0
         for k in range(2, K):                                                  # Xk = 2 L X(k-1) - X(k-2)
-            spmm(graph, basis[k - 2], x if k == 2 else basis[k - 3], None, out=basis[k - 1], alpha=2.0, beta=-1.0)
+            spmm(graph, basis[k - 2], x if k == 2 else basis[k - 3], None, out=basis[k - 1], alpha=2.0, beta=-1.0,
+                 reverse=_rev_fwd(k, K))
         return basis
     rowptr, col, val, width = graph.fwd
     rec = _rec(graph, 'fwd')
@@ -193,7 +213,7 @@ def cheb_basis_bwd(graph, G, monomial=False):
         for k in range(K - 2, -1, -1):
             a2 = G[k + 2] if (k + 2 <= K - 1 and not monomial) else None
             spmm(graph, G[k + 1], G[k], a2, out=G[k], alpha=2.0 if (k >= 1 and not monomial) else 1.0, beta=1.0,
-                 gamma=-1.0 if a2 is not None else 0.0, transpose=True)
+                 gamma=-1.0 if a2 is not None else 0.0, transpose=True, reverse=_rev_bwd(k, K))
         return G[0]
     tp = _tile(graph, 'bwd', K, B, F)
     if tp is not None:
@@ -209,7 +229,7 @@ def cheb_basis_bwd(graph, G, monomial=False):
         for k in range(K - 2, -1, -1):
             a2 = G[k + 2] if k + 2 <= K - 1 else None
             spmm(graph, G[k + 1], G[k], a2, out=G[k], alpha=2.0 if k >= 1 else 1.0, beta=1.0,
-                 gamma=-1.0 if a2 is not None else 0.0, transpose=True)
+                 gamma=-1.0 if a2 is not None else 0.0, transpose=True, reverse=_rev_bwd(k, K))
         return G[0]
     rowptr, col, val, width = graph.bwd
     rec = _rec(graph, 'bwd')

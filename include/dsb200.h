@@ -94,7 +94,8 @@ int dsb200_cheb_basis_bwd_ellp(const void* recT, const int32_t* colT, const floa
  * 16-byte cp.async, several items in flight per CTA; the arithmetic reads shared memory only.
  * tile_recs int2[ntiles][width][TR] = (LOCAL column, value bits): local column < TR = row of the tile, else TR + halo slot;
  * tile_ext int32[ntiles][HC] = global row of every halo slot; tile_nh int32[ntiles] = halo rows per tile
- * (graph.py: PipePlan).  dense != 0: DENSE-GROUP records instead -- per tile [18][TR/4] 16-byte pieces: a group = 4
+ * (graph.py: PipePlan).  `dense` carries two flags.  Bit 1: walk the items from the end of memory to its start (same items, same
+ * results; a launch that starts where its producer stopped finds the producer's last rows in L2).  Bit 0: DENSE-GROUP records instead -- per tile [18][TR/4] 16-byte pieces: a group = 4
  * consecutive rows and the <= 16 distinct local columns they touch; pieces 0..15 = the group's dense 4 x 16 weight block
  * (row r ^ (g & 1) of group g, columns 4q..4q+3 at piece 4r + q), pieces 16, 17 = the 16 uint16 local columns.  Each distinct neighbour is read
  * once per group (16 reads for 4 rows instead of 36); sums run in column order, so results equal the record form to

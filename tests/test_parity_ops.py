@@ -131,6 +131,42 @@ def test_packed_record_spmm_is_bit_identical_to_row_major(dev, F, graph, sb, mon
     assert_close(basis, _oracle_basis(L, x.cpu(), K)[1:], RTOL, 'basis vs oracle')
 
 
+@pytest.mark.parametrize('bf16', [False, True])
+@pytest.mark.parametrize('dense', [False, True])
+@pytest.mark.parametrize('graph', ['patch64', 'ragged'])
+def test_pipelined_spmm_walking_memory_backwards_gives_the_same_bits(dev, graph, dense, bf16, monkeypatch):
+    """`reverse=True` (bit 1 of the `dense` argument of dsb200_spmm_pipe; the zigzag recurrence of ops.ZIGZAG) only changes the
+    order in which the (row tile, sample) items are taken: every form of the operator, the in-place adjoint form included,
+    and the whole recurrence / adjoint under both zigzag parities are bit-identical to the forward walk."""
+    from scipy import sparse
+    from deepsphere_tf1_b200 import ops
+    L = {'patch64': lambda: healpix_L(64, order=2),
+         'ragged': lambda: sparse.coo_matrix(sparse.csr_matrix(healpix_L(16))[:3001, :3001])}[graph]()
+    g = _graph(L, dev)
+    monkeypatch.setattr(ops, 'PIPE_MIN_ITEMS', 1)
+    monkeypatch.setattr(ops, 'USE_DENSE_GROUPS', dense)
+    monkeypatch.setattr(ops, 'USE_TILE', False)
+    B, F, K = 7, 32, 5
+    if ops._pipe(g, 'fwd', B, g.M, F, esize=2 if bf16 else 4, min_items=1) is None:
+        pytest.skip('no tile plan for this shape')
+    rs = np.random.RandomState(3)
+    dt = torch.bfloat16 if bf16 else torch.float32
+    x, y, z = [torch.from_numpy(rs.randn(B, g.M, F).astype(np.float32)).to(dev).to(dt) for _ in range(3)]
+    G = torch.from_numpy(rs.randn(K, B, g.M, F).astype(np.float32)).to(dev).to(dt)
+    for kw in (dict(), dict(y=y, alpha=2.0, beta=-1.0), dict(y=y, z=z, alpha=0.5, beta=-1.5, gamma=0.25)):
+        assert torch.equal(ops.spmm(g, x, **kw), ops.spmm(g, x, reverse=True, **kw)), sorted(kw)
+    a, b = y.clone(), y.clone()
+    ops.spmm(g, x, a, z, out=a, alpha=2.0, beta=1.0, gamma=-1.0, transpose=True)
+    ops.spmm(g, x, b, z, out=b, alpha=2.0, beta=1.0, gamma=-1.0, transpose=True, reverse=True)
+    assert torch.equal(a, b)
+    monkeypatch.setattr(ops, 'ZIGZAG', 0)
+    basis, dx = ops.cheb_basis(g, x, K).clone(), ops.cheb_basis_bwd(g, G.clone()).clone()
+    for z_ in (1, 2):
+        monkeypatch.setattr(ops, 'ZIGZAG', z_)
+        assert ops._rev_fwd(K - 1, K) == (z_ == 1) and ops._rev_fwd(K - 2, K) == (z_ == 2)
+        assert torch.equal(ops.cheb_basis(g, x, K), basis) and torch.equal(ops.cheb_basis_bwd(g, G.clone()), dx)
+
+
 @pytest.mark.parametrize('dense', [False, True])
 @pytest.mark.parametrize('F', [16, 32, 64])
 @pytest.mark.parametrize('B', [1, 5, 16])
