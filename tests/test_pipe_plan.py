@@ -64,3 +64,35 @@ def test_dense_groups_only_read_rows_the_kernel_stages(M, TR):
                     got[t * TR + row] = float(np.dot(w, v))
     assert np.isfinite(got).all()
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize('M, width', [(3001, 9), (3072, 9), (2562, 7), (2900, 7)])
+def test_record_form_only_reads_rows_the_kernel_stages(M, width):
+    """The record form of the same plan (one lane group per row, `width` gathers): emulate the kernel's reads on a stage whose
+    unstaged part is NaN and compare with L x."""
+    if width == 9:
+        L = sparse.csr_matrix(healpix_L(16))[:M, :M]
+    else:                                   # a banded matrix of degree <= 7 (the icosahedral graphs have ELL width 7)
+        rs = np.random.RandomState(1)
+        rows = np.repeat(np.arange(M), 6)
+        cols = np.clip(rows + rs.randint(-40, 41, size=rows.size), 0, M - 1)
+        L = sparse.coo_matrix((rs.randn(rows.size).astype(np.float32), (rows, cols)), shape=(M, M)).tocsr()
+        L.sum_duplicates()
+    col, val = _ell(L, width)
+    TR = 128
+    plan = PipePlan(col, val, None, TR)
+    assert plan.valid and (plan.dense_np is None) == (width == 7)
+    rs = np.random.RandomState(0)
+    x = rs.randn(M)
+    want = sparse.csr_matrix(L, dtype=np.float64) @ x
+    got = np.zeros(M)
+    for t in range(plan.T):
+        nt = min(TR, M - t * TR)
+        stage = np.full(TR + plan.HC, np.nan)
+        stage[:nt] = x[t * TR:t * TR + nt]
+        stage[TR:TR + plan.HC] = x[plan.ext_np[t]]
+        rec = plan.rec_np[t]                                                         # [W, TR, 2]
+        lc, w = rec[:, :nt, 0], np.ascontiguousarray(rec[:, :nt, 1]).view(np.float32)
+        got[t * TR:t * TR + nt] = (w.astype(np.float64) * stage[lc]).sum(axis=0)
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-5)
