@@ -65,3 +65,37 @@ def test_integration_stub_matches_the_header():
         if name in _lib.PROTOS and name != 'dsb200_last_error':
             n = len([a for a in args.split(',') if a.strip()])
             assert n == len(_lib.PROTOS[name][1]), ('call of ' + name, n, len(_lib.PROTOS[name][1]))
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """include/dsb200.h is the contract for bindings from other host languages: it must compile as strict C99 (no C++, no
+    torch types) and every prototype must resolve against libdsb200.so at link time.  The program takes the address of every
+    declared entry point and calls the two that need no device."""
+    import shutil
+    import subprocess
+    from deepsphere_tf1_b200 import _lib
+    if shutil.which('gcc') is None:
+        pytest.skip('no C compiler')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = sorted(_lib.PROTOS)
+    src = ['#include <stdio.h>', '#include "dsb200.h"', 'int main(void) {', '    const void* entry[] = {']
+    src += ['        (const void*)&{},'.format(n) for n in names]
+    src += ['    };', '    unsigned n = 0, i;', '    for (i = 0; i < sizeof(entry) / sizeof(entry[0]); ++i) n += entry[i] != 0;',
+            '    printf("%d %u %s\\n", dsb200_abi_version(), n, dsb200_last_error()[0] ? "error" : "clean");', '    return 0;', '}']
+    c = tmp_path / 'abi.c'
+    c.write_text('\n'.join(src) + '\n')
+    exe = str(tmp_path / 'abi')
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    # -pedantic would object to the function -> object pointer casts of the table above, not to the header
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-Werror', '-I', os.path.join(root, 'include'), str(c), '-o', exe,
+                        '-L', libdir, '-ldsb200', '-Wl,-rpath,' + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ['2', str(len(names)), 'clean']
+    # and the header alone, strictly
+    h = tmp_path / 'only_header.c'
+    h.write_text('#include "dsb200.h"\nint dsb200_header_compiles;\n')
+    r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', os.path.join(root, 'include'), '-c', str(h),
+                        '-o', str(tmp_path / 'only_header.o')], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
