@@ -15,12 +15,20 @@ Parity pinning status (see DESIGN.md section "Oracle"):
     (tests/golden/make_golden.py) -- fixtures committed under tests/golden/.
   * HEALPix nested geometry (healpy.pix2vec / get_all_neighbours; healpy 1.11.0 is a
     third-party dependency absent from /root/reference): restated from the published
-    HEALPix algorithm; pinned only by the healpy docstring example and geometric
-    invariants -> "parity unpinned" for the absolute pixel coordinates.
-  * TF1 operators (chebyshev5, batch-norm, pooling, statistics, loss, Adam): the reference
-    has no tests, golden vectors or fixtures and TensorFlow 1.10 cannot run here ->
-    "parity unpinned"; anchored on line-by-line correspondence with models.py, mathematical
-    identities (Chebyshev polynomials on eigenvectors, float64 finite differences) and the
-    known answers printed in experiments/cosmo/demo.ipynb (parameter counts, level sizes,
-    learning-rate end points, initial loss ln 2).
+    HEALPix algorithm; pinned only by known answers from outside this repository (both
+    `get_all_neighbours` docstring examples and the `pix2ang` docstring angles of healpy,
+    base-pixel centres and Nside-2 children from the ring formulas of Gorski et al. 2005:
+    tests/test_graph_golden.py) and geometric invariants -> "parity unpinned" for the rest
+    of the absolute pixel coordinates.
+  * TF1 operators and models (chebyshev5, monomials, batch norm, pooling / unpooling, statistics,
+    fc, `_inference`, `_decoder`, losses): PINNED to the reference's OWN graph-construction code.
+    tests/golden/make_ops_golden.py imports the UNMODIFIED deepsphere/models.py with `tensorflow`
+    replaced by an eager torch-CPU stand-in (tests/golden/tf_shim.py) and commits variables, logits,
+    losses, every gradient and the batch-norm updates of 21 model cases (tests/golden/ops_golden.npz);
+    tests/test_ops_golden.py holds this oracle to 2e-5 and the CUDA path to 1e-4 of them.  What the
+    stand-in decides itself stays unpinned: the arithmetic INSIDE a TF op (summation order, the
+    moments of tf.layers.batch_normalization), the random streams, and the optimizer update rules
+    (oracle/optim_tf1.py: restated from the TF 1.10 sources, "parity unpinned").
+  * icosahedral mesh: PINNED bit for bit to the `SphereIcosahedron` class source of
+    notebooks/sphere_to_graph.ipynb (tests/golden/make_ico_golden.py).
 """

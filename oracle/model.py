@@ -1,8 +1,10 @@
 """Oracle restatement of `cgcnn._inference` / `_decoder` / loss / one training step
 (deepsphere/models.py:1219-1344, 777-843) on top of oracle.ops, torch-CPU.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity unpinned (no TF1 here); pinned
-known answers: parameter counts and level sizes of experiments/cosmo/demo.ipynb:861-889.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PINNED to the reference's own code: logits, loss, every
+gradient and the batch-norm updates of 21 model cases produced by the UNMODIFIED deepsphere/models.py (run through the
+TensorFlow stand-in of tests/golden/tf_shim.py) are reproduced to 2e-5 (tests/test_ops_golden.py); also the parameter counts
+and level sizes of experiments/cosmo/demo.ipynb:861-889.  Unpinned: the optimizer update rules (oracle/optim_tf1.py).
 
 Variables carry the reference's TF names (`conv1/weights`, `conv1/bias`,
 `conv1/batch_normalization/moving_mean`, `fc1/weights`, `logits/weights`, `upconv3/weights`,

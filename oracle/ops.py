@@ -1,10 +1,13 @@
 """Oracle restatement of the reference's TF1 graph operators, in torch-CPU (autograd gives
 the gradients TF1's `optimizer.compute_gradients` would, deepsphere/models.py:831).
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Parity unpinned: TensorFlow 1.10 cannot
-run here and the reference has no golden vectors for these operators; each function follows
-the cited lines of deepsphere/models.py statement by statement (same transposes / reshapes
-/ concatenations, so the memory order of every intermediate is the reference's).
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  Each function follows the cited lines of
+deepsphere/models.py statement by statement (same transposes / reshapes / concatenations, so
+the memory order of every intermediate is the reference's).  PINNED through the model cases of
+tests/golden/ops_golden.npz: the reference's own, unmodified operator code (chebyshev5, monomials,
+pool_*, unpool_*, batch_normalization, bias, fc, learned_histogram, loss) executed through the
+TensorFlow stand-in tests/golden/tf_shim.py; tests/test_ops_golden.py holds these functions to 2e-5
+of its outputs.  Unpinned: the arithmetic inside a TF op (TensorFlow 1.10 cannot run here).
 """
 import numpy as np
 import torch
