@@ -10,8 +10,10 @@ healpy 1.11.0 (environment.yml:29) wraps healpix_cxx; it is not vendored under
 restated below, deliberately in scalar per-pixel form (the product uses an independent
 vectorised implementation in deepsphere_tf1_b200/healpix.py; tests compare the two).
 
-Parity: pinned only by the healpy docstring example get_all_neighbours(1, 4) and by the
-geometric invariants of SURVEY.md Appendix C -> "parity unpinned" for absolute values.
+Parity: pinned by the known answers that exist outside this repository -- both `get_all_neighbours` docstring examples of
+healpy, the five (theta, phi) pairs of its `pix2ang` docstring at Nside 16, the base-pixel centres and the Nside-2 children of
+base pixel 0 from the ring formulas of Gorski et al. 2005 (tests/test_graph_golden.py) -- and by the geometric invariants of
+SURVEY.md Appendix C; every other absolute value is "parity unpinned" (healpy cannot run here).
 """
 import math
 

@@ -1,5 +1,5 @@
-"""CPU checks of the oracle itself (it is unpinned for the TF1 operators, so it is anchored on
-mathematical identities and on the known answers the reference prints in experiments/cosmo/demo.ipynb)."""
+"""CPU checks of the oracle itself, next to its pinning against the reference's own graph code (tests/test_ops_golden.py):
+mathematical identities and the known answers the reference prints in experiments/cosmo/demo.ipynb."""
 import numpy as np
 import pytest
 import torch
