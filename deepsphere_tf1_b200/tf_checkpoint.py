@@ -11,7 +11,8 @@ Format (tensorflow/core/util/tensor_bundle + the LevelDB-style table of tensorfl
                    name> -> BundleEntryProto (dtype, shape, shard_id, offset, size, crc32c).
   <prefix>.data-00000-of-00001   the raw little-endian tensor bytes at those offsets.
 Written from the published format; the reference repository ships no checkpoint file, so reading is verified against this module's
-own writer, the CRCs and the structural invariants only (tests/test_tf_checkpoint.py).  Snappy-compressed blocks are refused.
+own writer, the CRCs and the structural invariants only (tests/test_tf_checkpoint.py).  Snappy-compressed index blocks (block type 1) are
+decoded (`_snappy_decompress`, checked against a real snappy encoder); the writer emits uncompressed blocks as TensorFlow's BundleWriter does.
 """
 import os
 import struct
@@ -46,14 +47,60 @@ def _fields(buf):
         yield field, wire, v
 
 
+def _snappy_decompress(buf):
+    """Raw snappy format (format_description.txt of google/snappy): varint uncompressed length, then elements tagged by their
+    low two bits -- 00 literal (length - 1 in the upper six bits, or in the 1..4 following bytes for 60..63), 01 copy with a
+    3-bit length - 4 and an 11-bit offset, 10 / 11 copies with a 6-bit length - 1 and a 2- / 4-byte little-endian offset.
+    Copies may overlap their own output (offset < length repeats a pattern)."""
+    n, i = _read_varint(buf, 0)
+    out = bytearray()
+    while i < len(buf):
+        tag = buf[i]
+        i += 1
+        kind = tag & 3
+        if kind == 0:
+            ln = tag >> 2
+            if ln >= 60:
+                nb = ln - 59
+                ln = int.from_bytes(buf[i:i + nb], 'little')
+                i += nb
+            ln += 1
+            if i + ln > len(buf):
+                raise ValueError('snappy: literal runs past the end of the block')
+            out += buf[i:i + ln]
+            i += ln
+            continue
+        if kind == 1:
+            ln = 4 + ((tag >> 2) & 7)
+            off = ((tag >> 5) << 8) | buf[i]
+            i += 1
+        elif kind == 2:
+            ln = (tag >> 2) + 1
+            off = int.from_bytes(buf[i:i + 2], 'little')
+            i += 2
+        else:
+            ln = (tag >> 2) + 1
+            off = int.from_bytes(buf[i:i + 4], 'little')
+            i += 4
+        if off == 0 or off > len(out):
+            raise ValueError('snappy: copy offset outside the output')
+        for _ in range(ln):                             # byte by byte: the source may overlap what is being written
+            out.append(out[-off])
+    if len(out) != n:
+        raise ValueError('snappy: {} bytes decoded, header says {}'.format(len(out), n))
+    return bytes(out)
+
+
 def _block(data, offset, size):
     raw = data[offset:offset + size]
     ctype = data[offset + size]
     (crc,) = struct.unpack('<I', data[offset + size + 1:offset + size + 5])
     if crc != _masked_crc(raw + bytes([ctype])):
         raise ValueError('tensor bundle index: block checksum mismatch')
-    if ctype != 0:
-        raise NotImplementedError('tensor bundle index: compressed blocks (type {}) are not supported'.format(ctype))
+    if ctype == 1:                                      # kSnappyCompression of the table format
+        raw = _snappy_decompress(raw)
+    elif ctype != 0:
+        raise NotImplementedError('tensor bundle index: block compression type {} is not supported'.format(ctype))
     (nrestart,) = struct.unpack('<I', raw[-4:])
     end = len(raw) - 4 - 4 * nrestart
     entries, key, i = [], b'', 0

@@ -104,3 +104,46 @@ def test_model_restores_from_tensorflow_checkpoint(dev, tmp_path):
     c.fit(LabeledDataset(xs, ls, shuffle=False), LabeledDataset(xs[:4], ls[:4], shuffle=False), restore=True, verbose=False)
     assert c.global_step == 6 and os.path.exists(os.path.join(d, 'model-4.index')) and os.path.exists(os.path.join(d, 'model-6.pt'))
     shutil.rmtree(d, ignore_errors=True)
+
+
+def test_snappy_blocks_of_the_index_table_are_decoded(tmp_path, monkeypatch):
+    """The table format allows snappy-compressed blocks (type byte 1).  The decoder against hand-made streams of every element
+    kind, against a real snappy encoder (pyarrow's), and end to end on an index file whose blocks are compressed."""
+    # literal 'ab', then a 1-byte-offset copy of 8 bytes at distance 2: the copy overlaps its own output
+    assert tfc._snappy_decompress(bytes([10, 0x04]) + b'ab' + bytes([0x11, 0x02])) == b'ababababab'
+    # 2-byte-offset copy (kind 2: length - 1 in the upper six bits) and a 61-byte literal with its length in one extra byte
+    lit = bytes(range(61))
+    assert tfc._snappy_decompress(bytes([71, 60 << 2, 60]) + lit + bytes([(10 - 1) << 2 | 2, 61, 0])) == lit + lit[:10]
+    with pytest.raises(ValueError, match='header says'):
+        tfc._snappy_decompress(bytes([5, 0x04]) + b'ab')
+    with pytest.raises(ValueError, match='offset'):
+        tfc._snappy_decompress(bytes([6, 0x04]) + b'ab' + bytes([0x01, 0x09]))
+    pa = pytest.importorskip('pyarrow')
+    if not pa.Codec.is_available('snappy'):
+        pytest.skip('pyarrow without snappy')
+    rs = np.random.RandomState(0)
+    for n in (0, 1, 59, 60, 61, 300, 70000, 200000):
+        for kind in ('random', 'text', 'runs'):
+            if kind == 'random':
+                raw = rs.bytes(n)
+            elif kind == 'text':
+                raw = (b'conv1/weights conv1/bias conv2/batch_normalization/moving_mean ' * (n // 60 + 1))[:n]
+            else:
+                raw = bytes(np.repeat(rs.randint(0, 4, size=n // 50 + 1), 50).astype(np.uint8)[:n])
+            assert tfc._snappy_decompress(pa.compress(raw, codec='snappy', asbytes=True)) == raw, (n, kind)
+
+    def emit_snappy(out, block):
+        comp = pa.compress(block, codec='snappy', asbytes=True)
+        off = len(out)
+        out += comp + b'\x01' + struct.pack('<I', tfc._masked_crc(comp + b'\x01'))
+        return tfc._varint(off) + tfc._varint(len(comp))
+
+    import struct
+    monkeypatch.setattr(tfc, '_emit', emit_snappy)
+    v = _vars()
+    prefix = str(tmp_path / 'model-7')
+    tfc.write_checkpoint(prefix, v, block_entries=3)
+    got = tfc.read_checkpoint(prefix)
+    assert set(got) == set(v)
+    for k in v:
+        assert np.array_equal(got[k], v[k]), k
